@@ -1,0 +1,236 @@
+"""Mint the golden fixtures under tests/golden/ from the UNMODIFIED reference classes.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (needs /root/reference):   python oracle/make_golden.py
+
+For every case the reference's own `Network` / `RateNet` / `SpikeResetNet` / `Linear` / `RLS` / `Observer`
+(imported via oracle/ref_shim.py) are driven exactly like a user would (`add_node`, `add_func_node`, `add_edge`,
+`run`, `loss.backward()`), with the hand-written vector fields of oracle/rectipy_oracle.py supplying the part
+PyRates would have generated.  Inputs AND outputs are stored, so tests never need the reference at run time.
+All cases are seeded; fixtures are fp64 truth plus the fp32 reference run of the same inputs.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+import rectipy_oracle as orc  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+TD = {"float64": torch.float64, "float32": torch.float32}
+
+
+def ref_network(ref, model, n, W, dt, dtype, params=None, train_params=None, w_in=None, w_out=None,
+                train_in=False, train_out=False, in_act="identity", out_act="identity", spike_kwargs=None,
+                input_var="I_ext", output_var=None, in_mask=None):
+    """Assemble a reference Network around a reference RateNet/SpikeResetNet built on an oracle vector field."""
+    func, args, var_map, param_map = orc.build_node_args(model, n, W, params, dtype, input_var, output_var)
+    net = ref.Network(dt, device="cpu", dtype=dtype)
+    if model in orc.SPIKING:
+        node = ref.nodes.SpikeResetNet(func, args, var_map, param_map, dt=dt, dtype=dtype, train_params=train_params,
+                                       device="cpu", **(spike_kwargs or {}))
+    else:
+        node = ref.nodes.RateNet(func, args, var_map, param_map, dt=dt, dtype=dtype, train_params=train_params,
+                                 device="cpu")
+    net.add_node("rnn", node, node_type="diff_eq")
+    if w_in is not None:
+        net.add_func_node("inp", w_in.shape[1], in_act)
+        kw = {"mask": in_mask} if in_mask is not None else {}
+        net.add_edge("inp", "rnn", weights=np.asarray(w_in), train="gd" if train_in else None, **kw)
+    if w_out is not None:
+        net.add_func_node("out", w_out.shape[0], out_act)
+        net.add_edge("rnn", "out", weights=np.asarray(w_out), train="gd" if train_out else None)
+    return net, node
+
+
+def run_case(ref, spec, dtype_name):
+    dtype = TD[dtype_name]
+    n, T = spec["n"], spec["T"]
+    params = {k: v for k, v in spec.get("params", {}).items()}
+    net, node = ref_network(ref, spec["model"], n, spec["W"], spec["dt"], dtype, params=params,
+                            train_params=spec.get("train_params"), w_in=spec.get("w_in"), w_out=spec.get("w_out"),
+                            train_in=spec.get("train_in", False), train_out=spec.get("train_out", False),
+                            in_act=spec.get("in_act", "identity"), out_act=spec.get("out_act", "identity"),
+                            spike_kwargs=spec.get("spike_kwargs"), in_mask=spec.get("in_mask"))
+    inputs = torch.tensor(spec["inputs"], dtype=dtype)
+    rec = [("rnn", v, red) for v, red in spec.get("record_vars", [])]
+    kw = {}
+    if "truncate_steps" in spec:
+        kw["truncate_steps"] = spec["truncate_steps"]
+    obs = net.run(inputs, sampling_steps=spec.get("S", 1), cutoff=spec.get("cutoff", 0), verbose=False,
+                  enable_grad=spec.get("grad", False), record_vars=rec, **kw)
+    res = {"out": obs.to_numpy("out"), "steps": np.asarray(obs["steps"])}
+    for v, red in spec.get("record_vars", []):
+        res[f"var_{v}"] = obs.to_numpy(("rnn", v))
+    if spec["model"] in orc.SPIKING:
+        res["y_final"] = torch.cat((node._y_start, node._y_spike, node._y_stop), 0).detach().numpy()
+    else:
+        res["y_final"] = node.y.detach().numpy()
+    if spec.get("grad", False):
+        target = torch.tensor(spec["targets"], dtype=dtype)
+        loss = torch.nn.MSELoss()(torch.stack(obs["out"]), target)
+        loss.backward()
+        res["loss"] = loss.detach().numpy()
+        for name in spec.get("train_params", []) or []:
+            res[f"grad_{name}"] = node[name].grad.detach().numpy()
+        if spec.get("train_in"):
+            res["grad_w_in"] = net.get_edge("inp", "rnn").weights.grad.detach().numpy()
+        if spec.get("train_out"):
+            res["grad_w_out"] = net.get_edge("rnn", "out").weights.grad.detach().numpy()
+    return res
+
+
+def save_case(ref, name, spec):
+    blob = {}
+    for k, v in spec.items():
+        if isinstance(v, np.ndarray):
+            blob[f"in_{k}"] = v
+    for k, v in spec.get("params", {}).items():
+        blob[f"param_{k}"] = np.asarray(v, dtype=np.float64)
+    meta = {k: v for k, v in spec.items() if not isinstance(v, np.ndarray) and k != "params"}
+    blob["meta"] = np.asarray(repr(meta))
+    for dn in ("float64", "float32"):
+        res = run_case(ref, spec, dn)
+        for k, v in res.items():
+            blob[f"{dn}_{k}"] = v
+    path = os.path.join(OUT, f"{name}.npz")
+    np.savez_compressed(path, **blob)
+    print(f"{name}: wrote {os.path.getsize(path)/1024:.1f} KiB;  out {blob['float64_out'].shape}")
+
+
+def sin_inputs(rng, T, m, dt, amp=1.0, offset=0.0):
+    t = np.arange(T) * dt
+    freqs = rng.uniform(0.5, 3.0, size=m)
+    ph = rng.uniform(0, 2 * np.pi, size=m)
+    return amp * np.sin(2 * np.pi * freqs[None, :] * t[:, None] + ph[None, :]) + offset
+
+
+def main():
+    ref = ref_shim.import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.default_rng(20261018)
+
+    # ---- G1: LI-tanh rate net, BPTT with windowed readout (SURVEY Appendix A.2 set-up) ------------
+    n, T, m, k, dt = 32, 600, 3, 2, 1e-2
+    spec = dict(model="li_tanh", n=n, T=T, dt=dt, S=5, cutoff=7, grad=True,
+                W=rng.standard_normal((n, n)) / np.sqrt(n) * 1.5,
+                params=dict(tau=rng.uniform(1.0, 2.0, n), k=1.3, eta=0.2),
+                train_params=["weights", "tau", "k", "eta"], train_in=True, train_out=True,
+                w_in=rng.standard_normal((n, m)), w_out=rng.standard_normal((k, n)) / np.sqrt(n),
+                inputs=sin_inputs(rng, T, m, dt, amp=2.0), record_vars=[("v", False)])
+    n_rec = len([s for s in range(T) if s >= 7 and s % 5 == 0])
+    spec["targets"] = rng.standard_normal((n_rec, k))
+    save_case(ref, "li_tanh_bptt", spec)
+
+    # ---- G2: LI-sigmoid, forward only, direct input on the node, no readout (ridge-style X) -------
+    n, T, dt = 20, 300, 5e-2
+    spec = dict(model="li_sigmoid", n=n, T=T, dt=dt, S=3, cutoff=0, grad=False,
+                W=rng.standard_normal((n, n)) / np.sqrt(n) * 2.0,
+                params=dict(tau=2.0, k=1.5, eta=rng.standard_normal(n) * 0.3, r_max=2.0, s=1.5, v0=0.2),
+                inputs=sin_inputs(rng, T, n, dt, amp=1.0), record_vars=[("v", True)])
+    save_case(ref, "li_sigmoid_fwd", spec)
+
+    # ---- G3: QIF spiking net, BPTT through surrogate + reset gate ---------------------------------
+    n, T, m, k, dt = 24, 1500, 2, 3, 1e-3
+    spec = dict(model="qif", n=n, T=T, dt=dt, S=4, cutoff=0, grad=True,
+                W=rng.standard_normal((n, n)) * 2.0 / np.sqrt(n),
+                params=dict(eta=orc.lorentzian_etas(n), tau=1.0, k=1.2, tau_s=0.8),
+                train_params=["weights", "eta", "tau", "k", "tau_s"], train_in=True, train_out=True,
+                w_in=rng.standard_normal((n, m)), w_out=rng.standard_normal((k, n)) / np.sqrt(n),
+                inputs=sin_inputs(rng, T, m, dt, amp=10.0, offset=14.0), record_vars=[("v", False), ("s", True)])
+    spec["targets"] = rng.standard_normal((len(range(0, T, 4)), k))
+    save_case(ref, "qif_bptt", spec)
+
+    # ---- G4: QIF-SFA, config-1 style (random_connectivity p, k=15, step input through tanh node) ---
+    n, T, dt = 100, 4000, 1e-3
+    np.random.seed(7)
+    W = ref.random_connectivity(n, n, 0.2, normalize=True)
+    inp = np.zeros((T, 1))
+    inp[1000:3000, 0] = 3.0
+    spec = dict(model="qif_sfa", n=n, T=T, dt=dt, S=100, cutoff=0, grad=False, W=W,
+                params=dict(eta=orc.lorentzian_etas(n), k=15.0, alpha=0.3, tau_x=2.0),
+                w_in=rng.standard_normal((n, 1)), in_act="tanh", inputs=inp,
+                spike_kwargs=dict(spike_threshold=100.0, spike_reset=-100.0),
+                record_vars=[("s", True), ("v", False)])
+    save_case(ref, "qif_sfa_fwd", spec)
+
+    # ---- G5: QIF-SFA BPTT with alpha, truncated BPTT ----------------------------------------------
+    n, T, m, k, dt = 16, 800, 2, 2, 1e-3
+    spec = dict(model="qif_sfa", n=n, T=T, dt=dt, S=2, cutoff=10, grad=True, truncate_steps=300,
+                W=rng.standard_normal((n, n)) * 2.0 / np.sqrt(n),
+                params=dict(eta=orc.lorentzian_etas(n, eta=0.0), alpha=0.5, tau_x=1.5, k=2.0),
+                train_params=["weights", "eta"], train_in=False, train_out=True,
+                w_in=rng.standard_normal((n, m)), w_out=rng.standard_normal((k, n)) / np.sqrt(n),
+                inputs=sin_inputs(rng, T, m, dt, amp=10.0, offset=16.0))
+    spec["targets"] = rng.standard_normal((len([s for s in range(T) if s >= 10 and s % 2 == 0]), k))
+    save_case(ref, "qif_sfa_bptt_trunc", spec)
+
+    # ---- G6: LIF (documentation/bptt_spiking_neurons_recurrent.py set-up, N=10) -------------------
+    n, T, m, k, dt = 10, 2000, 2, 3, 5e-3
+    t = np.arange(T) * dt
+    inp = np.stack([np.sin(t * 2 * np.pi * w) * 40.0 for w in (0.3, 0.5)], axis=1)
+    spec = dict(model="lif", n=n, T=T, dt=dt, S=1, cutoff=0, grad=True,
+                W=rng.standard_normal((n, n)),
+                params=dict(eta=10.0, tau=rng.uniform(10.0, 20.0, n), tau_s=5.0, k=2.0),
+                train_params=["weights"], train_in=False, train_out=True,
+                w_in=rng.standard_normal((n, m)), w_out=rng.standard_normal((k, n)),
+                spike_kwargs=dict(spike_threshold=10.0, spike_reset=-10.0), inputs=inp)
+    spec["targets"] = rng.standard_normal((T, k))
+    save_case(ref, "lif_bptt", spec)
+
+    # ---- G7: output activation + masked input edge (LinearMasked, edges.py:150-174) ---------------
+    n, T, m, k, dt = 12, 200, 4, 3, 2e-2
+    spec = dict(model="li_tanh", n=n, T=T, dt=dt, S=2, cutoff=0, grad=True,
+                W=rng.standard_normal((n, n)) / np.sqrt(n),
+                params=dict(tau=1.5, k=1.0, eta=0.0), train_params=["weights"], train_in=True, train_out=True,
+                w_in=rng.standard_normal((n, m)), in_mask=(rng.uniform(size=(n, m)) < 0.6).astype(np.float64),
+                w_out=rng.standard_normal((k, n)), out_act="softmax", in_act="sigmoid",
+                inputs=sin_inputs(rng, T, m, dt, amp=1.5))
+    spec["targets"] = rng.uniform(size=(len(range(0, T, 2)), k))
+    save_case(ref, "li_tanh_masked_softmax", spec)
+
+    # ---- G8: edges known-answers: Linear vs torch.nn.Linear convention; RLS.update sequence --------
+    torch.manual_seed(3)
+    n_in, n_out, steps = 9, 4, 25
+    lin = ref.edges.Linear(n_in, n_out, weights=rng.standard_normal((n_out, n_in)), dtype=torch.float64)
+    xs = rng.standard_normal((steps, n_in))
+    ys = rng.standard_normal((steps, n_out))
+    lin_out = np.stack([lin.forward(torch.tensor(x)).numpy() for x in xs])
+    rls = ref.edges.RLS(n_in, n_out, dtype=torch.float64, beta=0.98, alpha=2.0)
+    w_hist, p_hist, loss_hist = [], [], []
+    for x, y in zip(xs, ys):
+        xt, yt = torch.tensor(x), torch.tensor(y)
+        y_hat = rls.forward(xt)
+        rls.update(xt, yt, y_hat)
+        w_hist.append(rls.weights.numpy().copy())
+        p_hist.append(rls.P.numpy().copy())
+        loss_hist.append(float(rls.loss))
+    np.savez_compressed(os.path.join(OUT, "edges.npz"), lin_w=lin.weights.numpy(), xs=xs, ys=ys, lin_out=lin_out,
+                        rls_w=np.stack(w_hist), rls_p=np.stack(p_hist), rls_loss=np.asarray(loss_hist),
+                        rls_beta=0.98, rls_alpha=2.0)
+    print("edges: ok")
+
+    # ---- G9: fit_ridge on a small reservoir (network.py:709-784) ----------------------------------
+    n, T, m, k, dt = 15, 400, 3, 2, 1e-2
+    W = rng.standard_normal((n, n)) / np.sqrt(n)
+    w_in = rng.standard_normal((n, m))
+    inputs = sin_inputs(rng, T, m, dt, amp=1.0)
+    targets = rng.standard_normal((T, k))   # fit_ridge demands len(inputs)==len(targets) (network.py:744-746) => S=1
+    blob = dict(W=W, w_in=w_in, inputs=inputs, targets=targets, dt=dt, alpha=1e-3, S=1)
+    net, node = ref_network(ref, "li_tanh", n, W, dt, torch.float64, params=dict(tau=1.0), w_in=w_in)
+    obs = net.fit_ridge(torch.tensor(inputs).numpy(), targets, sampling_steps=1, alpha=1e-3, verbose=False,
+                        add_readout_node=False)
+    blob["X"] = obs.to_numpy("out")
+    blob["w_out"] = obs["w_out"].detach().numpy()
+    blob["y"] = obs["y"].detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "ridge.npz"), **blob)
+    print("ridge: ok")
+
+
+if __name__ == "__main__":
+    main()
