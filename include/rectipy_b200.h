@@ -1,0 +1,139 @@
+/*
+ * rectipy_b200 -- C ABI of the B200 (sm_100a) engine for RectiPy's time-stepped integration hot path.
+ *
+ * The reference (pyrates-neuroscience/RectiPy) is pure Python and has no FFI; what this library replaces is the
+ * per-step operator boundary of the reference, executed for a whole horizon at once:
+ *
+ *   rp_forward   <->  Network.run step loop            rectipy/network.py:588-599
+ *                     Network.forward / _backward      rectipy/network.py:462-478,962-977
+ *                     Linear.forward (W_in, W_out)     rectipy/edges.py:48-49
+ *                     RateNet.forward                  rectipy/nodes.py:166-170
+ *                     SpikeResetNet.forward            rectipy/nodes.py:382-392
+ *                     Spike.forward (heaviside)        rectipy/nodes.py:473-476
+ *                     generated vector field f(t,y,*args), equations neuron_model_templates/ ** .yaml
+ *                     Observer.record window means     rectipy/network.py:590-597, rectipy/observer.py:79-105
+ *   rp_backward  <->  error.backward() over the unrolled tape      rectipy/network.py:1123-1130
+ *                     Spike.backward (surrogate)       rectipy/nodes.py:478-481
+ *                     truncated BPTT detach            rectipy/network.py:598-599, rectipy/nodes.py:176-196
+ *   rp_rls_run   <->  RLS.update applied per step      rectipy/edges.py:227-234, rectipy/network.py:1093-1121
+ *
+ * Conventions
+ *   - Plain C: pointers + sizes, no torch types.  All data pointers are DEVICE pointers to fp32, contiguous,
+ *     16-byte aligned, owned by the caller; the library borrows them for the duration of the call.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises the host.
+ *   - Every entry point returns 0 on success, non-zero on error; rp_last_error() gives a thread-local message.
+ *   - State layout ("SoA planes"): y[var][trial][neuron], var in {0:v, 1:s, 2:x}; plane stride = batch*n.
+ *   - A plan is not re-entrant: one host thread / one stream at a time per plan.
+ */
+#ifndef RECTIPY_B200_H
+#define RECTIPY_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RP_ABI_VERSION 1
+#define RP_MAX_IN 8      /* max fused input-projection width  m (wider inputs: use RP_IN_DENSE)  */
+#define RP_MAX_OUT 8     /* max fused readout width           k (wider readouts: use RP_OUT_DENSE) */
+#define RP_MAX_SV 3
+#define RP_MAX_REC 4
+
+/* vector fields (neuron_model_templates/rate_neurons/leaky_integrator.yaml, spiking_neurons/{qif,lif}.yaml) */
+enum { RP_LI_TANH = 0, RP_LI_SIGMOID = 1, RP_QIF = 2, RP_QIF_SFA = 3, RP_LIF = 4 };
+/* parameter slots; each is a device pointer to 1 float (shared) or n floats (per neuron) */
+enum { RP_P_TAU = 0, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_RMAX, RP_P_SIG_S, RP_P_V0, RP_NUM_PARAMS };
+enum { RP_IN_NONE = 0, RP_IN_DENSE = 1, RP_IN_PROJ = 2 };   /* x_t is [B,n] current | [B,m] projected by W_in[n,m] */
+enum { RP_OUT_DENSE = 0, RP_OUT_READOUT = 1 };             /* record y[out] itself | W_out[k,n] . y[out]         */
+enum { RP_VAR_V = 0, RP_VAR_S = 1, RP_VAR_X = 2, RP_VAR_R = 3 }; /* RP_VAR_R = activation(v) of a rate node       */
+enum { RP_PREC_FP32 = 0, RP_PREC_3XTF32 = 1 };             /* FFMA fp32 | tcgen05 error-compensated 3xTF32       */
+
+typedef struct rp_desc {
+    int model;              /* RP_LI_TANH ...                                                   */
+    int n;                  /* neurons                                                          */
+    int batch;              /* independent trials B (reference: 1)                              */
+    int in_mode;            /* RP_IN_*                                                          */
+    int n_in;               /* m (RP_IN_PROJ only)                                              */
+    int in_target;          /* 0: input enters v' (I_ext), 1: input enters s' (lif s_ext)       */
+    int out_mode;           /* RP_OUT_*                                                         */
+    int n_out;              /* k (RP_OUT_READOUT only)                                          */
+    int out_var;            /* RP_VAR_*: which variable is the node output                      */
+    int precision;          /* RP_PREC_*                                                        */
+    float dt;
+    float theta;            /* spike threshold   (nodes.py:338,349)                             */
+    float v_reset;          /* reset value       (nodes.py:338,348)                             */
+    float slope;            /* surrogate slope   (nodes.py:345-347)                             */
+    int param_per_neuron[RP_NUM_PARAMS]; /* 1: pointer holds n values, 0: one shared value      */
+} rp_desc;
+
+typedef struct rp_plan rp_plan;
+
+typedef struct rp_fwd_args {
+    int T;                  /* integration steps                                                */
+    int sampling_steps;     /* S  (network.py:592)                                              */
+    int cutoff;             /*    (network.py:590)                                              */
+    const float* x;         /* [T,B,m] (PROJ) | [T,B,n] (DENSE) | NULL                          */
+    const float* W;         /* [n,n] recurrent weights, row = target, col = source              */
+    const float* W_in;      /* [n,m] or NULL                                                    */
+    const float* W_out;     /* [k,n] or NULL                                                    */
+    const float* params[RP_NUM_PARAMS];
+    const float* y0;        /* [n_sv,B,n] initial state                                         */
+    float* yT;              /* [n_sv,B,n] state after T steps                                   */
+    float* out_rec;         /* [n_rec,B,k] | [n_rec,B,n] window means of the output, or NULL    */
+    int n_rec_vars;
+    int rec_var[RP_MAX_REC];     /* RP_VAR_V/S/X                                                */
+    int rec_reduce[RP_MAX_REC];  /* 1: mean over neurons -> [n_rec,B]; 0: [n_rec,B,n]           */
+    float* rec_buf[RP_MAX_REC];
+    float* history;         /* [(T+1),n_sv,B,n] state checkpoints for rp_backward, or NULL      */
+} rp_fwd_args;
+
+typedef struct rp_bwd_args {
+    int T, sampling_steps, cutoff;
+    int truncate_steps;     /* 0/>=T: full BPTT; else adjoint cut after steps t%tr==tr-1        */
+    const float* x;
+    const float* W;
+    const float* W_in;
+    const float* W_out;
+    const float* params[RP_NUM_PARAMS];
+    const float* history;   /* as written by rp_forward                                         */
+    const float* g_out_rec; /* dL/d out_rec, same shape as out_rec, or NULL                     */
+    const float* g_yT;      /* dL/d yT [n_sv,B,n] or NULL                                       */
+    float* dW;              /* [n,n]  (overwritten) or NULL                                     */
+    float* dW_in;           /* [n,m]  (overwritten) or NULL                                     */
+    float* dW_out;          /* [k,n]  (overwritten) or NULL                                     */
+    float* dparams[RP_NUM_PARAMS]; /* each [n] per-neuron sums over (t,trial) (overwritten) or NULL;
+                                      the caller reduces over neurons for shared parameters     */
+    float* g_y0;            /* [n_sv,B,n] or NULL                                               */
+    float* g_x;             /* RP_IN_DENSE only: dL/dx [T,B,n] or NULL                          */
+} rp_bwd_args;
+
+int         rp_abi_version(void);
+const char* rp_last_error(void);
+int         rp_num_state_vars(int model);                       /* LI 1, QIF/LIF 2, QIF-SFA 3   */
+int         rp_num_records(int T, int sampling_steps, int cutoff); /* records produced by a run  */
+
+int  rp_plan_create(const rp_desc* desc, rp_plan** plan);
+void rp_plan_destroy(rp_plan* plan);
+/* bytes of device workspace the plan holds (diagnostics) */
+long long rp_plan_workspace_bytes(const rp_plan* plan);
+/* kernels launched by this plan since creation (for bench.py's gpu_launches) */
+long long rp_plan_launch_count(const rp_plan* plan);
+
+int rp_forward(rp_plan* plan, const rp_fwd_args* args, void* stream);
+int rp_backward(rp_plan* plan, const rp_bwd_args* args, void* stream);
+
+/* Sequential recursive-least-squares readout training over a recorded state matrix (edges.py:227-234):
+ * for t in [0,T): y_hat = W x_t ; z = beta_inv*P x_t ; kappa = 1/(1+x_t.z) ;
+ *                 W += outer(y_t - kappa * (W + outer(y_t,z)) x_t , z) ; P -= kappa*outer(z,z) ; loss_t = |y_t-y_hat|^2
+ * X [T,n_in], Y [T,n_out], W [n_out,n_in] in/out, P [n_in,n_in] in/out, loss [T] out (or NULL), pred [T,n_out] out (or NULL). */
+int rp_rls_run(int T, int n_in, int n_out, float beta_inv, const float* X, const float* Y,
+               float* W, float* P, float* loss, float* pred, int update_every, void* stream);
+
+/* Standalone GEMM used by the engine, exposed for testing:  C[q*ldc+p] (+)= sum_k A[p*lda+k]*B[q*ldb+k]
+ * precision RP_PREC_FP32 -> FFMA kernel, RP_PREC_3XTF32 -> tcgen05 kernel (needs p,q,k extents it supports). */
+int rp_gemm_tn(int precision, int P, int Q, int K, const float* A, int lda, const float* B, int ldb,
+               float* C, int ldc, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECTIPY_B200_H */

@@ -1,0 +1,495 @@
+// C-ABI entry points of the rectipy_b200 engine (see include/rectipy_b200.h for the contract and the
+// reference lines each entry replaces).  Host side: plan/workspace management and the per-step launch
+// sequences; device side: rp_kernels.cuh (element-wise), rp_gemm_simt.cuh (FFMA), rp_gemm_tc.cuh (tcgen05).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+
+#include "../../include/rectipy_b200.h"
+#include "rp_kernels.cuh"
+#include "rp_gemm_simt.cuh"
+#include "rp_gemm_tc.cuh"
+#include "rp_rls.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+#define RP_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define RP_LAUNCH_CHECK()                                                                      \
+    do {                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+inline int nsv_of(int model) {
+    switch (model) {
+        case RP_LI_TANH: case RP_LI_SIGMOID: return 1;
+        case RP_QIF: case RP_LIF: return 2;
+        case RP_QIF_SFA: return 3;
+        default: return -1;
+    }
+}
+inline bool spiking(int model) { return model == RP_QIF || model == RP_QIF_SFA || model == RP_LIF; }
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+struct rp_plan {
+    rp_desc d;
+    int nsv;
+    int sm_count;
+    long long launches;
+    size_t ws_bytes;
+    bool use_tc;           // tcgen05 3xTF32 contractions
+    // fp32 workspaces
+    float* Wk = nullptr;     // [N][ldw]   k_i * W
+    float* WkT = nullptr;    // [N][ldw]
+    int ldw = 0;
+    float* u = nullptr;      // [B][ldu]   GEMM output (recurrent drive / Z)
+    int ldu = 0;
+    float* g = nullptr;      // [B][N]
+    float* src = nullptr;    // [B][N]     rate models: act(v)
+    float* adj = nullptr;    // [nsv][B][N]
+    float* win_acc = nullptr;// [B][N]
+    float* pp = nullptr;     // [2][nsv][B][N] ping-pong state when no history is kept
+    float* dWraw = nullptr;  // [N][ldw]
+    // 3xTF32 operand buffers (leading dims padded to the TMA box)
+    rp::TcWorkspace tc;
+};
+
+namespace {
+
+int plan_alloc(rp_plan* p, float** ptr, size_t n_floats) {
+    RP_CUDA(cudaMalloc(reinterpret_cast<void**>(ptr), n_floats * sizeof(float)));
+    p->ws_bytes += n_floats * sizeof(float);
+    return 0;
+}
+
+rp::ModelParams make_params(const rp_plan* p, const float* const* params) {
+    rp::ModelParams mp;
+    for (int q = 0; q < RP_NUM_PARAMS; ++q) {
+        mp.p[q] = params[q];
+        mp.stride[q] = p->d.param_per_neuron[q] ? 1 : 0;
+    }
+    return mp;
+}
+
+int check_params(const rp_plan* p, const float* const* params) {
+    static const int need_li[] = {RP_P_TAU, RP_P_K, RP_P_ETA};
+    for (int q : need_li) if (!params[q]) return fail("parameter slot %d (tau/k/eta) is NULL", q);
+    if (spiking(p->d.model) && !params[RP_P_TAU_S]) return fail("parameter tau_s is NULL");
+    if (p->d.model == RP_QIF_SFA && (!params[RP_P_TAU_X] || !params[RP_P_ALPHA])) return fail("parameters tau_x/alpha are NULL");
+    if (p->d.model == RP_LI_SIGMOID && (!params[RP_P_RMAX] || !params[RP_P_SIG_S] || !params[RP_P_V0]))
+        return fail("parameters r_max/s/v0 are NULL");
+    return 0;
+}
+
+inline int ew_grid(const rp_plan* p, size_t total) {
+    size_t blocks = (total + 255) / 256;
+    size_t cap = (size_t)p->sm_count * 8;
+    return (int)std::max<size_t>(1, std::min(blocks, cap));
+}
+
+// ---- contraction dispatch:  C[q*ldc+p] (+)= sum_k Aop(p,k) Bop(q,k) ------------------------------------
+int gemm_fp32(rp_plan* plan, bool kmajor, int P, int Q, int K, const float* A, int lda, const float* B, int ldb,
+              float* C, int ldc, int accumulate, cudaStream_t st, long long* launches) {
+    if (P <= 0 || Q <= 0) return 0;
+    if (K <= 0) {
+        if (!accumulate) RP_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)P * sizeof(float), Q, st));
+        return 0;
+    }
+    const bool al = aligned16(A) && aligned16(B) && aligned16(C) && (lda % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0);
+    if (kmajor && Q <= 16 && !accumulate) {
+        const bool vec = al && (K % 4 == 0);
+        for (int q0 = 0; q0 < Q; q0 += 8) {
+            const int qn = std::min(8, Q - q0);
+            const int blocks = (P + 7) / 8;   // 8 warps per block
+            if (vec) rp::k_gemv_rows<true><<<blocks, 256, 0, st>>>(P, qn, K, A, lda, B + (size_t)q0 * ldb, ldb, C + (size_t)q0 * ldc, ldc);
+            else     rp::k_gemv_rows<false><<<blocks, 256, 0, st>>>(P, qn, K, A, lda, B + (size_t)q0 * ldb, ldb, C + (size_t)q0 * ldc, ldc);
+            ++*launches;
+        }
+        RP_LAUNCH_CHECK();
+        return 0;
+    }
+    dim3 grid((P + rp::SG_BM - 1) / rp::SG_BM, (Q + rp::SG_BN - 1) / rp::SG_BN);
+    if (kmajor) {
+        const bool vec = al && (K % 4 == 0) && (P % 4 == 0);
+        if (vec) rp::k_sgemm<true, true><<<grid, 256, 0, st>>>(P, Q, K, A, lda, B, ldb, C, ldc, accumulate);
+        else     rp::k_sgemm<true, false><<<grid, 256, 0, st>>>(P, Q, K, A, lda, B, ldb, C, ldc, accumulate);
+    } else {
+        const bool vec = al && (P % 4 == 0) && (Q % 4 == 0);
+        if (vec) rp::k_sgemm<false, true><<<grid, 256, 0, st>>>(P, Q, K, A, lda, B, ldb, C, ldc, accumulate);
+        else     rp::k_sgemm<false, false><<<grid, 256, 0, st>>>(P, Q, K, A, lda, B, ldb, C, ldc, accumulate);
+    }
+    ++*launches;
+    RP_LAUNCH_CHECK();
+    (void)plan;
+    return 0;
+}
+
+// ---- model dispatch helpers -----------------------------------------------------------------------------
+#define RP_DISPATCH_MODEL(model, CALL)                                  \
+    switch (model) {                                                    \
+        case RP_LI_TANH:    { constexpr int M_ = RP_LI_TANH;    CALL; } break; \
+        case RP_LI_SIGMOID: { constexpr int M_ = RP_LI_SIGMOID; CALL; } break; \
+        case RP_QIF:        { constexpr int M_ = RP_QIF;        CALL; } break; \
+        case RP_QIF_SFA:    { constexpr int M_ = RP_QIF_SFA;    CALL; } break; \
+        case RP_LIF:        { constexpr int M_ = RP_LIF;        CALL; } break; \
+        default: return fail("unknown model id %d", model);             \
+    }
+
+struct Window { int j; int first; int close; int len; };
+
+// record windows of Network.run (network.py:590-597): records at t >= cutoff with t % S == 0, each holding the
+// mean of the outputs since the previous record; a trailing window that never reaches a record step is dropped.
+Window window_of(int t, int T, int S, int cutoff) {
+    Window w{-1, 0, 0, 0};
+    if (t < cutoff) return w;
+    const int r0 = ((cutoff + S - 1) / S) * S;
+    int j, start, rec;
+    if (t <= r0) { j = 0; start = cutoff; rec = r0; }
+    else { j = (t - r0 + S - 1) / S; rec = r0 + j * S; start = rec - S + 1; }
+    if (rec >= T) return w;
+    w.j = j; w.first = (t == start); w.close = (t == rec); w.len = rec - start + 1;
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rp_abi_version(void) { return RP_ABI_VERSION; }
+const char* rp_last_error(void) { return g_err; }
+int rp_num_state_vars(int model) { return nsv_of(model); }
+
+int rp_num_records(int T, int S, int cutoff) {
+    if (S <= 0 || T <= 0) return 0;
+    const int r0 = ((std::max(cutoff, 0) + S - 1) / S) * S;
+    if (r0 > T - 1) return 0;
+    return (T - 1 - r0) / S + 1;
+}
+
+int rp_plan_create(const rp_desc* d, rp_plan** out) {
+    if (!d || !out) return fail("rp_plan_create: null argument");
+    const int nsv = nsv_of(d->model);
+    if (nsv < 0) return fail("rp_plan_create: unknown model %d", d->model);
+    if (d->n <= 0 || d->batch <= 0) return fail("rp_plan_create: n and batch must be positive");
+    if (d->in_mode == RP_IN_PROJ && (d->n_in <= 0 || d->n_in > RP_MAX_IN)) return fail("rp_plan_create: n_in must be in [1,%d] for RP_IN_PROJ", RP_MAX_IN);
+    if (d->out_mode == RP_OUT_READOUT && (d->n_out <= 0 || d->n_out > RP_MAX_OUT)) return fail("rp_plan_create: n_out must be in [1,%d] for RP_OUT_READOUT", RP_MAX_OUT);
+    if (d->out_var < 0 || d->out_var > RP_VAR_R) return fail("rp_plan_create: bad out_var");
+    if (d->out_var == RP_VAR_R && spiking(d->model)) return fail("rp_plan_create: RP_VAR_R only exists on rate models");
+    if (d->out_var != RP_VAR_R && d->out_var >= nsv) return fail("rp_plan_create: out_var %d not a state variable of model %d", d->out_var, d->model);
+    if (d->in_target == 1 && d->model != RP_LIF) return fail("rp_plan_create: in_target=1 (s_ext) only exists on the lif template");
+    if (!(d->dt > 0.f)) return fail("rp_plan_create: dt must be positive");
+    int dev = 0, count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail("rp_plan_create: no CUDA device available (the engine has no CPU fallback)");
+    RP_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    RP_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail("rp_plan_create: device is sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor);
+
+    rp_plan* p = new (std::nothrow) rp_plan();
+    if (!p) return fail("rp_plan_create: out of host memory");
+    p->d = *d;
+    p->nsv = nsv;
+    p->sm_count = prop.multiProcessorCount;
+    p->launches = 0;
+    p->ws_bytes = 0;
+    const int N = d->n, B = d->batch;
+    p->use_tc = (d->precision == RP_PREC_3XTF32);
+    if (p->use_tc && !rp::tc_supported(N, B)) {
+        delete p;
+        return fail("rp_plan_create: RP_PREC_3XTF32 needs n %% 128 == 0 and batch %% 128 == 0 (got n=%d batch=%d)", N, B);
+    }
+    p->ldw = round_up(N, 4);
+    p->ldu = round_up(N, 4);
+    const size_t plane = (size_t)B * N;
+    int rc = 0;
+    rc |= plan_alloc(p, &p->u, (size_t)B * p->ldu);
+    rc |= plan_alloc(p, &p->adj, (size_t)nsv * plane);
+    rc |= plan_alloc(p, &p->win_acc, plane);
+    rc |= plan_alloc(p, &p->pp, 2 * (size_t)nsv * plane);
+    if (!p->use_tc) {
+        rc |= plan_alloc(p, &p->Wk, (size_t)N * p->ldw);
+        rc |= plan_alloc(p, &p->WkT, (size_t)N * p->ldw);
+        rc |= plan_alloc(p, &p->g, plane);
+        if (!spiking(d->model)) rc |= plan_alloc(p, &p->src, plane);
+    } else {
+        size_t bytes = 0;
+        rc |= rp::tc_workspace_create(&p->tc, N, B, &bytes);
+        if (rc) fail("rp_plan_create: tensor-core workspace allocation failed: %s", rp::tc_last_error());
+        p->ws_bytes += bytes;
+    }
+    if (rc) { rp_plan_destroy(p); return 1; }
+    *out = p;
+    return 0;
+}
+
+void rp_plan_destroy(rp_plan* p) {
+    if (!p) return;
+    float* bufs[] = {p->Wk, p->WkT, p->u, p->g, p->src, p->adj, p->win_acc, p->pp, p->dWraw};
+    for (float* b : bufs) if (b) cudaFree(b);
+    rp::tc_workspace_destroy(&p->tc);
+    delete p;
+}
+
+long long rp_plan_workspace_bytes(const rp_plan* p) { return p ? (long long)p->ws_bytes : 0; }
+long long rp_plan_launch_count(const rp_plan* p) { return p ? p->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------------
+int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
+    if (!p || !a) return fail("rp_forward: null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const rp_desc& d = p->d;
+    const int N = d.n, B = d.batch, nsv = p->nsv;
+    const size_t plane = (size_t)B * N, slot = (size_t)nsv * plane;
+    if (a->T < 0 || a->sampling_steps <= 0 || a->cutoff < 0) return fail("rp_forward: bad T/sampling_steps/cutoff");
+    if (!a->W || !a->y0 || !a->yT) return fail("rp_forward: W, y0 and yT are required");
+    if (d.in_mode != RP_IN_NONE && !a->x && a->T > 0) return fail("rp_forward: x is NULL but in_mode != RP_IN_NONE");
+    if (d.in_mode == RP_IN_PROJ && !a->W_in) return fail("rp_forward: W_in is NULL for RP_IN_PROJ");
+    if (d.out_mode == RP_OUT_READOUT && a->out_rec && !a->W_out) return fail("rp_forward: W_out is NULL for RP_OUT_READOUT");
+    if (a->n_rec_vars < 0 || a->n_rec_vars > RP_MAX_REC) return fail("rp_forward: n_rec_vars out of range");
+    for (int r = 0; r < a->n_rec_vars; ++r) {
+        if (a->rec_var[r] < 0 || a->rec_var[r] >= nsv) return fail("rp_forward: recorded variable %d is not a state variable", a->rec_var[r]);
+        if (!a->rec_buf[r]) return fail("rp_forward: rec_buf[%d] is NULL", r);
+    }
+    if (check_params(p, a->params)) return 1;
+    const rp::ModelParams mp = make_params(p, a->params);
+    const int kstride = d.param_per_neuron[RP_P_K] ? 1 : 0;
+
+    // weights: fold k into W once per call
+    {
+        dim3 grid((N + 31) / 32, (N + 31) / 32);
+        if (!p->use_tc) rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[RP_P_K], kstride, p->Wk, nullptr, p->ldw, nullptr, nullptr, nullptr, nullptr);
+        else rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[RP_P_K], kstride, nullptr, nullptr, p->tc.ldk, p->tc.W_hi, p->tc.W_lo, nullptr, nullptr);
+        ++p->launches;
+        RP_LAUNCH_CHECK();
+    }
+    float* base = a->history ? a->history : p->pp;
+    auto slot_ptr = [&](int t) -> float* { return a->history ? base + (size_t)t * slot : base + (size_t)(t & 1) * slot; };
+    RP_CUDA(cudaMemcpyAsync(slot_ptr(0), a->y0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+    const bool spk = spiking(d.model);
+    if (a->T > 0 && (!spk || p->use_tc)) {
+        RP_DISPATCH_MODEL(d.model, (rp::k_init_src<M_><<<ew_grid(p, plane), 256, 0, st>>>(N, B, slot_ptr(0), mp,
+                                    (!spk && !p->use_tc) ? p->src : nullptr, p->use_tc ? p->tc.src_hi : nullptr,
+                                    p->use_tc ? p->tc.src_lo : nullptr, p->tc.ldk)));
+        ++p->launches;
+        RP_LAUNCH_CHECK();
+    }
+    const size_t x_stride = d.in_mode == RP_IN_DENSE ? plane : (d.in_mode == RP_IN_PROJ ? (size_t)B * d.n_in : 0);
+    const size_t out_stride = d.out_mode == RP_OUT_READOUT ? (size_t)B * d.n_out : plane;
+
+    for (int t = 0; t < a->T; ++t) {
+        float* cur = slot_ptr(t);
+        float* nxt = slot_ptr(t + 1);
+        // u[b][i] = sum_j (kW)[i][j] src_t[b][j]
+        if (!p->use_tc) {
+            const float* srcp = spk ? cur + plane : p->src;
+            if (gemm_fp32(p, true, N, B, N, p->Wk, p->ldw, srcp, N, p->u, p->ldu, 0, st, &p->launches)) return 1;
+        } else {
+            if (rp::tc_gemm(&p->tc, rp::TC_FWD, p->u, p->ldu, 0, 0, st)) return fail("rp_forward: %s", rp::tc_last_error());
+            ++p->launches;
+        }
+        rp::FwdStepArgs fa;
+        fa.N = N; fa.B = B; fa.m = d.n_in; fa.in_mode = d.in_mode; fa.in_target = d.in_target;
+        fa.dt = d.dt; fa.theta = d.theta; fa.v_reset = d.v_reset;
+        fa.y_cur = cur; fa.y_next = nxt; fa.u = p->u; fa.ldu = p->ldu;
+        fa.x_t = a->x ? a->x + (size_t)t * x_stride : nullptr; fa.W_in = a->W_in; fa.mp = mp;
+        fa.src_next = (!spk && !p->use_tc) ? p->src : nullptr;
+        fa.src_hi = p->use_tc ? p->tc.src_hi : nullptr; fa.src_lo = p->use_tc ? p->tc.src_lo : nullptr; fa.ld_src = p->tc.ldk;
+        RP_DISPATCH_MODEL(d.model, (rp::k_fwd_step<M_><<<ew_grid(p, plane), 256, 0, st>>>(fa)));
+        ++p->launches;
+        RP_LAUNCH_CHECK();
+
+        const Window w = window_of(t, a->T, a->sampling_steps, a->cutoff);
+        const bool want = a->out_rec != nullptr || a->n_rec_vars > 0;
+        if (w.j >= 0 && want && (w.close || (a->out_rec && w.len > 1))) {
+            rp::ObsArgs oa;
+            oa.N = N; oa.B = B; oa.k = d.n_out; oa.out_mode = d.out_mode; oa.out_var = d.out_var; oa.model = d.model;
+            oa.y_pre = cur; oa.y_post = nxt; oa.W_out = a->W_out; oa.mp = mp; oa.win_acc = p->win_acc;
+            oa.win_first = w.first; oa.win_close = w.close; oa.inv_len = 1.0f / (float)w.len;
+            oa.out_rec_j = a->out_rec ? a->out_rec + (size_t)w.j * out_stride : nullptr;
+            oa.n_rec_vars = a->n_rec_vars;
+            for (int r = 0; r < RP_MAX_REC; ++r) {
+                oa.rec_var[r] = r < a->n_rec_vars ? a->rec_var[r] : 0;
+                oa.rec_reduce[r] = r < a->n_rec_vars ? a->rec_reduce[r] : 0;
+                oa.rec_buf_j[r] = r < a->n_rec_vars ? a->rec_buf[r] + (size_t)w.j * (a->rec_reduce[r] ? (size_t)B : plane) : nullptr;
+            }
+            oa.rec_post = spk ? 0 : 1;     // RateNet: y is post-update (nodes.py:169); SpikeResetNet: pre-update (nodes.py:387)
+            RP_DISPATCH_MODEL(d.model, (rp::k_observe<M_><<<B, 256, 0, st>>>(oa)));
+            ++p->launches;
+            RP_LAUNCH_CHECK();
+        }
+    }
+    RP_CUDA(cudaMemcpyAsync(a->yT, slot_ptr(a->T), slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
+    if (!p || !a) return fail("rp_backward: null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const rp_desc& d = p->d;
+    const int N = d.n, B = d.batch, nsv = p->nsv;
+    const size_t plane = (size_t)B * N, slot = (size_t)nsv * plane;
+    if (a->T < 0 || a->sampling_steps <= 0 || a->cutoff < 0) return fail("rp_backward: bad T/sampling_steps/cutoff");
+    if (!a->W || !a->history) return fail("rp_backward: W and history are required");
+    if (d.in_mode == RP_IN_PROJ && !a->W_in) return fail("rp_backward: W_in is NULL for RP_IN_PROJ");
+    if (d.in_mode != RP_IN_NONE && !a->x && a->T > 0) return fail("rp_backward: x is NULL but in_mode != RP_IN_NONE");
+    if (d.out_mode == RP_OUT_READOUT && a->g_out_rec && !a->W_out) return fail("rp_backward: W_out is NULL for RP_OUT_READOUT");
+    if (a->dW_in && d.in_mode != RP_IN_PROJ) return fail("rp_backward: dW_in requested without RP_IN_PROJ");
+    if (a->dW_out && d.out_mode != RP_OUT_READOUT) return fail("rp_backward: dW_out requested without RP_OUT_READOUT");
+    if (a->g_x && d.in_mode != RP_IN_DENSE) return fail("rp_backward: g_x requested without RP_IN_DENSE");
+    if (check_params(p, a->params)) return 1;
+    const rp::ModelParams mp = make_params(p, a->params);
+    const int kstride = d.param_per_neuron[RP_P_K] ? 1 : 0;
+    const bool spk = spiking(d.model);
+    const bool need_dW = a->dW != nullptr || a->dparams[RP_P_K] != nullptr;
+
+    if (need_dW && !p->dWraw) { if (plan_alloc(p, &p->dWraw, (size_t)N * p->ldw)) return 1; }
+    if (need_dW && p->use_tc) {
+        size_t bytes = 0;
+        if (rp::tc_workspace_ensure_wgrad(&p->tc, &bytes)) return fail("rp_backward: %s", rp::tc_last_error());
+        p->ws_bytes += bytes;
+    }
+    {
+        dim3 grid((N + 31) / 32, (N + 31) / 32);
+        if (!p->use_tc) rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[RP_P_K], kstride, nullptr, p->WkT, p->ldw, nullptr, nullptr, nullptr, nullptr);
+        else rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[RP_P_K], kstride, nullptr, nullptr, p->tc.ldk, nullptr, nullptr, p->tc.WT_hi, p->tc.WT_lo);
+        ++p->launches;
+        RP_LAUNCH_CHECK();
+    }
+    if (need_dW) RP_CUDA(cudaMemsetAsync(p->dWraw, 0, (size_t)N * p->ldw * sizeof(float), st));
+    for (int q = 0; q < RP_NUM_PARAMS; ++q)
+        if (a->dparams[q]) RP_CUDA(cudaMemsetAsync(a->dparams[q], 0, (size_t)N * sizeof(float), st));
+    if (a->dW_in) RP_CUDA(cudaMemsetAsync(a->dW_in, 0, (size_t)N * d.n_in * sizeof(float), st));
+    if (a->dW_out) RP_CUDA(cudaMemsetAsync(a->dW_out, 0, (size_t)N * d.n_out * sizeof(float), st));
+    if (a->g_yT) RP_CUDA(cudaMemcpyAsync(p->adj, a->g_yT, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else RP_CUDA(cudaMemsetAsync(p->adj, 0, slot * sizeof(float), st));
+
+    const size_t x_stride = d.in_mode == RP_IN_DENSE ? plane : (d.in_mode == RP_IN_PROJ ? (size_t)B * d.n_in : 0);
+    const size_t out_stride = d.out_mode == RP_OUT_READOUT ? (size_t)B * d.n_out : plane;
+    const int tr = a->truncate_steps;
+    const bool truncating = tr > 0 && tr < a->T;
+    const int wg_chunk = p->use_tc ? p->tc.wgrad_chunk : 1;
+
+    rp::AdjArgs aa;
+    memset(&aa, 0, sizeof(aa));
+    aa.N = N; aa.B = B; aa.m = d.n_in; aa.k = d.n_out; aa.in_mode = d.in_mode; aa.in_target = d.in_target;
+    aa.out_mode = d.out_mode; aa.out_var = d.out_var; aa.dt = d.dt; aa.theta = d.theta; aa.slope = d.slope;
+    aa.adj = p->adj; aa.Z = p->u; aa.ldz = p->ldu; aa.W_in = a->W_in; aa.W_out = a->W_out; aa.mp = mp;
+    if (!p->use_tc) { aa.g = p->g; aa.src = spk ? nullptr : p->src; }
+    else { aa.g_hi = p->tc.g_hi; aa.g_lo = p->tc.g_lo; aa.ld_g = p->tc.ldk; aa.ld_t = p->tc.ldt; }
+    for (int q = 0; q < RP_NUM_PARAMS; ++q) aa.dparams[q] = (q == RP_P_K) ? nullptr : a->dparams[q];
+    aa.dW_in = a->dW_in; aa.dW_out = a->dW_out;
+    aa.any_param_grad = (a->dW_in || a->dW_out) ? 1 : 0;
+    for (int q = 0; q < RP_NUM_PARAMS; ++q) if (aa.dparams[q]) aa.any_param_grad = 1;
+
+    dim3 agrid((N + rp::ADJ_TX - 1) / rp::ADJ_TX, (B + rp::ADJ_TY * rp::ADJ_BPT - 1) / (rp::ADJ_TY * rp::ADJ_BPT));
+    dim3 ablock(rp::ADJ_TX, rp::ADJ_TY);
+    int pending = 0;   // steps whose (g, src) columns sit in the tensor-core weight-gradient chunk
+
+    // t == T is the "pre only" launch that builds g_{T-1}
+    for (int t = a->T; t >= 0; --t) {
+        if (t == a->T && a->T == 0) break;
+        aa.do_post = (t < a->T) ? 1 : 0;
+        aa.do_pre = (t > 0) ? 1 : 0;
+        if (aa.do_post) {
+            // Z[b][j] = sum_i (kW)^T[j][i] g_t[b][i]
+            if (!p->use_tc) {
+                if (gemm_fp32(p, true, N, B, N, p->WkT, p->ldw, p->g, N, p->u, p->ldu, 0, st, &p->launches)) return 1;
+                if (need_dW) {
+                    const float* srcp = spk ? a->history + (size_t)t * slot + plane : p->src;
+                    if (B <= 16) {
+                        dim3 og((N + 255) / 256, N);
+                        rp::k_outer_acc<<<og, 256, 0, st>>>(N, B, p->g, N, srcp, N, p->dWraw, p->ldw);
+                        ++p->launches;
+                        RP_LAUNCH_CHECK();
+                    } else {
+                        // dWraw[i][j] += sum_b src[b][j] g[b][i]   (p = j, q = i)
+                        if (gemm_fp32(p, false, N, N, B, srcp, N, p->g, N, p->dWraw, p->ldw, 1, st, &p->launches)) return 1;
+                    }
+                }
+            } else {
+                if (rp::tc_gemm(&p->tc, rp::TC_DGRAD, p->u, p->ldu, 0, 0, st)) return fail("rp_backward: %s", rp::tc_last_error());
+                ++p->launches;
+            }
+            const Window w = window_of(t, a->T, a->sampling_steps, a->cutoff);
+            aa.y_t = a->history + (size_t)t * slot;
+            aa.x_t = a->x ? a->x + (size_t)t * x_stride : nullptr;
+            aa.e_t = (a->g_out_rec && w.j >= 0) ? a->g_out_rec + (size_t)w.j * out_stride : nullptr;
+            aa.e_scale = w.j >= 0 ? 1.0f / (float)w.len : 0.f;
+            aa.g_x_t = a->g_x ? a->g_x + (size_t)t * plane : nullptr;
+            aa.zero_after_post = (truncating && t > 0 && t % tr == 0) ? 1 : 0;
+        }
+        if (aa.do_pre) {
+            aa.y_tm1 = a->history + (size_t)(t - 1) * slot;
+            if (p->use_tc && need_dW) {
+                aa.gT_hi = p->tc.gT_hi; aa.gT_lo = p->tc.gT_lo; aa.srcT_hi = p->tc.srcT_hi; aa.srcT_lo = p->tc.srcT_lo;
+                aa.t_col0 = pending * B;
+            }
+        }
+        RP_DISPATCH_MODEL(d.model, (rp::k_adj_step<M_><<<agrid, ablock, 0, st>>>(aa)));
+        ++p->launches;
+        RP_LAUNCH_CHECK();
+        if (p->use_tc && need_dW && aa.do_pre) {
+            ++pending;
+            if (pending == wg_chunk || t == 1) {
+                // dWraw[i][j] += sum_{(t,b) in chunk} g[b][i] src[b][j]
+                if (rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, pending * B, 1, st)) return fail("rp_backward: %s", rp::tc_last_error());
+                ++p->launches;
+                pending = 0;
+            }
+        }
+    }
+    if (need_dW) {
+        rp::k_finish_wgrad<<<N, 256, 0, st>>>(N, p->dWraw, p->ldw, a->W, a->params[RP_P_K], kstride, a->dW, a->dparams[RP_P_K]);
+        ++p->launches;
+        RP_LAUNCH_CHECK();
+    }
+    if (a->g_y0) RP_CUDA(cudaMemcpyAsync(a->g_y0, p->adj, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int rp_gemm_tn(int precision, int P, int Q, int K, const float* A, int lda, const float* B, int ldb,
+               float* C, int ldc, int accumulate, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long launches = 0;
+    if (precision == RP_PREC_FP32) return gemm_fp32(nullptr, true, P, Q, K, A, lda, B, ldb, C, ldc, accumulate, st, &launches);
+    if (precision == RP_PREC_3XTF32) {
+        if (rp::tc_gemm_standalone(P, Q, K, A, lda, B, ldb, C, ldc, accumulate, st)) return fail("rp_gemm_tn: %s", rp::tc_last_error());
+        return 0;
+    }
+    return fail("rp_gemm_tn: unknown precision %d", precision);
+}
+
+int rp_rls_run(int T, int n_in, int n_out, float beta_inv, const float* X, const float* Y, float* W, float* P,
+               float* loss, float* pred, int update_every, void* stream) {
+    if (T < 0 || n_in <= 0 || n_out <= 0 || !X || !Y || !W || !P) return fail("rp_rls_run: bad argument");
+    if (n_out > RP_RLS_MAX_OUT) return fail("rp_rls_run: n_out must be <= %d", RP_RLS_MAX_OUT);
+    if (update_every <= 0) update_every = 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (rp::rls_run(T, n_in, n_out, beta_inv, X, Y, W, P, loss, pred, update_every, st)) return fail("rp_rls_run: %s", rp::rls_last_error());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+// tcgen05 (5th-gen tensor core) contraction with error-compensated 3xTF32 accumulation, sm_100a only.
+//
+//   C[q*ldc + p] (+)= sum_k A[p][k] * B[q][k]        A, B K-major fp32, each pre-split into tf32-exact (hi, lo)
+//   A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo         three kind::tf32 MMAs per logical product, fp32 accumulate in TMEM
+//
+// This is what replaces `weights @ x` (edges.py:49 / the generated field, nodes.py:169) and autograd's W^T.grad and
+// grad (x) r products when many trials are batched.  1e-5 parity (BASELINE.json) rules out single-pass TF32.
+//
+// Kernel shape: one CTA per 128(p) x BQ(q) tile, 6 warps:
+//   warp 0   TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B boxes of 32 fp32 = 128 B rows)
+//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (12 MMAs of K=8 per 32-wide K block)
+//   warps 2-5 epilogue      (tcgen05.ld 32x32b -> registers -> coalesced global stores, p fastest)
+// smem ring of full/empty mbarriers between producer and issuer; tcgen05.commit releases stages and signals the epilogue.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace rp {
+
+inline char* tc_err_buf() { static thread_local char buf[384] = ""; return buf; }
+inline const char* tc_last_error() { return tc_err_buf(); }
+#define RP_TC_FAIL(...) do { snprintf(rp::tc_err_buf(), 384, __VA_ARGS__); return 1; } while (0)
+
+constexpr int TC_BP = 128;          // tile rows (UMMA M, TMEM lanes)
+constexpr int TC_BK = 32;           // fp32 elements per K block = one 128-byte swizzle row
+constexpr int TC_UMMA_K = 8;        // tf32 MMA K
+constexpr int TC_THREADS = 192;
+
+enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
+
+// ---------------------------------------------------------------------------------------------------------
+// device helpers (inline PTX)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, %1;\n"
+        "@px mov.s32 %0, 1;\n"
+        "}\n" : "+r"(pred) : "r"(0xffffffffu));
+    return pred != 0;
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024>>4 | [46,48) version=1 | [61,64) layout=2
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format TF32 [7,10)=[10,13)=2,
+// a/b K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_tf32_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+template <int BQ> struct TcCfg {
+    static constexpr int STAGES = (BQ == 256) ? 2 : 3;
+    static constexpr int A_BYTES = TC_BP * 128;
+    static constexpr int B_BYTES = BQ * 128;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BQ>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+              float* __restrict__ C, int ldc, int num_k_blocks, int accumulate) {
+    using Cfg = TcCfg<BQ>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p0 = blockIdx.x * TC_BP, q0 = blockIdx.y * BQ;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        // allocate BQ TMEM columns (power of two >= 32) for the fp32 accumulator tile
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BQ) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                tma_load_2d(sa, &tmA_hi, &full_bar[stage], kb * TC_BK, p0);
+                tma_load_2d(sa + Cfg::A_BYTES, &tmA_lo, &full_bar[stage], kb * TC_BK, p0);
+                tma_load_2d(sa + 2 * Cfg::A_BYTES, &tmB_hi, &full_bar[stage], kb * TC_BK, q0);
+                tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tmB_lo, &full_bar[stage], kb * TC_BK, q0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected thread) =====
+        constexpr uint32_t idesc = make_tf32_idesc(TC_BP, BQ);
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                const uint64_t dA_hi = make_sw128_kmajor_desc(sa);
+                const uint64_t dA_lo = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
+                const uint64_t dB_hi = make_sw128_kmajor_desc(sa + 2 * Cfg::A_BYTES);
+                const uint64_t dB_lo = make_sw128_kmajor_desc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                    const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);     // 32 bytes per K=8 step, encoded >>4
+                    // small cross terms first, leading term last
+                    umma_tf32(tmem_base, dA_lo + adv, dB_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_tf32(tmem_base, dA_hi + adv, dB_lo + adv, idesc, 1u);
+                    umma_tf32(tmem_base, dA_hi + adv, dB_hi + adv, idesc, 1u);
+                }
+                umma_commit(&empty_bar[stage]);                       // frees the smem stage when these MMAs retire
+                if (kb == num_k_blocks - 1) umma_commit(tmem_full_bar);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+        const int lane_base = (warp & 3) * 32;
+        const int p = p0 + lane_base + lane;
+        if (num_k_blocks > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+#pragma unroll 1
+        for (int c = 0; c < BQ / 32; ++c) {
+            uint32_t r[32];
+            if (num_k_blocks > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(c * 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float* dst = C + (size_t)(q0 + c * 32 + j) * ldc + p;
+                float v = __uint_as_float(r[j]);
+                if (accumulate) v += *dst;
+                *dst = v;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BQ) : "memory");
+    }
+}
+
+// split a dense fp32 matrix [rows][ld] into tf32-exact hi/lo copies [rows][ld_out] (zero padded)
+__global__ void __launch_bounds__(256) k_split_matrix(int rows, int cols, const float* __restrict__ src, int ld,
+                                                       float* __restrict__ hi, float* __restrict__ lo, int ld_out, int rows_out) {
+    const size_t total = (size_t)rows_out * ld_out;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / ld_out), c = (int)(idx - (size_t)r * ld_out);
+        float h = 0.f, l = 0.f;
+        if (r < rows && c < cols) {
+            const float x = src[(size_t)r * ld + c];
+            h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+            l = __uint_as_float(__float_as_uint(x - h) & 0xffffe000u);
+        }
+        hi[idx] = h; lo[idx] = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+inline PFN_cuTensorMapEncodeTiled_v12000 tc_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+// 2D K-major operand map: global [rows][ld] fp32, box = 32 (K) x box_rows, 128-byte swizzle
+inline int tc_make_map(CUtensorMap* map, const float* base, int rows, int k_extent, int ld, int box_rows) {
+    auto fn = tc_encode_fn();
+    if (!fn) RP_TC_FAIL("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) RP_TC_FAIL("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d k=%d ld=%d box_rows=%d)", (int)r, rows, k_extent, ld, box_rows);
+    return 0;
+}
+
+inline bool tc_supported(int N, int B) { return N % 128 == 0 && B % 128 == 0 && N >= 128 && B >= 128; }
+
+struct TcWorkspace {
+    int N = 0, B = 0, ldk = 0, ldt = 0, wgrad_chunk = 0;
+    float *W_hi = nullptr, *W_lo = nullptr, *WT_hi = nullptr, *WT_lo = nullptr;       // [N][ldk]
+    float *src_hi = nullptr, *src_lo = nullptr, *g_hi = nullptr, *g_lo = nullptr;     // [B][ldk]
+    float *gT_hi = nullptr, *gT_lo = nullptr, *srcT_hi = nullptr, *srcT_lo = nullptr; // [N][ldt]
+    int bq_fwd = 0, bq_wg = 0;
+    CUtensorMap m_W[2], m_WT[2], m_src[2], m_g[2], m_gT[2], m_srcT[2];
+    bool attrs_set = false;
+};
+
+inline int tc_alloc(float** p, size_t n, size_t* bytes) {
+    if (cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(float)) != cudaSuccess) RP_TC_FAIL("cudaMalloc of %zu bytes failed", n * sizeof(float));
+    if (cudaMemset(*p, 0, n * sizeof(float)) != cudaSuccess) RP_TC_FAIL("cudaMemset failed");
+    *bytes += n * sizeof(float);
+    return 0;
+}
+
+inline int tc_set_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_3xtf32<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_3xtf32<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
+    if (e != cudaSuccess) RP_TC_FAIL("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+inline void tc_workspace_destroy(TcWorkspace* w) {
+    float* bufs[] = {w->W_hi, w->W_lo, w->WT_hi, w->WT_lo, w->src_hi, w->src_lo, w->g_hi, w->g_lo, w->gT_hi, w->gT_lo, w->srcT_hi, w->srcT_lo};
+    for (float* b : bufs) if (b) cudaFree(b);
+    *w = TcWorkspace();
+}
+
+inline int tc_workspace_create(TcWorkspace* w, int N, int B, size_t* bytes) {
+    w->N = N; w->B = B; w->ldk = N;
+    // weight-gradient K chunk: several steps' (g, src) columns per GEMM so that the read-modify-write of dW amortises
+    int chunk = 8192 / B; if (chunk < 1) chunk = 1; if (chunk > 16) chunk = 16;
+    w->wgrad_chunk = chunk;
+    w->ldt = chunk * B;
+    w->bq_fwd = (B % 256 == 0) ? 256 : 128;
+    w->bq_wg = (N % 256 == 0) ? 256 : 128;
+    const size_t nn = (size_t)N * w->ldk, bn = (size_t)B * w->ldk;
+    if (tc_alloc(&w->W_hi, nn, bytes) || tc_alloc(&w->W_lo, nn, bytes) || tc_alloc(&w->WT_hi, nn, bytes) || tc_alloc(&w->WT_lo, nn, bytes)) return 1;
+    if (tc_alloc(&w->src_hi, bn, bytes) || tc_alloc(&w->src_lo, bn, bytes) || tc_alloc(&w->g_hi, bn, bytes) || tc_alloc(&w->g_lo, bn, bytes)) return 1;
+    if (tc_make_map(&w->m_W[0], w->W_hi, N, N, w->ldk, TC_BP) || tc_make_map(&w->m_W[1], w->W_lo, N, N, w->ldk, TC_BP)) return 1;
+    if (tc_make_map(&w->m_WT[0], w->WT_hi, N, N, w->ldk, TC_BP) || tc_make_map(&w->m_WT[1], w->WT_lo, N, N, w->ldk, TC_BP)) return 1;
+    if (tc_make_map(&w->m_src[0], w->src_hi, B, N, w->ldk, w->bq_fwd) || tc_make_map(&w->m_src[1], w->src_lo, B, N, w->ldk, w->bq_fwd)) return 1;
+    if (tc_make_map(&w->m_g[0], w->g_hi, B, N, w->ldk, w->bq_fwd) || tc_make_map(&w->m_g[1], w->g_lo, B, N, w->ldk, w->bq_fwd)) return 1;
+    if (tc_set_attrs()) return 1;
+    return 0;
+}
+
+// the transposed (trial-major) operand buffers of the weight gradient are only needed by rp_backward
+inline int tc_workspace_ensure_wgrad(TcWorkspace* w, size_t* bytes) {
+    if (w->gT_hi) return 0;
+    const size_t nt = (size_t)w->N * w->ldt;
+    if (tc_alloc(&w->gT_hi, nt, bytes) || tc_alloc(&w->gT_lo, nt, bytes) || tc_alloc(&w->srcT_hi, nt, bytes) || tc_alloc(&w->srcT_lo, nt, bytes)) return 1;
+    if (tc_make_map(&w->m_srcT[0], w->srcT_hi, w->N, w->ldt, w->ldt, TC_BP) || tc_make_map(&w->m_srcT[1], w->srcT_lo, w->N, w->ldt, w->ldt, TC_BP)) return 1;
+    if (tc_make_map(&w->m_gT[0], w->gT_hi, w->N, w->ldt, w->ldt, w->bq_wg) || tc_make_map(&w->m_gT[1], w->gT_lo, w->N, w->ldt, w->ldt, w->bq_wg)) return 1;
+    return 0;
+}
+
+inline int tc_launch(int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, float* C, int ldc, int accumulate, cudaStream_t st) {
+    if (P % TC_BP || Q % bq || K % TC_BK) RP_TC_FAIL("tc_launch: extents P=%d Q=%d K=%d do not match tile %dx%dx%d", P, Q, K, TC_BP, bq, TC_BK);
+    dim3 grid(P / TC_BP, Q / bq);
+    if (bq == 256) k_gemm_3xtf32<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], C, ldc, K / TC_BK, accumulate);
+    else           k_gemm_3xtf32<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], C, ldc, K / TC_BK, accumulate);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) RP_TC_FAIL("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// mode TC_FWD:   C=u[b][i]     A = kW (hi,lo)      B = src (hi,lo)     K = N
+// mode TC_DGRAD: C=Z[b][j]     A = (kW)^T          B = g               K = N
+// mode TC_WGRAD: C=dW[i][j] += A = src^T [j][(t,b)] B = g^T [i][(t,b)] K = k_extent (columns filled in the chunk)
+inline int tc_gemm(TcWorkspace* w, int mode, float* C, int ldc, int k_extent, int accumulate, cudaStream_t st) {
+    switch (mode) {
+        case TC_FWD:   return tc_launch(w->bq_fwd, w->N, w->B, w->N, w->m_W, w->m_src, C, ldc, accumulate, st);
+        case TC_DGRAD: return tc_launch(w->bq_fwd, w->N, w->B, w->N, w->m_WT, w->m_g, C, ldc, accumulate, st);
+        case TC_WGRAD: return tc_launch(w->bq_wg, w->N, w->N, k_extent, w->m_srcT, w->m_gT, C, ldc, accumulate, st);
+    }
+    RP_TC_FAIL("tc_gemm: unknown mode %d", mode);
+}
+
+// test entry: arbitrary K-major fp32 operands (split on the fly into temporaries)
+inline int tc_gemm_standalone(int P, int Q, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                              int accumulate, cudaStream_t st) {
+    if (P % TC_BP || Q % 128 || K <= 0) RP_TC_FAIL("3xTF32 GEMM needs P %% 128 == 0, Q %% 128 == 0 (got P=%d Q=%d K=%d)", P, Q, K);
+    if (tc_set_attrs()) return 1;
+    const int Kp = (K + TC_BK - 1) / TC_BK * TC_BK;
+    const int bq = (Q % 256 == 0) ? 256 : 128;
+    float* tmp = nullptr;
+    const size_t na = (size_t)P * Kp, nb = (size_t)Q * Kp;
+    if (cudaMalloc(reinterpret_cast<void**>(&tmp), 2 * (na + nb) * sizeof(float)) != cudaSuccess) RP_TC_FAIL("cudaMalloc of split temporaries failed");
+    float *a_hi = tmp, *a_lo = tmp + na, *b_hi = tmp + 2 * na, *b_lo = tmp + 2 * na + nb;
+    k_split_matrix<<<1024, 256, 0, st>>>(P, K, A, lda, a_hi, a_lo, Kp, P);
+    k_split_matrix<<<1024, 256, 0, st>>>(Q, K, B, ldb, b_hi, b_lo, Kp, Q);
+    CUtensorMap mA[2], mB[2];
+    int rc = tc_make_map(&mA[0], a_hi, P, Kp, Kp, TC_BP) || tc_make_map(&mA[1], a_lo, P, Kp, Kp, TC_BP) ||
+             tc_make_map(&mB[0], b_hi, Q, Kp, Kp, bq) || tc_make_map(&mB[1], b_lo, Q, Kp, Kp, bq);
+    if (!rc) rc = tc_launch(bq, P, Q, Kp, mA, mB, C, ldc, accumulate, st);
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    return rc;
+}
+
+}  // namespace rp

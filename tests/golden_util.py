@@ -96,3 +96,71 @@ def oracle_run_case(case: Case, dtype_name: str):
 def rel_err(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
+
+
+# ---- the same cases on the engine (rectipy_b200 public API) -------------------------------------------------
+TEMPLATE_PATH = {
+    "li_tanh": ("neuron_model_templates.rate_neurons.leaky_integrator.tanh", "li_op", "tanh_op/r", "li_op/r_in"),
+    "li_sigmoid": ("neuron_model_templates.rate_neurons.leaky_integrator.sigmoid", "li_op", "sigmoid_op/r", "li_op/r_in"),
+    "qif": ("neuron_model_templates.spiking_neurons.qif.qif", "qif_op", "s", "s_in"),
+    "qif_sfa": ("neuron_model_templates.spiking_neurons.qif.qif_sfa", "qif_sfa_op", "s", "s_in"),
+    "lif": ("neuron_model_templates.spiking_neurons.lif.lif", "lif_op", "s", "s_in"),
+}
+
+
+def engine_net(case: "Case", device="cuda:0", batch=1, precision="auto", params_override=None):
+    """Build the golden case through the drop-in API (add_diffeq_node / add_func_node / add_edge)."""
+    import rectipy_b200 as rp
+    m = case.meta
+    model = m["model"]
+    path, op, svar, tvar = TEMPLATE_PATH[model]
+    net = rp.Network(m["dt"], device=device, batch=batch, precision=precision)
+    params = case.params_py()
+    if params_override:
+        params.update(params_override)
+    sigmoid_keys = {"r_max", "s", "v0"}
+    node_vars = {(f"sigmoid_op/{k}" if (model == "li_sigmoid" and k in sigmoid_keys) else f"{op}/{k}"): v
+                 for k, v in params.items()}
+    kw = dict(weights=case.inp["W"], source_var=svar, target_var=tvar, input_var=f"{op}/I_ext",
+              node_vars=node_vars, train_params=[("weights" if p == "weights" else f"{op}/{p}") for p in (m.get("train_params") or [])])
+    if model in orc.SPIKING:
+        kw.update(spike_var=f"{op}/spike", reset_var=f"{op}/v", output_var=f"{op}/s", **(m.get("spike_kwargs") or {}))
+    else:
+        kw.update(output_var=f"{op}/v")
+    node = net.add_diffeq_node("rnn", path, **kw)
+    if "w_in" in case.inp:
+        net.add_func_node("inp", case.inp["w_in"].shape[1], m.get("in_act", "identity"))
+        ekw = {"mask": case.inp["in_mask"]} if "in_mask" in case.inp else {}
+        net.add_edge("inp", "rnn", weights=case.inp["w_in"], train="gd" if m.get("train_in") else None, **ekw)
+    if "w_out" in case.inp:
+        net.add_func_node("out", case.inp["w_out"].shape[0], m.get("out_act", "identity"))
+        net.add_edge("rnn", "out", weights=case.inp["w_out"], train="gd" if m.get("train_out") else None)
+    return net, node
+
+
+def engine_run_case(case: "Case", device="cuda:0", precision="auto"):
+    """Run a golden case on the engine; same result keys as the golden blob."""
+    m = case.meta
+    net, node = engine_net(case, device=device, precision=precision)
+    rec = [("rnn", v, red) for v, red in m.get("record_vars", [])]
+    kw = {}
+    if "truncate_steps" in m:
+        kw["truncate_steps"] = m["truncate_steps"]
+    obs = net.run(case.inp["inputs"], sampling_steps=m.get("S", 1), cutoff=m.get("cutoff", 0), verbose=False,
+                  enable_grad=bool(m.get("grad")), record_vars=rec, **kw)
+    res = {"out": obs.to_numpy("out"), "steps": np.asarray(obs["steps"])}
+    for v, red in m.get("record_vars", []):
+        res[f"var_{v}"] = obs.to_numpy(("rnn", v))
+    res["y_final"] = node.y.detach().cpu().numpy()
+    if m.get("grad"):
+        target = torch.tensor(case.inp["targets"], dtype=torch.float32, device=device)
+        loss = torch.nn.MSELoss()(torch.stack(obs["out"]), target)
+        loss.backward()
+        res["loss"] = loss.detach().cpu().numpy()
+        for name in m.get("train_params") or []:
+            res[f"grad_{name}"] = node[name].grad.detach().cpu().numpy()
+        if m.get("train_in"):
+            res["grad_w_in"] = net.get_edge("inp", "rnn").weights.grad.detach().cpu().numpy()
+        if m.get("train_out"):
+            res["grad_w_out"] = net.get_edge("rnn", "out").weights.grad.detach().cpu().numpy()
+    return res

@@ -1,0 +1,168 @@
+"""GPU tests of the drop-in API semantics (mirrors rectipy_tests/test_network.py:293-420 and test_nodes.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import GOLDEN, rel_err, orc
+
+pytestmark = pytest.mark.gpu
+
+NODE = "neuron_model_templates.rate_neurons.leaky_integrator.tanh"
+
+
+def _rate_net(n=10, dt=1e-2, seed=0, **kw):
+    import rectipy_b200 as rp
+    rng = np.random.default_rng(seed)
+    W = rng.standard_normal((n, n))
+    net = rp.Network(dt=dt, device="cuda:0")
+    node = net.add_diffeq_node("rnn", NODE, weights=W, input_var="li_op/I_ext", output_var="li_op/v",
+                               source_var="tanh_op/r", target_var="li_op/r_in", **kw)
+    return net, node, W
+
+
+def test_run_equals_manual_forward_loop():
+    """rectipy_tests/test_network.py:293-339: run(sampling_steps=2) == forward loop with window means; recorded
+    variables == get_var after each forward."""
+    n, steps = 10, 100
+    x = torch.randn(steps, n, generator=torch.Generator().manual_seed(1))
+    net1, _, _ = _rate_net(n)
+    net2, _, _ = _rate_net(n)
+    net3, _, _ = _rate_net(n)
+    net3.compile()
+    res1 = net1.run(inputs=x, sampling_steps=2, verbose=False)
+    res2 = net2.run(inputs=x, record_output=False, record_vars=[("rnn", "li_op/v", False)], verbose=False)
+    res3, res4, buf = [], [], []
+    for step in range(steps):
+        out = net3.forward(x[step, :])
+        buf.append(out.detach().cpu().numpy())
+        if step % 2 == 0:
+            res3.append(np.mean(buf, axis=0))
+            buf = []
+        res4.append(net3.get_var("rnn", var="li_op/v").detach().cpu().numpy().copy())
+    a, b = res1.to_dataframe("out").values.flatten(), np.asarray(res3).flatten()
+    assert np.max(np.abs(a - b)) < 1e-5
+    a, b = res2.to_dataframe(("rnn", "li_op/v")).values.flatten(), np.asarray(res4).flatten()
+    assert np.max(np.abs(a - b)) < 1e-5
+
+
+def test_node_forward_and_state_protocol():
+    net, node, W = _rate_net(12)
+    assert len(node.y) == 12 and node.n_in == 12 and node.n_out == 12
+    x = torch.ones(12)
+    y_before = node.y.clone()
+    out = node.forward(x)                      # returns the PRE-update slice (nodes.py:166-170)
+    assert torch.allclose(out.cpu(), y_before.cpu())
+    dt, tau = 1e-2, 10.0
+    expect = y_before.cpu() + dt * (-y_before.cpu() / tau + torch.tensor(W, dtype=torch.float32) @ torch.tanh(y_before.cpu()) + 1.0)
+    assert torch.allclose(node.y.cpu(), expect, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        node.forward(torch.ones(5))
+    snap = net.state
+    node.forward(x)
+    net.reset(snap)
+    assert torch.allclose(node.y.cpu(), expect, atol=1e-6)
+    net.reset()
+    assert float(node.y.abs().sum()) == 0.0     # reset() -> zeros (nodes.py:199-200)
+    with pytest.raises(KeyError):
+        net.get_var("rnn", "nonexistent")
+
+
+def test_spiking_node_len_and_reset_quirk():
+    import rectipy_b200 as rp
+    n = 16
+    net = rp.Network(1e-3, device="cuda:0")
+    node = net.add_diffeq_node("qif", "neuron_model_templates.spiking_neurons.qif.qif", weights=np.zeros((n, n)),
+                               source_var="s", target_var="s_in", input_var="I_ext", output_var="s", spike_var="spike",
+                               reset_var="v", op="qif_op")
+    assert isinstance(node, rp.SpikeResetNet) and len(node.y) == 2 * n      # test_nodes.py:71
+    assert torch.allclose(net.get_var("qif", "v").cpu(), torch.full((n,), -2.0))
+    # one neuron driven over threshold: s jumps by exactly 1 one step after v >= theta, v goes to v_reset
+    node.reset(torch.cat([torch.full((n,), 150.0), torch.zeros(n)]))
+    node.forward(torch.zeros(n))
+    assert torch.allclose(net.get_var("qif", "v").cpu(), torch.full((n,), -100.0))
+    assert torch.allclose(net.get_var("qif", "s").cpu(), torch.ones(n))
+
+
+def test_fit_bptt_ridge_rls_recover_readout():
+    """rectipy_tests/test_network.py:342-420 scaled down: each fitter recovers a 3 x 10 readout."""
+    import rectipy_b200 as rp
+    rng = np.random.default_rng(3)
+    n, k, steps, dt = 10, 3, 400, 1e-2
+    W = rng.standard_normal((n, n)) / np.sqrt(n)
+    w_true = rng.standard_normal((k, n))
+    x = rng.standard_normal((steps, n)).astype(np.float32)
+
+    def make(train=None, weights=None):
+        net = rp.Network(dt=dt, device="cuda:0")
+        net.add_diffeq_node("rnn", NODE, weights=W, input_var="li_op/I_ext", output_var="li_op/v",
+                            source_var="tanh_op/r", target_var="li_op/r_in", node_vars={"li_op/tau": 1.0})
+        if train is not False:
+            net.add_func_node("out", k, "identity")
+            net.add_edge("rnn", "out", weights=weights, train=train)
+        return net
+
+    target_net = make(None, w_true)
+    targets = target_net.run(x, sampling_steps=1, verbose=False, enable_grad=False).to_numpy("out")
+
+    net_ridge = make(False)
+    obs = net_ridge.fit_ridge(x, targets, sampling_steps=1, alpha=1e-6, verbose=False, add_readout_node=True)
+    w_ridge = obs["w_out"].T.cpu().numpy()
+    assert np.mean((w_ridge - w_true) ** 2) < 0.5
+    fit = net_ridge.run(x, sampling_steps=1, verbose=False, enable_grad=False).to_numpy("out")
+    assert fit.shape == targets.shape
+
+    net_rls = make("rls", None)
+    net_rls.fit_rls(x, targets, update_steps=1, sampling_steps=10, verbose=False)
+    w_rls = net_rls.get_edge("rnn", "out").weights.cpu().numpy()
+    assert np.mean((w_rls - w_true) ** 2) < 0.5
+
+    net_gd = make("gd", np.zeros((k, n)))
+    net_gd.fit_bptt([x] * 150, [targets] * 150, optimizer="adam", lr=0.1, sampling_steps=1, verbose=False)
+    w_gd = net_gd.get_edge("rnn", "out").weights.detach().cpu().numpy()
+    assert np.mean((w_gd - w_true) ** 2) < 0.5
+
+
+def test_rls_and_ridge_fixtures():
+    from rectipy_b200 import engine
+    z = np.load(os.path.join(GOLDEN, "edges.npz"))
+    X = torch.tensor(z["xs"], dtype=torch.float32, device="cuda")
+    Y = torch.tensor(z["ys"], dtype=torch.float32, device="cuda")
+    n_in, n_out = X.shape[1], Y.shape[1]
+    Wt = torch.zeros((n_out, n_in), device="cuda")
+    P = float(z["rls_alpha"]) * torch.eye(n_in, device="cuda")
+    loss, pred = engine.rls_run(X, Y, Wt, P, 1.0 / float(z["rls_beta"]))
+    assert rel_err(Wt.cpu().numpy(), z["rls_w"][-1]) < 2e-4
+    assert rel_err(P.cpu().numpy(), z["rls_p"][-1]) < 2e-4
+    assert rel_err(loss.cpu().numpy(), z["rls_loss"]) < 2e-4
+
+    import rectipy_b200 as rp
+    r = np.load(os.path.join(GOLDEN, "ridge.npz"))
+    net = rp.Network(float(r["dt"]), device="cuda:0")
+    net.add_diffeq_node("rnn", NODE, weights=r["W"], input_var="li_op/I_ext", output_var="li_op/v",
+                        source_var="tanh_op/r", target_var="li_op/r_in", node_vars={"li_op/tau": 1.0})
+    net.add_func_node("inp", r["w_in"].shape[1], "identity")
+    net.add_edge("inp", "rnn", weights=r["w_in"])
+    obs = net.fit_ridge(r["inputs"], r["targets"], sampling_steps=1, alpha=float(r["alpha"]), verbose=False,
+                        add_readout_node=False)
+    assert rel_err(obs.to_numpy("out"), r["X"]) < 1e-5
+    assert rel_err(obs["y"].cpu().numpy(), r["y"]) < 5e-3       # normal equations in fp32 vs fp64
+    assert obs["w_out"].shape == r["w_out"].shape
+
+
+def test_truncated_bptt_array_mode_runs():
+    """fit_bptt with array inputs (network.py:1016-1048): optimizer step + detach every update_steps."""
+    import rectipy_b200 as rp
+    rng = np.random.default_rng(2)
+    n, k, T = 20, 2, 300
+    net = rp.Network(1e-2, device="cuda:0")
+    net.add_diffeq_node("rnn", NODE, weights=rng.standard_normal((n, n)) / np.sqrt(n), input_var="li_op/I_ext",
+                        output_var="li_op/v", source_var="tanh_op/r", target_var="li_op/r_in", train_params=["weights"])
+    net.add_func_node("out", k, "identity")
+    net.add_edge("rnn", "out", train="gd")
+    w0 = net.get_node("rnn")["weights"].detach().clone()
+    obs = net.fit_bptt(rng.standard_normal((T, n)), rng.standard_normal((T, k)), optimizer="sgd", lr=1e-2,
+                       update_steps=50, sampling_steps=10, verbose=False)
+    assert len(obs["steps"]) == 30 and len(obs["loss"]) == 30
+    assert not torch.equal(w0, net.get_node("rnn")["weights"].detach())

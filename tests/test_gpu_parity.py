@@ -1,0 +1,218 @@
+"""GPU parity: the CUDA engine, driven through the drop-in API and the C ABI, against the golden fixtures minted from
+the unmodified reference and against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * rate-neuron trajectories and gradients: <= 1e-5 relative error (max-norm) vs the fp64 reference run;
+  * spiking networks: identical spike counts, spike times within one step; continuous quantities as close to the fp64
+    truth as the reference's own fp32 run (x10 slack), because threshold dynamics amplify fp32 rounding.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Case, RUN_CASES, engine_run_case, engine_net, oracle_net, rel_err, orc
+
+pytestmark = pytest.mark.gpu
+
+RATE_TOL = 1e-5
+
+
+def _bar(case, key, rate):
+    """Allowed relative error vs fp64 truth for result `key`."""
+    ref32 = rel_err(case.ref("float32", key), case.ref("float64", key))
+    if rate:
+        return max(RATE_TOL, 3.0 * ref32)
+    return max(2e-5, 10.0 * ref32)
+
+
+@pytest.mark.parametrize("name", RUN_CASES)
+def test_engine_matches_reference_fixture(name):
+    case = Case(name)
+    res = engine_run_case(case, precision="fp32")
+    rate = case.meta["model"] in ("li_tanh", "li_sigmoid")
+    assert np.array_equal(res["steps"], case.ref("float64", "steps"))
+    report = {}
+    for key, val in res.items():
+        if key == "steps":
+            continue
+        ref = case.ref("float64", key)
+        assert val.shape == ref.shape, (key, val.shape, ref.shape)
+        err, bar = rel_err(val, ref), _bar(case, key, rate)
+        report[key] = (err, bar)
+    print(name, {k: f"{e:.2e}/{b:.1e}" for k, (e, b) in report.items()})
+    bad = {k: v for k, v in report.items() if not v[0] <= v[1]}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("model,n,B,m,k", [("li_tanh", 37, 3, 2, 2), ("qif", 50, 5, 3, 1), ("qif_sfa", 64, 20, 2, 3),
+                                            ("lif", 33, 2, 1, 2), ("li_sigmoid", 130, 17, 4, 8)])
+def test_batched_trials_match_per_trial_oracle(model, n, B, m, k):
+    """The trial axis is an engine extension: every trial must equal the unbatched reference path run on its own."""
+    import rectipy_b200 as rp
+    from golden_util import TEMPLATE_PATH
+    rng = np.random.default_rng(hash((model, n, B)) % 2**31)
+    dt, T, S = (1e-2, 120, 3) if model.startswith("li") else (1e-3, 400, 4)
+    W = rng.standard_normal((n, n)) * (1.5 if model.startswith("li") else 2.0) / np.sqrt(n)
+    w_in, w_out = rng.standard_normal((n, m)), rng.standard_normal((k, n)) / np.sqrt(n)
+    params = {"li_tanh": dict(tau=rng.uniform(1, 2, n), k=1.2, eta=0.1),
+              "li_sigmoid": dict(tau=2.0, k=rng.uniform(0.5, 1.5, n), eta=0.0, r_max=1.5, s=2.0, v0=0.1),
+              "qif": dict(eta=orc.lorentzian_etas(n), k=1.5, tau_s=0.7),
+              "qif_sfa": dict(eta=orc.lorentzian_etas(n, eta=0.0), alpha=0.4, tau_x=1.2),
+              "lif": dict(eta=10.0, tau=rng.uniform(10, 20, n), tau_s=5.0, k=2.0)}[model]
+    spike_kwargs = dict(spike_threshold=10.0, spike_reset=-10.0) if model == "lif" else {}
+    amp, off = (1.5, 0.0) if model.startswith("li") else ((40.0, 0.0) if model == "lif" else (10.0, 14.0))
+    t = np.arange(T) * dt
+    x = amp * np.sin(2 * np.pi * rng.uniform(0.5, 3, (1, B, m)) * t[:, None, None] * (50 if model == "lif" else 1) +
+                     rng.uniform(0, 6.28, (1, B, m))) + off
+    targets = rng.standard_normal((len(range(0, T, S)), B, k))
+    train = ["weights", "eta", "tau"]
+
+    # engine, all trials at once
+    path, op, svar, tvar = TEMPLATE_PATH[model]
+    net = rp.Network(dt, device="cuda:0", batch=B, precision="fp32")
+    sig = {"r_max", "s", "v0"}
+    node_vars = {(f"sigmoid_op/{p}" if p in sig and model == "li_sigmoid" else f"{op}/{p}"): v for p, v in params.items()}
+    kw = dict(weights=W, source_var=svar, target_var=tvar, input_var=f"{op}/I_ext", node_vars=node_vars,
+              train_params=["weights", f"{op}/eta", f"{op}/tau"])
+    if model in orc.SPIKING:
+        kw.update(spike_var=f"{op}/spike", reset_var=f"{op}/v", output_var=f"{op}/s", **spike_kwargs)
+    else:
+        kw.update(output_var=f"{op}/v")
+    node = net.add_diffeq_node("rnn", path, **kw)
+    net.add_func_node("inp", m, "identity"); net.add_edge("inp", "rnn", weights=w_in, train="gd")
+    net.add_func_node("out", k, "identity"); net.add_edge("rnn", "out", weights=w_out, train="gd")
+    obs = net.run(x, sampling_steps=S, verbose=False, enable_grad=True)
+    out = torch.stack(obs["out"])
+    assert out.shape == (len(range(0, T, S)), B, k)
+    loss = torch.nn.functional.mse_loss(out, torch.tensor(targets, dtype=torch.float32, device="cuda:0"))
+    loss.backward()
+
+    # oracle, one trial at a time in fp64; gradients of the mean loss add over trials
+    g_ref = None
+    out_ref = np.zeros(out.shape)
+    for b in range(B):
+        onode = orc.make_node(model, n, W, dt, params=params, dtype=torch.float64, train_params=train, **spike_kwargs)
+        onet = orc.OracleNet(onode, w_in=torch.tensor(w_in, requires_grad=True), w_out=torch.tensor(w_out, requires_grad=True))
+        r = onet.run(torch.tensor(x[:, b, :]), sampling_steps=S, enable_grad=True)
+        pred = torch.stack(r["out"])
+        out_ref[:, b, :] = pred.detach().numpy()
+        lb = torch.nn.functional.mse_loss(pred, torch.tensor(targets[:, b, :]), reduction="sum") / out.numel()
+        lb.backward()
+        gs = [p.grad.numpy().copy() for p in onet.parameters()]
+        g_ref = gs if g_ref is None else [a + c for a, c in zip(g_ref, gs)]
+    rate = model.startswith("li")
+    tol = RATE_TOL if rate else 1e-4
+    assert rel_err(out.detach().cpu().numpy(), out_ref) <= tol
+    g_eng = [node["weights"].grad, node[f"{op}/eta"].grad, node[f"{op}/tau"].grad,
+             net.get_edge("inp", "rnn").weights.grad, net.get_edge("rnn", "out").weights.grad]
+    names = ["weights", "eta", "tau", "w_in", "w_out"]
+    errs = {nm: rel_err(ge.detach().cpu().numpy().reshape(gr.shape), gr) for nm, ge, gr in zip(names, g_eng, g_ref)}
+    print(model, errs)
+    assert all(e <= (RATE_TOL if rate else 2e-3) for e in errs.values()), errs
+
+
+def test_spike_raster_parity_config1_style():
+    """QIF-SFA forward run in the regime of documentation/qif_example.py (scaled): spike counts identical and spike
+    times within one step of the fp32 CPU oracle over the stated horizon of 4000 steps."""
+    import rectipy_b200 as rp
+    n, T, dt = 256, 4000, 1e-3
+    rng = np.random.default_rng(5)
+    np.random.seed(5)
+    W = rp.random_connectivity(n, n, 0.2, normalize=True)
+    etas = orc.lorentzian_etas(n)
+    inp = np.zeros((T, 1)); inp[1000:3000, 0] = 3.0
+    w_in = np.ones((n, 1))
+    params = dict(eta=etas, k=15.0, alpha=0.3, tau_x=2.0)
+    net = rp.Network(dt, device="cuda:0", precision="fp32")
+    net.add_diffeq_node("qif", "neuron_model_templates.spiking_neurons.qif.qif_sfa", weights=W, source_var="s",
+                        target_var="s_in", input_var="I_ext", output_var="s", spike_var="spike", reset_var="v",
+                        op="qif_sfa_op", node_vars={"eta": etas, "k": 15.0, "alpha": 0.3, "tau_x": 2.0})
+    net.add_func_node("inp", 1, "identity"); net.add_edge("inp", "qif", weights=w_in)
+    obs = net.run(inp, sampling_steps=1, verbose=False, enable_grad=False, record_output=False,
+                  record_vars=[("qif", "v", False)])
+    v_eng = obs.to_numpy(("qif", "v"))
+    onode = orc.make_node("qif_sfa", n, W, dt, params=params, dtype=torch.float32)
+    onet = orc.OracleNet(onode, w_in=torch.tensor(w_in, dtype=torch.float32))
+    r = onet.run(torch.tensor(inp, dtype=torch.float32), sampling_steps=1, record_vars=[("v", False)], enable_grad=False)
+    v_ref = torch.stack(r["vars"]["v"]).numpy()
+    cmp_ = orc.compare_spikes(orc.spike_raster(v_ref, 100.0), orc.spike_raster(v_eng, 100.0))
+    print(cmp_)
+    assert cmp_["total_ref"] > 200
+    assert cmp_["neurons_count_mismatch"] == 0 and cmp_["unmatched"] == 0 and cmp_["max_shift"] <= 1
+
+
+@pytest.mark.parametrize("P,Q,K", [(128, 128, 32), (256, 512, 1024), (37, 5, 19), (130, 70, 257), (1000, 1, 1000), (64, 16, 64)])
+def test_fp32_contraction_kernels(P, Q, K):
+    from rectipy_b200 import engine
+    g = torch.Generator(device="cuda").manual_seed(P * 7 + Q)
+    A = torch.randn(P, K, device="cuda", generator=g)
+    B = torch.randn(Q, K, device="cuda", generator=g)
+    C = engine.gemm_tn(A, B)
+    ref = (B.double() @ A.double().T)
+    assert rel_err(C.cpu().numpy(), ref.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("P,Q,K", [(128, 128, 32), (128, 256, 64), (256, 128, 96), (512, 1024, 2048), (384, 384, 500)])
+def test_tcgen05_3xtf32_contraction(P, Q, K):
+    """tcgen05 3xTF32 kernel vs fp64 matmul: error must be at fp32 level (single-pass TF32 would be ~1e-3)."""
+    from rectipy_b200 import engine, _cabi
+    g = torch.Generator(device="cuda").manual_seed(P + Q + K)
+    A = torch.randn(P, K, device="cuda", generator=g)
+    B = torch.randn(Q, K, device="cuda", generator=g)
+    C = engine.gemm_tn(A, B, precision=_cabi.RP_PREC_3XTF32)
+    torch.cuda.synchronize()
+    ref = (B.double() @ A.double().T)
+    err = rel_err(C.cpu().numpy(), ref.cpu().numpy())
+    fp32_err = rel_err((B @ A.T).cpu().numpy(), ref.cpu().numpy())
+    print(f"3xTF32 rel err {err:.2e}  (torch fp32 matmul {fp32_err:.2e})")
+    assert err < 5e-6
+    C2 = engine.gemm_tn(A, B, precision=_cabi.RP_PREC_3XTF32, out=C.clone(), accumulate=True)
+    assert rel_err(C2.cpu().numpy(), 2 * ref.cpu().numpy()) < 5e-6
+
+
+@pytest.mark.parametrize("model", ["li_tanh", "qif"])
+def test_tensor_core_path_matches_fp32_path(model):
+    """N=256, B=256: the 3xTF32 engine path vs the FFMA path vs the oracle (sample of trials)."""
+    import rectipy_b200 as rp
+    from golden_util import TEMPLATE_PATH
+    n, B, m, k = 256, 256, 2, 3
+    rng = np.random.default_rng(11)
+    dt, T, S = (1e-2, 60, 2) if model == "li_tanh" else (1e-3, 300, 2)
+    W = rng.standard_normal((n, n)) * (1.5 if model == "li_tanh" else 2.0) / np.sqrt(n)
+    w_in, w_out = rng.standard_normal((n, m)), rng.standard_normal((k, n)) / np.sqrt(n)
+    params = dict(tau=rng.uniform(1, 2, n), k=1.2, eta=0.1) if model == "li_tanh" else dict(eta=orc.lorentzian_etas(n), k=1.5, tau_s=0.7)
+    t = np.arange(T) * dt
+    amp, off = (1.5, 0.0) if model == "li_tanh" else (10.0, 14.0)
+    x = amp * np.sin(2 * np.pi * rng.uniform(0.5, 3, (1, B, m)) * t[:, None, None] + rng.uniform(0, 6.28, (1, B, m))) + off
+    targets = torch.tensor(rng.standard_normal((len(range(0, T, S)), B, k)), dtype=torch.float32, device="cuda")
+    path, op, svar, tvar = TEMPLATE_PATH[model]
+    results = {}
+    for prec in ("fp32", "3xtf32"):
+        net = rp.Network(dt, device="cuda:0", batch=B, precision=prec)
+        kw = dict(weights=W, source_var=svar, target_var=tvar, input_var=f"{op}/I_ext",
+                  node_vars={f"{op}/{p}": v for p, v in params.items()}, train_params=["weights", f"{op}/eta"])
+        if model == "qif":
+            kw.update(spike_var=f"{op}/spike", reset_var=f"{op}/v", output_var=f"{op}/s")
+        else:
+            kw.update(output_var=f"{op}/v")
+        node = net.add_diffeq_node("rnn", path, **kw)
+        net.add_func_node("inp", m, "identity"); net.add_edge("inp", "rnn", weights=w_in, train="gd")
+        net.add_func_node("out", k, "identity"); net.add_edge("rnn", "out", weights=w_out, train="gd")
+        obs = net.run(x, sampling_steps=S, verbose=False, enable_grad=True)
+        out = torch.stack(obs["out"])
+        torch.nn.functional.mse_loss(out, targets).backward()
+        results[prec] = dict(out=out.detach().cpu().numpy(), gW=node["weights"].grad.cpu().numpy(),
+                             geta=node[f"{op}/eta"].grad.cpu().numpy(),
+                             gin=net.get_edge("inp", "rnn").weights.grad.cpu().numpy(),
+                             gout=net.get_edge("rnn", "out").weights.grad.cpu().numpy(), y=node.y.detach().cpu().numpy())
+    errs = {key: rel_err(results["3xtf32"][key], results["fp32"][key]) for key in results["fp32"]}
+    print(model, errs)
+    tol = 1e-5 if model == "li_tanh" else 1e-3
+    assert all(e <= tol for e in errs.values()), errs
+    # and against the oracle for two trials
+    for b in (0, B - 1):
+        onode = orc.make_node(model, n, W, dt, params=params, dtype=torch.float64)
+        onet = orc.OracleNet(onode, w_in=torch.tensor(w_in), w_out=torch.tensor(w_out))
+        r = onet.run(torch.tensor(x[:, b, :]), sampling_steps=S, enable_grad=False)
+        ref = torch.stack(r["out"]).numpy()
+        assert rel_err(results["3xtf32"]["out"][:, b, :], ref) <= (1e-5 if model == "li_tanh" else 1e-4)
