@@ -9,8 +9,9 @@
 // Kernel shape: one CTA per 128(p) x BQ(q) tile, 6 warps:
 //   warp 0   TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B boxes of 32 fp32 = 128 B rows)
 //   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (12 MMAs of K=8 per 32-wide K block)
-//   warps 2-5 epilogue      (tcgen05.ld 32x32b -> registers -> coalesced global stores, p fastest)
-// smem ring of full/empty mbarriers between producer and issuer; tcgen05.commit releases stages and signals the epilogue.
+//   warps 2-9 epilogue      (tcgen05.ld 32x32b -> fp32 register accumulators -> coalesced global stores, p fastest)
+// smem ring of full/empty mbarriers between producer and issuer; two TMEM accumulator buffers ping-pong between the
+// issuer and the epilogue (tcgen05.commit signals "chunk done", the epilogue's mbarrier.arrive signals "buffer drained").
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -27,7 +28,6 @@ inline const char* tc_last_error() { return tc_err_buf(); }
 constexpr int TC_BP = 128;          // tile rows (UMMA M, TMEM lanes)
 constexpr int TC_BK = 32;           // fp32 elements per K block = one 128-byte swizzle row
 constexpr int TC_UMMA_K = 8;        // tf32 MMA K
-constexpr int TC_THREADS = 192;
 
 enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
 
@@ -110,13 +110,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr));
 }
 
+// The tensor core adds into its fp32 accumulator with truncation (measured on B200: all-positive operands give a
+// systematic -2.3e-5 relative bias at K=2048, growing linearly with K).  To stay at fp32 accuracy the K loop is cut into
+// chunks of TC_KC K-blocks; each chunk accumulates into one of two TMEM buffers from zero and the epilogue warps add the
+// finished chunk into fp32 registers with round-to-nearest while the next chunk is being multiplied.
+constexpr int TC_KC = 4;            // K blocks (of 32) per TMEM accumulation chunk
+constexpr int TC_EPI_WARPS = 8;     // two warps per TMEM lane quadrant, each owning half of the tile's columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+
 template <int BQ> struct TcCfg {
     static constexpr int STAGES = (BQ == 256) ? 2 : 3;
     static constexpr int A_BYTES = TC_BP * 128;
     static constexpr int B_BYTES = BQ * 128;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BQ;
+    static constexpr int COLS_PER_THREAD = BQ / 2;
 };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 template <int BQ>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -125,25 +139,27 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
               float* __restrict__ C, int ldc, int num_k_blocks, int accumulate) {
     using Cfg = TcCfg<BQ>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int CPT = Cfg::COLS_PER_THREAD;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p0 = blockIdx.x * TC_BP, q0 = blockIdx.y * BQ;
+    const int num_chunks = (num_k_blocks + TC_KC - 1) / TC_KC;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        // allocate BQ TMEM columns (power of two >= 32) for the fp32 accumulator tile
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BQ) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -171,9 +187,17 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
         constexpr uint32_t idesc = make_tf32_idesc(TC_BP, BQ);
         int stage = 0; uint32_t phase = 0;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
+            const int chunk = kb / TC_KC, kin = kb - chunk * TC_KC;
+            const int buf = chunk & 1;
+            if (kin == 0) {
+                // the epilogue must have drained this buffer (chunk-2) before it is overwritten
+                mbar_wait(&tmem_empty_bar[buf], ((chunk >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
             mbar_wait(&full_bar[stage], phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BQ);
                 const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                 const uint64_t dA_hi = make_sw128_kmajor_desc(sa);
                 const uint64_t dA_lo = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
@@ -183,47 +207,54 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
                 for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
                     const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);     // 32 bytes per K=8 step, encoded >>4
                     // small cross terms first, leading term last
-                    umma_tf32(tmem_base, dA_lo + adv, dB_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_tf32(tmem_base, dA_hi + adv, dB_lo + adv, idesc, 1u);
-                    umma_tf32(tmem_base, dA_hi + adv, dB_hi + adv, idesc, 1u);
+                    umma_tf32(tmem_d, dA_lo + adv, dB_hi + adv, idesc, (kin > 0 || k > 0) ? 1u : 0u);
+                    umma_tf32(tmem_d, dA_hi + adv, dB_lo + adv, idesc, 1u);
+                    umma_tf32(tmem_d, dA_hi + adv, dB_hi + adv, idesc, 1u);
                 }
                 umma_commit(&empty_bar[stage]);                       // frees the smem stage when these MMAs retire
-                if (kb == num_k_blocks - 1) umma_commit(tmem_full_bar);
+                if (kin == TC_KC - 1 || kb == num_k_blocks - 1) umma_commit(&tmem_full_bar[buf]);
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+        // ===== epilogue: warps 2..9; warp w owns TMEM lanes 32*(w%4).., columns [half*CPT, (half+1)*CPT) =====
+        const int ew = warp - 2;
         const int lane_base = (warp & 3) * 32;
+        const int half = ew >> 2;
         const int p = p0 + lane_base + lane;
-        if (num_k_blocks > 0) {
-            mbar_wait(tmem_full_bar, 0);
+        float acc[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+        for (int chunk = 0; chunk < num_chunks; ++chunk) {
+            const int buf = chunk & 1;
+            mbar_wait(&tmem_full_bar[buf], (chunk >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-#pragma unroll 1
-        for (int c = 0; c < BQ / 32; ++c) {
-            uint32_t r[32];
-            if (num_k_blocks > 0) {
-                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(c * 32), r);
+            const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * BQ + half * CPT);
+#pragma unroll
+            for (int c = 0; c < CPT / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr + (uint32_t)(c * 32), r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
+                for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float* dst = C + (size_t)(q0 + c * 32 + j) * ldc + p;
-                float v = __uint_as_float(r[j]);
-                if (accumulate) v += *dst;
-                *dst = v;
-            }
+        for (int j = 0; j < CPT; ++j) {
+            float* dst = C + (size_t)(q0 + half * CPT + j) * ldc + p;
+            float v = acc[j];
+            if (accumulate) v += *dst;
+            *dst = v;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BQ) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -236,8 +267,11 @@ __global__ void __launch_bounds__(256) k_split_matrix(int rows, int cols, const 
         float h = 0.f, l = 0.f;
         if (r < rows && c < cols) {
             const float x = src[(size_t)r * ld + c];
-            h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-            l = __uint_as_float(__float_as_uint(x - h) & 0xffffe000u);
+            uint32_t uh, ul;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(uh) : "f"(x));
+            h = __uint_as_float(uh);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ul) : "f"(x - h));
+            l = __uint_as_float(ul);
         }
         hi[idx] = h; lo[idx] = l;
     }

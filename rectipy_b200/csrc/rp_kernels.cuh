@@ -54,9 +54,15 @@ __device__ __forceinline__ float rate_act_grad(const ModelParams& mp, int i, flo
 }
 
 // TF32 split used by the 3xTF32 tensor-core path: x ~= hi + lo with hi, lo exactly representable in tf32
+// (round-to-nearest on both parts: |x - hi - lo| <= 2^-24 |x|, and the dropped lo*lo product is <= 2^-24 relative)
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-    lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
+    hi = round_tf32(x);
+    lo = round_tf32(x - hi);
 }
 
 // ------------------------------------------------------------------------------------------------------

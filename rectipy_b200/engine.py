@@ -139,8 +139,8 @@ class EngineRun(torch.autograd.Function):
         B, N = key.batch, key.n
         nsv = lib.rp_num_state_vars(key.model)
         n_rec = lib.rp_num_records(cfg.T, cfg.sampling_steps, cfg.cutoff)
-        tensors = [t for t in (x, W, W_in, W_out, y0) + tuple(params) if t is not None]
-        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+        # grad mode is off inside Function.forward; needs_input_grad already accounts for no_grad() at apply time
+        needs_grad = any(ctx.needs_input_grad)
 
         x_c = None if x is None else _f32c(x)
         W_c, y0_c = _f32c(W), _f32c(y0)

@@ -120,7 +120,7 @@ def test_spike_raster_parity_config1_style():
     np.random.seed(5)
     W = rp.random_connectivity(n, n, 0.2, normalize=True)
     etas = orc.lorentzian_etas(n)
-    inp = np.zeros((T, 1)); inp[1000:3000, 0] = 3.0
+    inp = np.zeros((T, 1)); inp[500:3500, 0] = 6.0
     w_in = np.ones((n, 1))
     params = dict(eta=etas, k=15.0, alpha=0.3, tau_x=2.0)
     net = rp.Network(dt, device="cuda:0", precision="fp32")
@@ -165,7 +165,7 @@ def test_tcgen05_3xtf32_contraction(P, Q, K):
     err = rel_err(C.cpu().numpy(), ref.cpu().numpy())
     fp32_err = rel_err((B @ A.T).cpu().numpy(), ref.cpu().numpy())
     print(f"3xTF32 rel err {err:.2e}  (torch fp32 matmul {fp32_err:.2e})")
-    assert err < 5e-6
+    assert err < max(3e-6, 2.0 * fp32_err)     # chunked fp32 re-accumulation keeps the tcgen05 path at FFMA accuracy
     C2 = engine.gemm_tn(A, B, precision=_cabi.RP_PREC_3XTF32, out=C.clone(), accumulate=True)
     assert rel_err(C2.cpu().numpy(), 2 * ref.cpu().numpy()) < 5e-6
 
