@@ -128,6 +128,12 @@ int rp_backward(rp_plan* plan, const rp_bwd_args* args, void* stream);
 int rp_rls_run(int T, int n_in, int n_out, float beta_inv, const float* X, const float* Y,
                float* W, float* P, float* loss, float* pred, int update_every, void* stream);
 
+/* Profiling hook: launch the plan's dominant contraction (0: forward W.src, 1: adjoint W^T.g, 2: weight gradient over a
+ * full K chunk) `iters` times back to back on `stream`, bracketed by CUDA events; *avg_ms receives the mean launch
+ * duration, *flops the algorithmic (logical, not x3) flop count of one launch.  Operands are whatever the plan's
+ * workspaces currently hold (timing is data independent).  Synchronises the stream. */
+int rp_plan_time_contraction(rp_plan* plan, int which, int iters, float* avg_ms, double* flops, void* stream);
+
 /* Standalone GEMM used by the engine, exposed for testing:  C[q*ldc+p] (+)= sum_k A[p*lda+k]*B[q*ldb+k]
  * precision RP_PREC_FP32 -> FFMA kernel, RP_PREC_3XTF32 -> tcgen05 kernel (needs p,q,k extents it supports). */
 int rp_gemm_tn(int precision, int P, int Q, int K, const float* A, int lda, const float* B, int ldb,

@@ -48,7 +48,7 @@ class rp_bwd_args(C.Structure):
 #: every symbol include/rectipy_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = ["rp_abi_version", "rp_last_error", "rp_num_state_vars", "rp_num_records", "rp_plan_create",
            "rp_plan_destroy", "rp_plan_workspace_bytes", "rp_plan_launch_count", "rp_forward", "rp_backward",
-           "rp_rls_run", "rp_gemm_tn"]
+           "rp_rls_run", "rp_gemm_tn", "rp_plan_time_contraction"]
 
 _LIB = None
 
@@ -87,6 +87,8 @@ def load():
     lib.rp_backward.restype = C.c_int
     lib.rp_rls_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_void_p]
     lib.rp_rls_run.restype = C.c_int
+    lib.rp_plan_time_contraction.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]
+    lib.rp_plan_time_contraction.restype = C.c_int
     lib.rp_gemm_tn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_void_p]
     lib.rp_gemm_tn.restype = C.c_int
     if lib.rp_abi_version() != RP_ABI_VERSION:

@@ -470,6 +470,48 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     return 0;
 }
 
+int rp_plan_time_contraction(rp_plan* p, int which, int iters, float* avg_ms, double* flops, void* stream) {
+    if (!p || !avg_ms || !flops || iters <= 0 || which < 0 || which > 2) return fail("rp_plan_time_contraction: bad argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int N = p->d.n, B = p->d.batch;
+    const size_t plane = (size_t)B * N;
+    long long scratch_launches = 0;
+    int kext = B;
+    if (which == 2) {
+        if (!p->dWraw) { if (plan_alloc(p, &p->dWraw, (size_t)N * p->ldw)) return 1; RP_CUDA(cudaMemsetAsync(p->dWraw, 0, (size_t)N * p->ldw * sizeof(float), st)); }
+        if (p->use_tc) {
+            size_t bytes = 0;
+            if (rp::tc_workspace_ensure_wgrad(&p->tc, &bytes)) return fail("rp_plan_time_contraction: %s", rp::tc_last_error());
+            p->ws_bytes += bytes;
+            kext = p->tc.wgrad_chunk * B;
+        }
+    }
+    if (!p->use_tc && !p->src) { if (plan_alloc(p, &p->src, plane)) return 1; RP_CUDA(cudaMemsetAsync(p->src, 0, plane * sizeof(float), st)); }
+    auto launch = [&]() -> int {
+        if (p->use_tc) {
+            if (which == 2) return rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, kext, 1, st);
+            return rp::tc_gemm(&p->tc, which == 0 ? rp::TC_FWD : rp::TC_DGRAD, p->u, p->ldu, 0, 0, st);
+        }
+        if (which == 2) return gemm_fp32(p, false, N, N, B, p->src, N, p->g, N, p->dWraw, p->ldw, 1, st, &scratch_launches);
+        return gemm_fp32(p, true, N, B, N, which == 0 ? p->Wk : p->WkT, p->ldw, which == 0 ? p->src : p->g, N, p->u, p->ldu, 0, st, &scratch_launches);
+    };
+    for (int i = 0; i < 2; ++i) if (launch()) return fail("rp_plan_time_contraction: %s", p->use_tc ? rp::tc_last_error() : g_err);
+    cudaEvent_t e0, e1;
+    RP_CUDA(cudaEventCreate(&e0));
+    RP_CUDA(cudaEventCreate(&e1));
+    RP_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) if (launch()) return fail("rp_plan_time_contraction: launch failed");
+    RP_CUDA(cudaEventRecord(e1, st));
+    RP_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    RP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *avg_ms = ms / (float)iters;
+    *flops = which == 2 ? 2.0 * N * (double)N * kext : 2.0 * N * (double)N * B;
+    return 0;
+}
+
 int rp_gemm_tn(int precision, int P, int Q, int K, const float* A, int lda, const float* B, int ldb,
                float* C, int ldc, int accumulate, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

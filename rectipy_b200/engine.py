@@ -83,6 +83,14 @@ class Plan:
     def launches(self) -> int:
         return int(self.lib.rp_plan_launch_count(self.handle))
 
+    def time_contraction(self, which: int, iters: int = 20):
+        """(avg launch ms, algorithmic flops per launch) of the plan's contraction kernel: 0 fwd, 1 adjoint, 2 wgrad."""
+        ms, fl = C.c_float(), C.c_double()
+        with torch.cuda.device(self.key.device):
+            abi.check(self.lib.rp_plan_time_contraction(self.handle, which, iters, C.byref(ms), C.byref(fl), _stream()),
+                      "rp_plan_time_contraction")
+        return float(ms.value), float(fl.value)
+
     @property
     def workspace_bytes(self) -> int:
         return int(self.lib.rp_plan_workspace_bytes(self.handle))

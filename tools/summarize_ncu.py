@@ -1,0 +1,71 @@
+"""Turn ncu outputs brought back in gpurun_out/ into the small tracked summaries under profiles/.
+
+  python tools/summarize_ncu.py launches gpurun_out/launches_r1.csv profiles/r1_launches.md "<command>"
+  python tools/summarize_ncu.py full     gpurun_out/prof_gemm_r1.ncu-rep profiles/r1_gemm_full.md
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+
+def launches(src, dst, cmd):
+    lines = [l for l in open(src) if not l.startswith("==")]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    seq = []
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "")
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row["Metric Unit"]
+        us = v / 1000 if unit.startswith("n") else (v if unit.startswith("u") else v * 1000)
+        agg[name][0] += 1
+        agg[name][1] += us
+        seq.append((name, us))
+    tot = sum(v[1] for v in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)\n\n")
+        f.write(f"command: `{cmd}`\n\ncaptured launches: {len(seq)}, total {tot:.1f} us\n\n")
+        f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k[:90]}` | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.1f} | {100 * v[1] / tot:.1f}% |\n")
+        f.write("\nfirst 60 launches in order (name, us):\n\n```\n")
+        for n, u in seq[:60]:
+            f.write(f"{n[:60]:60s} {u:9.1f}\n")
+        f.write("```\n")
+    print("wrote", dst)
+
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "launch__shared_mem_per_block_dynamic", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "lts__t_bytes.sum", "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"]
+
+
+def full(src, dst):
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full --clock-control none ({src.split('/')[-1]}), one column per captured launch\n\n")
+        names = [re.sub(r"\(.*", "", r[idx["Kernel Name"]]) for r in rows[2:]]
+        f.write("| metric | unit | " + " | ".join(f"#{i} {n[:40]}" for i, n in enumerate(names)) + " |\n")
+        f.write("|---|---|" + "---:|" * len(names) + "\n")
+        for w in WANT:
+            if w in idx:
+                f.write(f"| {w} | {units[idx[w]]} | " + " | ".join(r[idx[w]] for r in rows[2:]) + " |\n")
+    print("wrote", dst)
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+    else:
+        full(sys.argv[2], sys.argv[3])
