@@ -1,0 +1,217 @@
+"""CPU tests of the host logic (no compute): template front-end, graph construction/compile rules, error types,
+Observer, utilities.  Mirrors the structural parts of rectipy_tests/test_network.py and test_edges.py."""
+import numpy as np
+import pytest
+import torch
+
+import rectipy_b200 as rp
+from rectipy_b200 import templates, _cabi as abi
+from rectipy_b200.network import _window_mean, _record_steps
+from golden_util import orc
+
+QIF = "neuron_model_templates.spiking_neurons.qif.qif"
+TANH = "neuron_model_templates.rate_neurons.leaky_integrator.tanh"
+
+
+def test_builtin_templates_resolve():
+    for path, name, nsv, model in [(TANH, "li_tanh", 1, abi.RP_LI_TANH),
+                                   ("neuron_model_templates.rate_neurons.leaky_integrator.sigmoid", "li_sigmoid", 1, abi.RP_LI_SIGMOID),
+                                   (QIF, "qif", 2, abi.RP_QIF), (QIF + "_sfa", "qif_sfa", 3, abi.RP_QIF_SFA),
+                                   ("neuron_model_templates.spiking_neurons.lif.lif", "lif", 2, abi.RP_LIF)]:
+        spec = templates.resolve_template(path)
+        assert (spec.name, spec.n_sv, spec.model) == (name, nsv, model)
+    # defaults of the reference YAML files
+    spec = templates.resolve_template(QIF + "_sfa")
+    assert spec.params["qif_sfa_op/tau_x"][1] == 10.0 and spec.params["qif_sfa_op/eta"][1] == -5.0
+    assert dict(spec.state_vars)["qif_sfa_op/v"] == -2.0
+    assert templates.resolve_template("neuron_model_templates.spiking_neurons.lif.lif").params["lif_op/tau_s"][1] == 0.5
+    with pytest.raises(FileNotFoundError):
+        templates.resolve_template("neuron_model_templates.nowhere.nothing.tanh")
+    with pytest.raises(AttributeError):
+        templates.resolve_template("neuron_model_templates.spiking_neurons.qif.invalid")
+
+
+def test_user_yaml_template(tmp_path, monkeypatch):
+    """A user file in PyRates template syntax with `base:` inheritance and changed defaults is parsed and matched."""
+    (tmp_path / "mymodels").mkdir()
+    (tmp_path / "mymodels" / "custom.yaml").write_text(
+        "my_qif_op:\n  base: OperatorTemplate\n  equations:\n    - \"v' = (v^2 + eta + I_ext)/tau + k*s_in\"\n"
+        "    - \"s' = -s/tau_s + spike\"\n  variables:\n    s: output(0.0)\n    v: variable(-1.0)\n    tau: 2.0\n    k: 3.0\n"
+        "    tau_s: 0.5\n    eta: 1.5\n    I_ext: input(0.0)\n    spike: input(0.0)\n    s_in: input(0.0)\n"
+        "my_sfa_op:\n  base: my_qif_op\n  equations:\n    replace:\n      eta: eta - x\n    add:\n      - \"x' = -x/tau_x + alpha*spike\"\n"
+        "  variables:\n    x: variable(0.0)\n    alpha: 0.25\n    tau_x: 7.0\n"
+        "my_neuron:\n  base: NodeTemplate\n  operators:\n    - my_sfa_op\n"
+        "weird_op:\n  base: OperatorTemplate\n  equations: \"v' = -v^3\"\n  variables:\n    v: output(0.0)\n"
+        "weird:\n  base: NodeTemplate\n  operators:\n    - weird_op\n")
+    monkeypatch.chdir(tmp_path)
+    spec = templates.resolve_template("mymodels.custom.my_neuron")
+    assert spec.name == "qif_sfa" and spec.ops == ("my_sfa_op",)
+    assert spec.params["my_sfa_op/tau"][1] == 2.0 and spec.params["my_sfa_op/alpha"][1] == 0.25
+    assert dict(spec.state_vars)["my_sfa_op/v"] == -1.0
+    with pytest.raises(NotImplementedError):
+        templates.resolve_template("mymodels.custom.weird")
+
+
+def _qif_net(n=10, **kw):
+    net = rp.Network(1e-3, device="cpu")
+    node = net.add_diffeq_node("qif", QIF, weights=np.random.randn(n, n), source_var="s", target_var="s_in",
+                               input_var="I_ext", output_var="s", spike_var="spike", reset_var="v", op="qif_op", **kw)
+    return net, node
+
+
+def test_node_construction_and_protocol():
+    net, node = _qif_net(10, node_vars={"eta": np.linspace(-1, 1, 10), "tau": 2.0}, train_params=["weights", "eta"],
+                         spike_threshold=50.0, spike_reset=-50.0)
+    assert isinstance(node, rp.SpikeResetNet)
+    assert len(node.y) == 20 and node.n_in == 10 and node.n_out == 10          # test_nodes.py:70-71
+    assert node.slope == pytest.approx(1.0) and node.theta == 50.0 and node.v_reset == -50.0   # nodes.py:345-347
+    assert torch.allclose(node["v"], torch.full((10,), -2.0)) and torch.allclose(node["qif_op/s"], torch.zeros(10))
+    assert node["eta"].shape == (10,) and node["tau"].shape == (1,) and float(node["tau"]) == 2.0
+    assert len(list(node.parameters())) == 2 and all(p.requires_grad for p in node.parameters())
+    assert net.get_var("qif", "eta") is node["qif_op/eta"]
+    with pytest.raises(KeyError):
+        node["nonexistent"]
+    slots, tensors, per_neuron = node.param_slots()
+    assert per_neuron[abi.RP_P_ETA] == 1 and per_neuron[abi.RP_P_TAU] == 0
+    node.set_param("k", 3.0)
+    assert float(node["k"]) == 3.0
+    node.reset()
+    assert float(node.y.abs().sum()) == 0.0                                    # reset() -> zeros (nodes.py:199-200)
+    y = np.arange(20, dtype=np.float32)
+    node.reset(y)
+    assert torch.allclose(node["s"], torch.arange(10, 20, dtype=torch.float32))
+    rate = rp.Network(1e-2, device="cpu").add_diffeq_node("rnn", TANH, weights=np.zeros((4, 4)), input_var="li_op/I_ext",
+                                                          output_var="li_op/v", source_var="tanh_op/r", target_var="li_op/r_in")
+    assert isinstance(rate, rp.RateNet) and not isinstance(rate, rp.SpikeResetNet) and len(rate.y) == 4
+
+
+def test_add_diffeq_node_errors():
+    net = rp.Network(1e-3, device="cpu")
+    with pytest.raises(ValueError):        # spiking node without reset_var (network.py:293-295)
+        net.add_diffeq_node("a", QIF, weights=np.zeros((3, 3)), source_var="s", target_var="s_in", input_var="I_ext",
+                            output_var="s", spike_var="spike", op="qif_op")
+    with pytest.raises(ValueError):        # weights without source/target variable (nodes.py:247-249)
+        net.add_diffeq_node("b", QIF, weights=np.zeros((3, 3)), input_var="I_ext", output_var="s", op="qif_op")
+    with pytest.raises(NotImplementedError):   # reset=False selects the upstream-broken SpikeNet
+        net.add_diffeq_node("c", QIF, weights=np.zeros((3, 3)), source_var="s", target_var="s_in", input_var="I_ext",
+                            output_var="s", spike_var="spike", reset_var="v", reset=False, op="qif_op")
+    with pytest.raises(KeyError):
+        net.add_diffeq_node("d", QIF, weights=np.zeros((3, 3)), source_var="s", target_var="s_in", input_var="I_ext",
+                            output_var="s", spike_var="spike", reset_var="v", op="qif_op", node_vars={"bogus": 1.0})
+    with pytest.raises(FileNotFoundError):
+        net.add_diffeq_node("e", "no_such_pkg.file.tmpl", weights=np.zeros((3, 3)), source_var="s", target_var="s_in",
+                            input_var="I_ext", output_var="s")
+    with pytest.raises(ValueError):
+        net.add_func_node("f", 3, "not_an_activation")
+
+
+def test_edges_compile_and_parameters():
+    """rectipy_tests/test_network.py:108-290 structure: edge class selection, shapes, compile rules, parameter counts."""
+    net, node = _qif_net(10, train_params=["weights"])
+    net.add_func_node("inp", 3, "tanh")
+    e_in = net.add_edge("inp", "qif")
+    assert isinstance(e_in, rp.Linear) and e_in.weights.shape == (10, 3) and not e_in.weights.requires_grad   # test_network.py:179
+    net.add_func_node("out", 2, "softmax")
+    e_out = net.add_edge("qif", "out", weights=np.random.randn(10, 2), train="gd")    # transposed weights are accepted
+    assert e_out.weights.shape == (2, 10) and e_out.weights.requires_grad
+    net.compile()
+    assert net._in_node == "inp" and net._out_node == "out" and len(net._bwd_graph) == 2
+    assert net.n_in == 3 and net.n_out == 2
+    assert len(list(net.parameters())) == 2
+    chain = net._get_chain()
+    assert (chain.diffeq, chain.in_func, chain.out_func) == ("qif", "inp", "out")
+    with pytest.raises(ValueError):
+        net.add_edge("qif", "out", weights=np.random.randn(3, 3))
+    with pytest.raises(ValueError):
+        net.add_edge("qif", "out", train="invalid")
+    with pytest.raises(NotImplementedError):
+        net.add_edge("qif", "out", delays=np.ones(10))
+    masked = net.add_edge("inp", "qif", weights=np.ones((10, 3)), mask=np.eye(10, 3))
+    assert isinstance(masked, rp.LinearMasked) and float(masked.effective_weights().sum()) == 3.0
+    rls = net.add_edge("qif", "out", train="rls", alpha=2.0, beta=0.9)
+    assert isinstance(rls, rp.RLS) and float(rls.P[0, 0]) == 2.0 and net._train_edge == ("qif", "out")
+    # ambiguous input node -> ValueError (test_network.py:237-238)
+    net.add_func_node("inp2", 3, "identity")
+    net.add_edge("inp2", "qif")
+    with pytest.raises(ValueError):
+        net.compile()
+    net.pop_node("inp2")
+    net.compile()
+    # run on a CPU network must fail loudly, not fall back
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net.run(np.zeros((5, 3)), verbose=False)
+    # two diffeq nodes are not an engine chain
+    net2, _ = _qif_net(4)
+    net2.add_diffeq_node("qif2", QIF, weights=np.zeros((4, 4)), source_var="s", target_var="s_in", input_var="I_ext",
+                         output_var="s", spike_var="spike", reset_var="v", op="qif_op")
+    net2.add_edge("qif", "qif2")
+    net2.compile()
+    with pytest.raises(NotImplementedError):
+        net2._get_chain()
+
+
+def test_linear_edge_known_answer():
+    """rectipy_tests/test_edges.py:34-92: Linear == torch.nn.Linear (no bias), shape/dtype rules."""
+    w = np.random.randn(4, 9)
+    lin = rp.Linear(9, 4, weights=w, dtype=torch.float64)
+    ref = torch.nn.Linear(9, 4, bias=False, dtype=torch.float64)
+    with torch.no_grad():
+        ref.weight.copy_(torch.tensor(w))
+    x = torch.randn(9, dtype=torch.float64)
+    assert torch.allclose(lin.forward(x), ref(x), atol=1e-12)
+    assert rp.Linear(9, 4, weights=w.T).weights.shape == (4, 9)
+    assert len(list(rp.Linear(9, 4, detach=False).parameters())) == 1 and len(list(rp.Linear(9, 4).parameters())) == 0
+    with pytest.raises(ValueError):
+        rp.Linear(9, 4, weights=np.zeros((5, 5)))
+    with pytest.raises(RuntimeError):
+        lin.forward(torch.randn(8, dtype=torch.float64))
+    with pytest.raises(ValueError):
+        rp.RLS(3, 2, beta=1.5)
+    rls, orls = rp.RLS(5, 2, dtype=torch.float64, beta=0.95, alpha=1.5), orc.OracleRLS(5, 2, beta=0.95, alpha=1.5)
+    for _ in range(10):
+        xx, yy = torch.randn(5, dtype=torch.float64), torch.randn(2, dtype=torch.float64)
+        rls.update(xx, yy, rls.forward(xx)); orls.update(xx, yy, orls.forward(xx))
+    assert torch.allclose(rls.weights, orls.weights, atol=1e-12) and torch.allclose(rls.P, orls.P, atol=1e-12)
+
+
+@pytest.mark.parametrize("T,S,cutoff", [(100, 1, 0), (100, 2, 0), (600, 5, 7), (50, 4, 49), (20, 7, 3), (10, 3, 12)])
+def test_window_mean_matches_reference_loop(T, S, cutoff):
+    """Host-side windowing (used for non-linear output nodes) == the loop of Network.run (network.py:588-597)."""
+    o = torch.randn(T, 2, 3, dtype=torch.float64)
+    ref, buf = [], []
+    for step in range(T):
+        if step >= cutoff:
+            buf.append(o[step])
+            if step % S == 0:
+                ref.append(torch.mean(torch.stack(buf, 0), 0)); buf = []
+    got = _window_mean(o, S, cutoff)
+    assert got.shape[0] == len(ref) == len(_record_steps(T, S, cutoff)) == abi.load().rp_num_records(T, S, cutoff)
+    if ref:
+        assert torch.allclose(got, torch.stack(ref), atol=1e-12)
+
+
+def test_observer_block_recording():
+    obs = rp.Observer(1e-2, record_output=True, record_loss=True, record_vars=[("rnn", "v", False), ("rnn", "s", True)])
+    assert obs.recorded_state_variables == [("rnn", "v"), ("rnn", "s")] and obs.reduce_flags == [False, True]
+    obs.record_block([0, 2, 4], torch.arange(6.).reshape(3, 2), 0.5, [torch.ones(3, 4), torch.zeros(3)])
+    assert len(obs["out"]) == 3 and torch.stack(obs["out"]).shape == (3, 2) and obs["steps"] == [0, 2, 4]
+    assert obs.to_numpy(("rnn", "v")).shape == (3, 4) and obs.to_numpy("loss").tolist() == [0.5, 0.5, 0.5]
+    assert obs.to_dataframe("out").shape == (3, 2)
+    obs.record(6, torch.zeros(2), 0.1, [torch.ones(4), torch.ones(4)])
+    assert len(obs["out"]) == 4 and float(obs[("rnn", "s")][-1]) == 1.0
+    obs.save("w", 3)
+    assert obs["w"] == 3
+
+
+def test_utilities():
+    np.random.seed(0)
+    C = rp.random_connectivity(20, 30, 0.2, normalize=True)
+    assert C.shape == (20, 30) and np.allclose(C.sum(1), 1.0) and ((C > 0).sum(1) == 6).all()
+    assert rp.normalize(np.array([1.0, 3.0, 5.0])).tolist() == [0.0, 0.5, 1.0]
+    assert rp.wta_score(np.eye(3), np.eye(3)) == 1.0
+    from scipy.stats import rv_discrete
+    dist = rv_discrete(values=([1, 2, 3], [0.5, 0.3, 0.2]))
+    Cc = rp.circular_connectivity(12, 0.5, dist)
+    assert Cc.shape == (12, 12) and np.allclose(Cc.sum(1), 1.0)
+    W = rp.input_connections(10, 8, 0.5, variance=2.0, zero_mean=True)
+    assert W.shape == (10, 8) and np.allclose(W.sum(1), 0.0, atol=1e-12)
