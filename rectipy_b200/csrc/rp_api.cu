@@ -13,6 +13,8 @@
 #include "rp_gemm_simt.cuh"
 #include "rp_gemm_tc.cuh"
 #include "rp_rls.cuh"
+#include "rp_persistent.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -71,6 +73,13 @@ struct rp_plan {
     float* win_acc = nullptr;// [B][N]
     float* pp = nullptr;     // [2][nsv][B][N] ping-pong state when no history is kept
     float* dWraw = nullptr;  // [N][ldw]
+    // persistent few-trial path (rp_persistent.cuh)
+    bool persistent = false;
+    int ps_rows = 0, ps_grid = 0, ps_npad = 0;
+    int ps_fwd_wres = 0, ps_bwd_wres = 0, ps_bwd_dwres = 0;
+    size_t ps_fwd_smem = 0, ps_bwd_smem = 0;
+    float* ps_vec = nullptr;        // [2][B][Npad] x {value, tag}: flag-in-data exchange buffer (r_t forward, g_t backward)
+    unsigned int* ps_bar = nullptr;
     // 3xTF32 operand buffers (leading dims padded to the TMA box)
     rp::TcWorkspace tc;
 };
@@ -172,6 +181,123 @@ Window window_of(int t, int T, int S, int cutoff) {
     return w;
 }
 
+template <typename K>
+int ps_prepare_kernel(K kernel, size_t smem, int grid, const char* what) {
+    RP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, rp::PS_THREADS, smem));
+    int dev = 0, sms = 0;
+    RP_CUDA(cudaGetDevice(&dev));
+    RP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (occ < 1 || grid > occ * sms) return fail("%s: persistent grid of %d CTAs is not co-resident (occupancy %d x %d SMs)", what, grid, occ, sms);
+    return 0;
+}
+
+// geometry of the persistent few-trial kernels; leaves p->persistent false when the shape does not fit
+int persistent_setup(rp_plan* p, const cudaDeviceProp& prop) {
+    const int N = p->d.n, B = p->d.batch;
+    int coop = 0, dev = 0;
+    RP_CUDA(cudaGetDevice(&dev));
+    RP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) return 0;
+    int rows = (N + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
+    rows = std::max(8, round_up(rows, 8));
+    if (rows > rp::PS_MAX_ROWS || rows * B > rp::PS_THREADS) return 0;
+    p->ps_rows = rows;
+    p->ps_grid = (N + rows - 1) / rows;
+    p->ps_npad = round_up(N, 4);
+    const size_t budget = std::min<size_t>(prop.sharedMemPerBlockOptin, 200 * 1024);
+    const size_t wbytes = (size_t)rows * p->ldw * sizeof(float);
+    const size_t base_f = ((size_t)B * p->ps_npad + rp::PS_MAX_ROWS * rp::PS_MAX_B + 64) * sizeof(float);
+    const size_t base_b = ((size_t)B * p->ps_npad + 2 * rp::PS_MAX_ROWS * rp::PS_MAX_B) * sizeof(float);
+    if (base_f > budget || base_b > budget) return 0;
+    // Only worth it while the owned rows of kW stay in shared memory: streaming them from L2 with one warp per row is
+    // slower than the per-step launch sequence (measured: N=4096, B=1: 156 vs 116 us/step).
+    if (base_f + wbytes > budget) return 0;
+    p->ps_fwd_wres = 1;
+    p->ps_fwd_smem = base_f + (p->ps_fwd_wres ? wbytes : 0);
+    p->ps_bwd_dwres = (base_b + 2 * wbytes <= budget) ? 1 : 0;
+    p->ps_bwd_wres = (p->ps_bwd_dwres || base_b + wbytes <= budget) ? 1 : 0;
+    p->ps_bwd_smem = base_b + (p->ps_bwd_wres ? wbytes : 0) + (p->ps_bwd_dwres ? wbytes : 0);
+    if (plan_alloc(p, &p->ps_vec, 4 * (size_t)B * p->ps_npad)) return 1;
+    RP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->ps_bar), sizeof(unsigned int)));
+    p->persistent = true;
+    return 0;
+}
+
+int persistent_forward(rp_plan* p, const rp_fwd_args* a, const rp::ModelParams& mp, cudaStream_t st) {
+    const rp_desc& d = p->d;
+    const int N = d.n, B = d.batch, nsv = p->nsv;
+    const size_t plane = (size_t)B * N, slot = (size_t)nsv * plane;
+    const int n_rec = rp_num_records(a->T, a->sampling_steps, a->cutoff);
+    if (a->history) RP_CUDA(cudaMemcpyAsync(a->history, a->y0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (a->T == 0) { RP_CUDA(cudaMemcpyAsync(a->yT, a->y0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st)); return 0; }
+    RP_CUDA(cudaMemsetAsync(p->ps_vec, 0, 4 * (size_t)B * p->ps_npad * sizeof(float), st));   // clear stale step tags
+    if (a->out_rec && d.out_mode == RP_OUT_READOUT && n_rec > 0)
+        RP_CUDA(cudaMemsetAsync(a->out_rec, 0, (size_t)n_rec * B * d.n_out * sizeof(float), st));
+    for (int r = 0; r < a->n_rec_vars; ++r)
+        if (a->rec_reduce[r] && n_rec > 0) RP_CUDA(cudaMemsetAsync(a->rec_buf[r], 0, (size_t)n_rec * B * sizeof(float), st));
+    rp::PersistFwdArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.N = N; pa.B = B; pa.T = a->T; pa.m = d.n_in; pa.k = d.n_out; pa.in_mode = d.in_mode; pa.in_target = d.in_target;
+    pa.out_mode = d.out_mode; pa.out_var = d.out_var; pa.S = a->sampling_steps; pa.cutoff = a->cutoff;
+    pa.dt = d.dt; pa.theta = d.theta; pa.v_reset = d.v_reset;
+    pa.Wk = p->Wk; pa.ldw = p->ldw; pa.rows_per_cta = p->ps_rows; pa.w_resident = p->ps_fwd_wres;
+    pa.x = a->x; pa.W_in = a->W_in; pa.W_out = a->W_out; pa.mp = mp; pa.y0 = a->y0; pa.yT = a->yT; pa.history = a->history;
+    pa.srcbuf = reinterpret_cast<uint2*>(p->ps_vec); pa.Npad = p->ps_npad; pa.out_rec = a->out_rec; pa.n_rec_vars = a->n_rec_vars;
+    for (int r = 0; r < a->n_rec_vars; ++r) { pa.rec_var[r] = a->rec_var[r]; pa.rec_reduce[r] = a->rec_reduce[r]; pa.rec_buf[r] = a->rec_buf[r]; }
+    pa.rec_post = spiking(d.model) ? 0 : 1;
+    pa.barrier = p->ps_bar;
+    void* args[] = {&pa};
+    RP_DISPATCH_MODEL(d.model, {
+        if (ps_prepare_kernel(rp::k_persist_fwd<M_>, p->ps_fwd_smem, p->ps_grid, "rp_forward")) return 1;
+        RP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rp::k_persist_fwd<M_>), dim3(p->ps_grid), dim3(rp::PS_THREADS), args, p->ps_fwd_smem, st));
+    });
+    ++p->launches;
+    return 0;
+}
+
+int persistent_backward(rp_plan* p, const rp_bwd_args* a, const rp::ModelParams& mp, bool need_dW, cudaStream_t st) {
+    const rp_desc& d = p->d;
+    const int N = d.n, B = d.batch;
+    const int kstride = d.param_per_neuron[RP_P_K] ? 1 : 0;
+    if (a->T == 0) {
+        const size_t slot = (size_t)p->nsv * B * N;
+        if (a->g_y0) {
+            if (a->g_yT) RP_CUDA(cudaMemcpyAsync(a->g_y0, a->g_yT, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            else RP_CUDA(cudaMemsetAsync(a->g_y0, 0, slot * sizeof(float), st));
+        }
+        if (a->dW) RP_CUDA(cudaMemsetAsync(a->dW, 0, (size_t)N * N * sizeof(float), st));
+        return 0;
+    }
+    RP_CUDA(cudaMemsetAsync(p->ps_vec, 0, 4 * (size_t)B * p->ps_npad * sizeof(float), st));   // clear stale step tags
+    if (need_dW && !p->ps_bwd_dwres) RP_CUDA(cudaMemsetAsync(p->dWraw, 0, (size_t)N * p->ldw * sizeof(float), st));
+    rp::PersistBwdArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.N = N; pa.B = B; pa.T = a->T; pa.m = d.n_in; pa.k = d.n_out; pa.in_mode = d.in_mode; pa.in_target = d.in_target;
+    pa.out_mode = d.out_mode; pa.out_var = d.out_var; pa.S = a->sampling_steps; pa.cutoff = a->cutoff; pa.truncate = a->truncate_steps;
+    pa.dt = d.dt; pa.theta = d.theta; pa.slope = d.slope;
+    pa.WkT = p->WkT; pa.ldw = p->ldw; pa.rows_per_cta = p->ps_rows; pa.w_resident = p->ps_bwd_wres; pa.dw_resident = p->ps_bwd_dwres;
+    pa.need_dW = need_dW ? 1 : 0;
+    pa.x = a->x; pa.W_in = a->W_in; pa.W_out = a->W_out; pa.mp = mp; pa.history = a->history; pa.g_out_rec = a->g_out_rec; pa.g_yT = a->g_yT;
+    pa.gbuf = reinterpret_cast<uint2*>(p->ps_vec); pa.Npad = p->ps_npad; pa.dWrawT = p->dWraw;
+    for (int q = 0; q < RP_NUM_PARAMS; ++q) pa.dparams[q] = (q == RP_P_K) ? nullptr : a->dparams[q];
+    pa.dW_in = a->dW_in; pa.dW_out = a->dW_out; pa.g_y0 = a->g_y0; pa.g_x = a->g_x; pa.barrier = p->ps_bar;
+    void* args[] = {&pa};
+    RP_DISPATCH_MODEL(d.model, {
+        if (ps_prepare_kernel(rp::k_persist_bwd<M_>, p->ps_bwd_smem, p->ps_grid, "rp_backward")) return 1;
+        RP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rp::k_persist_bwd<M_>), dim3(p->ps_grid), dim3(rp::PS_THREADS), args, p->ps_bwd_smem, st));
+    });
+    ++p->launches;
+    if (need_dW) {
+        dim3 grid((N + 31) / 32, (N + 31) / 32);
+        rp::k_finish_wgrad_T<<<grid, 256, 0, st>>>(N, p->dWraw, p->ldw, a->W, a->params[RP_P_K], kstride, a->dW, a->dparams[RP_P_K]);
+        ++p->launches;
+        RP_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -239,14 +365,18 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
         p->ws_bytes += bytes;
     }
     if (rc) { rp_plan_destroy(p); return 1; }
+    if (!p->use_tc && B <= rp::PS_MAX_B && !getenv("RP_NO_PERSISTENT")) {
+        if (persistent_setup(p, prop)) { rp_plan_destroy(p); return 1; }
+    }
     *out = p;
     return 0;
 }
 
 void rp_plan_destroy(rp_plan* p) {
     if (!p) return;
-    float* bufs[] = {p->Wk, p->WkT, p->u, p->g, p->src, p->adj, p->win_acc, p->pp, p->dWraw};
+    float* bufs[] = {p->Wk, p->WkT, p->u, p->g, p->src, p->adj, p->win_acc, p->pp, p->dWraw, p->ps_vec};
     for (float* b : bufs) if (b) cudaFree(b);
+    if (p->ps_bar) cudaFree(p->ps_bar);
     rp::tc_workspace_destroy(&p->tc);
     delete p;
 }
@@ -283,6 +413,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         ++p->launches;
         RP_LAUNCH_CHECK();
     }
+    if (p->persistent) return persistent_forward(p, a, mp, st);
     float* base = a->history ? a->history : p->pp;
     auto slot_ptr = [&](int t) -> float* { return a->history ? base + (size_t)t * slot : base + (size_t)(t & 1) * slot; };
     RP_CUDA(cudaMemcpyAsync(slot_ptr(0), a->y0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -290,7 +421,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
     const bool spk = spiking(d.model);
     if (a->T > 0 && (!spk || p->use_tc)) {
         RP_DISPATCH_MODEL(d.model, (rp::k_init_src<M_><<<ew_grid(p, plane), 256, 0, st>>>(N, B, slot_ptr(0), mp,
-                                    (!spk && !p->use_tc) ? p->src : nullptr, p->use_tc ? p->tc.src_hi : nullptr,
+                                    (!spk && !p->use_tc) ? p->src : nullptr, N, p->use_tc ? p->tc.src_hi : nullptr,
                                     p->use_tc ? p->tc.src_lo : nullptr, p->tc.ldk)));
         ++p->launches;
         RP_LAUNCH_CHECK();
@@ -383,6 +514,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         if (a->dparams[q]) RP_CUDA(cudaMemsetAsync(a->dparams[q], 0, (size_t)N * sizeof(float), st));
     if (a->dW_in) RP_CUDA(cudaMemsetAsync(a->dW_in, 0, (size_t)N * d.n_in * sizeof(float), st));
     if (a->dW_out) RP_CUDA(cudaMemsetAsync(a->dW_out, 0, (size_t)N * d.n_out * sizeof(float), st));
+    if (p->persistent) return persistent_backward(p, a, mp, need_dW, st);
     if (a->g_yT) RP_CUDA(cudaMemcpyAsync(p->adj, a->g_yT, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
     else RP_CUDA(cudaMemsetAsync(p->adj, 0, slot * sizeof(float), st));
 

@@ -164,13 +164,13 @@ __global__ void __launch_bounds__(256) k_fwd_step(FwdStepArgs a) {
 // source operand of the very first step (and of re-started runs): src_0 from y_0
 template <int MODEL>
 __global__ void __launch_bounds__(256) k_init_src(int N, int B, const float* y, ModelParams mp,
-                                                   float* src, float* src_hi, float* src_lo, int ld_src) {
+                                                   float* src, int ld_plain, float* src_hi, float* src_lo, int ld_src) {
     const size_t plane = (size_t)B * N;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane; idx += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(idx / N), i = (int)(idx - (size_t)b * N);
         float r;
         if constexpr (ModelTraits<MODEL>::SPIKING) r = y[plane + idx]; else r = rate_act<MODEL>(mp, i, y[idx]);
-        if (src) src[idx] = r;
+        if (src) src[(size_t)b * ld_plain + i] = r;
         if (src_hi) {
             float hi, lo;
             split_tf32(r, hi, lo);

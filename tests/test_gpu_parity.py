@@ -50,9 +50,9 @@ def test_batched_trials_match_per_trial_oracle(model, n, B, m, k):
     """The trial axis is an engine extension: every trial must equal the unbatched reference path run on its own."""
     import rectipy_b200 as rp
     from golden_util import TEMPLATE_PATH
-    rng = np.random.default_rng(hash((model, n, B)) % 2**31)
-    dt, T, S = (1e-2, 120, 3) if model.startswith("li") else (1e-3, 400, 4)
-    W = rng.standard_normal((n, n)) * (1.5 if model.startswith("li") else 2.0) / np.sqrt(n)
+    rng = np.random.default_rng(1000 * n + 10 * B + len(model))      # deterministic (str hashes are salted per process)
+    dt, T, S = (1e-2, 120, 3) if model.startswith("li_") else (1e-3, 400, 4)
+    W = rng.standard_normal((n, n)) * (1.5 if model.startswith("li_") else 2.0) / np.sqrt(n)
     w_in, w_out = rng.standard_normal((n, m)), rng.standard_normal((k, n)) / np.sqrt(n)
     params = {"li_tanh": dict(tau=rng.uniform(1, 2, n), k=1.2, eta=0.1),
               "li_sigmoid": dict(tau=2.0, k=rng.uniform(0.5, 1.5, n), eta=0.0, r_max=1.5, s=2.0, v0=0.1),
@@ -60,7 +60,7 @@ def test_batched_trials_match_per_trial_oracle(model, n, B, m, k):
               "qif_sfa": dict(eta=orc.lorentzian_etas(n, eta=0.0), alpha=0.4, tau_x=1.2),
               "lif": dict(eta=10.0, tau=rng.uniform(10, 20, n), tau_s=5.0, k=2.0)}[model]
     spike_kwargs = dict(spike_threshold=10.0, spike_reset=-10.0) if model == "lif" else {}
-    amp, off = (1.5, 0.0) if model.startswith("li") else ((40.0, 0.0) if model == "lif" else (10.0, 14.0))
+    amp, off = (1.5, 0.0) if model.startswith("li_") else ((40.0, 0.0) if model == "lif" else (10.0, 14.0))
     t = np.arange(T) * dt
     x = amp * np.sin(2 * np.pi * rng.uniform(0.5, 3, (1, B, m)) * t[:, None, None] * (50 if model == "lif" else 1) +
                      rng.uniform(0, 6.28, (1, B, m))) + off
@@ -100,7 +100,7 @@ def test_batched_trials_match_per_trial_oracle(model, n, B, m, k):
         lb.backward()
         gs = [p.grad.numpy().copy() for p in onet.parameters()]
         g_ref = gs if g_ref is None else [a + c for a, c in zip(g_ref, gs)]
-    rate = model.startswith("li")
+    rate = model.startswith("li_")
     tol = RATE_TOL if rate else 1e-4
     assert rel_err(out.detach().cpu().numpy(), out_ref) <= tol
     g_eng = [node["weights"].grad, node[f"{op}/eta"].grad, node[f"{op}/tau"].grad,
@@ -216,3 +216,65 @@ def test_tensor_core_path_matches_fp32_path(model):
         r = onet.run(torch.tensor(x[:, b, :]), sampling_steps=S, enable_grad=False)
         ref = torch.stack(r["out"]).numpy()
         assert rel_err(results["3xtf32"]["out"][:, b, :], ref) <= (1e-5 if model == "li_tanh" else 1e-4)
+
+
+@pytest.mark.parametrize("model,n,B", [("qif_sfa", 1000, 1), ("li_tanh", 203, 2), ("lif", 64, 4), ("qif", 1536, 1)])
+def test_persistent_kernels_match_per_step_path(model, n, B, monkeypatch):
+    """Few-trial shapes run as ONE cooperative persistent launch per pass (rp_persistent.cuh); RP_NO_PERSISTENT=1 forces
+    the per-step launch sequence.  Both must agree (same fp32 arithmetic up to summation order)."""
+    import rectipy_b200 as rp
+    from rectipy_b200 import engine
+    from golden_util import TEMPLATE_PATH
+    rng = np.random.default_rng(n + B)
+    rate = model.startswith("li_")
+    dt, T, S, cutoff = (1e-2, 150, 3, 4) if rate else (1e-3, 400, 2, 0)
+    m, k = 2, 3
+    W = rng.standard_normal((n, n)) * (1.5 if rate else 2.0) / np.sqrt(n)
+    w_in, w_out = rng.standard_normal((n, m)), rng.standard_normal((k, n)) / np.sqrt(n)
+    path, op, svar, tvar = TEMPLATE_PATH[model]
+    params = {"li_tanh": dict(tau=rng.uniform(1, 2, n), k=1.2, eta=0.1), "qif": dict(eta=orc.lorentzian_etas(n), k=1.5),
+              "qif_sfa": dict(eta=orc.lorentzian_etas(n, eta=0.0), alpha=0.4, tau_x=1.2),
+              "lif": dict(eta=10.0, tau=rng.uniform(10, 20, n), tau_s=5.0, k=2.0)}[model]
+    spike_kwargs = dict(spike_threshold=10.0, spike_reset=-10.0) if model == "lif" else {}
+    t = np.arange(T) * dt
+    amp, off = (1.5, 0.0) if rate else ((40.0, 0.0) if model == "lif" else (10.0, 14.0))
+    x = amp * np.sin(2 * np.pi * rng.uniform(0.5, 3, (1, B, m)) * t[:, None, None] * (50 if model == "lif" else 1)
+                     + rng.uniform(0, 6.28, (1, B, m))) + off
+    n_rec = len([s for s in range(T) if s >= cutoff and s % S == 0])
+    targets = torch.tensor(rng.standard_normal((n_rec, B, k)), dtype=torch.float32, device="cuda")
+    res = {}
+    for mode in ("persistent", "per_step"):
+        if mode == "per_step":
+            monkeypatch.setenv("RP_NO_PERSISTENT", "1")
+        else:
+            monkeypatch.delenv("RP_NO_PERSISTENT", raising=False)
+        engine.clear_plans()
+        net = rp.Network(dt, device="cuda:0", batch=B, precision="fp32")
+        kw = dict(weights=W, source_var=svar, target_var=tvar, input_var=f"{op}/I_ext",
+                  node_vars={f"{op}/{p}": v for p, v in params.items()}, train_params=["weights", f"{op}/eta", f"{op}/tau", f"{op}/k"])
+        if not rate:
+            kw.update(spike_var=f"{op}/spike", reset_var=f"{op}/v", output_var=f"{op}/s", **spike_kwargs)
+        else:
+            kw.update(output_var=f"{op}/v")
+        node = net.add_diffeq_node("rnn", path, **kw)
+        net.add_func_node("inp", m, "identity"); net.add_edge("inp", "rnn", weights=w_in, train="gd")
+        net.add_func_node("out", k, "identity"); net.add_edge("rnn", "out", weights=w_out, train="gd")
+        var = "v"
+        rec = [("rnn", f"{op}/v", False)] + ([] if rate else [("rnn", f"{op}/s", True)])
+        obs = net.run(x, sampling_steps=S, cutoff=cutoff, verbose=False, enable_grad=True, record_vars=rec, truncate_steps=170)
+        out = torch.stack(obs["out"])
+        torch.nn.functional.mse_loss(out.reshape(n_rec, B, k), targets).backward()
+        launches = engine.total_launches()
+        res[mode] = dict(out=out.detach().cpu().numpy(), var=obs.to_numpy(("rnn", f"{op}/{var}")), y=node.y.detach().cpu().numpy(),
+                         var2=obs.to_numpy(("rnn", f"{op}/v")) if rate else obs.to_numpy(("rnn", f"{op}/s")),
+                         gW=node["weights"].grad.cpu().numpy(), geta=node[f"{op}/eta"].grad.cpu().numpy(),
+                         gtau=node[f"{op}/tau"].grad.cpu().numpy(), gk=node[f"{op}/k"].grad.cpu().numpy(),
+                         gin=net.get_edge("inp", "rnn").weights.grad.cpu().numpy(),
+                         gout=net.get_edge("rnn", "out").weights.grad.cpu().numpy(), launches=launches)
+    monkeypatch.delenv("RP_NO_PERSISTENT", raising=False)
+    engine.clear_plans()
+    assert res["persistent"]["launches"] < 12 < res["per_step"]["launches"]
+    errs = {key: rel_err(res["persistent"][key], res["per_step"][key]) for key in res["persistent"] if key != "launches"}
+    print(model, n, B, errs)
+    tol = 2e-5 if rate else 2e-3
+    assert all(e <= tol for e in errs.values()), errs
