@@ -155,13 +155,13 @@ int gemm_fp32(rp_plan* plan, bool kmajor, int P, int Q, int K, const float* A, i
 }
 
 // ---- model dispatch helpers -----------------------------------------------------------------------------
-#define RP_DISPATCH_MODEL(model, CALL)                                  \
+#define RP_DISPATCH_MODEL(model, ...)                                  \
     switch (model) {                                                    \
-        case RP_LI_TANH:    { constexpr int M_ = RP_LI_TANH;    CALL; } break; \
-        case RP_LI_SIGMOID: { constexpr int M_ = RP_LI_SIGMOID; CALL; } break; \
-        case RP_QIF:        { constexpr int M_ = RP_QIF;        CALL; } break; \
-        case RP_QIF_SFA:    { constexpr int M_ = RP_QIF_SFA;    CALL; } break; \
-        case RP_LIF:        { constexpr int M_ = RP_LIF;        CALL; } break; \
+        case RP_LI_TANH:    { constexpr int M_ = RP_LI_TANH;    __VA_ARGS__; } break; \
+        case RP_LI_SIGMOID: { constexpr int M_ = RP_LI_SIGMOID; __VA_ARGS__; } break; \
+        case RP_QIF:        { constexpr int M_ = RP_QIF;        __VA_ARGS__; } break; \
+        case RP_QIF_SFA:    { constexpr int M_ = RP_QIF_SFA;    __VA_ARGS__; } break; \
+        case RP_LIF:        { constexpr int M_ = RP_LIF;        __VA_ARGS__; } break; \
         default: return fail("unknown model id %d", model);             \
     }
 
@@ -429,17 +429,18 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
     const size_t x_stride = d.in_mode == RP_IN_DENSE ? plane : (d.in_mode == RP_IN_PROJ ? (size_t)B * d.n_in : 0);
     const size_t out_stride = d.out_mode == RP_OUT_READOUT ? (size_t)B * d.n_out : plane;
 
+    // tensor-core path: the step (and, for spiking nets read out from s, the readout) is the contraction's epilogue
+    const bool fuse_readout = p->use_tc && spk && d.out_var == RP_VAR_S && d.out_mode == RP_OUT_READOUT && a->out_rec != nullptr;
+    if (fuse_readout) {
+        rp::k_split_matrix<<<64, 256, 0, st>>>(d.n_out, N, a->W_out, N, p->tc.W_hi + (size_t)N * p->tc.ldk,
+                                               p->tc.W_lo + (size_t)N * p->tc.ldk, p->tc.ldk, d.n_out);
+        ++p->launches;
+        RP_LAUNCH_CHECK();
+    }
     for (int t = 0; t < a->T; ++t) {
         float* cur = slot_ptr(t);
         float* nxt = slot_ptr(t + 1);
-        // u[b][i] = sum_j (kW)[i][j] src_t[b][j]
-        if (!p->use_tc) {
-            const float* srcp = spk ? cur + plane : p->src;
-            if (gemm_fp32(p, true, N, B, N, p->Wk, p->ldw, srcp, N, p->u, p->ldu, 0, st, &p->launches)) return 1;
-        } else {
-            if (rp::tc_gemm(&p->tc, rp::TC_FWD, p->u, p->ldu, 0, 0, st)) return fail("rp_forward: %s", rp::tc_last_error());
-            ++p->launches;
-        }
+        const Window w = window_of(t, a->T, a->sampling_steps, a->cutoff);
         rp::FwdStepArgs fa;
         fa.N = N; fa.B = B; fa.m = d.n_in; fa.in_mode = d.in_mode; fa.in_target = d.in_target;
         fa.dt = d.dt; fa.theta = d.theta; fa.v_reset = d.v_reset;
@@ -447,18 +448,33 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         fa.x_t = a->x ? a->x + (size_t)t * x_stride : nullptr; fa.W_in = a->W_in; fa.mp = mp;
         fa.src_next = (!spk && !p->use_tc) ? p->src : nullptr;
         fa.src_hi = p->use_tc ? p->tc.src_hi : nullptr; fa.src_lo = p->use_tc ? p->tc.src_lo : nullptr; fa.ld_src = p->tc.ldk;
-        RP_DISPATCH_MODEL(d.model, (rp::k_fwd_step<M_><<<ew_grid(p, plane), 256, 0, st>>>(fa)));
-        ++p->launches;
-        RP_LAUNCH_CHECK();
-
-        const Window w = window_of(t, a->T, a->sampling_steps, a->cutoff);
-        const bool want = a->out_rec != nullptr || a->n_rec_vars > 0;
-        if (w.j >= 0 && want && (w.close || (a->out_rec && w.len > 1))) {
+        if (!p->use_tc) {
+            // u[b][i] = sum_j (kW)[i][j] src_t[b][j], then the element-wise step
+            const float* srcp = spk ? cur + plane : p->src;
+            if (gemm_fp32(p, true, N, B, N, p->Wk, p->ldw, srcp, N, p->u, p->ldu, 0, st, &p->launches)) return 1;
+            RP_DISPATCH_MODEL(d.model, (rp::k_fwd_step<M_><<<ew_grid(p, plane), 256, 0, st>>>(fa)));
+            ++p->launches;
+            RP_LAUNCH_CHECK();
+        } else {
+            const bool ro = fuse_readout && w.j >= 0;
+            RP_DISPATCH_MODEL(d.model, {
+                rp::EpiFwd<M_> epi;
+                epi.a = fa;
+                epi.out_rec_j = ro ? a->out_rec + (size_t)w.j * out_stride : nullptr;
+                epi.k = d.n_out; epi.win_first = w.first; epi.win_close = w.close; epi.inv_len = w.j >= 0 ? 1.0f / (float)w.len : 0.f;
+                if (rp::tc_forward_step<M_>(&p->tc, epi, ro, st)) return fail("rp_forward: %s", rp::tc_last_error());
+            });
+            ++p->launches;
+        }
+        const bool want_out = a->out_rec != nullptr && !fuse_readout;
+        const bool want_rec = a->n_rec_vars > 0 && w.close;
+        if (w.j >= 0 && (want_rec || (want_out && (w.close || w.len > 1)))) {
             rp::ObsArgs oa;
             oa.N = N; oa.B = B; oa.k = d.n_out; oa.out_mode = d.out_mode; oa.out_var = d.out_var; oa.model = d.model;
             oa.y_pre = cur; oa.y_post = nxt; oa.W_out = a->W_out; oa.mp = mp; oa.win_acc = p->win_acc;
             oa.win_first = w.first; oa.win_close = w.close; oa.inv_len = 1.0f / (float)w.len;
-            oa.out_rec_j = a->out_rec ? a->out_rec + (size_t)w.j * out_stride : nullptr;
+            oa.out_rec_j = want_out ? a->out_rec + (size_t)w.j * out_stride : nullptr;
+            oa.skip_out = want_out ? 0 : 1;
             oa.n_rec_vars = a->n_rec_vars;
             for (int r = 0; r < RP_MAX_REC; ++r) {
                 oa.rec_var[r] = r < a->n_rec_vars ? a->rec_var[r] : 0;
@@ -536,6 +552,13 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     aa.any_param_grad = (a->dW_in || a->dW_out) ? 1 : 0;
     for (int q = 0; q < RP_NUM_PARAMS; ++q) if (aa.dparams[q]) aa.any_param_grad = 1;
 
+    // fused tensor-core adjoint: everything except runs that train W_in or drive the lif s_ext input, or want dL/dx
+    bool pgrad = false;
+    for (int q = 0; q < RP_NUM_PARAMS; ++q) if (aa.dparams[q]) pgrad = true;
+    // The fused adjoint epilogue is opt-in (RP_FUSED_ADJ=1): with one tile per CTA its element-wise work cannot overlap the
+    // MMA main loop and runs at 8 warps/SM, which measured slower (340 us/step) than the contraction followed by the
+    // full-occupancy k_adj_step (149 + ~60 us).  It becomes the default once tiles are software-pipelined per CTA.
+    const bool fused_adj = p->use_tc && getenv("RP_FUSED_ADJ") && !a->dW_in && !a->g_x && !(d.model == RP_LIF && d.in_target == 1);
     dim3 agrid((N + rp::ADJ_TX - 1) / rp::ADJ_TX, (B + rp::ADJ_TY * rp::ADJ_BPT - 1) / (rp::ADJ_TY * rp::ADJ_BPT));
     dim3 ablock(rp::ADJ_TX, rp::ADJ_TY);
     int pending = 0;   // steps whose (g, src) columns sit in the tensor-core weight-gradient chunk
@@ -561,9 +584,6 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                         if (gemm_fp32(p, false, N, N, B, srcp, N, p->g, N, p->dWraw, p->ldw, 1, st, &p->launches)) return 1;
                     }
                 }
-            } else {
-                if (rp::tc_gemm(&p->tc, rp::TC_DGRAD, p->u, p->ldu, 0, 0, st)) return fail("rp_backward: %s", rp::tc_last_error());
-                ++p->launches;
             }
             const Window w = window_of(t, a->T, a->sampling_steps, a->cutoff);
             aa.y_t = a->history + (size_t)t * slot;
@@ -580,9 +600,30 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                 aa.t_col0 = pending * B;
             }
         }
-        RP_DISPATCH_MODEL(d.model, (rp::k_adj_step<M_><<<agrid, ablock, 0, st>>>(aa)));
+        if (fused_adj && aa.do_post) {
+            // Z_t = (kW)^T g_t on the tensor cores with the adjoint recurrences as its epilogue
+            rp::AdjArgs fa = aa;
+            fa.dW_out = nullptr;                     // readout gradient: one pass over the checkpoints after the sweep
+            if (pgrad) {
+                RP_DISPATCH_MODEL(d.model, {
+                    rp::EpiAdj<M_, true> epi; epi.a = fa;
+                    if (rp::tc_adjoint_step<M_, true>(&p->tc, epi, st)) return fail("rp_backward: %s", rp::tc_last_error());
+                });
+            } else {
+                RP_DISPATCH_MODEL(d.model, {
+                    rp::EpiAdj<M_, false> epi; epi.a = fa;
+                    if (rp::tc_adjoint_step<M_, false>(&p->tc, epi, st)) return fail("rp_backward: %s", rp::tc_last_error());
+                });
+            }
+        } else {
+            if (p->use_tc && aa.do_post) {
+                if (rp::tc_gemm(&p->tc, rp::TC_DGRAD, p->u, p->ldu, 0, 0, st)) return fail("rp_backward: %s", rp::tc_last_error());
+                ++p->launches;
+            }
+            RP_DISPATCH_MODEL(d.model, (rp::k_adj_step<M_><<<agrid, ablock, 0, st>>>(aa)));
+            RP_LAUNCH_CHECK();
+        }
         ++p->launches;
-        RP_LAUNCH_CHECK();
         if (p->use_tc && need_dW && aa.do_pre) {
             ++pending;
             if (pending == wg_chunk || t == 1) {
@@ -592,6 +633,13 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                 pending = 0;
             }
         }
+    }
+    if (fused_adj && a->dW_out && a->g_out_rec && a->T > 0) {
+        dim3 rgrid((N + 127) / 128, std::max(1, std::min(a->T, 4 * p->sm_count / std::max(1, (N + 127) / 128))));
+        RP_DISPATCH_MODEL(d.model, (rp::k_readout_grad<M_><<<rgrid, 128, 0, st>>>(N, B, a->T, a->sampling_steps, a->cutoff, d.n_out, d.out_var,
+                                                                                   a->history, a->g_out_rec, mp, a->dW_out)));
+        ++p->launches;
+        RP_LAUNCH_CHECK();
     }
     if (need_dW) {
         rp::k_finish_wgrad<<<N, 256, 0, st>>>(N, p->dWraw, p->ldw, a->W, a->params[RP_P_K], kstride, a->dW, a->dparams[RP_P_K]);

@@ -18,6 +18,7 @@
 #include <cudaTypedefs.h>
 #include <stdint.h>
 #include <stdio.h>
+#include "rp_kernels.cuh"
 
 namespace rp {
 
@@ -132,11 +133,210 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BQ>
+// ---- epilogues -----------------------------------------------------------------------------------------------------------
+// While the K loop runs, epilogue thread (warp, lane) owns TMEM lane = tile row and CPT columns (that is how tcgen05.ld hands
+// out the accumulator).  Fused epilogues then park the fp32 tile in the idle shared-memory stages as tile[col][row], meet at a
+// named barrier and RE-PARTITION the work: thread (w, l) takes the 4 consecutive neurons 4l..4l+3 and a contiguous block of
+// BQ/8 trials.  Every global access of the element-wise step is then a 16-byte vector over neurons (512 B per warp and trial),
+// loads of a batch are issued before any store, and the weight-gradient operands are written as 16-byte vectors over trials.
+struct EpiStore {                       // C[q*ldc + p] (+)= acc
+    static constexpr bool kStage = false;
+    float* C; int ldc; int accumulate;
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+__device__ __forceinline__ float f4get(const float4& v, int r) { return r == 0 ? v.x : (r == 1 ? v.y : (r == 2 ? v.z : v.w)); }
+
+// forward step: u = (kW . r_t)[b][i] never touches global memory; tile rows >= N hold W_out (readout o_t = W_out . s_t)
+template <int MODEL>
+struct EpiFwd {
+    static constexpr bool kStage = true;
+    FwdStepArgs a;
+    float* out_rec_j; int k; int win_first, win_close; float inv_len;
+
+    template <int BQ>
+    __device__ __forceinline__ void run_tile(int p0, int q0, const float* tile, int et, float* /*extra*/) const {
+        constexpr int NSV = ModelTraits<MODEL>::NSV;
+        constexpr int NCOL = BQ / 8;
+        const int w = et >> 5, l = et & 31;
+        const int cbase = w * NCOL;
+        const size_t plane = (size_t)a.B * a.N;
+        if (p0 < a.N) {
+            const int i0 = p0 + 4 * l;
+            FwdRow row[4];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) row[rr] = fwd_row<MODEL>(a, i0 + rr);
+            for (int c = 0; c < NCOL; c += 2) {
+                float4 u4[2], v4[2], s4[2], x4[2], xd4[2];
+                float xin0[2], xin1[2];
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int b = q0 + cbase + c + cc;
+                    const size_t idx = (size_t)b * a.N + i0;
+                    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                    u4[cc] = *reinterpret_cast<const float4*>(tile + (size_t)(cbase + c + cc) * TC_BP + 4 * l);
+                    v4[cc] = ldg4(a.y_cur + idx);
+                    s4[cc] = NSV > 1 ? ldg4(a.y_cur + plane + idx) : zero;
+                    x4[cc] = NSV > 2 ? ldg4(a.y_cur + 2 * plane + idx) : zero;
+                    xd4[cc] = a.in_mode == RP_IN_DENSE ? ldg4(a.x_t + idx) : zero;
+                    xin0[cc] = a.in_mode == RP_IN_PROJ ? __ldg(a.x_t + (size_t)b * a.m) : 0.f;
+                    xin1[cc] = (a.in_mode == RP_IN_PROJ && a.m > 1) ? __ldg(a.x_t + (size_t)b * a.m + 1) : 0.f;
+                }
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int b = q0 + cbase + c + cc;
+                    const size_t idx = (size_t)b * a.N + i0;
+                    float v1[4], s1[4], x1[4], hi[4], lo[4];
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int i = i0 + rr;
+                        fwd_elem_fast<MODEL>(a, row[rr], i, b, f4get(u4[cc], rr), xin0[cc], xin1[cc], f4get(xd4[cc], rr),
+                                             f4get(v4[cc], rr), f4get(s4[cc], rr), f4get(x4[cc], rr), v1[rr], s1[rr], x1[rr]);
+                        float src1;
+                        if constexpr (ModelTraits<MODEL>::SPIKING) src1 = s1[rr]; else src1 = rate_act<MODEL>(a.mp, i, v1[rr]);
+                        split_tf32(src1, hi[rr], lo[rr]);
+                    }
+                    st4(a.y_next + idx, v1[0], v1[1], v1[2], v1[3]);
+                    if (NSV > 1) st4(a.y_next + plane + idx, s1[0], s1[1], s1[2], s1[3]);
+                    if (NSV > 2) st4(a.y_next + 2 * plane + idx, x1[0], x1[1], x1[2], x1[3]);
+                    st4(a.src_hi + (size_t)b * a.ld_src + i0, hi[0], hi[1], hi[2], hi[3]);
+                    st4(a.src_lo + (size_t)b * a.ld_src + i0, lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        } else if (out_rec_j != nullptr) {
+            // readout rows: row kk of this tile is W_out[kk]; o_t[b][kk] accumulates into the open record window
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int kk = 4 * l + rr;
+                if (kk < k) {
+                    for (int c = 0; c < NCOL; ++c) {
+                        float* dst = out_rec_j + (size_t)(q0 + cbase + c) * k + kk;
+                        float val = tile[(size_t)(cbase + c) * TC_BP + kk];
+                        if (!win_first) val += *dst;
+                        if (win_close) val *= inv_len;
+                        *dst = val;
+                    }
+                }
+            }
+        }
+    }
+};
+
+// reverse step: Z = ((kW)^T . g_t)[b][i] feeds the adjoint recurrences directly; the epilogue also emits the operands of
+// the next adjoint product (K-major) and of the weight gradient (trial-major) and the parameter-gradient partial sums
+// PG: template parameters (eta, tau, tau_s, tau_x, alpha) are trained -> five register sums per owned neuron.
+// Edge gradients are not accumulated here: dW_out comes from one pass over the checkpoints (k_readout_grad), and runs that
+// train W_in use the unfused adjoint path.
+template <int MODEL, bool PG>
+struct EpiAdj {
+    static constexpr bool kStage = true;
+    AdjArgs a;
+
+    template <int BQ>
+    __device__ __forceinline__ void run_tile(int p0, int q0, const float* tile, int et, float* /*extra*/) const {
+        constexpr int NSV = ModelTraits<MODEL>::NSV;
+        constexpr int NCOL = BQ / 8;
+        const int w = et >> 5, l = et & 31;
+        const int cbase = w * NCOL;
+        const int i0 = p0 + 4 * l;
+        const size_t plane = (size_t)a.B * a.N;
+        float pacc[4][5];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) pacc[rr][q] = 0.f;
+        AdjRowParams rp_[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) rp_[rr] = adj_row_params<MODEL>(a, i0 + rr);
+
+        for (int c = 0; c < NCOL; c += 4) {
+            float g[4][4], sv[4][4];          // [column][row]
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float4 z4[2], av4[2], as4[2], ax4[2], v4[2], s4[2], x4[2], vm4[2], sm4[2];
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int col = cbase + c + 2 * half + cc;
+                    const size_t idx = (size_t)(q0 + col) * a.N + i0;
+                    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                    z4[cc] = *reinterpret_cast<const float4*>(tile + (size_t)col * TC_BP + 4 * l);
+                    av4[cc] = *reinterpret_cast<const float4*>(a.adj + idx);
+                    as4[cc] = NSV > 1 ? *reinterpret_cast<const float4*>(a.adj + plane + idx) : zero;
+                    ax4[cc] = NSV > 2 ? *reinterpret_cast<const float4*>(a.adj + 2 * plane + idx) : zero;
+                    v4[cc] = ldg4(a.y_t + idx);
+                    s4[cc] = NSV > 1 ? ldg4(a.y_t + plane + idx) : zero;
+                    x4[cc] = NSV > 2 ? ldg4(a.y_t + 2 * plane + idx) : zero;
+                    vm4[cc] = a.do_pre ? ldg4(a.y_tm1 + idx) : zero;
+                    sm4[cc] = (a.do_pre && NSV > 1) ? ldg4(a.y_tm1 + plane + idx) : zero;
+                }
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int cl = 2 * half + cc;
+                    const int b = q0 + cbase + c + cl;
+                    const size_t idx = (size_t)b * a.N + i0;
+                    float nav[4], nas[4], nax[4], dI[4], gh[4], gl[4];
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int i = i0 + rr;
+                        nav[rr] = f4get(av4[cc], rr); nas[rr] = f4get(as4[cc], rr); nax[rr] = f4get(ax4[cc], rr);
+                        if constexpr (PG) {
+                            const RowAcc acc{pacc[rr]};
+                            dI[rr] = adj_post_math<MODEL>(a, rp_[rr], acc, i, b, f4get(z4[cc], rr), f4get(v4[cc], rr), f4get(s4[cc], rr),
+                                                          f4get(x4[cc], rr), nav[rr], nas[rr], nax[rr]);
+                        } else {
+                            const NoAcc acc;
+                            dI[rr] = adj_post_math<MODEL>(a, rp_[rr], acc, i, b, f4get(z4[cc], rr), f4get(v4[cc], rr), f4get(s4[cc], rr),
+                                                          f4get(x4[cc], rr), nav[rr], nas[rr], nax[rr]);
+                        }
+                        g[cl][rr] = 0.f; sv[cl][rr] = 0.f;
+                        if (a.do_pre) adj_pre_math<MODEL>(a, i, nav[rr], f4get(vm4[cc], rr), f4get(sm4[cc], rr), g[cl][rr], sv[cl][rr]);
+                        split_tf32(g[cl][rr], gh[rr], gl[rr]);
+                    }
+                    st4(a.adj + idx, nav[0], nav[1], nav[2], nav[3]);
+                    if (NSV > 1) st4(a.adj + plane + idx, nas[0], nas[1], nas[2], nas[3]);
+                    if (NSV > 2) st4(a.adj + 2 * plane + idx, nax[0], nax[1], nax[2], nax[3]);
+                    if (a.g_x_t) st4(a.g_x_t + idx, dI[0], dI[1], dI[2], dI[3]);
+                    if (a.do_pre) {
+                        st4(a.g_hi + (size_t)b * a.ld_g + i0, gh[0], gh[1], gh[2], gh[3]);
+                        st4(a.g_lo + (size_t)b * a.ld_g + i0, gl[0], gl[1], gl[2], gl[3]);
+                    }
+                }
+            }
+            if (a.do_pre && a.gT_hi) {
+                // weight-gradient operands, trial-major: 4 consecutive trials per 16-byte store, one row at a time
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    float gh[4], gl[4], sh[4], sl[4];
+#pragma unroll
+                    for (int cl = 0; cl < 4; ++cl) { split_tf32(g[cl][rr], gh[cl], gl[cl]); split_tf32(sv[cl][rr], sh[cl], sl[cl]); }
+                    const size_t off = (size_t)(i0 + rr) * a.ld_t + a.t_col0 + q0 + cbase + c;
+                    st4(a.gT_hi + off, gh[0], gh[1], gh[2], gh[3]);
+                    st4(a.gT_lo + off, gl[0], gl[1], gl[2], gl[3]);
+                    st4(a.srcT_hi + off, sh[0], sh[1], sh[2], sh[3]);
+                    st4(a.srcT_lo + off, sl[0], sl[1], sl[2], sl[3]);
+                }
+            }
+        }
+        if constexpr (PG) {
+            const int slots[5] = {RP_P_ETA, RP_P_TAU, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA};
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                float* dst = a.dparams[slots[q]];
+                if (dst != nullptr) {
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) atomicAdd(dst + i0 + rr, pacc[rr][q]);
+                }
+            }
+        }
+    }
+};
+
+template <int BQ, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-              float* __restrict__ C, int ldc, int num_k_blocks, int accumulate) {
+              int num_k_blocks, const __grid_constant__ Epi epi) {
     using Cfg = TcCfg<BQ>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int CPT = Cfg::COLS_PER_THREAD;
@@ -243,12 +443,22 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
+        if constexpr (!Epi::kStage) {
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-            float* dst = C + (size_t)(q0 + half * CPT + j) * ldc + p;
-            float v = acc[j];
-            if (accumulate) v += *dst;
-            *dst = v;
+            for (int j = 0; j < CPT; ++j) {
+                float* dst = epi.C + (size_t)(q0 + half * CPT + j) * epi.ldc + p;
+                float v = acc[j];
+                if (epi.accumulate) v += *dst;
+                *dst = v;
+            }
+        } else {
+            // all MMAs have retired (last tmem_full barrier) and every TMA load was consumed: the stages are free
+            float* tile = reinterpret_cast<float*>(smem);                      // tile[col][row], BQ x 128 fp32
+            float* my = tile + (size_t)(half * CPT) * TC_BP + lane_base + lane;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) my[j * TC_BP] = acc[j];
+            asm volatile("bar.sync 1, 256;" ::: "memory");                      // the 8 epilogue warps only
+            epi.template run_tile<BQ>(p0, q0, tile, ew * 32 + lane, tile + (size_t)BQ * TC_BP);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -325,10 +535,14 @@ inline int tc_alloc(float** p, size_t n, size_t* bytes) {
     return 0;
 }
 
+template <class Epi>
 inline int tc_set_attrs() {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_3xtf32<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_3xtf32<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
+    static bool done = false;
+    if (done) return 0;
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_3xtf32<256, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_3xtf32<128, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
     if (e != cudaSuccess) RP_TC_FAIL("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
+    done = true;
     return 0;
 }
 
@@ -347,13 +561,13 @@ inline int tc_workspace_create(TcWorkspace* w, int N, int B, size_t* bytes) {
     w->bq_fwd = (B % 256 == 0) ? 256 : 128;
     w->bq_wg = (N % 256 == 0) ? 256 : 128;
     const size_t nn = (size_t)N * w->ldk, bn = (size_t)B * w->ldk;
-    if (tc_alloc(&w->W_hi, nn, bytes) || tc_alloc(&w->W_lo, nn, bytes) || tc_alloc(&w->WT_hi, nn, bytes) || tc_alloc(&w->WT_lo, nn, bytes)) return 1;
+    const size_t nw = (size_t)(N + TC_BP) * w->ldk;        // + one row tile for the fused readout rows (W_out)
+    if (tc_alloc(&w->W_hi, nw, bytes) || tc_alloc(&w->W_lo, nw, bytes) || tc_alloc(&w->WT_hi, nn, bytes) || tc_alloc(&w->WT_lo, nn, bytes)) return 1;
     if (tc_alloc(&w->src_hi, bn, bytes) || tc_alloc(&w->src_lo, bn, bytes) || tc_alloc(&w->g_hi, bn, bytes) || tc_alloc(&w->g_lo, bn, bytes)) return 1;
-    if (tc_make_map(&w->m_W[0], w->W_hi, N, N, w->ldk, TC_BP) || tc_make_map(&w->m_W[1], w->W_lo, N, N, w->ldk, TC_BP)) return 1;
+    if (tc_make_map(&w->m_W[0], w->W_hi, N + TC_BP, N, w->ldk, TC_BP) || tc_make_map(&w->m_W[1], w->W_lo, N + TC_BP, N, w->ldk, TC_BP)) return 1;
     if (tc_make_map(&w->m_WT[0], w->WT_hi, N, N, w->ldk, TC_BP) || tc_make_map(&w->m_WT[1], w->WT_lo, N, N, w->ldk, TC_BP)) return 1;
     if (tc_make_map(&w->m_src[0], w->src_hi, B, N, w->ldk, w->bq_fwd) || tc_make_map(&w->m_src[1], w->src_lo, B, N, w->ldk, w->bq_fwd)) return 1;
     if (tc_make_map(&w->m_g[0], w->g_hi, B, N, w->ldk, w->bq_fwd) || tc_make_map(&w->m_g[1], w->g_lo, B, N, w->ldk, w->bq_fwd)) return 1;
-    if (tc_set_attrs()) return 1;
     return 0;
 }
 
@@ -367,14 +581,29 @@ inline int tc_workspace_ensure_wgrad(TcWorkspace* w, size_t* bytes) {
     return 0;
 }
 
-inline int tc_launch(int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, float* C, int ldc, int accumulate, cudaStream_t st) {
+template <class Epi>
+inline int tc_launch_epi(int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, const Epi& epi, cudaStream_t st) {
     if (P % TC_BP || Q % bq || K % TC_BK) RP_TC_FAIL("tc_launch: extents P=%d Q=%d K=%d do not match tile %dx%dx%d", P, Q, K, TC_BP, bq, TC_BK);
+    if (tc_set_attrs<Epi>()) return 1;
     dim3 grid(P / TC_BP, Q / bq);
-    if (bq == 256) k_gemm_3xtf32<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], C, ldc, K / TC_BK, accumulate);
-    else           k_gemm_3xtf32<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], C, ldc, K / TC_BK, accumulate);
+    if (bq == 256) k_gemm_3xtf32<256, Epi><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], K / TC_BK, epi);
+    else           k_gemm_3xtf32<128, Epi><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], K / TC_BK, epi);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) RP_TC_FAIL("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e));
     return 0;
+}
+inline int tc_launch(int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, float* C, int ldc, int accumulate, cudaStream_t st) {
+    EpiStore e{C, ldc, accumulate};
+    return tc_launch_epi<EpiStore>(bq, P, Q, K, A, Bm, e, st);
+}
+// fused launches: forward step (rows = N, or N+128 when the readout rows are appended) and adjoint step
+template <int MODEL>
+inline int tc_forward_step(TcWorkspace* w, const EpiFwd<MODEL>& epi, bool readout_rows, cudaStream_t st) {
+    return tc_launch_epi<EpiFwd<MODEL>>(w->bq_fwd, w->N + (readout_rows ? TC_BP : 0), w->B, w->N, w->m_W, w->m_src, epi, st);
+}
+template <int MODEL, bool PG>
+inline int tc_adjoint_step(TcWorkspace* w, const EpiAdj<MODEL, PG>& epi, cudaStream_t st) {
+    return tc_launch_epi<EpiAdj<MODEL, PG>>(w->bq_fwd, w->N, w->B, w->N, w->m_WT, w->m_g, epi, st);
 }
 
 // mode TC_FWD:   C=u[b][i]     A = kW (hi,lo)      B = src (hi,lo)     K = N
@@ -393,7 +622,6 @@ inline int tc_gemm(TcWorkspace* w, int mode, float* C, int ldc, int k_extent, in
 inline int tc_gemm_standalone(int P, int Q, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                               int accumulate, cudaStream_t st) {
     if (P % TC_BP || Q % 128 || K <= 0) RP_TC_FAIL("3xTF32 GEMM needs P %% 128 == 0, Q %% 128 == 0 (got P=%d Q=%d K=%d)", P, Q, K);
-    if (tc_set_attrs()) return 1;
     const int Kp = (K + TC_BK - 1) / TC_BK * TC_BK;
     const int bq = (Q % 256 == 0) ? 256 : 128;
     float* tmp = nullptr;

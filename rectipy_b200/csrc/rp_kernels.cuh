@@ -15,6 +15,20 @@
 
 namespace rp {
 
+// record windows of Network.run (network.py:590-597), usable on host and device
+struct PWindow { int j, first, close, len; };
+__host__ __device__ inline PWindow pwindow_of(int t, int T, int S, int cutoff) {
+    PWindow w{-1, 0, 0, 0};
+    if (t < cutoff) return w;
+    const int r0 = ((cutoff + S - 1) / S) * S;
+    int j, start, rec;
+    if (t <= r0) { j = 0; start = cutoff; rec = r0; }
+    else { j = (t - r0 + S - 1) / S; rec = r0 + j * S; start = rec - S + 1; }
+    if (rec >= T) return w;
+    w.j = j; w.first = (t == start); w.close = (t == rec); w.len = rec - start + 1;
+    return w;
+}
+
 struct ModelParams {
     const float* p[RP_NUM_PARAMS];
     int stride[RP_NUM_PARAMS];   // 0: shared scalar, 1: per neuron
@@ -132,32 +146,89 @@ __device__ __forceinline__ float input_current(int in_mode, int m, const float* 
     return 0.f;
 }
 
+// Per-neuron constants of the forward step, hoisted out of the trial loop by the fused epilogue.  Reciprocals replace the
+// per-element divisions (x * (1/tau) differs from x / tau by at most 1 ulp; exact for the template default tau = 1).
+struct FwdRow { float inv_tau, eta, inv_tau_s, inv_tau_x, alpha, wi0, wi1; };
+
 template <int MODEL>
-__global__ void __launch_bounds__(256) k_fwd_step(FwdStepArgs a) {
+__device__ __forceinline__ FwdRow fwd_row(const FwdStepArgs& a, int i) {
+    FwdRow r{1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f};
+    r.inv_tau = 1.0f / ldp(a.mp, RP_P_TAU, i);
+    r.eta = ldp(a.mp, RP_P_ETA, i);
+    if (ModelTraits<MODEL>::SPIKING) r.inv_tau_s = 1.0f / ldp(a.mp, RP_P_TAU_S, i);
+    if (MODEL == RP_QIF_SFA) { r.inv_tau_x = 1.0f / ldp(a.mp, RP_P_TAU_X, i); r.alpha = ldp(a.mp, RP_P_ALPHA, i); }
+    if (a.in_mode == RP_IN_PROJ) {
+        r.wi0 = __ldg(a.W_in + (size_t)i * a.m);
+        if (a.m > 1) r.wi1 = __ldg(a.W_in + (size_t)i * a.m + 1);
+    }
+    return r;
+}
+
+// x0, x1: the first two input channels of trial b (broadcast), further channels are fetched here
+template <int MODEL>
+__device__ __forceinline__ void fwd_elem_fast(const FwdStepArgs& a, const FwdRow& r, int i, int b, float u, float x0, float x1,
+                                              float xdense, float v, float s, float x, float& v1, float& s1, float& x1o) {
+    const float dt = a.dt;
+    float Iin = xdense;
+    if (a.in_mode == RP_IN_PROJ) {
+        Iin = fmaf(r.wi1, x1, r.wi0 * x0);
+        for (int j = 2; j < a.m; ++j) Iin = fmaf(__ldg(a.W_in + (size_t)i * a.m + j), __ldg(a.x_t + (size_t)b * a.m + j), Iin);
+    }
+    if constexpr (!ModelTraits<MODEL>::SPIKING) {
+        v1 = v + dt * (-v * r.inv_tau + u + Iin + r.eta);
+        s1 = 0.f; x1o = 0.f;
+    } else {
+        const bool p = v >= a.theta;
+        const float pf = p ? 1.0f : 0.0f;
+        float vt;
+        if constexpr (MODEL == RP_LIF) {
+            const float Iv = a.in_target == 0 ? Iin : 0.f, Is = a.in_target == 1 ? Iin : 0.f;
+            vt = v + dt * (-v * r.inv_tau + u + Iv + r.eta);
+            s1 = s + dt * (-s * r.inv_tau_s + Is) + pf;
+            x1o = 0.f;
+        } else {
+            float xx = 0.f;
+            if constexpr (MODEL == RP_QIF_SFA) xx = x;
+            vt = v + dt * ((v * v + r.eta - xx + Iin) * r.inv_tau + u);
+            s1 = s + dt * (-s * r.inv_tau_s) + pf;
+            if constexpr (MODEL == RP_QIF_SFA) x1o = x + dt * (-x * r.inv_tau_x) + r.alpha * pf; else x1o = 0.f;
+        }
+        v1 = p ? a.v_reset : vt;
+    }
+}
+
+// everything step t does for element (neuron i, trial b) once its recurrent drive u is known
+template <int MODEL>
+__device__ __forceinline__ void fwd_element(const FwdStepArgs& a, int i, int b, float u) {
     constexpr int NSV = ModelTraits<MODEL>::NSV;
     const size_t plane = (size_t)a.B * a.N;
-    const size_t total = plane;
+    const size_t idx = (size_t)b * a.N + i;
+    const float v = a.y_cur[idx];
+    const float s = NSV > 1 ? a.y_cur[plane + idx] : 0.f;
+    const float x = NSV > 2 ? a.y_cur[2 * plane + idx] : 0.f;
+    const float Iin = input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i);
+    float v1, s1, x1;
+    fwd_elem<MODEL>(a, i, u, Iin, v, s, x, v1, s1, x1);
+    a.y_next[idx] = v1;
+    if (NSV > 1) a.y_next[plane + idx] = s1;
+    if (NSV > 2) a.y_next[2 * plane + idx] = x1;
+    float src1;
+    if constexpr (ModelTraits<MODEL>::SPIKING) src1 = s1; else src1 = rate_act<MODEL>(a.mp, i, v1);
+    if (a.src_next) a.src_next[idx] = src1;
+    if (a.src_hi) {
+        float hi, lo;
+        split_tf32(src1, hi, lo);
+        a.src_hi[(size_t)b * a.ld_src + i] = hi;
+        a.src_lo[(size_t)b * a.ld_src + i] = lo;
+    }
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(256) k_fwd_step(FwdStepArgs a) {
+    const size_t total = (size_t)a.B * a.N;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(idx / a.N), i = (int)(idx - (size_t)b * a.N);
-        const float v = a.y_cur[idx];
-        const float s = NSV > 1 ? a.y_cur[plane + idx] : 0.f;
-        const float x = NSV > 2 ? a.y_cur[2 * plane + idx] : 0.f;
-        const float u = a.u[(size_t)b * a.ldu + i];
-        const float Iin = input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i);
-        float v1, s1, x1;
-        fwd_elem<MODEL>(a, i, u, Iin, v, s, x, v1, s1, x1);
-        a.y_next[idx] = v1;
-        if (NSV > 1) a.y_next[plane + idx] = s1;
-        if (NSV > 2) a.y_next[2 * plane + idx] = x1;
-        float src1;
-        if constexpr (ModelTraits<MODEL>::SPIKING) src1 = s1; else src1 = rate_act<MODEL>(a.mp, i, v1);
-        if (a.src_next) a.src_next[idx] = src1;
-        if (a.src_hi) {
-            float hi, lo;
-            split_tf32(src1, hi, lo);
-            a.src_hi[(size_t)b * a.ld_src + i] = hi;
-            a.src_lo[(size_t)b * a.ld_src + i] = lo;
-        }
+        fwd_element<MODEL>(a, i, b, a.u[(size_t)b * a.ldu + i]);
     }
 }
 
@@ -199,6 +270,7 @@ struct ObsArgs {
     int rec_reduce[RP_MAX_REC];
     float* rec_buf_j[RP_MAX_REC];   // [B][N] | [B]
     int rec_post;           // 1: recorded vars are post-update (RateNet), 0: pre-update (SpikeResetNet)
+    int skip_out;           // 1: the output is produced elsewhere (fused readout rows); only record state variables
 };
 
 template <int MODEL>
@@ -236,7 +308,7 @@ __global__ void __launch_bounds__(256) k_observe(ObsArgs a) {
     float part[RP_MAX_OUT];
 #pragma unroll
     for (int q = 0; q < RP_MAX_OUT; ++q) part[q] = 0.f;
-    const bool need_out = a.out_rec_j != nullptr || !a.win_close;
+    const bool need_out = !a.skip_out && (a.out_rec_j != nullptr || !a.win_close);
     if (need_out) {
         for (int i = threadIdx.x; i < a.N; i += blockDim.x) {
             const size_t idx = (size_t)b * a.N + i;
@@ -311,132 +383,234 @@ struct AdjArgs {
 };
 
 constexpr int ADJ_TX = 32, ADJ_TY = 8, ADJ_BPT = 8;   // block covers 32 neurons x 64 trials
+constexpr int ADJ_NACC = RP_NUM_PARAMS + RP_MAX_IN + RP_MAX_OUT;
+
+// per-thread context of the adjoint: one neuron i, running sums of its parameter-gradient contributions
+template <int MODEL>
+struct AdjCtx {
+    int i;
+    float tau, tau_s, tau_x, alpha;
+    float acc[ADJ_NACC];     // [0,RP_NUM_PARAMS): dparams ; then dW_in[i][0..m) ; then dW_out[0..k)[i]
+};
+
+template <int MODEL>
+__device__ __forceinline__ void adj_ctx_init(const AdjArgs& a, AdjCtx<MODEL>& c, int i) {
+    c.i = i;
+    c.tau = 1.f; c.tau_s = 1.f; c.tau_x = 1.f; c.alpha = 0.f;
+#pragma unroll
+    for (int q = 0; q < ADJ_NACC; ++q) c.acc[q] = 0.f;
+    if (i < a.N) {
+        c.tau = ldp(a.mp, RP_P_TAU, i);
+        if (ModelTraits<MODEL>::SPIKING) c.tau_s = ldp(a.mp, RP_P_TAU_S, i);
+        if (MODEL == RP_QIF_SFA) { c.tau_x = ldp(a.mp, RP_P_TAU_X, i); c.alpha = ldp(a.mp, RP_P_ALPHA, i); }
+    }
+}
+
+// Accumulation policies for the parameter-gradient contributions of one neuron
+struct RegAcc {            // private running sums (stand-alone kernel: reduced over trial lanes afterwards)
+    float* acc;
+    __device__ __forceinline__ void add(int q, float v) const { acc[q] += v; }
+};
+struct SmemAcc {           // shared-memory atomics, one column of [ADJ_NACC][stride] per neuron (fused epilogue)
+    float* base; int stride; unsigned mask;
+    __device__ __forceinline__ void add(int q, float v) const { if (mask & (1u << q)) atomicAdd(base + q * stride, v); }
+};
+
+struct RowAcc {            // five per-neuron template-parameter sums in registers (fused epilogue); edge gradients handled elsewhere
+    float* pacc;           // [5]: eta, tau, tau_s, tau_x, alpha
+    __device__ __forceinline__ void add(int q, float v) const {
+        if (q == RP_P_ETA) pacc[0] += v; else if (q == RP_P_TAU) pacc[1] += v; else if (q == RP_P_TAU_S) pacc[2] += v;
+        else if (q == RP_P_TAU_X) pacc[3] += v; else if (q == RP_P_ALPHA) pacc[4] += v;
+    }
+};
+struct NoAcc { __device__ __forceinline__ void add(int, float) const {} };
+
+struct AdjRowParams { float tau, tau_s, tau_x, alpha; };
+
+template <int MODEL>
+__device__ __forceinline__ AdjRowParams adj_row_params(const AdjArgs& a, int i) {
+    AdjRowParams r{1.f, 1.f, 1.f, 0.f};
+    if (i < a.N) {
+        r.tau = ldp(a.mp, RP_P_TAU, i);
+        if (ModelTraits<MODEL>::SPIKING) r.tau_s = ldp(a.mp, RP_P_TAU_S, i);
+        if (MODEL == RP_QIF_SFA) { r.tau_x = ldp(a.mp, RP_P_TAU_X, i); r.alpha = ldp(a.mp, RP_P_ALPHA, i); }
+    }
+    return r;
+}
+
+// "post" of reverse step t for one element, pure arithmetic: (av, as, ax) = adjoint at t+1 in, adjoint at t out.
+// (v, s, x) = y_t.  Z = ((kW)^T g_t)[b][i].  Returns dI = dL/d(input current of step t).
+template <int MODEL, class Acc>
+__device__ __forceinline__ float adj_post_math(const AdjArgs& a, const AdjRowParams& rp_, const Acc& acc, int i, int b, float Z,
+                                               float v, float s, float x, float& av, float& as, float& ax) {
+    constexpr bool SPK = ModelTraits<MODEL>::SPIKING;
+    const float dt = a.dt, tau = rp_.tau, tau_s = rp_.tau_s, tau_x = rp_.tau_x, alpha = rp_.alpha;
+    // readout / record gradient flowing into y_t[out]
+    float ro = 0.f, yout = 0.f;
+    if (a.e_t) {
+        if (a.out_var == RP_VAR_V) yout = v; else if (a.out_var == RP_VAR_S) yout = s;
+        else if (a.out_var == RP_VAR_X) yout = x;
+        else { if constexpr (!SPK) yout = rate_act<MODEL>(a.mp, i, v); }
+        if (a.out_mode == RP_OUT_DENSE) {
+            ro = __ldg(a.e_t + (size_t)b * a.N + i) * a.e_scale;
+        } else {
+#pragma unroll
+            for (int q = 0; q < RP_MAX_OUT; ++q) {
+                if (q < a.k) {
+                    const float e = __ldg(a.e_t + (size_t)b * a.k + q) * a.e_scale;
+                    ro = fmaf(__ldg(a.W_out + (size_t)q * a.N + i), e, ro);
+                    acc.add(RP_NUM_PARAMS + RP_MAX_IN + q, e * yout);
+                }
+            }
+        }
+    }
+    float dI = 0.f;
+    float nav, nas = 0.f, nax = 0.f;
+    if constexpr (!SPK) {
+        const float rg = rate_act_grad<MODEL>(a.mp, i, v);
+        nav = av * (1.0f - dt / tau) + rg * Z;
+        if (a.out_var == RP_VAR_V) nav += ro; else if (a.out_var == RP_VAR_R) nav += rg * ro;
+        dI = dt * av;
+        acc.add(RP_P_ETA, dt * av);
+        acc.add(RP_P_TAU, dt * av * v / (tau * tau));
+    } else {
+        const bool p = v >= a.theta;
+        const float gv = p ? 0.f : av;
+        const float d = 1.0f + a.slope * fabsf(v - a.theta);
+        const float sg = 1.0f / (d * d);                 // Spike.backward          nodes.py:478-481
+        if constexpr (MODEL == RP_LIF) {
+            nav = gv * (1.0f - dt / tau) + sg * as;
+            nas = as * (1.0f - dt / tau_s) + Z;
+            dI = a.in_target == 0 ? dt * gv : dt * as;
+            acc.add(RP_P_ETA, dt * gv);
+            acc.add(RP_P_TAU, dt * gv * v / (tau * tau));
+            acc.add(RP_P_TAU_S, as * s * dt / (tau_s * tau_s));
+        } else {
+            const float Iin = a.dparams[RP_P_TAU] ? input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i) : 0.f;
+            const float eta = ldp(a.mp, RP_P_ETA, i);
+            nav = gv * (1.0f + 2.0f * dt * v / tau) + sg * (as + alpha * ax);
+            nas = as * (1.0f - dt / tau_s) + Z;
+            dI = dt / tau * gv;
+            acc.add(RP_P_ETA, dI);
+            acc.add(RP_P_TAU, -dt * gv * (v * v + eta - x + Iin) / (tau * tau));
+            acc.add(RP_P_TAU_S, as * s * dt / (tau_s * tau_s));
+            if constexpr (MODEL == RP_QIF_SFA) {
+                nax = ax * (1.0f - dt / tau_x) - dI;
+                acc.add(RP_P_TAU_X, ax * x * dt / (tau_x * tau_x));
+                acc.add(RP_P_ALPHA, ax * (p ? 1.0f : 0.0f));
+            }
+        }
+        if (a.out_var == RP_VAR_V) nav += ro; else if (a.out_var == RP_VAR_S) nas += ro; else if (a.out_var == RP_VAR_X) nax += ro;
+    }
+    if (a.in_mode == RP_IN_PROJ && a.dW_in) {
+#pragma unroll
+        for (int j = 0; j < RP_MAX_IN; ++j)
+            if (j < a.m) acc.add(RP_NUM_PARAMS + j, dI * __ldg(a.x_t + (size_t)b * a.m + j));
+    }
+    av = nav; as = nas; ax = nax;
+    if (a.zero_after_post) { av = 0.f; as = 0.f; ax = 0.f; }
+    return dI;
+}
+
+// "pre" of reverse step t-1: g_{t-1} = dt * gate_{t-1} * a_t  and the source value r_{t-1};  (vm, sm) = (v, s) of y_{t-1}
+template <int MODEL>
+__device__ __forceinline__ void adj_pre_math(const AdjArgs& a, int i, float av, float vm, float sm, float& g, float& srcv) {
+    float gate = 1.0f;
+    if constexpr (ModelTraits<MODEL>::SPIKING) { gate = (vm >= a.theta) ? 0.f : 1.0f; srcv = sm; }
+    else srcv = rate_act<MODEL>(a.mp, i, vm);
+    g = a.dt * gate * av;
+}
+
+// scalar driver: loads, math, stores for element (neuron c.i, trial b)
+template <int MODEL>
+__device__ __forceinline__ void adj_element(const AdjArgs& a, AdjCtx<MODEL>& c, int b, float Z, float& g_out, float& src_out) {
+    constexpr int NSV = ModelTraits<MODEL>::NSV;
+    const int i = c.i;
+    const size_t plane = (size_t)a.B * a.N;
+    const size_t idx = (size_t)b * a.N + i;
+    float av = a.adj[idx];
+    float as = NSV > 1 ? a.adj[plane + idx] : 0.f;
+    float ax = NSV > 2 ? a.adj[2 * plane + idx] : 0.f;
+    if (a.do_post) {
+        const float v = __ldg(a.y_t + idx);
+        const float s = NSV > 1 ? __ldg(a.y_t + plane + idx) : 0.f;
+        const float x = NSV > 2 ? __ldg(a.y_t + 2 * plane + idx) : 0.f;
+        const AdjRowParams rp_{c.tau, c.tau_s, c.tau_x, c.alpha};
+        const RegAcc acc{c.acc};
+        const float dI = adj_post_math<MODEL>(a, rp_, acc, i, b, Z, v, s, x, av, as, ax);
+        if (a.g_x_t) a.g_x_t[idx] = dI;
+        a.adj[idx] = av;
+        if (NSV > 1) a.adj[plane + idx] = as;
+        if (NSV > 2) a.adj[2 * plane + idx] = ax;
+    }
+    g_out = 0.f; src_out = 0.f;
+    if (a.do_pre) {
+        const float vm = __ldg(a.y_tm1 + idx);
+        const float sm = NSV > 1 ? __ldg(a.y_tm1 + plane + idx) : 0.f;
+        float g, srcv;
+        adj_pre_math<MODEL>(a, i, av, vm, sm, g, srcv);
+        if (a.g) a.g[idx] = g;
+        if (a.src) a.src[idx] = srcv;
+        if (a.g_hi) {
+            float hi, lo;
+            split_tf32(g, hi, lo);
+            a.g_hi[(size_t)b * a.ld_g + i] = hi;
+            a.g_lo[(size_t)b * a.ld_g + i] = lo;
+        }
+        g_out = g; src_out = srcv;
+    }
+}
+
+// destination of accumulator q (nullptr: not requested); uniform across the grid
+__device__ __forceinline__ float* adj_acc_dst(const AdjArgs& a, int q, int i, size_t& off) {
+    float* dst = nullptr;
+    if (q < RP_NUM_PARAMS) { dst = a.dparams[q]; off = i; }
+    else if (q < RP_NUM_PARAMS + RP_MAX_IN) {
+        if (a.dW_in && (q - RP_NUM_PARAMS) < a.m) dst = a.dW_in;
+        off = (size_t)i * a.m + (q - RP_NUM_PARAMS);
+    } else {
+        if (a.dW_out && (q - RP_NUM_PARAMS - RP_MAX_IN) < a.k && a.out_mode == RP_OUT_READOUT) dst = a.dW_out;
+        off = (size_t)(q - RP_NUM_PARAMS - RP_MAX_IN) * a.N + i;
+    }
+    return dst;
+}
 
 template <int MODEL>
 __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
-    constexpr int NSV = ModelTraits<MODEL>::NSV;
-    constexpr bool SPK = ModelTraits<MODEL>::SPIKING;
-    constexpr int NACC = RP_NUM_PARAMS + RP_MAX_IN + RP_MAX_OUT;
     __shared__ float red[ADJ_TY][ADJ_TX + 1];
+    // block tile: 32 neurons x 64 trials.  The weight-gradient operands are wanted trial-major ([neuron][trial]); they are
+    // staged here and written with the trial index fastest so that both layouts are stored with full 128-byte rows.
+    __shared__ float tg[ADJ_TY * ADJ_BPT][ADJ_TX + 1];
+    __shared__ float ts[ADJ_TY * ADJ_BPT][ADJ_TX + 1];
     const int i = blockIdx.x * ADJ_TX + threadIdx.x;
-    const int b0 = blockIdx.y * (ADJ_TY * ADJ_BPT) + threadIdx.y;
-    const size_t plane = (size_t)a.B * a.N;
+    const int bblk = blockIdx.y * (ADJ_TY * ADJ_BPT);
     const bool valid_i = i < a.N;
-
-    float acc[NACC];
-#pragma unroll
-    for (int q = 0; q < NACC; ++q) acc[q] = 0.f;
-
-    float tau = 1.f, tau_s = 1.f, tau_x = 1.f, alpha = 0.f;
-    if (valid_i) {
-        tau = ldp(a.mp, RP_P_TAU, i);
-        if (SPK) tau_s = ldp(a.mp, RP_P_TAU_S, i);
-        if (MODEL == RP_QIF_SFA) { tau_x = ldp(a.mp, RP_P_TAU_X, i); alpha = ldp(a.mp, RP_P_ALPHA, i); }
-    }
-    const float dt = a.dt;
+    const bool transposed = a.do_pre && a.gT_hi != nullptr;
+    AdjCtx<MODEL> c;
+    adj_ctx_init<MODEL>(a, c, i);
 
     for (int l = 0; l < ADJ_BPT; ++l) {
-        const int b = b0 + l * ADJ_TY;
-        if (!valid_i || b >= a.B) continue;
-        const size_t idx = (size_t)b * a.N + i;
-        float av = a.adj[idx];
-        float as = NSV > 1 ? a.adj[plane + idx] : 0.f;
-        float ax = NSV > 2 ? a.adj[2 * plane + idx] : 0.f;
-
-        if (a.do_post) {
-            const float v = a.y_t[idx];
-            const float s = NSV > 1 ? a.y_t[plane + idx] : 0.f;
-            const float x = NSV > 2 ? a.y_t[2 * plane + idx] : 0.f;
-            const float Z = a.Z[(size_t)b * a.ldz + i];
-            // readout / record gradient flowing into y_t[out]
-            float ro = 0.f, yout = 0.f;
-            if (a.e_t) {
-                if (a.out_var == RP_VAR_V) yout = v; else if (a.out_var == RP_VAR_S) yout = s;
-                else if (a.out_var == RP_VAR_X) yout = x;
-                else { if constexpr (!SPK) yout = rate_act<MODEL>(a.mp, i, v); }
-                if (a.out_mode == RP_OUT_DENSE) {
-                    ro = a.e_t[idx] * a.e_scale;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < RP_MAX_OUT; ++q) {
-                        if (q < a.k) {
-                            const float e = __ldg(a.e_t + (size_t)b * a.k + q) * a.e_scale;
-                            ro = fmaf(__ldg(a.W_out + (size_t)q * a.N + i), e, ro);
-                            acc[RP_NUM_PARAMS + RP_MAX_IN + q] = fmaf(e, yout, acc[RP_NUM_PARAMS + RP_MAX_IN + q]);
-                        }
-                    }
-                }
-            }
-            float dI = 0.f;      // dL/d(input current of step t)
-            float nav, nas = 0.f, nax = 0.f;
-            if constexpr (!SPK) {
-                const float rg = rate_act_grad<MODEL>(a.mp, i, v);
-                nav = av * (1.0f - dt / tau) + rg * Z;
-                if (a.out_var == RP_VAR_V) nav += ro; else if (a.out_var == RP_VAR_R) nav += rg * ro;
-                dI = dt * av;
-                acc[RP_P_ETA] += dt * av;
-                acc[RP_P_TAU] += dt * av * v / (tau * tau);
-            } else {
-                const bool p = v >= a.theta;
-                const float gv = p ? 0.f : av;
-                const float d = 1.0f + a.slope * fabsf(v - a.theta);
-                const float sg = 1.0f / (d * d);                 // Spike.backward          nodes.py:478-481
-                if constexpr (MODEL == RP_LIF) {
-                    nav = gv * (1.0f - dt / tau) + sg * as;
-                    nas = as * (1.0f - dt / tau_s) + Z;
-                    dI = a.in_target == 0 ? dt * gv : dt * as;
-                    acc[RP_P_ETA] += dt * gv;
-                    acc[RP_P_TAU] += dt * gv * v / (tau * tau);
-                    acc[RP_P_TAU_S] += as * s * dt / (tau_s * tau_s);
-                } else {
-                    const float Iin = a.dparams[RP_P_TAU] ? input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i) : 0.f;
-                    const float eta = ldp(a.mp, RP_P_ETA, i);
-                    nav = gv * (1.0f + 2.0f * dt * v / tau) + sg * (as + alpha * ax);
-                    nas = as * (1.0f - dt / tau_s) + Z;
-                    dI = dt / tau * gv;
-                    acc[RP_P_ETA] += dI;
-                    acc[RP_P_TAU] -= dt * gv * (v * v + eta - x + Iin) / (tau * tau);
-                    acc[RP_P_TAU_S] += as * s * dt / (tau_s * tau_s);
-                    if constexpr (MODEL == RP_QIF_SFA) {
-                        nax = ax * (1.0f - dt / tau_x) - dI;
-                        acc[RP_P_TAU_X] += ax * x * dt / (tau_x * tau_x);
-                        acc[RP_P_ALPHA] += ax * (p ? 1.0f : 0.0f);
-                    }
-                }
-                if (a.out_var == RP_VAR_V) nav += ro; else if (a.out_var == RP_VAR_S) nas += ro; else if (a.out_var == RP_VAR_X) nax += ro;
-            }
-            if (a.in_mode == RP_IN_PROJ && a.dW_in) {
-#pragma unroll
-                for (int j = 0; j < RP_MAX_IN; ++j)
-                    if (j < a.m) acc[RP_NUM_PARAMS + j] = fmaf(dI, __ldg(a.x_t + (size_t)b * a.m + j), acc[RP_NUM_PARAMS + j]);
-            }
-            if (a.g_x_t) a.g_x_t[idx] = dI;
-            av = nav; as = nas; ax = nax;
-            if (a.zero_after_post) { av = 0.f; as = 0.f; ax = 0.f; }
-            a.adj[idx] = av;
-            if (NSV > 1) a.adj[plane + idx] = as;
-            if (NSV > 2) a.adj[2 * plane + idx] = ax;
-        }
-
-        if (a.do_pre) {
-            const float vm = a.y_tm1[idx];
-            float gate = 1.0f, srcv;
-            if constexpr (SPK) { gate = (vm >= a.theta) ? 0.f : 1.0f; srcv = a.y_tm1[plane + idx]; }
-            else srcv = rate_act<MODEL>(a.mp, i, vm);
-            const float g = dt * gate * av;
-            if (a.g) a.g[idx] = g;
-            if (a.src) a.src[idx] = srcv;
-            if (a.g_hi) {
-                float hi, lo;
-                split_tf32(g, hi, lo);
-                a.g_hi[(size_t)b * a.ld_g + i] = hi;
-                a.g_lo[(size_t)b * a.ld_g + i] = lo;
-                if (a.gT_hi) {
-                    a.gT_hi[(size_t)i * a.ld_t + a.t_col0 + b] = hi;
-                    a.gT_lo[(size_t)i * a.ld_t + a.t_col0 + b] = lo;
-                    split_tf32(srcv, hi, lo);
-                    a.srcT_hi[(size_t)i * a.ld_t + a.t_col0 + b] = hi;
-                    a.srcT_lo[(size_t)i * a.ld_t + a.t_col0 + b] = lo;
+        const int bl = l * ADJ_TY + threadIdx.y;
+        const int b = bblk + bl;
+        float g = 0.f, srcv = 0.f;
+        if (valid_i && b < a.B) adj_element<MODEL>(a, c, b, a.do_post ? a.Z[(size_t)b * a.ldz + i] : 0.f, g, srcv);
+        if (transposed) { tg[bl][threadIdx.x] = g; ts[bl][threadIdx.x] = srcv; }
+    }
+    if (transposed) {
+        __syncthreads();
+        // thread (tx, ty) -> trial bblk + tx (+32), neurons ty, ty+8, ... : 32 consecutive trials per warp store
+        for (int h = 0; h < (ADJ_TY * ADJ_BPT) / 32; ++h) {
+            const int bl = h * 32 + threadIdx.x;
+            const int b = bblk + bl;
+            for (int r = threadIdx.y; r < ADJ_TX; r += ADJ_TY) {
+                const int ii = blockIdx.x * ADJ_TX + r;
+                if (ii < a.N && b < a.B) {
+                    float hi, lo;
+                    const size_t off = (size_t)ii * a.ld_t + a.t_col0 + b;
+                    split_tf32(tg[bl][r], hi, lo);
+                    a.gT_hi[off] = hi; a.gT_lo[off] = lo;
+                    split_tf32(ts[bl][r], hi, lo);
+                    a.srcT_hi[off] = hi; a.srcT_lo[off] = lo;
                 }
             }
         }
@@ -445,23 +619,17 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
     if (a.do_post && a.any_param_grad) {
         // reduce the per-thread partial sums over the 8 trial lanes, then one atomic per (neuron, quantity)
 #pragma unroll
-        for (int q = 0; q < NACC; ++q) {
-            float* dst = nullptr;
-            if (q < RP_NUM_PARAMS) dst = a.dparams[q];
-            else if (q < RP_NUM_PARAMS + RP_MAX_IN) { if (a.dW_in && (q - RP_NUM_PARAMS) < a.m) dst = a.dW_in; }
-            else { if (a.dW_out && (q - RP_NUM_PARAMS - RP_MAX_IN) < a.k && a.out_mode == RP_OUT_READOUT) dst = a.dW_out; }
+        for (int q = 0; q < ADJ_NACC; ++q) {
+            size_t off = 0;
+            float* dst = adj_acc_dst(a, q, i, off);
             if (dst == nullptr) continue;     // uniform across the block
             __syncthreads();
-            red[threadIdx.y][threadIdx.x] = acc[q];
+            red[threadIdx.y][threadIdx.x] = c.acc[q];
             __syncthreads();
             if (threadIdx.y == 0 && valid_i) {
                 float t = 0.f;
 #pragma unroll
                 for (int r = 0; r < ADJ_TY; ++r) t += red[r][threadIdx.x];
-                size_t off;
-                if (q < RP_NUM_PARAMS) off = i;
-                else if (q < RP_NUM_PARAMS + RP_MAX_IN) off = (size_t)i * a.m + (q - RP_NUM_PARAMS);
-                else off = (size_t)(q - RP_NUM_PARAMS - RP_MAX_IN) * a.N + i;
                 atomicAdd(dst + off, t);
             }
         }
@@ -496,6 +664,39 @@ __global__ void __launch_bounds__(256) k_prepare_weights(int N, const float* __r
             if (WkT) WkT[(size_t)j * ldw + i] = w;
             if (WkT_hi) { float hi, lo; split_tf32(w, hi, lo); WkT_hi[(size_t)j * ldw + i] = hi; WkT_lo[(size_t)j * ldw + i] = lo; }
         }
+    }
+}
+
+// dW_out[q][i] = sum_{t,b} dL/do_t[b][q] * y_t[out][b][i]  over the stored checkpoints (one pass over the history, after the
+// reverse sweep; keeps the readout gradient out of the per-step adjoint epilogue).  grid = (ceil(N/128), t-splits)
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_readout_grad(int N, int B, int T, int S, int cutoff, int k, int out_var, const float* __restrict__ hist,
+                                                       const float* __restrict__ g_out_rec, ModelParams mp, float* dW_out) {
+    constexpr int NSV = ModelTraits<MODEL>::NSV;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const size_t plane = (size_t)B * N, slot = (size_t)NSV * plane;
+    const int per = (T + gridDim.y - 1) / gridDim.y;
+    const int t0 = blockIdx.y * per, t1 = min(T, t0 + per);
+    float acc[RP_MAX_OUT];
+#pragma unroll
+    for (int q = 0; q < RP_MAX_OUT; ++q) acc[q] = 0.f;
+    if (i < N) {
+        for (int t = t0; t < t1; ++t) {
+            const PWindow w = pwindow_of(t, T, S, cutoff);
+            if (w.j < 0) continue;
+            const float sc = 1.0f / (float)w.len;
+            const float* yt = hist + (size_t)t * slot + (out_var == RP_VAR_R ? 0 : (size_t)out_var * plane) + i;
+            const float* e = g_out_rec + (size_t)w.j * B * k;
+#pragma unroll 4
+            for (int b = 0; b < B; ++b) {
+                float y = __ldg(yt + (size_t)b * N);
+                if (out_var == RP_VAR_R) { if constexpr (!ModelTraits<MODEL>::SPIKING) y = rate_act<MODEL>(mp, i, y); }
+                y *= sc;
+#pragma unroll
+                for (int q = 0; q < RP_MAX_OUT; ++q) if (q < k) acc[q] = fmaf(__ldg(e + (size_t)b * k + q), y, acc[q]);
+            }
+        }
+        for (int q = 0; q < k; ++q) atomicAdd(dW_out + (size_t)q * N + i, acc[q]);
     }
 }
 

@@ -27,19 +27,6 @@ constexpr int PS_THREADS = 256;
 constexpr int PS_MAX_B = 4;
 constexpr int PS_MAX_ROWS = 64;      // owned neurons per CTA (rows * B <= 256 threads)
 
-struct PWindow { int j, first, close, len; };
-__host__ __device__ inline PWindow pwindow_of(int t, int T, int S, int cutoff) {
-    PWindow w{-1, 0, 0, 0};
-    if (t < cutoff) return w;
-    const int r0 = ((cutoff + S - 1) / S) * S;
-    int j, start, rec;
-    if (t <= r0) { j = 0; start = cutoff; rec = r0; }
-    else { j = (t - r0 + S - 1) / S; rec = r0 + j * S; start = rec - S + 1; }
-    if (rec >= T) return w;
-    w.j = j; w.first = (t == start); w.close = (t == rec); w.len = rec - start + 1;
-    return w;
-}
-
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
