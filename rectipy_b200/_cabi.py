@@ -54,6 +54,8 @@ _LIB = None
 
 
 def library_path() -> str:
+    if os.environ.get("RECTIPY_B200_LIB"):        # A/B builds of the same ABI (kernel tuning experiments)
+        return os.environ["RECTIPY_B200_LIB"]
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "librectipy_b200.so")
 
 

@@ -512,7 +512,8 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     const bool spk = spiking(d.model);
     const bool need_dW = a->dW != nullptr || a->dparams[RP_P_K] != nullptr;
 
-    if (need_dW && !p->dWraw) { if (plan_alloc(p, &p->dWraw, (size_t)N * p->ldw)) return 1; }
+    const int wg_slices = p->use_tc ? rp::TC_WGRAD_SPLITS : 1;
+    if (need_dW && !p->dWraw) { if (plan_alloc(p, &p->dWraw, (size_t)wg_slices * N * p->ldw)) return 1; }
     if (need_dW && p->use_tc) {
         size_t bytes = 0;
         if (rp::tc_workspace_ensure_wgrad(&p->tc, &bytes)) return fail("rp_backward: %s", rp::tc_last_error());
@@ -525,7 +526,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         ++p->launches;
         RP_LAUNCH_CHECK();
     }
-    if (need_dW) RP_CUDA(cudaMemsetAsync(p->dWraw, 0, (size_t)N * p->ldw * sizeof(float), st));
+    if (need_dW) RP_CUDA(cudaMemsetAsync(p->dWraw, 0, (size_t)wg_slices * N * p->ldw * sizeof(float), st));
     for (int q = 0; q < RP_NUM_PARAMS; ++q)
         if (a->dparams[q]) RP_CUDA(cudaMemsetAsync(a->dparams[q], 0, (size_t)N * sizeof(float), st));
     if (a->dW_in) RP_CUDA(cudaMemsetAsync(a->dW_in, 0, (size_t)N * d.n_in * sizeof(float), st));
@@ -642,7 +643,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         RP_LAUNCH_CHECK();
     }
     if (need_dW) {
-        rp::k_finish_wgrad<<<N, 256, 0, st>>>(N, p->dWraw, p->ldw, a->W, a->params[RP_P_K], kstride, a->dW, a->dparams[RP_P_K]);
+        rp::k_finish_wgrad<<<N, 256, 0, st>>>(N, p->dWraw, p->ldw, a->W, a->params[RP_P_K], kstride, a->dW, a->dparams[RP_P_K], wg_slices);
         ++p->launches;
         RP_LAUNCH_CHECK();
     }
@@ -658,7 +659,8 @@ int rp_plan_time_contraction(rp_plan* p, int which, int iters, float* avg_ms, do
     long long scratch_launches = 0;
     int kext = B;
     if (which == 2) {
-        if (!p->dWraw) { if (plan_alloc(p, &p->dWraw, (size_t)N * p->ldw)) return 1; RP_CUDA(cudaMemsetAsync(p->dWraw, 0, (size_t)N * p->ldw * sizeof(float), st)); }
+        const size_t nraw = (size_t)(p->use_tc ? rp::TC_WGRAD_SPLITS : 1) * N * p->ldw;
+        if (!p->dWraw) { if (plan_alloc(p, &p->dWraw, nraw)) return 1; RP_CUDA(cudaMemsetAsync(p->dWraw, 0, nraw * sizeof(float), st)); }
         if (p->use_tc) {
             size_t bytes = 0;
             if (rp::tc_workspace_ensure_wgrad(&p->tc, &bytes)) return fail("rp_plan_time_contraction: %s", rp::tc_last_error());

@@ -7,8 +7,9 @@
 // grad (x) r products when many trials are batched.  1e-5 parity (BASELINE.json) rules out single-pass TF32.
 //
 // Kernel shape: one CTA per 128(p) x BQ(q) tile, 6 warps:
-//   warp 0   TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B boxes of 32 fp32 = 128 B rows)
-//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (12 MMAs of K=8 per 32-wide K block)
+//   warp 0   TMA producer   (cp.async.bulk.tensor 2D; K blocks of 16 fp32 = 64-byte swizzled rows, 4-stage ring at BQ=256.
+//                            Measured: 2 stages of 32-wide blocks left the tensor pipe 75 % busy, 4 stages of 16 -> 124 vs 148 us)
+//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (6 MMAs of K=8 per 16-wide K block: lo.hi, hi.lo, hi.hi)
 //   warps 2-9 epilogue      (tcgen05.ld 32x32b -> fp32 register accumulators -> coalesced global stores, p fastest)
 // smem ring of full/empty mbarriers between producer and issuer; two TMEM accumulator buffers ping-pong between the
 // issuer and the epilogue (tcgen05.commit signals "chunk done", the epilogue's mbarrier.arrive signals "buffer drained").
@@ -27,10 +28,16 @@ inline const char* tc_last_error() { return tc_err_buf(); }
 #define RP_TC_FAIL(...) do { snprintf(rp::tc_err_buf(), 384, __VA_ARGS__); return 1; } while (0)
 
 constexpr int TC_BP = 128;          // tile rows (UMMA M, TMEM lanes)
-constexpr int TC_BK = 32;           // fp32 elements per K block = one 128-byte swizzle row
+#ifndef RP_TC_BK
+#define RP_TC_BK 16
+#endif
+constexpr int TC_BK = RP_TC_BK;     // fp32 elements per K block: 32 = one 128-byte swizzle row, 16 = one 64-byte swizzle row
+constexpr int TC_ROW_BYTES = TC_BK * 4;
+static_assert(TC_BK == 32 || TC_BK == 16, "K block must be one 128B or one 64B swizzle row");
 constexpr int TC_UMMA_K = 8;        // tf32 MMA K
 
 enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
+constexpr int TC_WGRAD_SPLITS = 2;
 
 // ---------------------------------------------------------------------------------------------------------
 // device helpers (inline PTX)
@@ -78,9 +85,9 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)((8u * TC_ROW_BYTES) >> 4) << 32;        // SBO: 8 rows of one swizzle row each
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(TC_BK == 32 ? 2 : 4) << 61;             // SWIZZLE_128B = 2, SWIZZLE_64B = 4
     return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format TF32 [7,10)=[10,13)=2,
@@ -115,15 +122,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // systematic -2.3e-5 relative bias at K=2048, growing linearly with K).  To stay at fp32 accuracy the K loop is cut into
 // chunks of TC_KC K-blocks; each chunk accumulates into one of two TMEM buffers from zero and the epilogue warps add the
 // finished chunk into fp32 registers with round-to-nearest while the next chunk is being multiplied.
-constexpr int TC_KC = 4;            // K blocks (of 32) per TMEM accumulation chunk
+constexpr int TC_KC = 128 / TC_BK;  // K blocks per TMEM accumulation chunk (k = 128 per chunk)
 constexpr int TC_EPI_WARPS = 8;     // two warps per TMEM lane quadrant, each owning half of the tile's columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 template <int BQ> struct TcCfg {
-    static constexpr int STAGES = (BQ == 256) ? 2 : 3;
-    static constexpr int A_BYTES = TC_BP * 128;
-    static constexpr int B_BYTES = BQ * 128;
+    static constexpr int A_BYTES = TC_BP * TC_ROW_BYTES;
+    static constexpr int B_BYTES = BQ * TC_ROW_BYTES;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;      // BK=32: 2 (BQ=256) / 3 ; BK=16: 4 / 6
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = 2 * BQ;
     static constexpr int COLS_PER_THREAD = BQ / 2;
@@ -139,9 +146,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // named barrier and RE-PARTITION the work: thread (w, l) takes the 4 consecutive neurons 4l..4l+3 and a contiguous block of
 // BQ/8 trials.  Every global access of the element-wise step is then a 16-byte vector over neurons (512 B per warp and trial),
 // loads of a batch are issued before any store, and the weight-gradient operands are written as 16-byte vectors over trials.
-struct EpiStore {                       // C[q*ldc + p] (+)= acc
+struct EpiStore {                       // C[q*ldc + p] (+)= acc ; split-K slices (blockIdx.z) go to C + z*split_stride
     static constexpr bool kStage = false;
-    float* C; int ldc; int accumulate;
+    float* C; int ldc; int accumulate; size_t split_stride;
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -351,6 +358,7 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p0 = blockIdx.x * TC_BP, q0 = blockIdx.y * BQ;
     const int num_chunks = (num_k_blocks + TC_KC - 1) / TC_KC;
+    const int kb0 = blockIdx.z * num_k_blocks;              // split-K: this CTA contracts K blocks [kb0, kb0 + num_k_blocks)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
@@ -375,10 +383,10 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                 mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                tma_load_2d(sa, &tmA_hi, &full_bar[stage], kb * TC_BK, p0);
-                tma_load_2d(sa + Cfg::A_BYTES, &tmA_lo, &full_bar[stage], kb * TC_BK, p0);
-                tma_load_2d(sa + 2 * Cfg::A_BYTES, &tmB_hi, &full_bar[stage], kb * TC_BK, q0);
-                tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tmB_lo, &full_bar[stage], kb * TC_BK, q0);
+                tma_load_2d(sa, &tmA_hi, &full_bar[stage], (kb0 + kb) * TC_BK, p0);
+                tma_load_2d(sa + Cfg::A_BYTES, &tmA_lo, &full_bar[stage], (kb0 + kb) * TC_BK, p0);
+                tma_load_2d(sa + 2 * Cfg::A_BYTES, &tmB_hi, &full_bar[stage], (kb0 + kb) * TC_BK, q0);
+                tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tmB_lo, &full_bar[stage], (kb0 + kb) * TC_BK, q0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -446,7 +454,7 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
         if constexpr (!Epi::kStage) {
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
-                float* dst = epi.C + (size_t)(q0 + half * CPT + j) * epi.ldc + p;
+                float* dst = epi.C + blockIdx.z * epi.split_stride + (size_t)(q0 + half * CPT + j) * epi.ldc + p;
                 float v = acc[j];
                 if (epi.accumulate) v += *dst;
                 *dst = v;
@@ -510,7 +518,7 @@ inline int tc_make_map(CUtensorMap* map, const float* base, int rows, int k_exte
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, TC_BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) RP_TC_FAIL("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d k=%d ld=%d box_rows=%d)", (int)r, rows, k_extent, ld, box_rows);
     return 0;
@@ -582,19 +590,21 @@ inline int tc_workspace_ensure_wgrad(TcWorkspace* w, size_t* bytes) {
 }
 
 template <class Epi>
-inline int tc_launch_epi(int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, const Epi& epi, cudaStream_t st) {
-    if (P % TC_BP || Q % bq || K % TC_BK) RP_TC_FAIL("tc_launch: extents P=%d Q=%d K=%d do not match tile %dx%dx%d", P, Q, K, TC_BP, bq, TC_BK);
+inline int tc_launch_epi(int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, const Epi& epi, cudaStream_t st, int k_splits = 1) {
+    if (P % TC_BP || Q % bq || K % (TC_BK * k_splits)) RP_TC_FAIL("tc_launch: extents P=%d Q=%d K=%d do not match tile %dx%dx%d (x%d splits)", P, Q, K, TC_BP, bq, TC_BK, k_splits);
     if (tc_set_attrs<Epi>()) return 1;
-    dim3 grid(P / TC_BP, Q / bq);
-    if (bq == 256) k_gemm_3xtf32<256, Epi><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], K / TC_BK, epi);
-    else           k_gemm_3xtf32<128, Epi><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], K / TC_BK, epi);
+    dim3 grid(P / TC_BP, Q / bq, k_splits);
+    const int kb = K / TC_BK / k_splits;
+    if (bq == 256) k_gemm_3xtf32<256, Epi><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi);
+    else           k_gemm_3xtf32<128, Epi><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) RP_TC_FAIL("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
-inline int tc_launch(int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, float* C, int ldc, int accumulate, cudaStream_t st) {
-    EpiStore e{C, ldc, accumulate};
-    return tc_launch_epi<EpiStore>(bq, P, Q, K, A, Bm, e, st);
+inline int tc_launch(int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, float* C, int ldc, int accumulate, cudaStream_t st,
+                     int k_splits = 1, size_t split_stride = 0) {
+    EpiStore e{C, ldc, accumulate, split_stride};
+    return tc_launch_epi<EpiStore>(bq, P, Q, K, A, Bm, e, st, k_splits);
 }
 // fused launches: forward step (rows = N, or N+128 when the readout rows are appended) and adjoint step
 template <int MODEL>
@@ -613,7 +623,9 @@ inline int tc_gemm(TcWorkspace* w, int mode, float* C, int ldc, int k_extent, in
     switch (mode) {
         case TC_FWD:   return tc_launch(w->bq_fwd, w->N, w->B, w->N, w->m_W, w->m_src, C, ldc, accumulate, st);
         case TC_DGRAD: return tc_launch(w->bq_fwd, w->N, w->B, w->N, w->m_WT, w->m_g, C, ldc, accumulate, st);
-        case TC_WGRAD: return tc_launch(w->bq_wg, w->N, w->N, k_extent, w->m_srcT, w->m_gT, C, ldc, accumulate, st);
+        // 2-way split-K into two accumulation slices: N=4096 gives 512 tiles = 3.46 waves of 148 SMs (86 % filled);
+        // 1024 work items = 6.92 waves (99 %).  The slices are summed by k_finish_wgrad.
+        case TC_WGRAD: return tc_launch(w->bq_wg, w->N, w->N, k_extent, w->m_srcT, w->m_gT, C, ldc, accumulate, st, TC_WGRAD_SPLITS, (size_t)w->N * ldc);
     }
     RP_TC_FAIL("tc_gemm: unknown mode %d", mode);
 }

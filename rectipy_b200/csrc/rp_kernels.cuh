@@ -589,12 +589,66 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
     AdjCtx<MODEL> c;
     adj_ctx_init<MODEL>(a, c, i);
 
-    for (int l = 0; l < ADJ_BPT; ++l) {
-        const int bl = l * ADJ_TY + threadIdx.y;
-        const int b = bblk + bl;
-        float g = 0.f, srcv = 0.f;
-        if (valid_i && b < a.B) adj_element<MODEL>(a, c, b, a.do_post ? a.Z[(size_t)b * a.ldz + i] : 0.f, g, srcv);
-        if (transposed) { tg[bl][threadIdx.x] = g; ts[bl][threadIdx.x] = srcv; }
+    // Loads of a batch of 4 trials are issued before any of its stores (the adjoint is updated in place, so the compiler
+    // cannot hoist them itself): ~30 independent 128-byte row requests in flight per warp.
+    constexpr int NSV = ModelTraits<MODEL>::NSV;
+    constexpr int BATCH = 4;
+    const size_t plane = (size_t)a.B * a.N;
+    const AdjRowParams rp_{c.tau, c.tau_s, c.tau_x, c.alpha};
+    const RegAcc racc{c.acc};
+    for (int l0 = 0; l0 < ADJ_BPT; l0 += BATCH) {
+        float av[BATCH], as[BATCH], ax[BATCH], v[BATCH], s[BATCH], x[BATCH], vm[BATCH], sm[BATCH], Z[BATCH];
+        bool ok[BATCH];
+#pragma unroll
+        for (int l = 0; l < BATCH; ++l) {
+            const int b = bblk + (l0 + l) * ADJ_TY + threadIdx.y;
+            ok[l] = valid_i && b < a.B;
+            const size_t idx = (size_t)b * a.N + i;
+            av[l] = as[l] = ax[l] = v[l] = s[l] = x[l] = vm[l] = sm[l] = Z[l] = 0.f;
+            if (ok[l]) {
+                av[l] = a.adj[idx];
+                if (NSV > 1) as[l] = a.adj[plane + idx];
+                if (NSV > 2) ax[l] = a.adj[2 * plane + idx];
+                if (a.do_post) {
+                    v[l] = __ldg(a.y_t + idx);
+                    if (NSV > 1) s[l] = __ldg(a.y_t + plane + idx);
+                    if (NSV > 2) x[l] = __ldg(a.y_t + 2 * plane + idx);
+                    Z[l] = a.Z[(size_t)b * a.ldz + i];
+                }
+                if (a.do_pre) {
+                    vm[l] = __ldg(a.y_tm1 + idx);
+                    if (NSV > 1) sm[l] = __ldg(a.y_tm1 + plane + idx);
+                }
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < BATCH; ++l) {
+            const int bl = (l0 + l) * ADJ_TY + threadIdx.y;
+            const int b = bblk + bl;
+            const size_t idx = (size_t)b * a.N + i;
+            float g = 0.f, srcv = 0.f;
+            if (ok[l]) {
+                if (a.do_post) {
+                    const float dI = adj_post_math<MODEL>(a, rp_, racc, i, b, Z[l], v[l], s[l], x[l], av[l], as[l], ax[l]);
+                    if (a.g_x_t) a.g_x_t[idx] = dI;
+                    a.adj[idx] = av[l];
+                    if (NSV > 1) a.adj[plane + idx] = as[l];
+                    if (NSV > 2) a.adj[2 * plane + idx] = ax[l];
+                }
+                if (a.do_pre) {
+                    adj_pre_math<MODEL>(a, i, av[l], vm[l], sm[l], g, srcv);
+                    if (a.g) a.g[idx] = g;
+                    if (a.src) a.src[idx] = srcv;
+                    if (a.g_hi) {
+                        float hi, lo;
+                        split_tf32(g, hi, lo);
+                        a.g_hi[(size_t)b * a.ld_g + i] = hi;
+                        a.g_lo[(size_t)b * a.ld_g + i] = lo;
+                    }
+                }
+            }
+            if (transposed) { tg[bl][threadIdx.x] = g; ts[bl][threadIdx.x] = srcv; }
+        }
     }
     if (transposed) {
         __syncthreads();
@@ -702,13 +756,14 @@ __global__ void __launch_bounds__(128) k_readout_grad(int N, int B, int T, int S
 
 // dW[i][j] = k_i * dWraw[i][j] ;  dk[i] = sum_j dWraw[i][j] * W[i][j]        (one block per row)
 __global__ void __launch_bounds__(256) k_finish_wgrad(int N, const float* __restrict__ dWraw, int ldr, const float* __restrict__ W,
-                                                       const float* __restrict__ kp, int k_stride, float* dW, float* dk) {
+                                                       const float* __restrict__ kp, int k_stride, float* dW, float* dk, int n_slices) {
     __shared__ float red[9];
     const int i = blockIdx.x;
     const float kv = __ldg(kp + (size_t)i * k_stride);
     float acc = 0.f;
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        const float r = dWraw[(size_t)i * ldr + j];
+        float r = dWraw[(size_t)i * ldr + j];
+        for (int z = 1; z < n_slices; ++z) r += dWraw[(size_t)z * N * ldr + (size_t)i * ldr + j];     // split-K slices
         if (dW) dW[(size_t)i * N + j] = kv * r;
         acc = fmaf(r, W[(size_t)i * N + j], acc);
     }
