@@ -4,6 +4,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <algorithm>
+#include "rp_persistent.cuh"
 
 #define RP_RLS_MAX_OUT 16
 
@@ -76,8 +79,131 @@ __global__ void __launch_bounds__(256) k_rls_p(int n, const float* __restrict__ 
     P[(size_t)r * n + c] = fmaf(-kp * z[r], z[c], P[(size_t)r * n + c]);
 }
 
+// ---- persistent variant ---------------------------------------------------------------------------------------------------
+// One cooperative launch for all T steps.  CTA c owns rows [c*R, c*R+R) of P in shared memory for the whole run; every CTA
+// keeps its own copy of W (k x n, updated identically everywhere) so the prediction needs no communication.  The only
+// per-step exchange is the vector z = beta^-1 P x (n floats), published with the flag-in-data protocol of rp_persistent.cuh.
+struct RlsArgs {
+    int T, n, k, npad, rows_per_cta, update_every;
+    float beta_inv;
+    const float* X; const float* Y;
+    float* W; float* P; float* loss; float* pred;
+    uint2* zbuf;            // [2][npad] {value, tag}, tags zeroed before the launch
+};
+
+__global__ void __launch_bounds__(PS_THREADS, 1) k_rls_persistent(RlsArgs a) {
+    extern __shared__ __align__(16) float rsm[];
+    const int n = a.n, npad = a.npad, k = a.k;
+    float* s_x = rsm;                      // [npad]
+    float* s_z = s_x + npad;               // [npad]
+    float* s_red = s_z + npad;             // [32 + 32]
+    float* s_W = s_red + 64;               // [k][npad]
+    float* s_P = s_W + (size_t)k * npad;   // [R][npad]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r0 = blockIdx.x * a.rows_per_cta;
+    const int R = max(0, min(a.rows_per_cta, n - r0));
+    for (int idx = tid; idx < k * npad; idx += PS_THREADS) { const int q = idx / npad, c = idx % npad; s_W[idx] = c < n ? a.W[(size_t)q * n + c] : 0.f; }
+    for (int idx = tid; idx < R * npad; idx += PS_THREADS) { const int r = idx / npad, c = idx % npad; s_P[idx] = c < n ? a.P[(size_t)(r0 + r) * n + c] : 0.f; }
+    if (tid < npad - n) { s_x[n + tid] = 0.f; s_z[n + tid] = 0.f; }
+    __syncthreads();
+    unsigned int tag = 0;
+    for (int t = 0; t < a.T; ++t) {
+        const bool upd = (t % a.update_every) == 0;
+        for (int c = tid; c < n; c += PS_THREADS) s_x[c] = __ldg(a.X + (size_t)t * n + c);
+        __syncthreads();
+        // prediction with the weights before this step's update: y_hat = W x  (warp q computes output q)
+        for (int q = warp; q < k; q += PS_THREADS / 32) {
+            float acc = 0.f;
+            for (int c = lane; c < n; c += 32) acc = fmaf(s_W[q * npad + c], s_x[c], acc);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) s_red[q] = acc;
+        }
+        if (upd) {
+            ++tag;
+            // z_r = beta^-1 * P[r][:] . x for the owned rows, published to everyone
+            for (int r = warp; r < R; r += PS_THREADS / 32) {
+                float acc = 0.f;
+                for (int c = lane; c < n; c += 32) acc = fmaf(s_P[r * npad + c], s_x[c], acc);
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) ll_store(a.zbuf + (size_t)(tag & 1) * npad + r0 + r, a.beta_inv * acc, tag);
+            }
+            ll_gather(a.zbuf + (size_t)(tag & 1) * npad, s_z, 1, n, npad, tag);
+            __syncthreads();
+            // x . z (every CTA computes it: n is small)
+            float part = 0.f;
+            for (int c = tid; c < n; c += PS_THREADS) part = fmaf(s_x[c], s_z[c], part);
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == 0) s_red[32 + warp] = part;
+            __syncthreads();
+            float xz = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < PS_THREADS / 32; ++w8) xz += s_red[32 + w8];
+            const float kappa = 1.0f / (1.0f + xz);
+            // P[r][c] -= kappa z_r z_c (owned rows) ;  W[q][c] += (y_q - kappa (y_hat_q + y_q xz)) z_c (all rows, every CTA)
+            for (int idx = tid; idx < R * n; idx += PS_THREADS) {
+                const int r = idx / n, c = idx - r * n;
+                s_P[r * npad + c] = fmaf(-kappa * s_z[r0 + r], s_z[c], s_P[r * npad + c]);
+            }
+            for (int idx = tid; idx < k * n; idx += PS_THREADS) {
+                const int q = idx / n, c = idx - q * n;
+                const float yq = __ldg(a.Y + (size_t)t * k + q);
+                s_W[q * npad + c] = fmaf(yq - kappa * (s_red[q] + yq * xz), s_z[c], s_W[q * npad + c]);
+            }
+        } else {
+            __syncthreads();
+        }
+        if (blockIdx.x == 0 && tid == 0) {
+            float ls = 0.f;
+            for (int q = 0; q < k; ++q) {
+                const float e = __ldg(a.Y + (size_t)t * k + q) - s_red[q];
+                ls = fmaf(e, e, ls);
+                if (a.pred) a.pred[(size_t)t * k + q] = s_red[q];
+            }
+            if (a.loss) a.loss[t] = ls;
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < R * n; idx += PS_THREADS) { const int r = idx / n, c = idx - r * n; a.P[(size_t)(r0 + r) * n + c] = s_P[r * npad + c]; }
+    if (blockIdx.x == 0) for (int idx = tid; idx < k * n; idx += PS_THREADS) { const int q = idx / n, c = idx - q * n; a.W[(size_t)q * n + c] = s_W[q * npad + c]; }
+}
+
+// returns 0 launched, 1 error, 2 shape does not fit the persistent kernel (caller falls back to per-step launches)
+inline int rls_run_persistent(int T, int n, int k, float beta_inv, const float* X, const float* Y, float* W, float* P,
+                              float* loss, float* pred, int update_every, cudaStream_t st) {
+    int dev = 0, sms = 0, coop = 0, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (!coop || getenv("RP_NO_PERSISTENT")) return 2;
+    const int npad = (n + 3) / 4 * 4;
+    int rows = (n + sms - 1) / sms;
+    rows = (rows + 7) / 8 * 8;
+    const int grid = (n + rows - 1) / rows;
+    const size_t smem = ((size_t)2 * npad + 64 + (size_t)k * npad + (size_t)rows * npad) * sizeof(float);
+    if (smem > (size_t)std::min(smem_max, 200 * 1024)) return 2;
+    if (cudaFuncSetAttribute(k_rls_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rls_persistent, PS_THREADS, smem);
+    if (occ < 1 || grid > occ * sms) return 2;
+    uint2* zbuf = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&zbuf), 2 * (size_t)npad * sizeof(uint2), st);
+    if (e != cudaSuccess) { snprintf(rls_err_buf(), 256, "cudaMallocAsync: %s", cudaGetErrorString(e)); return 1; }
+    cudaMemsetAsync(zbuf, 0, 2 * (size_t)npad * sizeof(uint2), st);
+    RlsArgs a{T, n, k, npad, rows, update_every, beta_inv, X, Y, W, P, loss, pred, zbuf};
+    void* args[] = {&a};
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_rls_persistent), dim3(grid), dim3(PS_THREADS), args, smem, st);
+    cudaFreeAsync(zbuf, st);
+    if (e != cudaSuccess) { snprintf(rls_err_buf(), 256, "cooperative launch: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
 inline int rls_run(int T, int n, int k, float beta_inv, const float* X, const float* Y, float* W, float* P,
                    float* loss, float* pred, int update_every, cudaStream_t st) {
+    if (T > 0) {
+        const int rc = rls_run_persistent(T, n, k, beta_inv, X, Y, W, P, loss, pred, update_every, st);
+        if (rc != 2) return rc;
+    }
     float* scratch = nullptr;   // z[n] + kappa
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&scratch), (size_t)(n + 1) * sizeof(float), st);
     if (e != cudaSuccess) { snprintf(rls_err_buf(), 256, "cudaMallocAsync: %s", cudaGetErrorString(e)); return 1; }

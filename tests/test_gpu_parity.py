@@ -278,3 +278,94 @@ def test_persistent_kernels_match_per_step_path(model, n, B, monkeypatch):
     print(model, n, B, errs)
     tol = 2e-5 if rate else 2e-3
     assert all(e <= tol for e in errs.values()), errs
+
+
+def test_full_size_properties_headline_config():
+    """BASELINE full size (QIF N=4096, 1024 trials): properties that need no CPU reference run.
+    (1) trials are independent: permuting the trial axis of the inputs permutes records and leaves dW unchanged (up to
+        summation order); (2) the adjoint is linear in the output gradient; (3) the 3xTF32 path reproduces the FFMA path's
+        spike rasters (counts identical, times within one step) on this size."""
+    import rectipy_b200 as rp
+    n, B, m, k, T, dt = 4096, 1024, 2, 3, 40, 1e-3
+    rng = np.random.default_rng(99)
+    W = (2.0 * rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32)
+    w_in, w_out = rng.standard_normal((n, m)).astype(np.float32), (rng.standard_normal((k, n)) / np.sqrt(n)).astype(np.float32)
+    etas = orc.lorentzian_etas(n).astype(np.float32)
+    t = np.arange(T, dtype=np.float32) * dt
+    x = (rng.uniform(5, 15, (1, B, 1)) * np.sin(2 * np.pi * np.array([3.0, 5.0])[None, None, :] * t[:, None, None]
+                                               + rng.uniform(0, 6.28, (1, B, m))) + 30.0).astype(np.float32)
+    y0 = np.concatenate([rng.uniform(-50, 99, (B, n)), np.zeros((B, n))], axis=1).astype(np.float32)   # spread phases -> spikes within T
+    gout = torch.tensor(rng.standard_normal((T, B, k)).astype(np.float32), device="cuda")
+
+    def run(prec, xin, y_init, g, vars_=False):
+        net = rp.Network(dt, device="cuda:0", batch=B, precision=prec)
+        node = net.add_diffeq_node("qif", "neuron_model_templates.spiking_neurons.qif.qif", weights=W, source_var="s", target_var="s_in",
+                                   input_var="I_ext", output_var="s", spike_var="spike", reset_var="v", op="qif_op",
+                                   node_vars={"eta": etas}, train_params=["weights"])
+        net.add_func_node("inp", m, "identity"); net.add_edge("inp", "qif", weights=w_in)
+        net.add_func_node("out", k, "identity"); net.add_edge("qif", "out", weights=w_out, train="gd")
+        node.reset(y_init)
+        rec = [("qif", "v", False)] if vars_ else []
+        obs = net.run(xin, verbose=False, enable_grad=True, record_vars=rec)
+        out = torch.stack(obs["out"])
+        (out * g).sum().backward()
+        res = dict(out=out.detach(), gW=node["weights"].grad.clone(), gout=net.get_edge("qif", "out").weights.grad.clone())
+        if vars_:
+            res["v"] = torch.stack(obs[("qif", "v")])
+        return res
+
+    base = run("3xtf32", x, y0, gout, vars_=True)
+    assert torch.isfinite(base["out"]).all() and torch.isfinite(base["gW"]).all()
+    n_spikes = int((base["v"] >= 100.0).sum())
+    assert n_spikes > 10000, n_spikes
+    # (1) permutation of trials
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+    pr = run("3xtf32", x[:, perm.numpy(), :], y0[perm.numpy()], gout[:, perm.cuda(), :])
+    assert torch.equal(pr["out"], base["out"][:, perm.cuda(), :])            # per-trial arithmetic is identical
+    assert rel_err(pr["gW"].cpu().numpy(), base["gW"].cpu().numpy()) < 1e-4
+    assert rel_err(pr["gout"].cpu().numpy(), base["gout"].cpu().numpy()) < 1e-4
+    # (2) linearity of the adjoint in dL/dout
+    lin = run("3xtf32", x, y0, 2.5 * gout)
+    assert rel_err(lin["gW"].cpu().numpy(), 2.5 * base["gW"].cpu().numpy()) < 1e-5
+    assert rel_err(lin["gout"].cpu().numpy(), 2.5 * base["gout"].cpu().numpy()) < 1e-5
+    # (3) tensor-core path vs FFMA path: spike rasters of a sample of trials
+    ff = run("fp32", x, y0, gout, vars_=True)
+    for b in (0, 511, 1023):
+        cmp_ = orc.compare_spikes((ff["v"][:, b, :] >= 100.0).cpu().numpy(), (base["v"][:, b, :] >= 100.0).cpu().numpy())
+        assert cmp_["total_ref"] > 0 and cmp_["neurons_count_mismatch"] == 0 and cmp_["max_shift"] <= 1, cmp_
+    assert rel_err(base["out"].cpu().numpy(), ff["out"].cpu().numpy()) < 1e-3
+
+
+def test_full_size_rate_network_directional_derivative():
+    """LI-tanh N=4096, 1024 trials on the tensor-core path: <dL/dW, D> from the adjoint equals the finite-difference
+    directional derivative of the loss (fp32 central difference, so 2 % tolerance)."""
+    import rectipy_b200 as rp
+    n, B, T, dt = 4096, 1024, 25, 1e-2
+    rng = np.random.default_rng(5)
+    W = (1.5 * rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32)
+    D = (rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32)
+    w_out = (rng.standard_normal((2, n)) / np.sqrt(n)).astype(np.float32)
+    x = torch.tensor(rng.standard_normal((T, B, n)).astype(np.float32), device="cuda")
+    tgt = torch.tensor(rng.standard_normal((T, B, 2)).astype(np.float32), device="cuda")
+
+    def loss_of(Wm, grad):
+        net = rp.Network(dt, device="cuda:0", batch=B, precision="3xtf32")
+        node = net.add_diffeq_node("rnn", "neuron_model_templates.rate_neurons.leaky_integrator.tanh", weights=Wm, source_var="tanh_op/r",
+                                   target_var="li_op/r_in", input_var="li_op/I_ext", output_var="li_op/v",
+                                   node_vars={"li_op/tau": 0.5, "li_op/k": 1.3}, train_params=["weights"] if grad else None)
+        net.add_func_node("out", 2, "identity"); net.add_edge("rnn", "out", weights=w_out)
+        obs = net.run(x, verbose=False, enable_grad=grad)
+        loss = torch.nn.functional.mse_loss(torch.stack(obs["out"]).double(), tgt.double(), reduction="sum")
+        if grad:
+            loss.backward()
+            return float(loss), node["weights"].grad.double()
+        return float(loss), None
+
+    l0, gW = loss_of(W, True)
+    analytic = float((gW * torch.tensor(D, device="cuda").double()).sum())
+    eps = 2e-2
+    lp, _ = loss_of(W + eps * D, False)
+    lm, _ = loss_of(W - eps * D, False)
+    numeric = (lp - lm) / (2 * eps)
+    print(f"directional derivative: adjoint {analytic:.6e}  finite difference {numeric:.6e}")
+    assert abs(analytic - numeric) <= 2e-2 * abs(numeric)
