@@ -23,6 +23,7 @@
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises the host.
  *   - Every entry point returns 0 on success, non-zero on error; rp_last_error() gives a thread-local message.
  *   - State layout ("SoA planes"): y[var][trial][neuron], var in {0:v, 1:s, 2:x}; plane stride = batch*n.
+ *     (ik_op: plane 2 holds the recovery variable u.)
  *   - A plan is not re-entrant: one host thread / one stream at a time per plan.
  */
 #ifndef RECTIPY_B200_H
@@ -32,16 +33,19 @@
 extern "C" {
 #endif
 
-#define RP_ABI_VERSION 1
+#define RP_ABI_VERSION 2
 #define RP_MAX_IN 8      /* max fused input-projection width  m (wider inputs: use RP_IN_DENSE)  */
 #define RP_MAX_OUT 8     /* max fused readout width           k (wider readouts: use RP_OUT_DENSE) */
 #define RP_MAX_SV 3
 #define RP_MAX_REC 4
 
 /* vector fields (neuron_model_templates/rate_neurons/leaky_integrator.yaml, spiking_neurons/{qif,lif}.yaml) */
-enum { RP_LI_TANH = 0, RP_LI_SIGMOID = 1, RP_QIF = 2, RP_QIF_SFA = 3, RP_LIF = 4 };
+enum { RP_LI_TANH = 0, RP_LI_SIGMOID = 1, RP_QIF = 2, RP_QIF_SFA = 3, RP_LIF = 4, RP_IK = 5 /* spiking_neurons/ik.yaml ik_op */ };
 /* parameter slots; each is a device pointer to 1 float (shared) or n floats (per neuron) */
-enum { RP_P_TAU = 0, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_RMAX, RP_P_SIG_S, RP_P_V0, RP_NUM_PARAMS };
+enum { RP_P_TAU = 0, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_RMAX, RP_P_SIG_S, RP_P_V0,
+       /* ik_op: */ RP_P_C, RP_P_VR, RP_P_VTH, RP_P_G, RP_P_ER, RP_P_B, RP_P_TAU_U, RP_P_KAPPA, RP_NUM_PARAMS };
+/* The coupling constant that scales the recurrent input (k for li/qif/lif, g for ik) is folded into the weights by the
+ * engine; its gradient is returned in its dparams slot as sum_j dWraw[i][j] * W[i][j]. */
 enum { RP_IN_NONE = 0, RP_IN_DENSE = 1, RP_IN_PROJ = 2 };   /* x_t is [B,n] current | [B,m] projected by W_in[n,m] */
 enum { RP_OUT_DENSE = 0, RP_OUT_READOUT = 1 };             /* record y[out] itself | W_out[k,n] . y[out]         */
 enum { RP_VAR_V = 0, RP_VAR_S = 1, RP_VAR_X = 2, RP_VAR_R = 3 }; /* RP_VAR_R = activation(v) of a rate node       */
@@ -83,7 +87,7 @@ typedef struct rp_fwd_args {
     int rec_var[RP_MAX_REC];     /* RP_VAR_V/S/X                                                */
     int rec_reduce[RP_MAX_REC];  /* 1: mean over neurons -> [n_rec,B]; 0: [n_rec,B,n]           */
     float* rec_buf[RP_MAX_REC];
-    float* history;         /* [(T+1),n_sv,B,n] state checkpoints for rp_backward, or NULL      */
+    float* history;         /* [(T+1),n_hist,B,n] state checkpoints for rp_backward (n_hist = rp_num_history_planes), or NULL */
 } rp_fwd_args;
 
 typedef struct rp_bwd_args {
@@ -108,7 +112,8 @@ typedef struct rp_bwd_args {
 
 int         rp_abi_version(void);
 const char* rp_last_error(void);
-int         rp_num_state_vars(int model);                       /* LI 1, QIF/LIF 2, QIF-SFA 3   */
+int         rp_num_state_vars(int model);                       /* LI 1, QIF/LIF 2, QIF-SFA/IK 3 */
+int         rp_num_history_planes(int model);                   /* planes per checkpoint slot: n_sv (+1 for ik: the recurrent drive) */
 int         rp_num_records(int T, int sampling_steps, int cutoff); /* records produced by a run  */
 
 int  rp_plan_create(const rp_desc* desc, rp_plan** plan);

@@ -110,8 +110,16 @@ def sin_inputs(rng, T, m, dt, amp=1.0, offset=0.0):
     return amp * np.sin(2 * np.pi * freqs[None, :] * t[:, None] + ph[None, :]) + offset
 
 
-def main():
+def main(only=None):
+    """`only`: regenerate a single case that has its own random stream (currently: ik_bptt)."""
     ref = ref_shim.import_reference()
+    if only is not None:
+        global save_case
+        _real_save = save_case
+
+        def save_case(ref_, name, spec):      # noqa: F811  -- skip every other case
+            if name == only:
+                _real_save(ref_, name, spec)
     os.makedirs(OUT, exist_ok=True)
     rng = np.random.default_rng(20261018)
 
@@ -183,6 +191,21 @@ def main():
     spec["targets"] = rng.standard_normal((T, k))
     save_case(ref, "lif_bptt", spec)
 
+    # ---- G6b: Izhikevich neurons (spiking_neurons/ik.yaml:8-30; regime of documentation/models/ik.py), BPTT -----------
+    n, T, m, k, dt = 20, 1200, 2, 2, 1e-1          # ms time scale: C=100, tau_u=33, spikes at 40 mV, reset to -60 mV
+    rng_main, rng = rng, np.random.default_rng(777)    # own stream: the case was added after the others were minted
+    spec = dict(model="ik", n=n, T=T, dt=dt, S=2, cutoff=0, grad=True,
+                W=np.abs(rng.standard_normal((n, n))) * 4.0 / n,
+                params=dict(eta=rng.uniform(60.0, 160.0, n), g=1.5, kappa=10.0, tau_s=6.0, E_r=0.0, b=-2.0, tau_u=33.33, k=0.7, C=100.0),
+                train_params=["weights", "eta", "g", "kappa", "tau_s", "b", "tau_u", "C", "k", "E_r"], train_in=True, train_out=True,
+                w_in=rng.standard_normal((n, m)) * 10.0, w_out=rng.standard_normal((k, n)) / np.sqrt(n),
+                inputs=sin_inputs(rng, T, m, dt * 1e-2, amp=3.0, offset=1.0),
+                spike_kwargs=dict(spike_threshold=40.0, spike_reset=-60.0), record_vars=[("v", False), ("u", True), ("s", False)])
+    spec["targets"] = rng.standard_normal((len(range(0, T, 2)), k))
+    if only in (None, "ik_bptt"):
+        save_case(ref, "ik_bptt", spec)
+    rng = rng_main
+
     # ---- G7: output activation + masked input edge (LinearMasked, edges.py:150-174) ---------------
     n, T, m, k, dt = 12, 200, 4, 3, 2e-2
     spec = dict(model="li_tanh", n=n, T=T, dt=dt, S=2, cutoff=0, grad=True,
@@ -233,4 +256,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

@@ -99,6 +99,21 @@ def field_lif(n: int) -> Tuple[Callable, List[str]]:
     return f, names
 
 
+def field_ik(n: int) -> Tuple[Callable, List[str]]:
+    """ik_op (spiking_neurons/ik.yaml:8-30), Izhikevich neuron with a conductance synapse:
+    v' = (k*(v-v_r)*(v-v_theta) - u + I_ext + eta + g*s_in*(E_r - v)) / C ;  u' = (b*(v-v_r) - u)/tau_u + kappa*spike ;
+    s' = -s/tau_s + spike.   State order = equation order: v, u, s."""
+    names = ["weights", "C", "k", "v_r", "v_theta", "eta", "g", "E_r", "b", "tau_u", "kappa", "tau_s", "I_ext", "spike"]
+
+    def f(t, y, weights, C, k, v_r, v_theta, eta, g, E_r, b, tau_u, kappa, tau_s, I_ext, spike):
+        v, u, s = y[:n], y[n:2 * n], y[2 * n:3 * n]
+        dv = (k * (v - v_r) * (v - v_theta) - u + I_ext + eta + g * (weights @ s) * (E_r - v)) / C
+        du = (b * (v - v_r) - u) / tau_u + kappa * spike
+        ds = -s / tau_s + spike
+        return torch.cat((dv, du, ds), 0)
+    return f, names
+
+
 #: template defaults (leaky_integrator.yaml:12-17,24-28; qif.yaml:13-22,33-35; lif.yaml:17-23)
 DEFAULTS = {
     "li_tanh":    dict(tau=10.0, k=1.0, eta=0.0),
@@ -106,14 +121,16 @@ DEFAULTS = {
     "qif":        dict(tau=1.0, k=1.0, tau_s=1.0, eta=-5.0),
     "qif_sfa":    dict(tau=1.0, k=1.0, tau_s=1.0, eta=-5.0, alpha=1.0, tau_x=10.0),
     "lif":        dict(tau=10.0, k=1.0, tau_s=0.5, eta=0.0),
+    "ik":         dict(C=100.0, k=0.7, v_r=-60.0, v_theta=-40.0, eta=0.0, g=1.0, E_r=0.0, b=-2.0, tau_u=33.33, kappa=10.0, tau_s=6.0),
 }
 #: initial values of the state variables, in state order
 INIT = {
     "li_tanh": [("v", 0.0)], "li_sigmoid": [("v", 0.0)],
     "qif": [("v", -2.0), ("s", 0.0)], "qif_sfa": [("v", -2.0), ("s", 0.0), ("x", 0.0)],
     "lif": [("v", 0.0), ("s", 0.0)],
+    "ik": [("v", -60.0), ("u", 0.0), ("s", 0.0)],
 }
-SPIKING = {"qif", "qif_sfa", "lif"}
+SPIKING = {"qif", "qif_sfa", "lif", "ik"}
 
 
 def build_field(model: str, n: int):
@@ -127,6 +144,8 @@ def build_field(model: str, n: int):
         return field_qif_sfa(n)
     if model == "lif":
         return field_lif(n)
+    if model == "ik":
+        return field_ik(n)
     raise ValueError(model)
 
 

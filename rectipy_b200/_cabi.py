@@ -9,11 +9,11 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-RP_ABI_VERSION = 1
+RP_ABI_VERSION = 2
 RP_MAX_IN, RP_MAX_OUT, RP_MAX_SV, RP_MAX_REC = 8, 8, 3, 4
-RP_LI_TANH, RP_LI_SIGMOID, RP_QIF, RP_QIF_SFA, RP_LIF = range(5)
+RP_LI_TANH, RP_LI_SIGMOID, RP_QIF, RP_QIF_SFA, RP_LIF, RP_IK = range(6)
 (RP_P_TAU, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_RMAX, RP_P_SIG_S, RP_P_V0,
- RP_NUM_PARAMS) = range(10)
+ RP_P_C, RP_P_VR, RP_P_VTH, RP_P_G, RP_P_ER, RP_P_B, RP_P_TAU_U, RP_P_KAPPA, RP_NUM_PARAMS) = range(18)
 RP_IN_NONE, RP_IN_DENSE, RP_IN_PROJ = range(3)
 RP_OUT_DENSE, RP_OUT_READOUT = range(2)
 RP_VAR_V, RP_VAR_S, RP_VAR_X, RP_VAR_R = range(4)
@@ -46,7 +46,7 @@ class rp_bwd_args(C.Structure):
 
 
 #: every symbol include/rectipy_b200.h declares (checked by tests/test_cabi.py)
-EXPORTS = ["rp_abi_version", "rp_last_error", "rp_num_state_vars", "rp_num_records", "rp_plan_create",
+EXPORTS = ["rp_abi_version", "rp_last_error", "rp_num_state_vars", "rp_num_history_planes", "rp_num_records", "rp_plan_create",
            "rp_plan_destroy", "rp_plan_workspace_bytes", "rp_plan_launch_count", "rp_forward", "rp_backward",
            "rp_rls_run", "rp_gemm_tn", "rp_plan_time_contraction"]
 
@@ -73,6 +73,8 @@ def load():
     lib.rp_last_error.restype = C.c_char_p
     lib.rp_num_state_vars.argtypes = [C.c_int]
     lib.rp_num_state_vars.restype = C.c_int
+    lib.rp_num_history_planes.argtypes = [C.c_int]
+    lib.rp_num_history_planes.restype = C.c_int
     lib.rp_num_records.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.rp_num_records.restype = C.c_int
     lib.rp_plan_create.argtypes = [C.POINTER(rp_desc), C.POINTER(C.c_void_p)]

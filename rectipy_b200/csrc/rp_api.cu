@@ -44,11 +44,12 @@ inline int nsv_of(int model) {
     switch (model) {
         case RP_LI_TANH: case RP_LI_SIGMOID: return 1;
         case RP_QIF: case RP_LIF: return 2;
-        case RP_QIF_SFA: return 3;
+        case RP_QIF_SFA: case RP_IK: return 3;
         default: return -1;
     }
 }
-inline bool spiking(int model) { return model == RP_QIF || model == RP_QIF_SFA || model == RP_LIF; }
+inline bool spiking(int model) { return model == RP_QIF || model == RP_QIF_SFA || model == RP_LIF || model == RP_IK; }
+inline int nhist_of(int model) { return nsv_of(model) + (model == RP_IK ? 1 : 0); }
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -102,6 +103,11 @@ rp::ModelParams make_params(const rp_plan* p, const float* const* params) {
 }
 
 int check_params(const rp_plan* p, const float* const* params) {
+    if (p->d.model == RP_IK) {
+        static const int need_ik[] = {RP_P_C, RP_P_K, RP_P_VR, RP_P_VTH, RP_P_ETA, RP_P_G, RP_P_ER, RP_P_B, RP_P_TAU_U, RP_P_KAPPA, RP_P_TAU_S};
+        for (int q : need_ik) if (!params[q]) return fail("ik_op parameter slot %d is NULL", q);
+        return 0;
+    }
     static const int need_li[] = {RP_P_TAU, RP_P_K, RP_P_ETA};
     for (int q : need_li) if (!params[q]) return fail("parameter slot %d (tau/k/eta) is NULL", q);
     if (spiking(p->d.model) && !params[RP_P_TAU_S]) return fail("parameter tau_s is NULL");
@@ -162,6 +168,7 @@ int gemm_fp32(rp_plan* plan, bool kmajor, int P, int Q, int K, const float* A, i
         case RP_QIF:        { constexpr int M_ = RP_QIF;        __VA_ARGS__; } break; \
         case RP_QIF_SFA:    { constexpr int M_ = RP_QIF_SFA;    __VA_ARGS__; } break; \
         case RP_LIF:        { constexpr int M_ = RP_LIF;        __VA_ARGS__; } break; \
+        case RP_IK:         { constexpr int M_ = RP_IK;         __VA_ARGS__; } break; \
         default: return fail("unknown model id %d", model);             \
     }
 
@@ -260,7 +267,8 @@ int persistent_forward(rp_plan* p, const rp_fwd_args* a, const rp::ModelParams& 
 int persistent_backward(rp_plan* p, const rp_bwd_args* a, const rp::ModelParams& mp, bool need_dW, cudaStream_t st) {
     const rp_desc& d = p->d;
     const int N = d.n, B = d.batch;
-    const int kstride = d.param_per_neuron[RP_P_K] ? 1 : 0;
+    const int fold = rp::fold_slot(d.model);
+    const int kstride = d.param_per_neuron[fold] ? 1 : 0;
     if (a->T == 0) {
         const size_t slot = (size_t)p->nsv * B * N;
         if (a->g_y0) {
@@ -281,7 +289,7 @@ int persistent_backward(rp_plan* p, const rp_bwd_args* a, const rp::ModelParams&
     pa.need_dW = need_dW ? 1 : 0;
     pa.x = a->x; pa.W_in = a->W_in; pa.W_out = a->W_out; pa.mp = mp; pa.history = a->history; pa.g_out_rec = a->g_out_rec; pa.g_yT = a->g_yT;
     pa.gbuf = reinterpret_cast<uint2*>(p->ps_vec); pa.Npad = p->ps_npad; pa.dWrawT = p->dWraw;
-    for (int q = 0; q < RP_NUM_PARAMS; ++q) pa.dparams[q] = (q == RP_P_K) ? nullptr : a->dparams[q];
+    for (int q = 0; q < RP_NUM_PARAMS; ++q) pa.dparams[q] = (q == fold) ? nullptr : a->dparams[q];
     pa.dW_in = a->dW_in; pa.dW_out = a->dW_out; pa.g_y0 = a->g_y0; pa.g_x = a->g_x; pa.barrier = p->ps_bar;
     void* args[] = {&pa};
     RP_DISPATCH_MODEL(d.model, {
@@ -291,7 +299,7 @@ int persistent_backward(rp_plan* p, const rp_bwd_args* a, const rp::ModelParams&
     ++p->launches;
     if (need_dW) {
         dim3 grid((N + 31) / 32, (N + 31) / 32);
-        rp::k_finish_wgrad_T<<<grid, 256, 0, st>>>(N, p->dWraw, p->ldw, a->W, a->params[RP_P_K], kstride, a->dW, a->dparams[RP_P_K]);
+        rp::k_finish_wgrad_T<<<grid, 256, 0, st>>>(N, p->dWraw, p->ldw, a->W, a->params[fold], kstride, a->dW, a->dparams[fold]);
         ++p->launches;
         RP_LAUNCH_CHECK();
     }
@@ -305,6 +313,7 @@ extern "C" {
 int rp_abi_version(void) { return RP_ABI_VERSION; }
 const char* rp_last_error(void) { return g_err; }
 int rp_num_state_vars(int model) { return nsv_of(model); }
+int rp_num_history_planes(int model) { return nsv_of(model) < 0 ? -1 : nhist_of(model); }
 
 int rp_num_records(int T, int S, int cutoff) {
     if (S <= 0 || T <= 0) return 0;
@@ -403,19 +412,21 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
     }
     if (check_params(p, a->params)) return 1;
     const rp::ModelParams mp = make_params(p, a->params);
-    const int kstride = d.param_per_neuron[RP_P_K] ? 1 : 0;
+    const int fold = rp::fold_slot(d.model);
+    const int kstride = d.param_per_neuron[fold] ? 1 : 0;
 
     // weights: fold k into W once per call
     {
         dim3 grid((N + 31) / 32, (N + 31) / 32);
-        if (!p->use_tc) rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[RP_P_K], kstride, p->Wk, nullptr, p->ldw, nullptr, nullptr, nullptr, nullptr);
-        else rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[RP_P_K], kstride, nullptr, nullptr, p->tc.ldk, p->tc.W_hi, p->tc.W_lo, nullptr, nullptr);
+        if (!p->use_tc) rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, p->Wk, nullptr, p->ldw, nullptr, nullptr, nullptr, nullptr);
+        else rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, nullptr, nullptr, p->tc.ldk, p->tc.W_hi, p->tc.W_lo, nullptr, nullptr);
         ++p->launches;
         RP_LAUNCH_CHECK();
     }
     if (p->persistent) return persistent_forward(p, a, mp, st);
     float* base = a->history ? a->history : p->pp;
-    auto slot_ptr = [&](int t) -> float* { return a->history ? base + (size_t)t * slot : base + (size_t)(t & 1) * slot; };
+    const size_t hslot = (size_t)nhist_of(d.model) * plane;          // checkpoint slot stride (ik: + recurrent-drive plane)
+    auto slot_ptr = [&](int t) -> float* { return a->history ? base + (size_t)t * hslot : base + (size_t)(t & 1) * slot; };
     RP_CUDA(cudaMemcpyAsync(slot_ptr(0), a->y0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
     const bool spk = spiking(d.model);
@@ -448,6 +459,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         fa.x_t = a->x ? a->x + (size_t)t * x_stride : nullptr; fa.W_in = a->W_in; fa.mp = mp;
         fa.src_next = (!spk && !p->use_tc) ? p->src : nullptr;
         fa.src_hi = p->use_tc ? p->tc.src_hi : nullptr; fa.src_lo = p->use_tc ? p->tc.src_lo : nullptr; fa.ld_src = p->tc.ldk;
+        fa.urec_out = (d.model == RP_IK && a->history) ? cur + (size_t)nsv * plane : nullptr;
         if (!p->use_tc) {
             // u[b][i] = sum_j (kW)[i][j] src_t[b][j], then the element-wise step
             const float* srcp = spk ? cur + plane : p->src;
@@ -508,9 +520,10 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     if (a->g_x && d.in_mode != RP_IN_DENSE) return fail("rp_backward: g_x requested without RP_IN_DENSE");
     if (check_params(p, a->params)) return 1;
     const rp::ModelParams mp = make_params(p, a->params);
-    const int kstride = d.param_per_neuron[RP_P_K] ? 1 : 0;
+    const int fold = rp::fold_slot(d.model);
+    const int kstride = d.param_per_neuron[fold] ? 1 : 0;
     const bool spk = spiking(d.model);
-    const bool need_dW = a->dW != nullptr || a->dparams[RP_P_K] != nullptr;
+    const bool need_dW = a->dW != nullptr || a->dparams[rp::fold_slot(d.model)] != nullptr;
 
     const int wg_slices = p->use_tc ? rp::TC_WGRAD_SPLITS : 1;
     if (need_dW && !p->dWraw) { if (plan_alloc(p, &p->dWraw, (size_t)wg_slices * N * p->ldw)) return 1; }
@@ -521,8 +534,8 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     }
     {
         dim3 grid((N + 31) / 32, (N + 31) / 32);
-        if (!p->use_tc) rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[RP_P_K], kstride, nullptr, p->WkT, p->ldw, nullptr, nullptr, nullptr, nullptr);
-        else rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[RP_P_K], kstride, nullptr, nullptr, p->tc.ldk, nullptr, nullptr, p->tc.WT_hi, p->tc.WT_lo);
+        if (!p->use_tc) rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, nullptr, p->WkT, p->ldw, nullptr, nullptr, nullptr, nullptr);
+        else rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, nullptr, nullptr, p->tc.ldk, nullptr, nullptr, p->tc.WT_hi, p->tc.WT_lo);
         ++p->launches;
         RP_LAUNCH_CHECK();
     }
@@ -537,6 +550,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
 
     const size_t x_stride = d.in_mode == RP_IN_DENSE ? plane : (d.in_mode == RP_IN_PROJ ? (size_t)B * d.n_in : 0);
     const size_t out_stride = d.out_mode == RP_OUT_READOUT ? (size_t)B * d.n_out : plane;
+    const size_t hslot = (size_t)nhist_of(d.model) * plane;
     const int tr = a->truncate_steps;
     const bool truncating = tr > 0 && tr < a->T;
     const int wg_chunk = p->use_tc ? p->tc.wgrad_chunk : 1;
@@ -548,7 +562,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     aa.adj = p->adj; aa.Z = p->u; aa.ldz = p->ldu; aa.W_in = a->W_in; aa.W_out = a->W_out; aa.mp = mp;
     if (!p->use_tc) { aa.g = p->g; aa.src = spk ? nullptr : p->src; }
     else { aa.g_hi = p->tc.g_hi; aa.g_lo = p->tc.g_lo; aa.ld_g = p->tc.ldk; aa.ld_t = p->tc.ldt; }
-    for (int q = 0; q < RP_NUM_PARAMS; ++q) aa.dparams[q] = (q == RP_P_K) ? nullptr : a->dparams[q];
+    for (int q = 0; q < RP_NUM_PARAMS; ++q) aa.dparams[q] = (q == fold) ? nullptr : a->dparams[q];
     aa.dW_in = a->dW_in; aa.dW_out = a->dW_out;
     aa.any_param_grad = (a->dW_in || a->dW_out) ? 1 : 0;
     for (int q = 0; q < RP_NUM_PARAMS; ++q) if (aa.dparams[q]) aa.any_param_grad = 1;
@@ -559,7 +573,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     // The fused adjoint epilogue is opt-in (RP_FUSED_ADJ=1): with one tile per CTA its element-wise work cannot overlap the
     // MMA main loop and runs at 8 warps/SM, which measured slower (340 us/step) than the contraction followed by the
     // full-occupancy k_adj_step (149 + ~60 us).  It becomes the default once tiles are software-pipelined per CTA.
-    const bool fused_adj = p->use_tc && getenv("RP_FUSED_ADJ") && !a->dW_in && !a->g_x && !(d.model == RP_LIF && d.in_target == 1);
+    const bool fused_adj = p->use_tc && getenv("RP_FUSED_ADJ") && !a->dW_in && !a->g_x && !(d.model == RP_LIF && d.in_target == 1) && d.model != RP_IK;
     dim3 agrid((N + rp::ADJ_TX - 1) / rp::ADJ_TX, (B + rp::ADJ_TY * rp::ADJ_BPT - 1) / (rp::ADJ_TY * rp::ADJ_BPT));
     dim3 ablock(rp::ADJ_TX, rp::ADJ_TY);
     int pending = 0;   // steps whose (g, src) columns sit in the tensor-core weight-gradient chunk
@@ -574,7 +588,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             if (!p->use_tc) {
                 if (gemm_fp32(p, true, N, B, N, p->WkT, p->ldw, p->g, N, p->u, p->ldu, 0, st, &p->launches)) return 1;
                 if (need_dW) {
-                    const float* srcp = spk ? a->history + (size_t)t * slot + plane : p->src;
+                    const float* srcp = spk ? a->history + (size_t)t * hslot + plane : p->src;
                     if (B <= 16) {
                         dim3 og((N + 255) / 256, N);
                         rp::k_outer_acc<<<og, 256, 0, st>>>(N, B, p->g, N, srcp, N, p->dWraw, p->ldw);
@@ -587,7 +601,8 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                 }
             }
             const Window w = window_of(t, a->T, a->sampling_steps, a->cutoff);
-            aa.y_t = a->history + (size_t)t * slot;
+            aa.y_t = a->history + (size_t)t * hslot;
+            aa.urec_t = d.model == RP_IK ? a->history + (size_t)t * hslot + (size_t)nsv * plane : nullptr;
             aa.x_t = a->x ? a->x + (size_t)t * x_stride : nullptr;
             aa.e_t = (a->g_out_rec && w.j >= 0) ? a->g_out_rec + (size_t)w.j * out_stride : nullptr;
             aa.e_scale = w.j >= 0 ? 1.0f / (float)w.len : 0.f;
@@ -595,7 +610,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             aa.zero_after_post = (truncating && t > 0 && t % tr == 0) ? 1 : 0;
         }
         if (aa.do_pre) {
-            aa.y_tm1 = a->history + (size_t)(t - 1) * slot;
+            aa.y_tm1 = a->history + (size_t)(t - 1) * hslot;
             if (p->use_tc && need_dW) {
                 aa.gT_hi = p->tc.gT_hi; aa.gT_lo = p->tc.gT_lo; aa.srcT_hi = p->tc.srcT_hi; aa.srcT_lo = p->tc.srcT_lo;
                 aa.t_col0 = pending * B;
@@ -643,7 +658,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         RP_LAUNCH_CHECK();
     }
     if (need_dW) {
-        rp::k_finish_wgrad<<<N, 256, 0, st>>>(N, p->dWraw, p->ldw, a->W, a->params[RP_P_K], kstride, a->dW, a->dparams[RP_P_K], wg_slices);
+        rp::k_finish_wgrad<<<N, 256, 0, st>>>(N, p->dWraw, p->ldw, a->W, a->params[fold], kstride, a->dW, a->dparams[fold], wg_slices);
         ++p->launches;
         RP_LAUNCH_CHECK();
     }

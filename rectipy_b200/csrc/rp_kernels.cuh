@@ -44,6 +44,11 @@ template <> struct ModelTraits<RP_LI_SIGMOID> { static constexpr int NSV = 1; st
 template <> struct ModelTraits<RP_QIF>        { static constexpr int NSV = 2; static constexpr bool SPIKING = true; };
 template <> struct ModelTraits<RP_QIF_SFA>    { static constexpr int NSV = 3; static constexpr bool SPIKING = true; };
 template <> struct ModelTraits<RP_LIF>        { static constexpr int NSV = 2; static constexpr bool SPIKING = true; };
+template <> struct ModelTraits<RP_IK>         { static constexpr int NSV = 3; static constexpr bool SPIKING = true; };   // planes v, s, u
+// checkpoint planes per step: the ik conductance synapse makes d(v')/dv depend on the recurrent drive, which is stored too
+template <int MODEL> struct HistPlanes { static constexpr int N = ModelTraits<MODEL>::NSV + (MODEL == RP_IK ? 1 : 0); };
+// parameter slot of the coupling constant that is folded into the weights
+__host__ __device__ constexpr int fold_slot(int model) { return model == RP_IK ? RP_P_G : RP_P_K; }
 
 // activation of the rate templates (leaky_integrator.yaml:20-36) and its derivative w.r.t. v
 template <int MODEL>
@@ -96,13 +101,14 @@ struct FwdStepArgs {
     float* src_hi;        // 3xTF32 path: source operand of the next step, split, [B][ld_src]
     float* src_lo;
     int ld_src;
+    float* urec_out;      // ik: checkpoint plane receiving the recurrent drive of this step [B][N], or nullptr
 };
 
 template <int MODEL>
 __device__ __forceinline__ void fwd_elem(const FwdStepArgs& a, int i, float u, float Iin,
                                          float v, float s, float x, float& v1, float& s1, float& x1) {
     const float dt = a.dt;
-    const float tau = ldp(a.mp, RP_P_TAU, i), eta = ldp(a.mp, RP_P_ETA, i);
+    const float tau = MODEL == RP_IK ? 1.f : ldp(a.mp, RP_P_TAU, i), eta = ldp(a.mp, RP_P_ETA, i);
     if constexpr (!ModelTraits<MODEL>::SPIKING) {
         // li_op: v' = -v/tau + k*r_in + I_ext + eta          (leaky_integrator.yaml:10)
         v1 = v + dt * (-v / tau + u + Iin + eta);
@@ -112,7 +118,15 @@ __device__ __forceinline__ void fwd_elem(const FwdStepArgs& a, int i, float u, f
         const bool p = v >= a.theta;                           // heaviside(v-theta, 1.0)   nodes.py:383,476
         const float pf = p ? 1.0f : 0.0f;
         float vt;
-        if constexpr (MODEL == RP_LIF) {
+        if constexpr (MODEL == RP_IK) {
+            // ik_op (ik.yaml:10-13): v' = (k (v-v_r)(v-v_theta) - u + I_ext + eta + g s_in (E_r - v)) / C
+            //                        u' = (b (v-v_r) - u)/tau_u + kappa*spike ;  s' = -s/tau_s + spike      (x holds u, u holds g*W.s)
+            const float C = ldp(a.mp, RP_P_C, i), kq = ldp(a.mp, RP_P_K, i), vr = ldp(a.mp, RP_P_VR, i), vth = ldp(a.mp, RP_P_VTH, i);
+            const float Er = ldp(a.mp, RP_P_ER, i), bb = ldp(a.mp, RP_P_B, i), tau_u = ldp(a.mp, RP_P_TAU_U, i), kappa = ldp(a.mp, RP_P_KAPPA, i);
+            vt = v + dt * ((kq * (v - vr) * (v - vth) - x + Iin + eta + u * (Er - v)) / C);
+            x1 = x + dt * ((bb * (v - vr) - x) / tau_u) + kappa * pf;
+            s1 = s + dt * (-s / tau_s) + pf;
+        } else if constexpr (MODEL == RP_LIF) {
             // lif_op: v' = -v/tau + k*s_in + I_ext + eta ; s' = -s/tau_s + spike + s_ext   (lif.yaml:10-15)
             const float Iv = a.in_target == 0 ? Iin : 0.f, Is = a.in_target == 1 ? Iin : 0.f;
             vt = v + dt * (-v / tau + u + Iv + eta);
@@ -153,7 +167,7 @@ struct FwdRow { float inv_tau, eta, inv_tau_s, inv_tau_x, alpha, wi0, wi1; };
 template <int MODEL>
 __device__ __forceinline__ FwdRow fwd_row(const FwdStepArgs& a, int i) {
     FwdRow r{1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f};
-    r.inv_tau = 1.0f / ldp(a.mp, RP_P_TAU, i);
+    if (MODEL != RP_IK) r.inv_tau = 1.0f / ldp(a.mp, RP_P_TAU, i);
     r.eta = ldp(a.mp, RP_P_ETA, i);
     if (ModelTraits<MODEL>::SPIKING) r.inv_tau_s = 1.0f / ldp(a.mp, RP_P_TAU_S, i);
     if (MODEL == RP_QIF_SFA) { r.inv_tau_x = 1.0f / ldp(a.mp, RP_P_TAU_X, i); r.alpha = ldp(a.mp, RP_P_ALPHA, i); }
@@ -209,6 +223,7 @@ __device__ __forceinline__ void fwd_element(const FwdStepArgs& a, int i, int b, 
     const float Iin = input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i);
     float v1, s1, x1;
     fwd_elem<MODEL>(a, i, u, Iin, v, s, x, v1, s1, x1);
+    if (MODEL == RP_IK && a.urec_out) a.urec_out[idx] = u;
     a.y_next[idx] = v1;
     if (NSV > 1) a.y_next[plane + idx] = s1;
     if (NSV > 2) a.y_next[2 * plane + idx] = x1;
@@ -361,6 +376,7 @@ struct AdjArgs {
     int do_post, do_pre, zero_after_post;   // zero_after_post: truncated-BPTT cut between step t-1 and t
     const float* y_t;      // history slot t      [nsv][B][N]  (post)
     const float* y_tm1;    // history slot t-1                 (pre)
+    const float* urec_t;   // ik: recurrent drive of step t [B][N] (checkpoint plane), else nullptr
     float* adj;            // [nsv][B][N] adjoint of the state, updated in place (t+1 -> t)
     const float* Z;        // [B][ldz]  (kW)^T g_t
     int ldz;
@@ -400,7 +416,7 @@ __device__ __forceinline__ void adj_ctx_init(const AdjArgs& a, AdjCtx<MODEL>& c,
 #pragma unroll
     for (int q = 0; q < ADJ_NACC; ++q) c.acc[q] = 0.f;
     if (i < a.N) {
-        c.tau = ldp(a.mp, RP_P_TAU, i);
+        if (MODEL != RP_IK) c.tau = ldp(a.mp, RP_P_TAU, i);
         if (ModelTraits<MODEL>::SPIKING) c.tau_s = ldp(a.mp, RP_P_TAU_S, i);
         if (MODEL == RP_QIF_SFA) { c.tau_x = ldp(a.mp, RP_P_TAU_X, i); c.alpha = ldp(a.mp, RP_P_ALPHA, i); }
     }
@@ -431,7 +447,7 @@ template <int MODEL>
 __device__ __forceinline__ AdjRowParams adj_row_params(const AdjArgs& a, int i) {
     AdjRowParams r{1.f, 1.f, 1.f, 0.f};
     if (i < a.N) {
-        r.tau = ldp(a.mp, RP_P_TAU, i);
+        if (MODEL != RP_IK) r.tau = ldp(a.mp, RP_P_TAU, i);
         if (ModelTraits<MODEL>::SPIKING) r.tau_s = ldp(a.mp, RP_P_TAU_S, i);
         if (MODEL == RP_QIF_SFA) { r.tau_x = ldp(a.mp, RP_P_TAU_X, i); r.alpha = ldp(a.mp, RP_P_ALPHA, i); }
     }
@@ -442,7 +458,7 @@ __device__ __forceinline__ AdjRowParams adj_row_params(const AdjArgs& a, int i) 
 // (v, s, x) = y_t.  Z = ((kW)^T g_t)[b][i].  Returns dI = dL/d(input current of step t).
 template <int MODEL, class Acc>
 __device__ __forceinline__ float adj_post_math(const AdjArgs& a, const AdjRowParams& rp_, const Acc& acc, int i, int b, float Z,
-                                               float v, float s, float x, float& av, float& as, float& ax) {
+                                               float v, float s, float x, float& av, float& as, float& ax, float urec = 0.f) {
     constexpr bool SPK = ModelTraits<MODEL>::SPIKING;
     const float dt = a.dt, tau = rp_.tau, tau_s = rp_.tau_s, tau_x = rp_.tau_x, alpha = rp_.alpha;
     // readout / record gradient flowing into y_t[out]
@@ -478,7 +494,29 @@ __device__ __forceinline__ float adj_post_math(const AdjArgs& a, const AdjRowPar
         const float gv = p ? 0.f : av;
         const float d = 1.0f + a.slope * fabsf(v - a.theta);
         const float sg = 1.0f / (d * d);                 // Spike.backward          nodes.py:478-481
-        if constexpr (MODEL == RP_LIF) {
+        if constexpr (MODEL == RP_IK) {
+            // x == u (recovery variable), ax == its adjoint; urec = g*(W s_t) of the forward step
+            const float C = ldp(a.mp, RP_P_C, i), kq = ldp(a.mp, RP_P_K, i), vr = ldp(a.mp, RP_P_VR, i), vth = ldp(a.mp, RP_P_VTH, i);
+            const float Er = ldp(a.mp, RP_P_ER, i), bb = ldp(a.mp, RP_P_B, i), tau_u = ldp(a.mp, RP_P_TAU_U, i), kappa = ldp(a.mp, RP_P_KAPPA, i);
+            const float eta = ldp(a.mp, RP_P_ETA, i);
+            const float pf = p ? 1.0f : 0.0f;
+            nav = gv * (1.0f + dt * (kq * (2.0f * v - vr - vth) - urec) / C) + ax * dt * bb / tau_u + sg * (as + kappa * ax);
+            nas = as * (1.0f - dt / tau_s) + Z;
+            nax = ax * (1.0f - dt / tau_u) - gv * dt / C;
+            dI = dt / C * gv;
+            const float Iin = a.dparams[RP_P_C] ? input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i) : 0.f;
+            const float q = kq * (v - vr) * (v - vth) - x + Iin + eta + urec * (Er - v);
+            acc.add(RP_P_ETA, dI);
+            acc.add(RP_P_C, -dt * gv * q / (C * C));
+            acc.add(RP_P_K, dt * gv * (v - vr) * (v - vth) / C);
+            acc.add(RP_P_VR, -dt * gv * kq * (v - vth) / C - ax * dt * bb / tau_u);
+            acc.add(RP_P_VTH, -dt * gv * kq * (v - vr) / C);
+            acc.add(RP_P_ER, dt * gv * urec / C);
+            acc.add(RP_P_B, ax * dt * (v - vr) / tau_u);
+            acc.add(RP_P_TAU_U, -ax * dt * (bb * (v - vr) - x) / (tau_u * tau_u));
+            acc.add(RP_P_KAPPA, ax * pf);
+            acc.add(RP_P_TAU_S, as * s * dt / (tau_s * tau_s));
+        } else if constexpr (MODEL == RP_LIF) {
             nav = gv * (1.0f - dt / tau) + sg * as;
             nas = as * (1.0f - dt / tau_s) + Z;
             dI = a.in_target == 0 ? dt * gv : dt * as;
@@ -519,6 +557,7 @@ __device__ __forceinline__ void adj_pre_math(const AdjArgs& a, int i, float av, 
     if constexpr (ModelTraits<MODEL>::SPIKING) { gate = (vm >= a.theta) ? 0.f : 1.0f; srcv = sm; }
     else srcv = rate_act<MODEL>(a.mp, i, vm);
     g = a.dt * gate * av;
+    if constexpr (MODEL == RP_IK) g *= (ldp(a.mp, RP_P_ER, i) - vm) / ldp(a.mp, RP_P_C, i);    // d v' / d(g W s) = dt (E_r - v) / C
 }
 
 // scalar driver: loads, math, stores for element (neuron c.i, trial b)
@@ -537,7 +576,8 @@ __device__ __forceinline__ void adj_element(const AdjArgs& a, AdjCtx<MODEL>& c, 
         const float x = NSV > 2 ? __ldg(a.y_t + 2 * plane + idx) : 0.f;
         const AdjRowParams rp_{c.tau, c.tau_s, c.tau_x, c.alpha};
         const RegAcc acc{c.acc};
-        const float dI = adj_post_math<MODEL>(a, rp_, acc, i, b, Z, v, s, x, av, as, ax);
+        const float urec = (MODEL == RP_IK && a.urec_t) ? __ldg(a.urec_t + idx) : 0.f;
+        const float dI = adj_post_math<MODEL>(a, rp_, acc, i, b, Z, v, s, x, av, as, ax, urec);
         if (a.g_x_t) a.g_x_t[idx] = dI;
         a.adj[idx] = av;
         if (NSV > 1) a.adj[plane + idx] = as;
@@ -597,14 +637,14 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
     const AdjRowParams rp_{c.tau, c.tau_s, c.tau_x, c.alpha};
     const RegAcc racc{c.acc};
     for (int l0 = 0; l0 < ADJ_BPT; l0 += BATCH) {
-        float av[BATCH], as[BATCH], ax[BATCH], v[BATCH], s[BATCH], x[BATCH], vm[BATCH], sm[BATCH], Z[BATCH];
+        float av[BATCH], as[BATCH], ax[BATCH], v[BATCH], s[BATCH], x[BATCH], vm[BATCH], sm[BATCH], Z[BATCH], ur[BATCH];
         bool ok[BATCH];
 #pragma unroll
         for (int l = 0; l < BATCH; ++l) {
             const int b = bblk + (l0 + l) * ADJ_TY + threadIdx.y;
             ok[l] = valid_i && b < a.B;
             const size_t idx = (size_t)b * a.N + i;
-            av[l] = as[l] = ax[l] = v[l] = s[l] = x[l] = vm[l] = sm[l] = Z[l] = 0.f;
+            av[l] = as[l] = ax[l] = v[l] = s[l] = x[l] = vm[l] = sm[l] = Z[l] = ur[l] = 0.f;
             if (ok[l]) {
                 av[l] = a.adj[idx];
                 if (NSV > 1) as[l] = a.adj[plane + idx];
@@ -614,6 +654,7 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
                     if (NSV > 1) s[l] = __ldg(a.y_t + plane + idx);
                     if (NSV > 2) x[l] = __ldg(a.y_t + 2 * plane + idx);
                     Z[l] = a.Z[(size_t)b * a.ldz + i];
+                    if (MODEL == RP_IK && a.urec_t) ur[l] = __ldg(a.urec_t + idx);
                 }
                 if (a.do_pre) {
                     vm[l] = __ldg(a.y_tm1 + idx);
@@ -629,7 +670,7 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
             float g = 0.f, srcv = 0.f;
             if (ok[l]) {
                 if (a.do_post) {
-                    const float dI = adj_post_math<MODEL>(a, rp_, racc, i, b, Z[l], v[l], s[l], x[l], av[l], as[l], ax[l]);
+                    const float dI = adj_post_math<MODEL>(a, rp_, racc, i, b, Z[l], v[l], s[l], x[l], av[l], as[l], ax[l], ur[l]);
                     if (a.g_x_t) a.g_x_t[idx] = dI;
                     a.adj[idx] = av[l];
                     if (NSV > 1) a.adj[plane + idx] = as[l];
@@ -728,7 +769,7 @@ __global__ void __launch_bounds__(128) k_readout_grad(int N, int B, int T, int S
                                                        const float* __restrict__ g_out_rec, ModelParams mp, float* dW_out) {
     constexpr int NSV = ModelTraits<MODEL>::NSV;
     const int i = blockIdx.x * 128 + threadIdx.x;
-    const size_t plane = (size_t)B * N, slot = (size_t)NSV * plane;
+    const size_t plane = (size_t)B * N, slot = (size_t)HistPlanes<MODEL>::N * plane;
     const int per = (T + gridDim.y - 1) / gridDim.y;
     const int t0 = blockIdx.y * per, t1 = min(T, t0 + per);
     float acc[RP_MAX_OUT];

@@ -185,15 +185,18 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
                 for (int j = 0; j < RP_MAX_IN; ++j) if (j < a.m) Iin = fmaf(w_in[j], __ldg(xt + j), Iin);
             }
             float v1, s1, x1;
-            fwd_elem<MODEL>(fa, i, s_u[r * PS_MAX_B + b], Iin, v, s, x, v1, s1, x1);
+            const float urec = s_u[r * PS_MAX_B + b];
+            fwd_elem<MODEL>(fa, i, urec, Iin, v, s, x, v1, s1, x1);
             float src1;
             if constexpr (SPK) src1 = s1; else src1 = rate_act<MODEL>(a.mp, i, v1);
             if (t + 1 < a.T) ll_store(a.srcbuf + (size_t)((t + 1) & 1) * B * Npad + (size_t)b * Npad + i, src1, (unsigned int)(t + 2));
             if (a.history) {
-                float* h = a.history + (size_t)(t + 1) * NSV * plane + idx;
+                constexpr int NH = HistPlanes<MODEL>::N;
+                float* h = a.history + (size_t)(t + 1) * NH * plane + idx;
                 h[0] = v1;
                 if (NSV > 1) h[plane] = s1;
                 if (NSV > 2) h[2 * plane] = x1;
+                if (NH > NSV) a.history[(size_t)t * NH * plane + (size_t)NSV * plane + idx] = urec;   // drive of step t, slot t
             }
             if (w.j >= 0) {
                 if (a.out_rec) {
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r0 = blockIdx.x * a.rows_per_cta;
     const int R = max(0, min(a.rows_per_cta, N - r0));
-    const size_t plane = (size_t)B * N, slot = (size_t)NSV * plane;
+    const size_t plane = (size_t)B * N, slot = (size_t)HistPlanes<MODEL>::N * plane;
 
     if (a.w_resident) for (int idx = tid; idx < R * a.ldw; idx += PS_THREADS) s_W[idx] = a.WkT[(size_t)r0 * a.ldw + idx];
     if (a.need_dW && a.dw_resident) for (int idx = tid; idx < R * a.ldw; idx += PS_THREADS) s_dW[idx] = 0.f;
@@ -290,23 +293,21 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
     const int r = own ? tid % R : 0, b = own ? tid / R : 0;
     const int i = r0 + r;                                 // owned neuron (called j in the header comment)
     float av = 0.f, as = 0.f, ax = 0.f;                   // adjoint of (v, s, x) at t+1
-    float tau = 1.f, tau_s = 1.f, tau_x = 1.f, alpha = 0.f, eta = 0.f;
-    float w_in[RP_MAX_IN], w_out[RP_MAX_OUT], d_in[RP_MAX_IN], d_out[RP_MAX_OUT];
-    float d_eta = 0.f, d_tau = 0.f, d_tau_s = 0.f, d_tau_x = 0.f, d_alpha = 0.f;
+    float acc[ADJ_NACC];                                  // parameter / edge gradient sums of the owned neuron
 #pragma unroll
-    for (int j = 0; j < RP_MAX_IN; ++j) { w_in[j] = 0.f; d_in[j] = 0.f; }
-#pragma unroll
-    for (int q = 0; q < RP_MAX_OUT; ++q) { w_out[q] = 0.f; d_out[q] = 0.f; }
+    for (int q = 0; q < ADJ_NACC; ++q) acc[q] = 0.f;
+    // the shared adjoint arithmetic (rp_kernels.cuh) reads its constants from an AdjArgs record
+    AdjArgs aa;
+    aa.N = N; aa.B = B; aa.m = a.m; aa.k = a.k; aa.in_mode = a.in_mode; aa.in_target = a.in_target;
+    aa.out_mode = a.out_mode; aa.out_var = a.out_var; aa.dt = a.dt; aa.theta = a.theta; aa.slope = a.slope;
+    aa.W_in = a.W_in; aa.W_out = a.W_out; aa.mp = a.mp; aa.dW_in = a.dW_in; aa.dW_out = a.dW_out;
+    for (int q = 0; q < RP_NUM_PARAMS; ++q) aa.dparams[q] = a.dparams[q];
+    aa.x_t = nullptr; aa.e_t = nullptr; aa.e_scale = 0.f; aa.zero_after_post = 0;
+    AdjRowParams rowp{1.f, 1.f, 1.f, 0.f};
     if (own) {
         const size_t idx = (size_t)b * N + i;
         if (a.g_yT) { av = a.g_yT[idx]; if (NSV > 1) as = a.g_yT[plane + idx]; if (NSV > 2) ax = a.g_yT[2 * plane + idx]; }
-        tau = ldp(a.mp, RP_P_TAU, i); eta = ldp(a.mp, RP_P_ETA, i);
-        if (SPK) tau_s = ldp(a.mp, RP_P_TAU_S, i);
-        if (MODEL == RP_QIF_SFA) { tau_x = ldp(a.mp, RP_P_TAU_X, i); alpha = ldp(a.mp, RP_P_ALPHA, i); }
-#pragma unroll
-        for (int j = 0; j < RP_MAX_IN; ++j) if (a.in_mode == RP_IN_PROJ && j < a.m) w_in[j] = a.W_in[(size_t)i * a.m + j];
-#pragma unroll
-        for (int q = 0; q < RP_MAX_OUT; ++q) if (a.out_mode == RP_OUT_READOUT && a.W_out && q < a.k) w_out[q] = a.W_out[(size_t)q * N + i];
+        rowp = adj_row_params<MODEL>(aa, i);
     }
     const float dt = a.dt;
     const int nvec = N >> 2;
@@ -316,9 +317,9 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
     auto make_g = [&](int tm1) -> float {
         const size_t idx = (size_t)b * N + i;
         const float vm = a.history[(size_t)tm1 * slot + idx];
-        float gate = 1.0f;
-        if constexpr (SPK) gate = (vm >= a.theta) ? 0.f : 1.0f;
-        return dt * gate * av;
+        float g, srcv;
+        adj_pre_math<MODEL>(aa, i, av, vm, 0.f, g, srcv);
+        return g;
     };
     // reverse step t consumes g_t carrying tag T - t (1, 2, ... as t runs down)
     if (own && a.T > 0) ll_store(a.gbuf + (size_t)((a.T - 1) & 1) * B * Npad + (size_t)b * Npad + i, make_g(a.T - 1), 1u);
@@ -385,93 +386,30 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
             const float v = yt[idx];
             const float s = NSV > 1 ? yt[plane + idx] : 0.f;
             const float x = NSV > 2 ? yt[2 * plane + idx] : 0.f;
-            const float Z = s_z[r * PS_MAX_B + b];
+            const float urec = HistPlanes<MODEL>::N > NSV ? yt[(size_t)NSV * plane + idx] : 0.f;
             const PWindow w = pwindow_of(t, a.T, a.S, a.cutoff);
-            float ro = 0.f;
-            if (a.g_out_rec && w.j >= 0) {
-                float yout;
-                if (a.out_var == RP_VAR_V) yout = v; else if (a.out_var == RP_VAR_S) yout = s;
-                else if (a.out_var == RP_VAR_X) yout = x;
-                else { if constexpr (!SPK) yout = rate_act<MODEL>(a.mp, i, v); else yout = 0.f; }
-                const float sc = 1.0f / (float)w.len;
-                if (a.out_mode == RP_OUT_DENSE) ro = a.g_out_rec[((size_t)w.j * B + b) * N + i] * sc;
-                else {
-#pragma unroll
-                    for (int q = 0; q < RP_MAX_OUT; ++q) {
-                        if (q < a.k) {
-                            const float e = __ldg(a.g_out_rec + ((size_t)w.j * B + b) * a.k + q) * sc;
-                            ro = fmaf(w_out[q], e, ro);
-                            d_out[q] = fmaf(e, yout, d_out[q]);
-                        }
-                    }
-                }
-            }
-            float Iin = 0.f;
-            if (a.in_mode == RP_IN_DENSE) Iin = __ldg(a.x + (size_t)t * plane + idx);
-            else if (a.in_mode == RP_IN_PROJ) {
-                const float* xt = a.x + ((size_t)t * B + b) * a.m;
-#pragma unroll
-                for (int j = 0; j < RP_MAX_IN; ++j) if (j < a.m) Iin = fmaf(w_in[j], __ldg(xt + j), Iin);
-            }
-            float dI, nav, nas = 0.f, nax = 0.f;
-            if constexpr (!SPK) {
-                const float rg = rate_act_grad<MODEL>(a.mp, i, v);
-                nav = av * (1.0f - dt / tau) + rg * Z;
-                if (a.out_var == RP_VAR_V) nav += ro; else if (a.out_var == RP_VAR_R) nav += rg * ro;
-                dI = dt * av;
-                d_eta += dt * av;
-                d_tau += dt * av * v / (tau * tau);
-            } else {
-                const bool p = v >= a.theta;
-                const float gv = p ? 0.f : av;
-                const float d = 1.0f + a.slope * fabsf(v - a.theta);
-                const float sg = 1.0f / (d * d);
-                if constexpr (MODEL == RP_LIF) {
-                    nav = gv * (1.0f - dt / tau) + sg * as;
-                    nas = as * (1.0f - dt / tau_s) + Z;
-                    dI = a.in_target == 0 ? dt * gv : dt * as;
-                    d_eta += dt * gv;
-                    d_tau += dt * gv * v / (tau * tau);
-                    d_tau_s += as * s * dt / (tau_s * tau_s);
-                } else {
-                    nav = gv * (1.0f + 2.0f * dt * v / tau) + sg * (as + alpha * ax);
-                    nas = as * (1.0f - dt / tau_s) + Z;
-                    dI = dt / tau * gv;
-                    d_eta += dI;
-                    d_tau -= dt * gv * (v * v + eta - x + Iin) / (tau * tau);
-                    d_tau_s += as * s * dt / (tau_s * tau_s);
-                    if constexpr (MODEL == RP_QIF_SFA) {
-                        nax = ax * (1.0f - dt / tau_x) - dI;
-                        d_tau_x += ax * x * dt / (tau_x * tau_x);
-                        d_alpha += ax * (p ? 1.0f : 0.0f);
-                    }
-                }
-                if (a.out_var == RP_VAR_V) nav += ro; else if (a.out_var == RP_VAR_S) nas += ro; else if (a.out_var == RP_VAR_X) nax += ro;
-            }
-            if (a.in_mode == RP_IN_PROJ && a.dW_in) {
-                const float* xt = a.x + ((size_t)t * B + b) * a.m;
-#pragma unroll
-                for (int j = 0; j < RP_MAX_IN; ++j) if (j < a.m) d_in[j] = fmaf(dI, __ldg(xt + j), d_in[j]);
-            }
+            const size_t estride = a.out_mode == RP_OUT_READOUT ? (size_t)B * a.k : plane;
+            aa.e_t = (a.g_out_rec && w.j >= 0) ? a.g_out_rec + (size_t)w.j * estride : nullptr;
+            aa.e_scale = w.j >= 0 ? 1.0f / (float)w.len : 0.f;
+            aa.x_t = a.x ? a.x + (size_t)t * (a.in_mode == RP_IN_DENSE ? plane : (size_t)B * a.m) : nullptr;
+            aa.zero_after_post = (truncating && t > 0 && t % a.truncate == 0) ? 1 : 0;
+            const RegAcc racc{acc};
+            const float dI = adj_post_math<MODEL>(aa, rowp, racc, i, b, s_z[r * PS_MAX_B + b], v, s, x, av, as, ax, urec);
             if (a.g_x) a.g_x[(size_t)t * plane + idx] = dI;
-            av = nav; as = nas; ax = nax;
-            if (truncating && t > 0 && t % a.truncate == 0) { av = 0.f; as = 0.f; ax = 0.f; }
             if (t > 0) ll_store(a.gbuf + (size_t)((t - 1) & 1) * B * Npad + (size_t)b * Npad + i, make_g(t - 1), (unsigned int)(a.T - t + 1));
         }
         __syncthreads();          // s_g / s_z / s_src are rewritten by the next step
     }
 
-    // write back: adjoint of y0, parameter gradients (sum over the B trial-threads of a neuron via atomics), dW^T rows
+    // write back: adjoint of y0, parameter / edge gradients (one thread per neuron and trial -> atomics across trials)
     if (own) {
         const size_t idx = (size_t)b * N + i;
         if (a.g_y0) { a.g_y0[idx] = av; if (NSV > 1) a.g_y0[plane + idx] = as; if (NSV > 2) a.g_y0[2 * plane + idx] = ax; }
-        if (a.dparams[RP_P_ETA]) atomicAdd(a.dparams[RP_P_ETA] + i, d_eta);
-        if (a.dparams[RP_P_TAU]) atomicAdd(a.dparams[RP_P_TAU] + i, d_tau);
-        if (a.dparams[RP_P_TAU_S]) atomicAdd(a.dparams[RP_P_TAU_S] + i, d_tau_s);
-        if (a.dparams[RP_P_TAU_X]) atomicAdd(a.dparams[RP_P_TAU_X] + i, d_tau_x);
-        if (a.dparams[RP_P_ALPHA]) atomicAdd(a.dparams[RP_P_ALPHA] + i, d_alpha);
-        if (a.dW_in) for (int j = 0; j < a.m; ++j) atomicAdd(a.dW_in + (size_t)i * a.m + j, d_in[j]);
-        if (a.dW_out) for (int q = 0; q < a.k; ++q) atomicAdd(a.dW_out + (size_t)q * N + i, d_out[q]);
+        for (int q = 0; q < ADJ_NACC; ++q) {
+            size_t off = 0;
+            float* dst = adj_acc_dst(aa, q, i, off);
+            if (dst != nullptr) atomicAdd(dst + off, acc[q]);
+        }
     }
     if (a.need_dW && a.dw_resident) {
         __syncthreads();

@@ -172,7 +172,8 @@ class EngineRun(torch.autograd.Function):
             buf = torch.empty((n_rec, B) if red else (n_rec, B, N), device=dev, dtype=torch.float32)
             recs.append(buf)
             a.rec_var[i], a.rec_reduce[i], a.rec_buf[i] = v, int(red), buf.data_ptr()
-        history = torch.empty((cfg.T + 1, nsv, B, N), device=dev, dtype=torch.float32) if needs_grad else None
+        nh = lib.rp_num_history_planes(key.model)
+        history = torch.empty((cfg.T + 1, nh, B, N), device=dev, dtype=torch.float32) if needs_grad else None
         a.history = _ptr(history)
         with torch.cuda.device(dev):
             abi.check(lib.rp_forward(plan.handle, C.byref(a), _stream()), "rp_forward")

@@ -125,8 +125,9 @@ class RateNet:
         # state: [n_sv, B, n]
         st = torch.empty((spec.n_sv, self.batch, self.n), dtype=torch.float32)
         over = getattr(self, "_init_override", {})
+        self._planes = spec.plane_order                       # engine plane of the i-th variable of the reference's y
         for i, (name, init) in enumerate(spec.state_vars):
-            st[i] = torch.as_tensor(np.asarray(over.get(name, init), dtype=np.float32))
+            st[self._planes[i]] = torch.as_tensor(np.asarray(over.get(name, init), dtype=np.float32))
         self._state = st.to(self.device)
         self._y0_template = self._state.clone()
 
@@ -138,9 +139,10 @@ class RateNet:
     @property
     def y(self) -> torch.Tensor:
         """Flat state vector `[n_sv*n]` (one trial) or `[B, n_sv*n]`, ordered like the reference's `y` (nodes.py:90)."""
+        st = self._state if self._planes == sorted(self._planes) else self._state[self._planes]
         if self.batch == 1:
-            return self._state.reshape(-1)
-        return self._state.permute(1, 0, 2).reshape(self.batch, -1)
+            return st.reshape(-1)
+        return st.permute(1, 0, 2).reshape(self.batch, -1)
 
     @y.setter
     def y(self, val):
@@ -158,6 +160,9 @@ class RateNet:
             st = t.reshape(self.batch, nsv, self.n).permute(1, 0, 2)
         else:
             raise RuntimeError(f"state of shape {tuple(t.shape)} does not match n_sv={nsv}, batch={self.batch}, n={self.n}")
+        if t.shape != (nsv, self.batch, self.n) and self._planes != sorted(self._planes):
+            inv = [self._planes.index(p) for p in range(nsv)]      # reference order -> engine planes
+            st = st[inv]
         self._state = st.contiguous().clone()
 
     @property
@@ -197,13 +202,13 @@ class RateNet:
             except KeyError:
                 raise KeyError(item)
             a, b = self._var_map[key]
-        i = a // self.n
+        i = self._planes[a // self.n]
         return self._state[i, 0] if self.batch == 1 else self._state[i]
 
     def var_index(self, name: str) -> int:
         """Index of a state variable in the engine layout (KeyError if `name` is not a state variable)."""
         key = self.spec.resolve(name, dict(self.spec.state_vars))
-        return self._var_map[key][0] // self.n
+        return self._planes[self._var_map[key][0] // self.n]
 
     def __call__(self, *args, **kwargs):
         return self.forward(*args, **kwargs)

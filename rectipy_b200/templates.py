@@ -39,6 +39,17 @@ class TemplateSpec:
     input_vars: Dict[str, int]              # "op/var" -> in_target code
     spike_var: Optional[str]                # "op/spike" for spiking templates
     out_vars: Dict[str, int] = field(default_factory=dict)   # "op/var" -> abi.RP_VAR_*
+    planes: Dict[str, int] = field(default_factory=dict)     # "op/var" -> engine state plane (0 v, 1 s, 2 x/u); the order of
+                                                             # `state_vars` is the reference's y order (equation order)
+    fold_param: str = ""                                     # "op/name" of the coupling constant folded into the weights
+
+    def plane_of(self, key: str) -> int:
+        return self.planes[key] if self.planes else [k for k, _ in self.state_vars].index(key)
+
+    @property
+    def plane_order(self) -> List[int]:
+        """engine plane of each state variable in reference order"""
+        return [self.plane_of(k) for k, _ in self.state_vars]
 
     @property
     def spiking(self) -> bool:
@@ -80,6 +91,8 @@ _QIF = [_canon("v' = (v^2 + eta + I_ext)/tau + k*s_in"), _canon("s' = -s/tau_s +
 _QIF_SFA = [_canon("v' = (v^2 + eta - x + I_ext)/tau + k*s_in"), _canon("s' = -s/tau_s + spike"),
             _canon("x' = -x/tau_x + alpha*spike")]
 _LIF = [_canon("v' = -v/tau + k*s_in + I_ext + eta"), _canon("s' = -s/tau_s + spike + s_ext")]
+_IK = [_canon("v' = (k*(v-v_r)*(v-v_theta) - u + I_ext + eta + g*s_in*(E_r - v)) / C"),
+       _canon("u' = (b*(v-v_r) - u) / tau_u + kappa*spike"), _canon("s' = -s/tau_s + spike")]
 
 _BUILTIN_OPS: Dict[str, OperatorDef] = {
     "li_op": OperatorDef("li_op", ["v' = -v/tau + k*r_in + I_ext + eta"],
@@ -99,12 +112,19 @@ _BUILTIN_OPS: Dict[str, OperatorDef] = {
                           dict(s=("output", 0.0), v=("variable", 0.0), tau=10.0, k=1.0, eta=0.0, tau_s=0.5,
                                I_ext=("input", 0.0), spike=("input", 0.0), s_in=("input", 0.0), s_ext=("input", 0.0))),
 }
+_BUILTIN_OPS["ik_op"] = OperatorDef(
+    "ik_op", ["v' = (k*(v-v_r)*(v-v_theta) - u + I_ext + eta + g*s_in*(E_r - v)) / C", "u' = (b*(v-v_r) - u) / tau_u + kappa*spike",
+              "s' = -s/tau_s + spike"],
+    dict(s=("output", 0.0), v=("variable", -60.0), u=("variable", 0.0), C=100.0, k=0.7, v_r=-60.0, v_theta=-40.0, eta=0.0, g=1.0,
+         E_r=0.0, b=-2.0, tau_u=33.33, kappa=10.0, tau_s=6.0, I_ext=("input", 0.0), spike=("input", 0.0), s_in=("input", 0.0)))
 _BUILTIN_NODES = {"tanh": ["li_op", "tanh_op"], "sigmoid": ["li_op", "sigmoid_op"], "qif": ["qif_op"],
-                  "qif_sfa": ["qif_sfa_op"], "lif": ["lif_op"]}
-_BUILTIN_MODULES = {"leaky_integrator": ["tanh", "sigmoid"], "qif": ["qif", "qif_sfa"], "lif": ["lif"]}
+                  "qif_sfa": ["qif_sfa_op"], "lif": ["lif_op"], "ik": ["ik_op"]}
+_BUILTIN_MODULES = {"leaky_integrator": ["tanh", "sigmoid"], "qif": ["qif", "qif_sfa"], "lif": ["lif"], "ik": ["ik"]}
 
 _SLOT = dict(tau=abi.RP_P_TAU, k=abi.RP_P_K, eta=abi.RP_P_ETA, tau_s=abi.RP_P_TAU_S, tau_x=abi.RP_P_TAU_X,
-             alpha=abi.RP_P_ALPHA, r_max=abi.RP_P_RMAX, s=abi.RP_P_SIG_S, v0=abi.RP_P_V0)
+             alpha=abi.RP_P_ALPHA, r_max=abi.RP_P_RMAX, s=abi.RP_P_SIG_S, v0=abi.RP_P_V0,
+             C=abi.RP_P_C, v_r=abi.RP_P_VR, v_theta=abi.RP_P_VTH, g=abi.RP_P_G, E_r=abi.RP_P_ER, b=abi.RP_P_B,
+             tau_u=abi.RP_P_TAU_U, kappa=abi.RP_P_KAPPA)
 
 
 def _val(v) -> float:
@@ -128,6 +148,15 @@ def _spec_from_ops(ops: List[OperatorDef]) -> TemplateSpec:
             ops=(main.name, act.name), state_vars=[(f"{main.name}/v", _val(mv["v"]))], params=params,
             source_var=f"{act.name}/r", target_var=f"{main.name}/r_in", input_vars={f"{main.name}/I_ext": 0},
             spike_var=None, out_vars={f"{main.name}/v": abi.RP_VAR_V, f"{act.name}/r": abi.RP_VAR_R})
+    if len(ops) == 1 and eqs[0] == _IK:
+        o = main.name
+        pn = ["C", "k", "v_r", "v_theta", "eta", "g", "E_r", "b", "tau_u", "kappa", "tau_s"]
+        return TemplateSpec(
+            name="ik", model=abi.RP_IK, ops=(o,), state_vars=[(f"{o}/{v}", _val(mv[v])) for v in ("v", "u", "s")],
+            params={f"{o}/{p}": (_SLOT[p], _val(mv[p])) for p in pn},
+            source_var=f"{o}/s", target_var=f"{o}/s_in", input_vars={f"{o}/I_ext": 0}, spike_var=f"{o}/spike",
+            out_vars={f"{o}/v": abi.RP_VAR_V, f"{o}/s": abi.RP_VAR_S, f"{o}/u": abi.RP_VAR_X},
+            planes={f"{o}/v": 0, f"{o}/s": 1, f"{o}/u": 2}, fold_param=f"{o}/g")
     if len(ops) == 1 and eqs[0] in (_QIF, _QIF_SFA, _LIF):
         o = main.name
         if eqs[0] == _QIF:
@@ -146,7 +175,7 @@ def _spec_from_ops(ops: List[OperatorDef]) -> TemplateSpec:
             out_vars={f"{o}/{v}": i for i, v in enumerate(sv)})
     raise NotImplementedError(
         "rectipy_b200: the operator equations " + str([op.equations for op in ops]) + " do not match any vector field "
-        "compiled into the engine (li_op+tanh_op, li_op+sigmoid_op, qif_op, qif_sfa_op, lif_op).")
+        "compiled into the engine (li_op+tanh_op, li_op+sigmoid_op, qif_op, qif_sfa_op, lif_op, ik_op).")
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -18,7 +18,7 @@ if os.path.join(ROOT, "oracle") not in sys.path:
 import rectipy_oracle as orc  # noqa: E402
 
 TD = {"float64": torch.float64, "float32": torch.float32}
-RUN_CASES = ["li_tanh_bptt", "li_sigmoid_fwd", "qif_bptt", "qif_sfa_fwd", "qif_sfa_bptt_trunc", "lif_bptt",
+RUN_CASES = ["li_tanh_bptt", "li_sigmoid_fwd", "qif_bptt", "qif_sfa_fwd", "qif_sfa_bptt_trunc", "lif_bptt", "ik_bptt",
              "li_tanh_masked_softmax"]
 
 
@@ -105,6 +105,7 @@ TEMPLATE_PATH = {
     "qif": ("neuron_model_templates.spiking_neurons.qif.qif", "qif_op", "s", "s_in"),
     "qif_sfa": ("neuron_model_templates.spiking_neurons.qif.qif_sfa", "qif_sfa_op", "s", "s_in"),
     "lif": ("neuron_model_templates.spiking_neurons.lif.lif", "lif_op", "s", "s_in"),
+    "ik": ("neuron_model_templates.spiking_neurons.ik.ik", "ik_op", "s", "s_in"),
 }
 
 

@@ -30,7 +30,8 @@ def test_header_symbols_are_exported(lib):
 def test_host_only_entry_points(lib):
     from rectipy_b200 import _cabi as abi
     assert lib.rp_abi_version() == abi.RP_ABI_VERSION
-    assert [lib.rp_num_state_vars(m) for m in range(5)] == [1, 1, 2, 3, 2]
+    assert [lib.rp_num_state_vars(m) for m in range(6)] == [1, 1, 2, 3, 2, 3]
+    assert [lib.rp_num_history_planes(m) for m in range(6)] == [1, 1, 2, 3, 2, 4]
     assert lib.rp_num_state_vars(99) == -1
     # record counting must match Network.run's windowing (network.py:590-597)
     for T, S, cut in [(100, 1, 0), (100, 2, 0), (600, 5, 7), (10, 3, 9), (10, 3, 10), (5, 100, 0), (0, 1, 0), (40, 4, 39)]:

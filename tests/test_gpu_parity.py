@@ -369,3 +369,38 @@ def test_full_size_rate_network_directional_derivative():
     numeric = (lp - lm) / (2 * eps)
     print(f"directional derivative: adjoint {analytic:.6e}  finite difference {numeric:.6e}")
     assert abs(analytic - numeric) <= 2e-2 * abs(numeric)
+
+
+def test_izhikevich_batched_paths_agree():
+    """ik_op on all three execution paths (persistent B=2, per-step FFMA B=20, tcgen05 B=128 N=128) vs the fp64 oracle."""
+    import rectipy_b200 as rp
+    n, m, k, T, dt = 128, 2, 2, 300, 1e-1
+    rng = np.random.default_rng(12)
+    W = np.abs(rng.standard_normal((n, n))) * 4.0 / n
+    w_in, w_out = rng.standard_normal((n, m)) * 10.0, rng.standard_normal((k, n)) / np.sqrt(n)
+    etas = rng.uniform(60.0, 160.0, n)
+    params = dict(eta=etas, g=1.5)
+    for B, prec in ((2, "fp32"), (20, "fp32"), (128, "3xtf32")):
+        x = (3.0 * np.sin(2 * np.pi * rng.uniform(5, 30, (1, B, m)) * (np.arange(T) * dt * 1e-3)[:, None, None]) + 1.0)
+        net = rp.Network(dt, device="cuda:0", batch=B, precision=prec)
+        node = net.add_diffeq_node("ik", "neuron_model_templates.spiking_neurons.ik.ik", weights=W, source_var="s", target_var="s_in",
+                                   input_var="I_ext", output_var="s", spike_var="spike", reset_var="v", op="ik_op",
+                                   node_vars={"eta": etas, "g": 1.5}, spike_threshold=40.0, spike_reset=-60.0,
+                                   train_params=["weights", "eta", "g", "kappa"])
+        net.add_func_node("inp", m, "identity"); net.add_edge("inp", "ik", weights=w_in)
+        net.add_func_node("out", k, "identity"); net.add_edge("ik", "out", weights=w_out, train="gd")
+        obs = net.run(x, sampling_steps=3, verbose=False, enable_grad=True, record_vars=[("ik", "u", False)])
+        out = torch.stack(obs["out"])
+        out.square().sum().backward()
+        for b in (0, B - 1):
+            onode = orc.make_node("ik", n, W, dt, params=params, dtype=torch.float64, train_params=["weights", "eta", "g", "kappa"],
+                                  spike_threshold=40.0, spike_reset=-60.0)
+            onet = orc.OracleNet(onode, w_in=torch.tensor(w_in), w_out=torch.tensor(w_out, requires_grad=True))
+            r = onet.run(torch.tensor(x[:, b, :]), sampling_steps=3, record_vars=[("u", False)], enable_grad=False)
+            ref = torch.stack(r["out"]).numpy()
+            got = out.detach().cpu().numpy().reshape(ref.shape[0], B, k)[:, b, :]
+            assert rel_err(got, ref) < 1e-4, (B, prec, b, rel_err(got, ref))
+            u_ref = torch.stack(r["vars"]["u"]).numpy()
+            u_got = obs.to_numpy(("ik", "u")).reshape(ref.shape[0], B, n)[:, b, :]
+            assert rel_err(u_got, u_ref) < 1e-4
+        assert all(torch.isfinite(p.grad).all() for p in net.parameters())

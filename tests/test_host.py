@@ -17,7 +17,8 @@ def test_builtin_templates_resolve():
     for path, name, nsv, model in [(TANH, "li_tanh", 1, abi.RP_LI_TANH),
                                    ("neuron_model_templates.rate_neurons.leaky_integrator.sigmoid", "li_sigmoid", 1, abi.RP_LI_SIGMOID),
                                    (QIF, "qif", 2, abi.RP_QIF), (QIF + "_sfa", "qif_sfa", 3, abi.RP_QIF_SFA),
-                                   ("neuron_model_templates.spiking_neurons.lif.lif", "lif", 2, abi.RP_LIF)]:
+                                   ("neuron_model_templates.spiking_neurons.lif.lif", "lif", 2, abi.RP_LIF),
+                                   ("neuron_model_templates.spiking_neurons.ik.ik", "ik", 3, abi.RP_IK)]:
         spec = templates.resolve_template(path)
         assert (spec.name, spec.n_sv, spec.model) == (name, nsv, model)
     # defaults of the reference YAML files
@@ -50,6 +51,25 @@ def test_user_yaml_template(tmp_path, monkeypatch):
     assert dict(spec.state_vars)["my_sfa_op/v"] == -1.0
     with pytest.raises(NotImplementedError):
         templates.resolve_template("mymodels.custom.weird")
+
+
+def test_ik_state_order_matches_reference():
+    """ik_op: the reference's y is [v, u, s] (equation order, ik.yaml:10-13); the engine keeps planes (v, s, u)."""
+    net = rp.Network(1e-1, device="cpu")
+    n = 4
+    node = net.add_diffeq_node("ik", "neuron_model_templates.spiking_neurons.ik.ik", weights=np.zeros((n, n)), source_var="s",
+                               target_var="s_in", input_var="I_ext", output_var="s", spike_var="spike", reset_var="v", op="ik_op",
+                               spike_threshold=40.0, spike_reset=-60.0, node_vars={"eta": 55.0})
+    assert len(node.y) == 3 * n
+    assert torch.allclose(node.y, torch.cat([torch.full((n,), -60.0), torch.zeros(2 * n)]))
+    node.reset(np.arange(3 * n, dtype=np.float32))
+    assert torch.allclose(node["v"], torch.arange(0., n)) and torch.allclose(node["u"], torch.arange(n, 2. * n))
+    assert torch.allclose(node["s"], torch.arange(2. * n, 3 * n))
+    assert torch.allclose(node.state[1, 0], torch.arange(2. * n, 3 * n)) and torch.allclose(node.state[2, 0], torch.arange(n, 2. * n))
+    assert torch.allclose(node.y, torch.arange(0., 3 * n))
+    assert node.var_index("u") == 2 and node.var_index("ik_op/s") == 1
+    slots, tensors, per_neuron = node.param_slots()
+    assert abi.RP_P_G in slots and abi.RP_P_KAPPA in slots and float(node["eta"]) == 55.0 and float(node["C"]) == 100.0
 
 
 def _qif_net(n=10, **kw):
