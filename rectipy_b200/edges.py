@@ -26,7 +26,7 @@ class Linear:
     _tensors = ["weights"]
 
     def __init__(self, n_in: int, n_out: int, weights: Union[np.ndarray, torch.Tensor] = None,
-                 dtype: torch.dtype = torch.float32, detach: bool = True, **kwargs):
+                 dtype: torch.dtype = torch.float64, detach: bool = True, **kwargs):
         if weights is None:
             weights = torch.randn(n_out, n_in, dtype=dtype)
         else:
@@ -34,13 +34,13 @@ class Linear:
         if weights.dim() != 2:
             raise ValueError("Edge weights have to be a 2D array.")
         if weights.shape[0] == n_in and weights.shape[1] == n_out and n_in != n_out:
-            weights = weights.T.contiguous()
+            weights = weights.T          # a view, like the reference (edges.py:22-23): keeps results bit-identical to it
         elif weights.shape[0] != n_out or weights.shape[1] != n_in:
             raise ValueError("Shape of the provided weights does not match the input and output dimensions of the "
                              "source and target nodes.")
         self.n_in = n_in
         self.n_out = n_out
-        self.weights = weights.contiguous()
+        self.weights = weights
         self.train_params = []
         if not detach:
             train_params = kwargs.pop("train_params", ["weights"])
@@ -84,7 +84,7 @@ class LinearMasked(Linear):
     _tensors = ["weights", "mask"]
 
     def __init__(self, n_in: int, n_out: int, mask: Union[np.ndarray, torch.Tensor],
-                 weights: Union[np.ndarray, torch.Tensor] = None, dtype: torch.dtype = torch.float32,
+                 weights: Union[np.ndarray, torch.Tensor] = None, dtype: torch.dtype = torch.float64,
                  detach: bool = True, **kwargs):
         mask = _to_tensor(mask, dtype)
         if mask.shape[0] == n_in and mask.shape[1] == n_out and n_in != n_out:
@@ -107,7 +107,7 @@ class RLS(Linear):
     _tensors = ["weights", "P"]
 
     def __init__(self, n_in: int, n_out: int, weights: Union[np.ndarray, torch.Tensor] = None,
-                 dtype: torch.dtype = torch.float32, beta: float = 1.0, alpha: float = 1.0, **kwargs):
+                 dtype: torch.dtype = torch.float64, beta: float = 1.0, alpha: float = 1.0, **kwargs):
         if beta > 1 or beta < 0:
             raise ValueError("Parameter beta should be a positive scalar between 0 and 1.")
         if alpha < 0:
@@ -121,9 +121,10 @@ class RLS(Linear):
         self.train_params = []
 
     def update(self, x: torch.Tensor, y: torch.Tensor, y_hat: torch.Tensor) -> None:
+        # operation order follows edges.py:229-234 exactly so that results are bit-identical on the same device
         z = self.beta * self.P @ x
-        kappa = 1.0 / (1.0 + x @ z)
+        kappa = (1.0 + x @ z) ** (-1)
         err = y - y_hat
-        self.weights += torch.outer(y - kappa * ((self.weights + torch.outer(y, z)) @ x), z)
+        self.weights += torch.outer((y - kappa * x @ (self.weights + torch.outer(y, z)).T), z)
         self.P -= kappa * torch.outer(z, z)
         self.loss = torch.inner(err, err)
