@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RP_ABI_VERSION 2
+#define RP_ABI_VERSION 3
 #define RP_MAX_IN 8      /* max fused input-projection width  m (wider inputs: use RP_IN_DENSE)  */
 #define RP_MAX_OUT 8     /* max fused readout width           k (wider readouts: use RP_OUT_DENSE) */
 #define RP_MAX_SV 3
@@ -88,6 +88,11 @@ typedef struct rp_fwd_args {
     int rec_reduce[RP_MAX_REC];  /* 1: mean over neurons -> [n_rec,B]; 0: [n_rec,B,n]           */
     float* rec_buf[RP_MAX_REC];
     float* history;         /* [(T+1),n_hist,B,n] state checkpoints for rp_backward (n_hist = rp_num_history_planes), or NULL */
+    /* Segmented horizons (checkpoint + recompute): this call integrates global steps [t_offset, t_offset+T) of a run of
+     * T_total steps (0: T_total = T).  Record windows are those of the whole run; out_rec / rec_buf point at record 0 of the
+     * whole run.  Segment starts must not split a record window: t_offset = 0, or (t_offset-1) % sampling_steps == 0. */
+    int t_offset;
+    int T_total;
 } rp_fwd_args;
 
 typedef struct rp_bwd_args {
@@ -108,6 +113,8 @@ typedef struct rp_bwd_args {
                                       the caller reduces over neurons for shared parameters     */
     float* g_y0;            /* [n_sv,B,n] or NULL                                               */
     float* g_x;             /* RP_IN_DENSE only: dL/dx [T,B,n] or NULL                          */
+    int t_offset;           /* as in rp_fwd_args; x / history / g_x are those of the segment, g_out_rec of the whole run */
+    int T_total;
 } rp_bwd_args;
 
 int         rp_abi_version(void);

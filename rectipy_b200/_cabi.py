@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-RP_ABI_VERSION = 2
+RP_ABI_VERSION = 3
 RP_MAX_IN, RP_MAX_OUT, RP_MAX_SV, RP_MAX_REC = 8, 8, 3, 4
 RP_LI_TANH, RP_LI_SIGMOID, RP_QIF, RP_QIF_SFA, RP_LIF, RP_IK = range(6)
 (RP_P_TAU, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_RMAX, RP_P_SIG_S, RP_P_V0,
@@ -34,7 +34,7 @@ class rp_fwd_args(C.Structure):
                 ("x", _fp), ("W", _fp), ("W_in", _fp), ("W_out", _fp), ("params", _fp * RP_NUM_PARAMS),
                 ("y0", _fp), ("yT", _fp), ("out_rec", _fp),
                 ("n_rec_vars", C.c_int), ("rec_var", C.c_int * RP_MAX_REC), ("rec_reduce", C.c_int * RP_MAX_REC),
-                ("rec_buf", _fp * RP_MAX_REC), ("history", _fp)]
+                ("rec_buf", _fp * RP_MAX_REC), ("history", _fp), ("t_offset", C.c_int), ("T_total", C.c_int)]
 
 
 class rp_bwd_args(C.Structure):
@@ -42,7 +42,7 @@ class rp_bwd_args(C.Structure):
                 ("x", _fp), ("W", _fp), ("W_in", _fp), ("W_out", _fp), ("params", _fp * RP_NUM_PARAMS),
                 ("history", _fp), ("g_out_rec", _fp), ("g_yT", _fp),
                 ("dW", _fp), ("dW_in", _fp), ("dW_out", _fp), ("dparams", _fp * RP_NUM_PARAMS),
-                ("g_y0", _fp), ("g_x", _fp)]
+                ("g_y0", _fp), ("g_x", _fp), ("t_offset", C.c_int), ("T_total", C.c_int)]
 
 
 #: every symbol include/rectipy_b200.h declares (checked by tests/test_cabi.py)

@@ -236,18 +236,23 @@ int persistent_forward(rp_plan* p, const rp_fwd_args* a, const rp::ModelParams& 
     const rp_desc& d = p->d;
     const int N = d.n, B = d.batch, nsv = p->nsv;
     const size_t plane = (size_t)B * N, slot = (size_t)nsv * plane;
-    const int n_rec = rp_num_records(a->T, a->sampling_steps, a->cutoff);
+    const int T_tot = a->T_total > 0 ? a->T_total : a->T;
+    const int n_rec = rp_num_records(T_tot, a->sampling_steps, a->cutoff);
     if (a->history) RP_CUDA(cudaMemcpyAsync(a->history, a->y0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (a->T == 0) { RP_CUDA(cudaMemcpyAsync(a->yT, a->y0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st)); return 0; }
     RP_CUDA(cudaMemsetAsync(p->ps_vec, 0, 4 * (size_t)B * p->ps_npad * sizeof(float), st));   // clear stale step tags
-    if (a->out_rec && d.out_mode == RP_OUT_READOUT && n_rec > 0)
-        RP_CUDA(cudaMemsetAsync(a->out_rec, 0, (size_t)n_rec * B * d.n_out * sizeof(float), st));
-    for (int r = 0; r < a->n_rec_vars; ++r)
-        if (a->rec_reduce[r] && n_rec > 0) RP_CUDA(cudaMemsetAsync(a->rec_buf[r], 0, (size_t)n_rec * B * sizeof(float), st));
+    // accumulated with atomics: clear once, when the first segment of a run is integrated
+    if (a->t_offset == 0) {
+        if (a->out_rec && d.out_mode == RP_OUT_READOUT && n_rec > 0)
+            RP_CUDA(cudaMemsetAsync(a->out_rec, 0, (size_t)n_rec * B * d.n_out * sizeof(float), st));
+        for (int r = 0; r < a->n_rec_vars; ++r)
+            if (a->rec_reduce[r] && n_rec > 0) RP_CUDA(cudaMemsetAsync(a->rec_buf[r], 0, (size_t)n_rec * B * sizeof(float), st));
+    }
     rp::PersistFwdArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.N = N; pa.B = B; pa.T = a->T; pa.m = d.n_in; pa.k = d.n_out; pa.in_mode = d.in_mode; pa.in_target = d.in_target;
     pa.out_mode = d.out_mode; pa.out_var = d.out_var; pa.S = a->sampling_steps; pa.cutoff = a->cutoff;
+    pa.t_offset = a->t_offset; pa.T_total = T_tot;
     pa.dt = d.dt; pa.theta = d.theta; pa.v_reset = d.v_reset;
     pa.Wk = p->Wk; pa.ldw = p->ldw; pa.rows_per_cta = p->ps_rows; pa.w_resident = p->ps_fwd_wres;
     pa.x = a->x; pa.W_in = a->W_in; pa.W_out = a->W_out; pa.mp = mp; pa.y0 = a->y0; pa.yT = a->yT; pa.history = a->history;
@@ -284,6 +289,7 @@ int persistent_backward(rp_plan* p, const rp_bwd_args* a, const rp::ModelParams&
     memset(&pa, 0, sizeof(pa));
     pa.N = N; pa.B = B; pa.T = a->T; pa.m = d.n_in; pa.k = d.n_out; pa.in_mode = d.in_mode; pa.in_target = d.in_target;
     pa.out_mode = d.out_mode; pa.out_var = d.out_var; pa.S = a->sampling_steps; pa.cutoff = a->cutoff; pa.truncate = a->truncate_steps;
+    pa.t_offset = a->t_offset; pa.T_total = a->T_total > 0 ? a->T_total : a->T;
     pa.dt = d.dt; pa.theta = d.theta; pa.slope = d.slope;
     pa.WkT = p->WkT; pa.ldw = p->ldw; pa.rows_per_cta = p->ps_rows; pa.w_resident = p->ps_bwd_wres; pa.dw_resident = p->ps_bwd_dwres;
     pa.need_dW = need_dW ? 1 : 0;
@@ -423,6 +429,8 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         ++p->launches;
         RP_LAUNCH_CHECK();
     }
+    const int T_tot = a->T_total > 0 ? a->T_total : a->T;
+    if (a->t_offset < 0 || a->t_offset + a->T > T_tot) return fail("rp_forward: bad t_offset/T_total");
     if (p->persistent) return persistent_forward(p, a, mp, st);
     float* base = a->history ? a->history : p->pp;
     const size_t hslot = (size_t)nhist_of(d.model) * plane;          // checkpoint slot stride (ik: + recurrent-drive plane)
@@ -451,7 +459,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
     for (int t = 0; t < a->T; ++t) {
         float* cur = slot_ptr(t);
         float* nxt = slot_ptr(t + 1);
-        const Window w = window_of(t, a->T, a->sampling_steps, a->cutoff);
+        const Window w = window_of(a->t_offset + t, T_tot, a->sampling_steps, a->cutoff);
         rp::FwdStepArgs fa;
         fa.N = N; fa.B = B; fa.m = d.n_in; fa.in_mode = d.in_mode; fa.in_target = d.in_target;
         fa.dt = d.dt; fa.theta = d.theta; fa.v_reset = d.v_reset;
@@ -551,8 +559,9 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     const size_t x_stride = d.in_mode == RP_IN_DENSE ? plane : (d.in_mode == RP_IN_PROJ ? (size_t)B * d.n_in : 0);
     const size_t out_stride = d.out_mode == RP_OUT_READOUT ? (size_t)B * d.n_out : plane;
     const size_t hslot = (size_t)nhist_of(d.model) * plane;
+    const int T_tot = a->T_total > 0 ? a->T_total : a->T;
     const int tr = a->truncate_steps;
-    const bool truncating = tr > 0 && tr < a->T;
+    const bool truncating = tr > 0 && tr < T_tot;
     const int wg_chunk = p->use_tc ? p->tc.wgrad_chunk : 1;
 
     rp::AdjArgs aa;
@@ -600,14 +609,14 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                     }
                 }
             }
-            const Window w = window_of(t, a->T, a->sampling_steps, a->cutoff);
+            const Window w = window_of(a->t_offset + t, T_tot, a->sampling_steps, a->cutoff);
             aa.y_t = a->history + (size_t)t * hslot;
             aa.urec_t = d.model == RP_IK ? a->history + (size_t)t * hslot + (size_t)nsv * plane : nullptr;
             aa.x_t = a->x ? a->x + (size_t)t * x_stride : nullptr;
             aa.e_t = (a->g_out_rec && w.j >= 0) ? a->g_out_rec + (size_t)w.j * out_stride : nullptr;
             aa.e_scale = w.j >= 0 ? 1.0f / (float)w.len : 0.f;
             aa.g_x_t = a->g_x ? a->g_x + (size_t)t * plane : nullptr;
-            aa.zero_after_post = (truncating && t > 0 && t % tr == 0) ? 1 : 0;
+            aa.zero_after_post = (truncating && (a->t_offset + t) > 0 && (a->t_offset + t) % tr == 0) ? 1 : 0;
         }
         if (aa.do_pre) {
             aa.y_tm1 = a->history + (size_t)(t - 1) * hslot;
@@ -653,7 +662,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     if (fused_adj && a->dW_out && a->g_out_rec && a->T > 0) {
         dim3 rgrid((N + 127) / 128, std::max(1, std::min(a->T, 4 * p->sm_count / std::max(1, (N + 127) / 128))));
         RP_DISPATCH_MODEL(d.model, (rp::k_readout_grad<M_><<<rgrid, 128, 0, st>>>(N, B, a->T, a->sampling_steps, a->cutoff, d.n_out, d.out_var,
-                                                                                   a->history, a->g_out_rec, mp, a->dW_out)));
+                                                                                   a->history, a->g_out_rec, mp, a->dW_out, a->t_offset, T_tot)));
         ++p->launches;
         RP_LAUNCH_CHECK();
     }

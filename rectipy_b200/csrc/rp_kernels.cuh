@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(256) k_prepare_weights(int N, const float* __r
 // reverse sweep; keeps the readout gradient out of the per-step adjoint epilogue).  grid = (ceil(N/128), t-splits)
 template <int MODEL>
 __global__ void __launch_bounds__(128) k_readout_grad(int N, int B, int T, int S, int cutoff, int k, int out_var, const float* __restrict__ hist,
-                                                       const float* __restrict__ g_out_rec, ModelParams mp, float* dW_out) {
+                                                       const float* __restrict__ g_out_rec, ModelParams mp, float* dW_out, int t_offset, int T_total) {
     constexpr int NSV = ModelTraits<MODEL>::NSV;
     const int i = blockIdx.x * 128 + threadIdx.x;
     const size_t plane = (size_t)B * N, slot = (size_t)HistPlanes<MODEL>::N * plane;
@@ -777,7 +777,7 @@ __global__ void __launch_bounds__(128) k_readout_grad(int N, int B, int T, int S
     for (int q = 0; q < RP_MAX_OUT; ++q) acc[q] = 0.f;
     if (i < N) {
         for (int t = t0; t < t1; ++t) {
-            const PWindow w = pwindow_of(t, T, S, cutoff);
+            const PWindow w = pwindow_of(t_offset + t, T_total, S, cutoff);
             if (w.j < 0) continue;
             const float sc = 1.0f / (float)w.len;
             const float* yt = hist + (size_t)t * slot + (out_var == RP_VAR_R ? 0 : (size_t)out_var * plane) + i;

@@ -71,7 +71,7 @@ __device__ __forceinline__ void ll_gather(const uint2* gsrc, float* s_dst, int B
 }
 
 struct PersistFwdArgs {
-    int N, B, T, m, k, in_mode, in_target, out_mode, out_var, S, cutoff;
+    int N, B, T, m, k, in_mode, in_target, out_mode, out_var, S, cutoff, t_offset, T_total;
     float dt, theta, v_reset;
     const float* Wk; int ldw;       // [N][ldw]  k_i * W
     int rows_per_cta, w_resident;
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
         }
         __syncthreads();
         // 3) vector field, threshold/reset, Observer -- the owning thread keeps the neuron's state in registers
-        const PWindow w = pwindow_of(t, a.T, a.S, a.cutoff);
+        const PWindow w = pwindow_of(a.t_offset + t, a.T_total, a.S, a.cutoff);
         if (own) {
             const size_t idx = (size_t)b * N + i;
             float Iin = 0.f;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
 // persistent reverse pass
 // ---------------------------------------------------------------------------------------------------------------
 struct PersistBwdArgs {
-    int N, B, T, m, k, in_mode, in_target, out_mode, out_var, S, cutoff, truncate;
+    int N, B, T, m, k, in_mode, in_target, out_mode, out_var, S, cutoff, truncate, t_offset, T_total;
     float dt, theta, slope;
     const float* WkT; int ldw;      // [N][ldw]  (k_i W_ij)^T : row j holds column j of kW
     int rows_per_cta, w_resident, dw_resident, need_dW;
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
     }
     const float dt = a.dt;
     const int nvec = N >> 2;
-    const bool truncating = a.truncate > 0 && a.truncate < a.T;
+    const bool truncating = a.truncate > 0 && a.truncate < a.T_total;
 
     // g_{T-1} = dt * gate_{T-1} * a_T  ("pre" of the first reverse step)
     auto make_g = [&](int tm1) -> float {
@@ -387,12 +387,12 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
             const float s = NSV > 1 ? yt[plane + idx] : 0.f;
             const float x = NSV > 2 ? yt[2 * plane + idx] : 0.f;
             const float urec = HistPlanes<MODEL>::N > NSV ? yt[(size_t)NSV * plane + idx] : 0.f;
-            const PWindow w = pwindow_of(t, a.T, a.S, a.cutoff);
+            const PWindow w = pwindow_of(a.t_offset + t, a.T_total, a.S, a.cutoff);
             const size_t estride = a.out_mode == RP_OUT_READOUT ? (size_t)B * a.k : plane;
             aa.e_t = (a.g_out_rec && w.j >= 0) ? a.g_out_rec + (size_t)w.j * estride : nullptr;
             aa.e_scale = w.j >= 0 ? 1.0f / (float)w.len : 0.f;
             aa.x_t = a.x ? a.x + (size_t)t * (a.in_mode == RP_IN_DENSE ? plane : (size_t)B * a.m) : nullptr;
-            aa.zero_after_post = (truncating && t > 0 && t % a.truncate == 0) ? 1 : 0;
+            aa.zero_after_post = (truncating && (a.t_offset + t) > 0 && (a.t_offset + t) % a.truncate == 0) ? 1 : 0;
             const RegAcc racc{acc};
             const float dI = adj_post_math<MODEL>(aa, rowp, racc, i, b, s_z[r * PS_MAX_B + b], v, s, x, av, as, ax, urec);
             if (a.g_x) a.g_x[(size_t)t * plane + idx] = dI;

@@ -8,6 +8,7 @@ loop (reference: rectipy/network.py:588-599,1123-1130).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -136,6 +137,40 @@ class RunConfig:
     param_slots: Tuple[int, ...]      # abi slot of each tensor in *params (same order)
 
 
+def history_budget_bytes() -> int:
+    """Checkpoint memory one autograd call may hold (env RECTIPY_B200_HISTORY_GB, default 64 GiB of the 180 GB HBM).
+    Longer horizons are integrated in segments: only segment-boundary states are kept and each segment's per-step
+    checkpoints are recomputed just before its reverse sweep."""
+    return int(float(os.environ.get("RECTIPY_B200_HISTORY_GB", "64")) * (1 << 30))
+
+
+def plan_segments(T: int, S: int, slot_bytes: int, budget: int) -> List[Tuple[int, int]]:
+    """[(t_offset, length)] covering [0, T).  One segment if the full history fits the budget; otherwise segment starts
+    sit right after a record step ((t_offset - 1) % S == 0) so that no Observer window is split."""
+    if T <= 0 or (T + 1) * slot_bytes <= budget:
+        return [(0, T)]
+    steps = max(1, budget // slot_bytes - 2)
+    L = max(S, (steps // S) * S)
+    segs, t0 = [], 0
+    first = min(T, L + 1)
+    segs.append((0, first))
+    t0 = first
+    while t0 < T:
+        n = min(L, T - t0)
+        segs.append((t0, n))
+        t0 += n
+    return segs
+
+
+def _fill_common(a, cfg, x_c, W_c, W_in_c, W_out_c, params_c, t0, n, T_total):
+    a.T, a.sampling_steps, a.cutoff = n, cfg.sampling_steps, cfg.cutoff
+    a.t_offset, a.T_total = t0, T_total
+    a.x = _ptr(x_c[t0:t0 + n]) if x_c is not None else None
+    a.W, a.W_in, a.W_out = _ptr(W_c), _ptr(W_in_c), _ptr(W_out_c)
+    for slot, p in zip(cfg.param_slots, params_c):
+        a.params[slot] = p.data_ptr()
+
+
 class EngineRun(torch.autograd.Function):
     """(x, W, W_in, W_out, y0, *params) -> (out_rec, yT, *recorded_vars) for a whole horizon."""
 
@@ -145,7 +180,7 @@ class EngineRun(torch.autograd.Function):
         lib = plan.lib
         dev = y0.device
         B, N = key.batch, key.n
-        nsv = lib.rp_num_state_vars(key.model)
+        nh = lib.rp_num_history_planes(key.model)
         n_rec = lib.rp_num_records(cfg.T, cfg.sampling_steps, cfg.cutoff)
         # grad mode is off inside Function.forward; needs_input_grad already accounts for no_grad() at apply time
         needs_grad = any(ctx.needs_input_grad)
@@ -156,34 +191,40 @@ class EngineRun(torch.autograd.Function):
         W_out_c = None if W_out is None else _f32c(W_out)
         params_c = [_f32c(p) for p in params]
 
-        a = abi.rp_fwd_args()
-        a.T, a.sampling_steps, a.cutoff = cfg.T, cfg.sampling_steps, cfg.cutoff
-        a.x, a.W, a.W_in, a.W_out = _ptr(x_c), _ptr(W_c), _ptr(W_in_c), _ptr(W_out_c)
-        for slot, p in zip(cfg.param_slots, params_c):
-            a.params[slot] = p.data_ptr()
-        yT = torch.empty_like(y0_c)
-        a.y0, a.yT = _ptr(y0_c), _ptr(yT)
         out_w = key.n_out if key.out_mode == abi.RP_OUT_READOUT else N
         out_rec = torch.empty((n_rec, B, out_w), device=dev, dtype=torch.float32) if cfg.want_out else None
-        a.out_rec = _ptr(out_rec)
-        recs = []
-        a.n_rec_vars = len(cfg.rec_vars)
-        for i, (v, red) in enumerate(zip(cfg.rec_vars, cfg.rec_reduce)):
-            buf = torch.empty((n_rec, B) if red else (n_rec, B, N), device=dev, dtype=torch.float32)
-            recs.append(buf)
-            a.rec_var[i], a.rec_reduce[i], a.rec_buf[i] = v, int(red), buf.data_ptr()
-        nh = lib.rp_num_history_planes(key.model)
-        history = torch.empty((cfg.T + 1, nh, B, N), device=dev, dtype=torch.float32) if needs_grad else None
-        a.history = _ptr(history)
+        recs = [torch.empty((n_rec, B) if red else (n_rec, B, N), device=dev, dtype=torch.float32) for red in cfg.rec_reduce]
+        segs = plan_segments(cfg.T, cfg.sampling_steps, nh * B * N * 4, history_budget_bytes()) if needs_grad else [(0, cfg.T)]
+        segmented = len(segs) > 1
+        history = None
+        if needs_grad and not segmented:
+            history = torch.empty((cfg.T + 1, nh, B, N), device=dev, dtype=torch.float32)
+        bounds = []
+        y_cur = y0_c
         with torch.cuda.device(dev):
-            abi.check(lib.rp_forward(plan.handle, C.byref(a), _stream()), "rp_forward")
+            for (t0, n) in segs:
+                a = abi.rp_fwd_args()
+                _fill_common(a, cfg, x_c, W_c, W_in_c, W_out_c, params_c, t0, n, cfg.T)
+                yT = torch.empty_like(y0_c)
+                a.y0, a.yT = _ptr(y_cur), _ptr(yT)
+                a.out_rec = _ptr(out_rec)
+                a.n_rec_vars = len(cfg.rec_vars)
+                for i, (v, red) in enumerate(zip(cfg.rec_vars, cfg.rec_reduce)):
+                    a.rec_var[i], a.rec_reduce[i], a.rec_buf[i] = v, int(red), recs[i].data_ptr()
+                a.history = _ptr(history)
+                abi.check(lib.rp_forward(plan.handle, C.byref(a), _stream()), "rp_forward")
+                if segmented:
+                    bounds.append(y_cur)
+                y_cur = yT
+        yT = y_cur
 
         ctx.plan, ctx.cfg = plan, cfg
         ctx.has = (x is not None, W_in is not None, W_out is not None)
-        ctx.n_params = len(params)
+        ctx.segs = segs
         ctx.param_shapes = [tuple(p.shape) for p in params]
         if needs_grad:
-            saved = [t for t in (x_c, W_c, W_in_c, W_out_c, history) if t is not None] + params_c
+            keep = history if not segmented else torch.stack(bounds)      # [n_seg, nsv, B, N] segment-start states
+            saved = [t for t in (x_c, W_c, W_in_c, W_out_c, keep) if t is not None] + params_c
             ctx.save_for_backward(*saved)
         if out_rec is None:
             out_rec = torch.empty((0,), device=dev)
@@ -197,58 +238,87 @@ class EngineRun(torch.autograd.Function):
         key, lib = plan.key, plan.lib
         B, N = key.batch, key.n
         nsv = lib.rp_num_state_vars(key.model)
+        nh = lib.rp_num_history_planes(key.model)
         saved = list(ctx.saved_tensors)
         has_x, has_win, has_wout = ctx.has
         x_c = saved.pop(0) if has_x else None
         W_c = saved.pop(0)
         W_in_c = saved.pop(0) if has_win else None
         W_out_c = saved.pop(0) if has_wout else None
-        history = saved.pop(0)
+        keep = saved.pop(0)
         params_c = saved
         dev = W_c.device
+        segs = ctx.segs
+        segmented = len(segs) > 1
         # needs_input_grad indices: plan, cfg, x, W, W_in, W_out, y0, *params
         need = ctx.needs_input_grad
         need_x, need_W, need_Win, need_Wout, need_y0 = need[2], need[3], need[4], need[5], need[6]
         need_p = need[7:]
+        if need_x and has_x and key.in_mode != abi.RP_IN_DENSE:
+            raise NotImplementedError("rectipy_b200: gradients w.r.t. projected inputs (RP_IN_PROJ) are not provided; "
+                                      "detach the input or use a dense input current")
 
-        b = abi.rp_bwd_args()
-        b.T, b.sampling_steps, b.cutoff, b.truncate_steps = cfg.T, cfg.sampling_steps, cfg.cutoff, cfg.truncate_steps
-        b.x, b.W, b.W_in, b.W_out = _ptr(x_c), _ptr(W_c), _ptr(W_in_c), _ptr(W_out_c)
-        for slot, p in zip(cfg.param_slots, params_c):
-            b.params[slot] = p.data_ptr()
-        b.history = _ptr(history)
         g_out_c = _f32c(g_out) if (g_out is not None and cfg.want_out) else None
-        g_yT_c = _f32c(g_yT) if g_yT is not None else None
-        b.g_out_rec, b.g_yT = _ptr(g_out_c), _ptr(g_yT_c)
-        dW = torch.empty_like(W_c) if need_W else None
-        dW_in = torch.empty_like(W_in_c) if (need_Win and has_win) else None
-        dW_out = torch.empty_like(W_out_c) if (need_Wout and has_wout) else None
-        g_y0 = torch.empty((nsv, B, N), device=dev, dtype=torch.float32) if need_y0 else None
-        g_x = torch.empty_like(x_c) if (need_x and has_x and key.in_mode == abi.RP_IN_DENSE) else None
-        b.dW, b.dW_in, b.dW_out, b.g_y0, b.g_x = _ptr(dW), _ptr(dW_in), _ptr(dW_out), _ptr(g_y0), _ptr(g_x)
-        dps: List[Optional[torch.Tensor]] = []
-        for slot, np_, shape in zip(cfg.param_slots, need_p, ctx.param_shapes):
-            if np_:
-                buf = torch.empty((N,), device=dev, dtype=torch.float32)
-                b.dparams[slot] = buf.data_ptr()
-                dps.append(buf)
+        g_state = _f32c(g_yT) if g_yT is not None else None
+        g_x = torch.empty_like(x_c) if (need_x and has_x) else None
+        totals = {}
+
+        def accumulate(name, t):
+            if t is None:
+                return
+            if name in totals:
+                totals[name].add_(t)
             else:
-                dps.append(None)
+                totals[name] = t
+
         with torch.cuda.device(dev):
-            abi.check(lib.rp_backward(plan.handle, C.byref(b), _stream()), "rp_backward")
+            for si in range(len(segs) - 1, -1, -1):
+                t0, n = segs[si]
+                if segmented:
+                    # recompute this segment's per-step checkpoints from its start state
+                    history = torch.empty((n + 1, nh, B, N), device=dev, dtype=torch.float32)
+                    f = abi.rp_fwd_args()
+                    _fill_common(f, cfg, x_c, W_c, W_in_c, W_out_c, params_c, t0, n, cfg.T)
+                    scratch = torch.empty((nsv, B, N), device=dev, dtype=torch.float32)
+                    f.y0, f.yT, f.history = _ptr(keep[si]), _ptr(scratch), _ptr(history)
+                    abi.check(lib.rp_forward(plan.handle, C.byref(f), _stream()), "rp_forward (recompute)")
+                else:
+                    history = keep
+                b = abi.rp_bwd_args()
+                _fill_common(b, cfg, x_c, W_c, W_in_c, W_out_c, params_c, t0, n, cfg.T)
+                b.truncate_steps = cfg.truncate_steps
+                b.history = _ptr(history)
+                b.g_out_rec, b.g_yT = _ptr(g_out_c), _ptr(g_state)
+                dW = torch.empty_like(W_c) if need_W else None
+                dW_in = torch.empty_like(W_in_c) if (need_Win and has_win) else None
+                dW_out = torch.empty_like(W_out_c) if (need_Wout and has_wout) else None
+                g_y0 = torch.empty((nsv, B, N), device=dev, dtype=torch.float32) if (need_y0 or si > 0) else None
+                b.dW, b.dW_in, b.dW_out, b.g_y0 = _ptr(dW), _ptr(dW_in), _ptr(dW_out), _ptr(g_y0)
+                b.g_x = _ptr(g_x[t0:t0 + n]) if g_x is not None else None
+                dps = []
+                for slot, np_ in zip(cfg.param_slots, need_p):
+                    buf = torch.empty((N,), device=dev, dtype=torch.float32) if np_ else None
+                    if buf is not None:
+                        b.dparams[slot] = buf.data_ptr()
+                    dps.append(buf)
+                abi.check(lib.rp_backward(plan.handle, C.byref(b), _stream()), "rp_backward")
+                accumulate("W", dW), accumulate("W_in", dW_in), accumulate("W_out", dW_out)
+                for i, buf in enumerate(dps):
+                    accumulate(("p", i), buf)
+                g_state = g_y0
+                del history
         grads_p = []
-        for buf, shape in zip(dps, ctx.param_shapes):
+        for i, shape in enumerate(ctx.param_shapes):
+            buf = totals.get(("p", i))
             if buf is None:
                 grads_p.append(None)
             else:
                 numel = 1
-                for s in shape:
-                    numel *= s
+                for sdim in shape:
+                    numel *= sdim
                 grads_p.append(buf.reshape(shape) if numel == N and N > 1 else buf.sum().reshape(shape))
-        if need_x and has_x and g_x is None:
-            raise NotImplementedError("rectipy_b200: gradients w.r.t. projected inputs (RP_IN_PROJ) are not provided; "
-                                      "detach the input or use a dense input current")
-        return (None, None, g_x, dW, dW_in, dW_out, g_y0) + tuple(grads_p)
+        return (None, None, g_x, totals.get("W"), totals.get("W_in"), totals.get("W_out"),
+                g_state if need_y0 else None) + tuple(grads_p)
 
 
 def rls_run(X: torch.Tensor, Y: torch.Tensor, W: torch.Tensor, P: torch.Tensor, beta_inv: float,

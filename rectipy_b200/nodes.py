@@ -131,6 +131,21 @@ class RateNet:
         self._state = st.to(self.device)
         self._y0_template = self._state.clone()
 
+    @classmethod
+    def from_pyrates(cls, node, input_var: str, output_var: str, weights=None, source_var: str = None,
+                     target_var: str = None, train_params: list = None, **kwargs):
+        """Same entry point as the reference (rectipy/nodes.py:112-164,363-380); no PyRates involved: the template is
+        recognised by `rectipy_b200.templates` and mapped onto a compiled vector field."""
+        if cls is RateNet:
+            kwargs.pop("spike_var", None)
+            kwargs.pop("reset_var", None)
+            return node_from_template(node, input_var, output_var, weights=weights, source_var=source_var,
+                                      target_var=target_var, train_params=train_params, **kwargs)
+        kwargs.setdefault("spike_var", "spike")
+        kwargs.setdefault("reset_var", "v")
+        return node_from_template(node, input_var, output_var, weights=weights, source_var=source_var,
+                                  target_var=target_var, train_params=train_params, **kwargs)
+
     # ---- reference-style views ---------------------------------------------------------------------------
     @property
     def train_params(self) -> List[torch.Tensor]:

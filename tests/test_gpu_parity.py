@@ -404,3 +404,59 @@ def test_izhikevich_batched_paths_agree():
             u_got = obs.to_numpy(("ik", "u")).reshape(ref.shape[0], B, n)[:, b, :]
             assert rel_err(u_got, u_ref) < 1e-4
         assert all(torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+@pytest.mark.parametrize("model,n,B,prec", [("qif", 128, 128, "3xtf32"), ("li_tanh", 64, 1, "fp32"), ("qif_sfa", 96, 20, "fp32"), ("ik", 64, 2, "fp32")])
+def test_checkpoint_recompute_segments_match_full_history(model, n, B, prec, monkeypatch):
+    """Long horizons run in segments (boundary checkpoints + recompute, engine.plan_segments).  With a tiny history budget the
+    same run must give the same records and the same gradients as the single-segment run, on all three execution paths."""
+    import rectipy_b200 as rp
+    from rectipy_b200 import engine
+    from golden_util import TEMPLATE_PATH
+    rng = np.random.default_rng(n * 3 + B)
+    rate = model.startswith("li_")
+    dt, T, S, cutoff, trunc = (1e-2, 230, 4, 6, 90) if rate else ((1e-1, 230, 4, 6, 90) if model == "ik" else (1e-3, 230, 3, 5, 100))
+    m, k = 2, 2
+    W = rng.standard_normal((n, n)) * (1.5 if rate else 2.0) / np.sqrt(n)
+    if model == "ik":
+        W = np.abs(W) / np.sqrt(n)
+    w_in, w_out = rng.standard_normal((n, m)) * (10.0 if model == "ik" else 1.0), rng.standard_normal((k, n)) / np.sqrt(n)
+    path, op, svar, tvar = TEMPLATE_PATH[model]
+    params = {"li_tanh": dict(tau=rng.uniform(1, 2, n), k=1.2, eta=0.1), "qif": dict(eta=orc.lorentzian_etas(n), k=1.5),
+              "qif_sfa": dict(eta=orc.lorentzian_etas(n, eta=0.0), alpha=0.4, tau_x=1.2), "ik": dict(eta=rng.uniform(60, 160, n), g=1.5)}[model]
+    skw = dict(spike_threshold=40.0, spike_reset=-60.0) if model == "ik" else {}
+    t = np.arange(T) * dt
+    amp, off = (1.5, 0.0) if rate else ((3.0, 1.0) if model == "ik" else (10.0, 14.0))
+    x = amp * np.sin(2 * np.pi * rng.uniform(0.5, 3, (1, B, m)) * t[:, None, None] + rng.uniform(0, 6.28, (1, B, m))) + off
+    n_rec = len([s for s in range(T) if s >= cutoff and s % S == 0])
+    targets = torch.tensor(rng.standard_normal((n_rec, B, k)), dtype=torch.float32, device="cuda")
+    res = {}
+    for mode in ("full", "segmented"):
+        if mode == "segmented":
+            nh = 4 if model == "ik" else (3 if model == "qif_sfa" else (1 if rate else 2))
+            monkeypatch.setenv("RECTIPY_B200_HISTORY_GB", repr(60 * nh * B * n * 4 / 2**30))      # ~57 steps per segment
+        else:
+            monkeypatch.delenv("RECTIPY_B200_HISTORY_GB", raising=False)
+        net = rp.Network(dt, device="cuda:0", batch=B, precision=prec)
+        kw = dict(weights=W, source_var=svar, target_var=tvar, input_var=f"{op}/I_ext",
+                  node_vars={f"{op}/{p}": v for p, v in params.items()}, train_params=["weights", f"{op}/eta"])
+        if not rate:
+            kw.update(spike_var=f"{op}/spike", reset_var=f"{op}/v", output_var=f"{op}/s", **skw)
+        else:
+            kw.update(output_var=f"{op}/v")
+        node = net.add_diffeq_node("rnn", path, **kw)
+        net.add_func_node("inp", m, "identity"); net.add_edge("inp", "rnn", weights=w_in, train="gd")
+        net.add_func_node("out", k, "identity"); net.add_edge("rnn", "out", weights=w_out, train="gd")
+        obs = net.run(x, sampling_steps=S, cutoff=cutoff, verbose=False, enable_grad=True,
+                      record_vars=[("rnn", f"{op}/v", False), ("rnn", f"{op}/v" if rate else f"{op}/s", True)][:1 if rate else 2], truncate_steps=trunc)
+        out = torch.stack(obs["out"])
+        torch.nn.functional.mse_loss(out.reshape(n_rec, B, k), targets).backward()
+        res[mode] = dict(out=out.detach().cpu().numpy(), var=obs.to_numpy(("rnn", f"{op}/v")), y=node.y.detach().cpu().numpy(),
+                         gW=node["weights"].grad.cpu().numpy(), geta=node[f"{op}/eta"].grad.cpu().numpy(),
+                         gin=net.get_edge("inp", "rnn").weights.grad.cpu().numpy(), gout=net.get_edge("rnn", "out").weights.grad.cpu().numpy())
+    segs = engine.plan_segments(T, S, (4 if model == "ik" else 3) * B * n * 4, int(60 * 3 * B * n * 4))
+    assert len(segs) >= 3
+    assert np.array_equal(res["full"]["y"], res["segmented"]["y"]) and np.array_equal(res["full"]["var"], res["segmented"]["var"])
+    errs = {key: rel_err(res["segmented"][key], res["full"][key]) for key in res["full"]}
+    print(model, errs)
+    assert all(e <= 2e-5 for e in errs.values()), errs
