@@ -180,7 +180,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _OUT.emit(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -190,6 +190,8 @@ def run_ours(args):
     import torch.distributed as dist
     from rectipy_b200 import engine, parallel, _cabi as abi
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
     rank, local_rank, world = parallel.init_from_env("nccl")
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (the engine has no CPU fallback)")
@@ -327,10 +329,32 @@ def run_ours(args):
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"oracle port of the reference path, 1 trial x {CPU_T} steps BPTT, median of 3 ({cpu_sec:.2f} s each)"},
         }
-        print(json.dumps(line), flush=True)
+        _OUT.emit(json.dumps(line))
     if world > 1:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
+
+
+class _QuietStdout:
+    """Route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr; the JSON line is the only stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text: str):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_OUT = None
 
 
 def main():
@@ -343,10 +367,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (profiling runs)")
     args = ap.parse_args()
     globals()["T_INNER"] = args.t_inner
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    global _OUT
+    with _QuietStdout() as q:
+        _OUT = q
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":
