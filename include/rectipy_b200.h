@@ -41,7 +41,7 @@ extern "C" {
 
 /* vector fields (neuron_model_templates/rate_neurons/leaky_integrator.yaml, spiking_neurons/{qif,lif}.yaml) */
 enum { RP_LI_TANH = 0, RP_LI_SIGMOID = 1, RP_QIF = 2, RP_QIF_SFA = 3, RP_LIF = 4, RP_IK = 5 /* spiking_neurons/ik.yaml ik_op */ };
-/* parameter slots; each is a device pointer to 1 float (shared) or n floats (per neuron) */
+/* parameter slots; each is a device pointer to 1, n, B or B*n floats (see rp_desc.param_per_neuron) */
 enum { RP_P_TAU = 0, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_RMAX, RP_P_SIG_S, RP_P_V0,
        /* ik_op: */ RP_P_C, RP_P_VR, RP_P_VTH, RP_P_G, RP_P_ER, RP_P_B, RP_P_TAU_U, RP_P_KAPPA, RP_NUM_PARAMS };
 /* The coupling constant that scales the recurrent input (k for li/qif/lif, g for ik) is folded into the weights by the
@@ -66,7 +66,8 @@ typedef struct rp_desc {
     float theta;            /* spike threshold   (nodes.py:338,349)                             */
     float v_reset;          /* reset value       (nodes.py:338,348)                             */
     float slope;            /* surrogate slope   (nodes.py:345-347)                             */
-    int param_per_neuron[RP_NUM_PARAMS]; /* 1: pointer holds n values, 0: one shared value      */
+    int param_per_neuron[RP_NUM_PARAMS]; /* layout of each parameter: 0 one shared value, 1 [n] per neuron,
+                                            2 [B] per trial, 3 [B][n] per trial and neuron (parameter sweeps; no gradients) */
 } rp_desc;
 
 typedef struct rp_plan rp_plan;

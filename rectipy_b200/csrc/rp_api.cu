@@ -62,6 +62,7 @@ struct rp_plan {
     long long launches;
     size_t ws_bytes;
     bool use_tc;           // tcgen05 3xTF32 contractions
+    bool per_trial = false;// some template parameter has one value per trial (parameter sweep)
     // fp32 workspaces
     float* Wk = nullptr;     // [N][ldw]   k_i * W
     float* WkT = nullptr;    // [N][ldw]
@@ -96,8 +97,10 @@ int plan_alloc(rp_plan* p, float** ptr, size_t n_floats) {
 rp::ModelParams make_params(const rp_plan* p, const float* const* params) {
     rp::ModelParams mp;
     for (int q = 0; q < RP_NUM_PARAMS; ++q) {
+        const int mode = p->d.param_per_neuron[q];      // 0 shared, 1 [n], 2 [B], 3 [B][n]
         mp.p[q] = params[q];
-        mp.stride[q] = p->d.param_per_neuron[q] ? 1 : 0;
+        mp.stride[q] = (mode & 1) ? 1 : 0;
+        mp.bstride[q] = mode == 2 ? 1 : (mode == 3 ? p->d.n : 0);
     }
     return mp;
 }
@@ -340,6 +343,10 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
     if (d->out_var != RP_VAR_R && d->out_var >= nsv) return fail("rp_plan_create: out_var %d not a state variable of model %d", d->out_var, d->model);
     if (d->in_target == 1 && d->model != RP_LIF) return fail("rp_plan_create: in_target=1 (s_ext) only exists on the lif template");
     if (!(d->dt > 0.f)) return fail("rp_plan_create: dt must be positive");
+    for (int q = 0; q < RP_NUM_PARAMS; ++q)
+        if (d->param_per_neuron[q] < 0 || d->param_per_neuron[q] > 3) return fail("rp_plan_create: param_per_neuron[%d] must be 0..3", q);
+    if (d->param_per_neuron[rp::fold_slot(d->model)] > 1)
+        return fail("rp_plan_create: the coupling constant (slot %d) is folded into the shared weights and cannot differ between trials", rp::fold_slot(d->model));
     int dev = 0, count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail("rp_plan_create: no CUDA device available (the engine has no CPU fallback)");
     RP_CUDA(cudaGetDevice(&dev));
@@ -356,6 +363,7 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
     p->ws_bytes = 0;
     const int N = d->n, B = d->batch;
     p->use_tc = (d->precision == RP_PREC_3XTF32);
+    for (int q = 0; q < RP_NUM_PARAMS; ++q) if (d->param_per_neuron[q] > 1) p->per_trial = true;
     if (p->use_tc && !rp::tc_supported(N, B)) {
         delete p;
         return fail("rp_plan_create: RP_PREC_3XTF32 needs n %% 128 == 0 and batch %% 128 == 0 (got n=%d batch=%d)", N, B);
@@ -468,6 +476,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         fa.src_next = (!spk && !p->use_tc) ? p->src : nullptr;
         fa.src_hi = p->use_tc ? p->tc.src_hi : nullptr; fa.src_lo = p->use_tc ? p->tc.src_lo : nullptr; fa.ld_src = p->tc.ldk;
         fa.urec_out = (d.model == RP_IK && a->history) ? cur + (size_t)nsv * plane : nullptr;
+        fa.per_trial = p->per_trial ? 1 : 0;
         if (!p->use_tc) {
             // u[b][i] = sum_j (kW)[i][j] src_t[b][j], then the element-wise step
             const float* srcp = spk ? cur + plane : p->src;
@@ -527,6 +536,8 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     if (a->dW_out && d.out_mode != RP_OUT_READOUT) return fail("rp_backward: dW_out requested without RP_OUT_READOUT");
     if (a->g_x && d.in_mode != RP_IN_DENSE) return fail("rp_backward: g_x requested without RP_IN_DENSE");
     if (check_params(p, a->params)) return 1;
+    for (int q = 0; q < RP_NUM_PARAMS; ++q)
+        if (a->dparams[q] && d.param_per_neuron[q] > 1) return fail("rp_backward: gradients of per-trial parameters (slot %d) are not provided", q);
     const rp::ModelParams mp = make_params(p, a->params);
     const int fold = rp::fold_slot(d.model);
     const int kstride = d.param_per_neuron[fold] ? 1 : 0;
@@ -573,6 +584,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     else { aa.g_hi = p->tc.g_hi; aa.g_lo = p->tc.g_lo; aa.ld_g = p->tc.ldk; aa.ld_t = p->tc.ldt; }
     for (int q = 0; q < RP_NUM_PARAMS; ++q) aa.dparams[q] = (q == fold) ? nullptr : a->dparams[q];
     aa.dW_in = a->dW_in; aa.dW_out = a->dW_out;
+    aa.per_trial = p->per_trial ? 1 : 0;
     aa.any_param_grad = (a->dW_in || a->dW_out) ? 1 : 0;
     for (int q = 0; q < RP_NUM_PARAMS; ++q) if (aa.dparams[q]) aa.any_param_grad = 1;
 
@@ -582,7 +594,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     // The fused adjoint epilogue is opt-in (RP_FUSED_ADJ=1): with one tile per CTA its element-wise work cannot overlap the
     // MMA main loop and runs at 8 warps/SM, which measured slower (340 us/step) than the contraction followed by the
     // full-occupancy k_adj_step (149 + ~60 us).  It becomes the default once tiles are software-pipelined per CTA.
-    const bool fused_adj = p->use_tc && getenv("RP_FUSED_ADJ") && !a->dW_in && !a->g_x && !(d.model == RP_LIF && d.in_target == 1) && d.model != RP_IK;
+    const bool fused_adj = p->use_tc && getenv("RP_FUSED_ADJ") && !a->dW_in && !a->g_x && !(d.model == RP_LIF && d.in_target == 1) && d.model != RP_IK && !p->per_trial;
     dim3 agrid((N + rp::ADJ_TX - 1) / rp::ADJ_TX, (B + rp::ADJ_TY * rp::ADJ_BPT - 1) / (rp::ADJ_TY * rp::ADJ_BPT));
     dim3 ablock(rp::ADJ_TX, rp::ADJ_TY);
     int pending = 0;   // steps whose (g, src) columns sit in the tensor-core weight-gradient chunk

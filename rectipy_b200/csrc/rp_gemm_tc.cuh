@@ -198,15 +198,15 @@ struct EpiFwd {
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
                         const int i = i0 + rr;
-                        if constexpr (MODEL == RP_IK) {       // general (per-element parameter loads) path; also checkpoints the drive
+                        if (MODEL == RP_IK || a.per_trial) {  // general (per-element parameter loads) path: ik, parameter sweeps
                             const float Iin = input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i);
-                            fwd_elem<MODEL>(a, i, f4get(u4[cc], rr), Iin, f4get(v4[cc], rr), f4get(s4[cc], rr), f4get(x4[cc], rr), v1[rr], s1[rr], x1[rr]);
+                            fwd_elem<MODEL>(a, i, f4get(u4[cc], rr), Iin, f4get(v4[cc], rr), f4get(s4[cc], rr), f4get(x4[cc], rr), v1[rr], s1[rr], x1[rr], b);
                         } else {
                             fwd_elem_fast<MODEL>(a, row[rr], i, b, f4get(u4[cc], rr), xin0[cc], xin1[cc], f4get(xd4[cc], rr),
                                                  f4get(v4[cc], rr), f4get(s4[cc], rr), f4get(x4[cc], rr), v1[rr], s1[rr], x1[rr]);
                         }
                         float src1;
-                        if constexpr (ModelTraits<MODEL>::SPIKING) src1 = s1[rr]; else src1 = rate_act<MODEL>(a.mp, i, v1[rr]);
+                        if constexpr (ModelTraits<MODEL>::SPIKING) src1 = s1[rr]; else src1 = rate_act<MODEL>(a.mp, i, v1[rr], b);
                         split_tf32(src1, hi[rr], lo[rr]);
                     }
                     if (MODEL == RP_IK && a.urec_out) *reinterpret_cast<float4*>(a.urec_out + idx) = u4[cc];

@@ -31,11 +31,13 @@ __host__ __device__ inline PWindow pwindow_of(int t, int T, int S, int cutoff) {
 
 struct ModelParams {
     const float* p[RP_NUM_PARAMS];
-    int stride[RP_NUM_PARAMS];   // 0: shared scalar, 1: per neuron
+    int stride[RP_NUM_PARAMS];   // neuron stride: 0 shared, 1 per neuron
+    int bstride[RP_NUM_PARAMS];  // trial stride: 0 shared across trials, 1 per trial ([B]), N per trial and neuron ([B][N])
 };
 
-__device__ __forceinline__ float ldp(const ModelParams& mp, int which, int i) {
-    return __ldg(mp.p[which] + (size_t)i * mp.stride[which]);
+// parameter `which` of neuron i in trial b (parameter sweeps give every trial its own value)
+__device__ __forceinline__ float ldp(const ModelParams& mp, int which, int i, int b = 0) {
+    return __ldg(mp.p[which] + (size_t)b * mp.bstride[which] + (size_t)i * mp.stride[which]);
 }
 
 template <int MODEL> struct ModelTraits;
@@ -52,21 +54,21 @@ __host__ __device__ constexpr int fold_slot(int model) { return model == RP_IK ?
 
 // activation of the rate templates (leaky_integrator.yaml:20-36) and its derivative w.r.t. v
 template <int MODEL>
-__device__ __forceinline__ float rate_act(const ModelParams& mp, int i, float v) {
+__device__ __forceinline__ float rate_act(const ModelParams& mp, int i, float v, int b = 0) {
     if constexpr (MODEL == RP_LI_TANH) {
         return tanhf(v);
     } else {
-        float rmax = ldp(mp, RP_P_RMAX, i), s = ldp(mp, RP_P_SIG_S, i), v0 = ldp(mp, RP_P_V0, i);
+        float rmax = ldp(mp, RP_P_RMAX, i, b), s = ldp(mp, RP_P_SIG_S, i, b), v0 = ldp(mp, RP_P_V0, i, b);
         return rmax / (1.0f + expf(s * (v0 - v)));
     }
 }
 template <int MODEL>
-__device__ __forceinline__ float rate_act_grad(const ModelParams& mp, int i, float v) {
+__device__ __forceinline__ float rate_act_grad(const ModelParams& mp, int i, float v, int b = 0) {
     if constexpr (MODEL == RP_LI_TANH) {
         float r = tanhf(v);
         return 1.0f - r * r;
     } else {
-        float rmax = ldp(mp, RP_P_RMAX, i), s = ldp(mp, RP_P_SIG_S, i), v0 = ldp(mp, RP_P_V0, i);
+        float rmax = ldp(mp, RP_P_RMAX, i, b), s = ldp(mp, RP_P_SIG_S, i, b), v0 = ldp(mp, RP_P_V0, i, b);
         float r = rmax / (1.0f + expf(s * (v0 - v)));
         return s * r * (1.0f - r / rmax);
     }
@@ -102,27 +104,28 @@ struct FwdStepArgs {
     float* src_lo;
     int ld_src;
     float* urec_out;      // ik: checkpoint plane receiving the recurrent drive of this step [B][N], or nullptr
+    int per_trial;        // 1: some parameter differs between trials (no per-neuron hoisting)
 };
 
 template <int MODEL>
 __device__ __forceinline__ void fwd_elem(const FwdStepArgs& a, int i, float u, float Iin,
-                                         float v, float s, float x, float& v1, float& s1, float& x1) {
+                                         float v, float s, float x, float& v1, float& s1, float& x1, int b = 0) {
     const float dt = a.dt;
-    const float tau = MODEL == RP_IK ? 1.f : ldp(a.mp, RP_P_TAU, i), eta = ldp(a.mp, RP_P_ETA, i);
+    const float tau = MODEL == RP_IK ? 1.f : ldp(a.mp, RP_P_TAU, i, b), eta = ldp(a.mp, RP_P_ETA, i, b);
     if constexpr (!ModelTraits<MODEL>::SPIKING) {
         // li_op: v' = -v/tau + k*r_in + I_ext + eta          (leaky_integrator.yaml:10)
         v1 = v + dt * (-v / tau + u + Iin + eta);
         s1 = 0.f; x1 = 0.f;
     } else {
-        const float tau_s = ldp(a.mp, RP_P_TAU_S, i);
+        const float tau_s = ldp(a.mp, RP_P_TAU_S, i, b);
         const bool p = v >= a.theta;                           // heaviside(v-theta, 1.0)   nodes.py:383,476
         const float pf = p ? 1.0f : 0.0f;
         float vt;
         if constexpr (MODEL == RP_IK) {
             // ik_op (ik.yaml:10-13): v' = (k (v-v_r)(v-v_theta) - u + I_ext + eta + g s_in (E_r - v)) / C
             //                        u' = (b (v-v_r) - u)/tau_u + kappa*spike ;  s' = -s/tau_s + spike      (x holds u, u holds g*W.s)
-            const float C = ldp(a.mp, RP_P_C, i), kq = ldp(a.mp, RP_P_K, i), vr = ldp(a.mp, RP_P_VR, i), vth = ldp(a.mp, RP_P_VTH, i);
-            const float Er = ldp(a.mp, RP_P_ER, i), bb = ldp(a.mp, RP_P_B, i), tau_u = ldp(a.mp, RP_P_TAU_U, i), kappa = ldp(a.mp, RP_P_KAPPA, i);
+            const float C = ldp(a.mp, RP_P_C, i, b), kq = ldp(a.mp, RP_P_K, i, b), vr = ldp(a.mp, RP_P_VR, i, b), vth = ldp(a.mp, RP_P_VTH, i, b);
+            const float Er = ldp(a.mp, RP_P_ER, i, b), bb = ldp(a.mp, RP_P_B, i, b), tau_u = ldp(a.mp, RP_P_TAU_U, i, b), kappa = ldp(a.mp, RP_P_KAPPA, i, b);
             vt = v + dt * ((kq * (v - vr) * (v - vth) - x + Iin + eta + u * (Er - v)) / C);
             x1 = x + dt * ((bb * (v - vr) - x) / tau_u) + kappa * pf;
             s1 = s + dt * (-s / tau_s) + pf;
@@ -139,7 +142,7 @@ __device__ __forceinline__ void fwd_elem(const FwdStepArgs& a, int i, float u, f
             vt = v + dt * ((v * v + eta - xx + Iin) / tau + u);
             s1 = s + dt * (-s / tau_s) + pf;                  // dt * (spike/dt) == 1 per spike  nodes.py:385
             if constexpr (MODEL == RP_QIF_SFA) {
-                const float tau_x = ldp(a.mp, RP_P_TAU_X, i), alpha = ldp(a.mp, RP_P_ALPHA, i);
+                const float tau_x = ldp(a.mp, RP_P_TAU_X, i, b), alpha = ldp(a.mp, RP_P_ALPHA, i, b);
                 x1 = x + dt * (-x / tau_x) + alpha * pf;      // x' = -x/tau_x + alpha*spike     (qif.yaml:31)
             } else {
                 x1 = 0.f;
@@ -222,13 +225,13 @@ __device__ __forceinline__ void fwd_element(const FwdStepArgs& a, int i, int b, 
     const float x = NSV > 2 ? a.y_cur[2 * plane + idx] : 0.f;
     const float Iin = input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i);
     float v1, s1, x1;
-    fwd_elem<MODEL>(a, i, u, Iin, v, s, x, v1, s1, x1);
+    fwd_elem<MODEL>(a, i, u, Iin, v, s, x, v1, s1, x1, b);
     if (MODEL == RP_IK && a.urec_out) a.urec_out[idx] = u;
     a.y_next[idx] = v1;
     if (NSV > 1) a.y_next[plane + idx] = s1;
     if (NSV > 2) a.y_next[2 * plane + idx] = x1;
     float src1;
-    if constexpr (ModelTraits<MODEL>::SPIKING) src1 = s1; else src1 = rate_act<MODEL>(a.mp, i, v1);
+    if constexpr (ModelTraits<MODEL>::SPIKING) src1 = s1; else src1 = rate_act<MODEL>(a.mp, i, v1, b);
     if (a.src_next) a.src_next[idx] = src1;
     if (a.src_hi) {
         float hi, lo;
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(256) k_init_src(int N, int B, const float* y, 
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane; idx += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(idx / N), i = (int)(idx - (size_t)b * N);
         float r;
-        if constexpr (ModelTraits<MODEL>::SPIKING) r = y[plane + idx]; else r = rate_act<MODEL>(mp, i, y[idx]);
+        if constexpr (ModelTraits<MODEL>::SPIKING) r = y[plane + idx]; else r = rate_act<MODEL>(mp, i, y[idx], b);
         if (src) src[(size_t)b * ld_plain + i] = r;
         if (src_hi) {
             float hi, lo;
@@ -292,7 +295,7 @@ template <int MODEL>
 __device__ __forceinline__ float out_value(const ObsArgs& a, const float* y, size_t plane, int b, int i) {
     const size_t idx = (size_t)b * a.N + i;
     if (a.out_var == RP_VAR_R) {
-        if constexpr (!ModelTraits<MODEL>::SPIKING) return rate_act<MODEL>(a.mp, i, y[idx]);
+        if constexpr (!ModelTraits<MODEL>::SPIKING) return rate_act<MODEL>(a.mp, i, y[idx], b);
         else return 0.f;
     }
     return y[(size_t)a.out_var * plane + idx];
@@ -396,6 +399,7 @@ struct AdjArgs {
     float* dW_out;         // [k][N] or nullptr
     float* g_x_t;          // dense input gradient of step t [B][N] or nullptr
     int any_param_grad;
+    int per_trial;         // 1: some parameter differs between trials (no per-neuron hoisting)
 };
 
 constexpr int ADJ_TX = 32, ADJ_TY = 8, ADJ_BPT = 8;   // block covers 32 neurons x 64 trials
@@ -444,12 +448,12 @@ struct NoAcc { __device__ __forceinline__ void add(int, float) const {} };
 struct AdjRowParams { float tau, tau_s, tau_x, alpha; };
 
 template <int MODEL>
-__device__ __forceinline__ AdjRowParams adj_row_params(const AdjArgs& a, int i) {
+__device__ __forceinline__ AdjRowParams adj_row_params(const AdjArgs& a, int i, int b = 0) {
     AdjRowParams r{1.f, 1.f, 1.f, 0.f};
     if (i < a.N) {
-        if (MODEL != RP_IK) r.tau = ldp(a.mp, RP_P_TAU, i);
-        if (ModelTraits<MODEL>::SPIKING) r.tau_s = ldp(a.mp, RP_P_TAU_S, i);
-        if (MODEL == RP_QIF_SFA) { r.tau_x = ldp(a.mp, RP_P_TAU_X, i); r.alpha = ldp(a.mp, RP_P_ALPHA, i); }
+        if (MODEL != RP_IK) r.tau = ldp(a.mp, RP_P_TAU, i, b);
+        if (ModelTraits<MODEL>::SPIKING) r.tau_s = ldp(a.mp, RP_P_TAU_S, i, b);
+        if (MODEL == RP_QIF_SFA) { r.tau_x = ldp(a.mp, RP_P_TAU_X, i, b); r.alpha = ldp(a.mp, RP_P_ALPHA, i, b); }
     }
     return r;
 }
@@ -466,7 +470,7 @@ __device__ __forceinline__ float adj_post_math(const AdjArgs& a, const AdjRowPar
     if (a.e_t) {
         if (a.out_var == RP_VAR_V) yout = v; else if (a.out_var == RP_VAR_S) yout = s;
         else if (a.out_var == RP_VAR_X) yout = x;
-        else { if constexpr (!SPK) yout = rate_act<MODEL>(a.mp, i, v); }
+        else { if constexpr (!SPK) yout = rate_act<MODEL>(a.mp, i, v, b); }
         if (a.out_mode == RP_OUT_DENSE) {
             ro = __ldg(a.e_t + (size_t)b * a.N + i) * a.e_scale;
         } else {
@@ -483,7 +487,7 @@ __device__ __forceinline__ float adj_post_math(const AdjArgs& a, const AdjRowPar
     float dI = 0.f;
     float nav, nas = 0.f, nax = 0.f;
     if constexpr (!SPK) {
-        const float rg = rate_act_grad<MODEL>(a.mp, i, v);
+        const float rg = rate_act_grad<MODEL>(a.mp, i, v, b);
         nav = av * (1.0f - dt / tau) + rg * Z;
         if (a.out_var == RP_VAR_V) nav += ro; else if (a.out_var == RP_VAR_R) nav += rg * ro;
         dI = dt * av;
@@ -496,9 +500,9 @@ __device__ __forceinline__ float adj_post_math(const AdjArgs& a, const AdjRowPar
         const float sg = 1.0f / (d * d);                 // Spike.backward          nodes.py:478-481
         if constexpr (MODEL == RP_IK) {
             // x == u (recovery variable), ax == its adjoint; urec = g*(W s_t) of the forward step
-            const float C = ldp(a.mp, RP_P_C, i), kq = ldp(a.mp, RP_P_K, i), vr = ldp(a.mp, RP_P_VR, i), vth = ldp(a.mp, RP_P_VTH, i);
-            const float Er = ldp(a.mp, RP_P_ER, i), bb = ldp(a.mp, RP_P_B, i), tau_u = ldp(a.mp, RP_P_TAU_U, i), kappa = ldp(a.mp, RP_P_KAPPA, i);
-            const float eta = ldp(a.mp, RP_P_ETA, i);
+            const float C = ldp(a.mp, RP_P_C, i, b), kq = ldp(a.mp, RP_P_K, i, b), vr = ldp(a.mp, RP_P_VR, i, b), vth = ldp(a.mp, RP_P_VTH, i, b);
+            const float Er = ldp(a.mp, RP_P_ER, i, b), bb = ldp(a.mp, RP_P_B, i, b), tau_u = ldp(a.mp, RP_P_TAU_U, i, b), kappa = ldp(a.mp, RP_P_KAPPA, i, b);
+            const float eta = ldp(a.mp, RP_P_ETA, i, b);
             const float pf = p ? 1.0f : 0.0f;
             nav = gv * (1.0f + dt * (kq * (2.0f * v - vr - vth) - urec) / C) + ax * dt * bb / tau_u + sg * (as + kappa * ax);
             nas = as * (1.0f - dt / tau_s) + Z;
@@ -525,7 +529,7 @@ __device__ __forceinline__ float adj_post_math(const AdjArgs& a, const AdjRowPar
             acc.add(RP_P_TAU_S, as * s * dt / (tau_s * tau_s));
         } else {
             const float Iin = a.dparams[RP_P_TAU] ? input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i) : 0.f;
-            const float eta = ldp(a.mp, RP_P_ETA, i);
+            const float eta = ldp(a.mp, RP_P_ETA, i, b);
             nav = gv * (1.0f + 2.0f * dt * v / tau) + sg * (as + alpha * ax);
             nas = as * (1.0f - dt / tau_s) + Z;
             dI = dt / tau * gv;
@@ -552,12 +556,12 @@ __device__ __forceinline__ float adj_post_math(const AdjArgs& a, const AdjRowPar
 
 // "pre" of reverse step t-1: g_{t-1} = dt * gate_{t-1} * a_t  and the source value r_{t-1};  (vm, sm) = (v, s) of y_{t-1}
 template <int MODEL>
-__device__ __forceinline__ void adj_pre_math(const AdjArgs& a, int i, float av, float vm, float sm, float& g, float& srcv) {
+__device__ __forceinline__ void adj_pre_math(const AdjArgs& a, int i, float av, float vm, float sm, float& g, float& srcv, int b = 0) {
     float gate = 1.0f;
     if constexpr (ModelTraits<MODEL>::SPIKING) { gate = (vm >= a.theta) ? 0.f : 1.0f; srcv = sm; }
-    else srcv = rate_act<MODEL>(a.mp, i, vm);
+    else srcv = rate_act<MODEL>(a.mp, i, vm, b);
     g = a.dt * gate * av;
-    if constexpr (MODEL == RP_IK) g *= (ldp(a.mp, RP_P_ER, i) - vm) / ldp(a.mp, RP_P_C, i);    // d v' / d(g W s) = dt (E_r - v) / C
+    if constexpr (MODEL == RP_IK) g *= (ldp(a.mp, RP_P_ER, i, b) - vm) / ldp(a.mp, RP_P_C, i, b);    // d v' / d(g W s) = dt (E_r - v) / C
 }
 
 // scalar driver: loads, math, stores for element (neuron c.i, trial b)
@@ -574,7 +578,7 @@ __device__ __forceinline__ void adj_element(const AdjArgs& a, AdjCtx<MODEL>& c, 
         const float v = __ldg(a.y_t + idx);
         const float s = NSV > 1 ? __ldg(a.y_t + plane + idx) : 0.f;
         const float x = NSV > 2 ? __ldg(a.y_t + 2 * plane + idx) : 0.f;
-        const AdjRowParams rp_{c.tau, c.tau_s, c.tau_x, c.alpha};
+        const AdjRowParams rp_ = a.per_trial ? adj_row_params<MODEL>(a, i, b) : AdjRowParams{c.tau, c.tau_s, c.tau_x, c.alpha};
         const RegAcc acc{c.acc};
         const float urec = (MODEL == RP_IK && a.urec_t) ? __ldg(a.urec_t + idx) : 0.f;
         const float dI = adj_post_math<MODEL>(a, rp_, acc, i, b, Z, v, s, x, av, as, ax, urec);
@@ -588,7 +592,7 @@ __device__ __forceinline__ void adj_element(const AdjArgs& a, AdjCtx<MODEL>& c, 
         const float vm = __ldg(a.y_tm1 + idx);
         const float sm = NSV > 1 ? __ldg(a.y_tm1 + plane + idx) : 0.f;
         float g, srcv;
-        adj_pre_math<MODEL>(a, i, av, vm, sm, g, srcv);
+        adj_pre_math<MODEL>(a, i, av, vm, sm, g, srcv, b);
         if (a.g) a.g[idx] = g;
         if (a.src) a.src[idx] = srcv;
         if (a.g_hi) {
@@ -634,7 +638,7 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
     constexpr int NSV = ModelTraits<MODEL>::NSV;
     constexpr int BATCH = 4;
     const size_t plane = (size_t)a.B * a.N;
-    const AdjRowParams rp_{c.tau, c.tau_s, c.tau_x, c.alpha};
+    const AdjRowParams rp0{c.tau, c.tau_s, c.tau_x, c.alpha};
     const RegAcc racc{c.acc};
     for (int l0 = 0; l0 < ADJ_BPT; l0 += BATCH) {
         float av[BATCH], as[BATCH], ax[BATCH], v[BATCH], s[BATCH], x[BATCH], vm[BATCH], sm[BATCH], Z[BATCH], ur[BATCH];
@@ -670,6 +674,7 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
             float g = 0.f, srcv = 0.f;
             if (ok[l]) {
                 if (a.do_post) {
+                    const AdjRowParams rp_ = a.per_trial ? adj_row_params<MODEL>(a, i, b) : rp0;
                     const float dI = adj_post_math<MODEL>(a, rp_, racc, i, b, Z[l], v[l], s[l], x[l], av[l], as[l], ax[l], ur[l]);
                     if (a.g_x_t) a.g_x_t[idx] = dI;
                     a.adj[idx] = av[l];
@@ -677,7 +682,7 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
                     if (NSV > 2) a.adj[2 * plane + idx] = ax[l];
                 }
                 if (a.do_pre) {
-                    adj_pre_math<MODEL>(a, i, av[l], vm[l], sm[l], g, srcv);
+                    adj_pre_math<MODEL>(a, i, av[l], vm[l], sm[l], g, srcv, b);
                     if (a.g) a.g[idx] = g;
                     if (a.src) a.src[idx] = srcv;
                     if (a.g_hi) {
@@ -785,7 +790,7 @@ __global__ void __launch_bounds__(128) k_readout_grad(int N, int B, int T, int S
 #pragma unroll 4
             for (int b = 0; b < B; ++b) {
                 float y = __ldg(yt + (size_t)b * N);
-                if (out_var == RP_VAR_R) { if constexpr (!ModelTraits<MODEL>::SPIKING) y = rate_act<MODEL>(mp, i, y); }
+                if (out_var == RP_VAR_R) { if constexpr (!ModelTraits<MODEL>::SPIKING) y = rate_act<MODEL>(mp, i, y, b); }
                 y *= sc;
 #pragma unroll
                 for (int q = 0; q < RP_MAX_OUT; ++q) if (q < k) acc[q] = fmaf(__ldg(e + (size_t)b * k + q), y, acc[q]);

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
     const int nvec = N >> 2;
     if (own && a.T > 0) {      // publish r_0 (tag 1) into slot 0
         float src0;
-        if constexpr (SPK) src0 = s; else src0 = rate_act<MODEL>(a.mp, i, v);
+        if constexpr (SPK) src0 = s; else src0 = rate_act<MODEL>(a.mp, i, v, b);
         ll_store(a.srcbuf + (size_t)b * Npad + i, src0, 1u);
     }
     __syncthreads();
@@ -186,9 +186,9 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
             }
             float v1, s1, x1;
             const float urec = s_u[r * PS_MAX_B + b];
-            fwd_elem<MODEL>(fa, i, urec, Iin, v, s, x, v1, s1, x1);
+            fwd_elem<MODEL>(fa, i, urec, Iin, v, s, x, v1, s1, x1, b);
             float src1;
-            if constexpr (SPK) src1 = s1; else src1 = rate_act<MODEL>(a.mp, i, v1);
+            if constexpr (SPK) src1 = s1; else src1 = rate_act<MODEL>(a.mp, i, v1, b);
             if (t + 1 < a.T) ll_store(a.srcbuf + (size_t)((t + 1) & 1) * B * Npad + (size_t)b * Npad + i, src1, (unsigned int)(t + 2));
             if (a.history) {
                 constexpr int NH = HistPlanes<MODEL>::N;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
                     float yout;
                     if (a.out_var == RP_VAR_V) yout = v; else if (a.out_var == RP_VAR_S) yout = s;
                     else if (a.out_var == RP_VAR_X) yout = x;
-                    else { if constexpr (!SPK) yout = rate_act<MODEL>(a.mp, i, v); else yout = 0.f; }
+                    else { if constexpr (!SPK) yout = rate_act<MODEL>(a.mp, i, v, b); else yout = 0.f; }
                     if (a.out_mode == RP_OUT_DENSE) {
                         win_sum = w.first ? yout : win_sum + yout;
                         if (w.close) a.out_rec[((size_t)w.j * B + b) * N + i] = win_sum / (float)w.len;
@@ -302,12 +302,12 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
     aa.out_mode = a.out_mode; aa.out_var = a.out_var; aa.dt = a.dt; aa.theta = a.theta; aa.slope = a.slope;
     aa.W_in = a.W_in; aa.W_out = a.W_out; aa.mp = a.mp; aa.dW_in = a.dW_in; aa.dW_out = a.dW_out;
     for (int q = 0; q < RP_NUM_PARAMS; ++q) aa.dparams[q] = a.dparams[q];
-    aa.x_t = nullptr; aa.e_t = nullptr; aa.e_scale = 0.f; aa.zero_after_post = 0;
+    aa.x_t = nullptr; aa.e_t = nullptr; aa.e_scale = 0.f; aa.zero_after_post = 0; aa.per_trial = 0;
     AdjRowParams rowp{1.f, 1.f, 1.f, 0.f};
     if (own) {
         const size_t idx = (size_t)b * N + i;
         if (a.g_yT) { av = a.g_yT[idx]; if (NSV > 1) as = a.g_yT[plane + idx]; if (NSV > 2) ax = a.g_yT[2 * plane + idx]; }
-        rowp = adj_row_params<MODEL>(aa, i);
+        rowp = adj_row_params<MODEL>(aa, i, b);
     }
     const float dt = a.dt;
     const int nvec = N >> 2;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
         const size_t idx = (size_t)b * N + i;
         const float vm = a.history[(size_t)tm1 * slot + idx];
         float g, srcv;
-        adj_pre_math<MODEL>(aa, i, av, vm, 0.f, g, srcv);
+        adj_pre_math<MODEL>(aa, i, av, vm, 0.f, g, srcv, b);
         return g;
     };
     // reverse step t consumes g_t carrying tag T - t (1, 2, ... as t runs down)
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
             const size_t idx = (size_t)b * N + i;
             float rv;
             if constexpr (SPK) rv = a.history[(size_t)t * slot + plane + idx];
-            else rv = rate_act<MODEL>(a.mp, i, a.history[(size_t)t * slot + idx]);
+            else rv = rate_act<MODEL>(a.mp, i, a.history[(size_t)t * slot + idx], b);
             s_src[r * PS_MAX_B + b] = rv;
         }
         __syncthreads();

@@ -57,11 +57,15 @@ class InstantNode:
         return self.func.parameters(**kwargs)
 
 
-def _as_param(val, n: int, device) -> torch.Tensor:
+def _as_param(val, n: int, device, batch: int = 1) -> torch.Tensor:
+    """scalar -> [1]; one value per neuron -> [n]; parameter sweeps: [B, 1] (one value per trial) or [B, n]."""
     t = torch.as_tensor(np.asarray(val, dtype=np.float32) if not isinstance(val, torch.Tensor) else val.detach().to(torch.float32))
+    if t.dim() == 2 and batch > 1 and t.shape[0] == batch and t.shape[1] in (1, n):
+        return t.to(device).contiguous().clone()
     t = t.reshape(-1).to(device).clone()
     if t.numel() not in (1, n):
-        raise ValueError(f"node parameter must be a scalar or have one value per neuron ({n}), got {t.numel()} values")
+        raise ValueError(f"node parameter must be a scalar, have one value per neuron ({n}), or be a [batch, 1] / [batch, {n}] "
+                         f"sweep; got shape {tuple(np.shape(val))}")
     return t
 
 
@@ -94,7 +98,7 @@ class RateNet:
         for key, val in (node_vars or {}).items():
             try:
                 pkey = spec.resolve(key, spec.params)
-                self._params[pkey] = _as_param(val, self.n, self.device)
+                self._params[pkey] = _as_param(val, self.n, self.device, self.batch)
             except KeyError:
                 try:
                     vkey = spec.resolve(key, dict(spec.state_vars))
@@ -121,6 +125,8 @@ class RateNet:
         for p in (train_params or []):
             self._train_keys.append(self._param_key(p))
         for k in self._train_keys:
+            if k != "weights" and self._params[k].dim() == 2:
+                raise NotImplementedError(f"rectipy_b200: per-trial parameter {k} (a sweep) cannot be trained")
             self._params[k].requires_grad_(True)
         # state: [n_sv, B, n]
         st = torch.empty((spec.n_sv, self.batch, self.n), dtype=torch.float32)
@@ -238,7 +244,7 @@ class RateNet:
         if key == "weights":
             new = torch.as_tensor(val).detach().to(device=self.device, dtype=torch.float32).reshape(self.n, self.n).clone()
         else:
-            new = _as_param(val, self.n, self.device)
+            new = _as_param(val, self.n, self.device, self.batch)
         new.requires_grad_(old.requires_grad)
         self._params[key] = new
 
@@ -285,7 +291,10 @@ class RateNet:
             t = self._params[key]
             slots.append(slot)
             tensors.append(t)
-            per_neuron[slot] = 1 if (t.numel() == self.n and self.n > 1) else 0
+            if t.dim() == 2:                      # parameter sweep: [B, 1] or [B, n]
+                per_neuron[slot] = 3 if t.shape[1] == self.n and self.n > 1 else 2
+            else:
+                per_neuron[slot] = 1 if (t.numel() == self.n and self.n > 1) else 0
         return tuple(slots), tensors, tuple(per_neuron)
 
     @property

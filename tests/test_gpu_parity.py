@@ -460,3 +460,60 @@ def test_checkpoint_recompute_segments_match_full_history(model, n, B, prec, mon
     errs = {key: rel_err(res["segmented"][key], res["full"][key]) for key in res["full"]}
     print(model, errs)
     assert all(e <= 2e-5 for e in errs.values()), errs
+
+
+@pytest.mark.parametrize("model,n,B,prec", [("qif", 40, 3, "fp32"), ("li_tanh", 50, 20, "fp32"), ("qif", 128, 128, "3xtf32"), ("li_sigmoid", 128, 128, "3xtf32")])
+def test_parameter_sweep_per_trial_values(model, n, B, prec):
+    """Parameter sweep: every trial carries its own parameter values ([B,1] and [B,n] tensors).  Each trial must equal the
+    reference path run on its own with that trial's parameters; the recurrent weights (and their gradient) are shared."""
+    import rectipy_b200 as rp
+    from golden_util import TEMPLATE_PATH
+    rng = np.random.default_rng(n + 7 * B)
+    rate = model.startswith("li_")
+    dt, T, S = (1e-2, 100, 2) if rate else (1e-3, 300, 3)
+    m, k = 2, 2
+    W = rng.standard_normal((n, n)) * (1.5 if rate else 2.0) / np.sqrt(n)
+    w_in, w_out = rng.standard_normal((n, m)), rng.standard_normal((k, n)) / np.sqrt(n)
+    path, op, svar, tvar = TEMPLATE_PATH[model]
+    eta_sweep = (rng.uniform(-1, 1, (B, 1)) if rate else rng.uniform(-8, 2, (B, 1)))                 # one value per trial
+    tau_sweep = rng.uniform(0.8, 2.0, (B, n))                                                       # per trial and neuron
+    node_vars = {f"{op}/eta": eta_sweep, f"{op}/tau": tau_sweep, f"{op}/k": 1.3}
+    if model == "li_sigmoid":
+        node_vars["sigmoid_op/r_max"] = rng.uniform(0.5, 2.0, (B, 1))
+    t = np.arange(T) * dt
+    amp, off = (1.5, 0.0) if rate else (10.0, 14.0)
+    x = amp * np.sin(2 * np.pi * rng.uniform(0.5, 3, (1, B, m)) * t[:, None, None] + rng.uniform(0, 6.28, (1, B, m))) + off
+    net = rp.Network(dt, device="cuda:0", batch=B, precision=prec)
+    kw = dict(weights=W, source_var=svar, target_var=tvar, input_var=f"{op}/I_ext", node_vars=node_vars, train_params=["weights"])
+    if not rate:
+        kw.update(spike_var=f"{op}/spike", reset_var=f"{op}/v", output_var=f"{op}/s")
+    else:
+        kw.update(output_var=f"{op}/v")
+    node = net.add_diffeq_node("rnn", path, **kw)
+    net.add_func_node("inp", m, "identity"); net.add_edge("inp", "rnn", weights=w_in)
+    net.add_func_node("out", k, "identity"); net.add_edge("rnn", "out", weights=w_out)
+    obs = net.run(x, sampling_steps=S, verbose=False, enable_grad=True)
+    out = torch.stack(obs["out"])
+    out.square().sum().backward()
+    gW = node["weights"].grad.cpu().numpy()
+    gW_ref = np.zeros_like(gW, dtype=np.float64)
+    sample = range(B) if B <= 20 else (0, 1, B // 2, B - 1)
+    for b in sample:
+        params = dict(eta=float(eta_sweep[b, 0]), tau=tau_sweep[b], k=1.3)
+        if model == "li_sigmoid":
+            params["r_max"] = float(node_vars["sigmoid_op/r_max"][b, 0])
+        onode = orc.make_node(model, n, W, dt, params=params, dtype=torch.float64, train_params=["weights"])
+        onet = orc.OracleNet(onode, w_in=torch.tensor(w_in), w_out=torch.tensor(w_out))
+        r = onet.run(torch.tensor(x[:, b, :]), sampling_steps=S, enable_grad=True)
+        ref = torch.stack(r["out"])
+        ref.square().sum().backward()
+        gW_ref += onode.get("weights").grad.numpy()
+        assert rel_err(out[:, b, :].detach().cpu().numpy(), ref.detach().numpy()) < (1e-5 if rate else 1e-4), (b,)
+    if B <= 20:
+        assert rel_err(gW, gW_ref) < (1e-5 if rate else 2e-3)
+    with pytest.raises(NotImplementedError):
+        rp.Network(dt, device="cuda:0", batch=B).add_diffeq_node("rnn", path, **{**kw, "train_params": [f"{op}/eta"]})
+    with pytest.raises(RuntimeError):      # the coupling constant is folded into the shared weights
+        bad = rp.Network(dt, device="cuda:0", batch=B, precision=prec)
+        bad.add_diffeq_node("rnn", path, **{**kw, "node_vars": {f"{op}/k": np.ones((B, 1))}, "train_params": None})
+        bad.run(x, verbose=False, enable_grad=False)
