@@ -75,6 +75,9 @@ struct rp_plan {
     float* win_acc = nullptr;// [B][N]
     float* pp = nullptr;     // [2][nsv][B][N] ping-pong state when no history is kept
     float* dWraw = nullptr;  // [N][ldw]
+    float* wg_g = nullptr;   // few-trial FFMA path: g_t and r_t of several steps, [chunk*B][N] each, so that the
+    float* wg_src = nullptr; // read-modify-write of dW happens once per chunk (rank chunk*B update) instead of every step
+    int wg_chunk = 0;
     // persistent few-trial path (rp_persistent.cuh)
     bool persistent = false;
     int ps_rows = 0, ps_grid = 0, ps_npad = 0;
@@ -397,7 +400,7 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
 
 void rp_plan_destroy(rp_plan* p) {
     if (!p) return;
-    float* bufs[] = {p->Wk, p->WkT, p->u, p->g, p->src, p->adj, p->win_acc, p->pp, p->dWraw, p->ps_vec};
+    float* bufs[] = {p->Wk, p->WkT, p->u, p->g, p->src, p->adj, p->win_acc, p->pp, p->dWraw, p->ps_vec, p->wg_g, p->wg_src};
     for (float* b : bufs) if (b) cudaFree(b);
     if (p->ps_bar) cudaFree(p->ps_bar);
     rp::tc_workspace_destroy(&p->tc);
@@ -575,12 +578,20 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     const bool truncating = tr > 0 && tr < T_tot;
     const int wg_chunk = p->use_tc ? p->tc.wgrad_chunk : 1;
 
+    // few trials on the FFMA path: batch the rank-B weight-gradient updates of `wg_chunk` steps into one contraction
+    const bool wg_batched = !p->use_tc && need_dW && B <= 16;
+    if (wg_batched && !p->wg_g) {
+        p->wg_chunk = std::max(1, 64 / B);
+        if (plan_alloc(p, &p->wg_g, (size_t)p->wg_chunk * plane) || plan_alloc(p, &p->wg_src, (size_t)p->wg_chunk * plane)) return 1;
+    }
+    int wg_pos = 0;                 // chunk slot holding (g_t, r_t) of the step being processed
+
     rp::AdjArgs aa;
     memset(&aa, 0, sizeof(aa));
     aa.N = N; aa.B = B; aa.m = d.n_in; aa.k = d.n_out; aa.in_mode = d.in_mode; aa.in_target = d.in_target;
     aa.out_mode = d.out_mode; aa.out_var = d.out_var; aa.dt = d.dt; aa.theta = d.theta; aa.slope = d.slope;
     aa.adj = p->adj; aa.Z = p->u; aa.ldz = p->ldu; aa.W_in = a->W_in; aa.W_out = a->W_out; aa.mp = mp;
-    if (!p->use_tc) { aa.g = p->g; aa.src = spk ? nullptr : p->src; }
+    if (!p->use_tc) { aa.g = wg_batched ? p->wg_g : p->g; aa.src = spk ? nullptr : (wg_batched ? p->wg_src : p->src); }
     else { aa.g_hi = p->tc.g_hi; aa.g_lo = p->tc.g_lo; aa.ld_g = p->tc.ldk; aa.ld_t = p->tc.ldt; }
     for (int q = 0; q < RP_NUM_PARAMS; ++q) aa.dparams[q] = (q == fold) ? nullptr : a->dparams[q];
     aa.dW_in = a->dW_in; aa.dW_out = a->dW_out;
@@ -607,10 +618,21 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         if (aa.do_post) {
             // Z[b][j] = sum_i (kW)^T[j][i] g_t[b][i]
             if (!p->use_tc) {
-                if (gemm_fp32(p, true, N, B, N, p->WkT, p->ldw, p->g, N, p->u, p->ldu, 0, st, &p->launches)) return 1;
+                const float* g_cur = wg_batched ? p->wg_g + (size_t)wg_pos * plane : p->g;
+                if (gemm_fp32(p, true, N, B, N, p->WkT, p->ldw, g_cur, N, p->u, p->ldu, 0, st, &p->launches)) return 1;
                 if (need_dW) {
                     const float* srcp = spk ? a->history + (size_t)t * hslot + plane : p->src;
-                    if (B <= 16) {
+                    if (wg_batched) {
+                        if (spk) RP_CUDA(cudaMemcpyAsync(p->wg_src + (size_t)wg_pos * plane, srcp, plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                        if (wg_pos + 1 == p->wg_chunk || t == 0) {
+                            // dWraw[i][j] += sum over the chunk's (step, trial) rows of r[j] * g[i]
+                            if (gemm_fp32(p, false, N, N, (wg_pos + 1) * B, p->wg_src, N, p->wg_g, N, p->dWraw, p->ldw, 1, st, &p->launches)) return 1;
+                            wg_pos = -1;
+                        }
+                        ++wg_pos;
+                        aa.g = p->wg_g + (size_t)wg_pos * plane;                 // where this launch's "pre" puts g_{t-1}, r_{t-1}
+                        if (!spk) aa.src = p->wg_src + (size_t)wg_pos * plane;
+                    } else if (B <= 16) {
                         dim3 og((N + 255) / 256, N);
                         rp::k_outer_acc<<<og, 256, 0, st>>>(N, B, p->g, N, srcp, N, p->dWraw, p->ldw);
                         ++p->launches;
