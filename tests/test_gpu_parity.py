@@ -186,6 +186,7 @@ def test_tensor_core_path_matches_fp32_path(model):
     x = amp * np.sin(2 * np.pi * rng.uniform(0.5, 3, (1, B, m)) * t[:, None, None] + rng.uniform(0, 6.28, (1, B, m))) + off
     targets = torch.tensor(rng.standard_normal((len(range(0, T, S)), B, k)), dtype=torch.float32, device="cuda")
     path, op, svar, tvar = TEMPLATE_PATH[model]
+    y_init = np.concatenate([rng.uniform(-50.0, 99.0, (B, n)), np.zeros((B, n))], axis=1).astype(np.float32)
     results = {}
     for prec in ("fp32", "3xtf32"):
         net = rp.Network(dt, device="cuda:0", batch=B, precision=prec)
@@ -198,6 +199,8 @@ def test_tensor_core_path_matches_fp32_path(model):
         node = net.add_diffeq_node("rnn", path, **kw)
         net.add_func_node("inp", m, "identity"); net.add_edge("inp", "rnn", weights=w_in, train="gd")
         net.add_func_node("out", k, "identity"); net.add_edge("rnn", "out", weights=w_out, train="gd")
+        if model == "qif":
+            node.reset(y_init)          # membrane potentials spread over the cycle -> threshold crossings within the horizon
         obs = net.run(x, sampling_steps=S, verbose=False, enable_grad=True)
         out = torch.stack(obs["out"])
         torch.nn.functional.mse_loss(out, targets).backward()
@@ -207,11 +210,12 @@ def test_tensor_core_path_matches_fp32_path(model):
                              gout=net.get_edge("rnn", "out").weights.grad.cpu().numpy(), y=node.y.detach().cpu().numpy())
     errs = {key: rel_err(results["3xtf32"][key], results["fp32"][key]) for key in results["fp32"]}
     print(model, errs)
+    assert np.abs(results["fp32"]["out"]).max() > 0 and np.abs(results["fp32"]["gW"]).max() > 0      # spikes happened, gradient is live
     tol = 1e-5 if model == "li_tanh" else 1e-3
     assert all(e <= tol for e in errs.values()), errs
     # and against the oracle for two trials
     for b in (0, B - 1):
-        onode = orc.make_node(model, n, W, dt, params=params, dtype=torch.float64)
+        onode = orc.make_node(model, n, W, dt, params=params, dtype=torch.float64, y0=y_init[b] if model == "qif" else None)
         onet = orc.OracleNet(onode, w_in=torch.tensor(w_in), w_out=torch.tensor(w_out))
         r = onet.run(torch.tensor(x[:, b, :]), sampling_steps=S, enable_grad=False)
         ref = torch.stack(r["out"]).numpy()
