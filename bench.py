@@ -49,6 +49,17 @@ def _peaks():
     return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
 
 
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture (profiles/ncu_traffic.json, written by tools/summarize_ncu.py); None when no capture is recorded."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -309,7 +320,7 @@ def run_ours(args):
         contr_ms = T * (ms_f + ms_b + ms_w / chunk_steps)
         roofline = {
             "bound": "tensor", "kernel": "rp::k_gemm_3xtf32<256>" if use_tc else "rp::k_sgemm", "achieved": ach,
-            "peak": peak_logical, "unit": "TFLOP/s", "frac": ach / peak_logical, "traffic": None,
+            "peak": peak_logical, "unit": "TFLOP/s", "frac": ach / peak_logical, "traffic": _ncu_traffic(),
             "note": ("achieved = logical 2*N*N*B flops per forward-contraction launch / CUDA-event launch time; the kernel issues "
                      "3 tf32 MMAs per logical product, so peak = max(bf16_tflops_sustained(%s)/2, cuBLAS tf32 8192^3 measured in this run = %.0f TF)/3"
                      % (peaks["source"], tf32_measured)),

@@ -62,6 +62,20 @@ def full(src, dst):
             if w in idx:
                 f.write(f"| {w} | {units[idx[w]]} | " + " | ".join(r[idx[w]] for r in rows[2:]) + " |\n")
     print("wrote", dst)
+    # dominant-kernel DRAM traffic for bench.py's roofline.traffic
+    try:
+        import json, os
+        def num(r, key):
+            v = float(r[idx[key]].replace(",", ""))
+            u = units[idx[key]].lower()
+            return v * (1e9 if u.startswith("g") else 1e6 if u.startswith("m") else 1e3 if u.startswith("k") else 1.0)
+        tot = [num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum") for r in rows[2:]]
+        out = {"kernel": names[0], "dram_bytes_per_launch": sum(tot) / len(tot), "source": os.path.basename(dst), "launches": len(tot)}
+        with open(os.path.join(os.path.dirname(dst), "ncu_traffic.json"), "w") as fh:
+            json.dump(out, fh)
+        print("wrote ncu_traffic.json", out)
+    except Exception as exc:   # pragma: no cover
+        print("traffic summary skipped:", exc)
 
 
 if __name__ == "__main__":
