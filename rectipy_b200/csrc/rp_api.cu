@@ -606,6 +606,8 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     // MMA main loop and runs at 8 warps/SM, which measured slower (340 us/step) than the contraction followed by the
     // full-occupancy k_adj_step (149 + ~60 us).  It becomes the default once tiles are software-pipelined per CTA.
     const bool fused_adj = p->use_tc && getenv("RP_FUSED_ADJ") && !a->dW_in && !a->g_x && !(d.model == RP_LIF && d.in_target == 1) && d.model != RP_IK && !p->per_trial;
+    // vectorised stand-alone adjoint kernel: tensor-core shapes, no per-neuron parameter sums (dW_out then comes from k_readout_grad)
+    const bool adj_v4 = p->use_tc && !fused_adj && !pgrad && !a->dW_in && !a->g_x && !p->per_trial && !getenv("RP_NO_ADJ_V4");
     dim3 agrid((N + rp::ADJ_TX - 1) / rp::ADJ_TX, (B + rp::ADJ_TY * rp::ADJ_BPT - 1) / (rp::ADJ_TY * rp::ADJ_BPT));
     dim3 ablock(rp::ADJ_TX, rp::ADJ_TY);
     int pending = 0;   // steps whose (g, src) columns sit in the tensor-core weight-gradient chunk
@@ -679,7 +681,13 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                 if (rp::tc_gemm(&p->tc, rp::TC_DGRAD, p->u, p->ldu, 0, 0, st)) return fail("rp_backward: %s", rp::tc_last_error());
                 ++p->launches;
             }
-            RP_DISPATCH_MODEL(d.model, (rp::k_adj_step<M_><<<agrid, ablock, 0, st>>>(aa)));
+            if (adj_v4) {
+                rp::AdjArgs va = aa;
+                va.dW_out = nullptr; va.any_param_grad = 0;
+                RP_DISPATCH_MODEL(d.model, (rp::k_adj_step_v4<M_><<<dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st>>>(va)));
+            } else {
+                RP_DISPATCH_MODEL(d.model, (rp::k_adj_step<M_><<<agrid, ablock, 0, st>>>(aa)));
+            }
             RP_LAUNCH_CHECK();
         }
         ++p->launches;
@@ -693,12 +701,16 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             }
         }
     }
-    if (fused_adj && a->dW_out && a->g_out_rec && a->T > 0) {
-        dim3 rgrid((N + 127) / 128, std::max(1, std::min(a->T, 4 * p->sm_count / std::max(1, (N + 127) / 128))));
-        RP_DISPATCH_MODEL(d.model, (rp::k_readout_grad<M_><<<rgrid, 128, 0, st>>>(N, B, a->T, a->sampling_steps, a->cutoff, d.n_out, d.out_var,
-                                                                                   a->history, a->g_out_rec, mp, a->dW_out, a->t_offset, T_tot)));
-        ++p->launches;
-        RP_LAUNCH_CHECK();
+    if ((fused_adj || adj_v4) && a->dW_out && a->g_out_rec && a->T > 0) {
+        for (int t0 = 0; t0 < a->T; t0 += 32768) {            // grid.y limit
+            const int tn = std::min(32768, a->T - t0);
+            dim3 rgrid((N + 127) / 128, tn, (B + rp::RG_TB - 1) / rp::RG_TB);
+            RP_DISPATCH_MODEL(d.model, (rp::k_readout_grad<M_><<<rgrid, 128, 0, st>>>(N, B, tn, a->sampling_steps, a->cutoff, d.n_out, d.out_var,
+                                                                                       a->history + (size_t)t0 * hslot, a->g_out_rec, mp, a->dW_out,
+                                                                                       a->t_offset + t0, T_tot)));
+            ++p->launches;
+            RP_LAUNCH_CHECK();
+        }
     }
     if (need_dW) {
         rp::k_finish_wgrad<<<N, 256, 0, st>>>(N, p->dWraw, p->ldw, a->W, a->params[fold], kstride, a->dW, a->dparams[fold], wg_slices);

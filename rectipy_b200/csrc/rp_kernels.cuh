@@ -736,6 +736,100 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
     }
 }
 
+// Vectorised variant for the tensor-core path when no per-neuron parameter sums are requested (edge gradients come from the
+// contractions / k_readout_grad): a thread owns 4 consecutive neurons -> every global access is a 16-byte vector, loads of two
+// trials are in flight before the first store, and the trial-major weight-gradient operands are transposed through shared memory.
+// Block = 32 x 8 threads, tile = 128 neurons x 32 trials.  Requires N % 128 == 0, B % 32 == 0, 16-byte aligned rows.
+constexpr int ADJ4_TB = 32;      // trials per block
+__device__ __forceinline__ float f4at(const float4& v, int r) { return r == 0 ? v.x : (r == 1 ? v.y : (r == 2 ? v.z : v.w)); }
+
+template <int MODEL>
+__global__ void __launch_bounds__(256) k_adj_step_v4(AdjArgs a) {
+    constexpr int NSV = ModelTraits<MODEL>::NSV;
+    __shared__ float tg[ADJ4_TB][128 + 4];
+    __shared__ float ts[ADJ4_TB][128 + 4];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i0 = blockIdx.x * 128 + 4 * tx;
+    const int bblk = blockIdx.y * ADJ4_TB;
+    const size_t plane = (size_t)a.B * a.N;
+    const bool transposed = a.do_pre && a.gT_hi != nullptr;
+    const NoAcc nacc;
+    AdjRowParams rp_[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) rp_[rr] = adj_row_params<MODEL>(a, i0 + rr);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int l0 = 0; l0 < ADJ4_TB / 8; l0 += 2) {
+        float4 av[2], as[2], ax[2], v[2], s[2], x[2], vm[2], sm[2], Z[2], ur[2];
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            const int b = bblk + (l0 + l) * 8 + ty;
+            const size_t idx = (size_t)b * a.N + i0;
+            av[l] = *reinterpret_cast<const float4*>(a.adj + idx);
+            as[l] = NSV > 1 ? *reinterpret_cast<const float4*>(a.adj + plane + idx) : zero;
+            ax[l] = NSV > 2 ? *reinterpret_cast<const float4*>(a.adj + 2 * plane + idx) : zero;
+            v[l] = s[l] = x[l] = vm[l] = sm[l] = Z[l] = ur[l] = zero;
+            if (a.do_post) {
+                v[l] = __ldg(reinterpret_cast<const float4*>(a.y_t + idx));
+                if (NSV > 1) s[l] = __ldg(reinterpret_cast<const float4*>(a.y_t + plane + idx));
+                if (NSV > 2) x[l] = __ldg(reinterpret_cast<const float4*>(a.y_t + 2 * plane + idx));
+                Z[l] = *reinterpret_cast<const float4*>(a.Z + (size_t)b * a.ldz + i0);
+                if (MODEL == RP_IK && a.urec_t) ur[l] = __ldg(reinterpret_cast<const float4*>(a.urec_t + idx));
+            }
+            if (a.do_pre) {
+                vm[l] = __ldg(reinterpret_cast<const float4*>(a.y_tm1 + idx));
+                if (NSV > 1) sm[l] = __ldg(reinterpret_cast<const float4*>(a.y_tm1 + plane + idx));
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            const int bl = (l0 + l) * 8 + ty;
+            const int b = bblk + bl;
+            const size_t idx = (size_t)b * a.N + i0;
+            float nav[4], nas[4], nax[4], g[4], sv[4], gh[4], gl[4];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                nav[rr] = f4at(av[l], rr); nas[rr] = f4at(as[l], rr); nax[rr] = f4at(ax[l], rr);
+                if (a.do_post)
+                    adj_post_math<MODEL>(a, rp_[rr], nacc, i0 + rr, b, f4at(Z[l], rr), f4at(v[l], rr), f4at(s[l], rr), f4at(x[l], rr),
+                                         nav[rr], nas[rr], nax[rr], f4at(ur[l], rr));
+                g[rr] = 0.f; sv[rr] = 0.f;
+                if (a.do_pre) adj_pre_math<MODEL>(a, i0 + rr, nav[rr], f4at(vm[l], rr), f4at(sm[l], rr), g[rr], sv[rr], b);
+                split_tf32(g[rr], gh[rr], gl[rr]);
+            }
+            if (a.do_post) {
+                *reinterpret_cast<float4*>(a.adj + idx) = make_float4(nav[0], nav[1], nav[2], nav[3]);
+                if (NSV > 1) *reinterpret_cast<float4*>(a.adj + plane + idx) = make_float4(nas[0], nas[1], nas[2], nas[3]);
+                if (NSV > 2) *reinterpret_cast<float4*>(a.adj + 2 * plane + idx) = make_float4(nax[0], nax[1], nax[2], nax[3]);
+            }
+            if (a.do_pre) {
+                if (a.g) *reinterpret_cast<float4*>(a.g + idx) = make_float4(g[0], g[1], g[2], g[3]);
+                if (a.src) *reinterpret_cast<float4*>(a.src + idx) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+                if (a.g_hi) {
+                    *reinterpret_cast<float4*>(a.g_hi + (size_t)b * a.ld_g + i0) = make_float4(gh[0], gh[1], gh[2], gh[3]);
+                    *reinterpret_cast<float4*>(a.g_lo + (size_t)b * a.ld_g + i0) = make_float4(gl[0], gl[1], gl[2], gl[3]);
+                }
+                if (transposed) {
+                    *reinterpret_cast<float4*>(&tg[bl][4 * tx]) = make_float4(g[0], g[1], g[2], g[3]);
+                    *reinterpret_cast<float4*>(&ts[bl][4 * tx]) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+                }
+            }
+        }
+    }
+    if (transposed) {
+        __syncthreads();
+        // lane tx -> trial bblk + tx; warp ty walks neurons ty, ty+8, ...: every store is 32 consecutive trials of one neuron
+        for (int r = ty; r < 128; r += 8) {
+            float hi, lo;
+            const size_t off = (size_t)(blockIdx.x * 128 + r) * a.ld_t + a.t_col0 + bblk + tx;
+            split_tf32(tg[tx][r], hi, lo);
+            a.gT_hi[off] = hi; a.gT_lo[off] = lo;
+            split_tf32(ts[tx][r], hi, lo);
+            a.srcT_hi[off] = hi; a.srcT_lo[off] = lo;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // weight preparation / finalisation
 // ------------------------------------------------------------------------------------------------------
@@ -768,36 +862,39 @@ __global__ void __launch_bounds__(256) k_prepare_weights(int N, const float* __r
 }
 
 // dW_out[q][i] = sum_{t,b} dL/do_t[b][q] * y_t[out][b][i]  over the stored checkpoints (one pass over the history, after the
-// reverse sweep; keeps the readout gradient out of the per-step adjoint epilogue).  grid = (ceil(N/128), t-splits)
+// reverse sweep; keeps the readout gradient out of the per-step adjoint kernel).
+// grid = (ceil(N/128), T, ceil(B/RG_TB)): one step and RG_TB trials per block, 8 independent row loads in flight per thread
+constexpr int RG_TB = 128;
 template <int MODEL>
 __global__ void __launch_bounds__(128) k_readout_grad(int N, int B, int T, int S, int cutoff, int k, int out_var, const float* __restrict__ hist,
                                                        const float* __restrict__ g_out_rec, ModelParams mp, float* dW_out, int t_offset, int T_total) {
-    constexpr int NSV = ModelTraits<MODEL>::NSV;
     const int i = blockIdx.x * 128 + threadIdx.x;
+    const int t = blockIdx.y;
+    const int b0 = blockIdx.z * RG_TB, b1 = min(B, b0 + RG_TB);
     const size_t plane = (size_t)B * N, slot = (size_t)HistPlanes<MODEL>::N * plane;
-    const int per = (T + gridDim.y - 1) / gridDim.y;
-    const int t0 = blockIdx.y * per, t1 = min(T, t0 + per);
+    const PWindow w = pwindow_of(t_offset + t, T_total, S, cutoff);
+    if (w.j < 0 || i >= N) return;
+    const float sc = 1.0f / (float)w.len;
+    const float* yt = hist + (size_t)t * slot + (out_var == RP_VAR_R ? 0 : (size_t)out_var * plane) + i;
+    const float* e = g_out_rec + (size_t)w.j * B * k;
     float acc[RP_MAX_OUT];
 #pragma unroll
     for (int q = 0; q < RP_MAX_OUT; ++q) acc[q] = 0.f;
-    if (i < N) {
-        for (int t = t0; t < t1; ++t) {
-            const PWindow w = pwindow_of(t_offset + t, T_total, S, cutoff);
-            if (w.j < 0) continue;
-            const float sc = 1.0f / (float)w.len;
-            const float* yt = hist + (size_t)t * slot + (out_var == RP_VAR_R ? 0 : (size_t)out_var * plane) + i;
-            const float* e = g_out_rec + (size_t)w.j * B * k;
-#pragma unroll 4
-            for (int b = 0; b < B; ++b) {
-                float y = __ldg(yt + (size_t)b * N);
-                if (out_var == RP_VAR_R) { if constexpr (!ModelTraits<MODEL>::SPIKING) y = rate_act<MODEL>(mp, i, y, b); }
-                y *= sc;
+    for (int bb = b0; bb < b1; bb += 8) {
+        float y[8];
 #pragma unroll
-                for (int q = 0; q < RP_MAX_OUT; ++q) if (q < k) acc[q] = fmaf(__ldg(e + (size_t)b * k + q), y, acc[q]);
+        for (int u = 0; u < 8; ++u) y[u] = (bb + u < b1) ? __ldg(yt + (size_t)(bb + u) * N) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int b = bb + u;
+            if (b < b1) {
+                float yv = y[u];
+                if (out_var == RP_VAR_R) { if constexpr (!ModelTraits<MODEL>::SPIKING) yv = rate_act<MODEL>(mp, i, yv, b); }
+                for (int q = 0; q < k; ++q) acc[q] = fmaf(__ldg(e + (size_t)b * k + q), yv, acc[q]);
             }
         }
-        for (int q = 0; q < k; ++q) atomicAdd(dW_out + (size_t)q * N + i, acc[q]);
     }
+    for (int q = 0; q < k; ++q) atomicAdd(dW_out + (size_t)q * N + i, acc[q] * sc);
 }
 
 // dW[i][j] = k_i * dWraw[i][j] ;  dk[i] = sum_j dWraw[i][j] * W[i][j]        (one block per row)
