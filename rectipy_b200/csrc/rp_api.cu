@@ -489,13 +489,22 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
             RP_LAUNCH_CHECK();
         } else {
             const bool ro = fuse_readout && w.j >= 0;
-            RP_DISPATCH_MODEL(d.model, {
-                rp::EpiFwd<M_> epi;
+            auto fill = [&](auto& epi) {
                 epi.a = fa;
                 epi.out_rec_j = ro ? a->out_rec + (size_t)w.j * out_stride : nullptr;
                 epi.k = d.n_out; epi.win_first = w.first; epi.win_close = w.close; epi.inv_len = w.j >= 0 ? 1.0f / (float)w.len : 0.f;
-                if (rp::tc_forward_step<M_>(&p->tc, epi, ro, st)) return fail("rp_forward: %s", rp::tc_last_error());
-            });
+            };
+            if (p->per_trial || d.model == RP_IK) {
+                RP_DISPATCH_MODEL(d.model, {
+                    rp::EpiFwd<M_, true> epi; fill(epi);
+                    if (rp::tc_forward_step<M_, true>(&p->tc, epi, ro, st)) return fail("rp_forward: %s", rp::tc_last_error());
+                });
+            } else {
+                RP_DISPATCH_MODEL(d.model, {
+                    rp::EpiFwd<M_, false> epi; fill(epi);
+                    if (rp::tc_forward_step<M_, false>(&p->tc, epi, ro, st)) return fail("rp_forward: %s", rp::tc_last_error());
+                });
+            }
             ++p->launches;
         }
         const bool want_out = a->out_rec != nullptr && !fuse_readout;

@@ -156,7 +156,8 @@ __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d
 __device__ __forceinline__ float f4get(const float4& v, int r) { return r == 0 ? v.x : (r == 1 ? v.y : (r == 2 ? v.z : v.w)); }
 
 // forward step: u = (kW . r_t)[b][i] never touches global memory; tile rows >= N hold W_out (readout o_t = W_out . s_t)
-template <int MODEL>
+// GEN: general element path (per-element parameter loads: ik_op, per-trial parameter sweeps) instead of hoisted row constants
+template <int MODEL, bool GEN = (MODEL == RP_IK)>
 struct EpiFwd {
     static constexpr bool kStage = true;
     FwdStepArgs a;
@@ -198,7 +199,7 @@ struct EpiFwd {
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
                         const int i = i0 + rr;
-                        if (MODEL == RP_IK || a.per_trial) {  // general (per-element parameter loads) path: ik, parameter sweeps
+                        if constexpr (GEN) {                  // general (per-element parameter loads) path: ik, parameter sweeps
                             const float Iin = input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i);
                             fwd_elem<MODEL>(a, i, f4get(u4[cc], rr), Iin, f4get(v4[cc], rr), f4get(s4[cc], rr), f4get(x4[cc], rr), v1[rr], s1[rr], x1[rr], b);
                         } else {
@@ -613,9 +614,9 @@ inline int tc_launch(int bq, int P, int Q, int K, const CUtensorMap* A, const CU
     return tc_launch_epi<EpiStore>(bq, P, Q, K, A, Bm, e, st, k_splits);
 }
 // fused launches: forward step (rows = N, or N+128 when the readout rows are appended) and adjoint step
-template <int MODEL>
-inline int tc_forward_step(TcWorkspace* w, const EpiFwd<MODEL>& epi, bool readout_rows, cudaStream_t st) {
-    return tc_launch_epi<EpiFwd<MODEL>>(w->bq_fwd, w->N + (readout_rows ? TC_BP : 0), w->B, w->N, w->m_W, w->m_src, epi, st);
+template <int MODEL, bool GEN>
+inline int tc_forward_step(TcWorkspace* w, const EpiFwd<MODEL, GEN>& epi, bool readout_rows, cudaStream_t st) {
+    return tc_launch_epi<EpiFwd<MODEL, GEN>>(w->bq_fwd, w->N + (readout_rows ? TC_BP : 0), w->B, w->N, w->m_W, w->m_src, epi, st);
 }
 template <int MODEL, bool PG>
 inline int tc_adjoint_step(TcWorkspace* w, const EpiAdj<MODEL, PG>& epi, cudaStream_t st) {
