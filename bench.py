@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 N_NEURONS, BATCH, N_IN, N_OUT, DT = 4096, 1024, 2, 3, 1e-3
 T_INNER = 100
+PRECISION = "auto"    # tensor-core operand format: auto -> 3xf16 (binary16 split words), or 3xtf32 / fp32
 METRIC = "neuron-steps/sec (QIF N=4096, batch 1024, BPTT fwd+bwd)"
 UNIT = "neuron-steps/s"
 CPU_T = 40            # Euler steps per CPU-baseline sample (one trial, BPTT)
@@ -137,7 +138,7 @@ def spread_state(seed: int, n: int, batch: int):
 
 def build_network(W, w_in, w_out, etas, batch, device):
     import rectipy_b200 as rp
-    net = rp.Network(DT, device=device, batch=batch, precision="auto")
+    net = rp.Network(DT, device=device, batch=batch, precision=PRECISION)
     node = net.add_diffeq_node("qif", "neuron_model_templates.spiking_neurons.qif.qif", weights=W, source_var="s",
                                target_var="s_in", input_var="I_ext", output_var="s", spike_var="spike", reset_var="v",
                                op="qif_op", node_vars={"eta": etas}, train_params=["weights"])
@@ -298,7 +299,8 @@ def run_ours(args):
         ms_f, fl_f = plan.time_contraction(0, 20)
         ms_b, fl_b = plan.time_contraction(1, 20)
         ms_w, fl_w = plan.time_contraction(2, 10)
-        use_tc = plan.key.precision == abi.RP_PREC_3XTF32
+        use_tc = plan.key.precision in (abi.RP_PREC_3XTF32, abi.RP_PREC_3XF16)
+        f16 = plan.key.precision == abi.RP_PREC_3XF16
         # measured TF32 dense peak of this box: cuBLAS (torch.matmul, allow_tf32) 8192^3, best of 5 -- MEASURED_PEAKS.json only
         # carries bf16; BASELINE.md asks for the tf32 figure to be measured in the run
         torch.backends.cuda.matmul.allow_tf32 = True
@@ -314,17 +316,24 @@ def run_ours(args):
         # tf32 tensor rate is half the bf16 rate; 3xTF32 issues 3 MMAs per logical product -> divide by 3 again.
         # These launches are timed inside a long, power-capped step -> compare with the sustained figure.
         # the contraction is timed alone (20 back-to-back launches, ~3 ms) -> burst figure; tf32 issues at half the bf16 rate
-        peak_logical = max(peaks["bf16"] / 2.0, tf32_measured) / 3.0 if use_tc else 72.0
+        # binary16 split words issue at the full 16-bit rate: peak = measured bf16 burst / 3
+        if f16:
+            peak_logical = peaks["bf16"] / 3.0
+        else:
+            peak_logical = max(peaks["bf16"] / 2.0, tf32_measured) / 3.0 if use_tc else 72.0
         ach = fl_f / (ms_f * 1e-3) / 1e12
         # share of one BPTT pass spent in the three contractions (per Euler step: 1 fwd + 1 adjoint + 1/chunk wgrad)
         chunk_steps = fl_w / (2.0 * n * n * B)
         contr_ms = T * (ms_f + ms_b + ms_w / chunk_steps)
         roofline = {
-            "bound": "tensor", "kernel": "rp::k_gemm_3xtf32<256>" if use_tc else "rp::k_sgemm", "achieved": ach,
+            "bound": "tensor", "kernel": ("rp::k_gemm_split3<256, EpiStore, f16=%d>" % int(f16)) if use_tc else "rp::k_sgemm", "achieved": ach,
             "peak": peak_logical, "unit": "TFLOP/s", "frac": ach / peak_logical, "traffic": _ncu_traffic(),
-            "note": ("achieved = logical 2*N*N*B flops per forward-contraction launch / CUDA-event launch time; the kernel issues "
-                     "3 tf32 MMAs per logical product, so peak = max(bf16_tflops burst (%s)/2, cuBLAS tf32 8192^3 measured in this run = %.0f TF)/3"
-                     % (peaks["source"], tf32_measured)),
+            "note": (("achieved = logical 2*N*N*B flops per forward-contraction launch / CUDA-event launch time; the kernel issues "
+                      "3 kind::f16 MMAs (binary16 hi/lo split words, fp32 accumulate) per logical product, so peak = bf16_tflops burst (%s)/3"
+                      % peaks["source"]) if f16 else
+                     ("achieved = logical 2*N*N*B flops per forward-contraction launch / CUDA-event launch time; the kernel issues "
+                      "3 tf32 MMAs per logical product, so peak = max(bf16_tflops burst (%s)/2, cuBLAS tf32 8192^3 measured in this run = %.0f TF)/3"
+                      % (peaks["source"], tf32_measured))),
             "tf32_cublas_tflops": tf32_measured,
             "launch_ms": {"fwd": ms_f, "adjoint": ms_b, "wgrad_chunk": ms_w, "wgrad_steps_per_chunk": chunk_steps},
             "achieved_all": {"fwd": ach, "adjoint": fl_b / (ms_b * 1e-3) / 1e12, "wgrad": fl_w / (ms_w * 1e-3) / 1e12},
@@ -337,7 +346,9 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (tcgen05 3xTF32 contractions, fp32 accumulate)" if use_tc else "f32", "data": "synthetic",
+            "dtype": ("f32 (tcgen05 split-3 contractions on binary16 hi/lo words with exact power-of-two scales = 22-bit significand "
+                      "products, fp32 accumulate)" if f16 else ("f32 (tcgen05 3xTF32 contractions, fp32 accumulate)" if use_tc else "f32")),
+            "data": "synthetic",
             "config": {"workload": "QIF recurrent spiking net BPTT (BASELINE configs[2]): N=4096, batch=1024 trials/GPU, "
                                    "m=2, k=3, dt=1e-3, T=%d Euler steps fwd + adjoint per step, train W and W_out" % T,
                        "n": n, "batch_per_gpu": B, "t_inner": T, "n_in": N_IN, "n_out": N_OUT, "dt": DT,
@@ -389,8 +400,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--t-inner", type=int, default=T_INNER, help="Euler steps per BPTT pass (profiling runs use fewer)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (profiling runs)")
+    ap.add_argument("--precision", default="auto", choices=["auto", "3xf16", "3xtf32", "fp32"], help="contraction path (A/B runs)")
     args = ap.parse_args()
     globals()["T_INNER"] = args.t_inner
+    globals()["PRECISION"] = args.precision
     global _OUT
     with _QuietStdout() as q:
         _OUT = q

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RP_ABI_VERSION 3
+#define RP_ABI_VERSION 4
 #define RP_MAX_IN 8      /* max fused input-projection width  m (wider inputs: use RP_IN_DENSE)  */
 #define RP_MAX_OUT 8     /* max fused readout width           k (wider readouts: use RP_OUT_DENSE) */
 #define RP_MAX_SV 3
@@ -49,7 +49,9 @@ enum { RP_P_TAU = 0, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_
 enum { RP_IN_NONE = 0, RP_IN_DENSE = 1, RP_IN_PROJ = 2 };   /* x_t is [B,n] current | [B,m] projected by W_in[n,m] */
 enum { RP_OUT_DENSE = 0, RP_OUT_READOUT = 1 };             /* record y[out] itself | W_out[k,n] . y[out]         */
 enum { RP_VAR_V = 0, RP_VAR_S = 1, RP_VAR_X = 2, RP_VAR_R = 3 }; /* RP_VAR_R = activation(v) of a rate node       */
-enum { RP_PREC_FP32 = 0, RP_PREC_3XTF32 = 1 };             /* FFMA fp32 | tcgen05 error-compensated 3xTF32       */
+/* FFMA fp32 | tcgen05 error-compensated split products, operands split into two tf32 words | the same split carried by two
+ * binary16 words with exact power-of-two operand scales (same 11-bit significands -> same accuracy, twice the MMA rate) */
+enum { RP_PREC_FP32 = 0, RP_PREC_3XTF32 = 1, RP_PREC_3XF16 = 2 };
 
 typedef struct rp_desc {
     int model;              /* RP_LI_TANH ...                                                   */
@@ -133,6 +135,9 @@ long long rp_plan_launch_count(const rp_plan* plan);
 
 int rp_forward(rp_plan* plan, const rp_fwd_args* args, void* stream);
 int rp_backward(rp_plan* plan, const rp_bwd_args* args, void* stream);
+/* Synchronises `stream` and reports whether a range guard of the plan tripped since the last call (RP_PREC_3XF16: the adjoint
+ * grew faster than the binary16 operand range allows within one weight-gradient chunk).  0: results are valid. */
+int rp_plan_status(rp_plan* plan, void* stream);
 
 /* Sequential recursive-least-squares readout training over a recorded state matrix (edges.py:227-234):
  * for t in [0,T): y_hat = W x_t ; z = beta_inv*P x_t ; kappa = 1/(1+x_t.z) ;
@@ -148,7 +153,7 @@ int rp_rls_run(int T, int n_in, int n_out, float beta_inv, const float* X, const
 int rp_plan_time_contraction(rp_plan* plan, int which, int iters, float* avg_ms, double* flops, void* stream);
 
 /* Standalone GEMM used by the engine, exposed for testing:  C[q*ldc+p] (+)= sum_k A[p*lda+k]*B[q*ldb+k]
- * precision RP_PREC_FP32 -> FFMA kernel, RP_PREC_3XTF32 -> tcgen05 kernel (needs p,q,k extents it supports). */
+ * precision RP_PREC_FP32 -> FFMA kernel, RP_PREC_3XTF32 / RP_PREC_3XF16 -> tcgen05 kernel (needs p,q,k extents it supports). */
 int rp_gemm_tn(int precision, int P, int Q, int K, const float* A, int lda, const float* B, int ldb,
                float* C, int ldc, int accumulate, void* stream);
 

@@ -61,7 +61,7 @@ struct rp_plan {
     int sm_count;
     long long launches;
     size_t ws_bytes;
-    bool use_tc;           // tcgen05 3xTF32 contractions
+    bool use_tc;           // tcgen05 split-3 contractions (tf32 or binary16 operands, see tc.f16)
     bool per_trial = false;// some template parameter has one value per trial (parameter sweep)
     // fp32 workspaces
     float* Wk = nullptr;     // [N][ldw]   k_i * W
@@ -365,11 +365,13 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
     p->launches = 0;
     p->ws_bytes = 0;
     const int N = d->n, B = d->batch;
-    p->use_tc = (d->precision == RP_PREC_3XTF32);
+    p->use_tc = (d->precision == RP_PREC_3XTF32 || d->precision == RP_PREC_3XF16);
+    // binary16 operands need a bound on the source variable one step ahead; the lif s_ext input adds an unbounded term to s'
+    const bool f16 = d->precision == RP_PREC_3XF16 && !(d->model == RP_LIF && d->in_target == 1) && !getenv("RP_NO_F16");
     for (int q = 0; q < RP_NUM_PARAMS; ++q) if (d->param_per_neuron[q] > 1) p->per_trial = true;
     if (p->use_tc && !rp::tc_supported(N, B)) {
         delete p;
-        return fail("rp_plan_create: RP_PREC_3XTF32 needs n %% 128 == 0 and batch %% 128 == 0 (got n=%d batch=%d)", N, B);
+        return fail("rp_plan_create: RP_PREC_3XTF32 / RP_PREC_3XF16 need n %% 128 == 0 and batch %% 128 == 0 (got n=%d batch=%d)", N, B);
     }
     p->ldw = round_up(N, 4);
     p->ldu = round_up(N, 4);
@@ -386,7 +388,7 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
         if (!spiking(d->model)) rc |= plan_alloc(p, &p->src, plane);
     } else {
         size_t bytes = 0;
-        rc |= rp::tc_workspace_create(&p->tc, N, B, &bytes);
+        rc |= rp::tc_workspace_create(&p->tc, N, B, f16, !spiking(d->model), &bytes);
         if (rc) fail("rp_plan_create: tensor-core workspace allocation failed: %s", rp::tc_last_error());
         p->ws_bytes += bytes;
     }
@@ -436,7 +438,14 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
     {
         dim3 grid((N + 31) / 32, (N + 31) / 32);
         if (!p->use_tc) rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, p->Wk, nullptr, p->ldw, nullptr, nullptr, nullptr, nullptr);
-        else rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, nullptr, nullptr, p->tc.ldk, p->tc.W_hi, p->tc.W_lo, nullptr, nullptr);
+        else if (!p->tc.f16) rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, nullptr, nullptr, p->tc.ldk,
+                                                                        (float*)p->tc.W_hi, (float*)p->tc.W_lo, nullptr, nullptr);
+        else {
+            RP_CUDA(cudaMemsetAsync(p->tc.meta + rp::TCM_AMAX_W, 0, 2 * sizeof(float), st));       // AMAX_W, AMAX_WOUT
+            rp::k_amax_2d<<<p->sm_count * 4, 256, 0, st>>>(N, N, a->W, (size_t)N, a->params[fold], kstride, p->tc.meta + rp::TCM_AMAX_W);
+            rp::k_prepare_weights_f16<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, p->tc.ldk, p->tc.W_hi, p->tc.W_lo, nullptr, nullptr, rp::tc_scale_W(&p->tc));
+            ++p->launches;
+        }
         ++p->launches;
         RP_LAUNCH_CHECK();
     }
@@ -449,10 +458,38 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
     RP_CUDA(cudaMemcpyAsync(slot_ptr(0), a->y0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
     const bool spk = spiking(d.model);
+    const bool f16 = p->use_tc && p->tc.f16;
+    // binary16 operands: bound of the source variable.  Rate models: static (|tanh| <= 1, sigmoid <= max r_max).  Spiking models:
+    // |s_{t+1}| <= |s_t| + 1 (one spike adds exactly 1, nodes.py:385), tracked per step in tc.amax_src.
+    const rp::ScaleRef sc_rate = rp::tc_scale_srcbound(&p->tc);
+    if (f16 && a->T > 0) {
+        if (spk) {
+            size_t bytes = 0;
+            if (rp::tc_workspace_ensure_amax(&p->tc, a->T + 2, &bytes)) return fail("rp_forward: %s", rp::tc_last_error());
+            p->ws_bytes += bytes;
+            RP_CUDA(cudaMemsetAsync(p->tc.amax_src, 0, (size_t)(a->T + 2) * sizeof(float), st));
+        } else if (d.model == RP_LI_TANH) {
+            rp::k_fill<<<1, 32, 0, st>>>(p->tc.meta + rp::TCM_SRC_BOUND, 1, 1.0f);
+            ++p->launches;
+        } else {
+            const int mode = d.param_per_neuron[RP_P_RMAX];
+            const int count = mode == 0 ? 1 : (mode == 1 ? N : (mode == 2 ? B : B * N));
+            RP_CUDA(cudaMemsetAsync(p->tc.meta + rp::TCM_SRC_BOUND, 0, sizeof(float), st));
+            rp::k_amax_2d<<<32, 256, 0, st>>>(1, count, a->params[RP_P_RMAX], (size_t)count, nullptr, 0, p->tc.meta + rp::TCM_SRC_BOUND);
+            ++p->launches;
+        }
+        RP_LAUNCH_CHECK();
+    }
     if (a->T > 0 && (!spk || p->use_tc)) {
+        if (f16 && spk) {    // first pass: exact maximum of src_0
+            RP_DISPATCH_MODEL(d.model, (rp::k_init_src<M_><<<ew_grid(p, plane), 256, 0, st>>>(N, B, slot_ptr(0), mp, nullptr, N, nullptr, nullptr,
+                                        p->tc.ldk, 0, rp::no_scale(), p->tc.amax_src)));
+            ++p->launches;
+        }
+        const rp::ScaleRef sc0 = f16 ? (spk ? rp::ScaleRef{p->tc.amax_src, 0.f, rp::CV_HSRC} : sc_rate) : rp::no_scale();
         RP_DISPATCH_MODEL(d.model, (rp::k_init_src<M_><<<ew_grid(p, plane), 256, 0, st>>>(N, B, slot_ptr(0), mp,
                                     (!spk && !p->use_tc) ? p->src : nullptr, N, p->use_tc ? p->tc.src_hi : nullptr,
-                                    p->use_tc ? p->tc.src_lo : nullptr, p->tc.ldk)));
+                                    p->use_tc ? p->tc.src_lo : nullptr, p->tc.ldk, f16 ? 1 : 0, sc0, nullptr)));
         ++p->launches;
         RP_LAUNCH_CHECK();
     }
@@ -462,8 +499,13 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
     // tensor-core path: the step (and, for spiking nets read out from s, the readout) is the contraction's epilogue
     const bool fuse_readout = p->use_tc && spk && d.out_var == RP_VAR_S && d.out_mode == RP_OUT_READOUT && a->out_rec != nullptr;
     if (fuse_readout) {
-        rp::k_split_matrix<<<64, 256, 0, st>>>(d.n_out, N, a->W_out, N, p->tc.W_hi + (size_t)N * p->tc.ldk,
-                                               p->tc.W_lo + (size_t)N * p->tc.ldk, p->tc.ldk, d.n_out);
+        const size_t roff = (size_t)N * p->tc.ldk * p->tc.esize();
+        if (f16) {
+            rp::k_amax_2d<<<32, 256, 0, st>>>(d.n_out, N, a->W_out, (size_t)N, nullptr, 0, p->tc.meta + rp::TCM_AMAX_WOUT);
+            ++p->launches;
+        }
+        rp::k_split_matrix<<<64, 256, 0, st>>>(d.n_out, N, a->W_out, N, (char*)p->tc.W_hi + roff, (char*)p->tc.W_lo + roff, p->tc.ldk, d.n_out,
+                                               f16 ? 1 : 0, rp::tc_scale_Wout(&p->tc));
         ++p->launches;
         RP_LAUNCH_CHECK();
     }
@@ -478,6 +520,17 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         fa.x_t = a->x ? a->x + (size_t)t * x_stride : nullptr; fa.W_in = a->W_in; fa.mp = mp;
         fa.src_next = (!spk && !p->use_tc) ? p->src : nullptr;
         fa.src_hi = p->use_tc ? p->tc.src_hi : nullptr; fa.src_lo = p->use_tc ? p->tc.src_lo : nullptr; fa.ld_src = p->tc.ldk;
+        fa.sc_out = rp::no_scale(); fa.amax_out = nullptr;
+        rp::ScaleRef sc_in = rp::no_scale();
+        if (f16) {
+            if (spk) {
+                sc_in = t == 0 ? rp::ScaleRef{p->tc.amax_src, 0.f, rp::CV_HSRC} : rp::ScaleRef{p->tc.amax_src + (t - 1), 1.f, rp::CV_HSRC};
+                fa.sc_out = rp::ScaleRef{p->tc.amax_src + t, 1.f, rp::CV_HSRC};
+                fa.amax_out = p->tc.amax_src + (t + 1);
+            } else {
+                sc_in = sc_rate; fa.sc_out = sc_rate;
+            }
+        }
         fa.urec_out = (d.model == RP_IK && a->history) ? cur + (size_t)nsv * plane : nullptr;
         fa.per_trial = p->per_trial ? 1 : 0;
         if (!p->use_tc) {
@@ -493,6 +546,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
                 epi.a = fa;
                 epi.out_rec_j = ro ? a->out_rec + (size_t)w.j * out_stride : nullptr;
                 epi.k = d.n_out; epi.win_first = w.first; epi.win_close = w.close; epi.inv_len = w.j >= 0 ? 1.0f / (float)w.len : 0.f;
+                epi.sA = rp::tc_scale_W(&p->tc); epi.sA_ro = rp::tc_scale_Wout(&p->tc); epi.sB = sc_in;
             };
             if (p->per_trial || d.model == RP_IK) {
                 RP_DISPATCH_MODEL(d.model, {
@@ -528,6 +582,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
             RP_LAUNCH_CHECK();
         }
     }
+    if (f16) { p->tc.fwd_history = a->history; p->tc.fwd_T = a->T; }
     RP_CUDA(cudaMemcpyAsync(a->yT, slot_ptr(a->T), slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
@@ -566,9 +621,40 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     {
         dim3 grid((N + 31) / 32, (N + 31) / 32);
         if (!p->use_tc) rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, nullptr, p->WkT, p->ldw, nullptr, nullptr, nullptr, nullptr);
-        else rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, nullptr, nullptr, p->tc.ldk, nullptr, nullptr, p->tc.WT_hi, p->tc.WT_lo);
+        else if (!p->tc.f16) rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, nullptr, nullptr, p->tc.ldk, nullptr, nullptr,
+                                                                        (float*)p->tc.WT_hi, (float*)p->tc.WT_lo);
+        else {
+            RP_CUDA(cudaMemsetAsync(p->tc.meta + rp::TCM_AMAX_W, 0, sizeof(float), st));
+            rp::k_amax_2d<<<p->sm_count * 4, 256, 0, st>>>(N, N, a->W, (size_t)N, a->params[fold], kstride, p->tc.meta + rp::TCM_AMAX_W);
+            rp::k_prepare_weights_f16<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, p->tc.ldk, nullptr, nullptr, p->tc.WT_hi, p->tc.WT_lo, rp::tc_scale_W(&p->tc));
+            ++p->launches;
+        }
         ++p->launches;
         RP_LAUNCH_CHECK();
+    }
+    const bool f16 = p->use_tc && p->tc.f16;
+    if (f16 && a->T > 0) {
+        // bound of the source operand over the sweep: the maxima tracked by the forward pass that wrote these checkpoints,
+        // else one pass over the checkpoints' source planes; rate models: static bound of the activation
+        float* sb = p->tc.meta + rp::TCM_SRC_BOUND;
+        if (spk) {
+            if (p->tc.fwd_history == a->history && p->tc.fwd_T == a->T && p->tc.amax_src) {
+                rp::k_max_of_array<<<1, 32, 0, st>>>(p->tc.amax_src, a->T + 1, sb);
+            } else {
+                RP_CUDA(cudaMemsetAsync(sb, 0, sizeof(float), st));
+                rp::k_amax_2d<<<p->sm_count * 4, 256, 0, st>>>(a->T, (int)plane, a->history + plane, (size_t)nhist_of(d.model) * plane, nullptr, 0, sb);
+            }
+        } else if (d.model == RP_LI_TANH) {
+            rp::k_fill<<<1, 32, 0, st>>>(sb, 1, 1.0f);
+        } else {
+            const int mode = d.param_per_neuron[RP_P_RMAX];
+            const int count = mode == 0 ? 1 : (mode == 1 ? N : (mode == 2 ? B : B * N));
+            RP_CUDA(cudaMemsetAsync(sb, 0, sizeof(float), st));
+            rp::k_amax_2d<<<32, 256, 0, st>>>(1, count, a->params[RP_P_RMAX], (size_t)count, nullptr, 0, sb);
+        }
+        ++p->launches;
+        RP_LAUNCH_CHECK();
+        RP_CUDA(cudaMemsetAsync(p->tc.meta + rp::TCM_G_AMAX0, 0, 4 * sizeof(float), st));      // G_AMAX0/1, CHUNK0/1
     }
     if (need_dW) RP_CUDA(cudaMemsetAsync(p->dWraw, 0, (size_t)wg_slices * N * p->ldw * sizeof(float), st));
     for (int q = 0; q < RP_NUM_PARAMS; ++q)
@@ -601,7 +687,10 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     aa.out_mode = d.out_mode; aa.out_var = d.out_var; aa.dt = d.dt; aa.theta = d.theta; aa.slope = d.slope;
     aa.adj = p->adj; aa.Z = p->u; aa.ldz = p->ldu; aa.W_in = a->W_in; aa.W_out = a->W_out; aa.mp = mp;
     if (!p->use_tc) { aa.g = wg_batched ? p->wg_g : p->g; aa.src = spk ? nullptr : (wg_batched ? p->wg_src : p->src); }
-    else { aa.g_hi = p->tc.g_hi; aa.g_lo = p->tc.g_lo; aa.ld_g = p->tc.ldk; aa.ld_t = p->tc.ldt; }
+    else if (!f16) { aa.g_hi = (float*)p->tc.g_hi; aa.g_lo = (float*)p->tc.g_lo; aa.ld_g = p->tc.ldk; aa.ld_t = p->tc.ldt; }
+    else { aa.g = p->tc.g32; aa.src = spk ? nullptr : p->tc.src32; }      // binary16: fp32 g + exact maximum, converted by k_adj_convert_f16
+    int gslot = 1;                  // binary16: meta slot holding max |g_t| of the step being processed
+    int cpar = 0;                   // binary16: parity of the weight-gradient chunk reference slot
     for (int q = 0; q < RP_NUM_PARAMS; ++q) aa.dparams[q] = (q == fold) ? nullptr : a->dparams[q];
     aa.dW_in = a->dW_in; aa.dW_out = a->dW_out;
     aa.per_trial = p->per_trial ? 1 : 0;
@@ -614,7 +703,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     // The fused adjoint epilogue is opt-in (RP_FUSED_ADJ=1): with one tile per CTA its element-wise work cannot overlap the
     // MMA main loop and runs at 8 warps/SM, which measured slower (340 us/step) than the contraction followed by the
     // full-occupancy k_adj_step (149 + ~60 us).  It becomes the default once tiles are software-pipelined per CTA.
-    const bool fused_adj = p->use_tc && getenv("RP_FUSED_ADJ") && !a->dW_in && !a->g_x && !(d.model == RP_LIF && d.in_target == 1) && d.model != RP_IK && !p->per_trial;
+    const bool fused_adj = p->use_tc && !f16 && getenv("RP_FUSED_ADJ") && !a->dW_in && !a->g_x && !(d.model == RP_LIF && d.in_target == 1) && d.model != RP_IK && !p->per_trial;
     // vectorised stand-alone adjoint kernel: tensor-core shapes, no per-neuron parameter sums (dW_out then comes from k_readout_grad)
     const bool adj_v4 = p->use_tc && !fused_adj && !pgrad && !a->dW_in && !a->g_x && !p->per_trial && !getenv("RP_NO_ADJ_V4");
     dim3 agrid((N + rp::ADJ_TX - 1) / rp::ADJ_TX, (B + rp::ADJ_TY * rp::ADJ_BPT - 1) / (rp::ADJ_TY * rp::ADJ_BPT));
@@ -665,10 +754,11 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         }
         if (aa.do_pre) {
             aa.y_tm1 = a->history + (size_t)(t - 1) * hslot;
-            if (p->use_tc && need_dW) {
-                aa.gT_hi = p->tc.gT_hi; aa.gT_lo = p->tc.gT_lo; aa.srcT_hi = p->tc.srcT_hi; aa.srcT_lo = p->tc.srcT_lo;
+            if (p->use_tc && need_dW && !f16) {
+                aa.gT_hi = (float*)p->tc.gT_hi; aa.gT_lo = (float*)p->tc.gT_lo; aa.srcT_hi = (float*)p->tc.srcT_hi; aa.srcT_lo = (float*)p->tc.srcT_lo;
                 aa.t_col0 = pending * B;
             }
+            if (f16) aa.g_amax = p->tc.meta + rp::TCM_G_AMAX0 + (gslot ^ 1);
         }
         if (fused_adj && aa.do_post) {
             // Z_t = (kW)^T g_t on the tensor cores with the adjoint recurrences as its epilogue
@@ -687,7 +777,8 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             }
         } else {
             if (p->use_tc && aa.do_post) {
-                if (rp::tc_gemm(&p->tc, rp::TC_DGRAD, p->u, p->ldu, 0, 0, st)) return fail("rp_backward: %s", rp::tc_last_error());
+                const rp::ScaleRef sg = f16 ? rp::ScaleRef{p->tc.meta + rp::TCM_G_AMAX0 + gslot, 0.f, rp::CV_HG} : rp::no_scale();
+                if (rp::tc_gemm(&p->tc, rp::TC_DGRAD, p->u, p->ldu, 0, 0, st, sg)) return fail("rp_backward: %s", rp::tc_last_error());
                 ++p->launches;
             }
             if (adj_v4) {
@@ -700,11 +791,34 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             RP_LAUNCH_CHECK();
         }
         ++p->launches;
+        if (f16 && aa.do_pre) {
+            rp::ConvArgs ca;
+            memset(&ca, 0, sizeof(ca));
+            ca.N = N; ca.B = B; ca.g32 = p->tc.g32;
+            ca.src32 = spk ? a->history + (size_t)(t - 1) * hslot + plane : p->tc.src32;
+            ca.g_hi = p->tc.g_hi; ca.g_lo = p->tc.g_lo; ca.ld_g = p->tc.ldk;
+            if (need_dW) {
+                ca.gT_hi = p->tc.gT_hi; ca.gT_lo = p->tc.gT_lo; ca.srcT_hi = p->tc.srcT_hi; ca.srcT_lo = p->tc.srcT_lo;
+                ca.ld_t = p->tc.ldt; ca.t_col0 = pending * B;
+            }
+            ca.g_amax = p->tc.meta + rp::TCM_G_AMAX0 + (gslot ^ 1);
+            ca.g_amax_clear = p->tc.meta + rp::TCM_G_AMAX0 + gslot;
+            ca.chunk_ref_in = p->tc.meta + rp::TCM_CHUNK0 + cpar;
+            ca.chunk_ref_out = p->tc.meta + rp::TCM_CHUNK0 + (cpar ^ 1);
+            ca.chunk_first = pending == 0 ? 1 : 0;
+            ca.sc_src = rp::tc_scale_srcbound(&p->tc);
+            ca.flags = reinterpret_cast<int*>(p->tc.meta + rp::TCM_FLAGS);
+            rp::k_adj_convert_f16<<<dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st>>>(ca);
+            RP_LAUNCH_CHECK();
+            ++p->launches;
+            gslot ^= 1; cpar ^= 1;
+        }
         if (p->use_tc && need_dW && aa.do_pre) {
             ++pending;
             if (pending == wg_chunk || t == 1) {
                 // dWraw[i][j] += sum_{(t,b) in chunk} g[b][i] src[b][j]
-                if (rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, pending * B, 1, st)) return fail("rp_backward: %s", rp::tc_last_error());
+                const rp::ScaleRef sc = f16 ? rp::ScaleRef{p->tc.meta + rp::TCM_CHUNK0 + cpar, 0.f, rp::CV_HCHUNK} : rp::no_scale();
+                if (rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, pending * B, 1, st, sc)) return fail("rp_backward: %s", rp::tc_last_error());
                 ++p->launches;
                 pending = 0;
             }
@@ -750,8 +864,9 @@ int rp_plan_time_contraction(rp_plan* p, int which, int iters, float* avg_ms, do
     if (!p->use_tc && !p->src) { if (plan_alloc(p, &p->src, plane)) return 1; RP_CUDA(cudaMemsetAsync(p->src, 0, plane * sizeof(float), st)); }
     auto launch = [&]() -> int {
         if (p->use_tc) {
-            if (which == 2) return rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, kext, 1, st);
-            return rp::tc_gemm(&p->tc, which == 0 ? rp::TC_FWD : rp::TC_DGRAD, p->u, p->ldu, 0, 0, st);
+            const rp::ScaleRef sb = p->tc.f16 ? rp::ScaleRef{p->tc.meta + rp::TCM_G_AMAX0, 0.f, rp::CV_HG} : rp::no_scale();
+            if (which == 2) return rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, kext, 1, st, sb);
+            return rp::tc_gemm(&p->tc, which == 0 ? rp::TC_FWD : rp::TC_DGRAD, p->u, p->ldu, 0, 0, st, sb);
         }
         if (which == 2) return gemm_fp32(p, false, N, N, B, p->src, N, p->g, N, p->dWraw, p->ldw, 1, st, &scratch_launches);
         return gemm_fp32(p, true, N, B, N, which == 0 ? p->Wk : p->WkT, p->ldw, which == 0 ? p->src : p->g, N, p->u, p->ldu, 0, st, &scratch_launches);
@@ -778,11 +893,27 @@ int rp_gemm_tn(int precision, int P, int Q, int K, const float* A, int lda, cons
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     long long launches = 0;
     if (precision == RP_PREC_FP32) return gemm_fp32(nullptr, true, P, Q, K, A, lda, B, ldb, C, ldc, accumulate, st, &launches);
-    if (precision == RP_PREC_3XTF32) {
-        if (rp::tc_gemm_standalone(P, Q, K, A, lda, B, ldb, C, ldc, accumulate, st)) return fail("rp_gemm_tn: %s", rp::tc_last_error());
+    if (precision == RP_PREC_3XTF32 || precision == RP_PREC_3XF16) {
+        if (rp::tc_gemm_standalone(precision == RP_PREC_3XF16, P, Q, K, A, lda, B, ldb, C, ldc, accumulate, st)) return fail("rp_gemm_tn: %s", rp::tc_last_error());
         return 0;
     }
     return fail("rp_gemm_tn: unknown precision %d", precision);
+}
+
+int rp_plan_status(rp_plan* p, void* stream) {
+    if (!p) return fail("rp_plan_status: null argument");
+    if (!(p->use_tc && p->tc.f16)) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int flags = 0;
+    int* dflags = reinterpret_cast<int*>(p->tc.meta + rp::TCM_FLAGS);
+    RP_CUDA(cudaMemcpyAsync(&flags, dflags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RP_CUDA(cudaStreamSynchronize(st));
+    if (flags & 1) {
+        RP_CUDA(cudaMemsetAsync(dflags, 0, sizeof(int), st));
+        return fail("rp_plan_status: the adjoint grew by more than 2^10 within one weight-gradient chunk, which exceeds the binary16 "
+                    "operand range of RP_PREC_3XF16; the gradients of this call are invalid -- use RP_PREC_3XTF32 for this problem");
+    }
+    return 0;
 }
 
 int rp_rls_run(int T, int n_in, int n_out, float beta_inv, const float* X, const float* Y, float* W, float* P,

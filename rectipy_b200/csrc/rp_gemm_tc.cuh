@@ -1,10 +1,18 @@
-// tcgen05 (5th-gen tensor core) contraction with error-compensated 3xTF32 accumulation, sm_100a only.
+// tcgen05 (5th-gen tensor core) contraction with error-compensated split accumulation, sm_100a only.
 //
-//   C[q*ldc + p] (+)= sum_k A[p][k] * B[q][k]        A, B K-major fp32, each pre-split into tf32-exact (hi, lo)
-//   A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo         three kind::tf32 MMAs per logical product, fp32 accumulate in TMEM
+//   C[q*ldc + p] (+)= sum_k A[p][k] * B[q][k]        A, B K-major, each pre-split into (hi, lo) with 11-bit significands
+//   A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo         three MMAs per logical product, fp32 accumulate in TMEM
+//
+// Two element formats carry the split (template parameter F16):
+//   tf32 (kind::tf32): hi, lo stored as fp32 words, fp32 exponent range, K = 8 per MMA
+//   fp16 (kind::f16) : hi, lo stored as binary16 -- the SAME 11-bit significand as tf32, so hi + lo represents x to
+//                      2^-22 |x| exactly like the tf32 split, but the tensor core issues it at twice the rate (K = 16 per
+//                      MMA) and the operands take half the bytes.  The 5-bit exponent is handled by exact power-of-two
+//                      operand scales derived on the device from tracked maxima (ScaleRef, rp_kernels.cuh); the epilogue
+//                      undoes them.  The product of two binary16 numbers is exact in fp32, so nothing else changes.
 //
 // This is what replaces `weights @ x` (edges.py:49 / the generated field, nodes.py:169) and autograd's W^T.grad and
-// grad (x) r products when many trials are batched.  1e-5 parity (BASELINE.json) rules out single-pass TF32.
+// grad (x) r products when many trials are batched.  1e-5 parity (BASELINE.json) rules out single-pass TF32 / FP16.
 //
 // Kernel shape: one CTA per 128(p) x BQ(q) tile, 6 warps:
 //   warp 0   TMA producer   (cp.async.bulk.tensor 2D; K blocks of 16 fp32 = 64-byte swizzled rows, 4-stage ring at BQ=256.
@@ -28,13 +36,25 @@ inline const char* tc_last_error() { return tc_err_buf(); }
 #define RP_TC_FAIL(...) do { snprintf(rp::tc_err_buf(), 384, __VA_ARGS__); return 1; } while (0)
 
 constexpr int TC_BP = 128;          // tile rows (UMMA M, TMEM lanes)
-#ifndef RP_TC_BK
-#define RP_TC_BK 16
+#ifndef RP_TC_ROW_BYTES
+#define RP_TC_ROW_BYTES 64
 #endif
-constexpr int TC_BK = RP_TC_BK;     // fp32 elements per K block: 32 = one 128-byte swizzle row, 16 = one 64-byte swizzle row
-constexpr int TC_ROW_BYTES = TC_BK * 4;
-static_assert(TC_BK == 32 || TC_BK == 16, "K block must be one 128B or one 64B swizzle row");
-constexpr int TC_UMMA_K = 8;        // tf32 MMA K
+constexpr int TC_ROW_BYTES = RP_TC_ROW_BYTES;   // bytes of one operand row per K block = one swizzle row
+static_assert(TC_ROW_BYTES == 128 || TC_ROW_BYTES == 64, "K block must be one 128B or one 64B swizzle row");
+#ifndef RP_TC_CHUNK_K
+#define RP_TC_CHUNK_K 128
+#endif
+#ifndef RP_TC_CHUNK_K_F16
+#define RP_TC_CHUNK_K_F16 128
+#endif
+// element format of the split operands
+template <bool F16> struct TcElt {
+    static constexpr int ESIZE = F16 ? 2 : 4;
+    static constexpr int BK = TC_ROW_BYTES / ESIZE;                            // elements per K block (64 B rows: 16 tf32 / 32 fp16)
+    static constexpr int KSTEPS = TC_ROW_BYTES / 32;                           // MMAs of 32 operand bytes (K = 8 tf32 / 16 fp16) per K block
+    static constexpr int KC = (F16 ? RP_TC_CHUNK_K_F16 : RP_TC_CHUNK_K) / BK;  // K blocks per TMEM accumulation chunk
+    static_assert(KC >= 1, "accumulation chunk shorter than one K block");
+};
 
 enum { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2 };
 constexpr int TC_WGRAD_SPLITS = 2;
@@ -87,21 +107,31 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((8u * TC_ROW_BYTES) >> 4) << 32;        // SBO: 8 rows of one swizzle row each
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)(TC_BK == 32 ? 2 : 4) << 61;             // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+    d |= (uint64_t)(TC_ROW_BYTES == 128 ? 2 : 4) << 61;     // SWIZZLE_128B = 2, SWIZZLE_64B = 4
     return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format TF32 [7,10)=[10,13)=2,
-// a/b K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_tf32_idesc(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format [7,10)/[10,13) (kind::tf32: TF32 = 2,
+// kind::f16: F16 = 0), a/b K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(bool f16, int M, int N) {
+    return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+template <bool F16>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (F16) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    }
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -122,7 +152,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // systematic -2.3e-5 relative bias at K=2048, growing linearly with K).  To stay at fp32 accuracy the K loop is cut into
 // chunks of TC_KC K-blocks; each chunk accumulates into one of two TMEM buffers from zero and the epilogue warps add the
 // finished chunk into fp32 registers with round-to-nearest while the next chunk is being multiplied.
-constexpr int TC_KC = 128 / TC_BK;  // K blocks per TMEM accumulation chunk (k = 128 per chunk)
 constexpr int TC_EPI_WARPS = 8;     // two warps per TMEM lane quadrant, each owning half of the tile's columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
@@ -130,7 +159,7 @@ template <int BQ> struct TcCfg {
     static constexpr int A_BYTES = TC_BP * TC_ROW_BYTES;
     static constexpr int B_BYTES = BQ * TC_ROW_BYTES;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;      // BK=32: 2 (BQ=256) / 3 ; BK=16: 4 / 6
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;      // 128 B rows: 2 (BQ=256) / 3 ; 64 B rows: 4 / 6
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = 2 * BQ;
     static constexpr int COLS_PER_THREAD = BQ / 2;
@@ -149,6 +178,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 struct EpiStore {                       // C[q*ldc + p] (+)= acc ; split-K slices (blockIdx.z) go to C + z*split_stride
     static constexpr bool kStage = false;
     float* C; int ldc; int accumulate; size_t split_stride;
+    ScaleRef sa, sb;                    // binary16 operands: scales of the A and B operand (undone here)
+    __device__ __forceinline__ float2 unscale(int /*p0*/) const { return make_float2(exp2i(-scale_expo(sa)), exp2i(-scale_expo(sb))); }
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -162,8 +193,12 @@ struct EpiFwd {
     static constexpr bool kStage = true;
     FwdStepArgs a;
     float* out_rec_j; int k; int win_first, win_close; float inv_len;
+    ScaleRef sA, sA_ro, sB;             // binary16 operands: scales of kW, of the appended W_out rows and of src_t
+    __device__ __forceinline__ float2 unscale(int p0) const {
+        return make_float2(exp2i(-scale_expo(p0 < a.N ? sA : sA_ro)), exp2i(-scale_expo(sB)));
+    }
 
-    template <int BQ>
+    template <int BQ, bool F16>
     __device__ __forceinline__ void run_tile(int p0, int q0, const float* tile, int et, float* /*extra*/) const {
         constexpr int NSV = ModelTraits<MODEL>::NSV;
         constexpr int NCOL = BQ / 8;
@@ -175,6 +210,8 @@ struct EpiFwd {
             FwdRow row[4];
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) row[rr] = fwd_row<MODEL>(a, i0 + rr);
+            const float so = F16 ? exp2i(scale_expo(a.sc_out)) : 1.f;
+            float smax = 0.f;
             for (int c = 0; c < NCOL; c += 2) {
                 float4 u4[2], v4[2], s4[2], x4[2], xd4[2];
                 float xin0[2], xin1[2];
@@ -195,7 +232,7 @@ struct EpiFwd {
                 for (int cc = 0; cc < 2; ++cc) {
                     const int b = q0 + cbase + c + cc;
                     const size_t idx = (size_t)b * a.N + i0;
-                    float v1[4], s1[4], x1[4], hi[4], lo[4];
+                    float v1[4], s1[4], x1[4], hi[4], lo[4], sr[4];
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
                         const int i = i0 + rr;
@@ -208,14 +245,25 @@ struct EpiFwd {
                         }
                         float src1;
                         if constexpr (ModelTraits<MODEL>::SPIKING) src1 = s1[rr]; else src1 = rate_act<MODEL>(a.mp, i, v1[rr], b);
-                        split_tf32(src1, hi[rr], lo[rr]);
+                        sr[rr] = src1;
+                        if constexpr (F16) smax = fmaxf(smax, fabsf(src1)); else split_tf32(src1, hi[rr], lo[rr]);
                     }
                     if (MODEL == RP_IK && a.urec_out) *reinterpret_cast<float4*>(a.urec_out + idx) = u4[cc];
                     st4(a.y_next + idx, v1[0], v1[1], v1[2], v1[3]);
                     if (NSV > 1) st4(a.y_next + plane + idx, s1[0], s1[1], s1[2], s1[3]);
                     if (NSV > 2) st4(a.y_next + 2 * plane + idx, x1[0], x1[1], x1[2], x1[3]);
-                    st4(a.src_hi + (size_t)b * a.ld_src + i0, hi[0], hi[1], hi[2], hi[3]);
-                    st4(a.src_lo + (size_t)b * a.ld_src + i0, lo[0], lo[1], lo[2], lo[3]);
+                    if constexpr (F16) {
+                        store_split4_f16(a.src_hi, a.src_lo, (size_t)b * a.ld_src + i0, sr, so);
+                    } else {
+                        st4(reinterpret_cast<float*>(a.src_hi) + (size_t)b * a.ld_src + i0, hi[0], hi[1], hi[2], hi[3]);
+                        st4(reinterpret_cast<float*>(a.src_lo) + (size_t)b * a.ld_src + i0, lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+            if constexpr (F16) {
+                if (a.amax_out) {
+                    smax = warp_max(smax);
+                    if (l == 0 && smax > 0.f) atomic_max_nonneg(a.amax_out, smax);
                 }
             }
         } else if (out_rec_j != nullptr) {
@@ -246,9 +294,11 @@ template <int MODEL, bool PG>
 struct EpiAdj {
     static constexpr bool kStage = true;
     AdjArgs a;
+    __device__ __forceinline__ float2 unscale(int /*p0*/) const { return make_float2(1.f, 1.f); }
 
-    template <int BQ>
+    template <int BQ, bool F16>
     __device__ __forceinline__ void run_tile(int p0, int q0, const float* tile, int et, float* /*extra*/) const {
+        static_assert(!F16, "the fused adjoint epilogue exists for the tf32 operand format only");
         constexpr int NSV = ModelTraits<MODEL>::NSV;
         constexpr int NCOL = BQ / 8;
         const int w = et >> 5, l = et & 31;
@@ -346,14 +396,16 @@ struct EpiAdj {
     }
 };
 
-template <int BQ, class Epi>
+template <int BQ, class Epi, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+k_gemm_split3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
               int num_k_blocks, const __grid_constant__ Epi epi) {
     using Cfg = TcCfg<BQ>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int CPT = Cfg::COLS_PER_THREAD;
+    constexpr int TC_BK = TcElt<F16>::BK;
+    constexpr int TC_KC = TcElt<F16>::KC;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -399,7 +451,7 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected thread) =====
-        constexpr uint32_t idesc = make_tf32_idesc(TC_BP, BQ);
+        constexpr uint32_t idesc = make_idesc(F16, TC_BP, BQ);
         int stage = 0; uint32_t phase = 0;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
             const int chunk = kb / TC_KC, kin = kb - chunk * TC_KC;
@@ -419,12 +471,12 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
                 const uint64_t dB_hi = make_sw128_kmajor_desc(sa + 2 * Cfg::A_BYTES);
                 const uint64_t dB_lo = make_sw128_kmajor_desc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
-                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-                    const uint64_t adv = (uint64_t)((k * TC_UMMA_K * 4) >> 4);     // 32 bytes per K=8 step, encoded >>4
+                for (int k = 0; k < TcElt<F16>::KSTEPS; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 32) >> 4);                // 32 operand bytes per MMA, encoded >>4
                     // small cross terms first, leading term last
-                    umma_tf32(tmem_d, dA_lo + adv, dB_hi + adv, idesc, (kin > 0 || k > 0) ? 1u : 0u);
-                    umma_tf32(tmem_d, dA_hi + adv, dB_lo + adv, idesc, 1u);
-                    umma_tf32(tmem_d, dA_hi + adv, dB_hi + adv, idesc, 1u);
+                    umma_ss<F16>(tmem_d, dA_lo + adv, dB_hi + adv, idesc, (kin > 0 || k > 0) ? 1u : 0u);
+                    umma_ss<F16>(tmem_d, dA_hi + adv, dB_lo + adv, idesc, 1u);
+                    umma_ss<F16>(tmem_d, dA_hi + adv, dB_hi + adv, idesc, 1u);
                 }
                 umma_commit(&empty_bar[stage]);                       // frees the smem stage when these MMAs retire
                 if (kin == TC_KC - 1 || kb == num_k_blocks - 1) umma_commit(&tmem_full_bar[buf]);
@@ -458,22 +510,40 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
+        float2 usc = make_float2(1.f, 1.f);
+        if constexpr (F16) usc = epi.unscale(p0);
         if constexpr (!Epi::kStage) {
+            float* cbase = epi.C + blockIdx.z * epi.split_stride + (size_t)(q0 + half * CPT) * epi.ldc + p;
+            if (epi.accumulate) {
+                // read-modify-write of the accumulation slice: 32 independent loads in flight before the first store
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-                float* dst = epi.C + blockIdx.z * epi.split_stride + (size_t)(q0 + half * CPT + j) * epi.ldc + p;
-                float v = acc[j];
-                if (epi.accumulate) v += *dst;
-                *dst = v;
+                for (int j0 = 0; j0 < CPT; j0 += 32) {
+                    float old[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) old[j] = __ldcg(cbase + (size_t)(j0 + j) * epi.ldc);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float v = acc[j0 + j];
+                        if constexpr (F16) v = v * usc.x * usc.y;
+                        cbase[(size_t)(j0 + j) * epi.ldc] = v + old[j];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    float v = acc[j];
+                    if constexpr (F16) v = v * usc.x * usc.y;
+                    cbase[(size_t)j * epi.ldc] = v;
+                }
             }
         } else {
             // all MMAs have retired (last tmem_full barrier) and every TMA load was consumed: the stages are free
             float* tile = reinterpret_cast<float*>(smem);                      // tile[col][row], BQ x 128 fp32
             float* my = tile + (size_t)(half * CPT) * TC_BP + lane_base + lane;
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) my[j * TC_BP] = acc[j];
+            for (int j = 0; j < CPT; ++j) my[j * TC_BP] = F16 ? acc[j] * usc.x * usc.y : acc[j];
             asm volatile("bar.sync 1, 256;" ::: "memory");                      // the 8 epilogue warps only
-            epi.template run_tile<BQ>(p0, q0, tile, ew * 32 + lane, tile + (size_t)BQ * TC_BP);
+            epi.template run_tile<BQ, F16>(p0, q0, tile, ew * 32 + lane, tile + (size_t)BQ * TC_BP);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -483,22 +553,22 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
     }
 }
 
-// split a dense fp32 matrix [rows][ld] into tf32-exact hi/lo copies [rows][ld_out] (zero padded)
+// split a dense fp32 matrix [rows][ld] into hi/lo copies [rows_out][ld_out] (zero padded): tf32-exact fp32 words, or
+// binary16 with the power-of-two scale of `sc` (f16 = 1)
 __global__ void __launch_bounds__(256) k_split_matrix(int rows, int cols, const float* __restrict__ src, int ld,
-                                                       float* __restrict__ hi, float* __restrict__ lo, int ld_out, int rows_out) {
+                                                       void* hi, void* lo, int ld_out, int rows_out, int f16, ScaleRef sc) {
     const size_t total = (size_t)rows_out * ld_out;
+    const float scale = f16 ? exp2i(scale_expo(sc)) : 1.f;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(idx / ld_out), c = (int)(idx - (size_t)r * ld_out);
-        float h = 0.f, l = 0.f;
-        if (r < rows && c < cols) {
-            const float x = src[(size_t)r * ld + c];
-            uint32_t uh, ul;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(uh) : "f"(x));
-            h = __uint_as_float(uh);
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ul) : "f"(x - h));
-            l = __uint_as_float(ul);
+        const float x = (r < rows && c < cols) ? src[(size_t)r * ld + c] : 0.f;
+        if (f16) {
+            store_split1_f16(hi, lo, idx, x, scale);
+        } else {
+            float h, l;
+            split_tf32(x, h, l);
+            reinterpret_cast<float*>(hi)[idx] = h; reinterpret_cast<float*>(lo)[idx] = l;
         }
-        hi[idx] = h; lo[idx] = l;
     }
 }
 
@@ -516,145 +586,198 @@ inline PFN_cuTensorMapEncodeTiled_v12000 tc_encode_fn() {
     return fn;
 }
 
-// 2D K-major operand map: global [rows][ld] fp32, box = 32 (K) x box_rows, 128-byte swizzle
-inline int tc_make_map(CUtensorMap* map, const float* base, int rows, int k_extent, int ld, int box_rows) {
+// 2D K-major operand map: global [rows][ld] elements (fp32 words or binary16), box = one swizzle row (K) x box_rows
+inline int tc_make_map(CUtensorMap* map, const void* base, bool f16, int rows, int k_extent, int ld, int box_rows) {
     auto fn = tc_encode_fn();
     if (!fn) RP_TC_FAIL("cuTensorMapEncodeTiled entry point not available");
+    const int esize = f16 ? 2 : 4;
     cuuint64_t gdim[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * esize};
+    cuuint32_t box[2] = {(cuuint32_t)(TC_ROW_BYTES / esize), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, TC_BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, TC_ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) RP_TC_FAIL("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d k=%d ld=%d box_rows=%d)", (int)r, rows, k_extent, ld, box_rows);
+    if (r != CUDA_SUCCESS) RP_TC_FAIL("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d k=%d ld=%d box_rows=%d f16=%d)", (int)r, rows, k_extent, ld, box_rows, (int)f16);
     return 0;
 }
 
 inline bool tc_supported(int N, int B) { return N % 128 == 0 && B % 128 == 0 && N >= 128 && B >= 128; }
 
+// device-resident scalars of the binary16 path (one small float array per plan)
+enum { TCM_AMAX_W = 0, TCM_AMAX_WOUT, TCM_SRC_BOUND, TCM_G_AMAX0, TCM_G_AMAX1, TCM_CHUNK0, TCM_CHUNK1, TCM_FLAGS, TCM_COUNT = 16 };
+
 struct TcWorkspace {
     int N = 0, B = 0, ldk = 0, ldt = 0, wgrad_chunk = 0;
-    float *W_hi = nullptr, *W_lo = nullptr, *WT_hi = nullptr, *WT_lo = nullptr;       // [N][ldk]
-    float *src_hi = nullptr, *src_lo = nullptr, *g_hi = nullptr, *g_lo = nullptr;     // [B][ldk]
-    float *gT_hi = nullptr, *gT_lo = nullptr, *srcT_hi = nullptr, *srcT_lo = nullptr; // [N][ldt]
+    bool f16 = false;
+    void *W_hi = nullptr, *W_lo = nullptr, *WT_hi = nullptr, *WT_lo = nullptr;       // [N][ldk]
+    void *src_hi = nullptr, *src_lo = nullptr, *g_hi = nullptr, *g_lo = nullptr;     // [B][ldk]
+    void *gT_hi = nullptr, *gT_lo = nullptr, *srcT_hi = nullptr, *srcT_lo = nullptr; // [N][ldt]
+    float* g32 = nullptr;        // binary16 path: g_{t-1} in fp32 [B][N] before the exact-maximum conversion
+    float* src32 = nullptr;      // binary16 path, rate models: act(v_{t-1}) [B][N]
+    float* meta = nullptr;       // [TCM_COUNT]
+    float* amax_src = nullptr;   // [amax_cap] max |src_t| of the steps of the last forward call
+    int amax_cap = 0;
+    const void* fwd_history = nullptr; int fwd_T = -1;      // which checkpoints amax_src describes
     int bq_fwd = 0, bq_wg = 0;
     CUtensorMap m_W[2], m_WT[2], m_src[2], m_g[2], m_gT[2], m_srcT[2];
-    bool attrs_set = false;
+    int esize() const { return f16 ? 2 : 4; }
 };
 
-inline int tc_alloc(float** p, size_t n, size_t* bytes) {
-    if (cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(float)) != cudaSuccess) RP_TC_FAIL("cudaMalloc of %zu bytes failed", n * sizeof(float));
-    if (cudaMemset(*p, 0, n * sizeof(float)) != cudaSuccess) RP_TC_FAIL("cudaMemset failed");
-    *bytes += n * sizeof(float);
+inline int tc_alloc(void** p, size_t bytes_wanted, size_t* bytes) {
+    if (cudaMalloc(p, bytes_wanted) != cudaSuccess) RP_TC_FAIL("cudaMalloc of %zu bytes failed", bytes_wanted);
+    if (cudaMemset(*p, 0, bytes_wanted) != cudaSuccess) RP_TC_FAIL("cudaMemset failed");
+    *bytes += bytes_wanted;
     return 0;
 }
 
-template <class Epi>
+template <class Epi, bool F16>
 inline int tc_set_attrs() {
     static bool done = false;
     if (done) return 0;
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_3xtf32<256, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_3xtf32<128, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_split3<256, Epi, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_split3<128, Epi, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
     if (e != cudaSuccess) RP_TC_FAIL("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
     done = true;
     return 0;
 }
 
 inline void tc_workspace_destroy(TcWorkspace* w) {
-    float* bufs[] = {w->W_hi, w->W_lo, w->WT_hi, w->WT_lo, w->src_hi, w->src_lo, w->g_hi, w->g_lo, w->gT_hi, w->gT_lo, w->srcT_hi, w->srcT_lo};
-    for (float* b : bufs) if (b) cudaFree(b);
+    void* bufs[] = {w->W_hi, w->W_lo, w->WT_hi, w->WT_lo, w->src_hi, w->src_lo, w->g_hi, w->g_lo, w->gT_hi, w->gT_lo, w->srcT_hi, w->srcT_lo,
+                    w->g32, w->src32, w->meta, w->amax_src};
+    for (void* b : bufs) if (b) cudaFree(b);
     *w = TcWorkspace();
 }
 
-inline int tc_workspace_create(TcWorkspace* w, int N, int B, size_t* bytes) {
-    w->N = N; w->B = B; w->ldk = N;
+inline int tc_workspace_create(TcWorkspace* w, int N, int B, bool f16, bool rate_model, size_t* bytes) {
+    w->N = N; w->B = B; w->ldk = N; w->f16 = f16;
+    const size_t es = w->esize();
     // weight-gradient K chunk: several steps' (g, src) columns per GEMM so that the read-modify-write of dW amortises
     int chunk = 8192 / B; if (chunk < 1) chunk = 1; if (chunk > 16) chunk = 16;
     w->wgrad_chunk = chunk;
     w->ldt = chunk * B;
     w->bq_fwd = (B % 256 == 0) ? 256 : 128;
     w->bq_wg = (N % 256 == 0) ? 256 : 128;
-    const size_t nn = (size_t)N * w->ldk, bn = (size_t)B * w->ldk;
-    const size_t nw = (size_t)(N + TC_BP) * w->ldk;        // + one row tile for the fused readout rows (W_out)
+    const size_t nn = (size_t)N * w->ldk * es, bn = (size_t)B * w->ldk * es;
+    const size_t nw = (size_t)(N + TC_BP) * w->ldk * es;        // + one row tile for the fused readout rows (W_out)
     if (tc_alloc(&w->W_hi, nw, bytes) || tc_alloc(&w->W_lo, nw, bytes) || tc_alloc(&w->WT_hi, nn, bytes) || tc_alloc(&w->WT_lo, nn, bytes)) return 1;
     if (tc_alloc(&w->src_hi, bn, bytes) || tc_alloc(&w->src_lo, bn, bytes) || tc_alloc(&w->g_hi, bn, bytes) || tc_alloc(&w->g_lo, bn, bytes)) return 1;
-    if (tc_make_map(&w->m_W[0], w->W_hi, N + TC_BP, N, w->ldk, TC_BP) || tc_make_map(&w->m_W[1], w->W_lo, N + TC_BP, N, w->ldk, TC_BP)) return 1;
-    if (tc_make_map(&w->m_WT[0], w->WT_hi, N, N, w->ldk, TC_BP) || tc_make_map(&w->m_WT[1], w->WT_lo, N, N, w->ldk, TC_BP)) return 1;
-    if (tc_make_map(&w->m_src[0], w->src_hi, B, N, w->ldk, w->bq_fwd) || tc_make_map(&w->m_src[1], w->src_lo, B, N, w->ldk, w->bq_fwd)) return 1;
-    if (tc_make_map(&w->m_g[0], w->g_hi, B, N, w->ldk, w->bq_fwd) || tc_make_map(&w->m_g[1], w->g_lo, B, N, w->ldk, w->bq_fwd)) return 1;
+    if (f16) {
+        if (tc_alloc(reinterpret_cast<void**>(&w->meta), TCM_COUNT * sizeof(float), bytes)) return 1;
+        if (tc_alloc(reinterpret_cast<void**>(&w->g32), (size_t)B * N * sizeof(float), bytes)) return 1;
+        if (rate_model && tc_alloc(reinterpret_cast<void**>(&w->src32), (size_t)B * N * sizeof(float), bytes)) return 1;
+    }
+    if (tc_make_map(&w->m_W[0], w->W_hi, f16, N + TC_BP, N, w->ldk, TC_BP) || tc_make_map(&w->m_W[1], w->W_lo, f16, N + TC_BP, N, w->ldk, TC_BP)) return 1;
+    if (tc_make_map(&w->m_WT[0], w->WT_hi, f16, N, N, w->ldk, TC_BP) || tc_make_map(&w->m_WT[1], w->WT_lo, f16, N, N, w->ldk, TC_BP)) return 1;
+    if (tc_make_map(&w->m_src[0], w->src_hi, f16, B, N, w->ldk, w->bq_fwd) || tc_make_map(&w->m_src[1], w->src_lo, f16, B, N, w->ldk, w->bq_fwd)) return 1;
+    if (tc_make_map(&w->m_g[0], w->g_hi, f16, B, N, w->ldk, w->bq_fwd) || tc_make_map(&w->m_g[1], w->g_lo, f16, B, N, w->ldk, w->bq_fwd)) return 1;
+    return 0;
+}
+
+// per-step source maxima of a forward call (binary16 path): grown on demand, zeroed by the caller
+inline int tc_workspace_ensure_amax(TcWorkspace* w, int n, size_t* bytes) {
+    if (n <= w->amax_cap) return 0;
+    if (w->amax_src) cudaFree(w->amax_src);
+    w->amax_src = nullptr; w->amax_cap = 0;
+    const int cap = n + 1024;
+    if (tc_alloc(reinterpret_cast<void**>(&w->amax_src), (size_t)cap * sizeof(float), bytes)) return 1;
+    w->amax_cap = cap;
     return 0;
 }
 
 // the transposed (trial-major) operand buffers of the weight gradient are only needed by rp_backward
 inline int tc_workspace_ensure_wgrad(TcWorkspace* w, size_t* bytes) {
     if (w->gT_hi) return 0;
-    const size_t nt = (size_t)w->N * w->ldt;
+    const size_t nt = (size_t)w->N * w->ldt * w->esize();
+    const bool f16 = w->f16;
     if (tc_alloc(&w->gT_hi, nt, bytes) || tc_alloc(&w->gT_lo, nt, bytes) || tc_alloc(&w->srcT_hi, nt, bytes) || tc_alloc(&w->srcT_lo, nt, bytes)) return 1;
-    if (tc_make_map(&w->m_srcT[0], w->srcT_hi, w->N, w->ldt, w->ldt, TC_BP) || tc_make_map(&w->m_srcT[1], w->srcT_lo, w->N, w->ldt, w->ldt, TC_BP)) return 1;
-    if (tc_make_map(&w->m_gT[0], w->gT_hi, w->N, w->ldt, w->ldt, w->bq_wg) || tc_make_map(&w->m_gT[1], w->gT_lo, w->N, w->ldt, w->ldt, w->bq_wg)) return 1;
+    if (tc_make_map(&w->m_srcT[0], w->srcT_hi, f16, w->N, w->ldt, w->ldt, TC_BP) || tc_make_map(&w->m_srcT[1], w->srcT_lo, f16, w->N, w->ldt, w->ldt, TC_BP)) return 1;
+    if (tc_make_map(&w->m_gT[0], w->gT_hi, f16, w->N, w->ldt, w->ldt, w->bq_wg) || tc_make_map(&w->m_gT[1], w->gT_lo, f16, w->N, w->ldt, w->ldt, w->bq_wg)) return 1;
     return 0;
 }
 
-template <class Epi>
+template <class Epi, bool F16>
 inline int tc_launch_epi(int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, const Epi& epi, cudaStream_t st, int k_splits = 1) {
-    if (P % TC_BP || Q % bq || K % (TC_BK * k_splits)) RP_TC_FAIL("tc_launch: extents P=%d Q=%d K=%d do not match tile %dx%dx%d (x%d splits)", P, Q, K, TC_BP, bq, TC_BK, k_splits);
-    if (tc_set_attrs<Epi>()) return 1;
+    constexpr int BK = TcElt<F16>::BK;
+    if (P % TC_BP || Q % bq || K % (BK * k_splits)) RP_TC_FAIL("tc_launch: extents P=%d Q=%d K=%d do not match tile %dx%dx%d (x%d splits)", P, Q, K, TC_BP, bq, BK, k_splits);
+    if (tc_set_attrs<Epi, F16>()) return 1;
     dim3 grid(P / TC_BP, Q / bq, k_splits);
-    const int kb = K / TC_BK / k_splits;
-    if (bq == 256) k_gemm_3xtf32<256, Epi><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi);
-    else           k_gemm_3xtf32<128, Epi><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi);
+    const int kb = K / BK / k_splits;
+    if (bq == 256) k_gemm_split3<256, Epi, F16><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi);
+    else           k_gemm_split3<128, Epi, F16><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) RP_TC_FAIL("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
-inline int tc_launch(int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, float* C, int ldc, int accumulate, cudaStream_t st,
-                     int k_splits = 1, size_t split_stride = 0) {
-    EpiStore e{C, ldc, accumulate, split_stride};
-    return tc_launch_epi<EpiStore>(bq, P, Q, K, A, Bm, e, st, k_splits);
+inline int tc_launch(bool f16, int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, float* C, int ldc, int accumulate, cudaStream_t st,
+                     int k_splits = 1, size_t split_stride = 0, ScaleRef sa = no_scale(), ScaleRef sb = no_scale()) {
+    EpiStore e{C, ldc, accumulate, split_stride, sa, sb};
+    if (f16) return tc_launch_epi<EpiStore, true>(bq, P, Q, K, A, Bm, e, st, k_splits);
+    return tc_launch_epi<EpiStore, false>(bq, P, Q, K, A, Bm, e, st, k_splits);
 }
 // fused launches: forward step (rows = N, or N+128 when the readout rows are appended) and adjoint step
 template <int MODEL, bool GEN>
 inline int tc_forward_step(TcWorkspace* w, const EpiFwd<MODEL, GEN>& epi, bool readout_rows, cudaStream_t st) {
-    return tc_launch_epi<EpiFwd<MODEL, GEN>>(w->bq_fwd, w->N + (readout_rows ? TC_BP : 0), w->B, w->N, w->m_W, w->m_src, epi, st);
+    const int P = w->N + (readout_rows ? TC_BP : 0);
+    if (w->f16) return tc_launch_epi<EpiFwd<MODEL, GEN>, true>(w->bq_fwd, P, w->B, w->N, w->m_W, w->m_src, epi, st);
+    return tc_launch_epi<EpiFwd<MODEL, GEN>, false>(w->bq_fwd, P, w->B, w->N, w->m_W, w->m_src, epi, st);
 }
 template <int MODEL, bool PG>
 inline int tc_adjoint_step(TcWorkspace* w, const EpiAdj<MODEL, PG>& epi, cudaStream_t st) {
-    return tc_launch_epi<EpiAdj<MODEL, PG>>(w->bq_fwd, w->N, w->B, w->N, w->m_WT, w->m_g, epi, st);
+    return tc_launch_epi<EpiAdj<MODEL, PG>, false>(w->bq_fwd, w->N, w->B, w->N, w->m_WT, w->m_g, epi, st);
 }
+
+// scale descriptors of the binary16 operands (no-ops on the tf32 path)
+inline ScaleRef tc_scale_W(const TcWorkspace* w) { return w->f16 ? ScaleRef{w->meta + TCM_AMAX_W, 0.f, CV_HG} : no_scale(); }
+inline ScaleRef tc_scale_Wout(const TcWorkspace* w) { return w->f16 ? ScaleRef{w->meta + TCM_AMAX_WOUT, 0.f, CV_HG} : no_scale(); }
+inline ScaleRef tc_scale_srcbound(const TcWorkspace* w) { return w->f16 ? ScaleRef{w->meta + TCM_SRC_BOUND, 0.f, CV_HSRC} : no_scale(); }
 
 // mode TC_FWD:   C=u[b][i]     A = kW (hi,lo)      B = src (hi,lo)     K = N
 // mode TC_DGRAD: C=Z[b][j]     A = (kW)^T          B = g               K = N
 // mode TC_WGRAD: C=dW[i][j] += A = src^T [j][(t,b)] B = g^T [i][(t,b)] K = k_extent (columns filled in the chunk)
-inline int tc_gemm(TcWorkspace* w, int mode, float* C, int ldc, int k_extent, int accumulate, cudaStream_t st) {
+// sb: scale of the B operand (binary16 path): src_t / g_t / the weight-gradient chunk; the A scale follows from the mode
+inline int tc_gemm(TcWorkspace* w, int mode, float* C, int ldc, int k_extent, int accumulate, cudaStream_t st, ScaleRef sb = no_scale()) {
     switch (mode) {
-        case TC_FWD:   return tc_launch(w->bq_fwd, w->N, w->B, w->N, w->m_W, w->m_src, C, ldc, accumulate, st);
-        case TC_DGRAD: return tc_launch(w->bq_fwd, w->N, w->B, w->N, w->m_WT, w->m_g, C, ldc, accumulate, st);
+        case TC_FWD:   return tc_launch(w->f16, w->bq_fwd, w->N, w->B, w->N, w->m_W, w->m_src, C, ldc, accumulate, st, 1, 0, tc_scale_W(w), sb);
+        case TC_DGRAD: return tc_launch(w->f16, w->bq_fwd, w->N, w->B, w->N, w->m_WT, w->m_g, C, ldc, accumulate, st, 1, 0, tc_scale_W(w), sb);
         // 2-way split-K into two accumulation slices: N=4096 gives 512 tiles = 3.46 waves of 148 SMs (86 % filled);
         // 1024 work items = 6.92 waves (99 %).  The slices are summed by k_finish_wgrad.
-        case TC_WGRAD: return tc_launch(w->bq_wg, w->N, w->N, k_extent, w->m_srcT, w->m_gT, C, ldc, accumulate, st, TC_WGRAD_SPLITS, (size_t)w->N * ldc);
+        case TC_WGRAD: return tc_launch(w->f16, w->bq_wg, w->N, w->N, k_extent, w->m_srcT, w->m_gT, C, ldc, accumulate, st, TC_WGRAD_SPLITS, (size_t)w->N * ldc,
+                                        tc_scale_srcbound(w), sb);
     }
     RP_TC_FAIL("tc_gemm: unknown mode %d", mode);
 }
 
 // test entry: arbitrary K-major fp32 operands (split on the fly into temporaries)
-inline int tc_gemm_standalone(int P, int Q, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+inline int tc_gemm_standalone(bool f16, int P, int Q, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                               int accumulate, cudaStream_t st) {
-    if (P % TC_BP || Q % 128 || K <= 0) RP_TC_FAIL("3xTF32 GEMM needs P %% 128 == 0, Q %% 128 == 0 (got P=%d Q=%d K=%d)", P, Q, K);
-    const int Kp = (K + TC_BK - 1) / TC_BK * TC_BK;
+    if (P % TC_BP || Q % 128 || K <= 0) RP_TC_FAIL("split-3 GEMM needs P %% 128 == 0, Q %% 128 == 0 (got P=%d Q=%d K=%d)", P, Q, K);
+    const int BK = f16 ? TcElt<true>::BK : TcElt<false>::BK;
+    const int Kp = (K + BK - 1) / BK * BK;
     const int bq = (Q % 256 == 0) ? 256 : 128;
-    float* tmp = nullptr;
-    const size_t na = (size_t)P * Kp, nb = (size_t)Q * Kp;
-    if (cudaMalloc(reinterpret_cast<void**>(&tmp), 2 * (na + nb) * sizeof(float)) != cudaSuccess) RP_TC_FAIL("cudaMalloc of split temporaries failed");
-    float *a_hi = tmp, *a_lo = tmp + na, *b_hi = tmp + 2 * na, *b_lo = tmp + 2 * na + nb;
-    k_split_matrix<<<1024, 256, 0, st>>>(P, K, A, lda, a_hi, a_lo, Kp, P);
-    k_split_matrix<<<1024, 256, 0, st>>>(Q, K, B, ldb, b_hi, b_lo, Kp, Q);
+    const size_t es = f16 ? 2 : 4;
+    uint8_t* tmp = nullptr;
+    float* amax = nullptr;
+    const size_t na = (size_t)P * Kp * es, nb = (size_t)Q * Kp * es;
+    if (cudaMalloc(reinterpret_cast<void**>(&tmp), 2 * (na + nb)) != cudaSuccess) RP_TC_FAIL("cudaMalloc of split temporaries failed");
+    if (cudaMalloc(reinterpret_cast<void**>(&amax), 2 * sizeof(float)) != cudaSuccess) { cudaFree(tmp); RP_TC_FAIL("cudaMalloc failed"); }
+    cudaMemsetAsync(amax, 0, 2 * sizeof(float), st);
+    void *a_hi = tmp, *a_lo = tmp + na, *b_hi = tmp + 2 * na, *b_lo = tmp + 2 * na + nb;
+    ScaleRef sa = no_scale(), sb = no_scale();
+    if (f16) {
+        k_amax_2d<<<256, 256, 0, st>>>(P, K, A, (size_t)lda, nullptr, 0, amax);
+        k_amax_2d<<<256, 256, 0, st>>>(Q, K, B, (size_t)ldb, nullptr, 0, amax + 1);
+        sa = ScaleRef{amax, 0.f, CV_HG}; sb = ScaleRef{amax + 1, 0.f, CV_HG};
+    }
+    k_split_matrix<<<1024, 256, 0, st>>>(P, K, A, lda, a_hi, a_lo, Kp, P, f16 ? 1 : 0, sa);
+    k_split_matrix<<<1024, 256, 0, st>>>(Q, K, B, ldb, b_hi, b_lo, Kp, Q, f16 ? 1 : 0, sb);
     CUtensorMap mA[2], mB[2];
-    int rc = tc_make_map(&mA[0], a_hi, P, Kp, Kp, TC_BP) || tc_make_map(&mA[1], a_lo, P, Kp, Kp, TC_BP) ||
-             tc_make_map(&mB[0], b_hi, Q, Kp, Kp, bq) || tc_make_map(&mB[1], b_lo, Q, Kp, Kp, bq);
-    if (!rc) rc = tc_launch(bq, P, Q, Kp, mA, mB, C, ldc, accumulate, st);
+    int rc = tc_make_map(&mA[0], a_hi, f16, P, Kp, Kp, TC_BP) || tc_make_map(&mA[1], a_lo, f16, P, Kp, Kp, TC_BP) ||
+             tc_make_map(&mB[0], b_hi, f16, Q, Kp, Kp, bq) || tc_make_map(&mB[1], b_lo, f16, Q, Kp, Kp, bq);
+    if (!rc) rc = tc_launch(f16, bq, P, Q, Kp, mA, mB, C, ldc, accumulate, st, 1, 0, sa, sb);
     cudaStreamSynchronize(st);
     cudaFree(tmp);
+    cudaFree(amax);
     return rc;
 }
 

@@ -9,6 +9,7 @@
 // Layout: state planes y[var][trial][neuron] (plane stride B*N, neuron fastest) so that a warp touches
 // 128 contiguous bytes per access.  All kernels are HBM/L2-bandwidth bound streaming kernels.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/rectipy_b200.h"
@@ -86,6 +87,55 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = round_tf32(x - hi);
 }
 
+// ---- binary16 split (3xFP16 tensor-core path) ------------------------------------------------------------------------------
+// binary16 has the same 11-bit significand as tf32, so hi = rn16(x), lo = rn16(x - hi) represents x to 2^-22 |x| as long as
+// both parts are normal binary16 numbers; below that the error is the absolute 2^-25 of the subnormal grid.  Every operand is
+// therefore multiplied by an exact power of two that puts its largest magnitude near the top of the binary16 range (65504):
+// the worst absolute error is then < 2^-37 of the operand's maximum -- far below fp32 rounding of the contraction itself.
+// The scale is never stored: producer and consumer both derive the exponent from the same device-resident bound.
+struct ScaleRef {
+    const float* bound;   // device scalar: an upper bound (or the exact maximum) of |x| over the operand; nullptr: unscaled
+    float add;            // added to *bound (growth allowance of one step, e.g. +1 for a synapse that gains one spike)
+    int H;                // the bound is mapped into [2^(H-1), 2^H)
+};
+__host__ __device__ inline ScaleRef no_scale() { return ScaleRef{nullptr, 0.f, 0}; }
+__device__ __forceinline__ int expo_for(float bound, int H) {
+    if (!(bound > 0.f) || bound > 3.0e38f) return 0;
+    const int e = H - 1 - ilogbf(bound);
+    return max(-100, min(100, e));
+}
+__device__ __forceinline__ float exp2i(int e) { return __int_as_float((e + 127) << 23); }       // 2^e, |e| <= 126
+__device__ __forceinline__ int scale_expo(const ScaleRef& r) { return r.bound ? expo_for(*r.bound + r.add, r.H) : 0; }
+__device__ __forceinline__ void split_f16(float xs, __half& hi, __half& lo) {
+    hi = __float2half_rn(xs);
+    lo = __float2half_rn(xs - __half2float(hi));
+}
+// four consecutive elements -> one 8-byte store per part
+__device__ __forceinline__ void store_split4_f16(void* hi_base, void* lo_base, size_t elem_off, const float* x, float scale) {
+    __half h[4], l[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) split_f16(x[r] * scale, h[r], l[r]);
+    uint2 ph, pl;
+    ph.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+    ph.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    pl.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+    pl.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi_base) + elem_off) = ph;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo_base) + elem_off) = pl;
+}
+__device__ __forceinline__ void store_split1_f16(void* hi_base, void* lo_base, size_t elem_off, float x, float scale) {
+    __half h, l;
+    split_f16(x * scale, h, l);
+    reinterpret_cast<__half*>(hi_base)[elem_off] = h;
+    reinterpret_cast<__half*>(lo_base)[elem_off] = l;
+}
+// running maximum of non-negative floats (bit patterns of non-negative floats order like unsigned integers)
+__device__ __forceinline__ void atomic_max_nonneg(float* dst, float v) { atomicMax(reinterpret_cast<unsigned int*>(dst), __float_as_uint(v)); }
+__device__ __forceinline__ float warp_max(float v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // forward step
 // ------------------------------------------------------------------------------------------------------
@@ -100,9 +150,11 @@ struct FwdStepArgs {
     const float* W_in;    // [N][m]
     ModelParams mp;
     float* src_next;      // rate models, fp32 path: act(v_{t+1}) [B][N], else nullptr
-    float* src_hi;        // 3xTF32 path: source operand of the next step, split, [B][ld_src]
-    float* src_lo;
+    void* src_hi;         // tensor-core path: source operand of the next step, split, [B][ld_src] (fp32 words or binary16)
+    void* src_lo;
     int ld_src;
+    ScaleRef sc_out;      // binary16 operands: scale of the operand written here; amax_out receives max |src_{t+1}|
+    float* amax_out;
     float* urec_out;      // ik: checkpoint plane receiving the recurrent drive of this step [B][N], or nullptr
     int per_trial;        // 1: some parameter differs between trials (no per-neuron hoisting)
 };
@@ -236,8 +288,8 @@ __device__ __forceinline__ void fwd_element(const FwdStepArgs& a, int i, int b, 
     if (a.src_hi) {
         float hi, lo;
         split_tf32(src1, hi, lo);
-        a.src_hi[(size_t)b * a.ld_src + i] = hi;
-        a.src_lo[(size_t)b * a.ld_src + i] = lo;
+        reinterpret_cast<float*>(a.src_hi)[(size_t)b * a.ld_src + i] = hi;
+        reinterpret_cast<float*>(a.src_lo)[(size_t)b * a.ld_src + i] = lo;
     }
 }
 
@@ -251,22 +303,51 @@ __global__ void __launch_bounds__(256) k_fwd_step(FwdStepArgs a) {
 }
 
 // source operand of the very first step (and of re-started runs): src_0 from y_0
+// f16: 0 -> tf32 split into fp32 words, 1 -> binary16 split with scale `sc`.  amax_out (optional): max |src_0|.
 template <int MODEL>
 __global__ void __launch_bounds__(256) k_init_src(int N, int B, const float* y, ModelParams mp,
-                                                   float* src, int ld_plain, float* src_hi, float* src_lo, int ld_src) {
+                                                   float* src, int ld_plain, void* src_hi, void* src_lo, int ld_src,
+                                                   int f16, ScaleRef sc, float* amax_out) {
     const size_t plane = (size_t)B * N;
+    const float scale = f16 ? exp2i(scale_expo(sc)) : 1.f;
+    float amax = 0.f;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane; idx += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(idx / N), i = (int)(idx - (size_t)b * N);
         float r;
         if constexpr (ModelTraits<MODEL>::SPIKING) r = y[plane + idx]; else r = rate_act<MODEL>(mp, i, y[idx], b);
+        amax = fmaxf(amax, fabsf(r));
         if (src) src[(size_t)b * ld_plain + i] = r;
         if (src_hi) {
-            float hi, lo;
-            split_tf32(r, hi, lo);
-            src_hi[(size_t)b * ld_src + i] = hi;
-            src_lo[(size_t)b * ld_src + i] = lo;
+            if (f16) {
+                store_split1_f16(src_hi, src_lo, (size_t)b * ld_src + i, r, scale);
+            } else {
+                float hi, lo;
+                split_tf32(r, hi, lo);
+                reinterpret_cast<float*>(src_hi)[(size_t)b * ld_src + i] = hi;
+                reinterpret_cast<float*>(src_lo)[(size_t)b * ld_src + i] = lo;
+            }
         }
     }
+    if (amax_out) {
+        amax = warp_max(amax);
+        if ((threadIdx.x & 31) == 0) atomic_max_nonneg(amax_out, amax);
+    }
+}
+
+// ---- absolute maxima that the binary16 operand scales are derived from --------------------------------------------------------
+// dst = max(dst, max |src[r*ld + c] * rowscale[r*rs_stride]|) over rows x cols   (rowscale == nullptr: 1)
+__global__ void __launch_bounds__(256) k_amax_2d(int rows, int cols, const float* __restrict__ src, size_t ld,
+                                                  const float* __restrict__ rowscale, int rs_stride, float* dst) {
+    float amax = 0.f;
+    const size_t total = (size_t)rows * cols;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = idx / cols, c = idx - r * cols;
+        float v = src[r * ld + c];
+        if (rowscale) v *= __ldg(rowscale + r * rs_stride);
+        amax = fmaxf(amax, fabsf(v));
+    }
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomic_max_nonneg(dst, amax);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -391,6 +472,7 @@ struct AdjArgs {
     ModelParams mp;
     float* g;              // [B][N]   operand for the next GEMMs (fp32 path)
     float* src;            // [B][N]   rate models: act(v_{t-1}) for the weight gradient (fp32 path), else nullptr
+    float* g_amax;         // optional: receives max |g_{t-1}| (binary16 operand scaling), accumulated with atomicMax
     float* g_hi; float* g_lo; int ld_g;           // 3xTF32 operands  [B][ld_g]
     float* gT_hi; float* gT_lo;                   // transposed copies [N][ld_t] for the weight gradient
     float* srcT_hi; float* srcT_lo; int ld_t; int t_col0;  // column offset (trial index base) inside the K-chunk
@@ -640,6 +722,7 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
     const size_t plane = (size_t)a.B * a.N;
     const AdjRowParams rp0{c.tau, c.tau_s, c.tau_x, c.alpha};
     const RegAcc racc{c.acc};
+    float gmax = 0.f;
     for (int l0 = 0; l0 < ADJ_BPT; l0 += BATCH) {
         float av[BATCH], as[BATCH], ax[BATCH], v[BATCH], s[BATCH], x[BATCH], vm[BATCH], sm[BATCH], Z[BATCH], ur[BATCH];
         bool ok[BATCH];
@@ -683,6 +766,7 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
                 }
                 if (a.do_pre) {
                     adj_pre_math<MODEL>(a, i, av[l], vm[l], sm[l], g, srcv, b);
+                    gmax = fmaxf(gmax, fabsf(g));
                     if (a.g) a.g[idx] = g;
                     if (a.src) a.src[idx] = srcv;
                     if (a.g_hi) {
@@ -695,6 +779,10 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
             }
             if (transposed) { tg[bl][threadIdx.x] = g; ts[bl][threadIdx.x] = srcv; }
         }
+    }
+    if (a.g_amax && a.do_pre) {
+        gmax = warp_max(gmax);
+        if (threadIdx.x == 0 && gmax > 0.f) atomic_max_nonneg(a.g_amax, gmax);
     }
     if (transposed) {
         __syncthreads();
@@ -758,6 +846,7 @@ __global__ void __launch_bounds__(256) k_adj_step_v4(AdjArgs a) {
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) rp_[rr] = adj_row_params<MODEL>(a, i0 + rr);
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float gmax = 0.f;
 
     for (int l0 = 0; l0 < ADJ4_TB / 8; l0 += 2) {
         float4 av[2], as[2], ax[2], v[2], s[2], x[2], vm[2], sm[2], Z[2], ur[2];
@@ -795,6 +884,7 @@ __global__ void __launch_bounds__(256) k_adj_step_v4(AdjArgs a) {
                                          nav[rr], nas[rr], nax[rr], f4at(ur[l], rr));
                 g[rr] = 0.f; sv[rr] = 0.f;
                 if (a.do_pre) adj_pre_math<MODEL>(a, i0 + rr, nav[rr], f4at(vm[l], rr), f4at(sm[l], rr), g[rr], sv[rr], b);
+                gmax = fmaxf(gmax, fabsf(g[rr]));
                 split_tf32(g[rr], gh[rr], gl[rr]);
             }
             if (a.do_post) {
@@ -816,6 +906,10 @@ __global__ void __launch_bounds__(256) k_adj_step_v4(AdjArgs a) {
             }
         }
     }
+    if (a.g_amax && a.do_pre) {
+        gmax = warp_max(gmax);
+        if (tx == 0 && gmax > 0.f) atomic_max_nonneg(a.g_amax, gmax);
+    }
     if (transposed) {
         __syncthreads();
         // lane tx -> trial bblk + tx; warp ty walks neurons ty, ty+8, ...: every store is 32 consecutive trials of one neuron
@@ -828,6 +922,95 @@ __global__ void __launch_bounds__(256) k_adj_step_v4(AdjArgs a) {
             a.srcT_hi[off] = hi; a.srcT_lo[off] = lo;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// binary16 operands of the reverse sweep.  The adjoint kernel leaves g_{t-1} in fp32 together with its exact maximum; this
+// kernel turns it (and the source values r_{t-1}) into the split binary16 operands of the next two contractions:
+//   K-major    g_hi/lo  [B][ld_g]           scale 2^e(max|g_{t-1}|)      -> Z_{t-1} = (kW)^T g_{t-1}
+//   trial-major gT, srcT [N][ld_t]          one scale per weight-gradient K chunk (several steps share one accumulator)
+// The chunk scale is fixed by the first step of the chunk with a non-zero gradient, with 2^8 headroom for growth inside the
+// chunk; growth beyond that is absorbed by moving up to 2^3 into the source operand, and anything beyond raises a flag that
+// rp_plan_status reports (the caller should then use RP_PREC_3XTF32).
+// ------------------------------------------------------------------------------------------------------
+constexpr int CV_HG = 14;        // exact-maximum operands: max -> [2^13, 2^14)
+constexpr int CV_HCHUNK = 8;     // weight-gradient chunk: first maximum -> [2^7, 2^8)
+constexpr int CV_HSRC = 12;      // source operand bound -> [2^11, 2^12)
+struct ConvArgs {
+    int N, B;
+    const float* g32;            // [B][N]
+    const float* src32;          // [B][N] source values of the same step (spiking: checkpoint plane s_{t-1}; rate: act(v_{t-1}))
+    void *g_hi, *g_lo; int ld_g;
+    void *gT_hi, *gT_lo, *srcT_hi, *srcT_lo; int ld_t, t_col0;     // gT_hi == nullptr: no weight gradient wanted
+    const float* g_amax;         // exact max |g32| (complete: written by the previous kernel)
+    float* g_amax_clear;         // the other parity slot, zeroed here for the next step
+    const float* chunk_ref_in;   // reference maximum of the open chunk (previous step's chunk_ref_out)
+    float* chunk_ref_out;
+    int chunk_first;             // 1: this step opens a new chunk
+    ScaleRef sc_src;             // bound of |src| over the whole sweep
+    int* flags;                  // bit 0: binary16 range exceeded
+};
+
+__global__ void __launch_bounds__(256) k_adj_convert_f16(ConvArgs a) {
+    __shared__ float tg[ADJ4_TB][128 + 4];
+    __shared__ float ts[ADJ4_TB][128 + 4];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i0 = blockIdx.x * 128 + 4 * tx;
+    const int bblk = blockIdx.y * ADJ4_TB;
+    const float gmax = *a.g_amax;
+    const int eg = expo_for(gmax, CV_HG);
+    const float sg = exp2i(eg);
+    const bool wg = a.gT_hi != nullptr;
+    float sgT = 1.f, ssT = 1.f;
+    if (wg) {
+        const float ref_in = *a.chunk_ref_in;
+        const float ref = (a.chunk_first || !(ref_in > 0.f)) ? gmax : ref_in;
+        const int ec = expo_for(ref, CV_HCHUNK);
+        const int elim = expo_for(gmax, 15);                 // largest exponent that keeps this step's g below 2^15 (binary16 max: 65504)
+        const int eu = gmax > 0.f ? min(ec, elim) : ec;     // an all-zero step (e.g. right after a truncation cut) constrains nothing
+        const int comp = ec - eu;                            // moved into the source operand so that the product scale stays 2^(ec+es)
+        const int es = scale_expo(a.sc_src);
+        sgT = exp2i(eu);
+        ssT = exp2i(es + min(comp, 3));
+        if (blockIdx.x == 0 && blockIdx.y == 0 && tx == 0 && ty == 0) {
+            *a.chunk_ref_out = ref;
+            *a.g_amax_clear = 0.f;
+            if (comp > 3) atomicOr(a.flags, 1);
+        }
+    } else if (blockIdx.x == 0 && blockIdx.y == 0 && tx == 0 && ty == 0) {
+        *a.g_amax_clear = 0.f;
+    }
+#pragma unroll
+    for (int l = 0; l < ADJ4_TB / 8; ++l) {
+        const int bl = l * 8 + ty;
+        const int b = bblk + bl;
+        const size_t idx = (size_t)b * a.N + i0;
+        const float4 g4 = *reinterpret_cast<const float4*>(a.g32 + idx);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+        store_split4_f16(a.g_hi, a.g_lo, (size_t)b * a.ld_g + i0, g, sg);
+        if (wg) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.src32 + idx));
+            *reinterpret_cast<float4*>(&tg[bl][4 * tx]) = g4;
+            *reinterpret_cast<float4*>(&ts[bl][4 * tx]) = s4;
+        }
+    }
+    if (wg) {
+        __syncthreads();
+        // lane tx -> trial bblk + tx; warp ty walks neurons ty, ty+8, ...: every store is 32 consecutive trials of one neuron
+        for (int r = ty; r < 128; r += 8) {
+            const size_t off = (size_t)(blockIdx.x * 128 + r) * a.ld_t + a.t_col0 + bblk + tx;
+            store_split1_f16(a.gT_hi, a.gT_lo, off, tg[tx][r], sgT);
+            store_split1_f16(a.srcT_hi, a.srcT_lo, off, ts[tx][r], ssT);
+        }
+    }
+}
+
+// max over a short device array (the per-step source maxima of the last forward pass) -> *dst
+__global__ void k_max_of_array(const float* src, int n, float* dst) {
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += 32) m = fmaxf(m, src[i]);
+    m = warp_max(m);
+    if (threadIdx.x == 0) *dst = m;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -857,6 +1040,29 @@ __global__ void __launch_bounds__(256) k_prepare_weights(int N, const float* __r
             const float w = tile[tx][r];
             if (WkT) WkT[(size_t)j * ldw + i] = w;
             if (WkT_hi) { float hi, lo; split_tf32(w, hi, lo); WkT_hi[(size_t)j * ldw + i] = hi; WkT_lo[(size_t)j * ldw + i] = lo; }
+        }
+    }
+}
+
+// binary16 variant: hi/lo of k_i W[i][j] * 2^e and/or of its transpose; e from the tracked maximum of |kW|
+__global__ void __launch_bounds__(256) k_prepare_weights_f16(int N, const float* __restrict__ W, const float* __restrict__ kp, int k_stride, int ldw,
+                                                              void* Wk_hi, void* Wk_lo, void* WkT_hi, void* WkT_lo, ScaleRef sc) {
+    __shared__ float tile[32][33];
+    const float scale = exp2i(scale_expo(sc));
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int i = by + r, j = bx + tx;
+        float w = 0.f;
+        if (i < N && j < N) w = W[(size_t)i * N + j] * __ldg(kp + (size_t)i * k_stride);
+        tile[r][tx] = w;
+        if (i < N && j < N && Wk_hi) store_split1_f16(Wk_hi, Wk_lo, (size_t)i * ldw + j, w, scale);
+    }
+    __syncthreads();
+    if (WkT_hi) {
+        for (int r = ty; r < 32; r += 8) {
+            const int j = bx + r, i = by + tx;
+            if (i < N && j < N) store_split1_f16(WkT_hi, WkT_lo, (size_t)j * ldw + i, tile[tx][r], scale);
         }
     }
 }

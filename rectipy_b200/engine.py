@@ -117,7 +117,7 @@ def total_launches() -> int:
 
 
 def tc_supported(n: int, batch: int) -> bool:
-    """Shapes the tcgen05 3xTF32 kernels accept (rp_gemm_tc.cuh: 128-row tiles on both operands)."""
+    """Shapes the tcgen05 split-3 kernels (3xTF32 / 3xFP16) accept (rp_gemm_tc.cuh: 128-row tiles on both operands)."""
     return n >= 128 and batch >= 128 and n % 128 == 0 and batch % 128 == 0
 
 
@@ -302,6 +302,8 @@ class EngineRun(torch.autograd.Function):
                         b.dparams[slot] = buf.data_ptr()
                     dps.append(buf)
                 abi.check(lib.rp_backward(plan.handle, C.byref(b), _stream()), "rp_backward")
+                if key.precision == abi.RP_PREC_3XF16:      # binary16 operand range guard (synchronises the stream)
+                    abi.check(lib.rp_plan_status(plan.handle, _stream()), "rp_backward")
                 accumulate("W", dW), accumulate("W_in", dW_in), accumulate("W_out", dW_out)
                 for i, buf in enumerate(dps):
                     accumulate(("p", i), buf)

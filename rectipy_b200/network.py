@@ -40,13 +40,13 @@ class _Chain:
 def _precision_code(precision: str, n: int, batch: int) -> int:
     if precision in ("fp32", "float32"):
         return abi.RP_PREC_FP32
-    if precision in ("3xtf32", "tf32x3"):
+    if precision in ("3xtf32", "tf32x3", "3xf16", "f16x3"):
         if not engine.tc_supported(n, batch):
-            raise ValueError(f"precision='3xtf32' needs n % 128 == 0 and batch % 128 == 0 (n={n}, batch={batch})")
-        return abi.RP_PREC_3XTF32
+            raise ValueError(f"precision={precision!r} needs n % 128 == 0 and batch % 128 == 0 (n={n}, batch={batch})")
+        return abi.RP_PREC_3XTF32 if precision in ("3xtf32", "tf32x3") else abi.RP_PREC_3XF16
     if precision == "auto":
-        return abi.RP_PREC_3XTF32 if engine.tc_supported(n, batch) else abi.RP_PREC_FP32
-    raise ValueError(f"unknown precision {precision!r}; use 'auto', 'fp32' or '3xtf32'")
+        return abi.RP_PREC_3XF16 if engine.tc_supported(n, batch) else abi.RP_PREC_FP32
+    raise ValueError(f"unknown precision {precision!r}; use 'auto', 'fp32', '3xtf32' or '3xf16'")
 
 
 def _record_steps(T: int, S: int, cutoff: int) -> List[int]:

@@ -152,27 +152,66 @@ def test_fp32_contraction_kernels(P, Q, K):
     assert rel_err(C.cpu().numpy(), ref.cpu().numpy()) < 2e-6
 
 
+TC_PRECS = ("3xtf32", "3xf16")      # tensor-core operand formats: two tf32 words | two binary16 words + power-of-two scales
+
+
+@pytest.mark.parametrize("prec", TC_PRECS)
 @pytest.mark.parametrize("P,Q,K", [(128, 128, 32), (128, 256, 64), (256, 128, 96), (512, 1024, 2048), (384, 384, 500)])
-def test_tcgen05_3xtf32_contraction(P, Q, K):
-    """tcgen05 3xTF32 kernel vs fp64 matmul: error must be at fp32 level (single-pass TF32 would be ~1e-3)."""
+def test_tcgen05_split3_contraction(P, Q, K, prec):
+    """tcgen05 split-3 kernel (tf32 and binary16 operands) vs fp64 matmul: error must be at fp32 level (a single-pass
+    TF32 / FP16 product would be ~1e-3)."""
     from rectipy_b200 import engine, _cabi
+    code = _cabi.RP_PREC_3XTF32 if prec == "3xtf32" else _cabi.RP_PREC_3XF16
     g = torch.Generator(device="cuda").manual_seed(P + Q + K)
     A = torch.randn(P, K, device="cuda", generator=g)
     B = torch.randn(Q, K, device="cuda", generator=g)
-    C = engine.gemm_tn(A, B, precision=_cabi.RP_PREC_3XTF32)
+    C = engine.gemm_tn(A, B, precision=code)
     torch.cuda.synchronize()
     ref = (B.double() @ A.double().T)
     err = rel_err(C.cpu().numpy(), ref.cpu().numpy())
     fp32_err = rel_err((B @ A.T).cpu().numpy(), ref.cpu().numpy())
-    print(f"3xTF32 rel err {err:.2e}  (torch fp32 matmul {fp32_err:.2e})")
+    print(f"{prec} rel err {err:.2e}  (torch fp32 matmul {fp32_err:.2e})")
     assert err < max(3e-6, 2.0 * fp32_err)     # chunked fp32 re-accumulation keeps the tcgen05 path at FFMA accuracy
-    C2 = engine.gemm_tn(A, B, precision=_cabi.RP_PREC_3XTF32, out=C.clone(), accumulate=True)
+    C2 = engine.gemm_tn(A, B, precision=code, out=C.clone(), accumulate=True)
     assert rel_err(C2.cpu().numpy(), 2 * ref.cpu().numpy()) < 5e-6
 
 
+@pytest.mark.parametrize("case", ["tiny", "huge", "positive", "wide_range", "sparse_spikes"])
+def test_binary16_split_operand_scaling(case):
+    """RP_PREC_3XF16 carries the split in binary16 words; its 5-bit exponent is handled by exact power-of-two operand
+    scales.  Operands far outside the binary16 range, one-signed sums (accumulator truncation) and operands spanning many
+    orders of magnitude must all come out at fp32 accuracy relative to the result's norm, like the tf32 split."""
+    from rectipy_b200 import engine, _cabi
+    P, Q, K = 256, 256, 1024
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A = torch.randn(P, K, device="cuda", generator=g)
+    B = torch.randn(Q, K, device="cuda", generator=g)
+    if case == "tiny":
+        A, B = A * 1e-20, B * 3e-9
+    elif case == "huge":
+        A, B = A * 1e15, B * 7e11
+    elif case == "positive":
+        A, B = A.abs() + 0.5, B.abs() + 0.25
+    elif case == "wide_range":
+        A = A * torch.exp(6.0 * torch.randn(P, K, device="cuda", generator=g))
+        B = B * torch.exp(6.0 * torch.randn(Q, K, device="cuda", generator=g))
+    else:
+        B = (torch.rand(Q, K, device="cuda", generator=g) < 0.02).float() + 0.3 * torch.rand(Q, K, device="cuda", generator=g) ** 8
+    ref = (B.double() @ A.double().T).cpu().numpy()
+    errs = {}
+    for prec, code in (("fp32", _cabi.RP_PREC_FP32), ("3xtf32", _cabi.RP_PREC_3XTF32), ("3xf16", _cabi.RP_PREC_3XF16)):
+        C = engine.gemm_tn(A, B, precision=code)
+        torch.cuda.synchronize()
+        assert torch.isfinite(C).all(), (case, prec)
+        errs[prec] = rel_err(C.cpu().numpy(), ref)
+    print(case, errs)
+    assert errs["3xf16"] < max(3e-6, 2.0 * errs["fp32"], 2.0 * errs["3xtf32"]), errs
+
+
+@pytest.mark.parametrize("tc_prec", TC_PRECS)
 @pytest.mark.parametrize("model", ["li_tanh", "qif"])
-def test_tensor_core_path_matches_fp32_path(model):
-    """N=256, B=256: the 3xTF32 engine path vs the FFMA path vs the oracle (sample of trials)."""
+def test_tensor_core_path_matches_fp32_path(model, tc_prec):
+    """N=256, B=256: the tensor-core engine path (both operand formats) vs the FFMA path vs the oracle (sample of trials)."""
     import rectipy_b200 as rp
     from golden_util import TEMPLATE_PATH
     n, B, m, k = 256, 256, 2, 3
@@ -188,7 +227,7 @@ def test_tensor_core_path_matches_fp32_path(model):
     path, op, svar, tvar = TEMPLATE_PATH[model]
     y_init = np.concatenate([rng.uniform(-50.0, 99.0, (B, n)), np.zeros((B, n))], axis=1).astype(np.float32)
     results = {}
-    for prec in ("fp32", "3xtf32"):
+    for prec in ("fp32", tc_prec):
         net = rp.Network(dt, device="cuda:0", batch=B, precision=prec)
         kw = dict(weights=W, source_var=svar, target_var=tvar, input_var=f"{op}/I_ext",
                   node_vars={f"{op}/{p}": v for p, v in params.items()}, train_params=["weights", f"{op}/eta"])
@@ -208,8 +247,8 @@ def test_tensor_core_path_matches_fp32_path(model):
                              geta=node[f"{op}/eta"].grad.cpu().numpy(),
                              gin=net.get_edge("inp", "rnn").weights.grad.cpu().numpy(),
                              gout=net.get_edge("rnn", "out").weights.grad.cpu().numpy(), y=node.y.detach().cpu().numpy())
-    errs = {key: rel_err(results["3xtf32"][key], results["fp32"][key]) for key in results["fp32"]}
-    print(model, errs)
+    errs = {key: rel_err(results[tc_prec][key], results["fp32"][key]) for key in results["fp32"]}
+    print(model, tc_prec, errs)
     assert np.abs(results["fp32"]["out"]).max() > 0 and np.abs(results["fp32"]["gW"]).max() > 0      # spikes happened, gradient is live
     tol = 1e-5 if model == "li_tanh" else 1e-3
     assert all(e <= tol for e in errs.values()), errs
@@ -219,7 +258,7 @@ def test_tensor_core_path_matches_fp32_path(model):
         onet = orc.OracleNet(onode, w_in=torch.tensor(w_in), w_out=torch.tensor(w_out))
         r = onet.run(torch.tensor(x[:, b, :]), sampling_steps=S, enable_grad=False)
         ref = torch.stack(r["out"]).numpy()
-        assert rel_err(results["3xtf32"]["out"][:, b, :], ref) <= (1e-5 if model == "li_tanh" else 1e-4)
+        assert rel_err(results[tc_prec]["out"][:, b, :], ref) <= (1e-5 if model == "li_tanh" else 1e-4)
 
 
 @pytest.mark.parametrize("model,n,B", [("qif_sfa", 1000, 1), ("li_tanh", 203, 2), ("lif", 64, 4), ("qif", 1536, 1)])
@@ -284,7 +323,8 @@ def test_persistent_kernels_match_per_step_path(model, n, B, monkeypatch):
     assert all(e <= tol for e in errs.values()), errs
 
 
-def test_full_size_properties_headline_config():
+@pytest.mark.parametrize("tc_prec", TC_PRECS)
+def test_full_size_properties_headline_config(tc_prec):
     """BASELINE full size (QIF N=4096, 1024 trials): properties that need no CPU reference run.
     (1) trials are independent: permuting the trial axis of the inputs permutes records and leaves dW unchanged (up to
         summation order); (2) the adjoint is linear in the output gradient; (3) the 3xTF32 path reproduces the FFMA path's
@@ -318,18 +358,18 @@ def test_full_size_properties_headline_config():
             res["v"] = torch.stack(obs[("qif", "v")])
         return res
 
-    base = run("3xtf32", x, y0, gout, vars_=True)
+    base = run(tc_prec, x, y0, gout, vars_=True)
     assert torch.isfinite(base["out"]).all() and torch.isfinite(base["gW"]).all()
     n_spikes = int((base["v"] >= 100.0).sum())
     assert n_spikes > 10000, n_spikes
     # (1) permutation of trials
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
-    pr = run("3xtf32", x[:, perm.numpy(), :], y0[perm.numpy()], gout[:, perm.cuda(), :])
+    pr = run(tc_prec, x[:, perm.numpy(), :], y0[perm.numpy()], gout[:, perm.cuda(), :])
     assert torch.equal(pr["out"], base["out"][:, perm.cuda(), :])            # per-trial arithmetic is identical
     assert rel_err(pr["gW"].cpu().numpy(), base["gW"].cpu().numpy()) < 1e-4
     assert rel_err(pr["gout"].cpu().numpy(), base["gout"].cpu().numpy()) < 1e-4
     # (2) linearity of the adjoint in dL/dout
-    lin = run("3xtf32", x, y0, 2.5 * gout)
+    lin = run(tc_prec, x, y0, 2.5 * gout)
     assert rel_err(lin["gW"].cpu().numpy(), 2.5 * base["gW"].cpu().numpy()) < 1e-5
     assert rel_err(lin["gout"].cpu().numpy(), 2.5 * base["gout"].cpu().numpy()) < 1e-5
     # (3) tensor-core path vs FFMA path: spike rasters of a sample of trials
@@ -340,7 +380,8 @@ def test_full_size_properties_headline_config():
     assert rel_err(base["out"].cpu().numpy(), ff["out"].cpu().numpy()) < 1e-3
 
 
-def test_full_size_rate_network_directional_derivative():
+@pytest.mark.parametrize("tc_prec", TC_PRECS)
+def test_full_size_rate_network_directional_derivative(tc_prec):
     """LI-tanh N=4096, 1024 trials on the tensor-core path: <dL/dW, D> from the adjoint equals the finite-difference
     directional derivative of the loss (fp32 central difference, so 2 % tolerance)."""
     import rectipy_b200 as rp
@@ -353,7 +394,7 @@ def test_full_size_rate_network_directional_derivative():
     tgt = torch.tensor(rng.standard_normal((T, B, 2)).astype(np.float32), device="cuda")
 
     def loss_of(Wm, grad):
-        net = rp.Network(dt, device="cuda:0", batch=B, precision="3xtf32")
+        net = rp.Network(dt, device="cuda:0", batch=B, precision=tc_prec)
         node = net.add_diffeq_node("rnn", "neuron_model_templates.rate_neurons.leaky_integrator.tanh", weights=Wm, source_var="tanh_op/r",
                                    target_var="li_op/r_in", input_var="li_op/I_ext", output_var="li_op/v",
                                    node_vars={"li_op/tau": 0.5, "li_op/k": 1.3}, train_params=["weights"] if grad else None)
@@ -384,7 +425,7 @@ def test_izhikevich_batched_paths_agree():
     w_in, w_out = rng.standard_normal((n, m)) * 10.0, rng.standard_normal((k, n)) / np.sqrt(n)
     etas = rng.uniform(60.0, 160.0, n)
     params = dict(eta=etas, g=1.5)
-    for B, prec in ((2, "fp32"), (20, "fp32"), (128, "3xtf32")):
+    for B, prec in ((2, "fp32"), (20, "fp32"), (128, "3xtf32"), (128, "3xf16")):
         x = (3.0 * np.sin(2 * np.pi * rng.uniform(5, 30, (1, B, m)) * (np.arange(T) * dt * 1e-3)[:, None, None]) + 1.0)
         net = rp.Network(dt, device="cuda:0", batch=B, precision=prec)
         node = net.add_diffeq_node("ik", "neuron_model_templates.spiking_neurons.ik.ik", weights=W, source_var="s", target_var="s_in",
@@ -410,7 +451,7 @@ def test_izhikevich_batched_paths_agree():
         assert all(torch.isfinite(p.grad).all() for p in net.parameters())
 
 
-@pytest.mark.parametrize("model,n,B,prec", [("qif", 128, 128, "3xtf32"), ("li_tanh", 64, 1, "fp32"), ("qif_sfa", 96, 20, "fp32"), ("ik", 64, 2, "fp32")])
+@pytest.mark.parametrize("model,n,B,prec", [("qif", 128, 128, "3xtf32"), ("qif", 128, 128, "3xf16"), ("li_tanh", 64, 1, "fp32"), ("qif_sfa", 96, 20, "fp32"), ("ik", 64, 2, "fp32")])
 def test_checkpoint_recompute_segments_match_full_history(model, n, B, prec, monkeypatch):
     """Long horizons run in segments (boundary checkpoints + recompute, engine.plan_segments).  With a tiny history budget the
     same run must give the same records and the same gradients as the single-segment run, on all three execution paths."""
@@ -466,7 +507,8 @@ def test_checkpoint_recompute_segments_match_full_history(model, n, B, prec, mon
     assert all(e <= 2e-5 for e in errs.values()), errs
 
 
-@pytest.mark.parametrize("model,n,B,prec", [("qif", 40, 3, "fp32"), ("li_tanh", 50, 20, "fp32"), ("qif", 128, 128, "3xtf32"), ("li_sigmoid", 128, 128, "3xtf32")])
+@pytest.mark.parametrize("model,n,B,prec", [("qif", 40, 3, "fp32"), ("li_tanh", 50, 20, "fp32"), ("qif", 128, 128, "3xtf32"), ("li_sigmoid", 128, 128, "3xtf32"),
+                                            ("qif", 128, 128, "3xf16"), ("li_sigmoid", 128, 128, "3xf16")])
 def test_parameter_sweep_per_trial_values(model, n, B, prec):
     """Parameter sweep: every trial carries its own parameter values ([B,1] and [B,n] tensors).  Each trial must equal the
     reference path run on its own with that trial's parameters; the recurrent weights (and their gradient) are shared."""
