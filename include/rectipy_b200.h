@@ -152,6 +152,12 @@ int rp_rls_run(int T, int n_in, int n_out, float beta_inv, const float* X, const
  * workspaces currently hold (timing is data independent).  Synchronises the stream. */
 int rp_plan_time_contraction(rp_plan* plan, int which, int iters, float* avg_ms, double* flops, void* stream);
 
+/* Debug / profiling aid: per-CTA timeline of the contraction and adjoint kernels.  rp_trace_enable(capacity > 0) arms a device
+ * buffer of `capacity` records (0 disarms and frees it); rp_trace_read synchronises the device, copies up to max_records records
+ * {uint32 tag, uint32 smid, uint64 start_ns, uint64 end_ns} (globaltimer) to host_buf and returns how many there are. */
+int rp_trace_enable(int capacity);
+int rp_trace_read(void* host_buf, int max_records);
+
 /* Standalone GEMM used by the engine, exposed for testing:  C[q*ldc+p] (+)= sum_k A[p*lda+k]*B[q*ldb+k]
  * precision RP_PREC_FP32 -> FFMA kernel, RP_PREC_3XTF32 / RP_PREC_3XF16 -> tcgen05 kernel (needs p,q,k extents it supports). */
 int rp_gemm_tn(int precision, int P, int Q, int K, const float* A, int lda, const float* B, int ldb,

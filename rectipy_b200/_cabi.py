@@ -48,7 +48,7 @@ class rp_bwd_args(C.Structure):
 #: every symbol include/rectipy_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = ["rp_abi_version", "rp_last_error", "rp_num_state_vars", "rp_num_history_planes", "rp_num_records", "rp_plan_create",
            "rp_plan_destroy", "rp_plan_workspace_bytes", "rp_plan_launch_count", "rp_forward", "rp_backward", "rp_plan_status",
-           "rp_rls_run", "rp_gemm_tn", "rp_plan_time_contraction"]
+           "rp_rls_run", "rp_gemm_tn", "rp_plan_time_contraction", "rp_trace_enable", "rp_trace_read"]
 
 _LIB = None
 
@@ -91,6 +91,10 @@ def load():
     lib.rp_backward.restype = C.c_int
     lib.rp_plan_status.argtypes = [C.c_void_p, C.c_void_p]
     lib.rp_plan_status.restype = C.c_int
+    lib.rp_trace_enable.argtypes = [C.c_int]
+    lib.rp_trace_enable.restype = C.c_int
+    lib.rp_trace_read.argtypes = [C.c_void_p, C.c_int]
+    lib.rp_trace_read.restype = C.c_int
     lib.rp_rls_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_void_p]
     lib.rp_rls_run.restype = C.c_int
     lib.rp_plan_time_contraction.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]

@@ -654,7 +654,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         }
         ++p->launches;
         RP_LAUNCH_CHECK();
-        RP_CUDA(cudaMemsetAsync(p->tc.meta + rp::TCM_G_AMAX0, 0, 4 * sizeof(float), st));      // G_AMAX0/1, CHUNK0/1
+        RP_CUDA(cudaMemsetAsync(p->tc.meta + rp::TCM_G_AMAX0, 0, 6 * sizeof(float), st));      // G_AMAX0/1, CHUNK[2][2]
     }
     if (need_dW) RP_CUDA(cudaMemsetAsync(p->dWraw, 0, (size_t)wg_slices * N * p->ldw * sizeof(float), st));
     for (int q = 0; q < RP_NUM_PARAMS; ++q)
@@ -690,7 +690,30 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     else if (!f16) { aa.g_hi = (float*)p->tc.g_hi; aa.g_lo = (float*)p->tc.g_lo; aa.ld_g = p->tc.ldk; aa.ld_t = p->tc.ldt; }
     else { aa.g = p->tc.g32; aa.src = spk ? nullptr : p->tc.src32; }      // binary16: fp32 g + exact maximum, converted by k_adj_convert_f16
     int gslot = 1;                  // binary16: meta slot holding max |g_t| of the step being processed
-    int cpar = 0;                   // binary16: parity of the weight-gradient chunk reference slot
+    int cpar = 0;                   // binary16: parity of the weight-gradient chunk reference slot (within the buffer being filled)
+    // binary16: the weight-gradient contraction of a finished K chunk runs on a side stream, cut into one slice of work items per
+    // reverse step of the NEXT chunk: each slice starts when that step's adjoint product has finished and its CTAs share the SMs with
+    // the HBM-bound adjoint kernels of the step (which are shaped to fit beside a resident GEMM CTA).
+    // Opt-in (RP_WG_OVERLAP=1).  Measured on B200 (profiles/r1d_timeline_overlap.txt): co-residency is achieved once the GEMM
+    // is capped at 144 registers, given the full shared-memory carveout and the adjoint block needs no shared memory, but a
+    // 4-warp adjoint block beside a GEMM CTA streams ~3x slower (the CTA's TMA and MMA operand traffic keeps the SM's L1/shared
+    // pipe ~70 % busy), so the step time does not improve: 35.5 ms vs 34.3 ms per 100-step pass without the overlap.
+    const bool overlap = f16 && need_dW && getenv("RP_WG_OVERLAP");
+    int cb_fill = 0, chunks_done = 0;
+    bool q_active = false; int q_cb = 0, q_K = 0, q_next = 0, q_ref = 0;
+    const int q_total = p->use_tc ? rp::tc_wgrad_items(&p->tc) : 0;
+    const int q_per_step = p->use_tc ? (q_total + p->tc.wgrad_chunk - 1) / p->tc.wgrad_chunk : 0;
+    cudaStream_t ws = overlap ? p->tc.ws : st;
+    auto launch_slices = [&](int count) -> int {      // next `count` work items of the queued chunk, on the side stream
+        count = std::min(count, q_total - q_next);
+        if (count <= 0) return 0;
+        const rp::ScaleRef sc{p->tc.meta + q_ref, 0.f, rp::CV_HCHUNK};
+        if (rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, q_K, 1, ws, sc, q_cb, q_next, count)) return fail("rp_backward: %s", rp::tc_last_error());
+        ++p->launches;
+        q_next += count;
+        if (q_next == q_total) { q_active = false; if (cudaEventRecord(p->tc.ev_done[q_cb], ws) != cudaSuccess) return fail("cudaEventRecord failed"); }
+        return 0;
+    };
     for (int q = 0; q < RP_NUM_PARAMS; ++q) aa.dparams[q] = (q == fold) ? nullptr : a->dparams[q];
     aa.dW_in = a->dW_in; aa.dW_out = a->dW_out;
     aa.per_trial = p->per_trial ? 1 : 0;
@@ -755,7 +778,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         if (aa.do_pre) {
             aa.y_tm1 = a->history + (size_t)(t - 1) * hslot;
             if (p->use_tc && need_dW && !f16) {
-                aa.gT_hi = (float*)p->tc.gT_hi; aa.gT_lo = (float*)p->tc.gT_lo; aa.srcT_hi = (float*)p->tc.srcT_hi; aa.srcT_lo = (float*)p->tc.srcT_lo;
+                aa.gT_hi = (float*)p->tc.gT_hi[0]; aa.gT_lo = (float*)p->tc.gT_lo[0]; aa.srcT_hi = (float*)p->tc.srcT_hi[0]; aa.srcT_lo = (float*)p->tc.srcT_lo[0];
                 aa.t_col0 = pending * B;
             }
             if (f16) aa.g_amax = p->tc.meta + rp::TCM_G_AMAX0 + (gslot ^ 1);
@@ -778,13 +801,32 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         } else {
             if (p->use_tc && aa.do_post) {
                 const rp::ScaleRef sg = f16 ? rp::ScaleRef{p->tc.meta + rp::TCM_G_AMAX0 + gslot, 0.f, rp::CV_HG} : rp::no_scale();
+                // The slice becomes eligible together with this step's adjoint product (both wait for the previous kernel of the
+                // chain) but is enqueued after it: the product takes its 128 SMs first, the slice's CTAs take the idle SMs and
+                // then every SM the product frees -- before the adjoint kernels, which fit beside them, become eligible.
+                const bool slice_now = overlap && q_active;
+                if (slice_now) {
+                    RP_CUDA(cudaEventRecord(p->tc.ev_z, st));
+                    RP_CUDA(cudaStreamWaitEvent(ws, p->tc.ev_z, 0));
+                }
                 if (rp::tc_gemm(&p->tc, rp::TC_DGRAD, p->u, p->ldu, 0, 0, st, sg)) return fail("rp_backward: %s", rp::tc_last_error());
                 ++p->launches;
+                if (slice_now && launch_slices(q_per_step)) return 1;
             }
             if (adj_v4) {
                 rp::AdjArgs va = aa;
                 va.dW_out = nullptr; va.any_param_grad = 0;
-                RP_DISPATCH_MODEL(d.model, (rp::k_adj_step_v4<M_><<<dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st>>>(va)));
+                if (f16 && !overlap) {
+                    RP_DISPATCH_MODEL(d.model, (rp::k_adj_step_v4<M_, false, 8><<<dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st>>>(va)));
+                } else if (f16) {
+                    RP_DISPATCH_MODEL(d.model, {
+                        // same shared-memory carveout as the GEMM CTAs, or the block cannot become resident beside one
+                        static bool carve = false;
+                        if (!carve) { cudaFuncSetAttribute(rp::k_adj_step_v4<M_, false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve = true; }
+                        rp::k_adj_step_v4<M_, false, 4><<<dim3(N / 128, B / 16), dim3(32, 4), 0, st>>>(va);
+                    });
+                }
+                else     { RP_DISPATCH_MODEL(d.model, (rp::k_adj_step_v4<M_, true, 8><<<dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st>>>(va))); }
             } else {
                 RP_DISPATCH_MODEL(d.model, (rp::k_adj_step<M_><<<agrid, ablock, 0, st>>>(aa)));
             }
@@ -792,23 +834,29 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         }
         ++p->launches;
         if (f16 && aa.do_pre) {
+            // the buffer about to be refilled must have been consumed by the side stream (chunk index - 2)
+            if (overlap && pending == 0 && chunks_done >= 2) RP_CUDA(cudaStreamWaitEvent(st, p->tc.ev_done[cb_fill], 0));
             rp::ConvArgs ca;
             memset(&ca, 0, sizeof(ca));
             ca.N = N; ca.B = B; ca.g32 = p->tc.g32;
             ca.src32 = spk ? a->history + (size_t)(t - 1) * hslot + plane : p->tc.src32;
             ca.g_hi = p->tc.g_hi; ca.g_lo = p->tc.g_lo; ca.ld_g = p->tc.ldk;
             if (need_dW) {
-                ca.gT_hi = p->tc.gT_hi; ca.gT_lo = p->tc.gT_lo; ca.srcT_hi = p->tc.srcT_hi; ca.srcT_lo = p->tc.srcT_lo;
+                ca.gT_hi = p->tc.gT_hi[cb_fill]; ca.gT_lo = p->tc.gT_lo[cb_fill]; ca.srcT_hi = p->tc.srcT_hi[cb_fill]; ca.srcT_lo = p->tc.srcT_lo[cb_fill];
                 ca.ld_t = p->tc.ldt; ca.t_col0 = pending * B;
             }
             ca.g_amax = p->tc.meta + rp::TCM_G_AMAX0 + (gslot ^ 1);
             ca.g_amax_clear = p->tc.meta + rp::TCM_G_AMAX0 + gslot;
-            ca.chunk_ref_in = p->tc.meta + rp::TCM_CHUNK0 + cpar;
-            ca.chunk_ref_out = p->tc.meta + rp::TCM_CHUNK0 + (cpar ^ 1);
+            ca.chunk_ref_in = p->tc.meta + rp::TCM_CHUNK0 + 2 * cb_fill + cpar;
+            ca.chunk_ref_out = p->tc.meta + rp::TCM_CHUNK0 + 2 * cb_fill + (cpar ^ 1);
             ca.chunk_first = pending == 0 ? 1 : 0;
             ca.sc_src = rp::tc_scale_srcbound(&p->tc);
             ca.flags = reinterpret_cast<int*>(p->tc.meta + rp::TCM_FLAGS);
-            rp::k_adj_convert_f16<<<dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st>>>(ca);
+            {
+                static bool carve = false;
+                if (!carve) { cudaFuncSetAttribute(rp::k_adj_convert_f16, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve = true; }
+            }
+            rp::k_adj_convert_f16<<<dim3(N / rp::CV_TN, B / rp::CV_TB), 256, 0, st>>>(ca);
             RP_LAUNCH_CHECK();
             ++p->launches;
             gslot ^= 1; cpar ^= 1;
@@ -817,12 +865,27 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             ++pending;
             if (pending == wg_chunk || t == 1) {
                 // dWraw[i][j] += sum_{(t,b) in chunk} g[b][i] src[b][j]
-                const rp::ScaleRef sc = f16 ? rp::ScaleRef{p->tc.meta + rp::TCM_CHUNK0 + cpar, 0.f, rp::CV_HCHUNK} : rp::no_scale();
-                if (rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, pending * B, 1, st, sc)) return fail("rp_backward: %s", rp::tc_last_error());
-                ++p->launches;
+                const int ref_slot = rp::TCM_CHUNK0 + 2 * cb_fill + cpar;
+                if (!overlap) {
+                    const rp::ScaleRef sc = f16 ? rp::ScaleRef{p->tc.meta + ref_slot, 0.f, rp::CV_HCHUNK} : rp::no_scale();
+                    if (rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, pending * B, 1, st, sc, f16 ? cb_fill : 0)) return fail("rp_backward: %s", rp::tc_last_error());
+                    ++p->launches;
+                } else {
+                    if (q_active && launch_slices(q_total)) return 1;              // whatever is left of the previous chunk
+                    RP_CUDA(cudaEventRecord(p->tc.ev_ops[cb_fill], st));
+                    RP_CUDA(cudaStreamWaitEvent(ws, p->tc.ev_ops[cb_fill], 0));
+                    q_active = true; q_cb = cb_fill; q_K = pending * B; q_next = 0; q_ref = ref_slot;
+                    if (t == 1 && launch_slices(q_total)) return 1;                // last chunk: only the final post step is left to overlap with
+                    cb_fill ^= 1; cpar = 0; ++chunks_done;
+                }
                 pending = 0;
             }
         }
+    }
+    if (overlap) {
+        if (q_active && launch_slices(q_total)) return 1;
+        RP_CUDA(cudaEventRecord(p->tc.ev_join, ws));
+        RP_CUDA(cudaStreamWaitEvent(st, p->tc.ev_join, 0));
     }
     if ((fused_adj || adj_v4) && a->dW_out && a->g_out_rec && a->T > 0) {
         for (int t0 = 0; t0 < a->T; t0 += 32768) {            // grid.y limit
@@ -898,6 +961,35 @@ int rp_gemm_tn(int precision, int P, int Q, int K, const float* A, int lda, cons
         return 0;
     }
     return fail("rp_gemm_tn: unknown precision %d", precision);
+}
+
+/* Debug / profiling: arm (capacity > 0) or disarm (0) the CTA timeline of the traced kernels; rp_trace_read copies the records
+ * (16 bytes: tag, smid, start ns, end ns as {u32, u32, u64, u64} = 24 bytes each) collected so far and returns their number. */
+static rp::TraceRec* g_trace_dev = nullptr;
+static unsigned g_trace_capacity = 0;
+int rp_trace_enable(int capacity) {
+    cudaDeviceSynchronize();
+    rp::TraceRec* null_buf = nullptr;
+    unsigned zero = 0;
+    if (g_trace_dev) { cudaFree(g_trace_dev); g_trace_dev = nullptr; g_trace_capacity = 0; }
+    if (capacity > 0) {
+        RP_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_trace_dev), (size_t)capacity * sizeof(rp::TraceRec)));
+        RP_CUDA(cudaMemset(g_trace_dev, 0, (size_t)capacity * sizeof(rp::TraceRec)));
+        g_trace_capacity = (unsigned)capacity;
+    }
+    RP_CUDA(cudaMemcpyToSymbol(rp::g_trace_n, &zero, sizeof(unsigned)));
+    RP_CUDA(cudaMemcpyToSymbol(rp::g_trace_cap, &g_trace_capacity, sizeof(unsigned)));
+    RP_CUDA(cudaMemcpyToSymbol(rp::g_trace_buf, g_trace_dev ? &g_trace_dev : &null_buf, sizeof(rp::TraceRec*)));
+    return 0;
+}
+int rp_trace_read(void* host_buf, int max_records) {
+    if (!g_trace_dev || !host_buf || max_records <= 0) return 0;
+    cudaDeviceSynchronize();
+    unsigned n = 0;
+    if (cudaMemcpyFromSymbol(&n, rp::g_trace_n, sizeof(unsigned)) != cudaSuccess) return -1;
+    n = std::min(n, std::min(g_trace_capacity, (unsigned)max_records));
+    if (cudaMemcpy(host_buf, g_trace_dev, (size_t)n * sizeof(rp::TraceRec), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int)n;
 }
 
 int rp_plan_status(rp_plan* p, void* stream) {

@@ -27,6 +27,8 @@
 #include <cudaTypedefs.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <type_traits>
 #include "rp_kernels.cuh"
 
 namespace rp {
@@ -148,6 +150,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
 // The tensor core adds into its fp32 accumulator with truncation (measured on B200: all-positive operands give a
 // systematic -2.3e-5 relative bias at K=2048, growing linearly with K).  To stay at fp32 accuracy the K loop is cut into
 // chunks of TC_KC K-blocks; each chunk accumulates into one of two TMEM buffers from zero and the epilogue warps add the
@@ -177,6 +188,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // loads of a batch are issued before any store, and the weight-gradient operands are written as 16-byte vectors over trials.
 struct EpiStore {                       // C[q*ldc + p] (+)= acc ; split-K slices (blockIdx.z) go to C + z*split_stride
     static constexpr bool kStage = false;
+    static constexpr unsigned kTag = TR_GEMM_STORE;
     float* C; int ldc; int accumulate; size_t split_stride;
     ScaleRef sa, sb;                    // binary16 operands: scales of the A and B operand (undone here)
     __device__ __forceinline__ float2 unscale(int /*p0*/) const { return make_float2(exp2i(-scale_expo(sa)), exp2i(-scale_expo(sb))); }
@@ -191,6 +203,7 @@ __device__ __forceinline__ float f4get(const float4& v, int r) { return r == 0 ?
 template <int MODEL, bool GEN = (MODEL == RP_IK)>
 struct EpiFwd {
     static constexpr bool kStage = true;
+    static constexpr unsigned kTag = TR_GEMM_FWD;
     FwdStepArgs a;
     float* out_rec_j; int k; int win_first, win_close; float inv_len;
     ScaleRef sA, sA_ro, sB;             // binary16 operands: scales of kW, of the appended W_out rows and of src_t
@@ -212,11 +225,15 @@ struct EpiFwd {
             for (int rr = 0; rr < 4; ++rr) row[rr] = fwd_row<MODEL>(a, i0 + rr);
             const float so = F16 ? exp2i(scale_expo(a.sc_out)) : 1.f;
             float smax = 0.f;
-            for (int c = 0; c < NCOL; c += 2) {
-                float4 u4[2], v4[2], s4[2], x4[2], xd4[2];
-                float xin0[2], xin1[2];
+            // NB trials per batch: all their loads are issued before the first store (8 warps per SM have to cover the HBM
+            // latency alone here: 2 trials per batch left the epilogue at ~30 us, i.e. 30 % of the fused kernel)
+            constexpr int NB = 4;
+            static_assert(NCOL % NB == 0, "trial batch must divide the per-warp column block");
+            for (int c = 0; c < NCOL; c += NB) {
+                float4 u4[NB], v4[NB], s4[NB], x4[NB], xd4[NB];
+                float xin0[NB], xin1[NB];
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
+                for (int cc = 0; cc < NB; ++cc) {
                     const int b = q0 + cbase + c + cc;
                     const size_t idx = (size_t)b * a.N + i0;
                     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -229,7 +246,7 @@ struct EpiFwd {
                     xin1[cc] = (a.in_mode == RP_IN_PROJ && a.m > 1) ? __ldg(a.x_t + (size_t)b * a.m + 1) : 0.f;
                 }
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
+                for (int cc = 0; cc < NB; ++cc) {
                     const int b = q0 + cbase + c + cc;
                     const size_t idx = (size_t)b * a.N + i0;
                     float v1[4], s1[4], x1[4], hi[4], lo[4], sr[4];
@@ -293,6 +310,7 @@ struct EpiFwd {
 template <int MODEL, bool PG>
 struct EpiAdj {
     static constexpr bool kStage = true;
+    static constexpr unsigned kTag = TR_GEMM_ADJ;
     AdjArgs a;
     __device__ __forceinline__ float2 unscale(int /*p0*/) const { return make_float2(1.f, 1.f); }
 
@@ -396,11 +414,20 @@ struct EpiAdj {
     }
 };
 
-template <int BQ, class Epi, bool F16>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_gemm_split3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-              int num_k_blocks, const __grid_constant__ Epi epi) {
+// A launch may cover only the work items [lin0, lin0 + gridDim.x) of the full (gx, gy, gz) grid, x fastest (gx == 0: the
+// launch grid is the full grid).  rp_backward uses this to spread one weight-gradient contraction over several reverse steps.
+struct TcSlice { int lin0, gx, gy; };
+
+// LEAN: register-lean variant (16-column TMEM drains, 16-deep read-modify-write batches) compiled to at most TC_LEAN_REGS
+// registers.  An SM's register file is split over its four sub-partitions (16 K registers each) and the 10 warps of this
+// kernel land 3/3/2/2 on them: at 168 registers the two full sub-partitions have 256 registers left and no other block can
+// become resident; at 144 every sub-partition keeps >= 2560 free = one 80-register warp, so one 4-warp block of the HBM-bound
+// adjoint kernels runs beside each weight-gradient CTA (rp_backward overlaps them on purpose).
+constexpr int TC_LEAN_REGS = 144;
+
+template <int BQ, class Epi, bool F16, bool LEAN>
+__device__ __forceinline__ void gemm_split3_body(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi, const CUtensorMap& tmB_lo,
+                                                 int num_k_blocks, const Epi& epi, const TcSlice slice) {
     using Cfg = TcCfg<BQ>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int CPT = Cfg::COLS_PER_THREAD;
@@ -415,11 +442,18 @@ k_gemm_split3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p0 = blockIdx.x * TC_BP, q0 = blockIdx.y * BQ;
+    int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+    if (slice.gx > 0) {
+        const int lin = slice.lin0 + (int)blockIdx.x;
+        bx = lin % slice.gx; by = (lin / slice.gx) % slice.gy; bz = lin / (slice.gx * slice.gy);
+    }
+    const int p0 = bx * TC_BP, q0 = by * BQ;
     const int num_chunks = (num_k_blocks + TC_KC - 1) / TC_KC;
-    const int kb0 = blockIdx.z * num_k_blocks;              // split-K: this CTA contracts K blocks [kb0, kb0 + num_k_blocks)
+    const int kb0 = bz * num_k_blocks;                      // split-K: this CTA contracts K blocks [kb0, kb0 + num_k_blocks)
 
+    TraceRec* trace = nullptr;
     if (warp == 0 && lane == 0) {
+        trace = trace_begin(slice.gx > 0 ? (unsigned)TR_GEMM_WGRAD : Epi::kTag);
         tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], TC_EPI_WARPS); }
@@ -498,13 +532,24 @@ k_gemm_split3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
             mbar_wait(&tmem_full_bar[buf], (chunk >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * BQ + half * CPT);
+            if constexpr (LEAN) {
 #pragma unroll
-            for (int c = 0; c < CPT / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(taddr + (uint32_t)(c * 32), r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                for (int c = 0; c < CPT / 16; ++c) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + (uint32_t)(c * 16), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+                    for (int j = 0; j < 16; ++j) acc[c * 16 + j] += __uint_as_float(r[j]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CPT / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + (uint32_t)(c * 32), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -513,16 +558,17 @@ k_gemm_split3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
         float2 usc = make_float2(1.f, 1.f);
         if constexpr (F16) usc = epi.unscale(p0);
         if constexpr (!Epi::kStage) {
-            float* cbase = epi.C + blockIdx.z * epi.split_stride + (size_t)(q0 + half * CPT) * epi.ldc + p;
+            float* cbase = epi.C + bz * epi.split_stride + (size_t)(q0 + half * CPT) * epi.ldc + p;
             if (epi.accumulate) {
-                // read-modify-write of the accumulation slice: 32 independent loads in flight before the first store
+                // read-modify-write of the accumulation slice: RB independent loads in flight before the first store
+                constexpr int RB = LEAN ? 8 : 32;
 #pragma unroll
-                for (int j0 = 0; j0 < CPT; j0 += 32) {
-                    float old[32];
+                for (int j0 = 0; j0 < CPT; j0 += RB) {
+                    float old[RB];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) old[j] = __ldcg(cbase + (size_t)(j0 + j) * epi.ldc);
+                    for (int j = 0; j < RB; ++j) old[j] = __ldcg(cbase + (size_t)(j0 + j) * epi.ldc);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < RB; ++j) {
                         float v = acc[j0 + j];
                         if constexpr (F16) v = v * usc.x * usc.y;
                         cbase[(size_t)(j0 + j) * epi.ldc] = v + old[j];
@@ -548,9 +594,26 @@ k_gemm_split3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    trace_end(trace);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
     }
+}
+
+template <int BQ, class Epi, bool F16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_split3(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+              int num_k_blocks, const __grid_constant__ Epi epi, const TcSlice slice) {
+    gemm_split3_body<BQ, Epi, F16, false>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, num_k_blocks, epi, slice);
+}
+// the co-residency variant (see TC_LEAN_REGS)
+template <int BQ, class Epi, bool F16>
+__global__ void __maxnreg__(TC_LEAN_REGS)
+k_gemm_split3_lean(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                   int num_k_blocks, const __grid_constant__ Epi epi, const TcSlice slice) {
+    gemm_split3_body<BQ, Epi, F16, true>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, num_k_blocks, epi, slice);
 }
 
 // split a dense fp32 matrix [rows][ld] into hi/lo copies [rows_out][ld_out] (zero padded): tf32-exact fp32 words, or
@@ -605,14 +668,19 @@ inline int tc_make_map(CUtensorMap* map, const void* base, bool f16, int rows, i
 inline bool tc_supported(int N, int B) { return N % 128 == 0 && B % 128 == 0 && N >= 128 && B >= 128; }
 
 // device-resident scalars of the binary16 path (one small float array per plan)
-enum { TCM_AMAX_W = 0, TCM_AMAX_WOUT, TCM_SRC_BOUND, TCM_G_AMAX0, TCM_G_AMAX1, TCM_CHUNK0, TCM_CHUNK1, TCM_FLAGS, TCM_COUNT = 16 };
+// TCM_CHUNK0 + 2*buffer + parity: reference maximum of the weight-gradient chunk being written into that operand buffer
+enum { TCM_AMAX_W = 0, TCM_AMAX_WOUT, TCM_SRC_BOUND, TCM_G_AMAX0, TCM_G_AMAX1, TCM_CHUNK0, TCM_FLAGS = TCM_CHUNK0 + 4, TCM_COUNT = 16 };
 
 struct TcWorkspace {
     int N = 0, B = 0, ldk = 0, ldt = 0, wgrad_chunk = 0;
     bool f16 = false;
     void *W_hi = nullptr, *W_lo = nullptr, *WT_hi = nullptr, *WT_lo = nullptr;       // [N][ldk]
     void *src_hi = nullptr, *src_lo = nullptr, *g_hi = nullptr, *g_lo = nullptr;     // [B][ldk]
-    void *gT_hi = nullptr, *gT_lo = nullptr, *srcT_hi = nullptr, *srcT_lo = nullptr; // [N][ldt]
+    // weight-gradient operands, trial-major [N][ldt]; two buffers so that the contraction of one K chunk (side stream) overlaps the
+    // reverse steps that fill the other (binary16 path; the tf32 path uses buffer 0 only)
+    void *gT_hi[2] = {nullptr, nullptr}, *gT_lo[2] = {nullptr, nullptr}, *srcT_hi[2] = {nullptr, nullptr}, *srcT_lo[2] = {nullptr, nullptr};
+    cudaStream_t ws = nullptr;                                    // side stream of the overlapped weight-gradient slices
+    cudaEvent_t ev_z = nullptr, ev_ops[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_join = nullptr;
     float* g32 = nullptr;        // binary16 path: g_{t-1} in fp32 [B][N] before the exact-maximum conversion
     float* src32 = nullptr;      // binary16 path, rate models: act(v_{t-1}) [B][N]
     float* meta = nullptr;       // [TCM_COUNT]
@@ -620,7 +688,7 @@ struct TcWorkspace {
     int amax_cap = 0;
     const void* fwd_history = nullptr; int fwd_T = -1;      // which checkpoints amax_src describes
     int bq_fwd = 0, bq_wg = 0;
-    CUtensorMap m_W[2], m_WT[2], m_src[2], m_g[2], m_gT[2], m_srcT[2];
+    CUtensorMap m_W[2], m_WT[2], m_src[2], m_g[2], m_gT[2][2], m_srcT[2][2];     // m_gT[buffer][hi/lo]
     int esize() const { return f16 ? 2 : 4; }
 };
 
@@ -637,15 +705,25 @@ inline int tc_set_attrs() {
     if (done) return 0;
     cudaError_t e = cudaFuncSetAttribute(k_gemm_split3<256, Epi, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_split3<128, Epi, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
+    if constexpr (std::is_same<Epi, EpiStore>::value && F16) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_split3_lean<256, Epi, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_split3_lean<128, Epi, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
+        // the full 228 KB carveout (the default would be the smallest one that holds the CTA, leaving no room for a co-resident block)
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_split3_lean<256, Epi, F16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_split3_lean<128, Epi, F16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     if (e != cudaSuccess) RP_TC_FAIL("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
     done = true;
     return 0;
 }
 
 inline void tc_workspace_destroy(TcWorkspace* w) {
-    void* bufs[] = {w->W_hi, w->W_lo, w->WT_hi, w->WT_lo, w->src_hi, w->src_lo, w->g_hi, w->g_lo, w->gT_hi, w->gT_lo, w->srcT_hi, w->srcT_lo,
-                    w->g32, w->src32, w->meta, w->amax_src};
+    void* bufs[] = {w->W_hi, w->W_lo, w->WT_hi, w->WT_lo, w->src_hi, w->src_lo, w->g_hi, w->g_lo, w->gT_hi[0], w->gT_lo[0], w->srcT_hi[0], w->srcT_lo[0],
+                    w->gT_hi[1], w->gT_lo[1], w->srcT_hi[1], w->srcT_lo[1], w->g32, w->src32, w->meta, w->amax_src};
     for (void* b : bufs) if (b) cudaFree(b);
+    cudaEvent_t evs[] = {w->ev_z, w->ev_ops[0], w->ev_ops[1], w->ev_done[0], w->ev_done[1], w->ev_join};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    if (w->ws) cudaStreamDestroy(w->ws);
     *w = TcWorkspace();
 }
 
@@ -657,6 +735,7 @@ inline int tc_workspace_create(TcWorkspace* w, int N, int B, bool f16, bool rate
     w->wgrad_chunk = chunk;
     w->ldt = chunk * B;
     w->bq_fwd = (B % 256 == 0) ? 256 : 128;
+    if (getenv("RP_TC_BQ_FWD") && atoi(getenv("RP_TC_BQ_FWD")) == 128) w->bq_fwd = 128;      // tuning experiments
     w->bq_wg = (N % 256 == 0) ? 256 : 128;
     const size_t nn = (size_t)N * w->ldk * es, bn = (size_t)B * w->ldk * es;
     const size_t nw = (size_t)(N + TC_BP) * w->ldk * es;        // + one row tile for the fused readout rows (W_out)
@@ -687,33 +766,60 @@ inline int tc_workspace_ensure_amax(TcWorkspace* w, int n, size_t* bytes) {
 
 // the transposed (trial-major) operand buffers of the weight gradient are only needed by rp_backward
 inline int tc_workspace_ensure_wgrad(TcWorkspace* w, size_t* bytes) {
-    if (w->gT_hi) return 0;
+    if (w->gT_hi[0]) return 0;
     const size_t nt = (size_t)w->N * w->ldt * w->esize();
     const bool f16 = w->f16;
-    if (tc_alloc(&w->gT_hi, nt, bytes) || tc_alloc(&w->gT_lo, nt, bytes) || tc_alloc(&w->srcT_hi, nt, bytes) || tc_alloc(&w->srcT_lo, nt, bytes)) return 1;
-    if (tc_make_map(&w->m_srcT[0], w->srcT_hi, f16, w->N, w->ldt, w->ldt, TC_BP) || tc_make_map(&w->m_srcT[1], w->srcT_lo, f16, w->N, w->ldt, w->ldt, TC_BP)) return 1;
-    if (tc_make_map(&w->m_gT[0], w->gT_hi, f16, w->N, w->ldt, w->ldt, w->bq_wg) || tc_make_map(&w->m_gT[1], w->gT_lo, f16, w->N, w->ldt, w->ldt, w->bq_wg)) return 1;
+    const int nbuf = f16 ? 2 : 1;
+    for (int c = 0; c < nbuf; ++c) {
+        if (tc_alloc(&w->gT_hi[c], nt, bytes) || tc_alloc(&w->gT_lo[c], nt, bytes) || tc_alloc(&w->srcT_hi[c], nt, bytes) || tc_alloc(&w->srcT_lo[c], nt, bytes)) return 1;
+        if (tc_make_map(&w->m_srcT[c][0], w->srcT_hi[c], f16, w->N, w->ldt, w->ldt, TC_BP) || tc_make_map(&w->m_srcT[c][1], w->srcT_lo[c], f16, w->N, w->ldt, w->ldt, TC_BP)) return 1;
+        if (tc_make_map(&w->m_gT[c][0], w->gT_hi[c], f16, w->N, w->ldt, w->ldt, w->bq_wg) || tc_make_map(&w->m_gT[c][1], w->gT_lo[c], f16, w->N, w->ldt, w->ldt, w->bq_wg)) return 1;
+    }
+    if (f16) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);           // lo = least priority (the default), hi = greatest
+        const int prio = getenv("RP_WS_HIGH_PRIORITY") ? hi : lo;
+        if (cudaStreamCreateWithPriority(&w->ws, cudaStreamNonBlocking, prio) != cudaSuccess) RP_TC_FAIL("cudaStreamCreateWithPriority failed");
+        cudaEvent_t* evs[] = {&w->ev_z, &w->ev_ops[0], &w->ev_ops[1], &w->ev_done[0], &w->ev_done[1], &w->ev_join};
+        for (cudaEvent_t* e : evs) if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) RP_TC_FAIL("cudaEventCreate failed");
+    }
     return 0;
 }
 
+// item0/items: launch only the work items [item0, item0 + items) of the full grid (items <= 0: all of it)
 template <class Epi, bool F16>
-inline int tc_launch_epi(int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, const Epi& epi, cudaStream_t st, int k_splits = 1) {
+inline int tc_launch_epi(int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, const Epi& epi, cudaStream_t st, int k_splits = 1,
+                         int item0 = 0, int items = 0) {
     constexpr int BK = TcElt<F16>::BK;
     if (P % TC_BP || Q % bq || K % (BK * k_splits)) RP_TC_FAIL("tc_launch: extents P=%d Q=%d K=%d do not match tile %dx%dx%d (x%d splits)", P, Q, K, TC_BP, bq, BK, k_splits);
     if (tc_set_attrs<Epi, F16>()) return 1;
     dim3 grid(P / TC_BP, Q / bq, k_splits);
+    TcSlice slice{0, 0, 0};
+    if (items > 0) {
+        const int total = (int)(grid.x * grid.y * grid.z);
+        if (item0 < 0 || item0 + items > total) RP_TC_FAIL("tc_launch: work items [%d, %d) outside the grid of %d", item0, item0 + items, total);
+        slice = TcSlice{item0, (int)grid.x, (int)grid.y};
+        grid = dim3(items, 1, 1);
+    }
     const int kb = K / BK / k_splits;
-    if (bq == 256) k_gemm_split3<256, Epi, F16><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi);
-    else           k_gemm_split3<128, Epi, F16><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi);
+    bool lean = false;
+    if constexpr (std::is_same<Epi, EpiStore>::value && F16) lean = items > 0 && !getenv("RP_NO_LEAN_SLICES");
+    if (lean) {
+        if constexpr (std::is_same<Epi, EpiStore>::value && F16) {
+            if (bq == 256) k_gemm_split3_lean<256, Epi, F16><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
+            else           k_gemm_split3_lean<128, Epi, F16><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
+        }
+    } else if (bq == 256) k_gemm_split3<256, Epi, F16><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
+    else                  k_gemm_split3<128, Epi, F16><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) RP_TC_FAIL("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
 inline int tc_launch(bool f16, int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, float* C, int ldc, int accumulate, cudaStream_t st,
-                     int k_splits = 1, size_t split_stride = 0, ScaleRef sa = no_scale(), ScaleRef sb = no_scale()) {
+                     int k_splits = 1, size_t split_stride = 0, ScaleRef sa = no_scale(), ScaleRef sb = no_scale(), int item0 = 0, int items = 0) {
     EpiStore e{C, ldc, accumulate, split_stride, sa, sb};
-    if (f16) return tc_launch_epi<EpiStore, true>(bq, P, Q, K, A, Bm, e, st, k_splits);
-    return tc_launch_epi<EpiStore, false>(bq, P, Q, K, A, Bm, e, st, k_splits);
+    if (f16) return tc_launch_epi<EpiStore, true>(bq, P, Q, K, A, Bm, e, st, k_splits, item0, items);
+    return tc_launch_epi<EpiStore, false>(bq, P, Q, K, A, Bm, e, st, k_splits, item0, items);
 }
 // fused launches: forward step (rows = N, or N+128 when the readout rows are appended) and adjoint step
 template <int MODEL, bool GEN>
@@ -736,14 +842,17 @@ inline ScaleRef tc_scale_srcbound(const TcWorkspace* w) { return w->f16 ? ScaleR
 // mode TC_DGRAD: C=Z[b][j]     A = (kW)^T          B = g               K = N
 // mode TC_WGRAD: C=dW[i][j] += A = src^T [j][(t,b)] B = g^T [i][(t,b)] K = k_extent (columns filled in the chunk)
 // sb: scale of the B operand (binary16 path): src_t / g_t / the weight-gradient chunk; the A scale follows from the mode
-inline int tc_gemm(TcWorkspace* w, int mode, float* C, int ldc, int k_extent, int accumulate, cudaStream_t st, ScaleRef sb = no_scale()) {
+// WGRAD only: cb = operand buffer, item0/items = slice of the work items (items <= 0: all)
+inline int tc_wgrad_items(const TcWorkspace* w) { return (w->N / TC_BP) * (w->N / w->bq_wg) * TC_WGRAD_SPLITS; }
+inline int tc_gemm(TcWorkspace* w, int mode, float* C, int ldc, int k_extent, int accumulate, cudaStream_t st, ScaleRef sb = no_scale(),
+                   int cb = 0, int item0 = 0, int items = 0) {
     switch (mode) {
         case TC_FWD:   return tc_launch(w->f16, w->bq_fwd, w->N, w->B, w->N, w->m_W, w->m_src, C, ldc, accumulate, st, 1, 0, tc_scale_W(w), sb);
         case TC_DGRAD: return tc_launch(w->f16, w->bq_fwd, w->N, w->B, w->N, w->m_WT, w->m_g, C, ldc, accumulate, st, 1, 0, tc_scale_W(w), sb);
         // 2-way split-K into two accumulation slices: N=4096 gives 512 tiles = 3.46 waves of 148 SMs (86 % filled);
         // 1024 work items = 6.92 waves (99 %).  The slices are summed by k_finish_wgrad.
-        case TC_WGRAD: return tc_launch(w->f16, w->bq_wg, w->N, w->N, k_extent, w->m_srcT, w->m_gT, C, ldc, accumulate, st, TC_WGRAD_SPLITS, (size_t)w->N * ldc,
-                                        tc_scale_srcbound(w), sb);
+        case TC_WGRAD: return tc_launch(w->f16, w->bq_wg, w->N, w->N, k_extent, w->m_srcT[cb], w->m_gT[cb], C, ldc, accumulate, st, TC_WGRAD_SPLITS, (size_t)w->N * ldc,
+                                        tc_scale_srcbound(w), sb, item0, items);
     }
     RP_TC_FAIL("tc_gemm: unknown mode %d", mode);
 }

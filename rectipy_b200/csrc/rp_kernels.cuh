@@ -16,6 +16,26 @@
 
 namespace rp {
 
+// ---- optional CTA timeline (debug / profiles): one record per traced CTA when rp_trace_enable() armed a buffer ---------------
+struct TraceRec { unsigned tag, smid; unsigned long long t0, t1; };
+__device__ TraceRec* g_trace_buf = nullptr;
+__device__ unsigned g_trace_cap = 0;
+__device__ unsigned g_trace_n = 0;
+enum { TR_GEMM_STORE = 1, TR_GEMM_WGRAD = 2, TR_GEMM_FWD = 3, TR_GEMM_ADJ = 4, TR_ADJ_STEP = 5, TR_ADJ_CONVERT = 6 };
+__device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// call from ONE thread of the CTA; returns nullptr when tracing is off
+__device__ __forceinline__ TraceRec* trace_begin(unsigned tag) {
+    TraceRec* buf = g_trace_buf;
+    if (buf == nullptr) return nullptr;
+    const unsigned slot = atomicAdd(&g_trace_n, 1u);
+    if (slot >= g_trace_cap) return nullptr;
+    unsigned sm;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    buf[slot].tag = tag; buf[slot].smid = sm; buf[slot].t0 = trace_now(); buf[slot].t1 = 0;
+    return buf + slot;
+}
+__device__ __forceinline__ void trace_end(TraceRec* r) { if (r) r->t1 = trace_now(); }
+
 // record windows of Network.run (network.py:590-597), usable on host and device
 struct PWindow { int j, first, close, len; };
 __host__ __device__ inline PWindow pwindow_of(int t, int T, int S, int cutoff) {
@@ -831,16 +851,25 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
 constexpr int ADJ4_TB = 32;      // trials per block
 __device__ __forceinline__ float f4at(const float4& v, int r) { return r == 0 ? v.x : (r == 1 ? v.y : (r == 2 ? v.z : v.w)); }
 
-template <int MODEL>
-__global__ void __launch_bounds__(256) k_adj_step_v4(AdjArgs a) {
+// TR: stage the trial-major weight-gradient operands (tf32 path); the binary16 path converts in k_adj_convert_f16 and needs no smem.
+// NTY: warps per block (block = 32 x NTY threads, tile = 128 neurons x 4*NTY trials).  The binary16 path runs 4-warp blocks of 80
+// registers so that one block fits beside a resident weight-gradient GEMM CTA (168 regs x 320 threads) on the same SM.
+template <int MODEL, bool TR, int NTY>
+__global__ void __launch_bounds__(32 * NTY, NTY == 4 ? 6 : 1) k_adj_step_v4(AdjArgs a) {      // 4-warp variant: <= 80 registers
     constexpr int NSV = ModelTraits<MODEL>::NSV;
-    __shared__ float tg[ADJ4_TB][128 + 4];
-    __shared__ float ts[ADJ4_TB][128 + 4];
+    constexpr int TB = 4 * NTY;
+    static_assert(!TR || TB == ADJ4_TB, "the transposing variant stages 32 trials");
+    // (no shared memory at all when !TR: a resident GEMM CTA leaves under 2 KB of the SM's carveout unused)
+    __shared__ float tg_[TR ? ADJ4_TB * (128 + 4) : 0 + !TR];
+    __shared__ float ts_[TR ? ADJ4_TB * (128 + 4) : 0 + !TR];
+    float (*tg)[128 + 4] = reinterpret_cast<float (*)[128 + 4]>(tg_);
+    float (*ts)[128 + 4] = reinterpret_cast<float (*)[128 + 4]>(ts_);
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int i0 = blockIdx.x * 128 + 4 * tx;
-    const int bblk = blockIdx.y * ADJ4_TB;
+    const int bblk = blockIdx.y * TB;
     const size_t plane = (size_t)a.B * a.N;
-    const bool transposed = a.do_pre && a.gT_hi != nullptr;
+    const bool transposed = TR && a.do_pre && a.gT_hi != nullptr;
+    TraceRec* trace = (tx == 0 && ty == 0) ? trace_begin(TR_ADJ_STEP) : nullptr;
     const NoAcc nacc;
     AdjRowParams rp_[4];
 #pragma unroll
@@ -848,11 +877,11 @@ __global__ void __launch_bounds__(256) k_adj_step_v4(AdjArgs a) {
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     float gmax = 0.f;
 
-    for (int l0 = 0; l0 < ADJ4_TB / 8; l0 += 2) {
+    for (int l0 = 0; l0 < 4; l0 += 2) {
         float4 av[2], as[2], ax[2], v[2], s[2], x[2], vm[2], sm[2], Z[2], ur[2];
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
-            const int b = bblk + (l0 + l) * 8 + ty;
+            const int b = bblk + (l0 + l) * NTY + ty;
             const size_t idx = (size_t)b * a.N + i0;
             av[l] = *reinterpret_cast<const float4*>(a.adj + idx);
             as[l] = NSV > 1 ? *reinterpret_cast<const float4*>(a.adj + plane + idx) : zero;
@@ -867,12 +896,13 @@ __global__ void __launch_bounds__(256) k_adj_step_v4(AdjArgs a) {
             }
             if (a.do_pre) {
                 vm[l] = __ldg(reinterpret_cast<const float4*>(a.y_tm1 + idx));
-                if (NSV > 1) sm[l] = __ldg(reinterpret_cast<const float4*>(a.y_tm1 + plane + idx));
+                // s_{t-1} is only the weight-gradient source value: on the binary16 path (!TR) the convert kernel reads it itself
+                if (NSV > 1 && (TR || a.src)) sm[l] = __ldg(reinterpret_cast<const float4*>(a.y_tm1 + plane + idx));
             }
         }
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
-            const int bl = (l0 + l) * 8 + ty;
+            const int bl = (l0 + l) * NTY + ty;
             const int b = bblk + bl;
             const size_t idx = (size_t)b * a.N + i0;
             float nav[4], nas[4], nax[4], g[4], sv[4], gh[4], gl[4];
@@ -899,9 +929,11 @@ __global__ void __launch_bounds__(256) k_adj_step_v4(AdjArgs a) {
                     *reinterpret_cast<float4*>(a.g_hi + (size_t)b * a.ld_g + i0) = make_float4(gh[0], gh[1], gh[2], gh[3]);
                     *reinterpret_cast<float4*>(a.g_lo + (size_t)b * a.ld_g + i0) = make_float4(gl[0], gl[1], gl[2], gl[3]);
                 }
-                if (transposed) {
-                    *reinterpret_cast<float4*>(&tg[bl][4 * tx]) = make_float4(g[0], g[1], g[2], g[3]);
-                    *reinterpret_cast<float4*>(&ts[bl][4 * tx]) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+                if constexpr (TR) {
+                    if (transposed) {
+                        *reinterpret_cast<float4*>(&tg[bl][4 * tx]) = make_float4(g[0], g[1], g[2], g[3]);
+                        *reinterpret_cast<float4*>(&ts[bl][4 * tx]) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+                    }
                 }
             }
         }
@@ -910,7 +942,8 @@ __global__ void __launch_bounds__(256) k_adj_step_v4(AdjArgs a) {
         gmax = warp_max(gmax);
         if (tx == 0 && gmax > 0.f) atomic_max_nonneg(a.g_amax, gmax);
     }
-    if (transposed) {
+    trace_end(trace);
+    if constexpr (TR) if (transposed) {
         __syncthreads();
         // lane tx -> trial bblk + tx; warp ty walks neurons ty, ty+8, ...: every store is 32 consecutive trials of one neuron
         for (int r = ty; r < 128; r += 8) {
@@ -951,12 +984,15 @@ struct ConvArgs {
     int* flags;                  // bit 0: binary16 range exceeded
 };
 
+constexpr int CV_TN = 64, CV_TB = 32;     // block tile: 64 neurons x 32 trials, 17 KB of shared memory (fits beside a GEMM CTA)
 __global__ void __launch_bounds__(256) k_adj_convert_f16(ConvArgs a) {
-    __shared__ float tg[ADJ4_TB][128 + 4];
-    __shared__ float ts[ADJ4_TB][128 + 4];
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int i0 = blockIdx.x * 128 + 4 * tx;
-    const int bblk = blockIdx.y * ADJ4_TB;
+    __shared__ float tg[CV_TB][CV_TN + 4];
+    __shared__ float ts[CV_TB][CV_TN + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;        // tx -> 4 neurons, ty -> trials ty, ty + 16
+    const int i0 = blockIdx.x * CV_TN + 4 * tx;
+    const int bblk = blockIdx.y * CV_TB;
+    const bool first = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+    TraceRec* trace = threadIdx.x == 0 ? trace_begin(TR_ADJ_CONVERT) : nullptr;
     const float gmax = *a.g_amax;
     const int eg = expo_for(gmax, CV_HG);
     const float sg = exp2i(eg);
@@ -972,17 +1008,15 @@ __global__ void __launch_bounds__(256) k_adj_convert_f16(ConvArgs a) {
         const int es = scale_expo(a.sc_src);
         sgT = exp2i(eu);
         ssT = exp2i(es + min(comp, 3));
-        if (blockIdx.x == 0 && blockIdx.y == 0 && tx == 0 && ty == 0) {
+        if (first) {
             *a.chunk_ref_out = ref;
-            *a.g_amax_clear = 0.f;
             if (comp > 3) atomicOr(a.flags, 1);
         }
-    } else if (blockIdx.x == 0 && blockIdx.y == 0 && tx == 0 && ty == 0) {
-        *a.g_amax_clear = 0.f;
     }
+    if (first) *a.g_amax_clear = 0.f;
 #pragma unroll
-    for (int l = 0; l < ADJ4_TB / 8; ++l) {
-        const int bl = l * 8 + ty;
+    for (int l = 0; l < 2; ++l) {
+        const int bl = l * 16 + ty;
         const int b = bblk + bl;
         const size_t idx = (size_t)b * a.N + i0;
         const float4 g4 = *reinterpret_cast<const float4*>(a.g32 + idx);
@@ -996,13 +1030,15 @@ __global__ void __launch_bounds__(256) k_adj_convert_f16(ConvArgs a) {
     }
     if (wg) {
         __syncthreads();
-        // lane tx -> trial bblk + tx; warp ty walks neurons ty, ty+8, ...: every store is 32 consecutive trials of one neuron
-        for (int r = ty; r < 128; r += 8) {
-            const size_t off = (size_t)(blockIdx.x * 128 + r) * a.ld_t + a.t_col0 + bblk + tx;
-            store_split1_f16(a.gT_hi, a.gT_lo, off, tg[tx][r], sgT);
-            store_split1_f16(a.srcT_hi, a.srcT_lo, off, ts[tx][r], ssT);
+        // lane -> trial bblk + lane; warp w walks neurons w, w+8, ...: every store is 32 consecutive trials of one neuron
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        for (int r = w; r < CV_TN; r += 8) {
+            const size_t off = (size_t)(blockIdx.x * CV_TN + r) * a.ld_t + a.t_col0 + bblk + lane;
+            store_split1_f16(a.gT_hi, a.gT_lo, off, tg[lane][r], sgT);
+            store_split1_f16(a.srcT_hi, a.srcT_lo, off, ts[lane][r], ssT);
         }
     }
+    trace_end(trace);
 }
 
 // max over a short device array (the per-step source maxima of the last forward pass) -> *dst
@@ -1103,18 +1139,32 @@ __global__ void __launch_bounds__(128) k_readout_grad(int N, int B, int T, int S
     for (int q = 0; q < k; ++q) atomicAdd(dW_out + (size_t)q * N + i, acc[q] * sc);
 }
 
-// dW[i][j] = k_i * dWraw[i][j] ;  dk[i] = sum_j dWraw[i][j] * W[i][j]        (one block per row)
+// dW[i][j] = k_i * dWraw[i][j] ;  dk[i] = sum_j dWraw[i][j] * W[i][j]        (one block per row; 16-byte accesses when N % 4 == 0)
 __global__ void __launch_bounds__(256) k_finish_wgrad(int N, const float* __restrict__ dWraw, int ldr, const float* __restrict__ W,
                                                        const float* __restrict__ kp, int k_stride, float* dW, float* dk, int n_slices) {
     __shared__ float red[9];
     const int i = blockIdx.x;
     const float kv = __ldg(kp + (size_t)i * k_stride);
     float acc = 0.f;
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        float r = dWraw[(size_t)i * ldr + j];
-        for (int z = 1; z < n_slices; ++z) r += dWraw[(size_t)z * N * ldr + (size_t)i * ldr + j];     // split-K slices
-        if (dW) dW[(size_t)i * N + j] = kv * r;
-        acc = fmaf(r, W[(size_t)i * N + j], acc);
+    const bool vec = (N % 4 == 0) && (ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(dWraw) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(dW)) & 15u) == 0;
+    if (vec) {
+        for (int j = 4 * threadIdx.x; j < N; j += 4 * blockDim.x) {
+            float4 r = __ldcs(reinterpret_cast<const float4*>(dWraw + (size_t)i * ldr + j));
+            for (int z = 1; z < n_slices; ++z) {
+                const float4 q = __ldcs(reinterpret_cast<const float4*>(dWraw + (size_t)z * N * ldr + (size_t)i * ldr + j));
+                r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+            }
+            const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)i * N + j));
+            if (dW) *reinterpret_cast<float4*>(dW + (size_t)i * N + j) = make_float4(kv * r.x, kv * r.y, kv * r.z, kv * r.w);
+            acc = fmaf(r.x, w.x, acc); acc = fmaf(r.y, w.y, acc); acc = fmaf(r.z, w.z, acc); acc = fmaf(r.w, w.w, acc);
+        }
+    } else {
+        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+            float r = dWraw[(size_t)i * ldr + j];
+            for (int z = 1; z < n_slices; ++z) r += dWraw[(size_t)z * N * ldr + (size_t)i * ldr + j];     // split-K slices
+            if (dW) dW[(size_t)i * N + j] = kv * r;
+            acc = fmaf(r, W[(size_t)i * N + j], acc);
+        }
     }
     if (dk) {
         const float tot = block_sum(acc, red);
