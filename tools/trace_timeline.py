@@ -85,6 +85,15 @@ def main():
                 co += 1
         lines.append(f"{TAGS.get(tag, str(tag)):18s} {(r['t0'].min() - t_base) / 1e3:9.1f} {(r['t1'].max() - t_base) / 1e3:9.1f} "
                      f"{(r['t1'].max() - r['t0'].min()) / 1e3:8.1f} {len(r):6d} {len(np.unique(r['smid'])):4d} {co:17d}")
+    # per-CTA detail of a few launches in the middle of the forward and reverse sweeps: start / end quantiles relative to the launch start
+    for want in (3, 1, 5, 6):
+        sel = [r for tag, r in launches if tag == want]
+        if not sel:
+            continue
+        r = sel[len(sel) // 2]
+        b = r["t0"].min()
+        q = lambda a: " ".join(f"{v / 1e3:7.1f}" for v in np.quantile(a - b, [0, 0.25, 0.5, 0.75, 1.0]))
+        lines.append(f"{TAGS[want]:18s} CTA start q0/25/50/75/100: {q(r['t0'])} | end: {q(r['t1'])} us")
     text = "\n".join(lines)
     print(text)
     if args.out:
