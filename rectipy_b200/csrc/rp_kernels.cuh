@@ -855,7 +855,7 @@ __device__ __forceinline__ float f4at(const float4& v, int r) { return r == 0 ? 
 // NTY: warps per block (block = 32 x NTY threads, tile = 128 neurons x 4*NTY trials).  The binary16 path runs 4-warp blocks of 80
 // registers so that one block fits beside a resident weight-gradient GEMM CTA (168 regs x 320 threads) on the same SM.
 template <int MODEL, bool TR, int NTY>
-__global__ void __launch_bounds__(32 * NTY, NTY == 4 ? 6 : 1) k_adj_step_v4(AdjArgs a) {      // 4-warp variant: <= 80 registers
+__global__ void __launch_bounds__(32 * NTY, NTY == 4 ? 6 : 3) k_adj_step_v4(AdjArgs a) {      // <= 80 registers: 24 warps per SM (113 registers left it at 16)
     constexpr int NSV = ModelTraits<MODEL>::NSV;
     constexpr int TB = 4 * NTY;
     static_assert(!TR || TB == ADJ4_TB, "the transposing variant stages 32 trials");
