@@ -138,3 +138,37 @@ def test_softmax_output_with_windows_batched():
         assert rel_err(out[:, b].detach().cpu().numpy(), ref) < 1e-5
         assert rel_err(obs.to_numpy(("rnn", "li_op/v"))[:, b], torch.stack([v.detach() for v in r["vars"]["v"]]).numpy()) < 1e-5
     assert torch.isfinite(node["weights"].grad).all() and float(node["weights"].grad.abs().max()) > 0
+
+
+def test_binary16_range_guard_reports_exploding_adjoint():
+    """RP_PREC_3XF16 keeps one power-of-two scale per weight-gradient K chunk (2^8 headroom + 2^3 absorbed by the source
+    operand).  An adjoint that grows ~9x per reverse step (diagonal W = 8, tau = 10, dt = 1, v = 0) leaves that range within
+    one chunk: the call must fail loudly with a pointer to RP_PREC_3XTF32 -- and the tf32 format must handle the same
+    problem (finite gradients, equal to the FFMA path)."""
+    n, B, T, dt, k = 128, 128, 24, 1.0, 2
+    rng = np.random.default_rng(0)
+    W = 8.0 * np.eye(n)
+    w_out = rng.standard_normal((k, n)) / np.sqrt(n)
+    x = np.zeros((T, B, n), dtype=np.float32)
+    tgt = torch.tensor(rng.standard_normal((T, B, k)).astype(np.float32), device="cuda")
+    grads = {}
+    for prec in ("3xf16", "3xtf32", "fp32"):
+        net, node = _engine("li_tanh", n, B, dt, W, dict(tau=10.0, k=1.0, eta=0.0), prec=prec)
+        net.add_func_node("out", k, "identity"); net.add_edge("rnn", "out", weights=w_out, train="gd")
+        obs = net.run(x, verbose=False, enable_grad=True)
+        loss = torch.nn.functional.mse_loss(torch.stack(obs["out"]), tgt)
+        if prec == "3xf16":
+            with pytest.raises(RuntimeError, match="RP_PREC_3XTF32"):
+                loss.backward()
+                torch.cuda.synchronize()
+        else:
+            loss.backward()
+            grads[prec] = net.get_edge("rnn", "out").weights.grad.cpu().numpy()
+            assert np.isfinite(grads[prec]).all() and np.isfinite(node["weights"].grad.cpu().numpy()).all()
+    assert rel_err(grads["3xtf32"], grads["fp32"]) < 1e-5
+    # the guard is sticky only until it is read: the same plan works again on a tame problem
+    net, node = _engine("li_tanh", n, B, 1e-2, rng.standard_normal((n, n)) / np.sqrt(n), dict(tau=10.0, k=1.0, eta=0.0), prec="3xf16")
+    net.add_func_node("out", k, "identity"); net.add_edge("rnn", "out", weights=w_out, train="gd")
+    obs = net.run(rng.standard_normal((T, B, n)).astype(np.float32), verbose=False, enable_grad=True)
+    torch.nn.functional.mse_loss(torch.stack(obs["out"]), tgt).backward()
+    assert np.isfinite(node["weights"].grad.cpu().numpy()).all()
