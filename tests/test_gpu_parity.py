@@ -261,6 +261,58 @@ def test_tensor_core_path_matches_fp32_path(model, tc_prec):
         assert rel_err(results[tc_prec]["out"][:, b, :], ref) <= (1e-5 if model == "li_tanh" else 1e-4)
 
 
+@pytest.mark.parametrize("model", ["qif_sfa", "lif", "li_sigmoid"])
+def test_binary16_path_remaining_templates(model):
+    """The default tensor-core format (binary16 split operands) on the templates the headline tests do not touch: records of
+    two trials vs the fp64 oracle, every gradient (weights, template parameters, both edges) vs the FFMA path."""
+    import rectipy_b200 as rp
+    from golden_util import TEMPLATE_PATH
+    n, B, m, k = 128, 128, 2, 3
+    rng = np.random.default_rng(21)
+    rate = model.startswith("li_")
+    dt, T, S = (1e-2, 90, 3) if rate else (1e-3, 300, 2)
+    W = rng.standard_normal((n, n)) * (1.5 if rate else 2.0) / np.sqrt(n)
+    w_in, w_out = rng.standard_normal((n, m)), rng.standard_normal((k, n)) / np.sqrt(n)
+    params = {"li_sigmoid": dict(tau=rng.uniform(1, 2, n), k=1.2, eta=0.1),
+              "qif_sfa": dict(eta=orc.lorentzian_etas(n, eta=0.0), alpha=0.4, tau_x=1.2),
+              "lif": dict(eta=10.0, tau=rng.uniform(10, 20, n), tau_s=5.0, k=2.0)}[model]
+    skw = dict(spike_threshold=10.0, spike_reset=-10.0) if model == "lif" else {}
+    t = np.arange(T) * dt
+    amp, off = (1.5, 0.0) if rate else ((40.0, 0.0) if model == "lif" else (10.0, 14.0))
+    x = amp * np.sin(2 * np.pi * rng.uniform(0.5, 3, (1, B, m)) * t[:, None, None] * (50 if model == "lif" else 1)
+                     + rng.uniform(0, 6.28, (1, B, m))) + off
+    targets = torch.tensor(rng.standard_normal((len(range(0, T, S)), B, k)), dtype=torch.float32, device="cuda")
+    path, op, svar, tvar = TEMPLATE_PATH[model]
+    res = {}
+    for prec in ("fp32", "3xf16"):
+        net = rp.Network(dt, device="cuda:0", batch=B, precision=prec)
+        kw = dict(weights=W, source_var=svar, target_var=tvar, input_var=f"{op}/I_ext",
+                  node_vars={f"{op}/{p}": v for p, v in params.items()}, train_params=["weights", f"{op}/eta", f"{op}/tau"])
+        if rate:
+            kw.update(output_var=f"{op}/v")
+        else:
+            kw.update(spike_var=f"{op}/spike", reset_var=f"{op}/v", output_var=f"{op}/s", **skw)
+        node = net.add_diffeq_node("rnn", path, **kw)
+        net.add_func_node("inp", m, "identity"); net.add_edge("inp", "rnn", weights=w_in, train="gd")
+        net.add_func_node("out", k, "identity"); net.add_edge("rnn", "out", weights=w_out, train="gd")
+        obs = net.run(x, sampling_steps=S, verbose=False, enable_grad=True)
+        out = torch.stack(obs["out"])
+        torch.nn.functional.mse_loss(out, targets).backward()
+        res[prec] = dict(out=out.detach().cpu().numpy(), gW=node["weights"].grad.cpu().numpy(), geta=node[f"{op}/eta"].grad.cpu().numpy(),
+                         gtau=node[f"{op}/tau"].grad.cpu().numpy(), gin=net.get_edge("inp", "rnn").weights.grad.cpu().numpy(),
+                         gout=net.get_edge("rnn", "out").weights.grad.cpu().numpy())
+    errs = {key: rel_err(res["3xf16"][key], res["fp32"][key]) for key in res["fp32"]}
+    print(model, errs)
+    assert np.abs(res["fp32"]["gW"]).max() > 0
+    tol = 1e-5 if rate else 1e-3
+    assert all(e <= tol for e in errs.values()), errs
+    for b in (0, B - 1):
+        onode = orc.make_node(model, n, W, dt, params=params, dtype=torch.float64, **skw)
+        onet = orc.OracleNet(onode, w_in=torch.tensor(w_in), w_out=torch.tensor(w_out))
+        ref = torch.stack(onet.run(torch.tensor(x[:, b, :]), sampling_steps=S, enable_grad=False)["out"]).numpy()
+        assert rel_err(res["3xf16"]["out"][:, b, :], ref) <= (1e-5 if rate else 1e-4)
+
+
 @pytest.mark.parametrize("model,n,B", [("qif_sfa", 1000, 1), ("li_tanh", 203, 2), ("lif", 64, 4), ("qif", 1536, 1)])
 def test_persistent_kernels_match_per_step_path(model, n, B, monkeypatch):
     """Few-trial shapes run as ONE cooperative persistent launch per pass (rp_persistent.cuh); RP_NO_PERSISTENT=1 forces
