@@ -33,14 +33,15 @@
 extern "C" {
 #endif
 
-#define RP_ABI_VERSION 4
+#define RP_ABI_VERSION 5
 #define RP_MAX_IN 8      /* max fused input-projection width  m (wider inputs: use RP_IN_DENSE)  */
 #define RP_MAX_OUT 8     /* max fused readout width           k (wider readouts: use RP_OUT_DENSE) */
 #define RP_MAX_SV 3
 #define RP_MAX_REC 4
 
 /* vector fields (neuron_model_templates/rate_neurons/leaky_integrator.yaml, spiking_neurons/{qif,lif}.yaml) */
-enum { RP_LI_TANH = 0, RP_LI_SIGMOID = 1, RP_QIF = 2, RP_QIF_SFA = 3, RP_LIF = 4, RP_IK = 5 /* spiking_neurons/ik.yaml ik_op */ };
+enum { RP_LI_TANH = 0, RP_LI_SIGMOID = 1, RP_QIF = 2, RP_QIF_SFA = 3, RP_LIF = 4, RP_IK = 5 /* spiking_neurons/ik.yaml ik_op */,
+       RP_IKU = 6 /* ik.yaml iku_op: recovery variable driven by the per-trial population means of v and of the spikes */ };
 /* parameter slots; each is a device pointer to 1, n, B or B*n floats (see rp_desc.param_per_neuron) */
 enum { RP_P_TAU = 0, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_RMAX, RP_P_SIG_S, RP_P_V0,
        /* ik_op: */ RP_P_C, RP_P_VR, RP_P_VTH, RP_P_G, RP_P_ER, RP_P_B, RP_P_TAU_U, RP_P_KAPPA, RP_NUM_PARAMS };

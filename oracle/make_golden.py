@@ -111,7 +111,7 @@ def sin_inputs(rng, T, m, dt, amp=1.0, offset=0.0):
 
 
 def main(only=None):
-    """`only`: regenerate a single case that has its own random stream (currently: ik_bptt)."""
+    """`only`: regenerate a single case that has its own random stream (currently: ik_bptt, iku_bptt)."""
     ref = ref_shim.import_reference()
     if only is not None:
         global save_case
@@ -204,6 +204,20 @@ def main(only=None):
     spec["targets"] = rng.standard_normal((len(range(0, T, 2)), k))
     if only in (None, "ik_bptt"):
         save_case(ref, "ik_bptt", spec)
+    # ---- G6c: Izhikevich neurons with a global recovery variable (ik.yaml:33-39, iku_op: mean(v), mean(spike)), BPTT ---------
+    rng = np.random.default_rng(778)
+    n, T, m, k, dt = 16, 1000, 2, 2, 1e-1
+    spec = dict(model="iku", n=n, T=T, dt=dt, S=2, cutoff=0, grad=True,
+                W=np.abs(rng.standard_normal((n, n))) * 4.0 / n,
+                params=dict(eta=rng.uniform(60.0, 160.0, n), g=1.5, kappa=rng.uniform(5.0, 15.0, n), tau_s=6.0, E_r=0.0, b=rng.uniform(-3.0, -1.0, n),
+                            tau_u=33.33, k=0.7, C=100.0),
+                train_params=["weights", "eta", "g", "kappa", "tau_s", "b", "tau_u", "C", "k", "E_r"], train_in=True, train_out=True,
+                w_in=rng.standard_normal((n, m)) * 10.0, w_out=rng.standard_normal((k, n)) / np.sqrt(n),
+                inputs=sin_inputs(rng, T, m, dt * 1e-2, amp=3.0, offset=1.0),
+                spike_kwargs=dict(spike_threshold=40.0, spike_reset=-60.0), record_vars=[("v", False), ("u", True), ("s", False)])
+    spec["targets"] = rng.standard_normal((len(range(0, T, 2)), k))
+    if only in (None, "iku_bptt"):
+        save_case(ref, "iku_bptt", spec)
     rng = rng_main
 
     # ---- G7: output activation + masked input edge (LinearMasked, edges.py:150-174) ---------------

@@ -114,6 +114,20 @@ def field_ik(n: int) -> Tuple[Callable, List[str]]:
     return f, names
 
 
+def field_iku(n: int) -> Tuple[Callable, List[str]]:
+    """iku_op (spiking_neurons/ik.yaml:33-39): ik_op whose recovery variable is driven by the population means,
+    u' = (b*(mean(v)-v_r) - u)/tau_u + kappa*mean(spike)  (`equations: replace` of ik_op).  State order v, u, s."""
+    names = ["weights", "C", "k", "v_r", "v_theta", "eta", "g", "E_r", "b", "tau_u", "kappa", "tau_s", "I_ext", "spike"]
+
+    def f(t, y, weights, C, k, v_r, v_theta, eta, g, E_r, b, tau_u, kappa, tau_s, I_ext, spike):
+        v, u, s = y[:n], y[n:2 * n], y[2 * n:3 * n]
+        dv = (k * (v - v_r) * (v - v_theta) - u + I_ext + eta + g * (weights @ s) * (E_r - v)) / C
+        du = (b * (torch.mean(v) - v_r) - u) / tau_u + kappa * torch.mean(spike)
+        ds = -s / tau_s + spike
+        return torch.cat((dv, du, ds), 0)
+    return f, names
+
+
 #: template defaults (leaky_integrator.yaml:12-17,24-28; qif.yaml:13-22,33-35; lif.yaml:17-23)
 DEFAULTS = {
     "li_tanh":    dict(tau=10.0, k=1.0, eta=0.0),
@@ -122,6 +136,7 @@ DEFAULTS = {
     "qif_sfa":    dict(tau=1.0, k=1.0, tau_s=1.0, eta=-5.0, alpha=1.0, tau_x=10.0),
     "lif":        dict(tau=10.0, k=1.0, tau_s=0.5, eta=0.0),
     "ik":         dict(C=100.0, k=0.7, v_r=-60.0, v_theta=-40.0, eta=0.0, g=1.0, E_r=0.0, b=-2.0, tau_u=33.33, kappa=10.0, tau_s=6.0),
+    "iku":        dict(C=100.0, k=0.7, v_r=-60.0, v_theta=-40.0, eta=0.0, g=1.0, E_r=0.0, b=-2.0, tau_u=33.33, kappa=10.0, tau_s=6.0),
 }
 #: initial values of the state variables, in state order
 INIT = {
@@ -129,8 +144,9 @@ INIT = {
     "qif": [("v", -2.0), ("s", 0.0)], "qif_sfa": [("v", -2.0), ("s", 0.0), ("x", 0.0)],
     "lif": [("v", 0.0), ("s", 0.0)],
     "ik": [("v", -60.0), ("u", 0.0), ("s", 0.0)],
+    "iku": [("v", -60.0), ("u", 0.0), ("s", 0.0)],
 }
-SPIKING = {"qif", "qif_sfa", "lif", "ik"}
+SPIKING = {"qif", "qif_sfa", "lif", "ik", "iku"}
 
 
 def build_field(model: str, n: int):
@@ -146,6 +162,8 @@ def build_field(model: str, n: int):
         return field_lif(n)
     if model == "ik":
         return field_ik(n)
+    if model == "iku":
+        return field_iku(n)
     raise ValueError(model)
 
 

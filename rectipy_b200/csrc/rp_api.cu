@@ -44,12 +44,12 @@ inline int nsv_of(int model) {
     switch (model) {
         case RP_LI_TANH: case RP_LI_SIGMOID: return 1;
         case RP_QIF: case RP_LIF: return 2;
-        case RP_QIF_SFA: case RP_IK: return 3;
+        case RP_QIF_SFA: case RP_IK: case RP_IKU: return 3;
         default: return -1;
     }
 }
-inline bool spiking(int model) { return model == RP_QIF || model == RP_QIF_SFA || model == RP_LIF || model == RP_IK; }
-inline int nhist_of(int model) { return nsv_of(model) + (model == RP_IK ? 1 : 0); }
+inline bool spiking(int model) { return model == RP_QIF || model == RP_QIF_SFA || model == RP_LIF || rp::is_ik(model); }
+inline int nhist_of(int model) { return nsv_of(model) + (rp::is_ik(model) ? 1 : 0); }
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -74,6 +74,8 @@ struct rp_plan {
     float* adj = nullptr;    // [nsv][B][N]
     float* win_acc = nullptr;// [B][N]
     float* pp = nullptr;     // [2][nsv][B][N] ping-pong state when no history is kept
+    float2* mf = nullptr;    // iku: [B] per-trial {mean v, mean spike} of the state being stepped
+    float2* asum = nullptr;  // iku: [B] per-trial means of the recovery-variable adjoint terms
     float* dWraw = nullptr;  // [N][ldw]
     float* wg_g = nullptr;   // few-trial FFMA path: g_t and r_t of several steps, [chunk*B][N] each, so that the
     float* wg_src = nullptr; // read-modify-write of dW happens once per chunk (rank chunk*B update) instead of every step
@@ -109,7 +111,7 @@ rp::ModelParams make_params(const rp_plan* p, const float* const* params) {
 }
 
 int check_params(const rp_plan* p, const float* const* params) {
-    if (p->d.model == RP_IK) {
+    if (rp::is_ik(p->d.model)) {
         static const int need_ik[] = {RP_P_C, RP_P_K, RP_P_VR, RP_P_VTH, RP_P_ETA, RP_P_G, RP_P_ER, RP_P_B, RP_P_TAU_U, RP_P_KAPPA, RP_P_TAU_S};
         for (int q : need_ik) if (!params[q]) return fail("ik_op parameter slot %d is NULL", q);
         return 0;
@@ -175,6 +177,7 @@ int gemm_fp32(rp_plan* plan, bool kmajor, int P, int Q, int K, const float* A, i
         case RP_QIF_SFA:    { constexpr int M_ = RP_QIF_SFA;    __VA_ARGS__; } break; \
         case RP_LIF:        { constexpr int M_ = RP_LIF;        __VA_ARGS__; } break; \
         case RP_IK:         { constexpr int M_ = RP_IK;         __VA_ARGS__; } break; \
+        case RP_IKU:        { constexpr int M_ = RP_IKU;        __VA_ARGS__; } break; \
         default: return fail("unknown model id %d", model);             \
     }
 
@@ -393,7 +396,16 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
         p->ws_bytes += bytes;
     }
     if (rc) { rp_plan_destroy(p); return 1; }
-    if (!p->use_tc && B <= rp::PS_MAX_B && !getenv("RP_NO_PERSISTENT")) {
+    if (d->model == RP_IKU) {
+        if (cudaMalloc(reinterpret_cast<void**>(&p->mf), (size_t)B * sizeof(float2)) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&p->asum), (size_t)B * sizeof(float2)) != cudaSuccess) {
+            rp_plan_destroy(p);
+            return fail("rp_plan_create: cudaMalloc of the mean-field buffers failed");
+        }
+        p->ws_bytes += 2 * (size_t)B * sizeof(float2);
+    }
+    // (iku_op needs a per-step reduction over all neurons of a trial: per-step launch sequences only)
+    if (!p->use_tc && B <= rp::PS_MAX_B && d->model != RP_IKU && !getenv("RP_NO_PERSISTENT")) {
         if (persistent_setup(p, prop)) { rp_plan_destroy(p); return 1; }
     }
     *out = p;
@@ -405,6 +417,8 @@ void rp_plan_destroy(rp_plan* p) {
     float* bufs[] = {p->Wk, p->WkT, p->u, p->g, p->src, p->adj, p->win_acc, p->pp, p->dWraw, p->ps_vec, p->wg_g, p->wg_src};
     for (float* b : bufs) if (b) cudaFree(b);
     if (p->ps_bar) cudaFree(p->ps_bar);
+    if (p->mf) cudaFree(p->mf);
+    if (p->asum) cudaFree(p->asum);
     rp::tc_workspace_destroy(&p->tc);
     delete p;
 }
@@ -531,7 +545,13 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
                 sc_in = sc_rate; fa.sc_out = sc_rate;
             }
         }
-        fa.urec_out = (d.model == RP_IK && a->history) ? cur + (size_t)nsv * plane : nullptr;
+        fa.urec_out = (rp::is_ik(d.model) && a->history) ? cur + (size_t)nsv * plane : nullptr;
+        fa.mf = p->mf;
+        if (d.model == RP_IKU) {
+            rp::k_trial_means<<<B, 256, 0, st>>>(N, cur, d.theta, p->mf);
+            ++p->launches;
+            RP_LAUNCH_CHECK();
+        }
         fa.per_trial = p->per_trial ? 1 : 0;
         if (!p->use_tc) {
             // u[b][i] = sum_j (kW)[i][j] src_t[b][j], then the element-wise step
@@ -548,7 +568,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
                 epi.k = d.n_out; epi.win_first = w.first; epi.win_close = w.close; epi.inv_len = w.j >= 0 ? 1.0f / (float)w.len : 0.f;
                 epi.sA = rp::tc_scale_W(&p->tc); epi.sA_ro = rp::tc_scale_Wout(&p->tc); epi.sB = sc_in;
             };
-            if (p->per_trial || d.model == RP_IK) {
+            if (p->per_trial || rp::is_ik(d.model)) {
                 RP_DISPATCH_MODEL(d.model, {
                     rp::EpiFwd<M_, true> epi; fill(epi);
                     if (rp::tc_forward_step<M_, true>(&p->tc, epi, ro, st)) return fail("rp_forward: %s", rp::tc_last_error());
@@ -726,9 +746,10 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     // The fused adjoint epilogue is opt-in (RP_FUSED_ADJ=1): with one tile per CTA its element-wise work cannot overlap the
     // MMA main loop and runs at 8 warps/SM, which measured slower (340 us/step) than the contraction followed by the
     // full-occupancy k_adj_step (149 + ~60 us).  It becomes the default once tiles are software-pipelined per CTA.
-    const bool fused_adj = p->use_tc && !f16 && getenv("RP_FUSED_ADJ") && !a->dW_in && !a->g_x && !(d.model == RP_LIF && d.in_target == 1) && d.model != RP_IK && !p->per_trial;
+    const bool fused_adj = p->use_tc && !f16 && getenv("RP_FUSED_ADJ") && !a->dW_in && !a->g_x && !(d.model == RP_LIF && d.in_target == 1) && !rp::is_ik(d.model) && !p->per_trial;
     // vectorised stand-alone adjoint kernel: tensor-core shapes, no per-neuron parameter sums (dW_out then comes from k_readout_grad)
     const bool adj_v4 = p->use_tc && !fused_adj && !pgrad && !a->dW_in && !a->g_x && !p->per_trial && !getenv("RP_NO_ADJ_V4");
+    aa.mf_t = p->mf; aa.asum = p->asum;
     dim3 agrid((N + rp::ADJ_TX - 1) / rp::ADJ_TX, (B + rp::ADJ_TY * rp::ADJ_BPT - 1) / (rp::ADJ_TY * rp::ADJ_BPT));
     dim3 ablock(rp::ADJ_TX, rp::ADJ_TY);
     int pending = 0;   // steps whose (g, src) columns sit in the tensor-core weight-gradient chunk
@@ -768,7 +789,14 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             }
             const Window w = window_of(a->t_offset + t, T_tot, a->sampling_steps, a->cutoff);
             aa.y_t = a->history + (size_t)t * hslot;
-            aa.urec_t = d.model == RP_IK ? a->history + (size_t)t * hslot + (size_t)nsv * plane : nullptr;
+            aa.urec_t = rp::is_ik(d.model) ? a->history + (size_t)t * hslot + (size_t)nsv * plane : nullptr;
+            if (d.model == RP_IKU) {
+                // population means of y_t and of the incoming adjoint of u, one block per trial, before the element-wise adjoint
+                rp::k_trial_means<<<B, 256, 0, st>>>(N, aa.y_t, d.theta, p->mf);
+                rp::k_trial_adj_sums<<<B, 256, 0, st>>>(N, B, p->adj + 2 * plane, mp, d.dt, p->asum);
+                p->launches += 2;
+                RP_LAUNCH_CHECK();
+            }
             aa.x_t = a->x ? a->x + (size_t)t * x_stride : nullptr;
             aa.e_t = (a->g_out_rec && w.j >= 0) ? a->g_out_rec + (size_t)w.j * out_stride : nullptr;
             aa.e_scale = w.j >= 0 ? 1.0f / (float)w.len : 0.f;

@@ -200,7 +200,7 @@ __device__ __forceinline__ float f4get(const float4& v, int r) { return r == 0 ?
 
 // forward step: u = (kW . r_t)[b][i] never touches global memory; tile rows >= N hold W_out (readout o_t = W_out . s_t)
 // GEN: general element path (per-element parameter loads: ik_op, per-trial parameter sweeps) instead of hoisted row constants
-template <int MODEL, bool GEN = (MODEL == RP_IK)>
+template <int MODEL, bool GEN = is_ik(MODEL)>
 struct EpiFwd {
     static constexpr bool kStage = true;
     static constexpr unsigned kTag = TR_GEMM_FWD;
@@ -265,7 +265,7 @@ struct EpiFwd {
                         sr[rr] = src1;
                         if constexpr (F16) smax = fmaxf(smax, fabsf(src1)); else split_tf32(src1, hi[rr], lo[rr]);
                     }
-                    if (MODEL == RP_IK && a.urec_out) *reinterpret_cast<float4*>(a.urec_out + idx) = u4[cc];
+                    if (is_ik(MODEL) && a.urec_out) *reinterpret_cast<float4*>(a.urec_out + idx) = u4[cc];
                     st4(a.y_next + idx, v1[0], v1[1], v1[2], v1[3]);
                     if (NSV > 1) st4(a.y_next + plane + idx, s1[0], s1[1], s1[2], s1[3]);
                     if (NSV > 2) st4(a.y_next + 2 * plane + idx, x1[0], x1[1], x1[2], x1[3]);

@@ -68,10 +68,12 @@ template <> struct ModelTraits<RP_QIF>        { static constexpr int NSV = 2; st
 template <> struct ModelTraits<RP_QIF_SFA>    { static constexpr int NSV = 3; static constexpr bool SPIKING = true; };
 template <> struct ModelTraits<RP_LIF>        { static constexpr int NSV = 2; static constexpr bool SPIKING = true; };
 template <> struct ModelTraits<RP_IK>         { static constexpr int NSV = 3; static constexpr bool SPIKING = true; };   // planes v, s, u
+template <> struct ModelTraits<RP_IKU>        { static constexpr int NSV = 3; static constexpr bool SPIKING = true; };   // planes v, s, u (mean-field u)
+__host__ __device__ constexpr bool is_ik(int model) { return model == RP_IK || model == RP_IKU; }
 // checkpoint planes per step: the ik conductance synapse makes d(v')/dv depend on the recurrent drive, which is stored too
-template <int MODEL> struct HistPlanes { static constexpr int N = ModelTraits<MODEL>::NSV + (MODEL == RP_IK ? 1 : 0); };
+template <int MODEL> struct HistPlanes { static constexpr int N = ModelTraits<MODEL>::NSV + (is_ik(MODEL) ? 1 : 0); };
 // parameter slot of the coupling constant that is folded into the weights
-__host__ __device__ constexpr int fold_slot(int model) { return model == RP_IK ? RP_P_G : RP_P_K; }
+__host__ __device__ constexpr int fold_slot(int model) { return is_ik(model) ? RP_P_G : RP_P_K; }
 
 // activation of the rate templates (leaky_integrator.yaml:20-36) and its derivative w.r.t. v
 template <int MODEL>
@@ -176,6 +178,7 @@ struct FwdStepArgs {
     ScaleRef sc_out;      // binary16 operands: scale of the operand written here; amax_out receives max |src_{t+1}|
     float* amax_out;
     float* urec_out;      // ik: checkpoint plane receiving the recurrent drive of this step [B][N], or nullptr
+    const float2* mf;     // iku: per trial {mean_i v_t, mean_i spike_t} of the state being stepped (k_trial_means), else nullptr
     int per_trial;        // 1: some parameter differs between trials (no per-neuron hoisting)
 };
 
@@ -183,7 +186,7 @@ template <int MODEL>
 __device__ __forceinline__ void fwd_elem(const FwdStepArgs& a, int i, float u, float Iin,
                                          float v, float s, float x, float& v1, float& s1, float& x1, int b = 0) {
     const float dt = a.dt;
-    const float tau = MODEL == RP_IK ? 1.f : ldp(a.mp, RP_P_TAU, i, b), eta = ldp(a.mp, RP_P_ETA, i, b);
+    const float tau = is_ik(MODEL) ? 1.f : ldp(a.mp, RP_P_TAU, i, b), eta = ldp(a.mp, RP_P_ETA, i, b);
     if constexpr (!ModelTraits<MODEL>::SPIKING) {
         // li_op: v' = -v/tau + k*r_in + I_ext + eta          (leaky_integrator.yaml:10)
         v1 = v + dt * (-v / tau + u + Iin + eta);
@@ -193,13 +196,19 @@ __device__ __forceinline__ void fwd_elem(const FwdStepArgs& a, int i, float u, f
         const bool p = v >= a.theta;                           // heaviside(v-theta, 1.0)   nodes.py:383,476
         const float pf = p ? 1.0f : 0.0f;
         float vt;
-        if constexpr (MODEL == RP_IK) {
+        if constexpr (is_ik(MODEL)) {
             // ik_op (ik.yaml:10-13): v' = (k (v-v_r)(v-v_theta) - u + I_ext + eta + g s_in (E_r - v)) / C
             //                        u' = (b (v-v_r) - u)/tau_u + kappa*spike ;  s' = -s/tau_s + spike      (x holds u, u holds g*W.s)
+            // iku_op (ik.yaml:33-39): u' = (b (mean(v)-v_r) - u)/tau_u + kappa*mean(spike)   (population means per trial)
             const float C = ldp(a.mp, RP_P_C, i, b), kq = ldp(a.mp, RP_P_K, i, b), vr = ldp(a.mp, RP_P_VR, i, b), vth = ldp(a.mp, RP_P_VTH, i, b);
             const float Er = ldp(a.mp, RP_P_ER, i, b), bb = ldp(a.mp, RP_P_B, i, b), tau_u = ldp(a.mp, RP_P_TAU_U, i, b), kappa = ldp(a.mp, RP_P_KAPPA, i, b);
             vt = v + dt * ((kq * (v - vr) * (v - vth) - x + Iin + eta + u * (Er - v)) / C);
-            x1 = x + dt * ((bb * (v - vr) - x) / tau_u) + kappa * pf;
+            if constexpr (MODEL == RP_IKU) {
+                const float2 mfb = a.mf[b];
+                x1 = x + dt * ((bb * (mfb.x - vr) - x) / tau_u) + kappa * mfb.y;
+            } else {
+                x1 = x + dt * ((bb * (v - vr) - x) / tau_u) + kappa * pf;
+            }
             s1 = s + dt * (-s / tau_s) + pf;
         } else if constexpr (MODEL == RP_LIF) {
             // lif_op: v' = -v/tau + k*s_in + I_ext + eta ; s' = -s/tau_s + spike + s_ext   (lif.yaml:10-15)
@@ -242,7 +251,7 @@ struct FwdRow { float inv_tau, eta, inv_tau_s, inv_tau_x, alpha, wi0, wi1; };
 template <int MODEL>
 __device__ __forceinline__ FwdRow fwd_row(const FwdStepArgs& a, int i) {
     FwdRow r{1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f};
-    if (MODEL != RP_IK) r.inv_tau = 1.0f / ldp(a.mp, RP_P_TAU, i);
+    if (!is_ik(MODEL)) r.inv_tau = 1.0f / ldp(a.mp, RP_P_TAU, i);
     r.eta = ldp(a.mp, RP_P_ETA, i);
     if (ModelTraits<MODEL>::SPIKING) r.inv_tau_s = 1.0f / ldp(a.mp, RP_P_TAU_S, i);
     if (MODEL == RP_QIF_SFA) { r.inv_tau_x = 1.0f / ldp(a.mp, RP_P_TAU_X, i); r.alpha = ldp(a.mp, RP_P_ALPHA, i); }
@@ -298,7 +307,7 @@ __device__ __forceinline__ void fwd_element(const FwdStepArgs& a, int i, int b, 
     const float Iin = input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i);
     float v1, s1, x1;
     fwd_elem<MODEL>(a, i, u, Iin, v, s, x, v1, s1, x1, b);
-    if (MODEL == RP_IK && a.urec_out) a.urec_out[idx] = u;
+    if (is_ik(MODEL) && a.urec_out) a.urec_out[idx] = u;
     a.y_next[idx] = v1;
     if (NSV > 1) a.y_next[plane + idx] = s1;
     if (NSV > 2) a.y_next[2 * plane + idx] = x1;
@@ -368,6 +377,44 @@ __global__ void __launch_bounds__(256) k_amax_2d(int rows, int cols, const float
     }
     amax = warp_max(amax);
     if ((threadIdx.x & 31) == 0 && amax > 0.f) atomic_max_nonneg(dst, amax);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// iku_op mean field: one block per trial.  Deterministic (fixed-order block reduction), so trials stay bit-independent.
+// ------------------------------------------------------------------------------------------------------
+// mf[b] = { mean_i v[b][i], mean_i [v[b][i] >= theta] }
+__global__ void __launch_bounds__(256) k_trial_means(int N, const float* __restrict__ v, float theta, float2* mf) {
+    __shared__ float red[2][8];
+    const int b = blockIdx.x;
+    float sv = 0.f, sp = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { const float x = v[(size_t)b * N + i]; sv += x; sp += (x >= theta) ? 1.f : 0.f; }
+    for (int o = 16; o > 0; o >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, o); sp += __shfl_xor_sync(0xffffffffu, sp, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sv; red[1][threadIdx.x >> 5] = sp; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, c = 0.f;
+        for (int w = 0; w < 8; ++w) { a += red[0][w]; c += red[1][w]; }
+        mf[b] = make_float2(a / (float)N, c / (float)N);
+    }
+}
+// asum[b] = { mean_i(ax[b][i] dt b_i / tau_u_i), mean_i(ax[b][i] kappa_i) }     (ax = adjoint of the recovery variable, plane 2)
+__global__ void __launch_bounds__(256) k_trial_adj_sums(int N, int B, const float* __restrict__ ax, ModelParams mp, float dt, float2* asum) {
+    __shared__ float red[2][8];
+    const int b = blockIdx.x;
+    float s0 = 0.f, s1 = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float a = ax[(size_t)b * N + i];
+        s0 += a * dt * ldp(mp, RP_P_B, i, b) / ldp(mp, RP_P_TAU_U, i, b);
+        s1 += a * ldp(mp, RP_P_KAPPA, i, b);
+    }
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, c = 0.f;
+        for (int w = 0; w < 8; ++w) { a += red[0][w]; c += red[1][w]; }
+        asum[b] = make_float2(a / (float)N, c / (float)N);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -481,6 +528,8 @@ struct AdjArgs {
     const float* y_t;      // history slot t      [nsv][B][N]  (post)
     const float* y_tm1;    // history slot t-1                 (pre)
     const float* urec_t;   // ik: recurrent drive of step t [B][N] (checkpoint plane), else nullptr
+    const float2* mf_t;    // iku: per trial {mean v_t, mean spike_t}
+    const float2* asum;    // iku: per trial {mean_i(ax_i dt b_i / tau_u_i), mean_i(ax_i kappa_i)} of the incoming adjoint of u
     float* adj;            // [nsv][B][N] adjoint of the state, updated in place (t+1 -> t)
     const float* Z;        // [B][ldz]  (kW)^T g_t
     int ldz;
@@ -522,7 +571,7 @@ __device__ __forceinline__ void adj_ctx_init(const AdjArgs& a, AdjCtx<MODEL>& c,
 #pragma unroll
     for (int q = 0; q < ADJ_NACC; ++q) c.acc[q] = 0.f;
     if (i < a.N) {
-        if (MODEL != RP_IK) c.tau = ldp(a.mp, RP_P_TAU, i);
+        if (!is_ik(MODEL)) c.tau = ldp(a.mp, RP_P_TAU, i);
         if (ModelTraits<MODEL>::SPIKING) c.tau_s = ldp(a.mp, RP_P_TAU_S, i);
         if (MODEL == RP_QIF_SFA) { c.tau_x = ldp(a.mp, RP_P_TAU_X, i); c.alpha = ldp(a.mp, RP_P_ALPHA, i); }
     }
@@ -553,7 +602,7 @@ template <int MODEL>
 __device__ __forceinline__ AdjRowParams adj_row_params(const AdjArgs& a, int i, int b = 0) {
     AdjRowParams r{1.f, 1.f, 1.f, 0.f};
     if (i < a.N) {
-        if (MODEL != RP_IK) r.tau = ldp(a.mp, RP_P_TAU, i, b);
+        if (!is_ik(MODEL)) r.tau = ldp(a.mp, RP_P_TAU, i, b);
         if (ModelTraits<MODEL>::SPIKING) r.tau_s = ldp(a.mp, RP_P_TAU_S, i, b);
         if (MODEL == RP_QIF_SFA) { r.tau_x = ldp(a.mp, RP_P_TAU_X, i, b); r.alpha = ldp(a.mp, RP_P_ALPHA, i, b); }
     }
@@ -600,7 +649,30 @@ __device__ __forceinline__ float adj_post_math(const AdjArgs& a, const AdjRowPar
         const float gv = p ? 0.f : av;
         const float d = 1.0f + a.slope * fabsf(v - a.theta);
         const float sg = 1.0f / (d * d);                 // Spike.backward          nodes.py:478-481
-        if constexpr (MODEL == RP_IK) {
+        if constexpr (MODEL == RP_IKU) {
+            // iku_op: as ik_op, but u' couples to the population means: d u_i'/d v_j = b_i / (N tau_u_i) and, through the surrogate,
+            // d u_i'/d v_j = kappa_i sg_j / N for every j  ->  the local terms ax*dt*b/tau_u and kappa*ax become trial means (asum)
+            const float C = ldp(a.mp, RP_P_C, i, b), kq = ldp(a.mp, RP_P_K, i, b), vr = ldp(a.mp, RP_P_VR, i, b), vth = ldp(a.mp, RP_P_VTH, i, b);
+            const float Er = ldp(a.mp, RP_P_ER, i, b), bb = ldp(a.mp, RP_P_B, i, b), tau_u = ldp(a.mp, RP_P_TAU_U, i, b);
+            const float eta = ldp(a.mp, RP_P_ETA, i, b);
+            const float2 mfb = a.mf_t[b], sums = a.asum[b];
+            nav = gv * (1.0f + dt * (kq * (2.0f * v - vr - vth) - urec) / C) + sums.x + sg * (as + sums.y);
+            nas = as * (1.0f - dt / tau_s) + Z;
+            nax = ax * (1.0f - dt / tau_u) - gv * dt / C;
+            dI = dt / C * gv;
+            const float Iin = a.dparams[RP_P_C] ? input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i) : 0.f;
+            const float q = kq * (v - vr) * (v - vth) - x + Iin + eta + urec * (Er - v);
+            acc.add(RP_P_ETA, dI);
+            acc.add(RP_P_C, -dt * gv * q / (C * C));
+            acc.add(RP_P_K, dt * gv * (v - vr) * (v - vth) / C);
+            acc.add(RP_P_VR, -dt * gv * kq * (v - vth) / C - ax * dt * bb / tau_u);
+            acc.add(RP_P_VTH, -dt * gv * kq * (v - vr) / C);
+            acc.add(RP_P_ER, dt * gv * urec / C);
+            acc.add(RP_P_B, ax * dt * (mfb.x - vr) / tau_u);
+            acc.add(RP_P_TAU_U, -ax * dt * (bb * (mfb.x - vr) - x) / (tau_u * tau_u));
+            acc.add(RP_P_KAPPA, ax * mfb.y);
+            acc.add(RP_P_TAU_S, as * s * dt / (tau_s * tau_s));
+        } else if constexpr (MODEL == RP_IK) {
             // x == u (recovery variable), ax == its adjoint; urec = g*(W s_t) of the forward step
             const float C = ldp(a.mp, RP_P_C, i, b), kq = ldp(a.mp, RP_P_K, i, b), vr = ldp(a.mp, RP_P_VR, i, b), vth = ldp(a.mp, RP_P_VTH, i, b);
             const float Er = ldp(a.mp, RP_P_ER, i, b), bb = ldp(a.mp, RP_P_B, i, b), tau_u = ldp(a.mp, RP_P_TAU_U, i, b), kappa = ldp(a.mp, RP_P_KAPPA, i, b);
@@ -663,7 +735,7 @@ __device__ __forceinline__ void adj_pre_math(const AdjArgs& a, int i, float av, 
     if constexpr (ModelTraits<MODEL>::SPIKING) { gate = (vm >= a.theta) ? 0.f : 1.0f; srcv = sm; }
     else srcv = rate_act<MODEL>(a.mp, i, vm, b);
     g = a.dt * gate * av;
-    if constexpr (MODEL == RP_IK) g *= (ldp(a.mp, RP_P_ER, i, b) - vm) / ldp(a.mp, RP_P_C, i, b);    // d v' / d(g W s) = dt (E_r - v) / C
+    if constexpr (is_ik(MODEL)) g *= (ldp(a.mp, RP_P_ER, i, b) - vm) / ldp(a.mp, RP_P_C, i, b);    // d v' / d(g W s) = dt (E_r - v) / C
 }
 
 // scalar driver: loads, math, stores for element (neuron c.i, trial b)
@@ -682,7 +754,7 @@ __device__ __forceinline__ void adj_element(const AdjArgs& a, AdjCtx<MODEL>& c, 
         const float x = NSV > 2 ? __ldg(a.y_t + 2 * plane + idx) : 0.f;
         const AdjRowParams rp_ = a.per_trial ? adj_row_params<MODEL>(a, i, b) : AdjRowParams{c.tau, c.tau_s, c.tau_x, c.alpha};
         const RegAcc acc{c.acc};
-        const float urec = (MODEL == RP_IK && a.urec_t) ? __ldg(a.urec_t + idx) : 0.f;
+        const float urec = (is_ik(MODEL) && a.urec_t) ? __ldg(a.urec_t + idx) : 0.f;
         const float dI = adj_post_math<MODEL>(a, rp_, acc, i, b, Z, v, s, x, av, as, ax, urec);
         if (a.g_x_t) a.g_x_t[idx] = dI;
         a.adj[idx] = av;
@@ -761,7 +833,7 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
                     if (NSV > 1) s[l] = __ldg(a.y_t + plane + idx);
                     if (NSV > 2) x[l] = __ldg(a.y_t + 2 * plane + idx);
                     Z[l] = a.Z[(size_t)b * a.ldz + i];
-                    if (MODEL == RP_IK && a.urec_t) ur[l] = __ldg(a.urec_t + idx);
+                    if (is_ik(MODEL) && a.urec_t) ur[l] = __ldg(a.urec_t + idx);
                 }
                 if (a.do_pre) {
                     vm[l] = __ldg(a.y_tm1 + idx);
@@ -892,7 +964,7 @@ __global__ void __launch_bounds__(32 * NTY, NTY == 4 ? 6 : 3) k_adj_step_v4(AdjA
                 if (NSV > 1) s[l] = __ldg(reinterpret_cast<const float4*>(a.y_t + plane + idx));
                 if (NSV > 2) x[l] = __ldg(reinterpret_cast<const float4*>(a.y_t + 2 * plane + idx));
                 Z[l] = *reinterpret_cast<const float4*>(a.Z + (size_t)b * a.ldz + i0);
-                if (MODEL == RP_IK && a.urec_t) ur[l] = __ldg(reinterpret_cast<const float4*>(a.urec_t + idx));
+                if (is_ik(MODEL) && a.urec_t) ur[l] = __ldg(reinterpret_cast<const float4*>(a.urec_t + idx));
             }
             if (a.do_pre) {
                 vm[l] = __ldg(reinterpret_cast<const float4*>(a.y_tm1 + idx));

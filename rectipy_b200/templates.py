@@ -94,6 +94,8 @@ _LIF = [_canon("v' = -v/tau + k*s_in + I_ext + eta"), _canon("s' = -s/tau_s + sp
 _IK = [_canon("v' = (k*(v-v_r)*(v-v_theta) - u + I_ext + eta + g*s_in*(E_r - v)) / C"),
        _canon("u' = (b*(v-v_r) - u) / tau_u + kappa*spike"), _canon("s' = -s/tau_s + spike")]
 
+_IKU = [_IK[0], _canon("u' = (b*(mean(v)-v_r) - u) / tau_u + kappa*mean(spike)"), _IK[2]]
+
 _BUILTIN_OPS: Dict[str, OperatorDef] = {
     "li_op": OperatorDef("li_op", ["v' = -v/tau + k*r_in + I_ext + eta"],
                          dict(v=("output", 0.0), tau=10.0, k=1.0, eta=0.0, r_in=("input", 0.0), I_ext=("input", 0.0))),
@@ -117,9 +119,13 @@ _BUILTIN_OPS["ik_op"] = OperatorDef(
               "s' = -s/tau_s + spike"],
     dict(s=("output", 0.0), v=("variable", -60.0), u=("variable", 0.0), C=100.0, k=0.7, v_r=-60.0, v_theta=-40.0, eta=0.0, g=1.0,
          E_r=0.0, b=-2.0, tau_u=33.33, kappa=10.0, tau_s=6.0, I_ext=("input", 0.0), spike=("input", 0.0), s_in=("input", 0.0)))
+# iku_op (ik.yaml:33-39): ik_op with  b*(v-v_r) -> b*(mean(v)-v_r)  and  kappa*spike -> kappa*mean(spike)
+_BUILTIN_OPS["iku_op"] = OperatorDef(
+    "iku_op", [_BUILTIN_OPS["ik_op"].equations[0], "u' = (b*(mean(v)-v_r) - u) / tau_u + kappa*mean(spike)", "s' = -s/tau_s + spike"],
+    dict(_BUILTIN_OPS["ik_op"].variables))
 _BUILTIN_NODES = {"tanh": ["li_op", "tanh_op"], "sigmoid": ["li_op", "sigmoid_op"], "qif": ["qif_op"],
-                  "qif_sfa": ["qif_sfa_op"], "lif": ["lif_op"], "ik": ["ik_op"]}
-_BUILTIN_MODULES = {"leaky_integrator": ["tanh", "sigmoid"], "qif": ["qif", "qif_sfa"], "lif": ["lif"], "ik": ["ik"]}
+                  "qif_sfa": ["qif_sfa_op"], "lif": ["lif_op"], "ik": ["ik_op"], "iku": ["iku_op"]}
+_BUILTIN_MODULES = {"leaky_integrator": ["tanh", "sigmoid"], "qif": ["qif", "qif_sfa"], "lif": ["lif"], "ik": ["ik", "iku"]}
 
 _SLOT = dict(tau=abi.RP_P_TAU, k=abi.RP_P_K, eta=abi.RP_P_ETA, tau_s=abi.RP_P_TAU_S, tau_x=abi.RP_P_TAU_X,
              alpha=abi.RP_P_ALPHA, r_max=abi.RP_P_RMAX, s=abi.RP_P_SIG_S, v0=abi.RP_P_V0,
@@ -148,11 +154,12 @@ def _spec_from_ops(ops: List[OperatorDef]) -> TemplateSpec:
             ops=(main.name, act.name), state_vars=[(f"{main.name}/v", _val(mv["v"]))], params=params,
             source_var=f"{act.name}/r", target_var=f"{main.name}/r_in", input_vars={f"{main.name}/I_ext": 0},
             spike_var=None, out_vars={f"{main.name}/v": abi.RP_VAR_V, f"{act.name}/r": abi.RP_VAR_R})
-    if len(ops) == 1 and eqs[0] == _IK:
+    if len(ops) == 1 and eqs[0] in (_IK, _IKU):
         o = main.name
         pn = ["C", "k", "v_r", "v_theta", "eta", "g", "E_r", "b", "tau_u", "kappa", "tau_s"]
+        mean_field = eqs[0] == _IKU
         return TemplateSpec(
-            name="ik", model=abi.RP_IK, ops=(o,), state_vars=[(f"{o}/{v}", _val(mv[v])) for v in ("v", "u", "s")],
+            name="iku" if mean_field else "ik", model=abi.RP_IKU if mean_field else abi.RP_IK, ops=(o,), state_vars=[(f"{o}/{v}", _val(mv[v])) for v in ("v", "u", "s")],
             params={f"{o}/{p}": (_SLOT[p], _val(mv[p])) for p in pn},
             source_var=f"{o}/s", target_var=f"{o}/s_in", input_vars={f"{o}/I_ext": 0}, spike_var=f"{o}/spike",
             out_vars={f"{o}/v": abi.RP_VAR_V, f"{o}/s": abi.RP_VAR_S, f"{o}/u": abi.RP_VAR_X},
@@ -175,7 +182,7 @@ def _spec_from_ops(ops: List[OperatorDef]) -> TemplateSpec:
             out_vars={f"{o}/{v}": i for i, v in enumerate(sv)})
     raise NotImplementedError(
         "rectipy_b200: the operator equations " + str([op.equations for op in ops]) + " do not match any vector field "
-        "compiled into the engine (li_op+tanh_op, li_op+sigmoid_op, qif_op, qif_sfa_op, lif_op, ik_op).")
+        "compiled into the engine (li_op+tanh_op, li_op+sigmoid_op, qif_op, qif_sfa_op, lif_op, ik_op, iku_op).")
 
 
 # ------------------------------------------------------------------------------------------------------------

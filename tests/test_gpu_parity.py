@@ -468,8 +468,10 @@ def test_full_size_rate_network_directional_derivative(tc_prec):
     assert abs(analytic - numeric) <= 2e-2 * abs(numeric)
 
 
-def test_izhikevich_batched_paths_agree():
-    """ik_op on all three execution paths (persistent B=2, per-step FFMA B=20, tcgen05 B=128 N=128) vs the fp64 oracle."""
+@pytest.mark.parametrize("tmpl", ["ik", "iku"])
+def test_izhikevich_batched_paths_agree(tmpl):
+    """ik_op / iku_op on all execution paths (persistent B=2 -- per-step for iku, whose recovery variable needs the population
+    means of every step --, per-step FFMA B=20, tcgen05 B=128 N=128 in both operand formats) vs the fp64 oracle."""
     import rectipy_b200 as rp
     n, m, k, T, dt = 128, 2, 2, 300, 1e-1
     rng = np.random.default_rng(12)
@@ -477,11 +479,13 @@ def test_izhikevich_batched_paths_agree():
     w_in, w_out = rng.standard_normal((n, m)) * 10.0, rng.standard_normal((k, n)) / np.sqrt(n)
     etas = rng.uniform(60.0, 160.0, n)
     params = dict(eta=etas, g=1.5)
-    for B, prec in ((2, "fp32"), (20, "fp32"), (128, "3xtf32"), (128, "3xf16")):
-        x = (3.0 * np.sin(2 * np.pi * rng.uniform(5, 30, (1, B, m)) * (np.arange(T) * dt * 1e-3)[:, None, None]) + 1.0)
+    xs = {B: (3.0 * np.sin(2 * np.pi * rng.uniform(5, 30, (1, B, m)) * (np.arange(T) * dt * 1e-3)[:, None, None]) + 1.0) for B in (2, 20, 128)}
+    grads128 = {}
+    for B, prec in ((2, "fp32"), (20, "fp32"), (128, "fp32"), (128, "3xtf32"), (128, "3xf16")):
+        x = xs[B]
         net = rp.Network(dt, device="cuda:0", batch=B, precision=prec)
-        node = net.add_diffeq_node("ik", "neuron_model_templates.spiking_neurons.ik.ik", weights=W, source_var="s", target_var="s_in",
-                                   input_var="I_ext", output_var="s", spike_var="spike", reset_var="v", op="ik_op",
+        node = net.add_diffeq_node("ik", f"neuron_model_templates.spiking_neurons.ik.{tmpl}", weights=W, source_var="s", target_var="s_in",
+                                   input_var="I_ext", output_var="s", spike_var="spike", reset_var="v", op=f"{tmpl}_op",
                                    node_vars={"eta": etas, "g": 1.5}, spike_threshold=40.0, spike_reset=-60.0,
                                    train_params=["weights", "eta", "g", "kappa"])
         net.add_func_node("inp", m, "identity"); net.add_edge("inp", "ik", weights=w_in)
@@ -490,7 +494,7 @@ def test_izhikevich_batched_paths_agree():
         out = torch.stack(obs["out"])
         out.square().sum().backward()
         for b in (0, B - 1):
-            onode = orc.make_node("ik", n, W, dt, params=params, dtype=torch.float64, train_params=["weights", "eta", "g", "kappa"],
+            onode = orc.make_node(tmpl, n, W, dt, params=params, dtype=torch.float64, train_params=["weights", "eta", "g", "kappa"],
                                   spike_threshold=40.0, spike_reset=-60.0)
             onet = orc.OracleNet(onode, w_in=torch.tensor(w_in), w_out=torch.tensor(w_out, requires_grad=True))
             r = onet.run(torch.tensor(x[:, b, :]), sampling_steps=3, record_vars=[("u", False)], enable_grad=False)
@@ -501,6 +505,11 @@ def test_izhikevich_batched_paths_agree():
             u_got = obs.to_numpy(("ik", "u")).reshape(ref.shape[0], B, n)[:, b, :]
             assert rel_err(u_got, u_ref) < 1e-4
         assert all(torch.isfinite(p.grad).all() for p in net.parameters())
+        if B == 128:
+            grads128[prec] = [p.grad.detach().cpu().numpy().copy() for p in net.parameters()]
+    for prec in ("3xtf32", "3xf16"):            # every gradient of the tensor-core paths vs the FFMA path (same trials)
+        for g_tc, g_ff in zip(grads128[prec], grads128["fp32"]):
+            assert rel_err(g_tc, g_ff) < 1e-3, (tmpl, prec, rel_err(g_tc, g_ff))
 
 
 @pytest.mark.parametrize("model,n,B,prec", [("qif", 128, 128, "3xtf32"), ("qif", 128, 128, "3xf16"), ("li_tanh", 64, 1, "fp32"), ("qif_sfa", 96, 20, "fp32"), ("ik", 64, 2, "fp32")])
