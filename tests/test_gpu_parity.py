@@ -270,7 +270,7 @@ def test_binary16_path_remaining_templates(model):
     n, B, m, k = 128, 128, 2, 3
     rng = np.random.default_rng(21)
     rate = model.startswith("li_")
-    dt, T, S = (1e-2, 90, 3) if rate else (1e-3, 300, 2)
+    dt, T, S = (1e-2, 90, 3) if rate else ((5e-3, 600, 2) if model == "lif" else (1e-3, 300, 2))     # lif: tau ~ 15 -> first spikes after ~200 steps
     W = rng.standard_normal((n, n)) * (1.5 if rate else 2.0) / np.sqrt(n)
     w_in, w_out = rng.standard_normal((n, m)), rng.standard_normal((k, n)) / np.sqrt(n)
     params = {"li_sigmoid": dict(tau=rng.uniform(1, 2, n), k=1.2, eta=0.1),
@@ -279,8 +279,7 @@ def test_binary16_path_remaining_templates(model):
     skw = dict(spike_threshold=10.0, spike_reset=-10.0) if model == "lif" else {}
     t = np.arange(T) * dt
     amp, off = (1.5, 0.0) if rate else ((40.0, 0.0) if model == "lif" else (10.0, 14.0))
-    x = amp * np.sin(2 * np.pi * rng.uniform(0.5, 3, (1, B, m)) * t[:, None, None] * (50 if model == "lif" else 1)
-                     + rng.uniform(0, 6.28, (1, B, m))) + off
+    x = amp * np.sin(2 * np.pi * rng.uniform(0.5, 3, (1, B, m)) * t[:, None, None] + rng.uniform(0, 6.28, (1, B, m))) + off
     targets = torch.tensor(rng.standard_normal((len(range(0, T, S)), B, k)), dtype=torch.float32, device="cuda")
     path, op, svar, tvar = TEMPLATE_PATH[model]
     res = {}
