@@ -845,16 +845,16 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                 rp::AdjArgs va = aa;
                 va.dW_out = nullptr; va.any_param_grad = 0;
                 if (f16 && !overlap) {
-                    RP_DISPATCH_MODEL(d.model, (rp::k_adj_step_v4<M_, false, 8><<<dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st>>>(va)));
+                    RP_DISPATCH_MODEL(d.model, (rp::launch_pdl(rp::k_adj_step_v4<M_, false, 8>, dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st, va)));
                 } else if (f16) {
                     RP_DISPATCH_MODEL(d.model, {
                         // same shared-memory carveout as the GEMM CTAs, or the block cannot become resident beside one
                         static bool carve = false;
                         if (!carve) { cudaFuncSetAttribute(rp::k_adj_step_v4<M_, false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve = true; }
-                        rp::k_adj_step_v4<M_, false, 4><<<dim3(N / 128, B / 16), dim3(32, 4), 0, st>>>(va);
+                        rp::launch_pdl(rp::k_adj_step_v4<M_, false, 4>, dim3(N / 128, B / 16), dim3(32, 4), 0, st, va);
                     });
                 }
-                else     { RP_DISPATCH_MODEL(d.model, (rp::k_adj_step_v4<M_, true, 8><<<dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st>>>(va))); }
+                else     { RP_DISPATCH_MODEL(d.model, (rp::launch_pdl(rp::k_adj_step_v4<M_, true, 8>, dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st, va))); }
             } else {
                 RP_DISPATCH_MODEL(d.model, (rp::k_adj_step<M_><<<agrid, ablock, 0, st>>>(aa)));
             }
@@ -884,7 +884,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                 static bool carve = false;
                 if (!carve) { cudaFuncSetAttribute(rp::k_adj_convert_f16, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve = true; }
             }
-            rp::k_adj_convert_f16<<<dim3(N / rp::CV_TN, B / rp::CV_TB), 256, 0, st>>>(ca);
+            rp::launch_pdl(rp::k_adj_convert_f16, dim3(N / rp::CV_TN, B / rp::CV_TB), dim3(256), 0, st, ca);
             RP_LAUNCH_CHECK();
             ++p->launches;
             gslot ^= 1; cpar ^= 1;

@@ -467,6 +467,10 @@ __device__ __forceinline__ void gemm_split3_body(const CUtensorMap& tmA_hi, cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barriers, tensor-map prefetch, TMEM allocation) overlapped the tail of the previous kernel of the chain;
+    // operands, scales and state are its products
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -806,11 +810,11 @@ inline int tc_launch_epi(int bq, int P, int Q, int K, const CUtensorMap* A, cons
     if constexpr (std::is_same<Epi, EpiStore>::value && F16) lean = items > 0 && !getenv("RP_NO_LEAN_SLICES");
     if (lean) {
         if constexpr (std::is_same<Epi, EpiStore>::value && F16) {
-            if (bq == 256) k_gemm_split3_lean<256, Epi, F16><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
-            else           k_gemm_split3_lean<128, Epi, F16><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
+            if (bq == 256) launch_pdl(k_gemm_split3_lean<256, Epi, F16>, grid, dim3(TC_THREADS), TcCfg<256>::SMEM_BYTES, st, A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
+            else           launch_pdl(k_gemm_split3_lean<128, Epi, F16>, grid, dim3(TC_THREADS), TcCfg<128>::SMEM_BYTES, st, A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
         }
-    } else if (bq == 256) k_gemm_split3<256, Epi, F16><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
-    else                  k_gemm_split3<128, Epi, F16><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
+    } else if (bq == 256) launch_pdl(k_gemm_split3<256, Epi, F16>, grid, dim3(TC_THREADS), TcCfg<256>::SMEM_BYTES, st, A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
+    else                  launch_pdl(k_gemm_split3<128, Epi, F16>, grid, dim3(TC_THREADS), TcCfg<128>::SMEM_BYTES, st, A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) RP_TC_FAIL("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e));
     return 0;
