@@ -740,15 +740,10 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     aa.any_param_grad = (a->dW_in || a->dW_out) ? 1 : 0;
     for (int q = 0; q < RP_NUM_PARAMS; ++q) if (aa.dparams[q]) aa.any_param_grad = 1;
 
-    // fused tensor-core adjoint: everything except runs that train W_in or drive the lif s_ext input, or want dL/dx
     bool pgrad = false;
     for (int q = 0; q < RP_NUM_PARAMS; ++q) if (aa.dparams[q]) pgrad = true;
-    // The fused adjoint epilogue is opt-in (RP_FUSED_ADJ=1): with one tile per CTA its element-wise work cannot overlap the
-    // MMA main loop and runs at 8 warps/SM, which measured slower (340 us/step) than the contraction followed by the
-    // full-occupancy k_adj_step (149 + ~60 us).  It becomes the default once tiles are software-pipelined per CTA.
-    const bool fused_adj = p->use_tc && !f16 && getenv("RP_FUSED_ADJ") && !a->dW_in && !a->g_x && !(d.model == RP_LIF && d.in_target == 1) && !rp::is_ik(d.model) && !p->per_trial;
     // vectorised stand-alone adjoint kernel: tensor-core shapes, no per-neuron parameter sums (dW_out then comes from k_readout_grad)
-    const bool adj_v4 = p->use_tc && !fused_adj && !pgrad && !a->dW_in && !a->g_x && !p->per_trial && !getenv("RP_NO_ADJ_V4");
+    const bool adj_v4 = p->use_tc && !pgrad && !a->dW_in && !a->g_x && !p->per_trial && !getenv("RP_NO_ADJ_V4");
     aa.mf_t = p->mf; aa.asum = p->asum;
     dim3 agrid((N + rp::ADJ_TX - 1) / rp::ADJ_TX, (B + rp::ADJ_TY * rp::ADJ_BPT - 1) / (rp::ADJ_TY * rp::ADJ_BPT));
     dim3 ablock(rp::ADJ_TX, rp::ADJ_TY);
@@ -811,22 +806,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             }
             if (f16) aa.g_amax = p->tc.meta + rp::TCM_G_AMAX0 + (gslot ^ 1);
         }
-        if (fused_adj && aa.do_post) {
-            // Z_t = (kW)^T g_t on the tensor cores with the adjoint recurrences as its epilogue
-            rp::AdjArgs fa = aa;
-            fa.dW_out = nullptr;                     // readout gradient: one pass over the checkpoints after the sweep
-            if (pgrad) {
-                RP_DISPATCH_MODEL(d.model, {
-                    rp::EpiAdj<M_, true> epi; epi.a = fa;
-                    if (rp::tc_adjoint_step<M_, true>(&p->tc, epi, st)) return fail("rp_backward: %s", rp::tc_last_error());
-                });
-            } else {
-                RP_DISPATCH_MODEL(d.model, {
-                    rp::EpiAdj<M_, false> epi; epi.a = fa;
-                    if (rp::tc_adjoint_step<M_, false>(&p->tc, epi, st)) return fail("rp_backward: %s", rp::tc_last_error());
-                });
-            }
-        } else {
+        {
             if (p->use_tc && aa.do_post) {
                 const rp::ScaleRef sg = f16 ? rp::ScaleRef{p->tc.meta + rp::TCM_G_AMAX0 + gslot, 0.f, rp::CV_HG} : rp::no_scale();
                 // The slice becomes eligible together with this step's adjoint product (both wait for the previous kernel of the
@@ -915,7 +895,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         RP_CUDA(cudaEventRecord(p->tc.ev_join, ws));
         RP_CUDA(cudaStreamWaitEvent(st, p->tc.ev_join, 0));
     }
-    if ((fused_adj || adj_v4) && a->dW_out && a->g_out_rec && a->T > 0) {
+    if (adj_v4 && a->dW_out && a->g_out_rec && a->T > 0) {
         for (int t0 = 0; t0 < a->T; t0 += 32768) {            // grid.y limit
             const int tn = std::min(32768, a->T - t0);
             dim3 rgrid((N + 127) / 128, tn, (B + rp::RG_TB - 1) / rp::RG_TB);

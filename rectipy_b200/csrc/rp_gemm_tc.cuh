@@ -302,118 +302,6 @@ struct EpiFwd {
     }
 };
 
-// reverse step: Z = ((kW)^T . g_t)[b][i] feeds the adjoint recurrences directly; the epilogue also emits the operands of
-// the next adjoint product (K-major) and of the weight gradient (trial-major) and the parameter-gradient partial sums
-// PG: template parameters (eta, tau, tau_s, tau_x, alpha) are trained -> five register sums per owned neuron.
-// Edge gradients are not accumulated here: dW_out comes from one pass over the checkpoints (k_readout_grad), and runs that
-// train W_in use the unfused adjoint path.
-template <int MODEL, bool PG>
-struct EpiAdj {
-    static constexpr bool kStage = true;
-    static constexpr unsigned kTag = TR_GEMM_ADJ;
-    AdjArgs a;
-    __device__ __forceinline__ float2 unscale(int /*p0*/) const { return make_float2(1.f, 1.f); }
-
-    template <int BQ, bool F16>
-    __device__ __forceinline__ void run_tile(int p0, int q0, const float* tile, int et, float* /*extra*/) const {
-        static_assert(!F16, "the fused adjoint epilogue exists for the tf32 operand format only");
-        constexpr int NSV = ModelTraits<MODEL>::NSV;
-        constexpr int NCOL = BQ / 8;
-        const int w = et >> 5, l = et & 31;
-        const int cbase = w * NCOL;
-        const int i0 = p0 + 4 * l;
-        const size_t plane = (size_t)a.B * a.N;
-        float pacc[4][5];
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr)
-#pragma unroll
-            for (int q = 0; q < 5; ++q) pacc[rr][q] = 0.f;
-        AdjRowParams rp_[4];
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) rp_[rr] = adj_row_params<MODEL>(a, i0 + rr);
-
-        for (int c = 0; c < NCOL; c += 4) {
-            float g[4][4], sv[4][4];          // [column][row]
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float4 z4[2], av4[2], as4[2], ax4[2], v4[2], s4[2], x4[2], vm4[2], sm4[2];
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int col = cbase + c + 2 * half + cc;
-                    const size_t idx = (size_t)(q0 + col) * a.N + i0;
-                    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-                    z4[cc] = *reinterpret_cast<const float4*>(tile + (size_t)col * TC_BP + 4 * l);
-                    av4[cc] = *reinterpret_cast<const float4*>(a.adj + idx);
-                    as4[cc] = NSV > 1 ? *reinterpret_cast<const float4*>(a.adj + plane + idx) : zero;
-                    ax4[cc] = NSV > 2 ? *reinterpret_cast<const float4*>(a.adj + 2 * plane + idx) : zero;
-                    v4[cc] = ldg4(a.y_t + idx);
-                    s4[cc] = NSV > 1 ? ldg4(a.y_t + plane + idx) : zero;
-                    x4[cc] = NSV > 2 ? ldg4(a.y_t + 2 * plane + idx) : zero;
-                    vm4[cc] = a.do_pre ? ldg4(a.y_tm1 + idx) : zero;
-                    sm4[cc] = (a.do_pre && NSV > 1) ? ldg4(a.y_tm1 + plane + idx) : zero;
-                }
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int cl = 2 * half + cc;
-                    const int b = q0 + cbase + c + cl;
-                    const size_t idx = (size_t)b * a.N + i0;
-                    float nav[4], nas[4], nax[4], dI[4], gh[4], gl[4];
-#pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
-                        const int i = i0 + rr;
-                        nav[rr] = f4get(av4[cc], rr); nas[rr] = f4get(as4[cc], rr); nax[rr] = f4get(ax4[cc], rr);
-                        if constexpr (PG) {
-                            const RowAcc acc{pacc[rr]};
-                            dI[rr] = adj_post_math<MODEL>(a, rp_[rr], acc, i, b, f4get(z4[cc], rr), f4get(v4[cc], rr), f4get(s4[cc], rr),
-                                                          f4get(x4[cc], rr), nav[rr], nas[rr], nax[rr]);
-                        } else {
-                            const NoAcc acc;
-                            dI[rr] = adj_post_math<MODEL>(a, rp_[rr], acc, i, b, f4get(z4[cc], rr), f4get(v4[cc], rr), f4get(s4[cc], rr),
-                                                          f4get(x4[cc], rr), nav[rr], nas[rr], nax[rr]);
-                        }
-                        g[cl][rr] = 0.f; sv[cl][rr] = 0.f;
-                        if (a.do_pre) adj_pre_math<MODEL>(a, i, nav[rr], f4get(vm4[cc], rr), f4get(sm4[cc], rr), g[cl][rr], sv[cl][rr]);
-                        split_tf32(g[cl][rr], gh[rr], gl[rr]);
-                    }
-                    st4(a.adj + idx, nav[0], nav[1], nav[2], nav[3]);
-                    if (NSV > 1) st4(a.adj + plane + idx, nas[0], nas[1], nas[2], nas[3]);
-                    if (NSV > 2) st4(a.adj + 2 * plane + idx, nax[0], nax[1], nax[2], nax[3]);
-                    if (a.g_x_t) st4(a.g_x_t + idx, dI[0], dI[1], dI[2], dI[3]);
-                    if (a.do_pre) {
-                        st4(a.g_hi + (size_t)b * a.ld_g + i0, gh[0], gh[1], gh[2], gh[3]);
-                        st4(a.g_lo + (size_t)b * a.ld_g + i0, gl[0], gl[1], gl[2], gl[3]);
-                    }
-                }
-            }
-            if (a.do_pre && a.gT_hi) {
-                // weight-gradient operands, trial-major: 4 consecutive trials per 16-byte store, one row at a time
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    float gh[4], gl[4], sh[4], sl[4];
-#pragma unroll
-                    for (int cl = 0; cl < 4; ++cl) { split_tf32(g[cl][rr], gh[cl], gl[cl]); split_tf32(sv[cl][rr], sh[cl], sl[cl]); }
-                    const size_t off = (size_t)(i0 + rr) * a.ld_t + a.t_col0 + q0 + cbase + c;
-                    st4(a.gT_hi + off, gh[0], gh[1], gh[2], gh[3]);
-                    st4(a.gT_lo + off, gl[0], gl[1], gl[2], gl[3]);
-                    st4(a.srcT_hi + off, sh[0], sh[1], sh[2], sh[3]);
-                    st4(a.srcT_lo + off, sl[0], sl[1], sl[2], sl[3]);
-                }
-            }
-        }
-        if constexpr (PG) {
-            const int slots[5] = {RP_P_ETA, RP_P_TAU, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA};
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                float* dst = a.dparams[slots[q]];
-                if (dst != nullptr) {
-#pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) atomicAdd(dst + i0 + rr, pacc[rr][q]);
-                }
-            }
-        }
-    }
-};
-
 // A launch may cover only the work items [lin0, lin0 + gridDim.x) of the full (gx, gy, gz) grid, x fastest (gx == 0: the
 // launch grid is the full grid).  rp_backward uses this to spread one weight-gradient contraction over several reverse steps.
 struct TcSlice { int lin0, gx, gy; };
@@ -825,18 +713,13 @@ inline int tc_launch(bool f16, int bq, int P, int Q, int K, const CUtensorMap* A
     if (f16) return tc_launch_epi<EpiStore, true>(bq, P, Q, K, A, Bm, e, st, k_splits, item0, items);
     return tc_launch_epi<EpiStore, false>(bq, P, Q, K, A, Bm, e, st, k_splits, item0, items);
 }
-// fused launches: forward step (rows = N, or N+128 when the readout rows are appended) and adjoint step
+// fused launch: forward step (rows = N, or N+128 when the readout rows are appended)
 template <int MODEL, bool GEN>
 inline int tc_forward_step(TcWorkspace* w, const EpiFwd<MODEL, GEN>& epi, bool readout_rows, cudaStream_t st) {
     const int P = w->N + (readout_rows ? TC_BP : 0);
     if (w->f16) return tc_launch_epi<EpiFwd<MODEL, GEN>, true>(w->bq_fwd, P, w->B, w->N, w->m_W, w->m_src, epi, st);
     return tc_launch_epi<EpiFwd<MODEL, GEN>, false>(w->bq_fwd, P, w->B, w->N, w->m_W, w->m_src, epi, st);
 }
-template <int MODEL, bool PG>
-inline int tc_adjoint_step(TcWorkspace* w, const EpiAdj<MODEL, PG>& epi, cudaStream_t st) {
-    return tc_launch_epi<EpiAdj<MODEL, PG>, false>(w->bq_fwd, w->N, w->B, w->N, w->m_WT, w->m_g, epi, st);
-}
-
 // scale descriptors of the binary16 operands (no-ops on the tf32 path)
 inline ScaleRef tc_scale_W(const TcWorkspace* w) { return w->f16 ? ScaleRef{w->meta + TCM_AMAX_W, 0.f, CV_HG} : no_scale(); }
 inline ScaleRef tc_scale_Wout(const TcWorkspace* w) { return w->f16 ? ScaleRef{w->meta + TCM_AMAX_WOUT, 0.f, CV_HG} : no_scale(); }

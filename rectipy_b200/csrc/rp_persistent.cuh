@@ -309,7 +309,6 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
         if (a.g_yT) { av = a.g_yT[idx]; if (NSV > 1) as = a.g_yT[plane + idx]; if (NSV > 2) ax = a.g_yT[2 * plane + idx]; }
         rowp = adj_row_params<MODEL>(aa, i, b);
     }
-    const float dt = a.dt;
     const int nvec = N >> 2;
     const bool truncating = a.truncate > 0 && a.truncate < a.T_total;
 
