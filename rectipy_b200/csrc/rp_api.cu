@@ -824,7 +824,20 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             if (adj_v4) {
                 rp::AdjArgs va = aa;
                 va.dW_out = nullptr; va.any_param_grad = 0;
-                if (f16 && !overlap) {
+                // rolling-pipeline kernel: spiking templates whose source value is not needed here (the conversion kernel reads
+                // s_{t-1} from the checkpoint itself), enough warps for one per neuron tile
+                const bool v5 = f16 && !overlap && spk && d.model != RP_IKU && va.src == nullptr && p->sm_count * 24 >= N / 128 && !getenv("RP_NO_ADJ_V5");
+                if (v5) {
+                    {
+                        switch (d.model) {
+                            case RP_QIF:     rp::launch_pdl(rp::k_adj_step_v5<RP_QIF>, dim3(p->sm_count * 3), dim3(256), 0, st, va); break;
+                            case RP_QIF_SFA: rp::launch_pdl(rp::k_adj_step_v5<RP_QIF_SFA>, dim3(p->sm_count * 3), dim3(256), 0, st, va); break;
+                            case RP_LIF:     rp::launch_pdl(rp::k_adj_step_v5<RP_LIF>, dim3(p->sm_count * 3), dim3(256), 0, st, va); break;
+                            case RP_IK:      rp::launch_pdl(rp::k_adj_step_v5<RP_IK>, dim3(p->sm_count * 3), dim3(256), 0, st, va); break;
+                            default: return fail("rp_backward: internal error (adjoint kernel dispatch)");
+                        }
+                    }
+                } else if (f16 && !overlap) {
                     RP_DISPATCH_MODEL(d.model, (rp::launch_pdl(rp::k_adj_step_v4<M_, false, 8>, dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st, va)));
                 } else if (f16) {
                     RP_DISPATCH_MODEL(d.model, {

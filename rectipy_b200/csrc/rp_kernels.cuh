@@ -1055,6 +1055,84 @@ __global__ void __launch_bounds__(32 * NTY, NTY == 4 ? 6 : 3) k_adj_step_v4(AdjA
     }
 }
 
+// Rolling-pipeline variant for the binary16 path (no transposed staging, no parameter sums): a warp owns one 128-neuron tile
+// (lane -> 4 neurons, per-neuron constants loaded once) and walks over trials with a stride; the loads of the NEXT trial are
+// issued before the current trial is computed and stored, so every warp keeps one trial's worth of 16-byte loads in flight all
+// the time instead of exposing the load latency once per batch.  Grid = 3 blocks of 8 warps per SM (<= 80 registers).
+template <int MODEL>
+struct AdjLoads { float4 av, as, ax, v, vm, Z, ur; };
+
+template <int MODEL>
+__device__ __forceinline__ void adj_v5_load(const AdjArgs& a, AdjLoads<MODEL>& L, int b, int i0, size_t plane) {
+    constexpr int NSV = ModelTraits<MODEL>::NSV;
+    const size_t idx = (size_t)b * a.N + i0;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    L.av = *reinterpret_cast<const float4*>(a.adj + idx);
+    L.as = NSV > 1 ? *reinterpret_cast<const float4*>(a.adj + plane + idx) : zero;
+    L.ax = NSV > 2 ? *reinterpret_cast<const float4*>(a.adj + 2 * plane + idx) : zero;
+    L.v = L.vm = L.Z = L.ur = zero;
+    if (a.do_post) {
+        L.v = __ldg(reinterpret_cast<const float4*>(a.y_t + idx));
+        L.Z = *reinterpret_cast<const float4*>(a.Z + (size_t)b * a.ldz + i0);
+        if (is_ik(MODEL) && a.urec_t) L.ur = __ldg(reinterpret_cast<const float4*>(a.urec_t + idx));
+    }
+    if (a.do_pre) L.vm = __ldg(reinterpret_cast<const float4*>(a.y_tm1 + idx));
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(256, 3) k_adj_step_v5(AdjArgs a) {
+    constexpr int NSV = ModelTraits<MODEL>::NSV;
+    static_assert(MODEL != RP_IKU, "iku_op uses the generic adjoint kernel (trial means)");
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+    const int NT = a.N / 128;
+    const int stride = nw / NT;                     // warps per neuron tile = trial stride (host guarantees nw >= NT)
+    const int tile = gw % NT, b0 = gw / NT;
+    const size_t plane = (size_t)a.B * a.N;
+    pdl_launch_dependents();
+    pdl_wait();
+    TraceRec* trace = threadIdx.x == 0 ? trace_begin(TR_ADJ_STEP) : nullptr;
+    float gmax = 0.f;
+    if (b0 < stride && b0 < a.B) {
+        const int i0 = tile * 128 + 4 * lane;
+        const NoAcc nacc;
+        AdjRowParams rp_[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) rp_[rr] = adj_row_params<MODEL>(a, i0 + rr);
+        AdjLoads<MODEL> cur, nxt;
+        adj_v5_load<MODEL>(a, cur, b0, i0, plane);
+        for (int b = b0; b < a.B; b += stride) {
+            const bool more = b + stride < a.B;
+            if (more) adj_v5_load<MODEL>(a, nxt, b + stride, i0, plane);
+            const size_t idx = (size_t)b * a.N + i0;
+            float nav[4], nas[4], nax[4], g[4];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                nav[rr] = f4at(cur.av, rr); nas[rr] = f4at(cur.as, rr); nax[rr] = f4at(cur.ax, rr);
+                if (a.do_post)
+                    adj_post_math<MODEL>(a, rp_[rr], nacc, i0 + rr, b, f4at(cur.Z, rr), f4at(cur.v, rr), 0.f, 0.f,
+                                         nav[rr], nas[rr], nax[rr], f4at(cur.ur, rr));
+                g[rr] = 0.f;
+                float sv_unused = 0.f;
+                if (a.do_pre) adj_pre_math<MODEL>(a, i0 + rr, nav[rr], f4at(cur.vm, rr), 0.f, g[rr], sv_unused, b);
+                gmax = fmaxf(gmax, fabsf(g[rr]));
+            }
+            if (a.do_post) {
+                *reinterpret_cast<float4*>(a.adj + idx) = make_float4(nav[0], nav[1], nav[2], nav[3]);
+                if (NSV > 1) *reinterpret_cast<float4*>(a.adj + plane + idx) = make_float4(nas[0], nas[1], nas[2], nas[3]);
+                if (NSV > 2) *reinterpret_cast<float4*>(a.adj + 2 * plane + idx) = make_float4(nax[0], nax[1], nax[2], nax[3]);
+            }
+            if (a.do_pre && a.g) *reinterpret_cast<float4*>(a.g + idx) = make_float4(g[0], g[1], g[2], g[3]);
+            if (more) cur = nxt;
+        }
+    }
+    if (a.g_amax && a.do_pre) {
+        gmax = warp_max(gmax);
+        if (lane == 0 && gmax > 0.f) atomic_max_nonneg(a.g_amax, gmax);
+    }
+    trace_end(trace);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // binary16 operands of the reverse sweep.  The adjoint kernel leaves g_{t-1} in fp32 together with its exact maximum; this
 // kernel turns it (and the source values r_{t-1}) into the split binary16 operands of the next two contractions:
