@@ -226,7 +226,8 @@ struct EpiFwd {
             const float so = F16 ? exp2i(scale_expo(a.sc_out)) : 1.f;
             float smax = 0.f;
             // NB trials per batch: all their loads are issued before the first store (8 warps per SM have to cover the HBM
-            // latency alone here: measured epilogue 35 us at 2 trials per batch, 25 us at 4, 43 us at 8)
+            // latency alone here: measured epilogue 35 us at 2 trials per batch, 25 us at 4, 43 us at 8; issuing batch k+1 before
+            // batch k is computed -- 2+2 or 4+4 trials in flight -- measured 27 and 31 us: no better than plain batches of 4)
             constexpr int NB = 4;
             static_assert(NCOL % NB == 0, "trial batch must divide the per-warp column block");
             for (int c = 0; c < NCOL; c += NB) {
