@@ -1023,7 +1023,7 @@ int rp_plan_status(rp_plan* p, void* stream) {
     RP_CUDA(cudaStreamSynchronize(st));
     if (flags & 1) {
         RP_CUDA(cudaMemsetAsync(dflags, 0, sizeof(int), st));
-        return fail("rp_plan_status: the adjoint grew by more than 2^10 within one weight-gradient chunk, which exceeds the binary16 "
+        return fail("rp_plan_status: the adjoint grew by more than 2^14 within one weight-gradient chunk, which exceeds the binary16 "
                     "operand range of RP_PREC_3XF16; the gradients of this call are invalid -- use RP_PREC_3XTF32 for this problem");
     }
     return 0;

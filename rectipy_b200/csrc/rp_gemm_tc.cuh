@@ -624,7 +624,9 @@ inline int tc_workspace_create(TcWorkspace* w, int N, int B, bool f16, bool rate
     w->N = N; w->B = B; w->ldk = N; w->f16 = f16;
     const size_t es = w->esize();
     // weight-gradient K chunk: several steps' (g, src) columns per GEMM so that the read-modify-write of dW amortises
-    int chunk = 8192 / B; if (chunk < 1) chunk = 1; if (chunk > 16) chunk = 16;
+    // (measured at N=4096, B=1024: 83 us per step at 4 steps per chunk, 72 at 8, 66 at 16)
+    int chunk = 16384 / B; if (chunk < 1) chunk = 1; if (chunk > 16) chunk = 16;
+    if (getenv("RP_WG_CHUNK") && atoi(getenv("RP_WG_CHUNK")) > 0) chunk = atoi(getenv("RP_WG_CHUNK"));     // tuning experiments
     w->wgrad_chunk = chunk;
     w->ldt = chunk * B;
     w->bq_fwd = (B % 256 == 0) ? 256 : 128;

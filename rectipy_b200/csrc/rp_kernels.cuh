@@ -1138,12 +1138,12 @@ __global__ void __launch_bounds__(256, 3) k_adj_step_v5(AdjArgs a) {
 // kernel turns it (and the source values r_{t-1}) into the split binary16 operands of the next two contractions:
 //   K-major    g_hi/lo  [B][ld_g]           scale 2^e(max|g_{t-1}|)      -> Z_{t-1} = (kW)^T g_{t-1}
 //   trial-major gT, srcT [N][ld_t]          one scale per weight-gradient K chunk (several steps share one accumulator)
-// The chunk scale is fixed by the first step of the chunk with a non-zero gradient, with 2^8 headroom for growth inside the
+// The chunk scale is fixed by the first step of the chunk with a non-zero gradient, with 2^11 headroom for growth inside the
 // chunk; growth beyond that is absorbed by moving up to 2^3 into the source operand, and anything beyond raises a flag that
 // rp_plan_status reports (the caller should then use RP_PREC_3XTF32).
 // ------------------------------------------------------------------------------------------------------
 constexpr int CV_HG = 14;        // exact-maximum operands: max -> [2^13, 2^14)
-constexpr int CV_HCHUNK = 8;     // weight-gradient chunk: first maximum -> [2^7, 2^8)
+constexpr int CV_HCHUNK = 4;     // weight-gradient chunk (up to 16 steps): first maximum -> [2^3, 2^4), i.e. 2^11 of growth before the 2^15 limit
 constexpr int CV_HSRC = 12;      // source operand bound -> [2^11, 2^12)
 struct ConvArgs {
     int N, B;

@@ -141,8 +141,8 @@ def test_softmax_output_with_windows_batched():
 
 
 def test_binary16_range_guard_reports_exploding_adjoint():
-    """RP_PREC_3XF16 keeps one power-of-two scale per weight-gradient K chunk (2^8 headroom + 2^3 absorbed by the source
-    operand).  An adjoint that grows ~9x per reverse step (diagonal W = 8, tau = 10, dt = 1, v = 0) leaves that range within
+    """RP_PREC_3XF16 keeps one power-of-two scale per weight-gradient K chunk (2^11 headroom + 2^3 absorbed by the
+    source operand).  An adjoint that grows ~9x per reverse step (diagonal W = 8, tau = 10, dt = 1, v = 0) leaves that range within
     one chunk: the call must fail loudly with a pointer to RP_PREC_3XTF32 -- and the tf32 format must handle the same
     problem (finite gradients, equal to the FFMA path)."""
     n, B, T, dt, k = 128, 128, 24, 1.0, 2
