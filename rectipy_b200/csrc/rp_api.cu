@@ -718,22 +718,34 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     // is capped at 144 registers, given the full shared-memory carveout and the adjoint block needs no shared memory, but a
     // 4-warp adjoint block beside a GEMM CTA streams ~3x slower (the CTA's TMA and MMA operand traffic keeps the SM's L1/shared
     // pipe ~70 % busy), so the step time does not improve: 35.5 ms vs 34.3 ms per 100-step pass without the overlap.
-    const bool overlap = f16 && need_dW && getenv("RP_WG_OVERLAP");
+    const bool coresident = f16 && need_dW && getenv("RP_WG_OVERLAP");
+    // Second opt-in variant (RP_WG_IDLE_SLICES=1): the adjoint product of a step runs on (n/128) x (batch/256) CTAs -- 128 of the 148
+    // SMs at the headline shape -- and a slice of exactly the idle SMs' worth of weight-gradient work items of the previous K chunk is
+    // launched beside it; what is left of the chunk runs as one ordinary launch when the next chunk's operands are complete.
+    // Measured: with 16-step chunks a work item (K = 8192) takes 140 us, twice the product, so the slice keeps 20 SMs busy through
+    // the adjoint step, whose persistent grid then needs a second wave (57 vs 31 us): 35.2 vs 34.1 ms per pass.  With 8-step chunks
+    // the items fit (73 us) but only 16 % of a chunk moves off the critical path, which the longer chunk already gains.
+    const int zgrid = p->use_tc ? (N / rp::TC_BP) * (B / p->tc.bq_fwd) : 0;
+    const int idle_sms = p->sm_count - zgrid;
+    const bool idle_slices = f16 && need_dW && !coresident && idle_sms >= 8 && getenv("RP_WG_IDLE_SLICES");
+    const bool overlap = coresident || idle_slices;         // weight-gradient slices on the side stream
     int cb_fill = 0, chunks_done = 0;
     bool q_active = false; int q_cb = 0, q_K = 0, q_next = 0, q_ref = 0;
     const int q_total = p->use_tc ? rp::tc_wgrad_items(&p->tc) : 0;
-    const int q_per_step = p->use_tc ? (q_total + p->tc.wgrad_chunk - 1) / p->tc.wgrad_chunk : 0;
+    const int q_per_step = !p->use_tc ? 0 : (coresident ? (q_total + p->tc.wgrad_chunk - 1) / p->tc.wgrad_chunk : idle_sms);
     cudaStream_t ws = overlap ? p->tc.ws : st;
-    auto launch_slices = [&](int count) -> int {      // next `count` work items of the queued chunk, on the side stream
+    // next `count` work items of the queued chunk on stream `on` (side stream: slices; main stream: the remainder, idle-SM mode)
+    auto launch_slices = [&](int count, cudaStream_t on) -> int {
         count = std::min(count, q_total - q_next);
         if (count <= 0) return 0;
         const rp::ScaleRef sc{p->tc.meta + q_ref, 0.f, rp::CV_HCHUNK};
-        if (rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, q_K, 1, ws, sc, q_cb, q_next, count)) return fail("rp_backward: %s", rp::tc_last_error());
+        if (rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, q_K, 1, on, sc, q_cb, q_next, count)) return fail("rp_backward: %s", rp::tc_last_error());
         ++p->launches;
         q_next += count;
         if (q_next == q_total) { q_active = false; if (cudaEventRecord(p->tc.ev_done[q_cb], ws) != cudaSuccess) return fail("cudaEventRecord failed"); }
         return 0;
     };
+    cudaStream_t rest_stream = coresident ? ws : st;       // where the remainder of a chunk goes
     for (int q = 0; q < RP_NUM_PARAMS; ++q) aa.dparams[q] = (q == fold) ? nullptr : a->dparams[q];
     aa.dW_in = a->dW_in; aa.dW_out = a->dW_out;
     aa.per_trial = p->per_trial ? 1 : 0;
@@ -819,14 +831,14 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                 }
                 if (rp::tc_gemm(&p->tc, rp::TC_DGRAD, p->u, p->ldu, 0, 0, st, sg)) return fail("rp_backward: %s", rp::tc_last_error());
                 ++p->launches;
-                if (slice_now && launch_slices(q_per_step)) return 1;
+                if (slice_now && launch_slices(q_per_step, ws)) return 1;
             }
             if (adj_v4) {
                 rp::AdjArgs va = aa;
                 va.dW_out = nullptr; va.any_param_grad = 0;
                 // rolling-pipeline kernel: spiking templates whose source value is not needed here (the conversion kernel reads
                 // s_{t-1} from the checkpoint itself), enough warps for one per neuron tile
-                const bool v5 = f16 && !overlap && spk && d.model != RP_IKU && va.src == nullptr && p->sm_count * 24 >= N / 128 && !getenv("RP_NO_ADJ_V5");
+                const bool v5 = f16 && !coresident && spk && d.model != RP_IKU && va.src == nullptr && p->sm_count * 24 >= N / 128 && !getenv("RP_NO_ADJ_V5");
                 if (v5) {
                     {
                         switch (d.model) {
@@ -837,7 +849,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                             default: return fail("rp_backward: internal error (adjoint kernel dispatch)");
                         }
                     }
-                } else if (f16 && !overlap) {
+                } else if (f16 && !coresident) {
                     RP_DISPATCH_MODEL(d.model, (rp::launch_pdl(rp::k_adj_step_v4<M_, false, 8>, dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st, va)));
                 } else if (f16) {
                     RP_DISPATCH_MODEL(d.model, {
@@ -892,11 +904,11 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                     if (rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, pending * B, 1, st, sc, f16 ? cb_fill : 0)) return fail("rp_backward: %s", rp::tc_last_error());
                     ++p->launches;
                 } else {
-                    if (q_active && launch_slices(q_total)) return 1;              // whatever is left of the previous chunk
-                    RP_CUDA(cudaEventRecord(p->tc.ev_ops[cb_fill], st));
+                    if (q_active && launch_slices(q_total, rest_stream)) return 1;  // whatever is left of the previous chunk
+                    RP_CUDA(cudaEventRecord(p->tc.ev_ops[cb_fill], st));           // (after that launch: the next slices touch the same dW tiles)
                     RP_CUDA(cudaStreamWaitEvent(ws, p->tc.ev_ops[cb_fill], 0));
                     q_active = true; q_cb = cb_fill; q_K = pending * B; q_next = 0; q_ref = ref_slot;
-                    if (t == 1 && launch_slices(q_total)) return 1;                // last chunk: only the final post step is left to overlap with
+                    if (t == 1 && launch_slices(q_total, rest_stream)) return 1;   // last chunk: only the final post step is left to overlap with
                     cb_fill ^= 1; cpar = 0; ++chunks_done;
                 }
                 pending = 0;
@@ -904,7 +916,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         }
     }
     if (overlap) {
-        if (q_active && launch_slices(q_total)) return 1;
+        if (q_active && launch_slices(q_total, rest_stream)) return 1;
         RP_CUDA(cudaEventRecord(p->tc.ev_join, ws));
         RP_CUDA(cudaStreamWaitEvent(st, p->tc.ev_join, 0));
     }

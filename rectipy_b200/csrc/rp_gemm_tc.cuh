@@ -698,7 +698,7 @@ inline int tc_launch_epi(int bq, int P, int Q, int K, const CUtensorMap* A, cons
     }
     const int kb = K / BK / k_splits;
     bool lean = false;
-    if constexpr (std::is_same<Epi, EpiStore>::value && F16) lean = items > 0 && !getenv("RP_NO_LEAN_SLICES");
+    if constexpr (std::is_same<Epi, EpiStore>::value && F16) lean = items > 0 && getenv("RP_WG_OVERLAP") && !getenv("RP_NO_LEAN_SLICES");
     if (lean) {
         if constexpr (std::is_same<Epi, EpiStore>::value && F16) {
             if (bq == 256) launch_pdl(k_gemm_split3_lean<256, Epi, F16>, grid, dim3(TC_THREADS), TcCfg<256>::SMEM_BYTES, st, A[0], A[1], Bm[0], Bm[1], kb, epi, slice);
