@@ -664,13 +664,14 @@ inline int tc_workspace_ensure_wgrad(TcWorkspace* w, size_t* bytes) {
     if (w->gT_hi[0]) return 0;
     const size_t nt = (size_t)w->N * w->ldt * w->esize();
     const bool f16 = w->f16;
-    const int nbuf = f16 ? 2 : 1;
+    const bool side = f16 && (getenv("RP_WG_OVERLAP") || getenv("RP_WG_IDLE_SLICES"));      // the opt-in overlap variants
+    const int nbuf = side ? 2 : 1;
     for (int c = 0; c < nbuf; ++c) {
         if (tc_alloc(&w->gT_hi[c], nt, bytes) || tc_alloc(&w->gT_lo[c], nt, bytes) || tc_alloc(&w->srcT_hi[c], nt, bytes) || tc_alloc(&w->srcT_lo[c], nt, bytes)) return 1;
         if (tc_make_map(&w->m_srcT[c][0], w->srcT_hi[c], f16, w->N, w->ldt, w->ldt, TC_BP) || tc_make_map(&w->m_srcT[c][1], w->srcT_lo[c], f16, w->N, w->ldt, w->ldt, TC_BP)) return 1;
         if (tc_make_map(&w->m_gT[c][0], w->gT_hi[c], f16, w->N, w->ldt, w->ldt, w->bq_wg) || tc_make_map(&w->m_gT[c][1], w->gT_lo[c], f16, w->N, w->ldt, w->ldt, w->bq_wg)) return 1;
     }
-    if (f16) {
+    if (side) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);           // lo = least priority (the default), hi = greatest
         const int prio = getenv("RP_WS_HIGH_PRIORITY") ? hi : lo;
