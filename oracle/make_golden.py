@@ -103,6 +103,53 @@ def save_case(ref, name, spec):
     print(f"{name}: wrote {os.path.getsize(path)/1024:.1f} KiB;  out {blob['float64_out'].shape}")
 
 
+def save_two_node_chain(ref):
+    """G9: a feed-forward chain of TWO differential-equation nodes, the general topology the reference's graph walk can
+    execute (rectipy/network.py:962-973; documentation/rnn_tryout.py):  inp -> Linear -> LI-tanh (RateNet, output v) ->
+    Linear -> QIF (SpikeResetNet, output s) -> Linear -> out.  BPTT through both nodes and all three edges."""
+    rng = np.random.default_rng(4242)
+    n1, n2, m, k, T, dt, S, cutoff = 10, 8, 2, 3, 900, 1e-3, 3, 4
+    W1 = rng.standard_normal((n1, n1)) * 1.5 / np.sqrt(n1)
+    W2 = rng.standard_normal((n2, n2)) * 2.0 / np.sqrt(n2)
+    p1 = dict(tau=rng.uniform(0.02, 0.05, n1), k=1.2, eta=0.3)
+    p2 = dict(eta=orc.lorentzian_etas(n2) + 20.0, k=1.5, tau_s=0.7)
+    w_in, w12, w_out = rng.standard_normal((n1, m)), rng.standard_normal((n2, n1)) * 8.0, rng.standard_normal((k, n2)) / np.sqrt(n2)
+    inputs = sin_inputs(rng, T, m, dt, amp=3.0, offset=1.0)
+    targets = rng.standard_normal((len([t for t in range(T) if t >= cutoff and t % S == 0]), k))
+    blob = dict(in_W1=W1, in_W2=W2, in_w_in=w_in, in_w12=w12, in_w_out=w_out, in_inputs=inputs, in_targets=targets,
+                p1_tau=np.asarray(p1["tau"]), p2_eta=np.asarray(p2["eta"]),
+                meta=np.asarray(repr(dict(n1=n1, n2=n2, m=m, k=k, T=T, dt=dt, S=S, cutoff=cutoff, p1_k=1.2, p1_eta=0.3, p2_k=1.5, p2_tau_s=0.7))))
+    for dn in ("float64", "float32"):
+        dtype = TD[dn]
+        net = ref.Network(dt, device="cpu", dtype=dtype)
+        f1, a1, vm1, pm1 = orc.build_node_args("li_tanh", n1, W1, p1, dtype, "I_ext", None)
+        node1 = ref.nodes.RateNet(f1, a1, vm1, pm1, dt=dt, dtype=dtype, train_params=["weights", "tau"], device="cpu")
+        f2, a2, vm2, pm2 = orc.build_node_args("qif", n2, W2, p2, dtype, "I_ext", None)
+        node2 = ref.nodes.SpikeResetNet(f2, a2, vm2, pm2, dt=dt, dtype=dtype, train_params=["weights", "eta"], device="cpu")
+        net.add_node("rate", node1, node_type="diff_eq")
+        net.add_node("spk", node2, node_type="diff_eq")
+        net.add_func_node("inp", m, "identity"); net.add_func_node("out", k, "identity")
+        net.add_edge("inp", "rate", weights=w_in, train="gd")
+        net.add_edge("rate", "spk", weights=w12, train="gd")
+        net.add_edge("spk", "out", weights=w_out, train="gd")
+        obs = net.run(torch.tensor(inputs, dtype=dtype), sampling_steps=S, cutoff=cutoff, verbose=False, enable_grad=True,
+                      record_vars=[("rate", "v", False), ("spk", "s", True)])
+        out = torch.stack(obs["out"])
+        loss = torch.nn.MSELoss()(out, torch.tensor(targets, dtype=dtype))
+        loss.backward()
+        res = dict(out=out.detach().numpy(), steps=np.asarray(obs["steps"]), var_rate_v=obs.to_numpy(("rate", "v")),
+                   var_spk_s=obs.to_numpy(("spk", "s")), loss=loss.detach().numpy(),
+                   grad_W1=node1["weights"].grad.numpy(), grad_tau1=node1["tau"].grad.numpy(),
+                   grad_W2=node2["weights"].grad.numpy(), grad_eta2=node2["eta"].grad.numpy(),
+                   grad_w_in=net.get_edge("inp", "rate").weights.grad.numpy(), grad_w12=net.get_edge("rate", "spk").weights.grad.numpy(),
+                   grad_w_out=net.get_edge("spk", "out").weights.grad.numpy(),
+                   n_spikes=np.asarray(float(obs.to_numpy(("spk", "s")).max())))
+        for kk, v in res.items():
+            blob[f"{dn}_{kk}"] = v
+    np.savez_compressed(os.path.join(OUT, "two_node_chain.npz"), **blob)
+    print("two_node_chain: out", blob["float64_out"].shape, "max mean-s", float(blob["float64_var_spk_s"].max()))
+
+
 def sin_inputs(rng, T, m, dt, amp=1.0, offset=0.0):
     t = np.arange(T) * dt
     freqs = rng.uniform(0.5, 3.0, size=m)
@@ -218,6 +265,8 @@ def main(only=None):
     spec["targets"] = rng.standard_normal((len(range(0, T, 2)), k))
     if only in (None, "iku_bptt"):
         save_case(ref, "iku_bptt", spec)
+    if only in (None, "two_node_chain"):
+        save_two_node_chain(ref)
     rng = rng_main
 
     # ---- G7: output activation + masked input edge (LinearMasked, edges.py:150-174) ---------------

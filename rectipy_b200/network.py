@@ -14,7 +14,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 from time import perf_counter
-from typing import Callable, Iterator, List, Optional, Tuple, Union
+from typing import Callable, Dict, Iterator, List, Optional, Tuple, Union
 
 import numpy as np
 import torch
@@ -339,8 +339,8 @@ class Network:
             self.compile()
         diffeq = [n for n in self.graph.nodes if self[n]["node_type"] == "diff_eq"]
         if len(diffeq) != 1:
-            raise NotImplementedError(f"rectipy_b200 executes networks with exactly one differential-equation node "
-                                      f"(found {len(diffeq)}: {diffeq}); multi-node graphs are not implemented.")
+            raise NotImplementedError(f"rectipy_b200: the fused single-node plan needs exactly one differential-equation node "
+                                      f"(found {len(diffeq)}: {diffeq}); feed-forward chains run through Network._get_path().")
         d = diffeq[0]
         g = self.graph
         preds, succs = list(g.predecessors(d)), list(g.successors(d))
@@ -363,16 +363,80 @@ class Network:
         self._chain = _Chain(d, in_func, out_func, in_edge, out_edge)
         return self._chain
 
+    def _engine_device(self) -> torch.device:
+        return next(self.get_node(n) for n in self.graph.nodes if self[n]["node_type"] == "diff_eq").device
+
+    # ---- feed-forward chains of several differential-equation nodes ------------------------------------------
+    def _is_multi(self) -> bool:
+        return sum(1 for n in self.graph.nodes if self[n]["node_type"] == "diff_eq") > 1
+
+    def _get_path(self) -> List[str]:
+        """Nodes from the input node to the output node when the graph is one simple path (every graph the reference's
+        recursive walk can execute, rectipy/network.py:962-973, is of this form: fan-in fails there).
+        A node's output never depends on a later node, so node i can be integrated for the whole horizon before node
+        i+1 starts: each differential-equation node is one engine call with dense per-step input and output, and
+        autograd chains the calls (dense input gradients)."""
+        if self._in_node is None or self._out_node is None:
+            self.compile()
+        g = self.graph
+        if any(g.in_degree(n) > 1 or g.out_degree(n) > 1 for n in g.nodes):
+            raise NotImplementedError("rectipy_b200: fan-in / fan-out is not supported (the reference cannot execute it "
+                                      "either, rectipy/network.py:968).")
+        path, n = [self._in_node], self._in_node
+        while g.out_degree(n) == 1:
+            n = next(iter(g.successors(n)))
+            path.append(n)
+        if len(path) != len(g.nodes) or path[-1] != self._out_node:
+            raise NotImplementedError("rectipy_b200: the graph is not a single chain from the input to the output node")
+        return path
+
+    def _run_engine_multi(self, x: torch.Tensor, S: int, cutoff: int, truncate: int, rec_specs: list, want_out: bool):
+        """Chain of several diffeq nodes: x [T,B,width] -> (out [n_rec,B,k] | None, [recorded vars], record steps)."""
+        path = self._get_path()
+        T = x.shape[0]
+        steps = _record_steps(T, S, cutoff)
+        series = x
+        per_node: Dict[str, list] = {}
+        for name, vi, red in rec_specs:
+            per_node.setdefault(name, []).append((vi, red))
+        got: Dict[Tuple[str, int, int], torch.Tensor] = {}
+        for i, name in enumerate(path):
+            if i > 0:
+                series = series @ self.get_edge(path[i - 1], name).effective_weights().T
+            node = self.get_node(name)
+            if self[name]["node_type"] == "diff_eq":
+                want = per_node.get(name, [])
+                # per-step PRE-update outputs (nodes.py:170,392) and per-step state records; windows are applied at the end
+                out, recs = _engine_call(node, series.contiguous(), abi.RP_IN_DENSE, None, abi.RP_OUT_DENSE, None, T, 1, 0,
+                                         truncate, tuple(v for v, _ in want), tuple(r for _, r in want), True)
+                for (vi, red), r in zip(want, recs):
+                    got[(name, vi, red)] = r
+                series = out
+            else:
+                series = node.apply_batched(series)
+        out = _window_mean(series, S, cutoff) if want_out else None
+        idx = torch.as_tensor(steps, dtype=torch.long, device=x.device)
+        recs = [got[key].index_select(0, idx) for key in rec_specs]
+        return out, recs, steps
+
     # ---- engine dispatch -----------------------------------------------------------------------------------
     def _prepare_inputs(self, inputs, T_axis: bool = True) -> torch.Tensor:
         """-> float32 device tensor [T, B, width]."""
-        chain = self._get_chain()
-        node: RateNet = self.get_node(chain.diffeq)
+        if self._is_multi():
+            first = self._get_path()[0]
+            fnode = self.get_node(first)
+            dnode = next(self.get_node(n) for n in self._get_path() if self[n]["node_type"] == "diff_eq")
+            node, width, has_in_func = dnode, (fnode.n if self[first]["node_type"] == "diff_eq" else self[first]["n_in"]), \
+                self[first]["node_type"] != "diff_eq"
+        else:
+            chain = self._get_chain()
+            node = self.get_node(chain.diffeq)
+            width = self[chain.in_func]["n_in"] if chain.in_func is not None else node.n
+            has_in_func = chain.in_func is not None
         x = inputs
         if not isinstance(x, torch.Tensor):
             x = torch.as_tensor(np.asarray(x), dtype=torch.float32)
         x = x.to(device=node.device, dtype=torch.float32, non_blocking=True)
-        width = self[chain.in_func]["n_in"] if chain.in_func is not None else node.n
         if x.dim() == 1:
             x = x.reshape(-1, 1) if T_axis else x.reshape(1, -1)
         if x.dim() == 2:
@@ -382,7 +446,7 @@ class Network:
         if x.shape[1] != node.batch:
             raise RuntimeError(f"inputs carry {x.shape[1]} trials but the network was built with batch={node.batch}")
         if x.shape[2] != width:
-            if x.shape[2] == 1 and chain.in_func is None:
+            if x.shape[2] == 1 and not has_in_func:
                 x = x.expand(x.shape[0], x.shape[1], width)
             else:
                 raise RuntimeError(f"Input dimensionality {x.shape[2]} does not match the network input size {width}.")
@@ -390,6 +454,8 @@ class Network:
 
     def _run_engine(self, x: torch.Tensor, S: int, cutoff: int, truncate: int, rec_specs: list, want_out: bool):
         """x [T,B,width] -> (out [n_rec,B,k] | None, [recorded vars], record steps)."""
+        if self._is_multi():
+            return self._run_engine_multi(x, S, cutoff, truncate, rec_specs, want_out)
         chain = self._get_chain()
         node: RateNet = self.get_node(chain.diffeq)
         T = x.shape[0]
@@ -431,6 +497,16 @@ class Network:
         return out, recs, steps
 
     def _rec_specs(self, obs: Observer) -> list:
+        if self._is_multi():          # (node, variable index, reduce) for every recorded variable of any diffeq node of the chain
+            specs = []
+            for (n, v), red in zip(obs.recorded_state_variables, obs.reduce_flags):
+                if n not in self.graph.nodes or self[n]["node_type"] != "diff_eq":
+                    raise KeyError(f"Variable {v} can only be recorded from a differential-equation node (got node {n}).")
+                try:
+                    specs.append((n, self.get_node(n).var_index(self._relabel_var(v)), int(red)))
+                except KeyError:
+                    raise KeyError(f"Variable {v} was not found on node {n}.")
+            return specs
         chain = self._get_chain()
         specs = []
         for (n, v), red in zip(obs.recorded_state_variables, obs.reduce_flags):
@@ -452,6 +528,12 @@ class Network:
     # ---- forward / run ---------------------------------------------------------------------------------------
     def forward(self, x) -> torch.Tensor:
         """One integration step of the whole network (rectipy/network.py:462-478); returns the network output."""
+        if self._is_multi():
+            xt = self._prepare_inputs(x, T_axis=False)
+            if xt.shape[0] != 1:
+                raise RuntimeError("Network.forward expects the input of a single step")
+            out, _, _ = self._run_engine_multi(xt, 1, 0, 0, [], True)
+            return self._squeeze(out[0:1])[0] if self.batch == 1 else out[0]
         chain = self._get_chain()
         node = self.get_node(chain.diffeq)
         xt = self._prepare_inputs(x, T_axis=False)
@@ -562,7 +644,7 @@ class Network:
         y0 = self.state
         epochs = len(inp)
         epoch_losses = []
-        dev = self.get_node(self._get_chain().diffeq).device
+        dev = self._engine_device()
         for epoch in range(epochs):
             obs = self.run(inp[epoch], verbose=False, sampling_steps=sampling_steps, enable_grad=True, **kwargs)
             tgt = torch.as_tensor(np.asarray(target[epoch]) if not isinstance(target[epoch], torch.Tensor) else target[epoch],

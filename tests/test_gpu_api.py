@@ -166,3 +166,48 @@ def test_truncated_bptt_array_mode_runs():
                        update_steps=50, sampling_steps=10, verbose=False)
     assert len(obs["steps"]) == 30 and len(obs["loss"]) == 30
     assert not torch.equal(w0, net.get_node("rnn")["weights"].detach())
+
+
+def test_two_node_feed_forward_chain_matches_reference():
+    """inp -> Linear -> LI-tanh -> Linear -> QIF -> Linear -> out: the reference executes such chains node by node inside its
+    step loop (network.py:962-973); here every node is one whole-horizon engine call and autograd chains them.  Records of
+    both nodes, the window means and ALL gradients (two recurrent matrices, tau, eta, three edges) vs the fixture generated
+    by the reference's own Network (oracle/make_golden.py::save_two_node_chain)."""
+    import ast
+    import os
+    import rectipy_b200 as rp
+    from golden_util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "two_node_chain.npz"))
+    m = ast.literal_eval(str(z["meta"]))
+    net = rp.Network(m["dt"], device="cuda:0")
+    rate = net.add_diffeq_node("rate", "neuron_model_templates.rate_neurons.leaky_integrator.tanh", weights=z["in_W1"],
+                               source_var="tanh_op/r", target_var="li_op/r_in", input_var="li_op/I_ext", output_var="li_op/v",
+                               node_vars={"li_op/tau": z["p1_tau"], "li_op/k": m["p1_k"], "li_op/eta": m["p1_eta"]},
+                               train_params=["weights", "li_op/tau"])
+    spk = net.add_diffeq_node("spk", "neuron_model_templates.spiking_neurons.qif.qif", weights=z["in_W2"], source_var="s",
+                              target_var="s_in", input_var="I_ext", output_var="s", spike_var="spike", reset_var="v", op="qif_op",
+                              node_vars={"eta": z["p2_eta"], "k": m["p2_k"], "tau_s": m["p2_tau_s"]}, train_params=["weights", "eta"])
+    net.add_func_node("inp", m["m"], "identity"); net.add_func_node("out", m["k"], "identity")
+    net.add_edge("inp", "rate", weights=z["in_w_in"], train="gd")
+    net.add_edge("rate", "spk", weights=z["in_w12"], train="gd")
+    net.add_edge("spk", "out", weights=z["in_w_out"], train="gd")
+    obs = net.run(z["in_inputs"], sampling_steps=m["S"], cutoff=m["cutoff"], verbose=False, enable_grad=True,
+                  record_vars=[("rate", "v", False), ("spk", "s", True)])
+    out = torch.stack(obs["out"])
+    loss = torch.nn.functional.mse_loss(out, torch.tensor(z["in_targets"], dtype=torch.float32, device="cuda"))
+    loss.backward()
+    ref = {k[len("float64_"):]: z[k] for k in z.files if k.startswith("float64_")}
+    tol32 = lambda key: 10.0 * max(rel_err(z["float32_" + key], ref[key]), 1e-6)      # as close to fp64 as the reference's own fp32 run (x10)
+    assert list(np.asarray(obs["steps"])) == list(ref["steps"])
+    assert rel_err(out.detach().cpu().numpy(), ref["out"]) <= tol32("out")
+    assert rel_err(obs.to_numpy(("rate", "v")), ref["var_rate_v"]) <= tol32("var_rate_v")
+    assert rel_err(obs.to_numpy(("spk", "s")), ref["var_spk_s"]) <= tol32("var_spk_s")
+    assert abs(float(loss.detach()) - float(ref["loss"])) <= 1e-4 * abs(float(ref["loss"]))
+    got = dict(grad_W1=rate["weights"].grad, grad_tau1=rate["li_op/tau"].grad, grad_W2=spk["weights"].grad, grad_eta2=spk["eta"].grad,
+               grad_w_in=net.get_edge("inp", "rate").weights.grad, grad_w12=net.get_edge("rate", "spk").weights.grad,
+               grad_w_out=net.get_edge("spk", "out").weights.grad)
+    for key, g in got.items():
+        assert rel_err(g.cpu().numpy().reshape(ref[key].shape), ref[key]) <= tol32(key), key
+    # single steps through the whole chain keep working (user loops / fit_rls style)
+    o1 = net.forward(z["in_inputs"][0])
+    assert o1.shape[-1] == m["k"] and torch.isfinite(o1).all()

@@ -235,3 +235,23 @@ def test_utilities():
     assert Cc.shape == (12, 12) and np.allclose(Cc.sum(1), 1.0)
     W = rp.input_connections(10, 8, 0.5, variance=2.0, zero_mean=True)
     assert W.shape == (10, 8) and np.allclose(W.sum(1), 0.0, atol=1e-12)
+
+
+def test_multi_node_chain_is_recognised():
+    """Feed-forward chains of several differential-equation nodes compile to a node path (no GPU needed for the matching)."""
+    import rectipy_b200 as rp
+    net = rp.Network(1e-3, device="cpu")
+    n1, n2 = 6, 5
+    net.add_diffeq_node("a", "neuron_model_templates.rate_neurons.leaky_integrator.tanh", weights=np.zeros((n1, n1)),
+                        source_var="tanh_op/r", target_var="li_op/r_in", input_var="li_op/I_ext", output_var="li_op/v")
+    net.add_diffeq_node("b", QIF, weights=np.zeros((n2, n2)), source_var="s", target_var="s_in", input_var="I_ext",
+                        output_var="s", spike_var="spike", reset_var="v", op="qif_op")
+    net.add_func_node("inp", 2, "identity"); net.add_func_node("out", 3, "sigmoid")
+    net.add_edge("inp", "a"); net.add_edge("a", "b"); net.add_edge("b", "out")
+    net.compile()
+    assert net._is_multi() and net._get_path() == ["inp", "a", "b", "out"]
+    with pytest.raises(NotImplementedError):
+        net._get_chain()                       # the fused single-node plan does not apply
+    net.add_func_node("side", 2, "identity"); net.add_edge("side", "b")
+    with pytest.raises((NotImplementedError, ValueError)):
+        net.compile(); net._get_path()        # fan-in: neither the reference nor the engine executes it
