@@ -301,6 +301,39 @@ def main(only=None):
                         rls_beta=0.98, rls_alpha=2.0)
     print("edges: ok")
 
+    # ---- G8b: stateful edges (edges.py:68-147): delay buffer, linear filter, both -- outputs of the reference classes --------
+    rng_e = np.random.default_rng(99)
+    n_in, n_out, Ts = 4, 3, 40
+    delays = np.asarray([2, 0, 1, 2])
+    filt = rng_e.standard_normal((n_in, n_in)) * 0.3
+    w = rng_e.standard_normal((n_out, n_in))
+    xs = rng_e.standard_normal((Ts, n_in))
+    blob = dict(delays=delays, filter=filt, w=w, xs=xs)
+    mem = ref.edges.LinearMemory(n_in, n_out, delays=delays, weights=w, dtype=torch.float64)
+    flt = ref.edges.LinearFilter(n_in, n_out, filter_weights=filt, weights=w, dtype=torch.float64)
+    mf = ref.edges.LinearMemoryFilter(n_in, n_out, delays=delays, filter_weights=filt, weights=w, dtype=torch.float64)
+    for name, e in (("memory", mem), ("filter", flt), ("memory_filter", mf)):
+        blob[f"{name}_out"] = np.stack([e.forward(torch.tensor(x)).detach().numpy().copy() for x in xs])
+    blob["memory_buffer"] = mem.buffer.numpy(); blob["filter_y"] = flt.y.numpy(); blob["memory_filter_buffer"] = mf.buffer.numpy()
+    # and inside a reference Network: delayed input edge -> LI-tanh node -> filtered readout edge
+    n, m, k, T, dt = 9, 3, 3, 150, 2e-2
+    W = rng_e.standard_normal((n, n)) / np.sqrt(n)
+    w_in, w_out = rng_e.standard_normal((n, m)), rng_e.standard_normal((k, n))
+    d_in = np.asarray([1, 3, 0]); f_out = rng_e.standard_normal((n, n)) * 0.2 / np.sqrt(n)
+    inputs = sin_inputs(rng_e, T, m, dt, amp=1.5)
+    func, args, var_map, param_map = orc.build_node_args("li_tanh", n, W, dict(tau=1.5, k=1.0, eta=0.1), torch.float64, "I_ext", None)
+    net = ref.Network(dt, device="cpu", dtype=torch.float64)
+    node = ref.nodes.RateNet(func, args, var_map, param_map, dt=dt, dtype=torch.float64, device="cpu")
+    net.add_node("rnn", node, node_type="diff_eq")
+    net.add_func_node("inp", m, "identity"); net.add_func_node("out", k, "identity")
+    net.add_edge("inp", "rnn", weights=w_in, delays=d_in)
+    net.add_edge("rnn", "out", weights=w_out, filter_weights=f_out)
+    obs = net.run(torch.tensor(inputs), sampling_steps=2, cutoff=3, verbose=False, enable_grad=False)
+    blob.update(net_W=W, net_w_in=w_in, net_w_out=w_out, net_d_in=d_in, net_f_out=f_out, net_inputs=inputs,
+                net_out=obs.to_numpy("out"), net_meta=np.asarray(repr(dict(n=n, m=m, k=k, T=T, dt=dt, S=2, cutoff=3, tau=1.5, k_c=1.0, eta=0.1))))
+    np.savez_compressed(os.path.join(OUT, "edges_stateful.npz"), **blob)
+    print("edges_stateful: ok", blob["memory_out"][:4, 0])
+
     # ---- G9: fit_ridge on a small reservoir (network.py:709-784) ----------------------------------
     n, T, m, k, dt = 15, 400, 3, 2, 1e-2
     W = rng.standard_normal((n, n)) / np.sqrt(n)

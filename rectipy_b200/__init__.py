@@ -8,12 +8,12 @@ fallback.
 from .network import Network
 from .observer import Observer
 from .nodes import RateNet, SpikeResetNet, InstantNode
-from .edges import Linear, LinearMasked, RLS
+from .edges import Linear, LinearFilter, LinearMasked, LinearMemory, LinearMemoryFilter, RLS
 from .utility import (random_connectivity, circular_connectivity, line_connectivity, input_connections, normalize,
                       wta_score, readout)
 from . import engine, templates, parallel
 
 __version__ = "0.1.0"
-__all__ = ["Network", "Observer", "RateNet", "SpikeResetNet", "InstantNode", "Linear", "LinearMasked", "RLS",
+__all__ = ["Network", "Observer", "RateNet", "SpikeResetNet", "InstantNode", "Linear", "LinearMasked", "LinearMemory", "LinearFilter", "LinearMemoryFilter", "RLS",
            "random_connectivity", "circular_connectivity", "line_connectivity", "input_connections", "normalize",
            "wta_score", "readout", "engine", "templates", "parallel"]

@@ -3,8 +3,9 @@
 Inside a compiled `Network` the projections are not executed here: `Network.compile` hands the edge weights to the
 engine, which fuses `W_in @ x` and `W_out @ y` into the step / observer / adjoint kernels (rp_kernels.cuh).  The
 `forward` methods below exist for the reference's stand-alone edge use (rectipy_tests/test_edges.py) and operate on
-whatever device the weights live on.  Delay/filter edges (LinearMemory, LinearFilter, LinearMemoryFilter) are out of
-scope of the engine and raise at construction time via `Network.add_edge`.
+whatever device the weights live on.  The stateful edges (LinearMemory, LinearFilter, LinearMemoryFilter: a delay buffer /
+a linear filter in front of the projection) are maps of the edge's input SERIES; `Network` applies them to the per-step
+series between two whole-horizon engine calls (`apply_series`), with the reference's per-step semantics.
 """
 from __future__ import annotations
 
@@ -24,6 +25,7 @@ class Linear:
     """`weights @ x` with weights stored `[n_out, n_in]` (rectipy/edges.py:8-65)."""
 
     _tensors = ["weights"]
+    stateful = False      # True: the edge carries state across steps (delay / filter edges) and maps a whole input series
 
     def __init__(self, n_in: int, n_out: int, weights: Union[np.ndarray, torch.Tensor] = None,
                  dtype: torch.dtype = torch.float64, detach: bool = True, **kwargs):
@@ -76,6 +78,133 @@ class Linear:
 
     def detach(self):
         pass   # the reference's Linear.detach is a no-op (edges.py:62-65)
+
+
+class _SeriesEdge(Linear):
+    """Stateful edge: `forward(x)` advances the state by one step like the reference's edge; `apply_series` does so for a
+    whole `[T, B, n_in]` series (state kept per trial, created on first use) and returns `[T, B, n_out]`."""
+
+    stateful = True
+
+    def _state_step(self, x: torch.Tensor) -> torch.Tensor:      # x [B, n_in] -> pre-projection vector [B, n_in]
+        raise NotImplementedError
+
+    def _expand_state(self, B: int) -> None:
+        raise NotImplementedError
+
+    def forward(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
+        single = x.dim() == 1
+        xb = x.reshape(1, -1) if single else x
+        self._expand_state(xb.shape[0])
+        z = self._state_step(xb)
+        out = z @ self.weights.T
+        return out[0] if single else out
+
+    def apply_series(self, x: torch.Tensor) -> torch.Tensor:
+        self._expand_state(x.shape[1])
+        w = self.weights.to(x.dtype)
+        return torch.stack([self._state_step(x[t]) @ w.T for t in range(x.shape[0])])
+
+
+class LinearMemory(_SeriesEdge):
+    """Delay buffer in front of the projection (rectipy/edges.py:68-94).  Per step the reference rolls its
+    `[n_in, max_delay+1]` buffer one column to the left, writes the input vector into the columns `delays` of EVERY row
+    (`buffer[:, delays] = x` broadcasts over rows), and projects column 0.  That literal behaviour is reproduced: column
+    `delays[j]` of all rows receives `x[j]` (the last channel wins when two channels share a delay)."""
+
+    _tensors = ["weights", "buffer", "delays"]
+
+    def __init__(self, n_in: int, n_out: int, delays: Union[np.ndarray, torch.Tensor],
+                 weights: Union[np.ndarray, torch.Tensor] = None, intrinsic_weights=None,
+                 dtype: torch.dtype = torch.float64, detach: bool = True, **kwargs):
+        if isinstance(delays, np.ndarray):
+            delays = torch.tensor(delays, dtype=torch.long)
+        if len(delays) != n_in:
+            raise ValueError("The number of delays must match the number of node inputs.")
+        self.delays = delays.to(torch.long)
+        self.buffer = torch.zeros((n_in, int(self.delays.max()) + 1), dtype=dtype)
+        train_params = kwargs.pop("train_params", ["weights"])
+        super().__init__(n_in, n_out, weights=weights, dtype=dtype, detach=detach, train_params=train_params, **kwargs)
+
+    def _writers(self):
+        """(written columns, channel whose value lands there): duplicates resolved like a sequential assignment (last wins)."""
+        d = self.delays.tolist()
+        cols = sorted(set(d))
+        winners = [max(j for j, dj in enumerate(d) if dj == c) for c in cols]
+        dev = self.buffer.device
+        return torch.tensor(cols, dtype=torch.long, device=dev), torch.tensor(winners, dtype=torch.long, device=dev)
+
+    def _expand_state(self, B: int) -> None:
+        if self.buffer.dim() == 2:
+            self.buffer = self.buffer.unsqueeze(0).repeat(B, 1, 1)
+        elif self.buffer.shape[0] != B:
+            raise RuntimeError(f"edge state holds {self.buffer.shape[0]} trials, input has {B}")
+
+    def _premix(self, buf: torch.Tensor) -> torch.Tensor:
+        return buf
+
+    def _state_step(self, x: torch.Tensor) -> torch.Tensor:
+        cols, winners = self._writers()
+        buf = self._premix(torch.roll(self.buffer.to(x.dtype), -1, dims=2)).clone()
+        buf[:, :, cols] = x[:, None, winners]
+        self.buffer = buf
+        return buf[:, :, 0]
+
+    def to(self, device: str, **kwargs):
+        super().to(device, **kwargs)
+        return self
+
+
+class LinearFilter(_SeriesEdge):
+    """Linear filter in front of the projection (rectipy/edges.py:97-120):  y <- filter @ y + x ;  out = weights @ y."""
+
+    _tensors = ["weights", "filter", "y"]
+
+    def __init__(self, n_in: int, n_out: int, filter_weights: Union[np.ndarray, torch.Tensor],
+                 weights: Union[np.ndarray, torch.Tensor] = None, dtype: torch.dtype = torch.float64,
+                 detach: bool = True, **kwargs):
+        if isinstance(filter_weights, np.ndarray):
+            filter_weights = torch.tensor(filter_weights, dtype=dtype)
+        if filter_weights.shape[0] != n_in or filter_weights.shape[1] != n_in:
+            raise ValueError("Intrinsic weights have to be a square matrix with the number of rows and columns matching"
+                             "the number of inputs to the edge.")
+        self.filter = filter_weights.to(dtype)
+        self.y = torch.zeros(n_in, dtype=dtype)
+        train_params = kwargs.pop("train_params", ["weights", "filter"])
+        super().__init__(n_in, n_out, weights=weights, dtype=dtype, detach=detach, train_params=train_params, **kwargs)
+
+    def _expand_state(self, B: int) -> None:
+        if self.y.dim() == 1:
+            self.y = self.y.unsqueeze(0).repeat(B, 1)
+        elif self.y.shape[0] != B:
+            raise RuntimeError(f"edge state holds {self.y.shape[0]} trials, input has {B}")
+
+    def _state_step(self, x: torch.Tensor) -> torch.Tensor:
+        self.y = self.y.to(x.dtype) @ self.filter.to(x.dtype).T + x
+        return self.y
+
+
+class LinearMemoryFilter(LinearMemory):
+    """Delay buffer whose rows are mixed by a filter matrix at every step (rectipy/edges.py:123-147):
+    buffer <- filter @ roll(buffer) ; buffer[:, delays] = x ; out = weights @ buffer[:, 0]."""
+
+    _tensors = ["weights", "buffer", "delays", "filter"]
+
+    def __init__(self, n_in: int, n_out: int, delays: Union[np.ndarray, torch.Tensor],
+                 filter_weights: Union[np.ndarray, torch.Tensor], weights: Union[np.ndarray, torch.Tensor] = None,
+                 dtype: torch.dtype = torch.float64, detach: bool = True, **kwargs):
+        if isinstance(filter_weights, np.ndarray):
+            filter_weights = torch.tensor(filter_weights, dtype=dtype)
+        if filter_weights.shape[0] != n_in or filter_weights.shape[1] != n_in:
+            raise ValueError("Intrinsic weights have to be a square matrix with the number of rows and columns matching"
+                             "the number of inputs to the edge.")
+        self.filter = filter_weights.to(dtype)
+        train_params = kwargs.pop("train_params", ["weights", "filter"])
+        super().__init__(n_in, n_out, delays=delays, weights=weights, dtype=dtype, detach=detach,
+                         train_params=train_params, **kwargs)
+
+    def _premix(self, buf: torch.Tensor) -> torch.Tensor:
+        return torch.matmul(self.filter.to(buf.dtype), buf)      # [n_in, n_in] @ [B, n_in, D+1]
 
 
 class LinearMasked(Linear):

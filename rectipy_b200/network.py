@@ -22,7 +22,7 @@ from networkx import DiGraph
 
 from . import _cabi as abi
 from . import engine
-from .edges import RLS, Linear, LinearMasked
+from .edges import RLS, Linear, LinearFilter, LinearMasked, LinearMemory, LinearMemoryFilter
 from .nodes import InstantNode, RateNet, SpikeResetNet, node_from_template
 from .observer import Observer
 from .utility import add_op_name, retrieve_from_dict
@@ -266,10 +266,12 @@ class Network:
         """Add a linear projection between two nodes (rectipy/network.py:340-400)."""
         if not edge_attrs:
             edge_attrs = {}
-        if "delays" in kwargs or "filter_weights" in kwargs:
-            raise NotImplementedError("rectipy_b200: delay / filter edges (LinearMemory, LinearFilter) are outside the "
-                                      "engine's hot path and not implemented")
-        LinEdge = LinearMasked if "mask" in kwargs else Linear
+        if "delays" in kwargs:                      # same selection rule as rectipy/network.py:375-383
+            LinEdge = LinearMemoryFilter if "filter_weights" in kwargs else LinearMemory
+        elif "filter_weights" in kwargs:
+            LinEdge = LinearFilter
+        else:
+            LinEdge = LinearMasked if "mask" in kwargs else Linear
         kwargs.update({"n_in": self[source]["n_out"], "n_out": self[target]["n_in"], "weights": weights,
                        "dtype": self.dtype})
         trainable = True
@@ -368,7 +370,10 @@ class Network:
 
     # ---- feed-forward chains of several differential-equation nodes ------------------------------------------
     def _is_multi(self) -> bool:
-        return sum(1 for n in self.graph.nodes if self[n]["node_type"] == "diff_eq") > 1
+        """True when the graph runs node by node on per-step series: several diffeq nodes, or a stateful (delay / filter) edge."""
+        if sum(1 for n in self.graph.nodes if self[n]["node_type"] == "diff_eq") > 1:
+            return True
+        return any(getattr(self.graph[s][t]["edge"], "stateful", False) for s, t in self.graph.edges)
 
     def _get_path(self) -> List[str]:
         """Nodes from the input node to the output node when the graph is one simple path (every graph the reference's
@@ -402,7 +407,8 @@ class Network:
         got: Dict[Tuple[str, int, int], torch.Tensor] = {}
         for i, name in enumerate(path):
             if i > 0:
-                series = series @ self.get_edge(path[i - 1], name).effective_weights().T
+                edge = self.get_edge(path[i - 1], name)
+                series = edge.apply_series(series) if edge.stateful else series @ edge.effective_weights().T
             node = self.get_node(name)
             if self[name]["node_type"] == "diff_eq":
                 want = per_node.get(name, [])

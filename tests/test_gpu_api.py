@@ -211,3 +211,24 @@ def test_two_node_feed_forward_chain_matches_reference():
     # single steps through the whole chain keep working (user loops / fit_rls style)
     o1 = net.forward(z["in_inputs"][0])
     assert o1.shape[-1] == m["k"] and torch.isfinite(o1).all()
+
+
+def test_delay_and_filter_edges_in_a_network():
+    """inp --LinearMemory(delays)--> LI-tanh --LinearFilter--> out, window means with cutoff: the reference's own Network output
+    (tests/golden/edges_stateful.npz).  The stateful edges map the per-step series on either side of the engine call."""
+    import ast
+    import os
+    import rectipy_b200 as rp
+    from golden_util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "edges_stateful.npz"))
+    m = ast.literal_eval(str(z["net_meta"]))
+    net = rp.Network(m["dt"], device="cuda:0")
+    net.add_diffeq_node("rnn", "neuron_model_templates.rate_neurons.leaky_integrator.tanh", weights=z["net_W"], source_var="tanh_op/r",
+                        target_var="li_op/r_in", input_var="li_op/I_ext", output_var="li_op/v",
+                        node_vars={"li_op/tau": m["tau"], "li_op/k": m["k_c"], "li_op/eta": m["eta"]})
+    net.add_func_node("inp", m["m"], "identity"); net.add_func_node("out", m["k"], "identity")
+    e_in = net.add_edge("inp", "rnn", weights=z["net_w_in"], delays=z["net_d_in"])
+    e_out = net.add_edge("rnn", "out", weights=z["net_w_out"], filter_weights=z["net_f_out"])
+    assert type(e_in).__name__ == "LinearMemory" and type(e_out).__name__ == "LinearFilter"
+    obs = net.run(z["net_inputs"], sampling_steps=m["S"], cutoff=m["cutoff"], verbose=False, enable_grad=False)
+    assert rel_err(obs.to_numpy("out"), z["net_out"]) < 1e-5

@@ -144,8 +144,10 @@ def test_edges_compile_and_parameters():
         net.add_edge("qif", "out", weights=np.random.randn(3, 3))
     with pytest.raises(ValueError):
         net.add_edge("qif", "out", train="invalid")
-    with pytest.raises(NotImplementedError):
-        net.add_edge("qif", "out", delays=np.ones(10))
+    delayed = net.add_edge("qif", "out", delays=np.ones(10, dtype=np.int64))      # edge class selection (network.py:375-383)
+    assert isinstance(delayed, rp.LinearMemory) and delayed.buffer.shape == (10, 2) and net._is_multi()
+    with pytest.raises(ValueError):
+        net.add_edge("qif", "out", delays=np.ones(4, dtype=np.int64))             # one delay per source output
     masked = net.add_edge("inp", "qif", weights=np.ones((10, 3)), mask=np.eye(10, 3))
     assert isinstance(masked, rp.LinearMasked) and float(masked.effective_weights().sum()) == 3.0
     rls = net.add_edge("qif", "out", train="rls", alpha=2.0, beta=0.9)
@@ -255,3 +257,28 @@ def test_multi_node_chain_is_recognised():
     net.add_func_node("side", 2, "identity"); net.add_edge("side", "b")
     with pytest.raises((NotImplementedError, ValueError)):
         net.compile(); net._get_path()        # fan-in: neither the reference nor the engine executes it
+
+
+def test_stateful_edges_match_reference_fixture():
+    """LinearMemory / LinearFilter / LinearMemoryFilter (rectipy/edges.py:68-147): 40 steps of the reference classes' outputs
+    (tests/golden/edges_stateful.npz, oracle/make_golden.py G8b), step by step and as a batched series."""
+    import os
+    from golden_util import GOLDEN
+    from rectipy_b200.edges import LinearMemory, LinearFilter, LinearMemoryFilter
+    z = np.load(os.path.join(GOLDEN, "edges_stateful.npz"))
+    n_in, n_out = z["w"].shape[1], z["w"].shape[0]
+    makers = {"memory": lambda: LinearMemory(n_in, n_out, delays=z["delays"], weights=z["w"], dtype=torch.float64),
+              "filter": lambda: LinearFilter(n_in, n_out, filter_weights=z["filter"], weights=z["w"], dtype=torch.float64),
+              "memory_filter": lambda: LinearMemoryFilter(n_in, n_out, delays=z["delays"], filter_weights=z["filter"], weights=z["w"],
+                                                          dtype=torch.float64)}
+    for name, mk in makers.items():
+        e = mk()
+        out = np.stack([e.forward(torch.tensor(x)).detach().numpy() for x in z["xs"]])
+        assert np.abs(out - z[f"{name}_out"]).max() < 1e-13, name
+        series = mk().apply_series(torch.tensor(z["xs"])[:, None, :].repeat(1, 3, 1)).numpy()
+        for b in range(3):
+            assert np.abs(series[:, b] - z[f"{name}_out"]).max() < 1e-13, (name, b)
+    with pytest.raises(ValueError):
+        LinearMemory(n_in, n_out, delays=np.asarray([0, 1]), weights=z["w"])
+    with pytest.raises(ValueError):
+        LinearFilter(n_in, n_out, filter_weights=np.zeros((n_in, n_in + 1)), weights=z["w"])
