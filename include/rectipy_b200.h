@@ -23,7 +23,7 @@
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises the host.
  *   - Every entry point returns 0 on success, non-zero on error; rp_last_error() gives a thread-local message.
  *   - State layout ("SoA planes"): y[var][trial][neuron], var in {0:v, 1:s, 2:x}; plane stride = batch*n.
- *     (ik_op: plane 2 holds the recovery variable u.)
+ *     (ik_op / iku_op: plane 2 holds the recovery variable u; ik_biexp_op: planes v, s, u, x.)
  *   - A plan is not re-entrant: one host thread / one stream at a time per plan.
  */
 #ifndef RECTIPY_B200_H
@@ -33,15 +33,17 @@
 extern "C" {
 #endif
 
-#define RP_ABI_VERSION 5
+#define RP_ABI_VERSION 6
 #define RP_MAX_IN 8      /* max fused input-projection width  m (wider inputs: use RP_IN_DENSE)  */
 #define RP_MAX_OUT 8     /* max fused readout width           k (wider readouts: use RP_OUT_DENSE) */
-#define RP_MAX_SV 3
+#define RP_MAX_SV 4
 #define RP_MAX_REC 4
 
 /* vector fields (neuron_model_templates/rate_neurons/leaky_integrator.yaml, spiking_neurons/{qif,lif}.yaml) */
 enum { RP_LI_TANH = 0, RP_LI_SIGMOID = 1, RP_QIF = 2, RP_QIF_SFA = 3, RP_LIF = 4, RP_IK = 5 /* spiking_neurons/ik.yaml ik_op */,
-       RP_IKU = 6 /* ik.yaml iku_op: recovery variable driven by the per-trial population means of v and of the spikes */ };
+       RP_IKU = 6 /* ik.yaml iku_op: recovery variable driven by the per-trial population means of v and of the spikes */,
+       RP_IK_BIEXP = 7 /* ik.yaml:42-70 ik_biexp_op: iku_op with a bi-exponential synapse s' = -s/tau_d + x, x' = -x/tau_r + spike;
+                          tau_d travels in slot RP_P_TAU_S, tau_r in slot RP_P_TAU_X */ };
 /* parameter slots; each is a device pointer to 1, n, B or B*n floats (see rp_desc.param_per_neuron) */
 enum { RP_P_TAU = 0, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_RMAX, RP_P_SIG_S, RP_P_V0,
        /* ik_op: */ RP_P_C, RP_P_VR, RP_P_VTH, RP_P_G, RP_P_ER, RP_P_B, RP_P_TAU_U, RP_P_KAPPA, RP_NUM_PARAMS };
@@ -88,7 +90,7 @@ typedef struct rp_fwd_args {
     float* yT;              /* [n_sv,B,n] state after T steps                                   */
     float* out_rec;         /* [n_rec,B,k] | [n_rec,B,n] window means of the output, or NULL    */
     int n_rec_vars;
-    int rec_var[RP_MAX_REC];     /* RP_VAR_V/S/X                                                */
+    int rec_var[RP_MAX_REC];     /* state plane index 0..n_sv-1 (RP_VAR_V/S/X, 3: ik_biexp_op x)  */
     int rec_reduce[RP_MAX_REC];  /* 1: mean over neurons -> [n_rec,B]; 0: [n_rec,B,n]           */
     float* rec_buf[RP_MAX_REC];
     float* history;         /* [(T+1),n_hist,B,n] state checkpoints for rp_backward (n_hist = rp_num_history_planes), or NULL */
@@ -123,7 +125,7 @@ typedef struct rp_bwd_args {
 
 int         rp_abi_version(void);
 const char* rp_last_error(void);
-int         rp_num_state_vars(int model);                       /* LI 1, QIF/LIF 2, QIF-SFA/IK 3 */
+int         rp_num_state_vars(int model);                       /* LI 1, QIF/LIF 2, QIF-SFA/IK/IKU 3, IK_BIEXP 4 */
 int         rp_num_history_planes(int model);                   /* planes per checkpoint slot: n_sv (+1 for ik: the recurrent drive) */
 int         rp_num_records(int T, int sampling_steps, int cutoff); /* records produced by a run  */
 

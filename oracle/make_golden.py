@@ -150,6 +150,68 @@ def save_two_node_chain(ref):
     print("two_node_chain: out", blob["float64_out"].shape, "max mean-s", float(blob["float64_var_spk_s"].max()))
 
 
+def save_feedback_net(ref):
+    """G10: the reference's own `FeedbackNetwork` (rectipy/network.py:1196-1357; documentation/rnn_tryout.py):
+    inp -> Linear -> p1 -> Linear -> p2 -> Linear -> out  plus a FEEDBACK edge p2 -> p1, BPTT through both nodes and all four edges.
+    Variant A: p1 LI-tanh (RateNet, output v), p2 QIF (SpikeResetNet, output s) -- the feedback reads the spiking node's `y`, which
+    the reference leaves at the state BEFORE that node's last step (nodes.py:387): one step of delay.
+    Variant B: p1 QIF, p2 LI-tanh -- the feedback reads the rate node's `y`, which is its current state (nodes.py:169): no delay."""
+    rng = np.random.default_rng(5151)
+    n1, n2, m, k, T, dt, S, cutoff = 10, 8, 2, 3, 700, 1e-3, 3, 4
+    blob = {}
+    for variant in ("A", "B"):
+        nr, nq = (n1, n2) if variant == "A" else (n2, n1)          # rate / spiking population sizes
+        Wr = rng.standard_normal((nr, nr)) * 1.5 / np.sqrt(nr)
+        Wq = rng.standard_normal((nq, nq)) * 2.0 / np.sqrt(nq)
+        pr = dict(tau=rng.uniform(0.02, 0.05, nr), k=1.2, eta=0.3)
+        pq = dict(eta=orc.lorentzian_etas(nq) + 20.0, k=1.5, tau_s=0.7)
+        if variant == "A":
+            w_in, w12, wfb = rng.standard_normal((n1, m)), rng.standard_normal((n2, n1)) * 8.0, rng.standard_normal((n1, n2)) * 0.5
+        else:
+            w_in, w12, wfb = rng.standard_normal((n1, m)) * 8.0, rng.standard_normal((n2, n1)) * 0.3, rng.standard_normal((n1, n2)) * 6.0
+        w_out = rng.standard_normal((k, n2)) / np.sqrt(n2)
+        inputs = sin_inputs(rng, T, m, dt, amp=3.0, offset=1.0)
+        targets = rng.standard_normal((len([t for t in range(T) if t >= cutoff and t % S == 0]), k))
+        pre = f"{variant}_"
+        blob.update({pre + "in_Wr": Wr, pre + "in_Wq": Wq, pre + "in_w_in": w_in, pre + "in_w12": w12, pre + "in_wfb": wfb, pre + "in_w_out": w_out,
+                     pre + "in_inputs": inputs, pre + "in_targets": targets, pre + "pr_tau": np.asarray(pr["tau"]), pre + "pq_eta": np.asarray(pq["eta"])})
+        for dn in ("float64", "float32"):
+            dtype = TD[dn]
+            net = ref.FeedbackNetwork(dt, device="cpu")
+            net.dtype = dtype                      # FeedbackNetwork.__init__ does not forward a dtype (network.py:1198-1200)
+            fr, ar, vmr, pmr = orc.build_node_args("li_tanh", nr, Wr, pr, dtype, "I_ext", None)
+            rate = ref.nodes.RateNet(fr, ar, vmr, pmr, dt=dt, dtype=dtype, train_params=["weights", "tau"], device="cpu")
+            fq, aq, vmq, pmq = orc.build_node_args("qif", nq, Wq, pq, dtype, "I_ext", None)
+            spk = ref.nodes.SpikeResetNet(fq, aq, vmq, pmq, dt=dt, dtype=dtype, train_params=["weights", "eta"], device="cpu")
+            first, second = (("rate", rate), ("spk", spk)) if variant == "A" else (("spk", spk), ("rate", rate))
+            net.add_node(first[0], first[1], node_type="diff_eq")
+            net.add_node(second[0], second[1], node_type="diff_eq")
+            net.add_func_node("inp", m, "identity"); net.add_func_node("out", k, "identity")
+            net.add_edge("inp", first[0], weights=w_in, train="gd")
+            net.add_edge(first[0], second[0], weights=w12, train="gd")
+            net.add_edge(second[0], "out", weights=w_out, train="gd")
+            net.add_edge(second[0], first[0], weights=wfb, train="gd", feedback=True)
+            obs = net.run(torch.tensor(inputs, dtype=dtype), sampling_steps=S, cutoff=cutoff, verbose=False, enable_grad=True,
+                          record_vars=[("rate", "v", False), ("spk", "s", True)])
+            out = torch.stack(obs["out"])
+            loss = torch.nn.MSELoss()(out, torch.tensor(targets, dtype=dtype))
+            loss.backward()
+            res = dict(out=out.detach().numpy(), steps=np.asarray(obs["steps"]), var_rate_v=obs.to_numpy(("rate", "v")),
+                       var_spk_s=obs.to_numpy(("spk", "s")), loss=loss.detach().numpy(),
+                       grad_Wr=rate["weights"].grad.numpy(), grad_tau=rate["tau"].grad.numpy(),
+                       grad_Wq=spk["weights"].grad.numpy(), grad_eta=spk["eta"].grad.numpy(),
+                       grad_w_in=net.get_edge("inp", first[0]).weights.grad.numpy(), grad_w12=net.get_edge(first[0], second[0]).weights.grad.numpy(),
+                       grad_wfb=net.get_edge(second[0], first[0]).weights.grad.numpy(),
+                       grad_w_out=net.get_edge(second[0], "out").weights.grad.numpy())
+            for kk, v in res.items():
+                blob[f"{pre}{dn}_{kk}"] = v
+        print(f"feedback_net {variant}: out", blob[pre + "float64_out"].shape, "max mean-s", float(blob[pre + "float64_var_spk_s"].max()),
+              "|grad_wfb|", float(np.abs(blob[pre + "float64_grad_wfb"]).max()),
+              "fp32 vs fp64 out", float(np.abs(blob[pre + "float32_out"] - blob[pre + "float64_out"]).max()))
+    blob["meta"] = np.asarray(repr(dict(n1=n1, n2=n2, m=m, k=k, T=T, dt=dt, S=S, cutoff=cutoff, pr_k=1.2, pr_eta=0.3, pq_k=1.5, pq_tau_s=0.7)))
+    np.savez_compressed(os.path.join(OUT, "feedback_net.npz"), **blob)
+
+
 def sin_inputs(rng, T, m, dt, amp=1.0, offset=0.0):
     t = np.arange(T) * dt
     freqs = rng.uniform(0.5, 3.0, size=m)
@@ -158,7 +220,7 @@ def sin_inputs(rng, T, m, dt, amp=1.0, offset=0.0):
 
 
 def main(only=None):
-    """`only`: regenerate a single case that has its own random stream (currently: ik_bptt, iku_bptt)."""
+    """`only`: regenerate a single case that has its own random stream (currently: ik_bptt, iku_bptt, ik_biexp_bptt, two_node_chain, feedback_net)."""
     ref = ref_shim.import_reference()
     if only is not None:
         global save_case
@@ -265,8 +327,25 @@ def main(only=None):
     spec["targets"] = rng.standard_normal((len(range(0, T, 2)), k))
     if only in (None, "iku_bptt"):
         save_case(ref, "iku_bptt", spec)
+    # ---- G6d: Izhikevich neurons with a bi-exponential synapse (ik.yaml:42-70, ik_biexp_op: 4 state variables v, u, s, x), BPTT ----
+    rng = np.random.default_rng(779)
+    n, T, m, k, dt = 16, 1000, 2, 2, 1e-1
+    spec = dict(model="ik_biexp", n=n, T=T, dt=dt, S=2, cutoff=0, grad=True,
+                W=np.abs(rng.standard_normal((n, n))) * 4.0 / n,
+                params=dict(eta=rng.uniform(60.0, 160.0, n), g=1.5, kappa=rng.uniform(5.0, 15.0, n), tau_d=rng.uniform(5.0, 7.0, n), tau_r=2.0,
+                            E_r=0.0, b=rng.uniform(-3.0, -1.0, n), tau_u=33.33, k=0.7, C=100.0),
+                train_params=["weights", "eta", "g", "kappa", "tau_d", "tau_r", "b", "tau_u", "C", "k", "E_r"], train_in=True, train_out=True,
+                w_in=rng.standard_normal((n, m)) * 10.0, w_out=rng.standard_normal((k, n)) / np.sqrt(n),
+                inputs=sin_inputs(rng, T, m, dt * 1e-2, amp=3.0, offset=1.0),
+                spike_kwargs=dict(spike_threshold=40.0, spike_reset=-60.0),
+                record_vars=[("v", False), ("u", True), ("s", False), ("x", False)])
+    spec["targets"] = rng.standard_normal((len(range(0, T, 2)), k))
+    if only in (None, "ik_biexp_bptt"):
+        save_case(ref, "ik_biexp_bptt", spec)
     if only in (None, "two_node_chain"):
         save_two_node_chain(ref)
+    if only in (None, "feedback_net"):
+        save_feedback_net(ref)
     rng = rng_main
 
     # ---- G7: output activation + masked input edge (LinearMasked, edges.py:150-174) ---------------

@@ -128,6 +128,21 @@ def field_iku(n: int) -> Tuple[Callable, List[str]]:
     return f, names
 
 
+def field_ik_biexp(n: int) -> Tuple[Callable, List[str]]:
+    """ik_biexp_op (spiking_neurons/ik.yaml:42-70): iku_op with a bi-exponential synapse,
+    s' = -s/tau_d + x ;  x' = -x/tau_r + spike.   State order = equation order: v, u, s, x."""
+    names = ["weights", "C", "k", "v_r", "v_theta", "eta", "g", "E_r", "b", "tau_u", "kappa", "tau_d", "tau_r", "I_ext", "spike"]
+
+    def f(t, y, weights, C, k, v_r, v_theta, eta, g, E_r, b, tau_u, kappa, tau_d, tau_r, I_ext, spike):
+        v, u, s, x = y[:n], y[n:2 * n], y[2 * n:3 * n], y[3 * n:4 * n]
+        dv = (k * (v - v_r) * (v - v_theta) - u + I_ext + eta + g * (weights @ s) * (E_r - v)) / C
+        du = (b * (torch.mean(v) - v_r) - u) / tau_u + kappa * torch.mean(spike)
+        ds = -s / tau_d + x
+        dx = -x / tau_r + spike
+        return torch.cat((dv, du, ds, dx), 0)
+    return f, names
+
+
 #: template defaults (leaky_integrator.yaml:12-17,24-28; qif.yaml:13-22,33-35; lif.yaml:17-23)
 DEFAULTS = {
     "li_tanh":    dict(tau=10.0, k=1.0, eta=0.0),
@@ -137,6 +152,7 @@ DEFAULTS = {
     "lif":        dict(tau=10.0, k=1.0, tau_s=0.5, eta=0.0),
     "ik":         dict(C=100.0, k=0.7, v_r=-60.0, v_theta=-40.0, eta=0.0, g=1.0, E_r=0.0, b=-2.0, tau_u=33.33, kappa=10.0, tau_s=6.0),
     "iku":        dict(C=100.0, k=0.7, v_r=-60.0, v_theta=-40.0, eta=0.0, g=1.0, E_r=0.0, b=-2.0, tau_u=33.33, kappa=10.0, tau_s=6.0),
+    "ik_biexp":   dict(C=100.0, k=0.7, v_r=-60.0, v_theta=-40.0, eta=0.0, g=1.0, E_r=0.0, b=-2.0, tau_u=33.33, kappa=10.0, tau_d=6.0, tau_r=2.0),
 }
 #: initial values of the state variables, in state order
 INIT = {
@@ -145,8 +161,9 @@ INIT = {
     "lif": [("v", 0.0), ("s", 0.0)],
     "ik": [("v", -60.0), ("u", 0.0), ("s", 0.0)],
     "iku": [("v", -60.0), ("u", 0.0), ("s", 0.0)],
+    "ik_biexp": [("v", -60.0), ("u", 0.0), ("s", 0.0), ("x", 0.0)],
 }
-SPIKING = {"qif", "qif_sfa", "lif", "ik", "iku"}
+SPIKING = {"qif", "qif_sfa", "lif", "ik", "iku", "ik_biexp"}
 
 
 def build_field(model: str, n: int):
@@ -164,6 +181,8 @@ def build_field(model: str, n: int):
         return field_ik(n)
     if model == "iku":
         return field_iku(n)
+    if model == "ik_biexp":
+        return field_ik_biexp(n)
     raise ValueError(model)
 
 

@@ -9,9 +9,9 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-RP_ABI_VERSION = 5
-RP_MAX_IN, RP_MAX_OUT, RP_MAX_SV, RP_MAX_REC = 8, 8, 3, 4
-RP_LI_TANH, RP_LI_SIGMOID, RP_QIF, RP_QIF_SFA, RP_LIF, RP_IK, RP_IKU = range(7)
+RP_ABI_VERSION = 6
+RP_MAX_IN, RP_MAX_OUT, RP_MAX_SV, RP_MAX_REC = 8, 8, 4, 4
+RP_LI_TANH, RP_LI_SIGMOID, RP_QIF, RP_QIF_SFA, RP_LIF, RP_IK, RP_IKU, RP_IK_BIEXP = range(8)
 (RP_P_TAU, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_RMAX, RP_P_SIG_S, RP_P_V0,
  RP_P_C, RP_P_VR, RP_P_VTH, RP_P_G, RP_P_ER, RP_P_B, RP_P_TAU_U, RP_P_KAPPA, RP_NUM_PARAMS) = range(18)
 RP_IN_NONE, RP_IN_DENSE, RP_IN_PROJ = range(3)

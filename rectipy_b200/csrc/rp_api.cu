@@ -45,6 +45,7 @@ inline int nsv_of(int model) {
         case RP_LI_TANH: case RP_LI_SIGMOID: return 1;
         case RP_QIF: case RP_LIF: return 2;
         case RP_QIF_SFA: case RP_IK: case RP_IKU: return 3;
+        case RP_IK_BIEXP: return 4;
         default: return -1;
     }
 }
@@ -114,6 +115,7 @@ int check_params(const rp_plan* p, const float* const* params) {
     if (rp::is_ik(p->d.model)) {
         static const int need_ik[] = {RP_P_C, RP_P_K, RP_P_VR, RP_P_VTH, RP_P_ETA, RP_P_G, RP_P_ER, RP_P_B, RP_P_TAU_U, RP_P_KAPPA, RP_P_TAU_S};
         for (int q : need_ik) if (!params[q]) return fail("ik_op parameter slot %d is NULL", q);
+        if (p->d.model == RP_IK_BIEXP && !params[RP_P_TAU_X]) return fail("ik_biexp_op parameter tau_r (slot RP_P_TAU_X) is NULL");
         return 0;
     }
     static const int need_li[] = {RP_P_TAU, RP_P_K, RP_P_ETA};
@@ -178,6 +180,7 @@ int gemm_fp32(rp_plan* plan, bool kmajor, int P, int Q, int K, const float* A, i
         case RP_LIF:        { constexpr int M_ = RP_LIF;        __VA_ARGS__; } break; \
         case RP_IK:         { constexpr int M_ = RP_IK;         __VA_ARGS__; } break; \
         case RP_IKU:        { constexpr int M_ = RP_IKU;        __VA_ARGS__; } break; \
+        case RP_IK_BIEXP:   { constexpr int M_ = RP_IK_BIEXP;   __VA_ARGS__; } break; \
         default: return fail("unknown model id %d", model);             \
     }
 
@@ -396,7 +399,7 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
         p->ws_bytes += bytes;
     }
     if (rc) { rp_plan_destroy(p); return 1; }
-    if (d->model == RP_IKU) {
+    if (rp::is_mean_field(d->model)) {
         if (cudaMalloc(reinterpret_cast<void**>(&p->mf), (size_t)B * sizeof(float2)) != cudaSuccess ||
             cudaMalloc(reinterpret_cast<void**>(&p->asum), (size_t)B * sizeof(float2)) != cudaSuccess) {
             rp_plan_destroy(p);
@@ -405,7 +408,7 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
         p->ws_bytes += 2 * (size_t)B * sizeof(float2);
     }
     // (iku_op needs a per-step reduction over all neurons of a trial: per-step launch sequences only)
-    if (!p->use_tc && B <= rp::PS_MAX_B && d->model != RP_IKU && !getenv("RP_NO_PERSISTENT")) {
+    if (!p->use_tc && B <= rp::PS_MAX_B && !rp::is_mean_field(d->model) && !getenv("RP_NO_PERSISTENT")) {
         if (persistent_setup(p, prop)) { rp_plan_destroy(p); return 1; }
     }
     *out = p;
@@ -547,7 +550,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         }
         fa.urec_out = (rp::is_ik(d.model) && a->history) ? cur + (size_t)nsv * plane : nullptr;
         fa.mf = p->mf;
-        if (d.model == RP_IKU) {
+        if (rp::is_mean_field(d.model)) {
             rp::k_trial_means<<<B, 256, 0, st>>>(N, cur, d.theta, p->mf);
             ++p->launches;
             RP_LAUNCH_CHECK();
@@ -797,7 +800,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             const Window w = window_of(a->t_offset + t, T_tot, a->sampling_steps, a->cutoff);
             aa.y_t = a->history + (size_t)t * hslot;
             aa.urec_t = rp::is_ik(d.model) ? a->history + (size_t)t * hslot + (size_t)nsv * plane : nullptr;
-            if (d.model == RP_IKU) {
+            if (rp::is_mean_field(d.model)) {
                 // population means of y_t and of the incoming adjoint of u, one block per trial, before the element-wise adjoint
                 rp::k_trial_means<<<B, 256, 0, st>>>(N, aa.y_t, d.theta, p->mf);
                 rp::k_trial_adj_sums<<<B, 256, 0, st>>>(N, B, p->adj + 2 * plane, mp, d.dt, p->asum);
@@ -838,7 +841,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                 va.dW_out = nullptr; va.any_param_grad = 0;
                 // rolling-pipeline kernel: spiking templates whose source value is not needed here (the conversion kernel reads
                 // s_{t-1} from the checkpoint itself), enough warps for one per neuron tile
-                const bool v5 = f16 && !coresident && spk && d.model != RP_IKU && va.src == nullptr && p->sm_count * 24 >= N / 128 && !getenv("RP_NO_ADJ_V5");
+                const bool v5 = f16 && !coresident && spk && !rp::is_mean_field(d.model) && va.src == nullptr && p->sm_count * 24 >= N / 128 && !getenv("RP_NO_ADJ_V5");
                 if (v5) {
                     {
                         switch (d.model) {

@@ -232,6 +232,7 @@ struct EpiFwd {
             static_assert(NCOL % NB == 0, "trial batch must divide the per-warp column block");
             for (int c = 0; c < NCOL; c += NB) {
                 float4 u4[NB], v4[NB], s4[NB], x4[NB], xd4[NB];
+                float4 w4[NSV > 3 ? NB : 1];       // fourth state plane (ik_biexp_op)
                 float xin0[NB], xin1[NB];
 #pragma unroll
                 for (int cc = 0; cc < NB; ++cc) {
@@ -242,6 +243,7 @@ struct EpiFwd {
                     v4[cc] = ldg4(a.y_cur + idx);
                     s4[cc] = NSV > 1 ? ldg4(a.y_cur + plane + idx) : zero;
                     x4[cc] = NSV > 2 ? ldg4(a.y_cur + 2 * plane + idx) : zero;
+                    if constexpr (NSV > 3) w4[cc] = ldg4(a.y_cur + 3 * plane + idx);
                     xd4[cc] = a.in_mode == RP_IN_DENSE ? ldg4(a.x_t + idx) : zero;
                     xin0[cc] = a.in_mode == RP_IN_PROJ ? __ldg(a.x_t + (size_t)b * a.m) : 0.f;
                     xin1[cc] = (a.in_mode == RP_IN_PROJ && a.m > 1) ? __ldg(a.x_t + (size_t)b * a.m + 1) : 0.f;
@@ -250,13 +252,16 @@ struct EpiFwd {
                 for (int cc = 0; cc < NB; ++cc) {
                     const int b = q0 + cbase + c + cc;
                     const size_t idx = (size_t)b * a.N + i0;
-                    float v1[4], s1[4], x1[4], hi[4], lo[4], sr[4];
+                    float v1[4], s1[4], x1[4], w1[4], hi[4], lo[4], sr[4];
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
                         const int i = i0 + rr;
+                        w1[rr] = 0.f;
                         if constexpr (GEN) {                  // general (per-element parameter loads) path: ik, parameter sweeps
                             const float Iin = input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i);
-                            fwd_elem<MODEL>(a, i, f4get(u4[cc], rr), Iin, f4get(v4[cc], rr), f4get(s4[cc], rr), f4get(x4[cc], rr), v1[rr], s1[rr], x1[rr], b);
+                            const float wv = NSV > 3 ? f4get(w4[NSV > 3 ? cc : 0], rr) : 0.f;
+                            fwd_elem<MODEL>(a, i, f4get(u4[cc], rr), Iin, f4get(v4[cc], rr), f4get(s4[cc], rr), f4get(x4[cc], rr), v1[rr], s1[rr], x1[rr], b,
+                                            wv, &w1[rr]);
                         } else {
                             fwd_elem_fast<MODEL>(a, row[rr], i, b, f4get(u4[cc], rr), xin0[cc], xin1[cc], f4get(xd4[cc], rr),
                                                  f4get(v4[cc], rr), f4get(s4[cc], rr), f4get(x4[cc], rr), v1[rr], s1[rr], x1[rr]);
@@ -270,6 +275,7 @@ struct EpiFwd {
                     st4(a.y_next + idx, v1[0], v1[1], v1[2], v1[3]);
                     if (NSV > 1) st4(a.y_next + plane + idx, s1[0], s1[1], s1[2], s1[3]);
                     if (NSV > 2) st4(a.y_next + 2 * plane + idx, x1[0], x1[1], x1[2], x1[3]);
+                    if constexpr (NSV > 3) st4(a.y_next + 3 * plane + idx, w1[0], w1[1], w1[2], w1[3]);
                     if constexpr (F16) {
                         store_split4_f16(a.src_hi, a.src_lo, (size_t)b * a.ld_src + i0, sr, so);
                     } else {

@@ -93,7 +93,10 @@ template <> struct ModelTraits<RP_QIF_SFA>    { static constexpr int NSV = 3; st
 template <> struct ModelTraits<RP_LIF>        { static constexpr int NSV = 2; static constexpr bool SPIKING = true; };
 template <> struct ModelTraits<RP_IK>         { static constexpr int NSV = 3; static constexpr bool SPIKING = true; };   // planes v, s, u
 template <> struct ModelTraits<RP_IKU>        { static constexpr int NSV = 3; static constexpr bool SPIKING = true; };   // planes v, s, u (mean-field u)
-__host__ __device__ constexpr bool is_ik(int model) { return model == RP_IK || model == RP_IKU; }
+template <> struct ModelTraits<RP_IK_BIEXP>   { static constexpr int NSV = 4; static constexpr bool SPIKING = true; };   // planes v, s, u (mean-field), x (synaptic rise)
+__host__ __device__ constexpr bool is_ik(int model) { return model == RP_IK || model == RP_IKU || model == RP_IK_BIEXP; }
+// templates whose recovery variable is driven by the per-trial population means (k_trial_means / k_trial_adj_sums every step)
+__host__ __device__ constexpr bool is_mean_field(int model) { return model == RP_IKU || model == RP_IK_BIEXP; }
 // checkpoint planes per step: the ik conductance synapse makes d(v')/dv depend on the recurrent drive, which is stored too
 template <int MODEL> struct HistPlanes { static constexpr int N = ModelTraits<MODEL>::NSV + (is_ik(MODEL) ? 1 : 0); };
 // parameter slot of the coupling constant that is folded into the weights
@@ -208,7 +211,8 @@ struct FwdStepArgs {
 
 template <int MODEL>
 __device__ __forceinline__ void fwd_elem(const FwdStepArgs& a, int i, float u, float Iin,
-                                         float v, float s, float x, float& v1, float& s1, float& x1, int b = 0) {
+                                         float v, float s, float x, float& v1, float& s1, float& x1, int b = 0,
+                                         float w = 0.f, float* w1 = nullptr) {      // (w, w1): fourth state plane (ik_biexp_op: x)
     const float dt = a.dt;
     const float tau = is_ik(MODEL) ? 1.f : ldp(a.mp, RP_P_TAU, i, b), eta = ldp(a.mp, RP_P_ETA, i, b);
     if constexpr (!ModelTraits<MODEL>::SPIKING) {
@@ -224,16 +228,23 @@ __device__ __forceinline__ void fwd_elem(const FwdStepArgs& a, int i, float u, f
             // ik_op (ik.yaml:10-13): v' = (k (v-v_r)(v-v_theta) - u + I_ext + eta + g s_in (E_r - v)) / C
             //                        u' = (b (v-v_r) - u)/tau_u + kappa*spike ;  s' = -s/tau_s + spike      (x holds u, u holds g*W.s)
             // iku_op (ik.yaml:33-39): u' = (b (mean(v)-v_r) - u)/tau_u + kappa*mean(spike)   (population means per trial)
+            // ik_biexp_op (ik.yaml:42-49): iku_op with  s' = -s/tau_d + x ;  x' = -x/tau_r + spike   (w holds x; tau_d, tau_r in the
+            //                              tau_s, tau_x slots)
             const float C = ldp(a.mp, RP_P_C, i, b), kq = ldp(a.mp, RP_P_K, i, b), vr = ldp(a.mp, RP_P_VR, i, b), vth = ldp(a.mp, RP_P_VTH, i, b);
             const float Er = ldp(a.mp, RP_P_ER, i, b), bb = ldp(a.mp, RP_P_B, i, b), tau_u = ldp(a.mp, RP_P_TAU_U, i, b), kappa = ldp(a.mp, RP_P_KAPPA, i, b);
             vt = v + dt * ((kq * (v - vr) * (v - vth) - x + Iin + eta + u * (Er - v)) / C);
-            if constexpr (MODEL == RP_IKU) {
+            if constexpr (is_mean_field(MODEL)) {
                 const float2 mfb = a.mf[b];
                 x1 = x + dt * ((bb * (mfb.x - vr) - x) / tau_u) + kappa * mfb.y;
             } else {
                 x1 = x + dt * ((bb * (v - vr) - x) / tau_u) + kappa * pf;
             }
-            s1 = s + dt * (-s / tau_s) + pf;
+            if constexpr (MODEL == RP_IK_BIEXP) {
+                s1 = s + dt * (-s / tau_s + w);
+                if (w1) *w1 = w + dt * (-w / ldp(a.mp, RP_P_TAU_X, i, b)) + pf;
+            } else {
+                s1 = s + dt * (-s / tau_s) + pf;
+            }
         } else if constexpr (MODEL == RP_LIF) {
             // lif_op: v' = -v/tau + k*s_in + I_ext + eta ; s' = -s/tau_s + spike + s_ext   (lif.yaml:10-15)
             const float Iv = a.in_target == 0 ? Iin : 0.f, Is = a.in_target == 1 ? Iin : 0.f;
@@ -328,13 +339,15 @@ __device__ __forceinline__ void fwd_element(const FwdStepArgs& a, int i, int b, 
     const float v = a.y_cur[idx];
     const float s = NSV > 1 ? a.y_cur[plane + idx] : 0.f;
     const float x = NSV > 2 ? a.y_cur[2 * plane + idx] : 0.f;
+    const float w = NSV > 3 ? a.y_cur[3 * plane + idx] : 0.f;
     const float Iin = input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i);
-    float v1, s1, x1;
-    fwd_elem<MODEL>(a, i, u, Iin, v, s, x, v1, s1, x1, b);
+    float v1, s1, x1, w1 = 0.f;
+    fwd_elem<MODEL>(a, i, u, Iin, v, s, x, v1, s1, x1, b, w, &w1);
     if (is_ik(MODEL) && a.urec_out) a.urec_out[idx] = u;
     a.y_next[idx] = v1;
     if (NSV > 1) a.y_next[plane + idx] = s1;
     if (NSV > 2) a.y_next[2 * plane + idx] = x1;
+    if (NSV > 3) a.y_next[3 * plane + idx] = w1;
     float src1;
     if constexpr (ModelTraits<MODEL>::SPIKING) src1 = s1; else src1 = rate_act<MODEL>(a.mp, i, v1, b);
     if (a.src_next) a.src_next[idx] = src1;
@@ -637,7 +650,8 @@ __device__ __forceinline__ AdjRowParams adj_row_params(const AdjArgs& a, int i, 
 // (v, s, x) = y_t.  Z = ((kW)^T g_t)[b][i].  Returns dI = dL/d(input current of step t).
 template <int MODEL, class Acc>
 __device__ __forceinline__ float adj_post_math(const AdjArgs& a, const AdjRowParams& rp_, const Acc& acc, int i, int b, float Z,
-                                               float v, float s, float x, float& av, float& as, float& ax, float urec = 0.f) {
+                                               float v, float s, float x, float& av, float& as, float& ax, float urec = 0.f,
+                                               float w = 0.f, float* aw = nullptr) {     // (w, aw): fourth state plane and its adjoint
     constexpr bool SPK = ModelTraits<MODEL>::SPIKING;
     const float dt = a.dt, tau = rp_.tau, tau_s = rp_.tau_s, tau_x = rp_.tau_x, alpha = rp_.alpha;
     // readout / record gradient flowing into y_t[out]
@@ -673,15 +687,24 @@ __device__ __forceinline__ float adj_post_math(const AdjArgs& a, const AdjRowPar
         const float gv = p ? 0.f : av;
         const float d = 1.0f + a.slope * fabsf(v - a.theta);
         const float sg = 1.0f / (d * d);                 // Spike.backward          nodes.py:478-481
-        if constexpr (MODEL == RP_IKU) {
+        if constexpr (is_mean_field(MODEL)) {
+            // ik_biexp_op: iku_op whose spike enters the rise variable x (plane 3: w, aw) instead of s:  s' = -s/tau_d + x,
+            // x' = -x/tau_r + spike  ->  the surrogate term carries aw, and  aw <- aw (1 - dt/tau_r) + dt as
             // iku_op: as ik_op, but u' couples to the population means: d u_i'/d v_j = b_i / (N tau_u_i) and, through the surrogate,
             // d u_i'/d v_j = kappa_i sg_j / N for every j  ->  the local terms ax*dt*b/tau_u and kappa*ax become trial means (asum)
             const float C = ldp(a.mp, RP_P_C, i, b), kq = ldp(a.mp, RP_P_K, i, b), vr = ldp(a.mp, RP_P_VR, i, b), vth = ldp(a.mp, RP_P_VTH, i, b);
             const float Er = ldp(a.mp, RP_P_ER, i, b), bb = ldp(a.mp, RP_P_B, i, b), tau_u = ldp(a.mp, RP_P_TAU_U, i, b);
             const float eta = ldp(a.mp, RP_P_ETA, i, b);
             const float2 mfb = a.mf_t[b], sums = a.asum[b];
-            nav = gv * (1.0f + dt * (kq * (2.0f * v - vr - vth) - urec) / C) + sums.x + sg * (as + sums.y);
+            float a_spk = as;                                   // adjoint of the variable that receives the spike
+            if constexpr (MODEL == RP_IK_BIEXP) a_spk = aw ? *aw : 0.f;
+            nav = gv * (1.0f + dt * (kq * (2.0f * v - vr - vth) - urec) / C) + sums.x + sg * (a_spk + sums.y);
             nas = as * (1.0f - dt / tau_s) + Z;
+            if constexpr (MODEL == RP_IK_BIEXP) {
+                const float tau_r = ldp(a.mp, RP_P_TAU_X, i, b);
+                acc.add(RP_P_TAU_X, a_spk * w * dt / (tau_r * tau_r));
+                if (aw) *aw = a_spk * (1.0f - dt / tau_r) + dt * as;
+            }
             nax = ax * (1.0f - dt / tau_u) - gv * dt / C;
             dI = dt / C * gv;
             const float Iin = a.dparams[RP_P_C] ? input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i) : 0.f;
@@ -748,7 +771,7 @@ __device__ __forceinline__ float adj_post_math(const AdjArgs& a, const AdjRowPar
             if (j < a.m) acc.add(RP_NUM_PARAMS + j, dI * __ldg(a.x_t + (size_t)b * a.m + j));
     }
     av = nav; as = nas; ax = nax;
-    if (a.zero_after_post) { av = 0.f; as = 0.f; ax = 0.f; }
+    if (a.zero_after_post) { av = 0.f; as = 0.f; ax = 0.f; if (aw) *aw = 0.f; }
     return dI;
 }
 
@@ -772,18 +795,21 @@ __device__ __forceinline__ void adj_element(const AdjArgs& a, AdjCtx<MODEL>& c, 
     float av = a.adj[idx];
     float as = NSV > 1 ? a.adj[plane + idx] : 0.f;
     float ax = NSV > 2 ? a.adj[2 * plane + idx] : 0.f;
+    float aw = NSV > 3 ? a.adj[3 * plane + idx] : 0.f;
     if (a.do_post) {
         const float v = __ldg(a.y_t + idx);
         const float s = NSV > 1 ? __ldg(a.y_t + plane + idx) : 0.f;
         const float x = NSV > 2 ? __ldg(a.y_t + 2 * plane + idx) : 0.f;
+        const float w = NSV > 3 ? __ldg(a.y_t + 3 * plane + idx) : 0.f;
         const AdjRowParams rp_ = a.per_trial ? adj_row_params<MODEL>(a, i, b) : AdjRowParams{c.tau, c.tau_s, c.tau_x, c.alpha};
         const RegAcc acc{c.acc};
         const float urec = (is_ik(MODEL) && a.urec_t) ? __ldg(a.urec_t + idx) : 0.f;
-        const float dI = adj_post_math<MODEL>(a, rp_, acc, i, b, Z, v, s, x, av, as, ax, urec);
+        const float dI = adj_post_math<MODEL>(a, rp_, acc, i, b, Z, v, s, x, av, as, ax, urec, w, &aw);
         if (a.g_x_t) a.g_x_t[idx] = dI;
         a.adj[idx] = av;
         if (NSV > 1) a.adj[plane + idx] = as;
         if (NSV > 2) a.adj[2 * plane + idx] = ax;
+        if (NSV > 3) a.adj[3 * plane + idx] = aw;
     }
     g_out = 0.f; src_out = 0.f;
     if (a.do_pre) {
@@ -841,21 +867,24 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
     float gmax = 0.f;
     for (int l0 = 0; l0 < ADJ_BPT; l0 += BATCH) {
         float av[BATCH], as[BATCH], ax[BATCH], v[BATCH], s[BATCH], x[BATCH], vm[BATCH], sm[BATCH], Z[BATCH], ur[BATCH];
+        float aw[BATCH], w[BATCH];      // fourth state plane (ik_biexp_op)
         bool ok[BATCH];
 #pragma unroll
         for (int l = 0; l < BATCH; ++l) {
             const int b = bblk + (l0 + l) * ADJ_TY + threadIdx.y;
             ok[l] = valid_i && b < a.B;
             const size_t idx = (size_t)b * a.N + i;
-            av[l] = as[l] = ax[l] = v[l] = s[l] = x[l] = vm[l] = sm[l] = Z[l] = ur[l] = 0.f;
+            av[l] = as[l] = ax[l] = v[l] = s[l] = x[l] = vm[l] = sm[l] = Z[l] = ur[l] = aw[l] = w[l] = 0.f;
             if (ok[l]) {
                 av[l] = a.adj[idx];
                 if (NSV > 1) as[l] = a.adj[plane + idx];
                 if (NSV > 2) ax[l] = a.adj[2 * plane + idx];
+                if (NSV > 3) aw[l] = a.adj[3 * plane + idx];
                 if (a.do_post) {
                     v[l] = __ldg(a.y_t + idx);
                     if (NSV > 1) s[l] = __ldg(a.y_t + plane + idx);
                     if (NSV > 2) x[l] = __ldg(a.y_t + 2 * plane + idx);
+                    if (NSV > 3) w[l] = __ldg(a.y_t + 3 * plane + idx);
                     Z[l] = a.Z[(size_t)b * a.ldz + i];
                     if (is_ik(MODEL) && a.urec_t) ur[l] = __ldg(a.urec_t + idx);
                 }
@@ -874,11 +903,12 @@ __global__ void __launch_bounds__(ADJ_TX * ADJ_TY) k_adj_step(AdjArgs a) {
             if (ok[l]) {
                 if (a.do_post) {
                     const AdjRowParams rp_ = a.per_trial ? adj_row_params<MODEL>(a, i, b) : rp0;
-                    const float dI = adj_post_math<MODEL>(a, rp_, racc, i, b, Z[l], v[l], s[l], x[l], av[l], as[l], ax[l], ur[l]);
+                    const float dI = adj_post_math<MODEL>(a, rp_, racc, i, b, Z[l], v[l], s[l], x[l], av[l], as[l], ax[l], ur[l], w[l], &aw[l]);
                     if (a.g_x_t) a.g_x_t[idx] = dI;
                     a.adj[idx] = av[l];
                     if (NSV > 1) a.adj[plane + idx] = as[l];
                     if (NSV > 2) a.adj[2 * plane + idx] = ax[l];
+                    if (NSV > 3) a.adj[3 * plane + idx] = aw[l];
                 }
                 if (a.do_pre) {
                     adj_pre_math<MODEL>(a, i, av[l], vm[l], sm[l], g, srcv, b);
@@ -977,6 +1007,7 @@ __global__ void __launch_bounds__(32 * NTY, NTY == 4 ? 6 : 3) k_adj_step_v4(AdjA
 
     for (int l0 = 0; l0 < 4; l0 += 2) {
         float4 av[2], as[2], ax[2], v[2], s[2], x[2], vm[2], sm[2], Z[2], ur[2];
+        float4 aw[2], w[2];             // fourth state plane (ik_biexp_op)
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
             const int b = bblk + (l0 + l) * NTY + ty;
@@ -984,11 +1015,13 @@ __global__ void __launch_bounds__(32 * NTY, NTY == 4 ? 6 : 3) k_adj_step_v4(AdjA
             av[l] = *reinterpret_cast<const float4*>(a.adj + idx);
             as[l] = NSV > 1 ? *reinterpret_cast<const float4*>(a.adj + plane + idx) : zero;
             ax[l] = NSV > 2 ? *reinterpret_cast<const float4*>(a.adj + 2 * plane + idx) : zero;
-            v[l] = s[l] = x[l] = vm[l] = sm[l] = Z[l] = ur[l] = zero;
+            aw[l] = NSV > 3 ? *reinterpret_cast<const float4*>(a.adj + 3 * plane + idx) : zero;
+            v[l] = s[l] = x[l] = vm[l] = sm[l] = Z[l] = ur[l] = w[l] = zero;
             if (a.do_post) {
                 v[l] = __ldg(reinterpret_cast<const float4*>(a.y_t + idx));
                 if (NSV > 1) s[l] = __ldg(reinterpret_cast<const float4*>(a.y_t + plane + idx));
                 if (NSV > 2) x[l] = __ldg(reinterpret_cast<const float4*>(a.y_t + 2 * plane + idx));
+                if (NSV > 3) w[l] = __ldg(reinterpret_cast<const float4*>(a.y_t + 3 * plane + idx));
                 Z[l] = *reinterpret_cast<const float4*>(a.Z + (size_t)b * a.ldz + i0);
                 if (is_ik(MODEL) && a.urec_t) ur[l] = __ldg(reinterpret_cast<const float4*>(a.urec_t + idx));
             }
@@ -1003,13 +1036,13 @@ __global__ void __launch_bounds__(32 * NTY, NTY == 4 ? 6 : 3) k_adj_step_v4(AdjA
             const int bl = (l0 + l) * NTY + ty;
             const int b = bblk + bl;
             const size_t idx = (size_t)b * a.N + i0;
-            float nav[4], nas[4], nax[4], g[4], sv[4], gh[4], gl[4];
+            float nav[4], nas[4], nax[4], naw[4], g[4], sv[4], gh[4], gl[4];
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
-                nav[rr] = f4at(av[l], rr); nas[rr] = f4at(as[l], rr); nax[rr] = f4at(ax[l], rr);
+                nav[rr] = f4at(av[l], rr); nas[rr] = f4at(as[l], rr); nax[rr] = f4at(ax[l], rr); naw[rr] = f4at(aw[l], rr);
                 if (a.do_post)
                     adj_post_math<MODEL>(a, rp_[rr], nacc, i0 + rr, b, f4at(Z[l], rr), f4at(v[l], rr), f4at(s[l], rr), f4at(x[l], rr),
-                                         nav[rr], nas[rr], nax[rr], f4at(ur[l], rr));
+                                         nav[rr], nas[rr], nax[rr], f4at(ur[l], rr), f4at(w[l], rr), &naw[rr]);
                 g[rr] = 0.f; sv[rr] = 0.f;
                 if (a.do_pre) adj_pre_math<MODEL>(a, i0 + rr, nav[rr], f4at(vm[l], rr), f4at(sm[l], rr), g[rr], sv[rr], b);
                 gmax = fmaxf(gmax, fabsf(g[rr]));
@@ -1019,6 +1052,7 @@ __global__ void __launch_bounds__(32 * NTY, NTY == 4 ? 6 : 3) k_adj_step_v4(AdjA
                 *reinterpret_cast<float4*>(a.adj + idx) = make_float4(nav[0], nav[1], nav[2], nav[3]);
                 if (NSV > 1) *reinterpret_cast<float4*>(a.adj + plane + idx) = make_float4(nas[0], nas[1], nas[2], nas[3]);
                 if (NSV > 2) *reinterpret_cast<float4*>(a.adj + 2 * plane + idx) = make_float4(nax[0], nax[1], nax[2], nax[3]);
+                if (NSV > 3) *reinterpret_cast<float4*>(a.adj + 3 * plane + idx) = make_float4(naw[0], naw[1], naw[2], naw[3]);
             }
             if (a.do_pre) {
                 if (a.g) *reinterpret_cast<float4*>(a.g + idx) = make_float4(g[0], g[1], g[2], g[3]);
@@ -1082,7 +1116,7 @@ __device__ __forceinline__ void adj_v5_load(const AdjArgs& a, AdjLoads<MODEL>& L
 template <int MODEL>
 __global__ void __launch_bounds__(256, 3) k_adj_step_v5(AdjArgs a) {
     constexpr int NSV = ModelTraits<MODEL>::NSV;
-    static_assert(MODEL != RP_IKU, "iku_op uses the generic adjoint kernel (trial means)");
+    static_assert(!is_mean_field(MODEL), "iku_op / ik_biexp_op use the generic adjoint kernels (trial means)");
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
     const int NT = a.N / 128;

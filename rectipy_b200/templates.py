@@ -95,6 +95,7 @@ _IK = [_canon("v' = (k*(v-v_r)*(v-v_theta) - u + I_ext + eta + g*s_in*(E_r - v))
        _canon("u' = (b*(v-v_r) - u) / tau_u + kappa*spike"), _canon("s' = -s/tau_s + spike")]
 
 _IKU = [_IK[0], _canon("u' = (b*(mean(v)-v_r) - u) / tau_u + kappa*mean(spike)"), _IK[2]]
+_IK_BIEXP = [_IK[0], _IKU[1], _canon("s' = -s/tau_d + x"), _canon("x' = -x/tau_r + spike")]
 
 _BUILTIN_OPS: Dict[str, OperatorDef] = {
     "li_op": OperatorDef("li_op", ["v' = -v/tau + k*r_in + I_ext + eta"],
@@ -123,9 +124,13 @@ _BUILTIN_OPS["ik_op"] = OperatorDef(
 _BUILTIN_OPS["iku_op"] = OperatorDef(
     "iku_op", [_BUILTIN_OPS["ik_op"].equations[0], "u' = (b*(mean(v)-v_r) - u) / tau_u + kappa*mean(spike)", "s' = -s/tau_s + spike"],
     dict(_BUILTIN_OPS["ik_op"].variables))
+# ik_biexp_op (ik.yaml:42-70): iku_op with a bi-exponential synapse  s' = -s/tau_d + x ,  x' = -x/tau_r + spike
+_BUILTIN_OPS["ik_biexp_op"] = OperatorDef(
+    "ik_biexp_op", [_BUILTIN_OPS["ik_op"].equations[0], _BUILTIN_OPS["iku_op"].equations[1], "s' = -s/tau_d + x", "x' = -x/tau_r + spike"],
+    dict({k: v for k, v in _BUILTIN_OPS["ik_op"].variables.items() if k != "tau_s"}, x=("variable", 0.0), tau_r=2.0, tau_d=6.0))
 _BUILTIN_NODES = {"tanh": ["li_op", "tanh_op"], "sigmoid": ["li_op", "sigmoid_op"], "qif": ["qif_op"],
-                  "qif_sfa": ["qif_sfa_op"], "lif": ["lif_op"], "ik": ["ik_op"], "iku": ["iku_op"]}
-_BUILTIN_MODULES = {"leaky_integrator": ["tanh", "sigmoid"], "qif": ["qif", "qif_sfa"], "lif": ["lif"], "ik": ["ik", "iku"]}
+                  "qif_sfa": ["qif_sfa_op"], "lif": ["lif_op"], "ik": ["ik_op"], "iku": ["iku_op"], "ik_biexp": ["ik_biexp_op"]}
+_BUILTIN_MODULES = {"leaky_integrator": ["tanh", "sigmoid"], "qif": ["qif", "qif_sfa"], "lif": ["lif"], "ik": ["ik", "iku", "ik_biexp"]}
 
 _SLOT = dict(tau=abi.RP_P_TAU, k=abi.RP_P_K, eta=abi.RP_P_ETA, tau_s=abi.RP_P_TAU_S, tau_x=abi.RP_P_TAU_X,
              alpha=abi.RP_P_ALPHA, r_max=abi.RP_P_RMAX, s=abi.RP_P_SIG_S, v0=abi.RP_P_V0,
@@ -164,6 +169,18 @@ def _spec_from_ops(ops: List[OperatorDef]) -> TemplateSpec:
             source_var=f"{o}/s", target_var=f"{o}/s_in", input_vars={f"{o}/I_ext": 0}, spike_var=f"{o}/spike",
             out_vars={f"{o}/v": abi.RP_VAR_V, f"{o}/s": abi.RP_VAR_S, f"{o}/u": abi.RP_VAR_X},
             planes={f"{o}/v": 0, f"{o}/s": 1, f"{o}/u": 2}, fold_param=f"{o}/g")
+    if len(ops) == 1 and eqs[0] == _IK_BIEXP:
+        # reference order of y: v, u, s, x (equation order); engine planes: v, s, u, x.  The decay / rise time constants travel in
+        # the tau_s / tau_x slots of the ABI.
+        o = main.name
+        slot = dict(_SLOT, tau_d=abi.RP_P_TAU_S, tau_r=abi.RP_P_TAU_X)
+        pn = ["C", "k", "v_r", "v_theta", "eta", "g", "E_r", "b", "tau_u", "kappa", "tau_d", "tau_r"]
+        return TemplateSpec(
+            name="ik_biexp", model=abi.RP_IK_BIEXP, ops=(o,), state_vars=[(f"{o}/{v}", _val(mv[v])) for v in ("v", "u", "s", "x")],
+            params={f"{o}/{p}": (slot[p], _val(mv[p])) for p in pn},
+            source_var=f"{o}/s", target_var=f"{o}/s_in", input_vars={f"{o}/I_ext": 0}, spike_var=f"{o}/spike",
+            out_vars={f"{o}/v": abi.RP_VAR_V, f"{o}/s": abi.RP_VAR_S, f"{o}/u": abi.RP_VAR_X},
+            planes={f"{o}/v": 0, f"{o}/s": 1, f"{o}/u": 2, f"{o}/x": 3}, fold_param=f"{o}/g")
     if len(ops) == 1 and eqs[0] in (_QIF, _QIF_SFA, _LIF):
         o = main.name
         if eqs[0] == _QIF:
@@ -182,7 +199,7 @@ def _spec_from_ops(ops: List[OperatorDef]) -> TemplateSpec:
             out_vars={f"{o}/{v}": i for i, v in enumerate(sv)})
     raise NotImplementedError(
         "rectipy_b200: the operator equations " + str([op.equations for op in ops]) + " do not match any vector field "
-        "compiled into the engine (li_op+tanh_op, li_op+sigmoid_op, qif_op, qif_sfa_op, lif_op, ik_op, iku_op).")
+        "compiled into the engine (li_op+tanh_op, li_op+sigmoid_op, qif_op, qif_sfa_op, lif_op, ik_op, iku_op, ik_biexp_op).")
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -18,7 +18,7 @@ if os.path.join(ROOT, "oracle") not in sys.path:
 import rectipy_oracle as orc  # noqa: E402
 
 TD = {"float64": torch.float64, "float32": torch.float32}
-RUN_CASES = ["li_tanh_bptt", "li_sigmoid_fwd", "qif_bptt", "qif_sfa_fwd", "qif_sfa_bptt_trunc", "lif_bptt", "ik_bptt", "iku_bptt",
+RUN_CASES = ["li_tanh_bptt", "li_sigmoid_fwd", "qif_bptt", "qif_sfa_fwd", "qif_sfa_bptt_trunc", "lif_bptt", "ik_bptt", "iku_bptt", "ik_biexp_bptt",
              "li_tanh_masked_softmax"]
 
 
@@ -107,6 +107,7 @@ TEMPLATE_PATH = {
     "lif": ("neuron_model_templates.spiking_neurons.lif.lif", "lif_op", "s", "s_in"),
     "ik": ("neuron_model_templates.spiking_neurons.ik.ik", "ik_op", "s", "s_in"),
     "iku": ("neuron_model_templates.spiking_neurons.ik.iku", "iku_op", "s", "s_in"),
+    "ik_biexp": ("neuron_model_templates.spiking_neurons.ik.ik_biexp", "ik_biexp_op", "s", "s_in"),
 }
 
 

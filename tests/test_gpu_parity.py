@@ -467,10 +467,10 @@ def test_full_size_rate_network_directional_derivative(tc_prec):
     assert abs(analytic - numeric) <= 2e-2 * abs(numeric)
 
 
-@pytest.mark.parametrize("tmpl", ["ik", "iku"])
+@pytest.mark.parametrize("tmpl", ["ik", "iku", "ik_biexp"])
 def test_izhikevich_batched_paths_agree(tmpl):
-    """ik_op / iku_op on all execution paths (persistent B=2 -- per-step for iku, whose recovery variable needs the population
-    means of every step --, per-step FFMA B=20, tcgen05 B=128 N=128 in both operand formats) vs the fp64 oracle."""
+    """ik_op / iku_op / ik_biexp_op on all execution paths (persistent B=2 -- per-step for iku and ik_biexp, whose recovery variable
+    needs the population means of every step --, per-step FFMA B=20, tcgen05 B=128 N=128 in both operand formats) vs the fp64 oracle."""
     import rectipy_b200 as rp
     n, m, k, T, dt = 128, 2, 2, 300, 1e-1
     rng = np.random.default_rng(12)

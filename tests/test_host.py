@@ -18,7 +18,9 @@ def test_builtin_templates_resolve():
                                    ("neuron_model_templates.rate_neurons.leaky_integrator.sigmoid", "li_sigmoid", 1, abi.RP_LI_SIGMOID),
                                    (QIF, "qif", 2, abi.RP_QIF), (QIF + "_sfa", "qif_sfa", 3, abi.RP_QIF_SFA),
                                    ("neuron_model_templates.spiking_neurons.lif.lif", "lif", 2, abi.RP_LIF),
-                                   ("neuron_model_templates.spiking_neurons.ik.ik", "ik", 3, abi.RP_IK)]:
+                                   ("neuron_model_templates.spiking_neurons.ik.ik", "ik", 3, abi.RP_IK),
+                                   ("neuron_model_templates.spiking_neurons.ik.iku", "iku", 3, abi.RP_IKU),
+                                   ("neuron_model_templates.spiking_neurons.ik.ik_biexp", "ik_biexp", 4, abi.RP_IK_BIEXP)]:
         spec = templates.resolve_template(path)
         assert (spec.name, spec.n_sv, spec.model) == (name, nsv, model)
     # defaults of the reference YAML files
@@ -70,6 +72,27 @@ def test_ik_state_order_matches_reference():
     assert node.var_index("u") == 2 and node.var_index("ik_op/s") == 1
     slots, tensors, per_neuron = node.param_slots()
     assert abi.RP_P_G in slots and abi.RP_P_KAPPA in slots and float(node["eta"]) == 55.0 and float(node["C"]) == 100.0
+
+
+def test_ik_biexp_state_order_and_time_constant_slots():
+    """ik_biexp_op (ik.yaml:42-70): the reference's y is [v, u, s, x]; engine planes (v, s, u, x); tau_d / tau_r travel in the tau_s /
+    tau_x slots of the ABI."""
+    net = rp.Network(1e-1, device="cpu")
+    n = 3
+    node = net.add_diffeq_node("ik", "neuron_model_templates.spiking_neurons.ik.ik_biexp", weights=np.zeros((n, n)), source_var="s",
+                               target_var="s_in", input_var="I_ext", output_var="s", spike_var="spike", reset_var="v", op="ik_biexp_op",
+                               spike_threshold=40.0, spike_reset=-60.0, node_vars={"tau_r": 1.5})
+    assert len(node.y) == 4 * n
+    assert torch.allclose(node.y, torch.cat([torch.full((n,), -60.0), torch.zeros(3 * n)]))
+    node.reset(np.arange(4 * n, dtype=np.float32))
+    for j, name in enumerate(("v", "u", "s", "x")):
+        assert torch.allclose(node[name], torch.arange(float(j * n), float((j + 1) * n)))
+    assert [node.var_index(v) for v in ("v", "s", "u", "x")] == [0, 1, 2, 3]
+    assert torch.allclose(node.state[3, 0], torch.arange(3. * n, 4 * n)) and torch.allclose(node.state[1, 0], torch.arange(2. * n, 3 * n))
+    assert torch.allclose(node.y, torch.arange(0., 4 * n))
+    slots, tensors, per_neuron = node.param_slots()
+    assert float(tensors[slots.index(abi.RP_P_TAU_X)]) == 1.5 and float(tensors[slots.index(abi.RP_P_TAU_S)]) == 6.0
+    assert float(node["tau_d"]) == 6.0 and float(node["kappa"]) == 10.0
 
 
 def _qif_net(n=10, **kw):
