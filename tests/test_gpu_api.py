@@ -213,6 +213,65 @@ def test_two_node_feed_forward_chain_matches_reference():
     assert o1.shape[-1] == m["k"] and torch.isfinite(o1).all()
 
 
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_feedback_network_matches_reference(variant):
+    """`FeedbackNetwork` (rectipy/network.py:1196-1357): inp -> p1 -> p2 -> out with a feedback edge p2 -> p1, against the fixture
+    produced by the reference's own FeedbackNetwork (oracle/make_golden.py::save_feedback_net).  Variant A: LI-tanh -> QIF, the
+    feedback reads the spiking node's stale `y` (one step of delay, nodes.py:387); variant B: QIF -> LI-tanh, the feedback reads the
+    rate node's current state.  Window means, records of both nodes and ALL gradients incl. the feedback edge."""
+    import ast
+    import os
+    import rectipy_b200 as rp
+    from golden_util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "feedback_net.npz"))
+    m = ast.literal_eval(str(z["meta"]))
+    zi = lambda key: z[f"{variant}_{key}"]
+    net = rp.FeedbackNetwork(m["dt"], device="cuda:0")
+
+    def add_rate():
+        return net.add_diffeq_node("rate", "neuron_model_templates.rate_neurons.leaky_integrator.tanh", weights=zi("in_Wr"),
+                                   source_var="tanh_op/r", target_var="li_op/r_in", input_var="li_op/I_ext", output_var="li_op/v",
+                                   node_vars={"li_op/tau": zi("pr_tau"), "li_op/k": m["pr_k"], "li_op/eta": m["pr_eta"]},
+                                   train_params=["weights", "li_op/tau"])
+
+    def add_spk():
+        return net.add_diffeq_node("spk", "neuron_model_templates.spiking_neurons.qif.qif", weights=zi("in_Wq"), source_var="s",
+                                   target_var="s_in", input_var="I_ext", output_var="s", spike_var="spike", reset_var="v", op="qif_op",
+                                   node_vars={"eta": zi("pq_eta"), "k": m["pq_k"], "tau_s": m["pq_tau_s"]}, train_params=["weights", "eta"])
+    if variant == "A":
+        rate, spk = add_rate(), add_spk()
+        first, second = "rate", "spk"
+    else:
+        spk, rate = add_spk(), add_rate()
+        first, second = "spk", "rate"
+    net.add_func_node("inp", m["m"], "identity"); net.add_func_node("out", m["k"], "identity")
+    net.add_edge("inp", first, weights=zi("in_w_in"), train="gd")
+    net.add_edge(first, second, weights=zi("in_w12"), train="gd")
+    net.add_edge(second, "out", weights=zi("in_w_out"), train="gd")
+    net.add_edge(second, first, weights=zi("in_wfb"), train="gd", feedback=True)
+    obs = net.run(zi("in_inputs"), sampling_steps=m["S"], cutoff=m["cutoff"], verbose=False, enable_grad=True,
+                  record_vars=[("rate", "v", False), ("spk", "s", True)])
+    out = torch.stack(obs["out"])
+    loss = torch.nn.functional.mse_loss(out, torch.tensor(zi("in_targets"), dtype=torch.float32, device="cuda"))
+    loss.backward()
+    ref = {k[len(f"{variant}_float64_"):]: z[k] for k in z.files if k.startswith(f"{variant}_float64_")}
+    tol32 = lambda key: 10.0 * max(rel_err(zi("float32_" + key), ref[key]), 1e-6)     # as close to fp64 as the reference's own fp32 run (x10)
+    assert list(np.asarray(obs["steps"])) == list(ref["steps"])
+    assert rel_err(out.detach().cpu().numpy(), ref["out"]) <= tol32("out")
+    assert rel_err(obs.to_numpy(("rate", "v")), ref["var_rate_v"]) <= tol32("var_rate_v")
+    assert rel_err(obs.to_numpy(("spk", "s")), ref["var_spk_s"]) <= tol32("var_spk_s")
+    assert abs(float(loss.detach()) - float(ref["loss"])) <= 1e-4 * abs(float(ref["loss"]))
+    got = dict(grad_Wr=rate["weights"].grad, grad_tau=rate["li_op/tau"].grad, grad_Wq=spk["weights"].grad, grad_eta=spk["eta"].grad,
+               grad_w_in=net.get_edge("inp", first).weights.grad, grad_w12=net.get_edge(first, second).weights.grad,
+               grad_wfb=net.get_edge(second, first).weights.grad, grad_w_out=net.get_edge(second, "out").weights.grad)
+    for key, g in got.items():
+        assert g is not None, key
+        assert rel_err(g.cpu().numpy().reshape(ref[key].shape), ref[key]) <= tol32(key), key
+    assert len(list(net.parameters())) == 8
+    o1 = net.forward(zi("in_inputs")[0])                       # single steps keep working (user loops)
+    assert o1.shape[-1] == m["k"] and torch.isfinite(o1).all()
+
+
 def test_delay_and_filter_edges_in_a_network():
     """inp --LinearMemory(delays)--> LI-tanh --LinearFilter--> out, window means with cutoff: the reference's own Network output
     (tests/golden/edges_stateful.npz).  The stateful edges map the per-step series on either side of the engine call."""

@@ -95,6 +95,29 @@ def test_ik_biexp_state_order_and_time_constant_slots():
     assert float(node["tau_d"]) == 6.0 and float(node["kappa"]) == 10.0
 
 
+def test_feedback_network_graph_bookkeeping():
+    """`FeedbackNetwork.compile` sorts the edges into the feed-forward graph (input / output node, evaluation order) and the
+    feedback graph; `get_edge` / `get_node` / `parameters` see both (rectipy/network.py:1204-1328)."""
+    net = rp.FeedbackNetwork(1e-3, device="cpu")
+    lif = "neuron_model_templates.spiking_neurons.lif.lif"
+    kw = dict(source_var="s", target_var="s_in", input_var="I_ext", output_var="s", spike_var="spike", reset_var="v", op="lif_op")
+    net.add_diffeq_node("p1", lif, weights=np.random.randn(6, 6), train_params=["weights"], **kw)
+    net.add_diffeq_node("p2", lif, weights=np.random.randn(4, 4), **kw)
+    e_ff = net.add_edge("p1", "p2", weights=np.random.rand(4, 6), train=None)
+    e_fb = net.add_edge("p2", "p1", weights=-np.random.rand(6, 4), train="gd", feedback=True)
+    for _ in range(2):                                  # compiling twice must not lose or duplicate the feedback edge
+        net.compile()
+        assert (net._in_node, net._out_node) == ("p1", "p2")
+        assert list(net.graph.edges) == [("p1", "p2")] and list(net._fb_graph.edges) == [("p2", "p1")]
+    assert net.get_edge("p1", "p2") is e_ff and net.get_edge("p2", "p1") is e_fb
+    assert net.get_node("p1") is net._fb_graph.nodes["p1"]["node"]
+    params = list(net.parameters())
+    assert len(params) == 2 and any(p is e_fb.weights for p in params)          # p1's weights once + the feedback edge
+    assert net._get_path() == ["p1", "p2"] and net._feedback_sources("p1") == ["p2"] and net._feedback_sources("p2") == []
+    with pytest.raises(RuntimeError):                   # no CPU fallback
+        net.run(np.zeros((3, 1)), verbose=False, enable_grad=False)
+
+
 def _qif_net(n=10, **kw):
     net = rp.Network(1e-3, device="cpu")
     node = net.add_diffeq_node("qif", QIF, weights=np.random.randn(n, n), source_var="s", target_var="s_in",
