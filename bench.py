@@ -13,7 +13,7 @@ One bench "step" = one BPTT pass over one batch: forward T_INNER Euler steps + t
     e2e          same pass through the public API (`Network.run` + loss + `backward`) with HOST inputs/targets
                  (pinned), host->device copies and the device->host read of the loss inside the timed region
     fwd          extra: forward-only neuron-steps/s (Network.run, no grad) over the same shapes
-    roofline     dominant kernel = tcgen05 3xTF32 contraction; achieved = logical flops/launch / CUDA-event time
+    roofline     dominant kernel = tcgen05 split-3 contraction (binary16 words); achieved = logical flops/launch / CUDA-event time
     cpu_baseline the CPU oracle port (= the reference's eager-torch path restated) on this box's host cores
 
 --impl reference times the reference's CPU algorithm (oracle port; the reference itself is a Python package that
@@ -232,7 +232,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "QIF N=4096 BPTT fwd+bwd, reference algorithm (eager torch, unbatched) on host CPU",
+        "config": {"workload": f"QIF N={N_NEURONS} BPTT fwd+bwd, reference algorithm (eager torch, unbatched) on host CPU",
                    "n": N_NEURONS, "batch": 1, "t_inner": CPU_T, "n_in": N_IN, "n_out": N_OUT, "dt": DT},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                          "sample": f"1 trial x {CPU_T} Euler steps BPTT per step (reference has no trial axis)"},
@@ -388,12 +388,13 @@ def run_ours(args):
             "dtype": ("f32 (tcgen05 split-3 contractions on binary16 hi/lo words with exact power-of-two scales = 22-bit significand "
                       "products, fp32 accumulate)" if f16 else ("f32 (tcgen05 3xTF32 contractions, fp32 accumulate)" if use_tc else "f32")),
             "data": "synthetic",
-            "config": {"workload": "QIF recurrent spiking net BPTT (BASELINE configs[2]): N=4096, batch=1024 trials/GPU, "
+            "config": {"workload": f"QIF recurrent spiking net BPTT (BASELINE configs[{2 if N_NEURONS == 4096 else 4}]): N={N_NEURONS}, batch={BATCH} trials/GPU, "
                                    "m=2, k=3, dt=1e-3, T=%d Euler steps fwd + adjoint per step, train W and W_out" % T,
                        "n": n, "batch_per_gpu": B, "t_inner": T, "n_in": N_IN, "n_out": N_OUT, "dt": DT,
                        "parallelism": f"trial-sharded x{world}" + (", NCCL grad all-reduce" if world > 1 else ""),
                        "initial_state": "v uniform in [-50, 99), s = 0 (active network: spikes, resets and surrogate terms occur within T)",
-                       "l2": "working set (3.3 GB of checkpoints + 256 MB of split weights per pass) exceeds the 126 MB L2"},
+                       "l2": "working set (%.1f GB of checkpoints + %d MB of split weights per pass) exceeds the 126 MB L2"
+                             % ((T + 1) * 2 * B * n * 4 / 1e9, (8 if f16 else 16) * n * n // 2**20)},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(x_host.numel() * 4 + tgt_host.numel() * 4), "d2h_bytes_per_step": 4},
             "fwd": {"value": fwd_value, "unit": UNIT, "ms_per_step": ms_fwd / args.steps},
@@ -441,10 +442,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--t-inner", type=int, default=T_INNER, help="Euler steps per BPTT pass (profiling runs use fewer)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (profiling runs)")
+    ap.add_argument("--neurons", dest="n", type=int, default=N_NEURONS, help="neurons (8192: BASELINE configs[4], the multi-GPU sweep shape)")
+    ap.add_argument("--trials", dest="batch", type=int, default=BATCH, help="trials per GPU")
     ap.add_argument("--precision", default="auto", choices=["auto", "3xf16", "3xtf32", "fp32"], help="contraction path (A/B runs)")
     args = ap.parse_args()
     globals()["T_INNER"] = args.t_inner
     globals()["PRECISION"] = args.precision
+    if (args.n, args.batch) != (N_NEURONS, BATCH):
+        globals()["N_NEURONS"], globals()["BATCH"] = args.n, args.batch
+        globals()["METRIC"] = f"neuron-steps/sec (QIF N={args.n}, batch {args.batch}, BPTT fwd+bwd)"
     global _OUT
     with _QuietStdout() as q:
         _OUT = q
