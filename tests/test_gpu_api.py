@@ -272,6 +272,39 @@ def test_feedback_network_matches_reference(variant):
     assert o1.shape[-1] == m["k"] and torch.isfinite(o1).all()
 
 
+def test_feedback_network_trial_axis_and_truncation():
+    """FeedbackNetwork with a trial axis: trials are independent, so a batch of different inputs equals the one-trial runs; a
+    truncated run (detach every 50 steps) keeps the forward result and still delivers gradients to the feedback edge."""
+    import rectipy_b200 as rp
+    rng = np.random.default_rng(5)
+    n1, n2, T, B, dt = 12, 9, 160, 3, 1e-3
+    W1, W2 = rng.standard_normal((n1, n1)) * 2.0 / np.sqrt(n1), rng.standard_normal((n2, n2)) * 2.0 / np.sqrt(n2)
+    ff, fb = rng.standard_normal((n2, n1)) * 3.0, rng.standard_normal((n1, n2)) * 3.0
+    x = (rng.standard_normal((T, B, n1)) * 5.0 + 30.0).astype(np.float32)
+    kw = dict(source_var="s", target_var="s_in", input_var="I_ext", output_var="s", spike_var="spike", reset_var="v", op="qif_op")
+
+    def make(batch):
+        net = rp.FeedbackNetwork(dt, device="cuda:0", batch=batch)
+        net.add_diffeq_node("p1", "neuron_model_templates.spiking_neurons.qif.qif", weights=W1, node_vars={"eta": 10.0}, **kw)
+        net.add_diffeq_node("p2", "neuron_model_templates.spiking_neurons.qif.qif", weights=W2, node_vars={"eta": 5.0}, **kw)
+        net.add_edge("p1", "p2", weights=ff, train="gd")
+        net.add_edge("p2", "p1", weights=fb, train="gd", feedback=True)
+        return net
+    netB = make(B)
+    outB = torch.stack(netB.run(x, sampling_steps=2, verbose=False, enable_grad=False)["out"]).cpu().numpy()
+    assert outB.shape == (T // 2, B, n2) and np.abs(outB).max() > 0.0
+    for b in range(B):
+        net1 = make(1)
+        out1 = torch.stack(net1.run(x[:, b, :], sampling_steps=2, verbose=False, enable_grad=False)["out"]).cpu().numpy()
+        assert rel_err(outB[:, b, :], out1) < 1e-6, b
+    net_t = make(B)
+    out_t = torch.stack(net_t.run(x, sampling_steps=2, verbose=False, enable_grad=True, truncate_steps=50)["out"])
+    assert rel_err(out_t.detach().cpu().numpy(), outB) < 1e-6
+    out_t.square().mean().backward()
+    g = net_t.get_edge("p2", "p1").weights.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0.0
+
+
 def test_delay_and_filter_edges_in_a_network():
     """inp --LinearMemory(delays)--> LI-tanh --LinearFilter--> out, window means with cutoff: the reference's own Network output
     (tests/golden/edges_stateful.npz).  The stateful edges map the per-step series on either side of the engine call."""

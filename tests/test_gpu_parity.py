@@ -511,7 +511,8 @@ def test_izhikevich_batched_paths_agree(tmpl):
             assert rel_err(g_tc, g_ff) < 1e-3, (tmpl, prec, rel_err(g_tc, g_ff))
 
 
-@pytest.mark.parametrize("model,n,B,prec", [("qif", 128, 128, "3xtf32"), ("qif", 128, 128, "3xf16"), ("li_tanh", 64, 1, "fp32"), ("qif_sfa", 96, 20, "fp32"), ("ik", 64, 2, "fp32")])
+@pytest.mark.parametrize("model,n,B,prec", [("qif", 128, 128, "3xtf32"), ("qif", 128, 128, "3xf16"), ("li_tanh", 64, 1, "fp32"), ("qif_sfa", 96, 20, "fp32"), ("ik", 64, 2, "fp32"),
+                                               ("ik_biexp", 64, 20, "fp32")])
 def test_checkpoint_recompute_segments_match_full_history(model, n, B, prec, monkeypatch):
     """Long horizons run in segments (boundary checkpoints + recompute, engine.plan_segments).  With a tiny history budget the
     same run must give the same records and the same gradients as the single-segment run, on all three execution paths."""
