@@ -3,6 +3,10 @@ reference's documentation/bptt_spiking_neurons_recurrent.py (BASELINE config 3: 
 
     python examples/bptt_spiking_recurrent.py [N] [trials] [steps]
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))      # run from a source checkout
 import sys
 import time
 

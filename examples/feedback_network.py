@@ -8,6 +8,10 @@ documentation/rnn_tryout.py, written against the current API (`reset_var="v"`; t
 it covers the reference's API, the fast paths are the single-plan `Network` runs of examples/qif_example.py and
 examples/bptt_spiking_recurrent.py.
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))      # run from a source checkout
 import time
 
 import numpy as np

@@ -3,6 +3,10 @@ against the current API (`reset_var="v"`; the upstream script still passes the r
 
     python examples/qif_example.py            # needs a B200 (sm_100a); the whole 40 000-step horizon is ONE kernel launch
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))      # run from a source checkout
 import time
 
 import numpy as np

@@ -283,18 +283,23 @@ def test_feedback_network_trial_axis_and_truncation():
     x = (rng.standard_normal((T, B, n1)) * 5.0 + 30.0).astype(np.float32)
     kw = dict(source_var="s", target_var="s_in", input_var="I_ext", output_var="s", spike_var="spike", reset_var="v", op="qif_op")
 
-    def make(batch):
+    def make(batch, trial=0):
         net = rp.FeedbackNetwork(dt, device="cuda:0", batch=batch)
         net.add_diffeq_node("p1", "neuron_model_templates.spiking_neurons.qif.qif", weights=W1, node_vars={"eta": 10.0}, **kw)
         net.add_diffeq_node("p2", "neuron_model_templates.spiking_neurons.qif.qif", weights=W2, node_vars={"eta": 5.0}, **kw)
         net.add_edge("p1", "p2", weights=ff, train="gd")
         net.add_edge("p2", "p1", weights=fb, train="gd", feedback=True)
+        # spread membrane potentials: neurons cross threshold within the horizon (otherwise s == 0 and nothing is coupled)
+        srng = np.random.default_rng(17)
+        for name, n in (("p1", n1), ("p2", n2)):
+            y0 = np.concatenate([srng.uniform(-50.0, 99.0, (B, n)), np.zeros((B, n))], axis=1).astype(np.float32)
+            net.get_node(name).reset(y0[:batch] if batch > 1 else y0[trial])
         return net
     netB = make(B)
     outB = torch.stack(netB.run(x, sampling_steps=2, verbose=False, enable_grad=False)["out"]).cpu().numpy()
     assert outB.shape == (T // 2, B, n2) and np.abs(outB).max() > 0.0
     for b in range(B):
-        net1 = make(1)
+        net1 = make(1, trial=b)
         out1 = torch.stack(net1.run(x[:, b, :], sampling_steps=2, verbose=False, enable_grad=False)["out"]).cpu().numpy()
         assert rel_err(outB[:, b, :], out1) < 1e-6, b
     net_t = make(B)

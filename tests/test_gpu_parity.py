@@ -521,25 +521,26 @@ def test_checkpoint_recompute_segments_match_full_history(model, n, B, prec, mon
     from golden_util import TEMPLATE_PATH
     rng = np.random.default_rng(n * 3 + B)
     rate = model.startswith("li_")
-    dt, T, S, cutoff, trunc = (1e-2, 230, 4, 6, 90) if rate else ((1e-1, 230, 4, 6, 90) if model == "ik" else (1e-3, 230, 3, 5, 100))
+    ik = model.startswith("ik")          # ik, ik_biexp
+    dt, T, S, cutoff, trunc = (1e-2, 230, 4, 6, 90) if rate else ((1e-1, 230, 4, 6, 90) if ik else (1e-3, 230, 3, 5, 100))
     m, k = 2, 2
     W = rng.standard_normal((n, n)) * (1.5 if rate else 2.0) / np.sqrt(n)
-    if model == "ik":
+    if ik:
         W = np.abs(W) / np.sqrt(n)
-    w_in, w_out = rng.standard_normal((n, m)) * (10.0 if model == "ik" else 1.0), rng.standard_normal((k, n)) / np.sqrt(n)
+    w_in, w_out = rng.standard_normal((n, m)) * (10.0 if ik else 1.0), rng.standard_normal((k, n)) / np.sqrt(n)
     path, op, svar, tvar = TEMPLATE_PATH[model]
     params = {"li_tanh": dict(tau=rng.uniform(1, 2, n), k=1.2, eta=0.1), "qif": dict(eta=orc.lorentzian_etas(n), k=1.5),
-              "qif_sfa": dict(eta=orc.lorentzian_etas(n, eta=0.0), alpha=0.4, tau_x=1.2), "ik": dict(eta=rng.uniform(60, 160, n), g=1.5)}[model]
-    skw = dict(spike_threshold=40.0, spike_reset=-60.0) if model == "ik" else {}
+              "qif_sfa": dict(eta=orc.lorentzian_etas(n, eta=0.0), alpha=0.4, tau_x=1.2), "ik": dict(eta=rng.uniform(60, 160, n), g=1.5)}["ik" if ik else model]
+    skw = dict(spike_threshold=40.0, spike_reset=-60.0) if ik else {}
     t = np.arange(T) * dt
-    amp, off = (1.5, 0.0) if rate else ((3.0, 1.0) if model == "ik" else (10.0, 14.0))
+    amp, off = (1.5, 0.0) if rate else ((3.0, 1.0) if ik else (10.0, 14.0))
     x = amp * np.sin(2 * np.pi * rng.uniform(0.5, 3, (1, B, m)) * t[:, None, None] + rng.uniform(0, 6.28, (1, B, m))) + off
     n_rec = len([s for s in range(T) if s >= cutoff and s % S == 0])
     targets = torch.tensor(rng.standard_normal((n_rec, B, k)), dtype=torch.float32, device="cuda")
     res = {}
     for mode in ("full", "segmented"):
         if mode == "segmented":
-            nh = 4 if model == "ik" else (3 if model == "qif_sfa" else (1 if rate else 2))
+            nh = (5 if model == "ik_biexp" else 4) if ik else (3 if model == "qif_sfa" else (1 if rate else 2))
             monkeypatch.setenv("RECTIPY_B200_HISTORY_GB", repr(60 * nh * B * n * 4 / 2**30))      # ~57 steps per segment
         else:
             monkeypatch.delenv("RECTIPY_B200_HISTORY_GB", raising=False)
@@ -560,7 +561,7 @@ def test_checkpoint_recompute_segments_match_full_history(model, n, B, prec, mon
         res[mode] = dict(out=out.detach().cpu().numpy(), var=obs.to_numpy(("rnn", f"{op}/v")), y=node.y.detach().cpu().numpy(),
                          gW=node["weights"].grad.cpu().numpy(), geta=node[f"{op}/eta"].grad.cpu().numpy(),
                          gin=net.get_edge("inp", "rnn").weights.grad.cpu().numpy(), gout=net.get_edge("rnn", "out").weights.grad.cpu().numpy())
-    segs = engine.plan_segments(T, S, (4 if model == "ik" else 3) * B * n * 4, int(60 * 3 * B * n * 4))
+    segs = engine.plan_segments(T, S, (4 if ik else 3) * B * n * 4, int(60 * 3 * B * n * 4))
     assert len(segs) >= 3
     assert np.array_equal(res["full"]["y"], res["segmented"]["y"]) and np.array_equal(res["full"]["var"], res["segmented"]["var"])
     errs = {key: rel_err(res["segmented"][key], res["full"][key]) for key in res["full"]}
