@@ -5,8 +5,10 @@ The reference hands the YAML template to PyRates, which vectorises N identical n
 templates shipped with the reference (neuron_model_templates/rate_neurons/leaky_integrator.yaml,
 spiking_neurons/qif.yaml, spiking_neurons/lif.yaml) are recognised by their equations and mapped onto the CUDA
 vector fields of rectipy_b200/csrc/rp_kernels.cuh.  User YAML files in the same PyRates template syntax
-(`base:`, `equations: replace/add`, `variables:`) are parsed and matched by equation text, so changed default
-values are honoured; an operator whose equations match none of the compiled fields raises NotImplementedError
+(`base:`, `equations: replace/add`, `variables:`) are parsed and matched against the compiled fields -- by equation text
+first, then symbolically (sympy: `v*v` for `v^2`, reordered terms, `-(1/tau)*v` for `-v/tau` are the same field) -- so changed
+default values and rewritten but identical equations are honoured; an operator whose equations match none of the compiled fields
+raises NotImplementedError
 (there is no generic/CPU fallback).
 """
 from __future__ import annotations
@@ -97,6 +99,47 @@ _IK = [_canon("v' = (k*(v-v_r)*(v-v_theta) - u + I_ext + eta + g*s_in*(E_r - v))
 _IKU = [_IK[0], _canon("u' = (b*(mean(v)-v_r) - u) / tau_u + kappa*mean(spike)"), _IK[2]]
 _IK_BIEXP = [_IK[0], _IKU[1], _canon("s' = -s/tau_d + x"), _canon("x' = -x/tau_r + spike")]
 
+_KNOWN_FIELDS = [_LI, _TANH, _SIGMOID, _QIF, _QIF_SFA, _LIF, _IK, _IKU, _IK_BIEXP]
+_FUNCS = ("tanh", "exp", "mean", "sigmoid", "sin", "cos", "sqrt", "log", "abs")
+
+
+def _rhs_expr(rhs: str):
+    """sympy expression of an equation's right-hand side; every identifier that is not a function name becomes a plain Symbol
+    (so that `E_r`, `I_ext`, `S`, `N`, `beta` ... are never taken for sympy constants / functions)."""
+    import sympy
+    names = set(re.findall(r"[A-Za-z_][A-Za-z_0-9]*", rhs))
+    local = {n: sympy.Symbol(n) for n in names if n not in _FUNCS}
+    local["mean"] = sympy.Function("mean")
+    return sympy.sympify(rhs.replace("^", "**"), locals=local)
+
+
+def _same_equation(a: str, b: str) -> bool:
+    """Same left-hand side and algebraically identical right-hand sides (v*v vs v^2, reordered terms, -(1/tau)*v vs -v/tau ...)."""
+    if a == b:
+        return True
+    la, _, ra = a.partition("=")
+    lb, _, rb = b.partition("=")
+    if la != lb or not ra or not rb:
+        return False
+    try:
+        import sympy
+        diff = _rhs_expr(ra) - _rhs_expr(rb)
+        return sympy.simplify(diff) == 0 or bool(diff.equals(0))
+    except Exception:      # unparsable user text: not one of the compiled fields
+        return False
+
+
+def _normalise(eq_list: List[str]) -> List[str]:
+    """The compiled vector field's canonical equation list that `eq_list` (canonical text, equation order = state order) is
+    algebraically identical to, or `eq_list` itself.  Variable and parameter names must be the template's: they select ABI slots."""
+    if eq_list in _KNOWN_FIELDS:
+        return eq_list
+    for known in _KNOWN_FIELDS:
+        if len(known) == len(eq_list) and all(_same_equation(a, b) for a, b in zip(eq_list, known)):
+            return known
+    return eq_list
+
+
 _BUILTIN_OPS: Dict[str, OperatorDef] = {
     "li_op": OperatorDef("li_op", ["v' = -v/tau + k*r_in + I_ext + eta"],
                          dict(v=("output", 0.0), tau=10.0, k=1.0, eta=0.0, r_in=("input", 0.0), I_ext=("input", 0.0))),
@@ -144,7 +187,7 @@ def _val(v) -> float:
 
 def _spec_from_ops(ops: List[OperatorDef]) -> TemplateSpec:
     """Recognise the operator combination by its equations and build the engine tables."""
-    eqs = [[_canon(e) for e in op.equations] for op in ops]
+    eqs = [_normalise([_canon(e) for e in op.equations]) for op in ops]
     main = ops[0]
     mv = main.variables
     if len(ops) == 2 and eqs[0] == _LI and eqs[1] in (_TANH, _SIGMOID):

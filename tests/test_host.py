@@ -55,6 +55,30 @@ def test_user_yaml_template(tmp_path, monkeypatch):
         templates.resolve_template("mymodels.custom.weird")
 
 
+def test_user_yaml_equivalent_equations_match_symbolically(tmp_path, monkeypatch):
+    """A user operator whose equations are algebraically identical to a compiled field, but written differently, resolves to it."""
+    (tmp_path / "mymodels").mkdir()
+    (tmp_path / "mymodels" / "rewritten.yaml").write_text(
+        "q_op:\n  base: OperatorTemplate\n  equations:\n    - \"v' = k*s_in + (I_ext + eta + v*v)/tau\"\n"
+        "    - \"s' = spike - (1/tau_s)*s\"\n  variables:\n    s: output(0.0)\n    v: variable(-3.0)\n    tau: 1.5\n    k: 2.0\n"
+        "    tau_s: 0.5\n    eta: 0.5\n    I_ext: input(0.0)\n    spike: input(0.0)\n    s_in: input(0.0)\n"
+        "q_neuron:\n  base: NodeTemplate\n  operators:\n    - q_op\n"
+        "cubic_op:\n  base: OperatorTemplate\n  equations:\n    - \"v' = k*s_in + (I_ext + eta + v*v*v)/tau\"\n"
+        "    - \"s' = spike - (1/tau_s)*s\"\n  variables:\n    s: output(0.0)\n    v: variable(-3.0)\n    tau: 1.5\n    k: 2.0\n"
+        "    tau_s: 0.5\n    eta: 0.5\n    I_ext: input(0.0)\n    spike: input(0.0)\n    s_in: input(0.0)\n"
+        "cubic_neuron:\n  base: NodeTemplate\n  operators:\n    - cubic_op\n")
+    monkeypatch.chdir(tmp_path)
+    spec = templates.resolve_template("mymodels.rewritten.q_neuron")
+    assert spec.name == "qif" and spec.model == abi.RP_QIF and spec.ops == ("q_op",)
+    assert spec.params["q_op/tau"][1] == 1.5 and dict(spec.state_vars)["q_op/v"] == -3.0
+    with pytest.raises(NotImplementedError):
+        templates.resolve_template("mymodels.rewritten.cubic_neuron")
+    # names that sympy would read as constants / functions stay plain symbols
+    assert templates._same_equation("v'=(E_r-v)*g*s_in/C", "v'=g*s_in*(E_r-v)/C")
+    assert not templates._same_equation("v'=(E_r-v)*g*s_in/C", "v'=g*s_in*(E_r+v)/C")
+    assert templates._same_equation("u'=(b*(mean(v)-v_r)-u)/tau_u+kappa*mean(spike)", "u'=kappa*mean(spike)-u/tau_u+b*(mean(v)-v_r)/tau_u")
+
+
 def test_ik_state_order_matches_reference():
     """ik_op: the reference's y is [v, u, s] (equation order, ik.yaml:10-13); the engine keeps planes (v, s, u)."""
     net = rp.Network(1e-1, device="cpu")
