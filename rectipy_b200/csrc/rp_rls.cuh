@@ -6,6 +6,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "rp_persistent.cuh"
 
 #define RP_RLS_MAX_OUT 16
@@ -14,6 +17,27 @@ namespace rp {
 
 inline char* rls_err_buf() { static thread_local char buf[256] = ""; return buf; }
 inline const char* rls_last_error() { return rls_err_buf(); }
+
+// Scratch of an rp_rls_run call (a few KB: the exchange buffer of the persistent kernel, or z + kappa of the per-step kernels).
+// Cached per (device, stream) and only ever grown: the stream-ordered allocator (cudaMallocAsync / cudaFreeAsync per call) gives its
+// memory back at every synchronisation and re-maps it on the next call, which showed up as intermittent stalls of 0.1 - 1.4 s on a
+// 25 ms call (round 1f, tools/exp_rls_var.py).  Calls on one stream are ordered, so reuse needs no further synchronisation.
+inline void* rls_scratch(size_t bytes, cudaStream_t st) {
+    struct Buf { void* p = nullptr; size_t cap = 0; };
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, Buf> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    Buf& b = cache[std::make_pair(dev, st)];
+    if (b.cap < bytes) {
+        if (b.p) { cudaStreamSynchronize(st); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+        const size_t want = std::max<size_t>(bytes, 64 * 1024);
+        if (cudaMalloc(&b.p, want) != cudaSuccess) { b.p = nullptr; return nullptr; }
+        b.cap = want;
+    }
+    return b.p;
+}
 
 // z[r] = beta_inv * sum_c P[r][c] x[c]     (one warp per row)
 __global__ void __launch_bounds__(256) k_rls_z(int n, float beta_inv, const float* __restrict__ P, const float* __restrict__ x, float* __restrict__ z) {
@@ -186,14 +210,12 @@ inline int rls_run_persistent(int T, int n, int k, float beta_inv, const float* 
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rls_persistent, PS_THREADS, smem);
     if (occ < 1 || grid > occ * sms) return 2;
-    uint2* zbuf = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&zbuf), 2 * (size_t)npad * sizeof(uint2), st);
-    if (e != cudaSuccess) { snprintf(rls_err_buf(), 256, "cudaMallocAsync: %s", cudaGetErrorString(e)); return 1; }
-    cudaMemsetAsync(zbuf, 0, 2 * (size_t)npad * sizeof(uint2), st);
+    uint2* zbuf = reinterpret_cast<uint2*>(rls_scratch(2 * (size_t)npad * sizeof(uint2), st));
+    if (!zbuf) { snprintf(rls_err_buf(), 256, "cudaMalloc of the RLS exchange buffer failed"); return 1; }
+    cudaError_t e = cudaMemsetAsync(zbuf, 0, 2 * (size_t)npad * sizeof(uint2), st);
     RlsArgs a{T, n, k, npad, rows, update_every, beta_inv, X, Y, W, P, loss, pred, zbuf};
     void* args[] = {&a};
-    e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_rls_persistent), dim3(grid), dim3(PS_THREADS), args, smem, st);
-    cudaFreeAsync(zbuf, st);
+    if (e == cudaSuccess) e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_rls_persistent), dim3(grid), dim3(PS_THREADS), args, smem, st);
     if (e != cudaSuccess) { snprintf(rls_err_buf(), 256, "cooperative launch: %s", cudaGetErrorString(e)); return 1; }
     return 0;
 }
@@ -204,9 +226,8 @@ inline int rls_run(int T, int n, int k, float beta_inv, const float* X, const fl
         const int rc = rls_run_persistent(T, n, k, beta_inv, X, Y, W, P, loss, pred, update_every, st);
         if (rc != 2) return rc;
     }
-    float* scratch = nullptr;   // z[n] + kappa
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&scratch), (size_t)(n + 1) * sizeof(float), st);
-    if (e != cudaSuccess) { snprintf(rls_err_buf(), 256, "cudaMallocAsync: %s", cudaGetErrorString(e)); return 1; }
+    float* scratch = reinterpret_cast<float*>(rls_scratch((size_t)(n + 1) * sizeof(float), st));   // z[n] + kappa
+    if (!scratch) { snprintf(rls_err_buf(), 256, "cudaMalloc of the RLS scratch failed"); return 1; }
     float* z = scratch; float* kappa = scratch + n;
     for (int t = 0; t < T; ++t) {
         const int upd = (t % update_every == 0) ? 1 : 0;
@@ -215,8 +236,7 @@ inline int rls_run(int T, int n, int k, float beta_inv, const float* X, const fl
         k_rls_w<<<1, 256, 0, st>>>(n, k, x, Y + (size_t)t * k, z, W, kappa, loss ? loss + t : nullptr, pred ? pred + (size_t)t * k : nullptr, upd);
         if (upd) k_rls_p<<<dim3((n + 255) / 256, n), 256, 0, st>>>(n, z, kappa, P);
     }
-    e = cudaGetLastError();
-    cudaFreeAsync(scratch, st);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(rls_err_buf(), 256, "launch: %s", cudaGetErrorString(e)); return 1; }
     return 0;
 }
