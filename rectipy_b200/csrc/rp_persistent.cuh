@@ -138,6 +138,16 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
     __syncthreads();
 
     for (int t = 0; t < a.T; ++t) {
+        // 0) input current of this step: independent of the exchange, so its global-memory latency is paid while the gather spins
+        float Iin = 0.f;
+        if (own) {
+            if (a.in_mode == RP_IN_DENSE) Iin = __ldg(a.x + (size_t)t * plane + (size_t)b * N + i);
+            else if (a.in_mode == RP_IN_PROJ) {
+                const float* xt = a.x + ((size_t)t * B + b) * a.m;
+#pragma unroll
+                for (int j = 0; j < RP_MAX_IN; ++j) if (j < a.m) Iin = fmaf(w_in[j], __ldg(xt + j), Iin);
+            }
+        }
         // 1) source vector of this step (tag t+1) -> shared memory; spins per element until every producer has published
         ll_gather(a.srcbuf + (size_t)(t & 1) * B * Npad, s_src, B, N, Npad, (unsigned int)(t + 1));
         __syncthreads();
@@ -177,13 +187,6 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
         const PWindow w = pwindow_of(a.t_offset + t, a.T_total, a.S, a.cutoff);
         if (own) {
             const size_t idx = (size_t)b * N + i;
-            float Iin = 0.f;
-            if (a.in_mode == RP_IN_DENSE) Iin = __ldg(a.x + (size_t)t * plane + idx);
-            else if (a.in_mode == RP_IN_PROJ) {
-                const float* xt = a.x + ((size_t)t * B + b) * a.m;
-#pragma unroll
-                for (int j = 0; j < RP_MAX_IN; ++j) if (j < a.m) Iin = fmaf(w_in[j], __ldg(xt + j), Iin);
-            }
             float v1, s1, x1;
             const float urec = s_u[r * PS_MAX_B + b];
             fwd_elem<MODEL>(fa, i, urec, Iin, v, s, x, v1, s1, x1, b);
@@ -325,13 +328,22 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
     __syncthreads();
 
     for (int t = a.T - 1; t >= 0; --t) {
+        // checkpoint y_t of the owned neuron: independent of the exchange, loaded while the gather spins
+        float v = 0.f, s = 0.f, x = 0.f, urec = 0.f, vm_prev = 0.f;
+        if (own) {
+            const size_t idx = (size_t)b * N + i;
+            const float* yt = a.history + (size_t)t * slot;
+            v = __ldg(yt + idx);
+            if (NSV > 1) s = __ldg(yt + plane + idx);
+            if (NSV > 2) x = __ldg(yt + 2 * plane + idx);
+            if (HistPlanes<MODEL>::N > NSV) urec = __ldg(yt + (size_t)NSV * plane + idx);
+            if (t > 0) vm_prev = __ldg(a.history + (size_t)(t - 1) * slot + idx);      // v_{t-1}: gate of g_{t-1}, needed right before the publish
+        }
         ll_gather(a.gbuf + (size_t)(t & 1) * B * Npad, s_g, B, N, Npad, (unsigned int)(a.T - t));
         // source value r_t of the owned neurons (rank-1 update operand)
         if (own && a.need_dW) {
-            const size_t idx = (size_t)b * N + i;
             float rv;
-            if constexpr (SPK) rv = a.history[(size_t)t * slot + plane + idx];
-            else rv = rate_act<MODEL>(a.mp, i, a.history[(size_t)t * slot + idx], b);
+            if constexpr (SPK) rv = s; else rv = rate_act<MODEL>(a.mp, i, v, b);
             s_src[r * PS_MAX_B + b] = rv;
         }
         __syncthreads();
@@ -381,11 +393,6 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
         // adjoint of step t for the owned neuron, then g_{t-1}
         if (own) {
             const size_t idx = (size_t)b * N + i;
-            const float* yt = a.history + (size_t)t * slot;
-            const float v = yt[idx];
-            const float s = NSV > 1 ? yt[plane + idx] : 0.f;
-            const float x = NSV > 2 ? yt[2 * plane + idx] : 0.f;
-            const float urec = HistPlanes<MODEL>::N > NSV ? yt[(size_t)NSV * plane + idx] : 0.f;
             const PWindow w = pwindow_of(a.t_offset + t, a.T_total, a.S, a.cutoff);
             const size_t estride = a.out_mode == RP_OUT_READOUT ? (size_t)B * a.k : plane;
             aa.e_t = (a.g_out_rec && w.j >= 0) ? a.g_out_rec + (size_t)w.j * estride : nullptr;
@@ -395,7 +402,11 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
             const RegAcc racc{acc};
             const float dI = adj_post_math<MODEL>(aa, rowp, racc, i, b, s_z[r * PS_MAX_B + b], v, s, x, av, as, ax, urec);
             if (a.g_x) a.g_x[(size_t)t * plane + idx] = dI;
-            if (t > 0) ll_store(a.gbuf + (size_t)((t - 1) & 1) * B * Npad + (size_t)b * Npad + i, make_g(t - 1), (unsigned int)(a.T - t + 1));
+            if (t > 0) {
+                float gm, srcv;
+                adj_pre_math<MODEL>(aa, i, av, vm_prev, 0.f, gm, srcv, b);
+                ll_store(a.gbuf + (size_t)((t - 1) & 1) * B * Npad + (size_t)b * Npad + i, gm, (unsigned int)(a.T - t + 1));
+            }
         }
         __syncthreads();          // s_g / s_z / s_src are rewritten by the next step
     }
