@@ -61,7 +61,8 @@ __device__ __forceinline__ void ll_gather(const uint2* gsrc, float* s_dst, int B
     const uint4* g4 = reinterpret_cast<const uint4*>(gsrc);
     const int pairs = (B * Npad) >> 1;
     for (int idx = threadIdx.x; idx < pairs; idx += PS_THREADS) {
-        const int col = (2 * idx) % Npad;
+        int col = 2 * idx;                                  // column of the first element of the pair: (2 idx) mod Npad without a division
+        while (col >= Npad) col -= Npad;                    // at most B - 1 <= 3 subtractions
         const bool need0 = col < N, need1 = col + 1 < N;
         uint4 q;
         do { q = ll_load2(g4 + idx); } while ((need0 && q.y != tag) || (need1 && q.w != tag));
@@ -129,6 +130,21 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
 #pragma unroll
         for (int j = 0; j < RP_MAX_IN; ++j) w_in[j] = (a.in_mode == RP_IN_PROJ && j < a.m) ? a.W_in[(size_t)i * a.m + j] : 0.f;
     }
+    // per-neuron constants of the owned neuron, loaded once for the whole horizon (templates other than ik: reciprocal form of the step,
+    // the same arithmetic as the fused tensor-core epilogue, <= 1 ulp per term away from the divisions of fwd_elem)
+    FwdRow frow{1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f};
+    FwdStepArgs fa_fast = fa;
+    fa_fast.in_mode = RP_IN_DENSE;                       // the input current is computed above the exchange and passed in as a dense value
+    fa_fast.per_trial = 0;
+    const bool fast_elem = !is_ik(MODEL) && a.mp.bstride[RP_P_TAU] == 0 && a.mp.bstride[RP_P_ETA] == 0 && a.mp.bstride[RP_P_TAU_S] == 0 &&
+                           a.mp.bstride[RP_P_TAU_X] == 0 && a.mp.bstride[RP_P_ALPHA] == 0;
+    if constexpr (!is_ik(MODEL)) { if (own && fast_elem) frow = fwd_row<MODEL>(fa_fast, i); }
+    // record-window bookkeeping without a division per step: [w_start, w_rec] is the window that contains (or follows) the current step
+    const int S_ = max(a.S, 1);
+    const int w_r0 = ((a.cutoff + S_ - 1) / S_) * S_;
+    int w_j, w_start, w_rec;
+    if (a.t_offset <= w_r0) { w_j = 0; w_start = a.cutoff; w_rec = w_r0; }
+    else { w_j = (a.t_offset - w_r0 + S_ - 1) / S_; w_rec = w_r0 + w_j * S_; w_start = w_rec - S_ + 1; }
     const int nvec = N >> 2;
     if (own && a.T > 0) {      // publish r_0 (tag 1) into slot 0
         float src0;
@@ -184,12 +200,19 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
         }
         __syncthreads();
         // 3) vector field, threshold/reset, Observer -- the owning thread keeps the neuron's state in registers
-        const PWindow w = pwindow_of(a.t_offset + t, a.T_total, a.S, a.cutoff);
+        const int tg = a.t_offset + t;
+        if (tg > w_rec) { ++w_j; w_start = w_rec + 1; w_rec += S_; }             // steps advance by one: at most one window per step
+        PWindow w{-1, 0, 0, 0};
+        if (tg >= a.cutoff && w_rec < a.T_total) { w.j = w_j; w.first = (tg == w_start); w.close = (tg == w_rec); w.len = w_rec - w_start + 1; }
         if (own) {
             const size_t idx = (size_t)b * N + i;
             float v1, s1, x1;
             const float urec = s_u[r * PS_MAX_B + b];
-            fwd_elem<MODEL>(fa, i, urec, Iin, v, s, x, v1, s1, x1, b);
+            bool done = false;
+            if constexpr (!is_ik(MODEL)) {
+                if (fast_elem) { fwd_elem_fast<MODEL>(fa_fast, frow, i, b, urec, 0.f, 0.f, Iin, v, s, x, v1, s1, x1); done = true; }
+            }
+            if (!done) fwd_elem<MODEL>(fa, i, urec, Iin, v, s, x, v1, s1, x1, b);
             float src1;
             if constexpr (SPK) src1 = s1; else src1 = rate_act<MODEL>(a.mp, i, v1, b);
             if (t + 1 < a.T) ll_store(a.srcbuf + (size_t)((t + 1) & 1) * B * Npad + (size_t)b * Npad + i, src1, (unsigned int)(t + 2));
