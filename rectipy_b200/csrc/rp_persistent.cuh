@@ -350,6 +350,15 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
     if (own && a.T > 0) ll_store(a.gbuf + (size_t)((a.T - 1) & 1) * B * Npad + (size_t)b * Npad + i, make_g(a.T - 1), 1u);
     __syncthreads();
 
+    // record-window bookkeeping without a division per step (steps run downwards): [w_start, w_rec] contains or follows the current step
+    const int S_ = max(a.S, 1);
+    const int w_r0 = ((a.cutoff + S_ - 1) / S_) * S_;
+    int w_j, w_start, w_rec;
+    {
+        const int tg_last = a.t_offset + a.T - 1;
+        if (tg_last <= w_r0) { w_j = 0; w_start = a.cutoff; w_rec = w_r0; }
+        else { w_j = (tg_last - w_r0 + S_ - 1) / S_; w_rec = w_r0 + w_j * S_; w_start = w_rec - S_ + 1; }
+    }
     for (int t = a.T - 1; t >= 0; --t) {
         // checkpoint y_t of the owned neuron: independent of the exchange, loaded while the gather spins
         float v = 0.f, s = 0.f, x = 0.f, urec = 0.f, vm_prev = 0.f;
@@ -416,7 +425,10 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
         // adjoint of step t for the owned neuron, then g_{t-1}
         if (own) {
             const size_t idx = (size_t)b * N + i;
-            const PWindow w = pwindow_of(a.t_offset + t, a.T_total, a.S, a.cutoff);
+            const int tg = a.t_offset + t;
+            if (tg < w_start && w_j > 0) { --w_j; w_rec = w_start - 1; w_start = (w_j == 0) ? a.cutoff : w_rec - S_ + 1; }
+            PWindow w{-1, 0, 0, 0};
+            if (tg >= a.cutoff && w_rec < a.T_total) { w.j = w_j; w.first = (tg == w_start); w.close = (tg == w_rec); w.len = w_rec - w_start + 1; }
             const size_t estride = a.out_mode == RP_OUT_READOUT ? (size_t)B * a.k : plane;
             aa.e_t = (a.g_out_rec && w.j >= 0) ? a.g_out_rec + (size_t)w.j * estride : nullptr;
             aa.e_scale = w.j >= 0 ? 1.0f / (float)w.len : 0.f;
