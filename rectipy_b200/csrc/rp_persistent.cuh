@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
     int w_j, w_start, w_rec;
     if (a.t_offset <= w_r0) { w_j = 0; w_start = a.cutoff; w_rec = w_r0; }
     else { w_j = (a.t_offset - w_r0 + S_ - 1) / S_; w_rec = w_r0 + w_j * S_; w_start = w_rec - S_ + 1; }
+    bool any_reduce = false;
+    for (int q = 0; q < a.n_rec_vars; ++q) any_reduce = any_reduce || (a.rec_reduce[q] != 0);
     const int nvec = N >> 2;
     if (own && a.T > 0) {      // publish r_0 (tag 1) into slot 0
         float src0;
@@ -248,7 +250,8 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
             }
             v = v1; s = s1; x = x1;
         }
-        if (w.j >= 0) {
+        // block-level reduction of this step's readout / neuron-mean contributions: only on steps that produced any (uniform condition)
+        if (w.j >= 0 && ((a.out_rec && a.out_mode == RP_OUT_READOUT) || (w.close && any_reduce))) {
             __syncthreads();
             if (a.out_rec && a.out_mode == RP_OUT_READOUT && tid < B * a.k) {
                 atomicAdd(a.out_rec + (size_t)w.j * B * a.k + tid, s_red[tid] / (float)w.len);
