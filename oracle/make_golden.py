@@ -212,6 +212,23 @@ def save_feedback_net(ref):
     np.savez_compressed(os.path.join(OUT, "feedback_net.npz"), **blob)
 
 
+def save_edges_square(ref):
+    """Square, non-symmetric edge weights: the reference transposes whenever shape == (n_in, n_out), which is always
+    true for an N x N matrix (edges.py:22-23,160-161) -- a user's W therefore acts as W.T.  Outputs of the unmodified classes."""
+    rng = np.random.default_rng(4242)
+    n, steps = 6, 5
+    w = rng.standard_normal((n, n))
+    mask = (rng.uniform(size=(n, n)) < 0.5).astype(np.float64)
+    xs = rng.standard_normal((steps, n))
+    lin = ref.edges.Linear(n, n, weights=w.copy(), dtype=torch.float64)
+    msk = ref.edges.LinearMasked(n, n, mask=mask.copy(), weights=w.copy(), dtype=torch.float64)
+    np.savez_compressed(os.path.join(OUT, "edges_square.npz"), w=w, mask=mask, xs=xs,
+                        lin_out=np.stack([lin.forward(torch.tensor(x)).numpy() for x in xs]),
+                        masked_out=np.stack([msk.forward(torch.tensor(x)).numpy() for x in xs]),
+                        lin_weights=lin.weights.numpy().copy(), masked_mask=msk.mask.numpy().copy())
+    print("edges_square: ok")
+
+
 def sin_inputs(rng, T, m, dt, amp=1.0, offset=0.0):
     t = np.arange(T) * dt
     freqs = rng.uniform(0.5, 3.0, size=m)
@@ -346,6 +363,8 @@ def main(only=None):
         save_two_node_chain(ref)
     if only in (None, "feedback_net"):
         save_feedback_net(ref)
+    if only in (None, "edges_square"):
+        save_edges_square(ref)
     rng = rng_main
 
     # ---- G7: output activation + masked input edge (LinearMasked, edges.py:150-174) ---------------

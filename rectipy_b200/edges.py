@@ -35,8 +35,11 @@ class Linear:
             weights = _to_tensor(weights, dtype)
         if weights.dim() != 2:
             raise ValueError("Edge weights have to be a 2D array.")
-        if weights.shape[0] == n_in and weights.shape[1] == n_out and n_in != n_out:
-            weights = weights.T          # a view, like the reference (edges.py:22-23): keeps results bit-identical to it
+        if weights.shape[0] == n_in and weights.shape[1] == n_out:
+            # a view, like the reference (edges.py:22-23).  NB: for a square matrix this branch is always taken, so a user's
+            # N x N `weights` acts as `weights.T @ x` -- a reference quirk that ported scripts rely on
+            # (documentation/rnn_tryout.py:23,26); pinned by tests/golden/edges_square.npz
+            weights = weights.T
         elif weights.shape[0] != n_out or weights.shape[1] != n_in:
             raise ValueError("Shape of the provided weights does not match the input and output dimensions of the "
                              "source and target nodes.")
@@ -216,7 +219,7 @@ class LinearMasked(Linear):
                  weights: Union[np.ndarray, torch.Tensor] = None, dtype: torch.dtype = torch.float64,
                  detach: bool = True, **kwargs):
         mask = _to_tensor(mask, dtype)
-        if mask.shape[0] == n_in and mask.shape[1] == n_out and n_in != n_out:
+        if mask.shape[0] == n_in and mask.shape[1] == n_out:      # square masks are transposed too (edges.py:160-161)
             mask = mask.T.contiguous()
         elif mask.shape[0] != n_out or mask.shape[1] != n_in:
             raise ValueError("Shape of the provided mask does not match the input and output dimensions of the "

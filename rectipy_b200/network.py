@@ -22,6 +22,7 @@ from networkx import DiGraph
 
 from . import _cabi as abi
 from . import engine
+from . import parallel
 from .edges import RLS, Linear, LinearFilter, LinearMasked, LinearMemory, LinearMemoryFilter
 from .nodes import InstantNode, RateNet, SpikeResetNet, node_from_template
 from .observer import Observer
@@ -682,6 +683,7 @@ class Network:
                 # per-step predictions; recorded vars are read at the observer's own sampling grid below
                 pred, recs, _ = self._run_engine(inp[start:stop], 1, 0, 0, rec_specs, True)
             pred_s = self._squeeze(pred)
+            prev_error = error
             if complete:
                 error = self._bptt_step(pred_s, target[start:stop], optimizer=optimizer, loss=loss,
                                         error_kwargs=error_kwargs, step_kwargs=step_kwargs)
@@ -689,28 +691,60 @@ class Network:
             rec_local = [t - start for t in range(start, stop) if t % sampling_steps == 0]
             if rec_local:
                 idx = torch.as_tensor(rec_local, dtype=torch.long, device=pred.device)
-                obs.record_block([start + t for t in rec_local], pred_s.detach().index_select(0, idx), error,
+                # the reference records a step before the optimizer step of its chunk has run -- all steps of a chunk but its
+                # last carry the previous chunk's loss (rectipy/network.py:1035-1046)
+                losses = [error if (complete and start + t == stop - 1) else prev_error for t in rec_local]
+                obs.record_block([start + t for t in rec_local], pred_s.detach().index_select(0, idx), losses,
                                  [self._squeeze(r).index_select(0, idx) for r in recs])
             if verbose:
                 print(f"Progress: {stop}/{steps} training steps finished. Current loss: {error}.")
         return obs
 
-    @staticmethod
-    def _bptt_step(predictions: torch.Tensor, targets: torch.Tensor, optimizer, loss: Callable, error_kwargs: dict,
+    def _bptt_step(self, predictions: torch.Tensor, targets: torch.Tensor, optimizer, loss: Callable, error_kwargs: dict,
                    step_kwargs: dict) -> float:
+        """One optimizer step (rectipy/network.py:1123-1130).  When `torch.distributed` is initialised (one process per GPU,
+        trials sharded over the ranks, parameters replicated) the gradients are summed over the ranks -- weighted by the
+        ranks' trial counts, so the update is that of the global batch -- between `backward()` and `optimizer.step()`;
+        every rank then applies the same update and the replicas stay identical.  The returned loss is the global one."""
         error = loss(predictions, targets)
         optimizer.zero_grad()
         error.backward(**error_kwargs)
+        if parallel.dist.is_initialized() and parallel.dist.get_world_size() > 1:
+            sync = self.allreduce_gradients(async_op=True, params=[p for g in optimizer.param_groups for p in g["params"]])
+            # the scalar loss rides along while the gradient collectives are in flight
+            n_loc, n_glob = self.batch, self._global_trials()
+            err = parallel.allreduce_scalar(error.detach().double() * (n_loc / n_glob))
+            if sync is not None:
+                sync.wait()
+            optimizer.step(**step_kwargs)
+            return err.item()
         optimizer.step(**step_kwargs)
         return error.item()
+
+    # ---- trial-sharded data parallelism (one process per GPU; SURVEY 8e) -----------------------------------------
+    def _global_trials(self) -> int:
+        if getattr(self, "_dp_trials", None) is None or self._dp_trials[0] != self.batch:
+            self._dp_trials = (self.batch, parallel.global_trial_count(self.batch, device=self._engine_device()))
+        return self._dp_trials[1]
+
+    def allreduce_gradients(self, async_op: bool = False, params=None):
+        """Sum the `.grad` of every trainable parameter of the network over the ranks of `torch.distributed`, weighted by
+        the ranks' trial counts (`batch` of each replica).  `fit_bptt` calls this itself before every optimizer step; a
+        user-level loop (`obs = net.run(...); loss.backward(); net.allreduce_gradients(); opt.step()`) calls it by hand.
+        No-op without an initialised process group.  async_op=True returns a handle whose `.wait()` must precede the
+        optimizer step."""
+        if not (parallel.dist.is_initialized() and parallel.dist.get_world_size() > 1):
+            return None
+        if params is None:
+            params = list(self.parameters())
+        return parallel.allreduce_gradients(params, self.batch, self._global_trials(), async_op=async_op)
 
     def fit_ridge(self, inputs, targets, sampling_steps: int = 100, alpha: float = 1e-4, verbose: bool = True,
                   add_readout_node: bool = True, **kwargs) -> Observer:
         """Ridge-regression readout on the recorded network states (rectipy/network.py:709-784); the state matrix
         stays on the device from the Observer recording to the normal-equation solve."""
         self.compile()
-        chain = self._get_chain()
-        dev = self.get_node(chain.diffeq).device
+        dev = self._engine_device()
         target_tensor = torch.as_tensor(np.asarray(targets) if not isinstance(targets, torch.Tensor) else targets,
                                         dtype=torch.float32).to(dev)
         if inputs.shape[0] != target_tensor.shape[0]:
@@ -797,6 +831,10 @@ class Network:
         edge.weights = edge.weights.contiguous()
         edge.P = edge.P.contiguous()
         loss, pred = engine.rls_run(X, tgt.reshape(X.shape[0], -1), edge.weights, edge.P, edge.beta, optim_steps)
+        if optim_steps > 1 and loss.numel():
+            # between updates the reference keeps reporting the loss of the last update (rectipy/network.py:1108-1118)
+            held = (torch.arange(loss.shape[0], device=loss.device) // optim_steps) * optim_steps
+            loss = loss.index_select(0, held)
         edge.loss = loss[-1] if loss.numel() else 0.0
         if obs is not None:
             steps = [t for t in range(X.shape[0]) if t % sampling_steps == 0]

@@ -96,6 +96,8 @@ class Observer:
                 self._recordings["loss"].extend([0.0] * len(steps))
             elif isinstance(loss, torch.Tensor) and loss.dim() > 0:
                 self._recordings["loss"].extend(loss.unbind(0))
+            elif isinstance(loss, (list, tuple)):
+                self._recordings["loss"].extend(loss)
             else:
                 self._recordings["loss"].extend([loss] * len(steps))
 

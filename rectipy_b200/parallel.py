@@ -40,45 +40,74 @@ def shard_trials(n_trials: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
-def allreduce_gradients(params: Iterable[torch.Tensor], n_trials_local: int = None, n_trials_global: int = None,
-                        bucket_bytes: int = 256 << 20) -> None:
-    """Sum parameter gradients over ranks in place (flat fp32 buckets, one collective per bucket).
+class GradientSync:
+    """Handles of an in-flight gradient all-reduce; `wait()` blocks the current stream until the sums have landed."""
 
-    If the local losses are *means* over local trials, pass the trial counts: each rank's gradient is weighted by
-    n_local / n_global before the sum, so the result equals the gradient of the global mean.
+    def __init__(self):
+        self.works = []
+        self.unpack = []          # (flat bucket, [grad tensors]) to scatter back after the collective
+
+    def wait(self) -> None:
+        for w in self.works:
+            w.wait()
+        for flat, grads in self.unpack:
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        self.works, self.unpack = [], []
+
+
+def allreduce_gradients(params: Iterable[torch.Tensor], n_trials_local: int = None, n_trials_global: int = None,
+                        bucket_bytes: int = 1 << 20, async_op: bool = False):
+    """Sum parameter gradients over ranks in place (fp32 sum all-reduce, NCCL over NVLink on the GPU box).
+
+    * Every parameter takes part, in the order given, on every rank: a parameter whose `.grad` is None on this rank (its
+      shard produced no dependence on it) contributes zeros, so the collectives' sizes never differ between ranks.
+    * A gradient of at least `bucket_bytes` (the recurrent weights: 64 MiB at N=4096, 256 MiB at N=8192) is reduced in
+      place, without staging copies; smaller ones are packed into one flat bucket per dtype.
+    * If the local losses are *means* over local trials, pass the trial counts: each rank's gradient is weighted by
+      n_local / n_global before the sum, so the result equals the gradient of the global mean.
+    * `async_op=True` returns a `GradientSync` right after the collectives are enqueued (on the communicator's own stream);
+      call `.wait()` before the optimizer step.  Otherwise the call waits itself and returns None.
     """
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
-        return
+        return None
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return None
     scale = None
     if n_trials_local is not None and n_trials_global is not None:
         scale = float(n_trials_local) / float(n_trials_global)
-    bucket: List[torch.Tensor] = []
-    size = 0
-
-    def flush():
-        nonlocal bucket, size
-        if not bucket:
-            return
-        flat = torch.cat([g.reshape(-1) for g in bucket])
+    sync = GradientSync()
+    small = {}                    # dtype -> [grad]
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+        g = p.grad
         if scale is not None:
-            flat.mul_(scale)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        off = 0
-        for g in bucket:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
-        bucket, size = [], 0
+            g.mul_(scale)
+        if g.is_contiguous() and g.numel() * g.element_size() >= bucket_bytes:
+            sync.works.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True))
+        else:
+            small.setdefault(g.dtype, []).append(g)
+    for dtype, grads in small.items():
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        sync.works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
+        sync.unpack.append((flat, grads))
+    if async_op:
+        return sync
+    sync.wait()
+    return None
 
-    for g in grads:
-        nbytes = g.numel() * g.element_size()
-        if size and size + nbytes > bucket_bytes:
-            flush()
-        bucket.append(g)
-        size += nbytes
-    flush()
+
+def global_trial_count(n_trials_local: int, device=None) -> int:
+    """Sum of the ranks' local trial counts (one scalar all-reduce; call once per fit, not per step)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return int(n_trials_local)
+    t = torch.tensor([float(n_trials_local)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(round(float(t.item())))
 
 
 def allreduce_scalar(value: torch.Tensor, op=None) -> torch.Tensor:

@@ -1,5 +1,7 @@
 """CPU tests of the host logic (no compute): template front-end, graph construction/compile rules, error types,
 Observer, utilities.  Mirrors the structural parts of rectipy_tests/test_network.py and test_edges.py."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -264,6 +266,20 @@ def test_linear_edge_known_answer():
         xx, yy = torch.randn(5, dtype=torch.float64), torch.randn(2, dtype=torch.float64)
         rls.update(xx, yy, rls.forward(xx)); orls.update(xx, yy, orls.forward(xx))
     assert torch.allclose(rls.weights, orls.weights, atol=1e-12) and torch.allclose(rls.P, orls.P, atol=1e-12)
+
+
+def test_square_edge_weights_follow_the_reference_transposition():
+    """rectipy/edges.py:22-23,160-161: weights (and masks) of shape (n_in, n_out) are transposed, which for a square matrix is
+    ALWAYS the case -- a user's N x N matrix acts as its transpose.  Fixture: outputs of the unmodified reference classes."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "edges_square.npz"))
+    n = z["w"].shape[0]
+    lin = rp.Linear(n, n, weights=z["w"].copy(), dtype=torch.float64)
+    msk = rp.LinearMasked(n, n, mask=z["mask"].copy(), weights=z["w"].copy(), dtype=torch.float64)
+    assert np.array_equal(lin.weights.numpy(), z["lin_weights"]) and np.array_equal(msk.mask.numpy(), z["masked_mask"])
+    assert np.array_equal(lin.weights.numpy(), z["w"].T)
+    for x, y_lin, y_msk in zip(z["xs"], z["lin_out"], z["masked_out"]):
+        assert np.allclose(lin.forward(torch.tensor(x)).numpy(), y_lin, atol=1e-14)
+        assert np.allclose(msk.forward(torch.tensor(x)).numpy(), y_msk, atol=1e-14)
 
 
 @pytest.mark.parametrize("T,S,cutoff", [(100, 1, 0), (100, 2, 0), (600, 5, 7), (50, 4, 49), (20, 7, 3), (10, 3, 12)])

@@ -37,6 +37,40 @@ def _worker(rank, world, port, ret):
     ok = torch.allclose(Wp.grad, W2.grad, atol=1e-12) and torch.allclose(bp.grad, b2.grad, atol=1e-12)
     tot = parallel.allreduce_scalar(torch.tensor([float(hi - lo)]))
     ok = ok and float(tot) == n_trials
+    ok = ok and parallel.global_trial_count(hi - lo) == n_trials
+    # a parameter without a gradient on ONE rank still takes part (zeros), so the collectives' sizes match
+    qa = torch.ones(40, dtype=torch.float64, requires_grad=True)
+    qb = torch.ones(3, dtype=torch.float32, requires_grad=True)
+    if rank == 0:
+        (qa.sum() * 2.0).backward()
+    (qb.sum() * float(rank + 1)).backward()
+    h = parallel.allreduce_gradients([qa, qb], bucket_bytes=64, async_op=True)
+    h.wait()
+    ok = ok and torch.allclose(qa.grad, torch.full((40,), 2.0, dtype=torch.float64)) and torch.allclose(qb.grad, torch.full((3,), 3.0))
+
+    # Network._bptt_step (rectipy/network.py:1123-1130) with trials sharded over the ranks == one process on the global batch
+    import rectipy_b200 as rp
+
+    class Stub(rp.Network):
+        def __init__(self, batch, params):
+            self.batch, self._params = batch, params
+
+        def _engine_device(self):
+            return torch.device("cpu")
+
+        def parameters(self, recurse=True):
+            return iter(self._params)
+
+    tgt = torch.randn(n_trials, 5, dtype=torch.float64)
+    Wl = torch.ones(5, 5, dtype=torch.float64, requires_grad=True)
+    net = Stub(hi - lo, [Wl])
+    opt = torch.optim.SGD([Wl], lr=0.1)
+    err = net._bptt_step(data[lo:hi] @ Wl, tgt[lo:hi], optimizer=opt, loss=torch.nn.MSELoss(), error_kwargs={}, step_kwargs={})
+    Wg = torch.ones(5, 5, dtype=torch.float64, requires_grad=True)
+    og = torch.optim.SGD([Wg], lr=0.1)
+    lg = torch.nn.MSELoss()(data @ Wg, tgt)
+    lg.backward(); og.step()
+    ok = ok and torch.allclose(Wl, Wg, atol=1e-12) and abs(err - float(lg)) < 1e-12
     ret[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
