@@ -78,6 +78,7 @@ struct rp_plan {
     float2* mf = nullptr;    // iku: [B] per-trial {mean v, mean spike} of the state being stepped
     float2* asum = nullptr;  // iku: [B] per-trial means of the recovery-variable adjoint terms
     float* dWraw = nullptr;  // [N][ldw]
+    float* dwout_part = nullptr;   // fused reverse kernel: [B/32][k][N] partial sums of dW_out
     float* wg_g = nullptr;   // few-trial FFMA path: g_t and r_t of several steps, [chunk*B][N] each, so that the
     float* wg_src = nullptr; // read-modify-write of dW happens once per chunk (rank chunk*B update) instead of every step
     int wg_chunk = 0;
@@ -417,7 +418,7 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
 
 void rp_plan_destroy(rp_plan* p) {
     if (!p) return;
-    float* bufs[] = {p->Wk, p->WkT, p->u, p->g, p->src, p->adj, p->win_acc, p->pp, p->dWraw, p->ps_vec, p->wg_g, p->wg_src};
+    float* bufs[] = {p->Wk, p->WkT, p->u, p->g, p->src, p->adj, p->win_acc, p->pp, p->dWraw, p->ps_vec, p->wg_g, p->wg_src, p->dwout_part};
     for (float* b : bufs) if (b) cudaFree(b);
     if (p->ps_bar) cudaFree(p->ps_bar);
     if (p->mf) cudaFree(p->mf);
@@ -678,6 +679,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         ++p->launches;
         RP_LAUNCH_CHECK();
         RP_CUDA(cudaMemsetAsync(p->tc.meta + rp::TCM_G_AMAX0, 0, 6 * sizeof(float), st));      // G_AMAX0/1, CHUNK[2][2]
+        RP_CUDA(cudaMemsetAsync(p->tc.meta + rp::TCM_NB0, 0, 3 * sizeof(float), st));
     }
     if (need_dW) RP_CUDA(cudaMemsetAsync(p->dWraw, 0, (size_t)wg_slices * N * p->ldw * sizeof(float), st));
     for (int q = 0; q < RP_NUM_PARAMS; ++q)
@@ -759,6 +761,26 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     for (int q = 0; q < RP_NUM_PARAMS; ++q) if (aa.dparams[q]) pgrad = true;
     // vectorised stand-alone adjoint kernel: tensor-core shapes, no per-neuron parameter sums (dW_out then comes from k_readout_grad)
     const bool adj_v4 = p->use_tc && !pgrad && !a->dW_in && !a->g_x && !p->per_trial && !getenv("RP_NO_ADJ_V4");
+    // one fused kernel per reverse step instead of k_adj_step_v5 + k_adj_convert_f16 (+ k_readout_grad): the spiking templates whose
+    // a_{t-1}[v] does not involve Z_{t-1} (see k_adj_fused_f16)
+    const bool fused = f16 && adj_v4 && spk && !rp::is_ik(d.model) && !overlap && aa.src == nullptr && (size_t)B * N < (1u << 31) &&
+                       (d.out_mode == RP_OUT_READOUT || !a->g_out_rec) && !(d.model == RP_LIF && d.in_target == 1) && !getenv("RP_NO_ADJ_FUSED");
+    const bool fold_ro = fused && a->dW_out && a->g_out_rec && a->T > 0 && d.out_mode == RP_OUT_READOUT && d.out_var == RP_VAR_S;
+    int nbr = 0;                    // fused: meta slot TCM_NB0 + nbr holds the bound the next fused launch reads
+    int g_scale_slot = rp::TCM_NB0; // fused: slot whose bound scaled the K-major g operand currently in the workspace
+    if (fused && a->T > 0) {
+        if (a->g_yT) {               // bound of g_{T-1} = dt * gate * a_T[v]
+            rp::k_amax_2d<<<p->sm_count * 4, 256, 0, st>>>(1, (int)plane, p->adj, plane, nullptr, 0, p->tc.meta + rp::TCM_NB0);
+            rp::k_scale_scalar<<<1, 32, 0, st>>>(p->tc.meta + rp::TCM_NB0, d.dt);
+            p->launches += 2;
+            RP_LAUNCH_CHECK();
+        }
+        if (fold_ro) {
+            const size_t np = (size_t)(B / rp::FA_TB) * d.n_out * N;
+            if (!p->dwout_part) { if (plan_alloc(p, &p->dwout_part, np)) return 1; }
+            RP_CUDA(cudaMemsetAsync(p->dwout_part, 0, np * sizeof(float), st));
+        }
+    }
     aa.mf_t = p->mf; aa.asum = p->asum;
     dim3 agrid((N + rp::ADJ_TX - 1) / rp::ADJ_TX, (B + rp::ADJ_TY * rp::ADJ_BPT - 1) / (rp::ADJ_TY * rp::ADJ_BPT));
     dim3 ablock(rp::ADJ_TX, rp::ADJ_TY);
@@ -823,7 +845,8 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         }
         {
             if (p->use_tc && aa.do_post) {
-                const rp::ScaleRef sg = f16 ? rp::ScaleRef{p->tc.meta + rp::TCM_G_AMAX0 + gslot, 0.f, rp::CV_HG} : rp::no_scale();
+                const rp::ScaleRef sg = fused ? rp::ScaleRef{p->tc.meta + g_scale_slot, 0.f, rp::CV_HGB}
+                                              : (f16 ? rp::ScaleRef{p->tc.meta + rp::TCM_G_AMAX0 + gslot, 0.f, rp::CV_HG} : rp::no_scale());
                 // The slice becomes eligible together with this step's adjoint product (both wait for the previous kernel of the
                 // chain) but is enqueued after it: the product takes its 128 SMs first, the slice's CTAs take the idle SMs and
                 // then every SM the product frees -- before the adjoint kernels, which fit beside them, become eligible.
@@ -836,7 +859,44 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                 ++p->launches;
                 if (slice_now && launch_slices(q_per_step, ws)) return 1;
             }
-            if (adj_v4) {
+            if (fused) {
+                rp::AdjArgs va = aa;
+                va.dW_out = nullptr; va.any_param_grad = 0; va.g = nullptr; va.g_amax = nullptr;
+                rp::FusedAdjArgs fa;
+                memset(&fa, 0, sizeof(fa));
+                fa.g_hi = p->tc.g_hi; fa.g_lo = p->tc.g_lo; fa.ld_g = p->tc.ldk;
+                if (need_dW && aa.do_pre) {
+                    fa.gT_hi = p->tc.gT_hi[0]; fa.gT_lo = p->tc.gT_lo[0]; fa.srcT_hi = p->tc.srcT_hi[0]; fa.srcT_lo = p->tc.srcT_lo[0];
+                    fa.ld_t = p->tc.ldt; fa.t_col0 = pending * B;
+                }
+                fa.nb_in = p->tc.meta + rp::TCM_NB0 + nbr;
+                fa.nb_out = p->tc.meta + rp::TCM_NB0 + (nbr + 1) % 3;
+                fa.nb_clear = p->tc.meta + rp::TCM_NB0 + (nbr + 2) % 3;
+                fa.chunk_ref_in = p->tc.meta + rp::TCM_CHUNK0 + cpar;
+                fa.chunk_ref_out = p->tc.meta + rp::TCM_CHUNK0 + (cpar ^ 1);
+                fa.chunk_first = pending == 0 ? 1 : 0;
+                fa.sc_src = rp::tc_scale_srcbound(&p->tc);
+                fa.flags = reinterpret_cast<int*>(p->tc.meta + rp::TCM_FLAGS);
+                if (aa.do_pre && a->g_out_rec) {
+                    const Window w1 = window_of(a->t_offset + t - 1, T_tot, a->sampling_steps, a->cutoff);
+                    if (w1.j >= 0) { fa.e_tm1 = a->g_out_rec + (size_t)w1.j * out_stride; fa.e_scale_tm1 = 1.0f / (float)w1.len; }
+                }
+                fa.dwout_part = fold_ro ? p->dwout_part : nullptr;
+                const dim3 fgrid(N / rp::FA_TN, B / rp::FA_TB);
+                const bool full = aa.do_post && aa.do_pre;
+#define RP_FUSED_LAUNCH(M_) (full ? rp::launch_pdl(rp::k_adj_fused_f16<M_, true>, fgrid, dim3(256), 0, st, va, fa) \
+                                  : rp::launch_pdl(rp::k_adj_fused_f16<M_, false>, fgrid, dim3(256), 0, st, va, fa))
+                switch (d.model) {
+                    case RP_QIF:     RP_FUSED_LAUNCH(RP_QIF); break;
+                    case RP_QIF_SFA: RP_FUSED_LAUNCH(RP_QIF_SFA); break;
+                    case RP_LIF:     RP_FUSED_LAUNCH(RP_LIF); break;
+                    default: return fail("rp_backward: internal error (fused adjoint kernel dispatch)");
+                }
+#undef RP_FUSED_LAUNCH
+                g_scale_slot = rp::TCM_NB0 + nbr;
+                nbr = (nbr + 1) % 3;
+                if (aa.do_pre) cpar ^= 1;
+            } else if (adj_v4) {
                 rp::AdjArgs va = aa;
                 va.dW_out = nullptr; va.any_param_grad = 0;
                 // rolling-pipeline kernel: spiking templates whose source value is not needed here (the conversion kernel reads
@@ -869,7 +929,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             RP_LAUNCH_CHECK();
         }
         ++p->launches;
-        if (f16 && aa.do_pre) {
+        if (f16 && aa.do_pre && !fused) {
             // the buffer about to be refilled must have been consumed by the side stream (chunk index - 2)
             if (overlap && pending == 0 && chunks_done >= 2) RP_CUDA(cudaStreamWaitEvent(st, p->tc.ev_done[cb_fill], 0));
             rp::ConvArgs ca;
@@ -923,7 +983,12 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         RP_CUDA(cudaEventRecord(p->tc.ev_join, ws));
         RP_CUDA(cudaStreamWaitEvent(st, p->tc.ev_join, 0));
     }
-    if (adj_v4 && a->dW_out && a->g_out_rec && a->T > 0) {
+    if (fold_ro) {
+        const size_t nk = (size_t)d.n_out * N;
+        rp::k_sum_parts<<<(int)std::min<size_t>((nk + 255) / 256, 1024), 256, 0, st>>>(p->dwout_part, B / rp::FA_TB, nk, a->dW_out);
+        ++p->launches;
+        RP_LAUNCH_CHECK();
+    } else if (adj_v4 && a->dW_out && a->g_out_rec && a->T > 0) {
         for (int t0 = 0; t0 < a->T; t0 += 32768) {            // grid.y limit
             const int tn = std::min(32768, a->T - t0);
             dim3 rgrid((N + 127) / 128, tn, (B + rp::RG_TB - 1) / rp::RG_TB);

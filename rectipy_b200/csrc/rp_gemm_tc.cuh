@@ -568,7 +568,9 @@ inline bool tc_supported(int N, int B) { return N % 128 == 0 && B % 128 == 0 && 
 
 // device-resident scalars of the binary16 path (one small float array per plan)
 // TCM_CHUNK0 + 2*buffer + parity: reference maximum of the weight-gradient chunk being written into that operand buffer
-enum { TCM_AMAX_W = 0, TCM_AMAX_WOUT, TCM_SRC_BOUND, TCM_G_AMAX0, TCM_G_AMAX1, TCM_CHUNK0, TCM_FLAGS = TCM_CHUNK0 + 4, TCM_COUNT = 16 };
+// TCM_NB0..2: rotating bounds of max |g| of the fused reverse kernel (read / accumulate / clear, see k_adj_fused_f16)
+enum { TCM_AMAX_W = 0, TCM_AMAX_WOUT, TCM_SRC_BOUND, TCM_G_AMAX0, TCM_G_AMAX1, TCM_CHUNK0, TCM_FLAGS = TCM_CHUNK0 + 4, TCM_NB0, TCM_COUNT = 16 };
+static_assert(TCM_NB0 + 3 <= TCM_COUNT, "meta slots");
 
 struct TcWorkspace {
     int N = 0, B = 0, ldk = 0, ldt = 0, wgrad_chunk = 0;

@@ -150,7 +150,8 @@ struct ScaleRef {
 __host__ __device__ inline ScaleRef no_scale() { return ScaleRef{nullptr, 0.f, 0}; }
 __device__ __forceinline__ int expo_for(float bound, int H) {
     if (!(bound > 0.f) || bound > 3.0e38f) return 0;
-    const int e = H - 1 - ilogbf(bound);
+    // exponent field instead of ilogbf(): identical for normal numbers, and a subnormal bound clamps to +100 either way
+    const int e = H - 1 - (int)((__float_as_uint(bound) >> 23) & 0xffu) + 127;
     return max(-100, min(100, e));
 }
 __device__ __forceinline__ float exp2i(int e) { return __int_as_float((e + 127) << 23); }       // 2^e, |e| <= 126
@@ -1252,6 +1253,287 @@ __global__ void __launch_bounds__(256) k_adj_convert_f16(ConvArgs a) {
     }
     trace_end(trace);
 }
+
+// ------------------------------------------------------------------------------------------------------
+// Fused reverse element-wise step of the binary16 path (round 2): ONE kernel per reverse step does what k_adj_step_v5 +
+// k_adj_convert_f16 (+ k_readout_grad after the sweep) did in two kernels and an fp32 round trip of g:
+//   post  adjoint of step t from Z_t = (kW)^T g_t                                   
+//   pre   g_{t-1} = dt * gate_{t-1} * a_t, written straight as split binary16 operands: K-major (next adjoint product) and
+//         trial-major together with s_{t-1} (weight-gradient chunk; transposed through shared memory)
+//   dW_out contribution of step t-1 (readout from s): per-trial-block partial sums, plain read-modify-write -> deterministic
+// The K-major scale no longer needs the exact max |g_{t-1}| (which is only known when the kernel has finished): for the
+// spiking templates a_{t-1}[v] is a function of (a_t, v_{t-1}) alone -- it does not involve Z_{t-1} -- so THIS kernel
+// evaluates |a_{t-1}[v]| for every element it holds and leaves  nb = dt * max|a_{t-1}[v]| >= max|g_{t-2}|  for the next
+// kernel (three rotating device scalars: read / accumulate / clear).  The bound is tight up to the spike gate of step t-2,
+// it is mapped to [2^12, 2^13) (CV_HGB), and a range guard flags any element that would leave the binary16 range anyway.
+// ------------------------------------------------------------------------------------------------------
+constexpr int CV_HGB = 13;
+struct FusedAdjArgs {
+    void *g_hi, *g_lo; int ld_g;
+    void *gT_hi, *gT_lo, *srcT_hi, *srcT_lo; int ld_t, t_col0;     // gT_hi == nullptr: no weight gradient wanted
+    const float* nb_in;          // bound of max |g_{t-1}| (complete: written by the previous kernel of the sweep)
+    float* nb_out;               // receives the bound of max |g_{t-2}| (atomicMax, zero on entry)
+    float* nb_clear;             // the slot the NEXT kernel accumulates into, zeroed here
+    const float* chunk_ref_in;   // reference maximum of the open weight-gradient chunk (as in ConvArgs)
+    float* chunk_ref_out;
+    int chunk_first;
+    ScaleRef sc_src;
+    int* flags;                  // bit 0: weight-gradient chunk range exceeded; bit 1: K-major operand range exceeded
+    const float* e_tm1;          // dL/d out_rec of the record window that contains step t-1 ([B][k] | [B][N]) or nullptr
+    float e_scale_tm1;
+    float* dwout_part;           // [B / FA_TB][k][N] partial sums of dW_out (readout from s), or nullptr
+};
+
+constexpr int FA_TN = 64, FA_TB = 32, FA_LD = FA_TB + 1;
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// per-neuron constants of the reverse step, reciprocals hoisted (the generic adj_post_math divides per element)
+struct FaRow { float fa, ds, dx, alpha, c1; };
+template <int MODEL>
+__device__ __forceinline__ FaRow fa_row(const AdjArgs& a, int i) {
+    FaRow r;
+    const float dt_tau = a.dt * rcp_approx(ldp(a.mp, RP_P_TAU, i));         // (an IEEE division costs ~15 instructions and a slow path)
+    r.fa = MODEL == RP_LIF ? 1.0f - dt_tau : 2.0f * dt_tau;                 // d v_{t+1} / d v_t = fa (lif) | 1 + fa v_t (qif)
+    r.ds = 1.0f - a.dt * rcp_approx(ldp(a.mp, RP_P_TAU_S, i));
+    r.dx = 1.f; r.alpha = 0.f; r.c1 = dt_tau;
+    if (MODEL == RP_QIF_SFA) { r.dx = 1.0f - a.dt * rcp_approx(ldp(a.mp, RP_P_TAU_X, i)); r.alpha = ldp(a.mp, RP_P_ALPHA, i); }
+    return r;
+}
+// FULL: both halves of the step run (every launch of a sweep but its first and last) -- the flags become compile-time constants
+template <int MODEL, bool FULL>
+__global__ void __launch_bounds__(256, 3) k_adj_fused_f16(AdjArgs a, FusedAdjArgs f) {
+    constexpr int NSV = ModelTraits<MODEL>::NSV;
+    constexpr bool SFA = MODEL == RP_QIF_SFA;
+    static_assert(MODEL == RP_QIF || MODEL == RP_QIF_SFA || MODEL == RP_LIF, "templates whose a_{t-1}[v] does not involve Z_{t-1}");
+    __shared__ float tgT[FA_TN][FA_LD];        // g_{t-1}  [neuron][trial]  (row stride 33: conflict-free both ways)
+    __shared__ float tsT[FA_TN][FA_LD];        // s_{t-1}
+    __shared__ __align__(16) float se0[FA_TB][RP_MAX_OUT];    // e_t     of the tile's trials, divided by the window length
+    __shared__ __align__(16) float se1[FA_TB][RP_MAX_OUT];    // e_{t-1}
+    __shared__ __align__(16) float swo[RP_MAX_OUT][FA_TN];    // W_out columns of the tile's neurons
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;        // tx -> 4 neurons, ty -> trials ty, ty + 16
+    const int i0 = blockIdx.x * FA_TN + 4 * tx;
+    const int bblk = blockIdx.y * FA_TB;
+    const bool first = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+    const int N = a.N;
+    const int plane = a.B * N;                  // (host guarantees batch * n < 2^31)
+    const bool do_post = FULL || a.do_post, do_pre = FULL || a.do_pre;
+    pdl_launch_dependents();
+    pdl_wait();
+    TraceRec* trace = threadIdx.x == 0 ? trace_begin(TR_ADJ_STEP) : nullptr;
+    const bool wg = f.gT_hi != nullptr && do_pre;
+    const bool have_e0 = a.e_t != nullptr && do_post, have_e1 = f.e_tm1 != nullptr && do_pre;
+    const bool ro_acc = have_e1 && f.dwout_part != nullptr;
+    __shared__ float s_scale[3];               // operand scales of this step: one thread derives them, everyone reads after the barrier
+    __shared__ __align__(16) float s_row[FA_TN][SFA ? 8 : 2];      // per-neuron constants of the tile
+    if (threadIdx.x == 0) {
+        const float gb = *f.nb_in;
+        float sgT = 1.f, ssT = 1.f;
+        if (wg) {
+            const float ref_in = *f.chunk_ref_in;
+            const float ref = (f.chunk_first || !(ref_in > 0.f)) ? gb : ref_in;
+            const int ec = expo_for(ref, CV_HCHUNK);
+            const int elim = expo_for(gb, 15);
+            const int eu = gb > 0.f ? min(ec, elim) : ec;
+            const int comp = ec - eu;
+            const int es = scale_expo(f.sc_src);
+            sgT = exp2i(eu);
+            ssT = exp2i(es + min(comp, 3));
+            if (first) {
+                *f.chunk_ref_out = ref;
+                if (comp > 3) atomicOr(f.flags, 1);
+            }
+        }
+        s_scale[0] = exp2i(expo_for(gb, CV_HGB)); s_scale[1] = sgT; s_scale[2] = ssT;
+        if (first) *f.nb_clear = 0.f;
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + FA_TN) {        // warps 2-3: the tile's per-neuron constants
+        const int ii = threadIdx.x - 64;
+        const FaRow r = fa_row<MODEL>(a, blockIdx.x * FA_TN + ii);
+        s_row[ii][0] = r.fa; s_row[ii][1] = r.ds;
+        if (SFA) { s_row[ii][2] = r.dx; s_row[ii][3] = r.alpha; s_row[ii][4] = r.c1; }
+    }
+    {   // readout-gradient operands of the tile (READOUT mode only; the host keeps dense-output problems off this kernel)
+        const int bl = threadIdx.x / RP_MAX_OUT, q = threadIdx.x % RP_MAX_OUT;        // 32 x 8 == blockDim
+        se0[bl][q] = (have_e0 && q < a.k) ? __ldg(a.e_t + (size_t)(bblk + bl) * a.k + q) * a.e_scale : 0.f;
+        se1[bl][q] = (have_e1 && q < a.k) ? __ldg(f.e_tm1 + (size_t)(bblk + bl) * a.k + q) * f.e_scale_tm1 : 0.f;
+        if (have_e0 || have_e1) {
+            for (int idx = threadIdx.x; idx < RP_MAX_OUT * FA_TN; idx += 256) {
+                const int qq = idx / FA_TN, ii = idx % FA_TN;
+                swo[qq][ii] = qq < a.k ? __ldg(a.W_out + (size_t)qq * N + blockIdx.x * FA_TN + ii) : 0.f;
+            }
+        }
+    }
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 av[2], as[2], ax[2], v[2], Z[2], vm[2], sm[2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        const int b = bblk + l * 16 + ty;
+        const int idx = b * N + i0;
+        av[l] = *reinterpret_cast<const float4*>(a.adj + idx);
+        as[l] = *reinterpret_cast<const float4*>(a.adj + plane + idx);
+        ax[l] = NSV > 2 ? *reinterpret_cast<const float4*>(a.adj + 2 * (size_t)plane + idx) : zero;
+        v[l] = Z[l] = vm[l] = sm[l] = zero;
+        if (do_post) {
+            v[l] = __ldg(reinterpret_cast<const float4*>(a.y_t + idx));
+            Z[l] = *reinterpret_cast<const float4*>(a.Z + (size_t)b * a.ldz + i0);
+        }
+        if (do_pre) {
+            vm[l] = __ldg(reinterpret_cast<const float4*>(a.y_tm1 + idx));
+            if (wg || ro_acc) sm[l] = __ldg(reinterpret_cast<const float4*>(a.y_tm1 + plane + idx));
+        }
+    }
+    __syncthreads();                       // scales / row constants / se0 / se1 / swo are staged (the loads above stay in flight)
+    const float sg = s_scale[0], sgT = s_scale[1], ssT = s_scale[2];
+    FaRow row[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        row[rr].fa = s_row[4 * tx + rr][0]; row[rr].ds = s_row[4 * tx + rr][1];
+        row[rr].dx = SFA ? s_row[4 * tx + rr][2] : 1.f; row[rr].alpha = SFA ? s_row[4 * tx + rr][3] : 0.f; row[rr].c1 = SFA ? s_row[4 * tx + rr][4] : 0.f;
+    }
+    const int ov = a.out_var;
+    const float theta = a.theta, slope = a.slope, dt = a.dt;
+    const bool cut = a.zero_after_post != 0;
+    float nbmax = 0.f, gabs = 0.f;
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        const int bl = l * 16 + ty;
+        const int b = bblk + bl;
+        const int idx = b * N + i0;
+        // readout terms of the 4 neurons: W_out^T e_t (enters a_t) and W_out^T e_{t-1} (enters the bound when the output is v)
+        float ro0[4] = {0.f, 0.f, 0.f, 0.f}, ro1[4] = {0.f, 0.f, 0.f, 0.f};
+        if (have_e0) {
+#pragma unroll 1
+            for (int q = 0; q < a.k; ++q) {
+                const float4 w4 = *reinterpret_cast<const float4*>(&swo[q][4 * tx]);
+                const float e0 = se0[bl][q];
+                ro0[0] = fmaf(w4.x, e0, ro0[0]); ro0[1] = fmaf(w4.y, e0, ro0[1]); ro0[2] = fmaf(w4.z, e0, ro0[2]); ro0[3] = fmaf(w4.w, e0, ro0[3]);
+            }
+        }
+        if (have_e1 && ov == RP_VAR_V) {
+#pragma unroll 1
+            for (int q = 0; q < a.k; ++q) {
+                const float4 w4 = *reinterpret_cast<const float4*>(&swo[q][4 * tx]);
+                const float e1 = se1[bl][q];
+                ro1[0] = fmaf(w4.x, e1, ro1[0]); ro1[1] = fmaf(w4.y, e1, ro1[1]); ro1[2] = fmaf(w4.z, e1, ro1[2]); ro1[3] = fmaf(w4.w, e1, ro1[3]);
+            }
+        }
+        float nav[4], nas[4], nax[4], g[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            nav[rr] = f4at(av[l], rr); nas[rr] = f4at(as[l], rr); nax[rr] = f4at(ax[l], rr);
+            if (do_post) {
+                // adjoint of step t: spike gate on the v row, surrogate coupling of (s, x) into v
+                const float vr = f4at(v[l], rr);
+                const float gv = vr >= theta ? 0.f : nav[rr];
+                const float dq = fmaf(slope, fabsf(vr - theta), 1.0f);
+                const float sgr = rcp_approx(dq * dq);                              // Spike.backward, nodes.py:478-481
+                const float F = MODEL == RP_LIF ? row[rr].fa : fmaf(row[rr].fa, vr, 1.0f);
+                const float coup = SFA ? fmaf(row[rr].alpha, nax[rr], nas[rr]) : nas[rr];
+                float n_v = fmaf(gv, F, sgr * coup);
+                float n_s = fmaf(nas[rr], row[rr].ds, f4at(Z[l], rr));
+                float n_x = SFA ? fmaf(nax[rr], row[rr].dx, -row[rr].c1 * gv) : 0.f;
+                if (ov == RP_VAR_V) n_v += ro0[rr]; else if (ov == RP_VAR_S) n_s += ro0[rr]; else if (ov == RP_VAR_X) n_x += ro0[rr];
+                if (cut) { n_v = 0.f; n_s = 0.f; n_x = 0.f; }
+                nav[rr] = n_v; nas[rr] = n_s; nax[rr] = n_x;
+            }
+            g[rr] = 0.f;
+            if (do_pre) {
+                const float vmr = f4at(vm[l], rr);
+                const float gn = vmr >= theta ? 0.f : nav[rr];                      // gate_{t-1} a_t[v]
+                g[rr] = dt * gn;
+                // |a_{t-1}[v]| of this element: the next kernel evaluates the same expression from the same stored values
+                const float dq = fmaf(slope, fabsf(vmr - theta), 1.0f);
+                const float sgr = rcp_approx(dq * dq);
+                const float F = MODEL == RP_LIF ? row[rr].fa : fmaf(row[rr].fa, vmr, 1.0f);
+                const float coup = SFA ? fmaf(row[rr].alpha, nax[rr], nas[rr]) : nas[rr];
+                float nv = fmaf(gn, F, sgr * coup);
+                if (ov == RP_VAR_V) nv += ro1[rr];
+                nbmax = fmaxf(nbmax, fabsf(nv));
+                gabs = fmaxf(gabs, fabsf(g[rr]));
+            }
+        }
+        if (do_post) {
+            *reinterpret_cast<float4*>(a.adj + idx) = make_float4(nav[0], nav[1], nav[2], nav[3]);
+            *reinterpret_cast<float4*>(a.adj + plane + idx) = make_float4(nas[0], nas[1], nas[2], nas[3]);
+            if (NSV > 2) *reinterpret_cast<float4*>(a.adj + 2 * (size_t)plane + idx) = make_float4(nax[0], nax[1], nax[2], nax[3]);
+        }
+        if (do_pre) {
+            store_split4_f16(f.g_hi, f.g_lo, (size_t)b * f.ld_g + i0, g, sg);
+            if (wg || ro_acc) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) { tgT[4 * tx + rr][bl] = g[rr]; tsT[4 * tx + rr][bl] = f4at(sm[l], rr); }
+            }
+        }
+    }
+    if (do_pre) {
+        nbmax = warp_max(nbmax);
+        if ((threadIdx.x & 31) == 0 && nbmax > 0.f) atomic_max_nonneg(f.nb_out, dt * nbmax * 1.001f);
+        if (!(gabs * sg < 60000.0f)) atomicOr(f.flags, 2);
+    }
+    trace_end(trace);
+    if (wg || ro_acc) {
+        __syncthreads();
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (wg) {
+            // half-warp -> one neuron row, lane -> two consecutive trials: every store instruction writes 2 x 64 contiguous bytes
+            const int c = 2 * (lane & 15);
+            __half* gth = reinterpret_cast<__half*>(f.gT_hi); __half* gtl = reinterpret_cast<__half*>(f.gT_lo);
+            __half* sth = reinterpret_cast<__half*>(f.srcT_hi); __half* stl = reinterpret_cast<__half*>(f.srcT_lo);
+#pragma unroll
+            for (int j = 0; j < FA_TN / 16; ++j) {
+                const int r = 16 * j + 2 * w + (lane >> 4);
+                const size_t off = (size_t)(blockIdx.x * FA_TN + r) * f.ld_t + f.t_col0 + bblk + c;
+                __half h0, l0, h1, l1;
+                split_f16(tgT[r][c] * sgT, h0, l0); split_f16(tgT[r][c + 1] * sgT, h1, l1);
+                *reinterpret_cast<__half2*>(gth + off) = __halves2half2(h0, h1);
+                *reinterpret_cast<__half2*>(gtl + off) = __halves2half2(l0, l1);
+                split_f16(tsT[r][c] * ssT, h0, l0); split_f16(tsT[r][c + 1] * ssT, h1, l1);
+                *reinterpret_cast<__half2*>(sth + off) = __halves2half2(h0, h1);
+                *reinterpret_cast<__half2*>(stl + off) = __halves2half2(l0, l1);
+            }
+        }
+        if (ro_acc) {
+            // dW_out[q][i] += sum_b e_{t-1}[b][q] s_{t-1}[b][i] over the tile's 32 trials: thread (i, trial octet) -> partial sums,
+            // summed over the four octets in a fixed order, then one plain read-modify-write per (q, i) of this block's own slice
+            const int i = threadIdx.x & 63, grp = threadIdx.x >> 6;
+            float acc[RP_MAX_OUT];
+#pragma unroll
+            for (int q = 0; q < RP_MAX_OUT; ++q) acc[q] = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float sv = tsT[i][8 * grp + u];
+                const float4 ea = *reinterpret_cast<const float4*>(&se1[8 * grp + u][0]);
+                acc[0] = fmaf(ea.x, sv, acc[0]); acc[1] = fmaf(ea.y, sv, acc[1]); acc[2] = fmaf(ea.z, sv, acc[2]); acc[3] = fmaf(ea.w, sv, acc[3]);
+                if (a.k > 4) {
+                    const float4 eb = *reinterpret_cast<const float4*>(&se1[8 * grp + u][4]);
+                    acc[4] = fmaf(eb.x, sv, acc[4]); acc[5] = fmaf(eb.y, sv, acc[5]); acc[6] = fmaf(eb.z, sv, acc[6]); acc[7] = fmaf(eb.w, sv, acc[7]);
+                }
+            }
+            __syncthreads();                       // everyone is done reading tgT
+            float* red = &tgT[0][0];               // [4][RP_MAX_OUT][64] = 2048 floats <= 64 * 33
+#pragma unroll
+            for (int q = 0; q < RP_MAX_OUT; ++q) red[(grp * RP_MAX_OUT + q) * FA_TN + i] = acc[q];
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < a.k * FA_TN; idx += 256) {
+                const int q = idx / FA_TN, ii = idx % FA_TN;
+                const float tot = (red[(0 * RP_MAX_OUT + q) * FA_TN + ii] + red[(1 * RP_MAX_OUT + q) * FA_TN + ii]) +
+                                  (red[(2 * RP_MAX_OUT + q) * FA_TN + ii] + red[(3 * RP_MAX_OUT + q) * FA_TN + ii]);
+                float* dst = f.dwout_part + ((size_t)blockIdx.y * a.k + q) * N + blockIdx.x * FA_TN + ii;
+                *dst += tot;
+            }
+        }
+    }
+}
+
+// dst[j] = sum over parts (fixed order) of part[p][j]
+__global__ void __launch_bounds__(256) k_sum_parts(const float* __restrict__ part, int nparts, size_t n, float* dst) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int p = 0; p < nparts; ++p) acc += part[(size_t)p * n + j];
+        dst[j] = acc;
+    }
+}
+// *p *= v  (one thread)
+__global__ void k_scale_scalar(float* p, float v) { if (threadIdx.x == 0 && blockIdx.x == 0) *p *= v; }
 
 // max over a short device array (the per-step source maxima of the last forward pass) -> *dst
 __global__ void k_max_of_array(const float* src, int n, float* dst) {
