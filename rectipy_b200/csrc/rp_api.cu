@@ -557,6 +557,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
             RP_LAUNCH_CHECK();
         }
         fa.per_trial = p->per_trial ? 1 : 0;
+        fa.no_lean = getenv("RP_NO_FWD_LEAN") ? 1 : 0;
         if (!p->use_tc) {
             // u[b][i] = sum_j (kW)[i][j] src_t[b][j], then the element-wise step
             const float* srcp = spk ? cur + plane : p->src;

@@ -212,7 +212,7 @@ struct EpiFwd {
     }
 
     template <int BQ, bool F16>
-    __device__ __forceinline__ void run_tile(int p0, int q0, const float* tile, int et, float* /*extra*/) const {
+    __device__ __forceinline__ void run_tile(int p0, int q0, const float* tile, int et, float* extra) const {
         constexpr int NSV = ModelTraits<MODEL>::NSV;
         constexpr int NCOL = BQ / 8;
         const int w = et >> 5, l = et & 31;
@@ -225,6 +225,86 @@ struct EpiFwd {
             for (int rr = 0; rr < 4; ++rr) row[rr] = fwd_row<MODEL>(a, i0 + rr);
             const float so = F16 ? exp2i(scale_expo(a.sc_out)) : 1.f;
             float smax = 0.f;
+            // Round 2, lean loop for the headline templates (qif_op / lif_op, projected input of width <= 2, binary16 operands).
+            // ncu source page of the round-1 loop: 587 instructions per batch of 16 elements, of which ~240 integer / control
+            // (64-bit index arithmetic per access, the per-element in_mode / channel-loop branches, constant reloads) and IPC per
+            // warp ~0.15 -- with 8 warps per SM the loop is bound by the length of each warp's instruction stream, not by memory
+            // (a double-buffered cp.async pipeline for the state loads was measured: 31.35 vs 31.34 ms per pass, no gain).  Here:
+            // running pointers, input mode resolved once, packed binary16 conversions; the arithmetic is expression for expression that of
+            // fwd_elem_fast (a cheaper s' = fma(s, 1 - dt/tau_s, spike) moved a lif spike by a step in the parity tests).
+            if constexpr (!GEN && F16 && (MODEL == RP_QIF || MODEL == RP_LIF)) {
+                if (!a.no_lean && a.in_target == 0 && (a.in_mode == RP_IN_NONE || (a.in_mode == RP_IN_PROJ && a.m <= 2))) {
+                    constexpr int NB = 4;
+                    const int N = a.N;
+                    const bool proj = a.in_mode == RP_IN_PROJ;
+                    const int xm = proj ? a.m : 0;
+                    const float dt = a.dt, theta = a.theta, v_reset = a.v_reset;
+                    float its[4], eta[4], itau[4], wi0[4], wi1[4];
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        its[rr] = row[rr].inv_tau_s; eta[rr] = row[rr].eta; itau[rr] = row[rr].inv_tau;
+                        wi0[rr] = row[rr].wi0; wi1[rr] = (proj && a.m > 1) ? row[rr].wi1 : 0.f;
+                    }
+                    const size_t o0 = (size_t)(q0 + cbase) * N + i0;
+                    const float* yv = a.y_cur + o0;
+                    const float* ys = yv + plane;
+                    float* nv = a.y_next + o0;
+                    float* ns = nv + plane;
+                    __half* ph = reinterpret_cast<__half*>(a.src_hi) + (size_t)(q0 + cbase) * a.ld_src + i0;
+                    __half* pl = reinterpret_cast<__half*>(a.src_lo) + (size_t)(q0 + cbase) * a.ld_src + i0;
+                    const float* xp = proj ? a.x_t + (size_t)(q0 + cbase) * xm : nullptr;
+                    const float* ut = tile + (size_t)cbase * TC_BP + 4 * l;
+                    const int x1off = xm > 1 ? 1 : 0;
+                    for (int c = 0; c < NCOL; c += NB) {
+                        float4 u4[NB], v4[NB], s4[NB];
+                        float x0[NB], x1[NB];
+#pragma unroll
+                        for (int cc = 0; cc < NB; ++cc) {
+                            u4[cc] = *reinterpret_cast<const float4*>(ut + cc * TC_BP);
+                            v4[cc] = ldg4(yv + (size_t)cc * N);
+                            s4[cc] = ldg4(ys + (size_t)cc * N);
+                            x0[cc] = proj ? __ldg(xp + cc * xm) : 0.f;
+                            x1[cc] = proj ? __ldg(xp + cc * xm + x1off) : 0.f;
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < NB; ++cc) {
+                            float v1[4], s1[4];
+#pragma unroll
+                            for (int rr = 0; rr < 4; ++rr) {
+                                const float v = f4get(v4[cc], rr), sv = f4get(s4[cc], rr), u = f4get(u4[cc], rr);
+                                const float Iin = fmaf(wi1[rr], x1[cc], wi0[rr] * x0[cc]);
+                                const bool spike = v >= theta;                                   // heaviside(v - theta, 1.0)  nodes.py:383,476
+                                float vt;
+                                if constexpr (MODEL == RP_LIF) vt = fmaf(dt, fmaf(-v, itau[rr], u) + Iin + eta[rr], v);      // lif.yaml:10-15
+                                else vt = fmaf(dt, fmaf(fmaf(v, v, eta[rr]) + Iin, itau[rr], u), v);                           // qif.yaml:10-12
+                                s1[rr] = sv + dt * (-sv * its[rr]) + (spike ? 1.0f : 0.0f);      // same expression as every other path; dt * (spike / dt) == 1  nodes.py:385
+                                v1[rr] = spike ? v_reset : vt;                                   // reset blend  nodes.py:390
+                                smax = fmaxf(smax, fabsf(s1[rr]));
+                            }
+                            st4(nv + (size_t)cc * N, v1[0], v1[1], v1[2], v1[3]);
+                            st4(ns + (size_t)cc * N, s1[0], s1[1], s1[2], s1[3]);
+                            // binary16 split of the next source operand, two elements per conversion
+                            const __half2 h01 = __floats2half2_rn(s1[0] * so, s1[1] * so), h23 = __floats2half2_rn(s1[2] * so, s1[3] * so);
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            const __half2 l01 = __floats2half2_rn(fmaf(s1[0], so, -f01.x), fmaf(s1[1], so, -f01.y));
+                            const __half2 l23 = __floats2half2_rn(fmaf(s1[2], so, -f23.x), fmaf(s1[3], so, -f23.y));
+                            uint2 wh, wl;
+                            wh.x = *reinterpret_cast<const uint32_t*>(&h01); wh.y = *reinterpret_cast<const uint32_t*>(&h23);
+                            wl.x = *reinterpret_cast<const uint32_t*>(&l01); wl.y = *reinterpret_cast<const uint32_t*>(&l23);
+                            *reinterpret_cast<uint2*>(ph + (size_t)cc * a.ld_src) = wh;
+                            *reinterpret_cast<uint2*>(pl + (size_t)cc * a.ld_src) = wl;
+                        }
+                        yv += (size_t)NB * N; ys += (size_t)NB * N; nv += (size_t)NB * N; ns += (size_t)NB * N;
+                        ph += (size_t)NB * a.ld_src; pl += (size_t)NB * a.ld_src; ut += NB * TC_BP;
+                        if (proj) xp += NB * xm;
+                    }
+                    if (a.amax_out) {
+                        smax = warp_max(smax);
+                        if (l == 0 && smax > 0.f) atomic_max_nonneg(a.amax_out, smax);
+                    }
+                    return;
+                }
+            }
             // NB trials per batch: all their loads are issued before the first store (8 warps per SM have to cover the HBM
             // latency alone here: measured epilogue 35 us at 2 trials per batch, 25 us at 4, 43 us at 8; issuing batch k+1 before
             // batch k is computed -- 2+2 or 4+4 trials in flight -- measured 27 and 31 us: no better than plain batches of 4)

@@ -208,6 +208,7 @@ struct FwdStepArgs {
     float* urec_out;      // ik: checkpoint plane receiving the recurrent drive of this step [B][N], or nullptr
     const float2* mf;     // iku: per trial {mean_i v_t, mean_i spike_t} of the state being stepped (k_trial_means), else nullptr
     int per_trial;        // 1: some parameter differs between trials (no per-neuron hoisting)
+    int no_lean;          // 1: fused forward epilogue uses the generic element loop instead of the lean one (A/B runs)
 };
 
 template <int MODEL>
