@@ -315,6 +315,8 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), engine.total_launches() - l0
 
+    # CPU-side group for the final wait: ranks > 0 must not spin inside an NCCL barrier kernel while rank 0 runs its CPU baseline
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -322,6 +324,12 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
     ms_fwd, _ = timed(step_fwd, args.steps, 1)
+    # one more pass with a CUDA event before every launch of the step loops: device time per stage of the pass AS IT RUNS
+    plan0 = next(iter(engine._PLANS.values()))
+    plan0.stage_timing(True)
+    step_device()
+    stages = plan0.stage_times()
+    plan0.stage_timing(False)
 
     work = float(n) * B * T * args.steps * world
     value = work / (ms_dev * 1e-3)
@@ -359,20 +367,53 @@ def run_ours(args):
         ach = fl_f / (ms_f * 1e-3) / 1e12
         # share of one BPTT pass spent in the three contractions (per Euler step: 1 fwd + 1 adjoint + 1/chunk wgrad)
         chunk_steps = fl_w / (2.0 * n * n * B)
-        contr_ms = T * (ms_f + ms_b + ms_w / chunk_steps)
+        pass_ms = ms_dev / args.steps
+        # ---- per-stage entries from the event-timed pass (the kernels that actually run, gaps included) -----------------------
+        hbm = peaks["hbm"]
+        f_fwd, f_bptt = 2.0 * n + 2 * N_IN + 2 * N_OUT + 14, 6.0 * n + 60          # flops per neuron-step
+        adj_bytes = 44.0                                                              # B per neuron-step of the fused reverse kernel
+        names = {"fwd_fused": "rp::k_gemm_split3<256, EpiFwd<QIF>, f16=%d> (W.s contraction + Euler step + readout)" % int(f16),
+                 "dgrad": "rp::k_gemm_split3<256, EpiStore, f16=%d> (Z = (kW)^T g)" % int(f16),
+                 "wgrad": "rp::k_gemm_split3<256, EpiStore, f16=%d> (dW += g (x) s, K = %d steps x batch)" % (int(f16), int(chunk_steps)),
+                 "adjoint_elementwise": "rp::k_adj_fused_f16<QIF> (adjoint step + split operands + dW_out partials)",
+                 "other": "per-call kernels (weight split, maxima, dW finish) + the loss between the two calls"}
+        stage_total = sum(v[0] for v in stages.values()) or 1.0
+        kernels = {}
+        for key, (ms_tot, cnt) in stages.items():
+            ent = {"kernel": names[key], "launches": cnt, "ms_total": ms_tot, "ms_per_launch": ms_tot / max(cnt, 1), "share_of_pass": ms_tot / stage_total}
+            if key in ("fwd_fused", "dgrad") and cnt:
+                tf = 2.0 * n * n * B / (ent["ms_per_launch"] * 1e-3) / 1e12
+                ent.update(bound="tensor", achieved_tflops=tf, frac_of_burst_peak=tf / peak_logical, frac_of_sustained_peak=tf / (peaks["bf16_sustained"] / 3.0))
+            elif key == "wgrad" and cnt:
+                steps_cov = T          # all chunks of the pass together cover T steps
+                tf = 2.0 * n * n * B * steps_cov / (ms_tot * 1e-3) / 1e12
+                ent.update(bound="tensor", achieved_tflops=tf, frac_of_burst_peak=tf / peak_logical, frac_of_sustained_peak=tf / (peaks["bf16_sustained"] / 3.0))
+            elif key == "adjoint_elementwise" and cnt:
+                gbs = adj_bytes * n * B / (ent["ms_per_launch"] * 1e-3) / 1e9
+                ent.update(bound="hbm", algorithmic_bytes_per_launch=adj_bytes * n * B, achieved_gbs=gbs, frac_of_hbm_peak=gbs / hbm)
+            kernels[key] = ent
+        top = max((k for k in kernels if k != "other"), key=lambda k: kernels[k]["ms_total"])
+        contr_ms = sum(kernels[k]["ms_total"] for k in ("fwd_fused", "dgrad", "wgrad"))
+        top_ent = kernels[top]
         roofline = {
-            "bound": "tensor", "kernel": ("rp::k_gemm_split3<256, EpiStore, f16=%d>" % int(f16)) if use_tc else "rp::k_sgemm", "achieved": ach,
-            "peak": peak_logical, "unit": "TFLOP/s", "frac": ach / peak_logical, "traffic": _ncu_traffic(),
-            "note": (("achieved = logical 2*N*N*B flops per forward-contraction launch / CUDA-event launch time; the kernel issues "
-                      "3 kind::f16 MMAs (binary16 hi/lo split words, fp32 accumulate) per logical product, so peak = bf16_tflops burst (%s)/3"
-                      % peaks["source"]) if f16 else
-                     ("achieved = logical 2*N*N*B flops per forward-contraction launch / CUDA-event launch time; the kernel issues "
-                      "3 tf32 MMAs per logical product, so peak = max(bf16_tflops burst (%s)/2, cuBLAS tf32 8192^3 measured in this run = %.0f TF)/3"
-                      % (peaks["source"], tf32_measured))),
+            "bound": "tensor", "kernel": names[top], "achieved": top_ent.get("achieved_tflops", ach), "peak": peak_logical, "unit": "TFLOP/s",
+            "frac": top_ent.get("frac_of_burst_peak", ach / peak_logical), "traffic": _ncu_traffic(),
+            "note": ("the dominant kernel of the pass as it runs (largest share of the event-timed pass): achieved = logical 2*N*N*B flops per launch / "
+                     "mean launch-to-launch time incl. its element-wise epilogue and the launch gap; the kernel issues 3 kind::f16 MMAs "
+                     "(binary16 hi/lo split words, fp32 accumulate) per logical product, so peak = bf16_tflops burst (%s)/3; `kernels` holds every stage, "
+                     "`isolated_contractions` the bare contractions timed alone back to back" % peaks["source"]),
+            "kernels": kernels,
+            "whole_pass_frac": {"burst": f_bptt * value / 1e12 / peak_logical, "sustained": f_bptt * value / 1e12 / (peaks["bf16_sustained"] / 3.0),
+                                "fwd_only_burst": f_fwd * fwd_value / 1e12 / peak_logical,
+                                "flops_per_neuron_step": {"fwd": f_fwd, "bptt": f_bptt},
+                                "note": "algorithmic flops per neuron-step (SURVEY 8d) x measured neuron-steps/s / (measured bf16 peak / 3)"},
+            "isolated_contractions": {"launch_ms": {"fwd": ms_f, "adjoint": ms_b, "wgrad_chunk": ms_w, "wgrad_steps_per_chunk": chunk_steps},
+                                      "achieved_tflops": {"fwd": ach, "adjoint": fl_b / (ms_b * 1e-3) / 1e12, "wgrad": fl_w / (ms_w * 1e-3) / 1e12},
+                                      "frac_of_burst_peak": {"fwd": ach / peak_logical, "adjoint": fl_b / (ms_b * 1e-3) / 1e12 / peak_logical,
+                                                             "wgrad": fl_w / (ms_w * 1e-3) / 1e12 / peak_logical}},
             "tf32_cublas_tflops": tf32_measured,
-            "launch_ms": {"fwd": ms_f, "adjoint": ms_b, "wgrad_chunk": ms_w, "wgrad_steps_per_chunk": chunk_steps},
-            "achieved_all": {"fwd": ach, "adjoint": fl_b / (ms_b * 1e-3) / 1e12, "wgrad": fl_w / (ms_w * 1e-3) / 1e12},
-            "contraction_share_of_step": contr_ms / (ms_dev / args.steps),
+            "contraction_share_of_step": contr_ms / stage_total,
+            "stage_pass_ms": stage_total, "timed_pass_ms": pass_ms,
         }
         if args.no_cpu_baseline:
             cpu_rate, cores, cpu_sec = float("nan"), os.cpu_count(), float("nan")
@@ -406,7 +447,7 @@ def run_ours(args):
         }
         _OUT.emit(json.dumps(line))
     if world > 1:
-        dist.barrier(device_ids=[local_rank])
+        dist.barrier(group=cpu_group)         # a CPU wait: no GPU spins while rank 0 finishes its host-side work
         dist.destroy_process_group()
 
 

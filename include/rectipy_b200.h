@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RP_ABI_VERSION 6
+#define RP_ABI_VERSION 7
 #define RP_MAX_IN 8      /* max fused input-projection width  m (wider inputs: use RP_IN_DENSE)  */
 #define RP_MAX_OUT 8     /* max fused readout width           k (wider readouts: use RP_OUT_DENSE) */
 #define RP_MAX_SV 4
@@ -154,6 +154,16 @@ int rp_rls_run(int T, int n_in, int n_out, float beta_inv, const float* X, const
  * duration, *flops the algorithmic (logical, not x3) flop count of one launch.  Operands are whatever the plan's
  * workspaces currently hold (timing is data independent).  Synchronises the stream. */
 int rp_plan_time_contraction(rp_plan* plan, int which, int iters, float* avg_ms, double* flops, void* stream);
+
+/* Profiling hook: per-stage device time of the calls as they actually run.  rp_plan_stage_timing(plan, 1) makes rp_forward /
+ * rp_backward record a CUDA event on the launching stream before every launch of their step loops; rp_plan_stage_times
+ * synchronises, adds the event-to-event intervals up per stage and disarms nothing (call rp_plan_stage_timing(plan, 0) for that).
+ * ms[RP_NUM_STAGES] / marks[RP_NUM_STAGES]: 0 fused forward step (contraction + element-wise epilogue), 1 adjoint product
+ * Z = (kW)^T g, 2 weight-gradient chunk, 3 reverse element-wise kernel(s), 4 everything else between the first and last mark
+ * (per-call kernels, and whatever the caller enqueued between the two calls).  marks = intervals summed = launches of that stage. */
+#define RP_NUM_STAGES 5
+int rp_plan_stage_timing(rp_plan* plan, int enable);
+int rp_plan_stage_times(rp_plan* plan, float* ms, int* marks, void* stream);
 
 /* Debug / profiling aid: per-CTA timeline of the contraction and adjoint kernels.  rp_trace_enable(capacity > 0) arms a device
  * buffer of `capacity` records (0 disarms and frees it); rp_trace_read synchronises the device, copies up to max_records records

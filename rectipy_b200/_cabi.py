@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-RP_ABI_VERSION = 6
+RP_ABI_VERSION = 7
 RP_MAX_IN, RP_MAX_OUT, RP_MAX_SV, RP_MAX_REC = 8, 8, 4, 4
 RP_LI_TANH, RP_LI_SIGMOID, RP_QIF, RP_QIF_SFA, RP_LIF, RP_IK, RP_IKU, RP_IK_BIEXP = range(8)
 (RP_P_TAU, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_RMAX, RP_P_SIG_S, RP_P_V0,
@@ -18,6 +18,8 @@ RP_IN_NONE, RP_IN_DENSE, RP_IN_PROJ = range(3)
 RP_OUT_DENSE, RP_OUT_READOUT = range(2)
 RP_VAR_V, RP_VAR_S, RP_VAR_X, RP_VAR_R = range(4)
 RP_PREC_FP32, RP_PREC_3XTF32, RP_PREC_3XF16 = range(3)
+RP_NUM_STAGES = 5
+STAGE_NAMES = ("fwd_fused", "dgrad", "wgrad", "adjoint_elementwise", "other")
 
 _fp = C.c_void_p   # device pointers travel as plain integers
 
@@ -48,7 +50,8 @@ class rp_bwd_args(C.Structure):
 #: every symbol include/rectipy_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = ["rp_abi_version", "rp_last_error", "rp_num_state_vars", "rp_num_history_planes", "rp_num_records", "rp_plan_create",
            "rp_plan_destroy", "rp_plan_workspace_bytes", "rp_plan_launch_count", "rp_forward", "rp_backward", "rp_plan_status",
-           "rp_rls_run", "rp_gemm_tn", "rp_plan_time_contraction", "rp_trace_enable", "rp_trace_read"]
+           "rp_rls_run", "rp_gemm_tn", "rp_plan_time_contraction", "rp_trace_enable", "rp_trace_read", "rp_plan_stage_timing",
+           "rp_plan_stage_times"]
 
 _LIB = None
 
@@ -99,6 +102,10 @@ def load():
     lib.rp_rls_run.restype = C.c_int
     lib.rp_plan_time_contraction.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p]
     lib.rp_plan_time_contraction.restype = C.c_int
+    lib.rp_plan_stage_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.rp_plan_stage_timing.restype = C.c_int
+    lib.rp_plan_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_void_p]
+    lib.rp_plan_stage_times.restype = C.c_int
     lib.rp_gemm_tn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_void_p]
     lib.rp_gemm_tn.restype = C.c_int
     if lib.rp_abi_version() != RP_ABI_VERSION:

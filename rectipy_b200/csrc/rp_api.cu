@@ -7,6 +7,7 @@
 #include <string.h>
 #include <algorithm>
 #include <new>
+#include <vector>
 
 #include "../../include/rectipy_b200.h"
 #include "rp_kernels.cuh"
@@ -79,6 +80,11 @@ struct rp_plan {
     float2* asum = nullptr;  // iku: [B] per-trial means of the recovery-variable adjoint terms
     float* dWraw = nullptr;  // [N][ldw]
     float* dwout_part = nullptr;   // fused reverse kernel: [B/32][k][N] partial sums of dW_out
+    // optional per-stage timing (rp_plan_stage_timing): a CUDA event on the launching stream before every launch of the step loops
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_cat;
+    size_t ev_used = 0;
     float* wg_g = nullptr;   // few-trial FFMA path: g_t and r_t of several steps, [chunk*B][N] each, so that the
     float* wg_src = nullptr; // read-modify-write of dW happens once per chunk (rank chunk*B update) instead of every step
     int wg_chunk = 0;
@@ -94,6 +100,20 @@ struct rp_plan {
 };
 
 namespace {
+
+// stage categories of rp_plan_stage_times
+enum { ST_FWD = 0, ST_DGRAD = 1, ST_WGRAD = 2, ST_ADJ = 3, ST_OTHER = 4, ST_COUNT = RP_NUM_STAGES };
+// everything enqueued on `st` from here to the next mark is attributed to `cat`
+inline void stage_mark(rp_plan* p, int cat, cudaStream_t st) {
+    if (!p->timing) return;
+    if (p->ev_used == p->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { p->timing = false; return; }
+        p->ev_pool.push_back(e); p->ev_cat.push_back(ST_OTHER);
+    }
+    p->ev_cat[p->ev_used] = cat;
+    cudaEventRecord(p->ev_pool[p->ev_used++], st);
+}
 
 int plan_alloc(rp_plan* p, float** ptr, size_t n_floats) {
     RP_CUDA(cudaMalloc(reinterpret_cast<void**>(ptr), n_floats * sizeof(float)));
@@ -423,6 +443,7 @@ void rp_plan_destroy(rp_plan* p) {
     if (p->ps_bar) cudaFree(p->ps_bar);
     if (p->mf) cudaFree(p->mf);
     if (p->asum) cudaFree(p->asum);
+    for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
     rp::tc_workspace_destroy(&p->tc);
     delete p;
 }
@@ -451,6 +472,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
     const rp::ModelParams mp = make_params(p, a->params);
     const int fold = rp::fold_slot(d.model);
     const int kstride = d.param_per_neuron[fold] ? 1 : 0;
+    stage_mark(p, ST_OTHER, st);
 
     // weights: fold k into W once per call
     {
@@ -461,7 +483,11 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         else {
             RP_CUDA(cudaMemsetAsync(p->tc.meta + rp::TCM_AMAX_W, 0, 2 * sizeof(float), st));       // AMAX_W, AMAX_WOUT
             rp::k_amax_2d<<<p->sm_count * 4, 256, 0, st>>>(N, N, a->W, (size_t)N, a->params[fold], kstride, p->tc.meta + rp::TCM_AMAX_W);
-            rp::k_prepare_weights_f16<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, p->tc.ldk, p->tc.W_hi, p->tc.W_lo, nullptr, nullptr, rp::tc_scale_W(&p->tc));
+            // a call that keeps checkpoints is followed by rp_backward on the same weights: split the transpose in the same pass
+            const bool with_T = a->history != nullptr;
+            rp::k_prepare_weights_f16<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, p->tc.ldk, p->tc.W_hi, p->tc.W_lo,
+                                                            with_T ? p->tc.WT_hi : nullptr, with_T ? p->tc.WT_lo : nullptr, rp::tc_scale_W(&p->tc));
+            p->tc.wt_W = with_T ? a->W : nullptr;
             ++p->launches;
         }
         ++p->launches;
@@ -557,6 +583,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
             RP_LAUNCH_CHECK();
         }
         fa.per_trial = p->per_trial ? 1 : 0;
+        stage_mark(p, ST_FWD, st);
         fa.no_lean = getenv("RP_NO_FWD_LEAN") ? 1 : 0;
         if (!p->use_tc) {
             // u[b][i] = sum_j (kW)[i][j] src_t[b][j], then the element-wise step
@@ -602,11 +629,13 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
                 oa.rec_buf_j[r] = r < a->n_rec_vars ? a->rec_buf[r] + (size_t)w.j * (a->rec_reduce[r] ? (size_t)B : plane) : nullptr;
             }
             oa.rec_post = spk ? 0 : 1;     // RateNet: y is post-update (nodes.py:169); SpikeResetNet: pre-update (nodes.py:387)
+            stage_mark(p, ST_OTHER, st);
             RP_DISPATCH_MODEL(d.model, (rp::k_observe<M_><<<B, 256, 0, st>>>(oa)));
             ++p->launches;
             RP_LAUNCH_CHECK();
         }
     }
+    stage_mark(p, ST_OTHER, st);
     if (f16) { p->tc.fwd_history = a->history; p->tc.fwd_T = a->T; }
     RP_CUDA(cudaMemcpyAsync(a->yT, slot_ptr(a->T), slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return 0;
@@ -635,6 +664,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     const int kstride = d.param_per_neuron[fold] ? 1 : 0;
     const bool spk = spiking(d.model);
     const bool need_dW = a->dW != nullptr || a->dparams[rp::fold_slot(d.model)] != nullptr;
+    stage_mark(p, ST_OTHER, st);
 
     const int wg_slices = p->use_tc ? rp::TC_WGRAD_SPLITS : 1;
     if (need_dW && !p->dWraw) { if (plan_alloc(p, &p->dWraw, (size_t)wg_slices * N * p->ldw)) return 1; }
@@ -648,7 +678,9 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
         if (!p->use_tc) rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, nullptr, p->WkT, p->ldw, nullptr, nullptr, nullptr, nullptr);
         else if (!p->tc.f16) rp::k_prepare_weights<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, nullptr, nullptr, p->tc.ldk, nullptr, nullptr,
                                                                         (float*)p->tc.WT_hi, (float*)p->tc.WT_lo);
-        else {
+        else if (p->tc.wt_W == a->W && p->tc.fwd_history == a->history && a->history != nullptr) {
+            --p->launches;           // the forward call that wrote these checkpoints already split (kW)^T with the same scale
+        } else {
             RP_CUDA(cudaMemsetAsync(p->tc.meta + rp::TCM_AMAX_W, 0, sizeof(float), st));
             rp::k_amax_2d<<<p->sm_count * 4, 256, 0, st>>>(N, N, a->W, (size_t)N, a->params[fold], kstride, p->tc.meta + rp::TCM_AMAX_W);
             rp::k_prepare_weights_f16<<<grid, 256, 0, st>>>(N, a->W, a->params[fold], kstride, p->tc.ldk, nullptr, nullptr, p->tc.WT_hi, p->tc.WT_lo, rp::tc_scale_W(&p->tc));
@@ -856,10 +888,12 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                     RP_CUDA(cudaEventRecord(p->tc.ev_z, st));
                     RP_CUDA(cudaStreamWaitEvent(ws, p->tc.ev_z, 0));
                 }
+                stage_mark(p, ST_DGRAD, st);
                 if (rp::tc_gemm(&p->tc, rp::TC_DGRAD, p->u, p->ldu, 0, 0, st, sg)) return fail("rp_backward: %s", rp::tc_last_error());
                 ++p->launches;
                 if (slice_now && launch_slices(q_per_step, ws)) return 1;
             }
+            stage_mark(p, ST_ADJ, st);
             if (fused) {
                 rp::AdjArgs va = aa;
                 va.dW_out = nullptr; va.any_param_grad = 0; va.g = nullptr; va.g_amax = nullptr;
@@ -965,6 +999,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                 const int ref_slot = rp::TCM_CHUNK0 + 2 * cb_fill + cpar;
                 if (!overlap) {
                     const rp::ScaleRef sc = f16 ? rp::ScaleRef{p->tc.meta + ref_slot, 0.f, rp::CV_HCHUNK} : rp::no_scale();
+                    stage_mark(p, ST_WGRAD, st);
                     if (rp::tc_gemm(&p->tc, rp::TC_WGRAD, p->dWraw, p->ldw, pending * B, 1, st, sc, f16 ? cb_fill : 0)) return fail("rp_backward: %s", rp::tc_last_error());
                     ++p->launches;
                 } else {
@@ -979,6 +1014,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             }
         }
     }
+    stage_mark(p, ST_OTHER, st);
     if (overlap) {
         if (q_active && launch_slices(q_total, rest_stream)) return 1;
         RP_CUDA(cudaEventRecord(p->tc.ev_join, ws));
@@ -1092,6 +1128,33 @@ int rp_trace_read(void* host_buf, int max_records) {
     n = std::min(n, std::min(g_trace_capacity, (unsigned)max_records));
     if (cudaMemcpy(host_buf, g_trace_dev, (size_t)n * sizeof(rp::TraceRec), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return (int)n;
+}
+
+int rp_plan_stage_timing(rp_plan* p, int enable) {
+    if (!p) return fail("rp_plan_stage_timing: null argument");
+    p->timing = enable != 0;
+    p->ev_used = 0;
+    return 0;
+}
+
+int rp_plan_stage_times(rp_plan* p, float* ms, int* marks, void* stream) {
+    if (!p || !ms || !marks) return fail("rp_plan_stage_times: null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    for (int c = 0; c < ST_COUNT; ++c) { ms[c] = 0.f; marks[c] = 0; }
+    if (p->ev_used == 0) return 0;
+    const bool was = p->timing;
+    p->timing = true;
+    stage_mark(p, ST_OTHER, st);          // closing event
+    p->timing = was;
+    RP_CUDA(cudaEventSynchronize(p->ev_pool[p->ev_used - 1]));
+    for (size_t e = 0; e + 1 < p->ev_used; ++e) {
+        float dtm = 0.f;
+        RP_CUDA(cudaEventElapsedTime(&dtm, p->ev_pool[e], p->ev_pool[e + 1]));
+        ms[p->ev_cat[e]] += dtm;
+        ++marks[p->ev_cat[e]];
+    }
+    p->ev_used = 0;
+    return 0;
 }
 
 int rp_plan_status(rp_plan* p, void* stream) {

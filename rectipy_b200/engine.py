@@ -99,6 +99,18 @@ class Plan:
                       "rp_plan_time_contraction")
         return float(ms.value), float(fl.value)
 
+    def stage_timing(self, enable: bool) -> None:
+        """Arm / disarm the per-stage CUDA-event timing of rp_forward / rp_backward (profiling passes only)."""
+        abi.check(self.lib.rp_plan_stage_timing(self.handle, int(enable)), "rp_plan_stage_timing")
+
+    def stage_times(self):
+        """{stage: (total ms, launches)} since timing was armed (synchronises the current stream)."""
+        ms = (C.c_float * abi.RP_NUM_STAGES)()
+        marks = (C.c_int * abi.RP_NUM_STAGES)()
+        with torch.cuda.device(self.key.device):
+            abi.check(self.lib.rp_plan_stage_times(self.handle, ms, marks, _stream()), "rp_plan_stage_times")
+        return {name: (float(ms[i]), int(marks[i])) for i, name in enumerate(abi.STAGE_NAMES)}
+
     @property
     def workspace_bytes(self) -> int:
         return int(self.lib.rp_plan_workspace_bytes(self.handle))

@@ -22,6 +22,7 @@ from rectipy_b200 import parallel  # noqa: E402
 
 
 def main():
+    os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep stdout to the JSON line
     rank, local_rank, world = parallel.init_from_env("nccl")
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
