@@ -90,7 +90,8 @@ struct rp_plan {
     int wg_chunk = 0;
     // persistent few-trial path (rp_persistent.cuh)
     bool persistent = false;
-    int ps_rows = 0, ps_grid = 0, ps_npad = 0;
+    int ps_rows = 0, ps_grid = 0, ps_npad = 0, ps_nrb = 0, ps_bl = 0, ps_ntb = 0;     // grid = ps_nrb row blocks x ps_ntb trial blocks of ps_bl trials
+    float* ps_part = nullptr; size_t ps_part_floats = 0;      // per-row-block partial records (ordered reduction of readout / neuron means)
     int ps_fwd_wres = 0, ps_bwd_wres = 0, ps_bwd_dwres = 0;
     size_t ps_fwd_smem = 0, ps_bwd_smem = 0;
     float* ps_vec = nullptr;        // [2][B][Npad] x {value, tag}: flag-in-data exchange buffer (r_t forward, g_t backward)
@@ -233,32 +234,44 @@ int ps_prepare_kernel(K kernel, size_t smem, int grid, const char* what) {
     return 0;
 }
 
-// geometry of the persistent few-trial kernels; leaves p->persistent false when the shape does not fit
+// geometry of the persistent few-trial kernels; leaves p->persistent false when the shape does not fit.
+// Two-dimensional: n_tb trial blocks of BL <= PS_MAX_B trials x n_rb row blocks.  Among the feasible splits the one with the
+// fewest trials per CTA wins (smallest per-step gather), i.e. the largest n_tb whose rows of kW still fit in shared memory.
 int persistent_setup(rp_plan* p, const cudaDeviceProp& prop) {
     const int N = p->d.n, B = p->d.batch;
     int coop = 0, dev = 0;
     RP_CUDA(cudaGetDevice(&dev));
     RP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     if (!coop) return 0;
-    int rows = (N + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
-    rows = std::max(8, round_up(rows, 8));
-    if (rows > rp::PS_MAX_ROWS || rows * B > rp::PS_THREADS) return 0;
-    p->ps_rows = rows;
-    p->ps_grid = (N + rows - 1) / rows;
-    p->ps_npad = round_up(N, 4);
+    const int sms = prop.multiProcessorCount;
+    const int npad = round_up(N, 4);
     const size_t budget = std::min<size_t>(prop.sharedMemPerBlockOptin, 200 * 1024);
-    const size_t wbytes = (size_t)rows * p->ldw * sizeof(float);
-    const size_t base_f = ((size_t)B * p->ps_npad + rp::PS_MAX_ROWS * rp::PS_MAX_B + 64) * sizeof(float);
-    const size_t base_b = ((size_t)B * p->ps_npad + 2 * rp::PS_MAX_ROWS * rp::PS_MAX_B) * sizeof(float);
-    if (base_f > budget || base_b > budget) return 0;
-    // Only worth it while the owned rows of kW stay in shared memory: streaming them from L2 with one warp per row is
-    // slower than the per-step launch sequence (measured: N=4096, B=1: 156 vs 116 us/step).
-    if (base_f + wbytes > budget) return 0;
-    p->ps_fwd_wres = 1;
-    p->ps_fwd_smem = base_f + (p->ps_fwd_wres ? wbytes : 0);
-    p->ps_bwd_dwres = (base_b + 2 * wbytes <= budget) ? 1 : 0;
-    p->ps_bwd_wres = (p->ps_bwd_dwres || base_b + wbytes <= budget) ? 1 : 0;
-    p->ps_bwd_smem = base_b + (p->ps_bwd_wres ? wbytes : 0) + (p->ps_bwd_dwres ? wbytes : 0);
+    bool found = false;
+    for (int bl = 1; bl <= std::min(B, rp::PS_MAX_B) && !found; ++bl) {
+        const int ntb = (B + bl - 1) / bl;
+        if (ntb > sms) continue;
+        const int nrb_max = sms / ntb;
+        int rows = (N + nrb_max - 1) / nrb_max;
+        rows = std::max(8, round_up(rows, 8));
+        if (rows > rp::PS_MAX_ROWS || rows * bl > rp::PS_THREADS) continue;
+        const size_t wbytes = (size_t)rows * p->ldw * sizeof(float);
+        const size_t base_f = rp::ps_fwd_base_floats(bl, npad) * sizeof(float);
+        const size_t base_b = ((size_t)bl * npad + 2 * rp::PS_MAX_ROWS * rp::PS_MAX_B) * sizeof(float);
+        // Only worth it while the owned rows of kW stay in shared memory: streaming them from L2 with one warp per row is
+        // slower than the per-step launch sequence (measured: N=4096, B=1: 156 vs 116 us/step).
+        if (base_f + wbytes > budget || base_b > budget) continue;
+        p->ps_rows = rows; p->ps_bl = bl; p->ps_ntb = ntb;
+        p->ps_nrb = (N + rows - 1) / rows;
+        p->ps_grid = p->ps_nrb * ntb;
+        p->ps_npad = npad;
+        p->ps_fwd_wres = 1;
+        p->ps_fwd_smem = base_f + wbytes;
+        p->ps_bwd_dwres = (base_b + 2 * wbytes <= budget) ? 1 : 0;
+        p->ps_bwd_wres = (p->ps_bwd_dwres || base_b + wbytes <= budget) ? 1 : 0;
+        p->ps_bwd_smem = base_b + (p->ps_bwd_wres ? wbytes : 0) + (p->ps_bwd_dwres ? wbytes : 0);
+        found = true;
+    }
+    if (!found) return 0;
     if (plan_alloc(p, &p->ps_vec, 4 * (size_t)B * p->ps_npad)) return 1;
     RP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->ps_bar), sizeof(unsigned int)));
     p->persistent = true;
@@ -274,10 +287,22 @@ int persistent_forward(rp_plan* p, const rp_fwd_args* a, const rp::ModelParams& 
     if (a->history) RP_CUDA(cudaMemcpyAsync(a->history, a->y0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (a->T == 0) { RP_CUDA(cudaMemcpyAsync(a->yT, a->y0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st)); return 0; }
     RP_CUDA(cudaMemsetAsync(p->ps_vec, 0, 4 * (size_t)B * p->ps_npad * sizeof(float), st));   // clear stale step tags
-    // accumulated with atomics: clear once, when the first segment of a run is integrated
-    if (a->t_offset == 0) {
-        if (a->out_rec && d.out_mode == RP_OUT_READOUT && n_rec > 0)
-            RP_CUDA(cudaMemsetAsync(a->out_rec, 0, (size_t)n_rec * B * d.n_out * sizeof(float), st));
+    // Readout / neuron-mean records: every row block leaves one partial per record and k_sum_row_blocks adds them in a fixed order
+    // (bit-reproducible); only when that buffer would exceed 256 MiB do the kernels fall back to atomics on the zeroed records.
+    const bool readout = a->out_rec && d.out_mode == RP_OUT_READOUT && n_rec > 0;
+    int n_red = 0;
+    for (int r = 0; r < a->n_rec_vars; ++r) if (a->rec_reduce[r]) ++n_red;
+    const size_t part_out = readout ? (size_t)n_rec * p->ps_nrb * B * d.n_out : 0;
+    const size_t part_one = (size_t)n_rec * p->ps_nrb * B;
+    const size_t part_need = part_out + (size_t)n_red * part_one;
+    const bool ordered = part_need > 0 && part_need * sizeof(float) <= ((size_t)256 << 20);
+    if (ordered && part_need > p->ps_part_floats) {
+        if (p->ps_part) { RP_CUDA(cudaFree(p->ps_part)); p->ps_part = nullptr; p->ps_part_floats = 0; }
+        RP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->ps_part), part_need * sizeof(float)));
+        p->ps_part_floats = part_need;
+    }
+    if (!ordered && a->t_offset == 0) {      // accumulated with atomics: clear once, when the first segment of a run is integrated
+        if (readout) RP_CUDA(cudaMemsetAsync(a->out_rec, 0, (size_t)n_rec * B * d.n_out * sizeof(float), st));
         for (int r = 0; r < a->n_rec_vars; ++r)
             if (a->rec_reduce[r] && n_rec > 0) RP_CUDA(cudaMemsetAsync(a->rec_buf[r], 0, (size_t)n_rec * B * sizeof(float), st));
     }
@@ -288,6 +313,12 @@ int persistent_forward(rp_plan* p, const rp_fwd_args* a, const rp::ModelParams& 
     pa.t_offset = a->t_offset; pa.T_total = T_tot;
     pa.dt = d.dt; pa.theta = d.theta; pa.v_reset = d.v_reset;
     pa.Wk = p->Wk; pa.ldw = p->ldw; pa.rows_per_cta = p->ps_rows; pa.w_resident = p->ps_fwd_wres;
+    pa.n_rb = p->ps_nrb; pa.BL = p->ps_bl;
+    if (ordered) {
+        float* cur = p->ps_part;
+        if (readout) { pa.out_part = cur; cur += part_out; }
+        for (int r = 0; r < a->n_rec_vars; ++r) if (a->rec_reduce[r]) { pa.rec_part[r] = cur; cur += part_one; }
+    }
     pa.x = a->x; pa.W_in = a->W_in; pa.W_out = a->W_out; pa.mp = mp; pa.y0 = a->y0; pa.yT = a->yT; pa.history = a->history;
     pa.srcbuf = reinterpret_cast<uint2*>(p->ps_vec); pa.Npad = p->ps_npad; pa.out_rec = a->out_rec; pa.n_rec_vars = a->n_rec_vars;
     for (int r = 0; r < a->n_rec_vars; ++r) { pa.rec_var[r] = a->rec_var[r]; pa.rec_reduce[r] = a->rec_reduce[r]; pa.rec_buf[r] = a->rec_buf[r]; }
@@ -299,6 +330,27 @@ int persistent_forward(rp_plan* p, const rp_fwd_args* a, const rp::ModelParams& 
         RP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rp::k_persist_fwd<M_>), dim3(p->ps_grid), dim3(rp::PS_THREADS), args, p->ps_fwd_smem, st));
     });
     ++p->launches;
+    if (ordered) {
+        // records that closed inside this segment: [j0, j1)
+        const int j0 = rp_num_records(a->t_offset, a->sampling_steps, a->cutoff);
+        const int j1 = rp_num_records(std::min(a->t_offset + a->T, T_tot), a->sampling_steps, a->cutoff);
+        const int nj = std::min(j1, n_rec) - j0;
+        if (nj > 0) {
+            if (readout) {
+                const int width = B * d.n_out;
+                rp::k_sum_row_blocks<<<ew_grid(p, (size_t)nj * width), 256, 0, st>>>(pa.out_part + (size_t)j0 * p->ps_nrb * width, nj, p->ps_nrb, width, 1.0f,
+                                                                                   a->out_rec + (size_t)j0 * width);
+                ++p->launches;
+            }
+            for (int r = 0; r < a->n_rec_vars; ++r) {
+                if (!a->rec_reduce[r]) continue;
+                rp::k_sum_row_blocks<<<ew_grid(p, (size_t)nj * B), 256, 0, st>>>(pa.rec_part[r] + (size_t)j0 * p->ps_nrb * B, nj, p->ps_nrb, B, 1.0f / (float)N,
+                                                                              a->rec_buf[r] + (size_t)j0 * B);
+                ++p->launches;
+            }
+            RP_LAUNCH_CHECK();
+        }
+    }
     return 0;
 }
 
@@ -317,7 +369,7 @@ int persistent_backward(rp_plan* p, const rp_bwd_args* a, const rp::ModelParams&
         return 0;
     }
     RP_CUDA(cudaMemsetAsync(p->ps_vec, 0, 4 * (size_t)B * p->ps_npad * sizeof(float), st));   // clear stale step tags
-    if (need_dW && !p->ps_bwd_dwres) RP_CUDA(cudaMemsetAsync(p->dWraw, 0, (size_t)N * p->ldw * sizeof(float), st));
+    if (need_dW && !p->ps_bwd_dwres) RP_CUDA(cudaMemsetAsync(p->dWraw, 0, (size_t)p->ps_ntb * N * p->ldw * sizeof(float), st));
     rp::PersistBwdArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.N = N; pa.B = B; pa.T = a->T; pa.m = d.n_in; pa.k = d.n_out; pa.in_mode = d.in_mode; pa.in_target = d.in_target;
@@ -325,6 +377,7 @@ int persistent_backward(rp_plan* p, const rp_bwd_args* a, const rp::ModelParams&
     pa.t_offset = a->t_offset; pa.T_total = a->T_total > 0 ? a->T_total : a->T;
     pa.dt = d.dt; pa.theta = d.theta; pa.slope = d.slope;
     pa.WkT = p->WkT; pa.ldw = p->ldw; pa.rows_per_cta = p->ps_rows; pa.w_resident = p->ps_bwd_wres; pa.dw_resident = p->ps_bwd_dwres;
+    pa.n_rb = p->ps_nrb; pa.BL = p->ps_bl;
     pa.need_dW = need_dW ? 1 : 0;
     pa.x = a->x; pa.W_in = a->W_in; pa.W_out = a->W_out; pa.mp = mp; pa.history = a->history; pa.g_out_rec = a->g_out_rec; pa.g_yT = a->g_yT;
     pa.gbuf = reinterpret_cast<uint2*>(p->ps_vec); pa.Npad = p->ps_npad; pa.dWrawT = p->dWraw;
@@ -338,7 +391,7 @@ int persistent_backward(rp_plan* p, const rp_bwd_args* a, const rp::ModelParams&
     ++p->launches;
     if (need_dW) {
         dim3 grid((N + 31) / 32, (N + 31) / 32);
-        rp::k_finish_wgrad_T<<<grid, 256, 0, st>>>(N, p->dWraw, p->ldw, a->W, a->params[fold], kstride, a->dW, a->dparams[fold]);
+        rp::k_finish_wgrad_T<<<grid, 256, 0, st>>>(N, p->dWraw, p->ldw, a->W, a->params[fold], kstride, a->dW, a->dparams[fold], p->ps_ntb);
         ++p->launches;
         RP_LAUNCH_CHECK();
     }
@@ -429,7 +482,7 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
         p->ws_bytes += 2 * (size_t)B * sizeof(float2);
     }
     // (iku_op needs a per-step reduction over all neurons of a trial: per-step launch sequences only)
-    if (!p->use_tc && B <= rp::PS_MAX_B && !rp::is_mean_field(d->model) && !getenv("RP_NO_PERSISTENT")) {
+    if (!p->use_tc && !rp::is_mean_field(d->model) && !getenv("RP_NO_PERSISTENT")) {
         if (persistent_setup(p, prop)) { rp_plan_destroy(p); return 1; }
     }
     *out = p;
@@ -441,6 +494,7 @@ void rp_plan_destroy(rp_plan* p) {
     float* bufs[] = {p->Wk, p->WkT, p->u, p->g, p->src, p->adj, p->win_acc, p->pp, p->dWraw, p->ps_vec, p->wg_g, p->wg_src, p->dwout_part};
     for (float* b : bufs) if (b) cudaFree(b);
     if (p->ps_bar) cudaFree(p->ps_bar);
+    if (p->ps_part) cudaFree(p->ps_part);
     if (p->mf) cudaFree(p->mf);
     if (p->asum) cudaFree(p->asum);
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
@@ -666,7 +720,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     const bool need_dW = a->dW != nullptr || a->dparams[rp::fold_slot(d.model)] != nullptr;
     stage_mark(p, ST_OTHER, st);
 
-    const int wg_slices = p->use_tc ? rp::TC_WGRAD_SPLITS : 1;
+    const int wg_slices = p->use_tc ? rp::TC_WGRAD_SPLITS : (p->persistent ? std::max(1, p->ps_ntb) : 1);
     if (need_dW && !p->dWraw) { if (plan_alloc(p, &p->dWraw, (size_t)wg_slices * N * p->ldw)) return 1; }
     if (need_dW && p->use_tc) {
         size_t bytes = 0;

@@ -23,9 +23,17 @@
 
 namespace rp {
 
+// Round 2: two-dimensional decomposition for more than a handful of trials.  CTA (rb, tb) owns a block of neuron rows AND a block
+// of BL <= PS_MAX_B trials; it gathers only the source vectors of its own trials (the all-to-all volume per CTA shrinks by the
+// number of trial blocks) while its rows of kW serve all of them.  With more than 4 trials per CTA the row x trial products run
+// as register tiles (PS_RG rows x PS_BT trials per warp and pass over the columns: 12 shared-memory vector loads per 128 FMAs
+// instead of 9 per 32), reduced across the lanes with a halving butterfly (31 shuffles for the 32 sums).
+// The readout and neuron-mean records no longer use floating-point atomics: every CTA reduces its rows in a fixed order, keeps
+// its own window sum, and stores one partial per record; a final pass adds the row blocks in order (bit-reproducible runs).
 constexpr int PS_THREADS = 256;
-constexpr int PS_MAX_B = 4;
-constexpr int PS_MAX_ROWS = 64;      // owned neurons per CTA (rows * B <= 256 threads)
+constexpr int PS_MAX_B = 8;          // trials per CTA
+constexpr int PS_MAX_ROWS = 64;      // owned neurons per CTA (rows * trials-per-CTA <= 256 threads)
+constexpr int PS_RG = 8, PS_BT = 4;  // register tile of the blocked product
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
     unsigned int v;
@@ -57,18 +65,114 @@ __device__ __forceinline__ uint4 ll_load2(const uint4* p) {
     return q;
 }
 // gather the [B][Npad] vector tagged `tag` from global {value, tag} pairs into shared memory (columns >= N are padding)
+// All polling loads of a thread are issued before the first tag is examined (a mismatch re-polls that word only): one L2 round
+// trip per batch instead of one per word -- with the words polled one after the other the gather cost 16 round trips per step at
+// 8 trials per CTA (11.5 us per step, N = 1000, 32 trials) and 2 at the reference's own shape (C1).
 __device__ __forceinline__ void ll_gather(const uint2* gsrc, float* s_dst, int B, int N, int Npad, unsigned int tag) {
     const uint4* g4 = reinterpret_cast<const uint4*>(gsrc);
-    const int pairs = (B * Npad) >> 1;
-    for (int idx = threadIdx.x; idx < pairs; idx += PS_THREADS) {
-        int col = 2 * idx;                                  // column of the first element of the pair: (2 idx) mod Npad without a division
-        while (col >= Npad) col -= Npad;                    // at most B - 1 <= 3 subtractions
-        const bool need0 = col < N, need1 = col + 1 < N;
-        uint4 q;
-        do { q = ll_load2(g4 + idx); } while ((need0 && q.y != tag) || (need1 && q.w != tag));
-        s_dst[2 * idx] = __uint_as_float(q.x);
-        s_dst[2 * idx + 1] = __uint_as_float(q.z);
+    const int half = Npad >> 1;                             // pairs per trial row (Npad is a multiple of 4)
+    if (B <= 2) {
+        constexpr int U = 8;                                // column iterations in flight
+        for (int bq = 0; bq < B; ++bq) {
+            for (int cb = threadIdx.x; cb < half; cb += PS_THREADS * U) {
+                uint4 q[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) { const int c2 = cb + u * PS_THREADS; if (c2 < half) q[u] = ll_load2(g4 + bq * half + c2); }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int c2 = cb + u * PS_THREADS;
+                    if (c2 < half) {
+                        const int col = 2 * c2, idx = bq * half + c2;
+                        const bool need0 = col < N, need1 = col + 1 < N;
+                        while ((need0 && q[u].y != tag) || (need1 && q[u].w != tag)) q[u] = ll_load2(g4 + idx);
+                        s_dst[2 * idx] = __uint_as_float(q[u].x);
+                        s_dst[2 * idx + 1] = __uint_as_float(q[u].z);
+                    }
+                }
+            }
+        }
+    } else {
+        for (int c2 = threadIdx.x; c2 < half; c2 += PS_THREADS) {
+            const int col = 2 * c2;
+            const bool need0 = col < N, need1 = col + 1 < N;
+            uint4 q[PS_MAX_B];
+#pragma unroll
+            for (int bq = 0; bq < PS_MAX_B; ++bq) if (bq < B) q[bq] = ll_load2(g4 + bq * half + c2);
+#pragma unroll
+            for (int bq = 0; bq < PS_MAX_B; ++bq) {
+                if (bq < B) {
+                    const int idx = bq * half + c2;
+                    while ((need0 && q[bq].y != tag) || (need1 && q[bq].w != tag)) q[bq] = ll_load2(g4 + idx);
+                    s_dst[2 * idx] = __uint_as_float(q[bq].x);
+                    s_dst[2 * idx + 1] = __uint_as_float(q[bq].z);
+                }
+            }
+        }
     }
+}
+
+// sum of s_con[base + rr], rr in [0, R), R <= 64, over the lanes of one warp in a fixed order (same tree every run)
+__device__ __forceinline__ float warp_ordered_sum(const float* s_con, int base, int R, int lane) {
+    float v = (lane < R ? s_con[base + lane] : 0.f) + (lane + 32 < R ? s_con[base + lane + 32] : 0.f);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 32 per-lane partial sums v[0..31] -> lane L returns the total (over the 32 lanes) of element L: halving butterfly, 31 shuffles
+__device__ __forceinline__ float lane_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            const float send = upper ? v[j] : v[j + off];
+            const float keep = upper ? v[j + off] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// out[rr][q] = sum_k W[row rbase+rr][k] * vec[trial bbase+q][k] for one PS_RG x PS_BT unit of a warp; lane L ends with element
+// (rr, q) = (L / PS_BT, L % PS_BT).  rows >= R and trials >= Bl contribute zeros.
+__device__ __forceinline__ float blocked_unit(const float* s_W, const float* gW, int ldw, bool w_resident, const float* s_vec, int Npad,
+                                              int N, int rbase, int R, int bbase, int Bl, int lane) {
+    static_assert(PS_RG * PS_BT == 32, "one reduced element per lane");
+    float acc[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+    const int nvec = N >> 2;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kv = lane; kv < nvec; kv += 32) {
+        float4 s4[PS_BT];
+#pragma unroll
+        for (int q = 0; q < PS_BT; ++q) s4[q] = (bbase + q < Bl) ? reinterpret_cast<const float4*>(s_vec + (bbase + q) * Npad)[kv] : zero;
+#pragma unroll
+        for (int rr = 0; rr < PS_RG; ++rr) {
+            if (rbase + rr < R) {
+                const float4 w4 = w_resident ? reinterpret_cast<const float4*>(s_W + (size_t)(rbase + rr) * ldw)[kv]
+                                             : __ldg(reinterpret_cast<const float4*>(gW + (size_t)(rbase + rr) * ldw) + kv);
+#pragma unroll
+                for (int q = 0; q < PS_BT; ++q) {
+                    float t = acc[rr * PS_BT + q];
+                    t = fmaf(w4.x, s4[q].x, t); t = fmaf(w4.y, s4[q].y, t); t = fmaf(w4.z, s4[q].z, t); t = fmaf(w4.w, s4[q].w, t);
+                    acc[rr * PS_BT + q] = t;
+                }
+            }
+        }
+    }
+    const int kt = (nvec << 2) + lane;                      // ragged tail (N % 4 columns)
+    if (kt < N) {
+#pragma unroll
+        for (int rr = 0; rr < PS_RG; ++rr) {
+            if (rbase + rr < R) {
+                const float wv = w_resident ? s_W[(size_t)(rbase + rr) * ldw + kt] : __ldg(gW + (size_t)(rbase + rr) * ldw + kt);
+#pragma unroll
+                for (int q = 0; q < PS_BT; ++q) if (bbase + q < Bl) acc[rr * PS_BT + q] = fmaf(wv, s_vec[(bbase + q) * Npad + kt], acc[rr * PS_BT + q]);
+            }
+        }
+    }
+    return lane_transpose_reduce(acc, lane);
 }
 
 struct PersistFwdArgs {
@@ -76,6 +180,7 @@ struct PersistFwdArgs {
     float dt, theta, v_reset;
     const float* Wk; int ldw;       // [N][ldw]  k_i * W
     int rows_per_cta, w_resident;
+    int n_rb, BL;                   // grid = n_rb row blocks x ceil(B / BL) trial blocks; CTA = (blockIdx.x % n_rb, blockIdx.x / n_rb)
     const float* x;                 // [T][B][m] | [T][B][N]
     const float* W_in;              // [N][m]
     const float* W_out;             // [k][N]
@@ -85,14 +190,21 @@ struct PersistFwdArgs {
     float* history;                 // [(T+1)][nsv][B][N] (slot 0 written by the host) or nullptr
     uint2* srcbuf;                  // [2][B][Npad] {value, tag} pairs, tags zeroed by the host before the launch
     int Npad;
-    float* out_rec;                 // READOUT: [n_rec][B][k] zero-initialised (atomics) ; DENSE: [n_rec][B][N]
+    float* out_rec;                 // READOUT without out_part: [n_rec][B][k] zero-initialised (atomics) ; DENSE: [n_rec][B][N]
+    float* out_part;                // READOUT: [n_rec][n_rb][B][k] per-row-block partial window means (plain stores), or nullptr
     int n_rec_vars;
     int rec_var[RP_MAX_REC];
     int rec_reduce[RP_MAX_REC];
-    float* rec_buf[RP_MAX_REC];     // reduce: [n_rec][B] zero-initialised (atomics); else [n_rec][B][N]
+    float* rec_buf[RP_MAX_REC];     // reduce without rec_part: [n_rec][B] zero-initialised (atomics); else [n_rec][B][N]
+    float* rec_part[RP_MAX_REC];    // reduce: [n_rec][n_rb][B] per-row-block partial sums (plain stores), or nullptr
     int rec_post;
     unsigned int* barrier;          // zero-initialised
 };
+
+// floats of shared memory the forward kernel needs besides the resident rows of kW
+__host__ __device__ inline size_t ps_fwd_base_floats(int BL, int Npad) {
+    return (size_t)BL * Npad + PS_MAX_ROWS * PS_MAX_B + (RP_MAX_OUT + RP_MAX_REC) * PS_THREADS + PS_MAX_B * RP_MAX_OUT + 64;
+}
 
 template <int MODEL>
 __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a) {
@@ -100,23 +212,28 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
     constexpr bool SPK = ModelTraits<MODEL>::SPIKING;
     extern __shared__ __align__(16) float psm[];
     const int N = a.N, B = a.B, Npad = a.Npad;
-    float* s_src = psm;                                  // [B][Npad]
-    float* s_u = s_src + B * Npad;                       // [rows][B]
-    float* s_red = s_u + PS_MAX_ROWS * PS_MAX_B;         // [B*k + RP_MAX_REC*B] block partials
-    float* s_W = s_red + 64;                             // [rows][ldw] when resident
+    const int rb = blockIdx.x % a.n_rb, tb = blockIdx.x / a.n_rb;
+    const int b0 = tb * a.BL;
+    const int Bl = max(0, min(a.BL, B - b0));            // trials of this CTA
+    float* s_src = psm;                                  // [BL][Npad]
+    float* s_u = s_src + a.BL * Npad;                    // [rows][PS_MAX_B]
+    float* s_con = s_u + PS_MAX_ROWS * PS_MAX_B;         // [RP_MAX_OUT + RP_MAX_REC][PS_THREADS] per-element contributions of a step
+    float* s_win = s_con + (RP_MAX_OUT + RP_MAX_REC) * PS_THREADS;   // [BL * k] open record window of the readout
+    float* s_W = s_win + PS_MAX_B * RP_MAX_OUT + 64;     // [rows][ldw] when resident
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int r0 = blockIdx.x * a.rows_per_cta;
+    const int r0 = rb * a.rows_per_cta;
     const int R = max(0, min(a.rows_per_cta, N - r0));
     const size_t plane = (size_t)B * N;
 
     if (a.w_resident) {
         for (int idx = tid; idx < R * a.ldw; idx += PS_THREADS) s_W[idx] = a.Wk[(size_t)r0 * a.ldw + idx];
     }
-    if (tid < 64) s_red[tid] = 0.f;
+    if (tid < PS_MAX_B * RP_MAX_OUT) s_win[tid] = 0.f;
 
-    // element ownership: thread e -> (row r, trial b)
-    const bool own = tid < R * B;
-    const int r = own ? tid % R : 0, b = own ? tid / R : 0;
+    // element ownership: thread e -> (row r, local trial bl); b = global trial
+    const bool own = tid < R * Bl;
+    const int r = own ? tid % R : 0, bl = own ? tid / R : 0;
+    const int b = b0 + bl;
     const int i = r0 + r;
     float v = 0.f, s = 0.f, x = 0.f, win_sum = 0.f;
     float w_in[RP_MAX_IN];
@@ -139,6 +256,10 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
     const bool fast_elem = !is_ik(MODEL) && a.mp.bstride[RP_P_TAU] == 0 && a.mp.bstride[RP_P_ETA] == 0 && a.mp.bstride[RP_P_TAU_S] == 0 &&
                            a.mp.bstride[RP_P_TAU_X] == 0 && a.mp.bstride[RP_P_ALPHA] == 0;
     if constexpr (!is_ik(MODEL)) { if (own && fast_elem) frow = fwd_row<MODEL>(fa_fast, i); }
+    // readout weights of the owned neuron
+    float w_out[RP_MAX_OUT];
+#pragma unroll
+    for (int q = 0; q < RP_MAX_OUT; ++q) w_out[q] = (own && a.out_rec && a.out_mode == RP_OUT_READOUT && q < a.k) ? __ldg(a.W_out + (size_t)q * N + i) : 0.f;
     // record-window bookkeeping without a division per step: [w_start, w_rec] is the window that contains (or follows) the current step
     const int S_ = max(a.S, 1);
     const int w_r0 = ((a.cutoff + S_ - 1) / S_) * S_;
@@ -147,6 +268,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
     else { w_j = (a.t_offset - w_r0 + S_ - 1) / S_; w_rec = w_r0 + w_j * S_; w_start = w_rec - S_ + 1; }
     bool any_reduce = false;
     for (int q = 0; q < a.n_rec_vars; ++q) any_reduce = any_reduce || (a.rec_reduce[q] != 0);
+    const bool readout = a.out_rec != nullptr && a.out_mode == RP_OUT_READOUT;
     const int nvec = N >> 2;
     if (own && a.T > 0) {      // publish r_0 (tag 1) into slot 0
         float src0;
@@ -166,38 +288,50 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
                 for (int j = 0; j < RP_MAX_IN; ++j) if (j < a.m) Iin = fmaf(w_in[j], __ldg(xt + j), Iin);
             }
         }
-        // 1) source vector of this step (tag t+1) -> shared memory; spins per element until every producer has published
-        ll_gather(a.srcbuf + (size_t)(t & 1) * B * Npad, s_src, B, N, Npad, (unsigned int)(t + 1));
+        // 1) source vectors of this CTA's trials (tag t+1) -> shared memory; spins per element until every producer has published
+        ll_gather(a.srcbuf + (size_t)(t & 1) * B * Npad + (size_t)b0 * Npad, s_src, Bl, N, Npad, (unsigned int)(t + 1));
         __syncthreads();
-        // 2) recurrent drive of the owned rows: one warp per row, lanes stride the columns
-        for (int rr = warp; rr < R; rr += PS_THREADS / 32) {
-            const float* wrow = a.w_resident ? s_W + (size_t)rr * a.ldw : a.Wk + (size_t)(r0 + rr) * a.ldw;
-            float acc[PS_MAX_B];
+        // 2) recurrent drive of the owned rows
+        if (Bl <= 4) {
+            // one warp per row, lanes stride the columns, all (<= 4) trials in registers
+            for (int rr = warp; rr < R; rr += PS_THREADS / 32) {
+                const float* wrow = a.w_resident ? s_W + (size_t)rr * a.ldw : a.Wk + (size_t)(r0 + rr) * a.ldw;
+                float acc[4];
 #pragma unroll
-            for (int q = 0; q < PS_MAX_B; ++q) acc[q] = 0.f;
-            for (int kv = lane; kv < nvec; kv += 32) {
-                const float4 w4 = a.w_resident ? reinterpret_cast<const float4*>(wrow)[kv] : __ldg(reinterpret_cast<const float4*>(wrow) + kv);
+                for (int q = 0; q < 4; ++q) acc[q] = 0.f;
+                for (int kv = lane; kv < nvec; kv += 32) {
+                    const float4 w4 = a.w_resident ? reinterpret_cast<const float4*>(wrow)[kv] : __ldg(reinterpret_cast<const float4*>(wrow) + kv);
 #pragma unroll
-                for (int q = 0; q < PS_MAX_B; ++q) {
-                    if (q < B) {
-                        const float4 s4 = reinterpret_cast<const float4*>(s_src + q * Npad)[kv];
-                        acc[q] = fmaf(w4.x, s4.x, acc[q]); acc[q] = fmaf(w4.y, s4.y, acc[q]);
-                        acc[q] = fmaf(w4.z, s4.z, acc[q]); acc[q] = fmaf(w4.w, s4.w, acc[q]);
+                    for (int q = 0; q < 4; ++q) {
+                        if (q < Bl) {
+                            const float4 s4 = reinterpret_cast<const float4*>(s_src + q * Npad)[kv];
+                            acc[q] = fmaf(w4.x, s4.x, acc[q]); acc[q] = fmaf(w4.y, s4.y, acc[q]);
+                            acc[q] = fmaf(w4.z, s4.z, acc[q]); acc[q] = fmaf(w4.w, s4.w, acc[q]);
+                        }
+                    }
+                }
+                const int kt = (nvec << 2) + lane;              // ragged tail (N % 4 columns)
+                if (kt < N) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (q < Bl) acc[q] = fmaf(wrow[kt], s_src[q * Npad + kt], acc[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < Bl) {
+                        float tot = acc[q];
+                        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                        if (lane == 0) s_u[rr * PS_MAX_B + q] = tot;
                     }
                 }
             }
-            const int kt = (nvec << 2) + lane;              // ragged tail (N % 4 columns)
-            if (kt < N) {
-#pragma unroll
-                for (int q = 0; q < PS_MAX_B; ++q) if (q < B) acc[q] = fmaf(wrow[kt], s_src[q * Npad + kt], acc[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < PS_MAX_B; ++q) {
-                if (q < B) {
-                    float tot = acc[q];
-                    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-                    if (lane == 0) s_u[rr * PS_MAX_B + q] = tot;
-                }
+        } else {
+            // register tiles of PS_RG rows x PS_BT trials per warp
+            const int n_bt = (Bl + PS_BT - 1) / PS_BT, n_units = ((R + PS_RG - 1) / PS_RG) * n_bt;
+            for (int unit = warp; unit < n_units; unit += PS_THREADS / 32) {
+                const int rbase = (unit / n_bt) * PS_RG, bbase = (unit % n_bt) * PS_BT;
+                const float tot = blocked_unit(s_W, a.Wk + (size_t)r0 * a.ldw, a.ldw, a.w_resident != 0, s_src, Npad, N, rbase, R, bbase, Bl, lane);
+                const int rr = rbase + lane / PS_BT, q = bbase + lane % PS_BT;
+                if (rr < R && q < Bl) s_u[rr * PS_MAX_B + q] = tot;
             }
         }
         __syncthreads();
@@ -209,7 +343,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
         if (own) {
             const size_t idx = (size_t)b * N + i;
             float v1, s1, x1;
-            const float urec = s_u[r * PS_MAX_B + b];
+            const float urec = s_u[r * PS_MAX_B + bl];
             bool done = false;
             if constexpr (!is_ik(MODEL)) {
                 if (fast_elem) { fwd_elem_fast<MODEL>(fa_fast, frow, i, b, urec, 0.f, 0.f, Iin, v, s, x, v1, s1, x1); done = true; }
@@ -236,42 +370,71 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
                         win_sum = w.first ? yout : win_sum + yout;
                         if (w.close) a.out_rec[((size_t)w.j * B + b) * N + i] = win_sum / (float)w.len;
                     } else {
-                        for (int q = 0; q < a.k; ++q) atomicAdd(&s_red[b * a.k + q], __ldg(a.W_out + (size_t)q * N + i) * yout);
+#pragma unroll
+                        for (int q = 0; q < RP_MAX_OUT; ++q) if (q < a.k) s_con[q * PS_THREADS + tid] = w_out[q] * yout;
                     }
                 }
                 if (w.close) {
                     for (int q = 0; q < a.n_rec_vars; ++q) {
                         const int var = a.rec_var[q];
                         const float val = a.rec_post ? (var == 0 ? v1 : (var == 1 ? s1 : x1)) : (var == 0 ? v : (var == 1 ? s : x));
-                        if (a.rec_reduce[q]) atomicAdd(&s_red[32 + q * PS_MAX_B + b], val);
+                        if (a.rec_reduce[q]) s_con[(RP_MAX_OUT + q) * PS_THREADS + tid] = val;
                         else a.rec_buf[q][((size_t)w.j * B + b) * N + i] = val;
                     }
                 }
             }
             v = v1; s = s1; x = x1;
         }
-        // block-level reduction of this step's readout / neuron-mean contributions: only on steps that produced any (uniform condition)
-        if (w.j >= 0 && ((a.out_rec && a.out_mode == RP_OUT_READOUT) || (w.close && any_reduce))) {
+        // block-level reduction of this step's readout / neuron-mean contributions in a FIXED order (rows ascending), only on steps
+        // that produced any (uniform condition); the readout window accumulates in shared memory and leaves the CTA once per record
+        if (w.j >= 0 && (readout || (w.close && any_reduce))) {
             __syncthreads();
-            if (a.out_rec && a.out_mode == RP_OUT_READOUT && tid < B * a.k) {
-                atomicAdd(a.out_rec + (size_t)w.j * B * a.k + tid, s_red[tid] / (float)w.len);
-                s_red[tid] = 0.f;
+            if (readout) {
+                for (int pr = warp; pr < Bl * a.k; pr += PS_THREADS / 32) {           // one warp per (trial, readout channel)
+                    const int bq = pr / a.k, q = pr - bq * a.k;
+                    const float tot = warp_ordered_sum(s_con, q * PS_THREADS + bq * R, R, lane);
+                    if (lane == 0) {
+                        const float acc = w.first ? tot : s_win[pr] + tot;
+                        if (w.close) {
+                            const float mean = acc / (float)w.len;
+                            if (a.out_part) a.out_part[(((size_t)w.j * a.n_rb + rb) * B + b0 + bq) * a.k + q] = mean;
+                            else atomicAdd(a.out_rec + ((size_t)w.j * B + b0 + bq) * a.k + q, mean);
+                        } else {
+                            s_win[pr] = acc;
+                        }
+                    }
+                }
             }
-            if (w.close && tid >= 32 && tid < 32 + RP_MAX_REC * PS_MAX_B) {
-                const int q = (tid - 32) / PS_MAX_B, bb = (tid - 32) % PS_MAX_B;
-                if (q < a.n_rec_vars && a.rec_reduce[q] && bb < B) {
-                    atomicAdd(a.rec_buf[q] + (size_t)w.j * B + bb, s_red[tid] / (float)N);
-                    s_red[tid] = 0.f;
+            if (w.close && any_reduce) {
+                for (int pr = warp; pr < a.n_rec_vars * Bl; pr += PS_THREADS / 32) {  // one warp per (recorded variable, trial)
+                    const int q = pr / Bl, bq = pr - q * Bl;
+                    if (!a.rec_reduce[q]) continue;
+                    const float tot = warp_ordered_sum(s_con, (RP_MAX_OUT + q) * PS_THREADS + bq * R, R, lane);
+                    if (lane == 0) {
+                        if (a.rec_part[q]) a.rec_part[q][((size_t)w.j * a.n_rb + rb) * B + b0 + bq] = tot;
+                        else atomicAdd(a.rec_buf[q] + (size_t)w.j * B + b0 + bq, tot / (float)N);
+                    }
                 }
             }
         }
-        __syncthreads();          // s_src / s_u / s_red are rewritten by the next step
+        __syncthreads();          // s_src / s_u / s_con are rewritten by the next step
     }
     if (own) {
         const size_t idx = (size_t)b * N + i;
         a.yT[idx] = v;
         if (NSV > 1) a.yT[plane + idx] = s;
         if (NSV > 2) a.yT[2 * plane + idx] = x;
+    }
+}
+
+// out[j][e] = scale * sum_rb part[j][rb][e]   (fixed order over the row blocks)
+__global__ void __launch_bounds__(256) k_sum_row_blocks(const float* __restrict__ part, int n_rec, int n_rb, int width, float scale, float* out) {
+    const size_t total = (size_t)n_rec * width;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t j = idx / width, e = idx - j * width;
+        float acc = 0.f;
+        for (int rbk = 0; rbk < n_rb; ++rbk) acc += part[(j * n_rb + rbk) * width + e];
+        out[idx] = acc * scale;
     }
 }
 
@@ -283,6 +446,7 @@ struct PersistBwdArgs {
     float dt, theta, slope;
     const float* WkT; int ldw;      // [N][ldw]  (k_i W_ij)^T : row j holds column j of kW
     int rows_per_cta, w_resident, dw_resident, need_dW;
+    int n_rb, BL;                   // grid = n_rb row blocks x ceil(B / BL) trial blocks (as in the forward kernel)
     const float* x; const float* W_in; const float* W_out;
     ModelParams mp;
     const float* history;           // [(T+1)][nsv][B][N]
@@ -290,7 +454,7 @@ struct PersistBwdArgs {
     const float* g_yT;              // [nsv][B][N] or nullptr
     uint2* gbuf;                    // [2][B][Npad] {value, tag} pairs, tags zeroed by the host before the launch
     int Npad;
-    float* dWrawT;                  // [N][ldw]  dWraw^T (row j, col i), zero-initialised when not resident; written at the end
+    float* dWrawT;                  // [n_tb][N][ldw]  dWraw^T (row j, col i) of every trial block, zero-initialised when not resident; written at the end
     float* dparams[RP_NUM_PARAMS];  // [N] each (plain stores: one owner thread per neuron and trial -> atomics only across trials)
     float* dW_in;                   // [N][m]
     float* dW_out;                  // [k][N]
@@ -305,21 +469,27 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
     constexpr bool SPK = ModelTraits<MODEL>::SPIKING;
     extern __shared__ __align__(16) float psm[];
     const int N = a.N, B = a.B, Npad = a.Npad;
-    float* s_g = psm;                                    // [B][Npad]  g_t of all neurons
-    float* s_z = s_g + B * Npad;                         // [rows][B]
-    float* s_src = s_z + PS_MAX_ROWS * PS_MAX_B;         // [rows][B]  r_t of the owned neurons (for the rank-1 update)
+    const int rb = blockIdx.x % a.n_rb, tb = blockIdx.x / a.n_rb;
+    const int b0 = tb * a.BL;
+    const int Bl = max(0, min(a.BL, B - b0));            // trials of this CTA
+    float* s_g = psm;                                    // [BL][Npad]  g_t of all neurons, this CTA's trials
+    float* s_z = s_g + a.BL * Npad;                      // [rows][PS_MAX_B]
+    float* s_src = s_z + PS_MAX_ROWS * PS_MAX_B;         // [rows][PS_MAX_B]  r_t of the owned neurons (for the rank-Bl update)
     float* s_W = s_src + PS_MAX_ROWS * PS_MAX_B;         // [rows][ldw] when resident
     float* s_dW = s_W + (a.w_resident ? (size_t)a.rows_per_cta * a.ldw : 0);   // [rows][ldw] when resident
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int r0 = blockIdx.x * a.rows_per_cta;
+    const int r0 = rb * a.rows_per_cta;
     const int R = max(0, min(a.rows_per_cta, N - r0));
     const size_t plane = (size_t)B * N, slot = (size_t)HistPlanes<MODEL>::N * plane;
+    float* dW_slice = a.dWrawT + (size_t)tb * N * a.ldw;  // this trial block's accumulation slice
 
     if (a.w_resident) for (int idx = tid; idx < R * a.ldw; idx += PS_THREADS) s_W[idx] = a.WkT[(size_t)r0 * a.ldw + idx];
     if (a.need_dW && a.dw_resident) for (int idx = tid; idx < R * a.ldw; idx += PS_THREADS) s_dW[idx] = 0.f;
+    for (int idx = tid; idx < 2 * PS_MAX_ROWS * PS_MAX_B; idx += PS_THREADS) s_z[idx] = 0.f;      // s_z and s_src (unused trial slots stay 0)
 
-    const bool own = tid < R * B;
-    const int r = own ? tid % R : 0, b = own ? tid / R : 0;
+    const bool own = tid < R * Bl;
+    const int r = own ? tid % R : 0, bl = own ? tid / R : 0;
+    const int b = b0 + bl;
     const int i = r0 + r;                                 // owned neuron (called j in the header comment)
     float av = 0.f, as = 0.f, ax = 0.f;                   // adjoint of (v, s, x) at t+1
     float acc[ADJ_NACC];                                  // parameter / edge gradient sums of the owned neuron
@@ -374,53 +544,106 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
             if (HistPlanes<MODEL>::N > NSV) urec = __ldg(yt + (size_t)NSV * plane + idx);
             if (t > 0) vm_prev = __ldg(a.history + (size_t)(t - 1) * slot + idx);      // v_{t-1}: gate of g_{t-1}, needed right before the publish
         }
-        ll_gather(a.gbuf + (size_t)(t & 1) * B * Npad, s_g, B, N, Npad, (unsigned int)(a.T - t));
-        // source value r_t of the owned neurons (rank-1 update operand)
+        ll_gather(a.gbuf + (size_t)(t & 1) * B * Npad + (size_t)b0 * Npad, s_g, Bl, N, Npad, (unsigned int)(a.T - t));
+        // source value r_t of the owned neurons (rank-Bl update operand)
         if (own && a.need_dW) {
             float rv;
             if constexpr (SPK) rv = s; else rv = rate_act<MODEL>(a.mp, i, v, b);
-            s_src[r * PS_MAX_B + b] = rv;
+            s_src[r * PS_MAX_B + bl] = rv;
         }
         __syncthreads();
-        // Z_j = sum_i (kW)^T[j][i] g_i   and   dWraw^T[j][i] += r_j * g_i
-        for (int rr = warp; rr < R; rr += PS_THREADS / 32) {
-            const float* wrow = a.w_resident ? s_W + (size_t)rr * a.ldw : a.WkT + (size_t)(r0 + rr) * a.ldw;
-            float* drow = a.dw_resident ? s_dW + (size_t)rr * a.ldw : a.dWrawT + (size_t)(r0 + rr) * a.ldw;
-            float acc[PS_MAX_B], rj[PS_MAX_B];
+        // Z_j = sum_i (kW)^T[j][i] g_i   and   dWraw^T[j][i] += sum_trials r_j * g_i
+        if (Bl <= 4) {
+            for (int rr = warp; rr < R; rr += PS_THREADS / 32) {
+                const float* wrow = a.w_resident ? s_W + (size_t)rr * a.ldw : a.WkT + (size_t)(r0 + rr) * a.ldw;
+                float* drow = a.dw_resident ? s_dW + (size_t)rr * a.ldw : dW_slice + (size_t)(r0 + rr) * a.ldw;
+                float acc[4], rj[4];
 #pragma unroll
-            for (int q = 0; q < PS_MAX_B; ++q) { acc[q] = 0.f; rj[q] = (a.need_dW && q < B) ? s_src[rr * PS_MAX_B + q] : 0.f; }
-            for (int kv = lane; kv < nvec; kv += 32) {
-                const float4 w4 = a.w_resident ? reinterpret_cast<const float4*>(wrow)[kv] : __ldg(reinterpret_cast<const float4*>(wrow) + kv);
-                float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 4; ++q) { acc[q] = 0.f; rj[q] = (a.need_dW && q < Bl) ? s_src[rr * PS_MAX_B + q] : 0.f; }
+                for (int kv = lane; kv < nvec; kv += 32) {
+                    const float4 w4 = a.w_resident ? reinterpret_cast<const float4*>(wrow)[kv] : __ldg(reinterpret_cast<const float4*>(wrow) + kv);
+                    float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int q = 0; q < PS_MAX_B; ++q) {
-                    if (q < B) {
-                        const float4 g4 = reinterpret_cast<const float4*>(s_g + q * Npad)[kv];
-                        acc[q] = fmaf(w4.x, g4.x, acc[q]); acc[q] = fmaf(w4.y, g4.y, acc[q]);
-                        acc[q] = fmaf(w4.z, g4.z, acc[q]); acc[q] = fmaf(w4.w, g4.w, acc[q]);
-                        d4.x = fmaf(rj[q], g4.x, d4.x); d4.y = fmaf(rj[q], g4.y, d4.y);
-                        d4.z = fmaf(rj[q], g4.z, d4.z); d4.w = fmaf(rj[q], g4.w, d4.w);
+                    for (int q = 0; q < 4; ++q) {
+                        if (q < Bl) {
+                            const float4 g4 = reinterpret_cast<const float4*>(s_g + q * Npad)[kv];
+                            acc[q] = fmaf(w4.x, g4.x, acc[q]); acc[q] = fmaf(w4.y, g4.y, acc[q]);
+                            acc[q] = fmaf(w4.z, g4.z, acc[q]); acc[q] = fmaf(w4.w, g4.w, acc[q]);
+                            d4.x = fmaf(rj[q], g4.x, d4.x); d4.y = fmaf(rj[q], g4.y, d4.y);
+                            d4.z = fmaf(rj[q], g4.z, d4.z); d4.w = fmaf(rj[q], g4.w, d4.w);
+                        }
+                    }
+                    if (a.need_dW) {
+                        float4 o = reinterpret_cast<float4*>(drow)[kv];
+                        o.x += d4.x; o.y += d4.y; o.z += d4.z; o.w += d4.w;
+                        reinterpret_cast<float4*>(drow)[kv] = o;
                     }
                 }
-                if (a.need_dW) {
-                    float4 o = reinterpret_cast<float4*>(drow)[kv];
-                    o.x += d4.x; o.y += d4.y; o.z += d4.z; o.w += d4.w;
-                    reinterpret_cast<float4*>(drow)[kv] = o;
+                const int kt = (nvec << 2) + lane;
+                if (kt < N) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (q < Bl) { const float gq = s_g[q * Npad + kt]; acc[q] = fmaf(wrow[kt], gq, acc[q]); d = fmaf(rj[q], gq, d); }
+                    if (a.need_dW) drow[kt] += d;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < Bl) {
+                        float tot = acc[q];
+                        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                        if (lane == 0) s_z[rr * PS_MAX_B + q] = tot;
+                    }
                 }
             }
-            const int kt = (nvec << 2) + lane;
-            if (kt < N) {
-                float d = 0.f;
-#pragma unroll
-                for (int q = 0; q < PS_MAX_B; ++q) if (q < B) { const float gq = s_g[q * Npad + kt]; acc[q] = fmaf(wrow[kt], gq, acc[q]); d = fmaf(rj[q], gq, d); }
-                if (a.need_dW) drow[kt] += d;
+        } else {
+            // Z: register tiles of PS_RG rows x PS_BT trials per warp
+            const int n_bt = (Bl + PS_BT - 1) / PS_BT, n_units = ((R + PS_RG - 1) / PS_RG) * n_bt;
+            for (int unit = warp; unit < n_units; unit += PS_THREADS / 32) {
+                const int rbase = (unit / n_bt) * PS_RG, bbase = (unit % n_bt) * PS_BT;
+                const float tot = blocked_unit(s_W, a.WkT + (size_t)r0 * a.ldw, a.ldw, a.w_resident != 0, s_g, Npad, N, rbase, R, bbase, Bl, lane);
+                const int rr = rbase + lane / PS_BT, q = bbase + lane % PS_BT;
+                if (rr < R && q < Bl) s_z[rr * PS_MAX_B + q] = tot;
             }
+            // dW: every thread owns columns (no reduction), PS_RG rows at a time, the trials in tiles of 4
+            if (a.need_dW) {
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int rbase = 0; rbase < R; rbase += PS_RG) {
+                    for (int kv = tid; kv < nvec; kv += PS_THREADS) {
+                        float4 d4[PS_RG];
 #pragma unroll
-            for (int q = 0; q < PS_MAX_B; ++q) {
-                if (q < B) {
-                    float tot = acc[q];
-                    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-                    if (lane == 0) s_z[rr * PS_MAX_B + q] = tot;
+                        for (int rr = 0; rr < PS_RG; ++rr) d4[rr] = zero;
+                        for (int qt = 0; qt < Bl; qt += 4) {
+                            float4 g4[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) g4[q] = (qt + q < Bl) ? reinterpret_cast<const float4*>(s_g + (qt + q) * Npad)[kv] : zero;
+#pragma unroll
+                            for (int rr = 0; rr < PS_RG; ++rr) {
+                                const float4 rj = *reinterpret_cast<const float4*>(s_src + (rbase + rr) * PS_MAX_B + qt);     // rows >= R / trials >= Bl hold 0
+                                d4[rr].x = fmaf(rj.x, g4[0].x, d4[rr].x); d4[rr].y = fmaf(rj.x, g4[0].y, d4[rr].y); d4[rr].z = fmaf(rj.x, g4[0].z, d4[rr].z); d4[rr].w = fmaf(rj.x, g4[0].w, d4[rr].w);
+                                d4[rr].x = fmaf(rj.y, g4[1].x, d4[rr].x); d4[rr].y = fmaf(rj.y, g4[1].y, d4[rr].y); d4[rr].z = fmaf(rj.y, g4[1].z, d4[rr].z); d4[rr].w = fmaf(rj.y, g4[1].w, d4[rr].w);
+                                d4[rr].x = fmaf(rj.z, g4[2].x, d4[rr].x); d4[rr].y = fmaf(rj.z, g4[2].y, d4[rr].y); d4[rr].z = fmaf(rj.z, g4[2].z, d4[rr].z); d4[rr].w = fmaf(rj.z, g4[2].w, d4[rr].w);
+                                d4[rr].x = fmaf(rj.w, g4[3].x, d4[rr].x); d4[rr].y = fmaf(rj.w, g4[3].y, d4[rr].y); d4[rr].z = fmaf(rj.w, g4[3].z, d4[rr].z); d4[rr].w = fmaf(rj.w, g4[3].w, d4[rr].w);
+                            }
+                        }
+#pragma unroll
+                        for (int rr = 0; rr < PS_RG; ++rr) {
+                            if (rbase + rr < R) {
+                                float* drow = a.dw_resident ? s_dW + (size_t)(rbase + rr) * a.ldw : dW_slice + (size_t)(r0 + rbase + rr) * a.ldw;
+                                float4 o = reinterpret_cast<float4*>(drow)[kv];
+                                o.x += d4[rr].x; o.y += d4[rr].y; o.z += d4[rr].z; o.w += d4[rr].w;
+                                reinterpret_cast<float4*>(drow)[kv] = o;
+                            }
+                        }
+                    }
+                    const int kt = (nvec << 2) + tid;               // ragged tail (N % 4 columns)
+                    if (kt < N) {
+                        for (int rr = 0; rr < PS_RG && rbase + rr < R; ++rr) {
+                            float d = 0.f;
+                            for (int q = 0; q < Bl; ++q) d = fmaf(s_src[(rbase + rr) * PS_MAX_B + q], s_g[q * Npad + kt], d);
+                            float* drow = a.dw_resident ? s_dW + (size_t)(rbase + rr) * a.ldw : dW_slice + (size_t)(r0 + rbase + rr) * a.ldw;
+                            drow[kt] += d;
+                        }
+                    }
                 }
             }
         }
@@ -438,7 +661,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
             aa.x_t = a.x ? a.x + (size_t)t * (a.in_mode == RP_IN_DENSE ? plane : (size_t)B * a.m) : nullptr;
             aa.zero_after_post = (truncating && (a.t_offset + t) > 0 && (a.t_offset + t) % a.truncate == 0) ? 1 : 0;
             const RegAcc racc{acc};
-            const float dI = adj_post_math<MODEL>(aa, rowp, racc, i, b, s_z[r * PS_MAX_B + b], v, s, x, av, as, ax, urec);
+            const float dI = adj_post_math<MODEL>(aa, rowp, racc, i, b, s_z[r * PS_MAX_B + bl], v, s, x, av, as, ax, urec);
             if (a.g_x) a.g_x[(size_t)t * plane + idx] = dI;
             if (t > 0) {
                 float gm, srcv;
@@ -461,19 +684,21 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
     }
     if (a.need_dW && a.dw_resident) {
         __syncthreads();
-        for (int idx = tid; idx < R * a.ldw; idx += PS_THREADS) a.dWrawT[(size_t)r0 * a.ldw + idx] = s_dW[idx];
+        for (int idx = tid; idx < R * a.ldw; idx += PS_THREADS) dW_slice[(size_t)r0 * a.ldw + idx] = s_dW[idx];
     }
 }
 
 // dWraw^T -> dW = diag(k) dWraw and dk  (persistent path keeps the weight gradient transposed: row = source neuron j)
 __global__ void __launch_bounds__(256) k_finish_wgrad_T(int N, const float* __restrict__ dWrawT, int ldr, const float* __restrict__ W,
-                                                        const float* __restrict__ kp, int k_stride, float* dW, float* dk) {
+                                                        const float* __restrict__ kp, int k_stride, float* dW, float* dk, int n_slices) {
     __shared__ float tile[32][33];
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;   // bx: i base, by: j base (rows of dWrawT)
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int rr = ty; rr < 32; rr += 8) {
         const int j = by + rr, i = bx + tx;
-        tile[rr][tx] = (i < N && j < N) ? dWrawT[(size_t)j * ldr + i] : 0.f;
+        float acc = 0.f;
+        if (i < N && j < N) for (int z = 0; z < n_slices; ++z) acc += dWrawT[(size_t)z * N * ldr + (size_t)j * ldr + i];     // trial blocks, fixed order
+        tile[rr][tx] = acc;
     }
     __syncthreads();
     for (int rr = ty; rr < 32; rr += 8) {

@@ -312,10 +312,12 @@ def test_binary16_path_remaining_templates(model):
         assert rel_err(res["3xf16"]["out"][:, b, :], ref) <= (1e-5 if rate else 1e-4)
 
 
-@pytest.mark.parametrize("model,n,B", [("qif_sfa", 1000, 1), ("li_tanh", 203, 2), ("lif", 64, 4), ("qif", 1536, 1)])
+@pytest.mark.parametrize("model,n,B", [("qif_sfa", 1000, 1), ("li_tanh", 203, 2), ("lif", 64, 4), ("qif", 1536, 1),
+                                       ("qif", 1000, 32), ("li_tanh", 203, 7), ("qif_sfa", 500, 20), ("lif", 130, 64)])
 def test_persistent_kernels_match_per_step_path(model, n, B, monkeypatch):
     """Few-trial shapes run as ONE cooperative persistent launch per pass (rp_persistent.cuh); RP_NO_PERSISTENT=1 forces
-    the per-step launch sequence.  Both must agree (same fp32 arithmetic up to summation order)."""
+    the per-step launch sequence.  Both must agree (same fp32 arithmetic up to summation order).  Round 2: trial counts above 4
+    run on the two-dimensional (row block x trial block) grid, with register-tiled products when a CTA holds more than 4 trials."""
     import rectipy_b200 as rp
     from rectipy_b200 import engine
     from golden_util import TEMPLATE_PATH

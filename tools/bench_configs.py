@@ -44,6 +44,21 @@ def c1_cpu():
 tc = cpu_time(c1_cpu)
 rows.append(("C1 QIF-SFA fwd N=1000 B=1 T=40000", n * T / tg, n * Tc / tc, tg / T * 1e6))
 
+# ---- sweep: QIF forward N=1000, 32 trials (north_star: parameter sweeps of 8-64 trials), persistent 2-D grid ---------------------
+n, T, dt, Bs = 1000, 20000, 1e-3, 32
+rng = np.random.default_rng(3)
+Ws = (2.0 * rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32)
+nets = rp.Network(dt, device="cuda:0", batch=Bs)
+nets.add_diffeq_node("qif", "neuron_model_templates.spiking_neurons.qif.qif", weights=Ws, source_var="s", target_var="s_in", input_var="I_ext",
+                     output_var="s", spike_var="spike", reset_var="v", op="qif_op", node_vars={"eta": orc.lorentzian_etas(n)})
+nets.add_func_node("inp", 2, "identity"); nets.add_edge("inp", "qif", weights=rng.standard_normal((n, 2)))
+nets.add_func_node("out", 3, "identity"); nets.add_edge("qif", "out", weights=rng.standard_normal((3, n)) / np.sqrt(n))
+xs = torch.randn(T, Bs, 2, device="cuda") * 5 + 8; y0s = nets.state
+def sweep():
+    nets.reset(y0s); return nets.run(xs, sampling_steps=10, verbose=False, enable_grad=False)
+tg = gpu_time(sweep)
+rows.append((f"sweep QIF fwd N={n} B={Bs} T={T} (readout, S=10)", n * Bs * T / tg, float("nan"), tg / T * 1e6))
+
 # ---- C2: LI-tanh rate net BPTT, N=200, dt=1e-2, T=10000 (documentation/bptt_rate_neurons.py) -----------------------
 for n in (200, 4096):
     T = 10000 if n == 200 else 500
