@@ -1285,6 +1285,9 @@ struct FusedAdjArgs {
     float* dwout_part;           // [B / FA_TB][k][N] partial sums of dW_out (readout from s), or nullptr
 };
 
+#ifndef RP_FUSED_OCC
+#define RP_FUSED_OCC 3
+#endif
 constexpr int FA_TN = 64, FA_TB = 32, FA_LD = FA_TB + 1;
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 // per-neuron constants of the reverse step, reciprocals hoisted (the generic adj_post_math divides per element)
@@ -1301,7 +1304,7 @@ __device__ __forceinline__ FaRow fa_row(const AdjArgs& a, int i) {
 }
 // FULL: both halves of the step run (every launch of a sweep but its first and last) -- the flags become compile-time constants
 template <int MODEL, bool FULL>
-__global__ void __launch_bounds__(256, 3) k_adj_fused_f16(AdjArgs a, FusedAdjArgs f) {
+__global__ void __launch_bounds__(256, RP_FUSED_OCC) k_adj_fused_f16(AdjArgs a, FusedAdjArgs f) {
     constexpr int NSV = ModelTraits<MODEL>::NSV;
     constexpr bool SFA = MODEL == RP_QIF_SFA;
     static_assert(MODEL == RP_QIF || MODEL == RP_QIF_SFA || MODEL == RP_LIF, "templates whose a_{t-1}[v] does not involve Z_{t-1}");
