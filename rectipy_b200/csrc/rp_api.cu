@@ -607,7 +607,43 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         ++p->launches;
         RP_LAUNCH_CHECK();
     }
-    for (int t = 0; t < a->T; ++t) {
+    // Round 2: the whole horizon of the batched path as ONE persistent cooperative launch (binary16 operands, 256-trial tiles, nothing
+    // that needs a per-step side kernel: no recorded state variables, output = fused readout or none, no mean-field template)
+    bool persisted = false;
+    if (f16 && p->tc.bq_fwd == 256 && a->T > 1 && !rp::is_mean_field(d.model) && a->n_rec_vars == 0 && (fuse_readout || a->out_rec == nullptr) &&
+        !getenv("RP_NO_FWD_PERSIST")) {
+        size_t bytes = 0;
+        if (rp::tc_workspace_ensure_persist(&p->tc, &bytes)) return fail("rp_forward: %s", rp::tc_last_error());
+        p->ws_bytes += bytes;
+        rp::FwdStepArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.N = N; fa.B = B; fa.m = d.n_in; fa.in_mode = d.in_mode; fa.in_target = d.in_target;
+        fa.dt = d.dt; fa.theta = d.theta; fa.v_reset = d.v_reset; fa.u = p->u; fa.ldu = p->ldu;
+        fa.W_in = a->W_in; fa.mp = mp; fa.ld_src = p->tc.ldk; fa.mf = p->mf;
+        fa.sc_out = rp::no_scale(); fa.per_trial = p->per_trial ? 1 : 0; fa.no_lean = getenv("RP_NO_FWD_LEAN") ? 1 : 0;
+        rp::FwdPersist ps;
+        memset(&ps, 0, sizeof(ps));
+        ps.T = a->T; ps.t_offset = a->t_offset; ps.T_total = T_tot; ps.S = a->sampling_steps; ps.cutoff = a->cutoff;
+        ps.n_row_tiles = N / rp::TC_BP; ps.readout = fuse_readout ? 1 : 0;
+        ps.y_hist = a->history; ps.hslot = hslot; ps.y_pp = p->pp; ps.slot = slot;
+        ps.x = a->x; ps.x_stride = x_stride; ps.out_rec = a->out_rec; ps.out_stride = out_stride;
+        ps.amax_src = spk ? p->tc.amax_src : nullptr; ps.sc_static = sc_rate;
+        ps.nsv = nsv; ps.plane = plane; ps.urec = (rp::is_ik(d.model) && a->history) ? 1 : 0;
+        int prc = 0;
+        auto fill0 = [&](auto& epi) {
+            epi.a = fa; epi.out_rec_j = nullptr; epi.k = d.n_out; epi.win_first = 0; epi.win_close = 0; epi.inv_len = 0.f;
+            epi.sA = rp::tc_scale_W(&p->tc); epi.sA_ro = rp::tc_scale_Wout(&p->tc); epi.sB = sc_rate;
+        };
+        stage_mark(p, ST_FWD, st);
+        if (p->per_trial || rp::is_ik(d.model)) {
+            RP_DISPATCH_MODEL(d.model, { rp::EpiFwd<M_, true> epi; fill0(epi); prc = rp::tc_forward_persistent<M_, true>(&p->tc, epi, ps, p->sm_count, st); });
+        } else {
+            RP_DISPATCH_MODEL(d.model, { rp::EpiFwd<M_, false> epi; fill0(epi); prc = rp::tc_forward_persistent<M_, false>(&p->tc, epi, ps, p->sm_count, st); });
+        }
+        if (prc == 1) return fail("rp_forward: %s", rp::tc_last_error());
+        if (prc == 0) { persisted = true; ++p->launches; }
+    }
+    for (int t = 0; t < (persisted ? 0 : a->T); ++t) {
         float* cur = slot_ptr(t);
         float* nxt = slot_ptr(t + 1);
         const Window w = window_of(a->t_offset + t, T_tot, a->sampling_steps, a->cutoff);

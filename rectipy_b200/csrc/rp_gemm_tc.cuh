@@ -595,6 +595,247 @@ k_gemm_split3_lean(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     gemm_split3_body<BQ, Epi, F16, true>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, num_k_blocks, epi, slice);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Persistent multi-step forward kernel of the batched path (round 2): ONE cooperative launch integrates all T steps.
+//
+// CTA (bx, by) owns output tile (row tile bx, trial group by) for the whole horizon: barriers, TMEM and tensor maps are set up
+// once, the smem ring and the TMEM ping-pong simply keep cycling through their phases, and the kernel boundary per step -- its
+// launch gap, drain and ramp -- is replaced by a per-trial-group dependency: step t+1 of a tile needs src_{t+1} of ITS trials from
+// all row tiles, nothing from the other trial groups.  Protocol per step:
+//   epilogue warps   write y_{t+1}, src_{t+1} (buffer (t+1) & 1), fence, meet at the named barrier, one thread adds 1 to done[by]
+//                    and to done[groups] (the all-groups counter);
+//   TMA producer     before loading step t's operands: spin until done[by] == (#row tiles that write src) * t, then a
+//                    generic->async proxy fence (the operands were written with ordinary stores by other SMs);
+//   epilogue warps   before reading the scale of src_{t+1} (a maximum over ALL trials of step t-1's epilogues): spin until the
+//                    all-groups counter reached (#writing CTAs) * t -- one main loop later than the increments, i.e. never in practice.
+// The source operand is double buffered by step parity (with one launch per step a single buffer is enough only because the CTAs of
+// a launch run in lock step).  A spin that lasts longer than ~2 s traps instead of hanging the device.
+// ---------------------------------------------------------------------------------------------------------------------------
+struct FwdPersist {
+    int T, t_offset, T_total, S, cutoff;
+    int n_row_tiles;               // tiles of kW rows (a further tile holds the readout rows when `readout`)
+    int readout;                   // 1: grid.x = n_row_tiles + 1, the last row tile computes o_t = W_out . s_t
+    const float* y_hist; size_t hslot;      // checkpoints [(T+1)][hslot] or nullptr
+    float* y_pp; size_t slot;               // ping-pong state [2][slot] when no checkpoints are kept
+    const float* x; size_t x_stride;
+    float* out_rec; size_t out_stride;
+    float* amax_src;               // binary16 + spiking: per-step maxima of the source operand (else nullptr)
+    ScaleRef sc_static;            // binary16 + rate models: static bound of the activation
+    void* src_hi[2]; void* src_lo[2];
+    int nsv; size_t plane; int urec;        // ik: the recurrent drive goes into checkpoint plane nsv of slot t
+    unsigned int* done;            // [groups + 1] zero-initialised
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int target) {
+    if (ld_acquire_gpu_u32(p) >= target) return;
+    const long long t0 = clock64();
+    while (ld_acquire_gpu_u32(p) < target) {
+        if (clock64() - t0 > 4000000000LL) __trap();           // ~2 s: a protocol error must not hang the device
+    }
+}
+
+template <int BQ, class Epi, bool F16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_fwd_persist(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB0_hi, const __grid_constant__ CUtensorMap tmB0_lo,
+                   const __grid_constant__ CUtensorMap tmB1_hi, const __grid_constant__ CUtensorMap tmB1_lo,
+                   int num_k_blocks, const __grid_constant__ Epi epi0, const __grid_constant__ FwdPersist ps) {
+    using Cfg = TcCfg<BQ>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int CPT = Cfg::COLS_PER_THREAD;
+    constexpr int TC_BK = TcElt<F16>::BK;
+    constexpr int TC_KC = TcElt<F16>::KC;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* tile_free_bar = tmem_empty_bar + 3;      // the epilogue has finished with the tile parked in the stage memory
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bx = blockIdx.x, by = blockIdx.y;
+    const int p0 = bx * TC_BP, q0 = by * BQ;
+    const int num_chunks = (num_k_blocks + TC_KC - 1) / TC_KC;
+    // every CTA of a trial group takes part in the step counters -- also the readout tile, which writes no operand but READS the
+    // source buffer that the others overwrite two steps later
+    const unsigned int writers = gridDim.x;
+    const unsigned int writers_all = writers * gridDim.y;
+    const bool is_writer = true;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB0_hi); tma_prefetch_desc(&tmB0_lo);
+        tma_prefetch_desc(&tmB1_hi); tma_prefetch_desc(&tmB1_lo);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], TC_EPI_WARPS); }
+        mbar_init(tile_free_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: one elected thread, all steps =====
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = 0; t < ps.T; ++t) {
+                const CUtensorMap* mb_hi = (t & 1) ? &tmB1_hi : &tmB0_hi;
+                const CUtensorMap* mb_lo = (t & 1) ? &tmB1_lo : &tmB0_lo;
+                bool ready = (t == 0);
+                // the stages double as the parking space of the previous step's output tile: wait until this CTA's epilogue has left it
+                if (t > 0) mbar_wait(tile_free_bar, (uint32_t)((t - 1) & 1));
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    // the weight tiles do not depend on the step: they are on their way while the source operand is awaited
+                    tma_load_2d(sa, &tmA_hi, &full_bar[stage], kb * TC_BK, p0);
+                    tma_load_2d(sa + Cfg::A_BYTES, &tmA_lo, &full_bar[stage], kb * TC_BK, p0);
+                    if (!ready) {
+                        // src_t of this trial group is complete when every CTA of the group has finished step t-1; the operand was
+                        // written with ordinary stores by other SMs: generic -> async proxy fence before the TMA reads it
+                        spin_until(ps.done + by, writers * (unsigned int)t);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        ready = true;
+                    }
+                    tma_load_2d(sa + 2 * Cfg::A_BYTES, mb_hi, &full_bar[stage], kb * TC_BK, q0);
+                    tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, mb_lo, &full_bar[stage], kb * TC_BK, q0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the chunk counter (TMEM ping-pong parity) runs on across the steps =====
+        constexpr uint32_t idesc = make_idesc(F16, TC_BP, BQ);
+        int stage = 0; uint32_t phase = 0;
+        int chunk_g = 0;                                   // global chunk index
+        for (int t = 0; t < ps.T; ++t) {
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int kin = kb % TC_KC;
+                const int buf = chunk_g & 1;
+                if (kin == 0) {
+                    mbar_wait(&tmem_empty_bar[buf], ((chunk_g >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                mbar_wait(&full_bar[stage], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BQ);
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t dA_hi = make_sw128_kmajor_desc(sa);
+                    const uint64_t dA_lo = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
+                    const uint64_t dB_hi = make_sw128_kmajor_desc(sa + 2 * Cfg::A_BYTES);
+                    const uint64_t dB_lo = make_sw128_kmajor_desc(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TcElt<F16>::KSTEPS; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                        umma_ss<F16>(tmem_d, dA_lo + adv, dB_hi + adv, idesc, (kin > 0 || k > 0) ? 1u : 0u);
+                        umma_ss<F16>(tmem_d, dA_hi + adv, dB_lo + adv, idesc, 1u);
+                        umma_ss<F16>(tmem_d, dA_hi + adv, dB_hi + adv, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (kin == TC_KC - 1 || kb == num_k_blocks - 1) umma_commit(&tmem_full_bar[buf]);
+                }
+                __syncwarp();
+                if (kin == TC_KC - 1 || kb == num_k_blocks - 1) ++chunk_g;
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int ew = warp - 2;
+        const int lane_base = (warp & 3) * 32;
+        const int half = ew >> 2;
+        Epi e = epi0;                                      // per-step fields are rewritten below
+        const bool f16_spk = F16 && ps.amax_src != nullptr;
+        int chunk_g = 0;
+        // record-window bookkeeping without a division per step (as in the persistent few-trial kernel)
+        const int S_ = max(ps.S, 1);
+        const int w_r0 = ((ps.cutoff + S_ - 1) / S_) * S_;
+        int w_j, w_start, w_rec;
+        if (ps.t_offset <= w_r0) { w_j = 0; w_start = ps.cutoff; w_rec = w_r0; }
+        else { w_j = (ps.t_offset - w_r0 + S_ - 1) / S_; w_rec = w_r0 + w_j * S_; w_start = w_rec - S_ + 1; }
+        for (int t = 0; t < ps.T; ++t) {
+            float acc[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+            for (int chunk = 0; chunk < num_chunks; ++chunk, ++chunk_g) {
+                const int buf = chunk_g & 1;
+                mbar_wait(&tmem_full_bar[buf], (chunk_g >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * BQ + half * CPT);
+#pragma unroll
+                for (int c = 0; c < CPT / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + (uint32_t)(c * 32), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+            }
+            // ---- per-step view of the epilogue arguments ----
+            const float* cur = ps.y_hist ? ps.y_hist + (size_t)t * ps.hslot : ps.y_pp + (size_t)(t & 1) * ps.slot;
+            float* nxt = ps.y_hist ? const_cast<float*>(ps.y_hist) + (size_t)(t + 1) * ps.hslot : ps.y_pp + (size_t)((t + 1) & 1) * ps.slot;
+            e.a.y_cur = cur; e.a.y_next = nxt;
+            e.a.x_t = ps.x ? ps.x + (size_t)t * ps.x_stride : nullptr;
+            e.a.src_hi = ps.src_hi[(t + 1) & 1]; e.a.src_lo = ps.src_lo[(t + 1) & 1];
+            e.a.urec_out = ps.urec ? const_cast<float*>(cur) + (size_t)ps.nsv * ps.plane : nullptr;
+            if (f16_spk) {
+                e.sB = t == 0 ? ScaleRef{ps.amax_src, 0.f, CV_HSRC} : ScaleRef{ps.amax_src + (t - 1), 1.f, CV_HSRC};
+                e.a.sc_out = ScaleRef{ps.amax_src + t, 1.f, CV_HSRC};
+                e.a.amax_out = ps.amax_src + (t + 1);
+            } else if (F16) {
+                e.sB = ps.sc_static; e.a.sc_out = ps.sc_static; e.a.amax_out = nullptr;
+            }
+            const int tg = ps.t_offset + t;
+            if (tg > w_rec) { ++w_j; w_start = w_rec + 1; w_rec += S_; }
+            const bool in_win = tg >= ps.cutoff && w_rec < ps.T_total;
+            e.out_rec_j = (ps.readout && in_win && ps.out_rec) ? ps.out_rec + (size_t)w_j * ps.out_stride : nullptr;
+            e.win_first = (tg == w_start); e.win_close = (tg == w_rec);
+            e.inv_len = in_win ? 1.0f / (float)(w_rec - w_start + 1) : 0.f;
+            // the scale of src_{t+1} is a maximum over ALL trials of step t-1's epilogues
+            if (t > 0 && f16_spk) { if (lane == 0) spin_until(ps.done + gridDim.y, writers_all * (unsigned int)t); __syncwarp(); }
+            float2 usc = make_float2(1.f, 1.f);
+            if constexpr (F16) usc = e.unscale(p0);
+            float* tile = reinterpret_cast<float*>(smem);
+            float* my = tile + (size_t)(half * CPT) * TC_BP + lane_base + lane;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) my[j * TC_BP] = F16 ? acc[j] * usc.x * usc.y : acc[j];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            e.template run_tile<BQ, F16>(p0, q0, tile, ew * 32 + lane, tile + (size_t)BQ * TC_BP);
+            // publish: the named barrier orders every epilogue thread's stores before the one thread that fences (cumulativity, the
+            // pattern of a cooperative-groups grid barrier) and bumps the counters
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (ew == 0 && lane == 0) mbar_arrive(tile_free_bar);
+            if (ew == 0 && lane == 0 && is_writer) {
+                __threadfence();
+                atomicAdd(ps.done + by, 1u);
+                atomicAdd(ps.done + gridDim.y, 1u);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
 // split a dense fp32 matrix [rows][ld] into hi/lo copies [rows_out][ld_out] (zero padded): tf32-exact fp32 words, or
 // binary16 with the power-of-two scale of `sc` (f16 = 1)
 __global__ void __launch_bounds__(256) k_split_matrix(int rows, int cols, const float* __restrict__ src, int ld,
@@ -669,6 +910,9 @@ struct TcWorkspace {
     int amax_cap = 0;
     const void* fwd_history = nullptr; int fwd_T = -1;      // which checkpoints amax_src describes
     const void* wt_W = nullptr;                             // weights whose transposed split (WT_hi/lo) the last forward call left behind
+    void *src2_hi = nullptr, *src2_lo = nullptr;            // second source-operand buffer of the persistent multi-step forward kernel
+    CUtensorMap m_src2[2];
+    unsigned int* fwd_done = nullptr;                       // [B / bq_fwd + 1] step counters of that kernel
     int bq_fwd = 0, bq_wg = 0;
     CUtensorMap m_W[2], m_WT[2], m_src[2], m_g[2], m_gT[2][2], m_srcT[2][2];     // m_gT[buffer][hi/lo]
     int esize() const { return f16 ? 2 : 4; }
@@ -701,7 +945,7 @@ inline int tc_set_attrs() {
 
 inline void tc_workspace_destroy(TcWorkspace* w) {
     void* bufs[] = {w->W_hi, w->W_lo, w->WT_hi, w->WT_lo, w->src_hi, w->src_lo, w->g_hi, w->g_lo, w->gT_hi[0], w->gT_lo[0], w->srcT_hi[0], w->srcT_lo[0],
-                    w->gT_hi[1], w->gT_lo[1], w->srcT_hi[1], w->srcT_lo[1], w->g32, w->src32, w->meta, w->amax_src};
+                    w->gT_hi[1], w->gT_lo[1], w->srcT_hi[1], w->srcT_lo[1], w->g32, w->src32, w->meta, w->amax_src, w->src2_hi, w->src2_lo, w->fwd_done};
     for (void* b : bufs) if (b) cudaFree(b);
     cudaEvent_t evs[] = {w->ev_z, w->ev_ops[0], w->ev_ops[1], w->ev_done[0], w->ev_done[1], w->ev_join};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -813,6 +1057,39 @@ inline int tc_forward_step(TcWorkspace* w, const EpiFwd<MODEL, GEN>& epi, bool r
     const int P = w->N + (readout_rows ? TC_BP : 0);
     if (w->f16) return tc_launch_epi<EpiFwd<MODEL, GEN>, true>(w->bq_fwd, P, w->B, w->N, w->m_W, w->m_src, epi, st);
     return tc_launch_epi<EpiFwd<MODEL, GEN>, false>(w->bq_fwd, P, w->B, w->N, w->m_W, w->m_src, epi, st);
+}
+// second source buffer + step counters of the persistent multi-step forward kernel (allocated on first use)
+inline int tc_workspace_ensure_persist(TcWorkspace* w, size_t* bytes) {
+    if (w->src2_hi) return 0;
+    const size_t bn = (size_t)w->B * w->ldk * w->esize();
+    if (tc_alloc(&w->src2_hi, bn, bytes) || tc_alloc(&w->src2_lo, bn, bytes)) return 1;
+    if (tc_alloc(reinterpret_cast<void**>(&w->fwd_done), 64 * sizeof(unsigned int), bytes)) return 1;
+    if (tc_make_map(&w->m_src2[0], w->src2_hi, w->f16, w->B, w->N, w->ldk, w->bq_fwd) || tc_make_map(&w->m_src2[1], w->src2_lo, w->f16, w->B, w->N, w->ldk, w->bq_fwd)) return 1;
+    return 0;
+}
+// whole horizon in one cooperative launch (binary16 operands, 256-trial tiles); returns 2 when the grid cannot be co-resident
+template <int MODEL, bool GEN>
+inline int tc_forward_persistent(TcWorkspace* w, const EpiFwd<MODEL, GEN>& epi, FwdPersist ps, int sm_count, cudaStream_t st) {
+    using Epi = EpiFwd<MODEL, GEN>;
+    auto kernel = k_gemm_fwd_persist<256, Epi, true>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES) != cudaSuccess) RP_TC_FAIL("cudaFuncSetAttribute failed");
+        attr_done = true;
+    }
+    const dim3 grid(ps.n_row_tiles + (ps.readout ? 1 : 0), w->B / 256);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TC_THREADS, TcCfg<256>::SMEM_BYTES) != cudaSuccess || occ < 1) return 2;
+    if ((int)(grid.x * grid.y) > occ * sm_count || (int)grid.y + 1 > 64) return 2;
+    ps.src_hi[0] = w->src_hi; ps.src_lo[0] = w->src_lo; ps.src_hi[1] = w->src2_hi; ps.src_lo[1] = w->src2_lo;
+    ps.done = w->fwd_done;
+    if (cudaMemsetAsync(w->fwd_done, 0, 64 * sizeof(unsigned int), st) != cudaSuccess) RP_TC_FAIL("cudaMemsetAsync failed");
+    int kb = w->N / TcElt<true>::BK;
+    Epi e = epi;
+    void* args[] = {&w->m_W[0], &w->m_W[1], &w->m_src[0], &w->m_src[1], &w->m_src2[0], &w->m_src2[1], &kb, &e, &ps};
+    cudaError_t err = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), grid, dim3(TC_THREADS), args, TcCfg<256>::SMEM_BYTES, st);
+    if (err != cudaSuccess) { cudaGetLastError(); return 2; }      // e.g. not co-resident next to another tenant's kernels: per-step launches instead
+    return 0;
 }
 // scale descriptors of the binary16 operands (no-ops on the tf32 path)
 inline ScaleRef tc_scale_W(const TcWorkspace* w) { return w->f16 ? ScaleRef{w->meta + TCM_AMAX_W, 0.f, CV_HG} : no_scale(); }

@@ -191,3 +191,39 @@ def test_headline_rate_network_trajectories_and_gradients_1e5():
     print("headline rate network, realised rel err vs fp64 oracle:", {k_: f"{e:.2e}" for k_, e in errs.items()})
     assert all(e <= 1e-5 for e in errs.values()), errs
     engine.clear_plans()
+
+
+def test_persistent_forward_kernel_is_bit_identical_to_per_step_launches(monkeypatch):
+    """Round 2: the batched forward runs as ONE persistent cooperative launch per horizon (k_gemm_fwd_persist: per-trial-group
+    dependency counters instead of a kernel boundary per step, double-buffered source operand).  RP_NO_FWD_PERSIST=1 forces one
+    launch per step.  Same kernels' arithmetic, same operand scales -> records, final state and gradients must be bit-identical,
+    with and without checkpoints, over a horizon long enough for every barrier phase to wrap many times."""
+    from rectipy_b200 import engine
+    n, B, T = 1024, 512, 300
+    W, w_in, w_out, etas, x, y0 = _qif_problem(n, B, T, seed=5)
+    g = torch.tensor(np.random.default_rng(6).standard_normal((T, B, w_out.shape[0])).astype(np.float32), device="cuda:0")
+    res = {}
+    for mode in ("persistent", "per_step"):
+        if mode == "per_step":
+            monkeypatch.setenv("RP_NO_FWD_PERSIST", "1")
+        else:
+            monkeypatch.delenv("RP_NO_FWD_PERSIST", raising=False)
+        engine.clear_plans()
+        net, node, _cabi = _qif_engine(n, B, W, w_in, w_out, etas, y0, train=True)
+        obs = net.run(x, sampling_steps=1, verbose=False, enable_grad=True)
+        launches_fwd = engine.total_launches()
+        out = torch.stack(obs["out"])
+        (out * g).sum().backward()
+        rec = dict(out=out.detach().clone(), y=node.y.detach().clone(), gW=node["weights"].grad.clone(),
+                   gWo=net.get_edge("qif", "out").weights.grad.clone(), launches_fwd=launches_fwd)
+        node.reset(y0)
+        obs2 = net.run(x, sampling_steps=7, cutoff=11, verbose=False, enable_grad=False)      # no checkpoints, windowed records
+        rec["out_nograd"] = torch.stack(obs2["out"]).clone()
+        rec["y_nograd"] = node.y.detach().clone()
+        res[mode] = rec
+    monkeypatch.delenv("RP_NO_FWD_PERSIST", raising=False)
+    engine.clear_plans()
+    assert res["persistent"]["launches_fwd"] < 20 < res["per_step"]["launches_fwd"], (res["persistent"]["launches_fwd"], res["per_step"]["launches_fwd"])
+    assert float(res["per_step"]["out"].abs().max()) > 0 and float(res["per_step"]["gW"].abs().max()) > 0
+    for key in ("out", "y", "gW", "gWo", "out_nograd", "y_nograd"):
+        assert torch.equal(res["persistent"][key], res["per_step"][key]), key
