@@ -596,6 +596,196 @@ k_gemm_split3_lean(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2) of the plain contraction (adjoint product, weight gradient), round 2.
+// Two CTAs of a cluster (neighbouring row tiles, the SAME 256 columns) run one M = 256 MMA: each CTA keeps its own 128 rows of A and
+// its 128 x 256 accumulator, and only HALF of the B tile -- the tensor cores of the pair read both halves.  Per CTA and K block the
+// shared-memory fill drops from 48 KB to 32 KB and every MMA reads 8 KB instead of 12 KB: the contraction is power-bound under the
+// 1000 W cap, so bytes moved per flop is what is left to save.  Protocol (as in CUTLASS' 2-SM kernels): both producers load with
+// cp.async.bulk.tensor...cta_group::2 onto the LEADER's full barrier (address with the peer bit cleared), the leader's elected
+// thread issues tcgen05.mma.cta_group::2 and commits with a cluster multicast onto both CTAs' empty / accumulator-ready barriers,
+// the epilogue warps of both CTAs arrive on the leader's accumulator-free barrier.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t TC_PEER_MASK = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the even CTA of the pair
+struct TcCfg2 {
+    static constexpr int BQ = 256;
+    static constexpr int A_BYTES = TC_BP * TC_ROW_BYTES;
+    static constexpr int BH_BYTES = (BQ / 2) * TC_ROW_BYTES;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = 2 * BQ;
+    static constexpr int COLS_PER_THREAD = BQ / 2;
+};
+__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & TC_PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_ss_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2_mc(uint64_t* bar) {     // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & TC_PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_split3_cg2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,      // boxes of 128 rows
+                  int num_k_blocks, const __grid_constant__ EpiStore epi) {
+    using Cfg = TcCfg2;
+    constexpr int BQ = Cfg::BQ;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int CPT = Cfg::COLS_PER_THREAD;
+    constexpr int TC_BK = TcElt<true>::BK;
+    constexpr int TC_KC = TcElt<true>::KC;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);      // used in the leader only
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2] used in the leader only (both CTAs' epilogue warps arrive)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const bool leader = rank == 0;
+    const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+    const int p0 = bx * TC_BP, q0 = by * BQ;
+    const int qh = q0 + (int)rank * (BQ / 2);               // this CTA's half of the B tile
+    const int num_chunks = (num_k_blocks + TC_KC - 1) / TC_KC;
+    const int kb0 = bz * num_k_blocks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 2 * TC_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                      // the peer's barriers exist before anything arrives on them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own rows of A, own half of B, transaction bytes onto the leader's barrier =====
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                tma_load_2d_cg2(sa, &tmA_hi, &full_bar[stage], (kb0 + kb) * TC_BK, p0);
+                tma_load_2d_cg2(sa + Cfg::A_BYTES, &tmA_lo, &full_bar[stage], (kb0 + kb) * TC_BK, p0);
+                tma_load_2d_cg2(sa + 2 * Cfg::A_BYTES, &tmB_hi, &full_bar[stage], (kb0 + kb) * TC_BK, qh);
+                tma_load_2d_cg2(sa + 2 * Cfg::A_BYTES + Cfg::BH_BYTES, &tmB_lo, &full_bar[stage], (kb0 + kb) * TC_BK, qh);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one elected thread of the LEADER CTA drives both tensor cores =====
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc(true, 2 * TC_BP, BQ);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int chunk = kb / TC_KC, kin = kb - chunk * TC_KC;
+                const int buf = chunk & 1;
+                if (kin == 0) {
+                    mbar_wait(&tmem_empty_bar[buf], ((chunk >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                mbar_wait(&full_bar[stage], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BQ);
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t dA_hi = make_sw128_kmajor_desc(sa);
+                    const uint64_t dA_lo = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
+                    const uint64_t dB_hi = make_sw128_kmajor_desc(sa + 2 * Cfg::A_BYTES);
+                    const uint64_t dB_lo = make_sw128_kmajor_desc(sa + 2 * Cfg::A_BYTES + Cfg::BH_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TcElt<true>::KSTEPS; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                        umma_ss_cg2(tmem_d, dA_lo + adv, dB_hi + adv, idesc, (kin > 0 || k > 0) ? 1u : 0u);
+                        umma_ss_cg2(tmem_d, dA_hi + adv, dB_lo + adv, idesc, 1u);
+                        umma_ss_cg2(tmem_d, dA_hi + adv, dB_hi + adv, idesc, 1u);
+                    }
+                    umma_commit_cg2_mc(&empty_bar[stage]);
+                    if (kin == TC_KC - 1 || kb == num_k_blocks - 1) umma_commit_cg2_mc(&tmem_full_bar[buf]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): own 128 rows x 256 columns =====
+        const int ew = warp - 2;
+        const int lane_base = (warp & 3) * 32;
+        const int half = ew >> 2;
+        const int p = p0 + lane_base + lane;
+        float acc[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+        for (int chunk = 0; chunk < num_chunks; ++chunk) {
+            const int buf = chunk & 1;
+            mbar_wait(&tmem_full_bar[buf], (chunk >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * BQ + half * CPT);
+#pragma unroll
+            for (int c = 0; c < CPT / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr + (uint32_t)(c * 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[buf]);
+        }
+        const float2 usc = epi.unscale(p0);
+        float* cbase = epi.C + bz * epi.split_stride + (size_t)(q0 + half * CPT) * epi.ldc + p;
+        if (epi.accumulate) {
+            constexpr int RB = 32;
+#pragma unroll
+            for (int j0 = 0; j0 < CPT; j0 += RB) {
+                float old[RB];
+#pragma unroll
+                for (int j = 0; j < RB; ++j) old[j] = __ldcg(cbase + (size_t)(j0 + j) * epi.ldc);
+#pragma unroll
+                for (int j = 0; j < RB; ++j) cbase[(size_t)(j0 + j) * epi.ldc] = acc[j0 + j] * usc.x * usc.y + old[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) cbase[(size_t)j * epi.ldc] = acc[j] * usc.x * usc.y;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                      // nobody leaves while the peer may still read its shared memory / arrive on its barriers
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // Persistent multi-step forward kernel of the batched path (round 2): ONE cooperative launch integrates all T steps.
 //
 // CTA (bx, by) owns output tile (row tile bx, trial group by) for the whole horizon: barriers, TMEM and tensor maps are set up
@@ -910,6 +1100,7 @@ struct TcWorkspace {
     int amax_cap = 0;
     const void* fwd_history = nullptr; int fwd_T = -1;      // which checkpoints amax_src describes
     const void* wt_W = nullptr;                             // weights whose transposed split (WT_hi/lo) the last forward call left behind
+    CUtensorMap m_g_h[2], m_gT_h[2][2];                     // 128-row boxes of the B operands (CTA-pair kernel)
     void *src2_hi = nullptr, *src2_lo = nullptr;            // second source-operand buffer of the persistent multi-step forward kernel
     CUtensorMap m_src2[2];
     unsigned int* fwd_done = nullptr;                       // [B / bq_fwd + 1] step counters of that kernel
@@ -979,6 +1170,7 @@ inline int tc_workspace_create(TcWorkspace* w, int N, int B, bool f16, bool rate
     if (tc_make_map(&w->m_WT[0], w->WT_hi, f16, N, N, w->ldk, TC_BP) || tc_make_map(&w->m_WT[1], w->WT_lo, f16, N, N, w->ldk, TC_BP)) return 1;
     if (tc_make_map(&w->m_src[0], w->src_hi, f16, B, N, w->ldk, w->bq_fwd) || tc_make_map(&w->m_src[1], w->src_lo, f16, B, N, w->ldk, w->bq_fwd)) return 1;
     if (tc_make_map(&w->m_g[0], w->g_hi, f16, B, N, w->ldk, w->bq_fwd) || tc_make_map(&w->m_g[1], w->g_lo, f16, B, N, w->ldk, w->bq_fwd)) return 1;
+    if (tc_make_map(&w->m_g_h[0], w->g_hi, f16, B, N, w->ldk, 128) || tc_make_map(&w->m_g_h[1], w->g_lo, f16, B, N, w->ldk, 128)) return 1;
     return 0;
 }
 
@@ -1004,6 +1196,7 @@ inline int tc_workspace_ensure_wgrad(TcWorkspace* w, size_t* bytes) {
         if (tc_alloc(&w->gT_hi[c], nt, bytes) || tc_alloc(&w->gT_lo[c], nt, bytes) || tc_alloc(&w->srcT_hi[c], nt, bytes) || tc_alloc(&w->srcT_lo[c], nt, bytes)) return 1;
         if (tc_make_map(&w->m_srcT[c][0], w->srcT_hi[c], f16, w->N, w->ldt, w->ldt, TC_BP) || tc_make_map(&w->m_srcT[c][1], w->srcT_lo[c], f16, w->N, w->ldt, w->ldt, TC_BP)) return 1;
         if (tc_make_map(&w->m_gT[c][0], w->gT_hi[c], f16, w->N, w->ldt, w->ldt, w->bq_wg) || tc_make_map(&w->m_gT[c][1], w->gT_lo[c], f16, w->N, w->ldt, w->ldt, w->bq_wg)) return 1;
+        if (tc_make_map(&w->m_gT_h[c][0], w->gT_hi[c], f16, w->N, w->ldt, w->ldt, 128) || tc_make_map(&w->m_gT_h[c][1], w->gT_lo[c], f16, w->N, w->ldt, w->ldt, 128)) return 1;
     }
     if (side) {
         int lo = 0, hi = 0;
@@ -1045,9 +1238,34 @@ inline int tc_launch_epi(int bq, int P, int Q, int K, const CUtensorMap* A, cons
     if (e != cudaSuccess) RP_TC_FAIL("tcgen05 GEMM launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
+// CTA-pair launch of the plain contraction: Bh = maps of the B operand with 128-row boxes; cluster (2,1,1) along the row tiles
+// default on (A/B on one box, alternating: pass 31.99 / 31.87 ms vs 32.40 / 32.76 ms; weight-gradient chunk alone 1.94 vs 2.05 ms, adjoint
+// product alone 80.0 vs 81.3 us); RP_NO_TC_CG2=1 restores the single-CTA kernel
+inline bool tc_cg2_enabled() { static const bool on = getenv("RP_NO_TC_CG2") == nullptr; return on; }
+inline int tc_launch_cg2(int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bh, const EpiStore& epi, cudaStream_t st, int k_splits) {
+    constexpr int BK = TcElt<true>::BK;
+    if (P % (2 * TC_BP) || Q % 256 || K % (BK * k_splits)) RP_TC_FAIL("tc_launch_cg2: extents P=%d Q=%d K=%d", P, Q, K);
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(k_gemm_split3_cg2, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg2::SMEM_BYTES) != cudaSuccess) RP_TC_FAIL("cudaFuncSetAttribute failed");
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(P / TC_BP, Q / 256, k_splits); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg2::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int kb = K / BK / k_splits;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_gemm_split3_cg2, A[0], A[1], Bh[0], Bh[1], kb, epi);
+    if (e != cudaSuccess) RP_TC_FAIL("CTA-pair GEMM launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
 inline int tc_launch(bool f16, int bq, int P, int Q, int K, const CUtensorMap* A, const CUtensorMap* Bm, float* C, int ldc, int accumulate, cudaStream_t st,
-                     int k_splits = 1, size_t split_stride = 0, ScaleRef sa = no_scale(), ScaleRef sb = no_scale(), int item0 = 0, int items = 0) {
+                     int k_splits = 1, size_t split_stride = 0, ScaleRef sa = no_scale(), ScaleRef sb = no_scale(), int item0 = 0, int items = 0,
+                     const CUtensorMap* Bhalf = nullptr) {
     EpiStore e{C, ldc, accumulate, split_stride, sa, sb};
+    if (f16 && bq == 256 && Bhalf != nullptr && items <= 0 && P % (2 * TC_BP) == 0 && tc_cg2_enabled()) return tc_launch_cg2(P, Q, K, A, Bhalf, e, st, k_splits);
     if (f16) return tc_launch_epi<EpiStore, true>(bq, P, Q, K, A, Bm, e, st, k_splits, item0, items);
     return tc_launch_epi<EpiStore, false>(bq, P, Q, K, A, Bm, e, st, k_splits, item0, items);
 }
@@ -1106,11 +1324,11 @@ inline int tc_gemm(TcWorkspace* w, int mode, float* C, int ldc, int k_extent, in
                    int cb = 0, int item0 = 0, int items = 0) {
     switch (mode) {
         case TC_FWD:   return tc_launch(w->f16, w->bq_fwd, w->N, w->B, w->N, w->m_W, w->m_src, C, ldc, accumulate, st, 1, 0, tc_scale_W(w), sb);
-        case TC_DGRAD: return tc_launch(w->f16, w->bq_fwd, w->N, w->B, w->N, w->m_WT, w->m_g, C, ldc, accumulate, st, 1, 0, tc_scale_W(w), sb);
+        case TC_DGRAD: return tc_launch(w->f16, w->bq_fwd, w->N, w->B, w->N, w->m_WT, w->m_g, C, ldc, accumulate, st, 1, 0, tc_scale_W(w), sb, 0, 0, w->m_g_h);
         // 2-way split-K into two accumulation slices: N=4096 gives 512 tiles = 3.46 waves of 148 SMs (86 % filled);
         // 1024 work items = 6.92 waves (99 %).  The slices are summed by k_finish_wgrad.
         case TC_WGRAD: return tc_launch(w->f16, w->bq_wg, w->N, w->N, k_extent, w->m_srcT[cb], w->m_gT[cb], C, ldc, accumulate, st, TC_WGRAD_SPLITS, (size_t)w->N * ldc,
-                                        tc_scale_srcbound(w), sb, item0, items);
+                                        tc_scale_srcbound(w), sb, item0, items, w->m_gT_h[cb]);
     }
     RP_TC_FAIL("tc_gemm: unknown mode %d", mode);
 }
@@ -1141,7 +1359,9 @@ inline int tc_gemm_standalone(bool f16, int P, int Q, int K, const float* A, int
     CUtensorMap mA[2], mB[2];
     int rc = tc_make_map(&mA[0], a_hi, f16, P, Kp, Kp, TC_BP) || tc_make_map(&mA[1], a_lo, f16, P, Kp, Kp, TC_BP) ||
              tc_make_map(&mB[0], b_hi, f16, Q, Kp, Kp, bq) || tc_make_map(&mB[1], b_lo, f16, Q, Kp, Kp, bq);
-    if (!rc) rc = tc_launch(f16, bq, P, Q, Kp, mA, mB, C, ldc, accumulate, st, 1, 0, sa, sb);
+    CUtensorMap mBh[2];
+    if (!rc && f16 && bq == 256) rc = tc_make_map(&mBh[0], b_hi, f16, Q, Kp, Kp, 128) || tc_make_map(&mBh[1], b_lo, f16, Q, Kp, Kp, 128);
+    if (!rc) rc = tc_launch(f16, bq, P, Q, Kp, mA, mB, C, ldc, accumulate, st, 1, 0, sa, sb, 0, 0, (f16 && bq == 256) ? mBh : nullptr);
     cudaStreamSynchronize(st);
     cudaFree(tmp);
     cudaFree(amax);
