@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RP_ABI_VERSION 7
+#define RP_ABI_VERSION 8
 #define RP_MAX_IN 8      /* max fused input-projection width  m (wider inputs: use RP_IN_DENSE)  */
 #define RP_MAX_OUT 8     /* max fused readout width           k (wider readouts: use RP_OUT_DENSE) */
 #define RP_MAX_SV 4
@@ -43,7 +43,8 @@ extern "C" {
 enum { RP_LI_TANH = 0, RP_LI_SIGMOID = 1, RP_QIF = 2, RP_QIF_SFA = 3, RP_LIF = 4, RP_IK = 5 /* spiking_neurons/ik.yaml ik_op */,
        RP_IKU = 6 /* ik.yaml iku_op: recovery variable driven by the per-trial population means of v and of the spikes */,
        RP_IK_BIEXP = 7 /* ik.yaml:42-70 ik_biexp_op: iku_op with a bi-exponential synapse s' = -s/tau_d + x, x' = -x/tau_r + spike;
-                          tau_d travels in slot RP_P_TAU_S, tau_r in slot RP_P_TAU_X */ };
+                          tau_d travels in slot RP_P_TAU_S, tau_r in slot RP_P_TAU_X */,
+       RP_JIT = 8 /* a vector field compiled at run time from a user template (rp_plan_set_jit_module); rp_desc.jit_* describe it */ };
 /* parameter slots; each is a device pointer to 1, n, B or B*n floats (see rp_desc.param_per_neuron) */
 enum { RP_P_TAU = 0, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_RMAX, RP_P_SIG_S, RP_P_V0,
        /* ik_op: */ RP_P_C, RP_P_VR, RP_P_VTH, RP_P_G, RP_P_ER, RP_P_B, RP_P_TAU_U, RP_P_KAPPA, RP_NUM_PARAMS };
@@ -73,6 +74,10 @@ typedef struct rp_desc {
     float slope;            /* surrogate slope   (nodes.py:345-347)                             */
     int param_per_neuron[RP_NUM_PARAMS]; /* layout of each parameter: 0 one shared value, 1 [n] per neuron,
                                             2 [B] per trial, 3 [B][n] per trial and neuron (parameter sweeps; no gradients) */
+    /* RP_JIT only: */
+    int jit_nsv;            /* state variables (1..RP_MAX_SV); plane 0 is the reset variable of a spiking field */
+    int jit_spiking;        /* 1: threshold / reset on plane 0 with the surrogate gradient (SpikeResetNet), 0: RateNet */
+    int jit_src_plane;      /* plane projected by the recurrent weights, or -1: the source is an expression of the state */
 } rp_desc;
 
 typedef struct rp_plan rp_plan;
@@ -123,6 +128,8 @@ typedef struct rp_bwd_args {
     int T_total;
 } rp_bwd_args;
 
+#define RP_NUM_STAGES 5
+#ifndef __CUDACC_RTC__   /* device code compiled at run time (RP_JIT) includes this header for the constants and records only */
 int         rp_abi_version(void);
 const char* rp_last_error(void);
 int         rp_num_state_vars(int model);                       /* LI 1, QIF/LIF 2, QIF-SFA/IK/IKU 3, IK_BIEXP 4 */
@@ -135,6 +142,12 @@ void rp_plan_destroy(rp_plan* plan);
 long long rp_plan_workspace_bytes(const rp_plan* plan);
 /* kernels launched by this plan since creation (for bench.py's gpu_launches) */
 long long rp_plan_launch_count(const rp_plan* plan);
+
+/* RP_JIT: hand the plan the device code of its vector field -- a cubin / PTX image (e.g. from NVRTC, see rectipy_b200/jit.py) that
+ * defines the  extern "C" __global__  kernels `rp_jit_init_src`, `rp_jit_fwd_step` (one rp::FwdStepArgs record) and `rp_jit_adj_step`
+ * (one rp::AdjArgs record) against the argument records of rectipy_b200/csrc/rp_jit_abi.cuh.  This replaces what PyRates' code generation does in the reference
+ * (rectipy/nodes.py:232-262: `_circuit_from_yaml` -> `get_run_func`).  Must precede the first rp_forward of the plan. */
+int rp_plan_set_jit_module(rp_plan* plan, const void* image, long long nbytes);
 
 int rp_forward(rp_plan* plan, const rp_fwd_args* args, void* stream);
 int rp_backward(rp_plan* plan, const rp_bwd_args* args, void* stream);
@@ -161,7 +174,6 @@ int rp_plan_time_contraction(rp_plan* plan, int which, int iters, float* avg_ms,
  * ms[RP_NUM_STAGES] / marks[RP_NUM_STAGES]: 0 fused forward step (contraction + element-wise epilogue), 1 adjoint product
  * Z = (kW)^T g, 2 weight-gradient chunk, 3 reverse element-wise kernel(s), 4 everything else between the first and last mark
  * (per-call kernels, and whatever the caller enqueued between the two calls).  marks = intervals summed = launches of that stage. */
-#define RP_NUM_STAGES 5
 int rp_plan_stage_timing(rp_plan* plan, int enable);
 int rp_plan_stage_times(rp_plan* plan, float* ms, int* marks, void* stream);
 
@@ -175,6 +187,7 @@ int rp_trace_read(void* host_buf, int max_records);
  * precision RP_PREC_FP32 -> FFMA kernel, RP_PREC_3XTF32 / RP_PREC_3XF16 -> tcgen05 kernel (needs p,q,k extents it supports). */
 int rp_gemm_tn(int precision, int P, int Q, int K, const float* A, int lda, const float* B, int ldb,
                float* C, int ldc, int accumulate, void* stream);
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -9,9 +9,9 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-RP_ABI_VERSION = 7
+RP_ABI_VERSION = 8
 RP_MAX_IN, RP_MAX_OUT, RP_MAX_SV, RP_MAX_REC = 8, 8, 4, 4
-RP_LI_TANH, RP_LI_SIGMOID, RP_QIF, RP_QIF_SFA, RP_LIF, RP_IK, RP_IKU, RP_IK_BIEXP = range(8)
+RP_LI_TANH, RP_LI_SIGMOID, RP_QIF, RP_QIF_SFA, RP_LIF, RP_IK, RP_IKU, RP_IK_BIEXP, RP_JIT = range(9)
 (RP_P_TAU, RP_P_K, RP_P_ETA, RP_P_TAU_S, RP_P_TAU_X, RP_P_ALPHA, RP_P_RMAX, RP_P_SIG_S, RP_P_V0,
  RP_P_C, RP_P_VR, RP_P_VTH, RP_P_G, RP_P_ER, RP_P_B, RP_P_TAU_U, RP_P_KAPPA, RP_NUM_PARAMS) = range(18)
 RP_IN_NONE, RP_IN_DENSE, RP_IN_PROJ = range(3)
@@ -28,7 +28,8 @@ class rp_desc(C.Structure):
     _fields_ = [("model", C.c_int), ("n", C.c_int), ("batch", C.c_int), ("in_mode", C.c_int), ("n_in", C.c_int),
                 ("in_target", C.c_int), ("out_mode", C.c_int), ("n_out", C.c_int), ("out_var", C.c_int),
                 ("precision", C.c_int), ("dt", C.c_float), ("theta", C.c_float), ("v_reset", C.c_float),
-                ("slope", C.c_float), ("param_per_neuron", C.c_int * RP_NUM_PARAMS)]
+                ("slope", C.c_float), ("param_per_neuron", C.c_int * RP_NUM_PARAMS),
+                ("jit_nsv", C.c_int), ("jit_spiking", C.c_int), ("jit_src_plane", C.c_int)]
 
 
 class rp_fwd_args(C.Structure):
@@ -51,7 +52,7 @@ class rp_bwd_args(C.Structure):
 EXPORTS = ["rp_abi_version", "rp_last_error", "rp_num_state_vars", "rp_num_history_planes", "rp_num_records", "rp_plan_create",
            "rp_plan_destroy", "rp_plan_workspace_bytes", "rp_plan_launch_count", "rp_forward", "rp_backward", "rp_plan_status",
            "rp_rls_run", "rp_gemm_tn", "rp_plan_time_contraction", "rp_trace_enable", "rp_trace_read", "rp_plan_stage_timing",
-           "rp_plan_stage_times"]
+           "rp_plan_stage_times", "rp_plan_set_jit_module"]
 
 _LIB = None
 
@@ -106,6 +107,8 @@ def load():
     lib.rp_plan_stage_timing.restype = C.c_int
     lib.rp_plan_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_void_p]
     lib.rp_plan_stage_times.restype = C.c_int
+    lib.rp_plan_set_jit_module.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
+    lib.rp_plan_set_jit_module.restype = C.c_int
     lib.rp_gemm_tn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_void_p]
     lib.rp_gemm_tn.restype = C.c_int
     if lib.rp_abi_version() != RP_ABI_VERSION:

@@ -1,6 +1,7 @@
 // C-ABI entry points of the rectipy_b200 engine (see include/rectipy_b200.h for the contract and the
 // reference lines each entry replaces).  Host side: plan/workspace management and the per-step launch
 // sequences; device side: rp_kernels.cuh (element-wise), rp_gemm_simt.cuh (FFMA), rp_gemm_tc.cuh (tcgen05).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -52,6 +53,12 @@ inline int nsv_of(int model) {
 }
 inline bool spiking(int model) { return model == RP_QIF || model == RP_QIF_SFA || model == RP_LIF || rp::is_ik(model); }
 inline int nhist_of(int model) { return nsv_of(model) + (rp::is_ik(model) ? 1 : 0); }
+// plan-aware variants (RP_JIT: the description carries what the template id implies for the compiled fields)
+inline int nsv_of(const rp_desc& d) { return d.model == RP_JIT ? d.jit_nsv : nsv_of(d.model); }
+inline bool spiking(const rp_desc& d) { return d.model == RP_JIT ? d.jit_spiking != 0 : spiking(d.model); }
+inline int nhist_of(const rp_desc& d) { return d.model == RP_JIT ? d.jit_nsv + 1 : nhist_of(d.model); }      // JIT: + recurrent drive
+// plane of the state that the recurrent weights project (-1: an expression of the state kept in plan->src)
+inline int src_plane_of(const rp_desc& d) { return d.model == RP_JIT ? d.jit_src_plane : (spiking(d.model) ? 1 : -1); }
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -80,6 +87,9 @@ struct rp_plan {
     float2* asum = nullptr;  // iku: [B] per-trial means of the recovery-variable adjoint terms
     float* dWraw = nullptr;  // [N][ldw]
     float* dwout_part = nullptr;   // fused reverse kernel: [B/32][k][N] partial sums of dW_out
+    // RP_JIT: module with the run-time compiled kernels of the template
+    CUmodule jit_mod = nullptr;
+    CUfunction jit_init_src = nullptr, jit_fwd = nullptr, jit_adj = nullptr;
     // optional per-stage timing (rp_plan_stage_timing): a CUDA event on the launching stream before every launch of the step loops
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -116,6 +126,28 @@ inline void stage_mark(rp_plan* p, int cat, cudaStream_t st) {
     cudaEventRecord(p->ev_pool[p->ev_used++], st);
 }
 
+// ---- driver API through the runtime's entry-point query (the library must load on a box without libcuda) -------------------
+typedef CUresult (*pfn_cuModuleLoadData)(CUmodule*, const void*);
+typedef CUresult (*pfn_cuModuleGetFunction)(CUfunction*, CUmodule, const char*);
+typedef CUresult (*pfn_cuModuleUnload)(CUmodule);
+typedef CUresult (*pfn_cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**);
+template <typename F> F drv_entry(const char* name) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<F>(ptr);
+}
+// launch one of the plan's run-time compiled kernels (single by-value argument record)
+int jit_launch(CUfunction fn, int grid, int block, void* arg_record, cudaStream_t st) {
+    static pfn_cuLaunchKernel launch = drv_entry<pfn_cuLaunchKernel>("cuLaunchKernel");
+    if (!launch || !fn) return fail("run-time compiled kernel not available (rp_plan_set_jit_module not called?)");
+    void* params[] = {arg_record};
+    const CUresult r = launch(fn, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, 0, reinterpret_cast<CUstream>(st), params, nullptr);
+    if (r != CUDA_SUCCESS) return fail("cuLaunchKernel of a run-time compiled kernel failed with CUresult %d", (int)r);
+    return 0;
+}
+struct JitInitSrcArgs { int N, B; const float* y; rp::ModelParams mp; float* src; int ld; };
+
 int plan_alloc(rp_plan* p, float** ptr, size_t n_floats) {
     RP_CUDA(cudaMalloc(reinterpret_cast<void**>(ptr), n_floats * sizeof(float)));
     p->ws_bytes += n_floats * sizeof(float);
@@ -134,6 +166,7 @@ rp::ModelParams make_params(const rp_plan* p, const float* const* params) {
 }
 
 int check_params(const rp_plan* p, const float* const* params) {
+    if (p->d.model == RP_JIT) return params[RP_P_K] ? 0 : fail("RP_JIT: parameter slot RP_P_K (the constant coupling factor 1) is NULL");
     if (rp::is_ik(p->d.model)) {
         static const int need_ik[] = {RP_P_C, RP_P_K, RP_P_VR, RP_P_VTH, RP_P_ETA, RP_P_G, RP_P_ER, RP_P_B, RP_P_TAU_U, RP_P_KAPPA, RP_P_TAU_S};
         for (int q : need_ik) if (!params[q]) return fail("ik_op parameter slot %d is NULL", q);
@@ -416,13 +449,17 @@ int rp_num_records(int T, int S, int cutoff) {
 
 int rp_plan_create(const rp_desc* d, rp_plan** out) {
     if (!d || !out) return fail("rp_plan_create: null argument");
-    const int nsv = nsv_of(d->model);
-    if (nsv < 0) return fail("rp_plan_create: unknown model %d", d->model);
+    const int nsv = nsv_of(*d);
+    if (nsv < 0 || (d->model == RP_JIT && (nsv < 1 || nsv > RP_MAX_SV))) return fail("rp_plan_create: unknown model %d / bad state-variable count", d->model);
+    if (d->model == RP_JIT) {
+        if (d->precision != RP_PREC_FP32) return fail("rp_plan_create: run-time compiled fields run on the per-step fp32 path (precision must be RP_PREC_FP32)");
+        if (d->jit_src_plane >= nsv || d->out_var >= 3 || d->out_var >= nsv) return fail("rp_plan_create: RP_JIT source / output plane out of range (output planes 0..2)");
+    }
     if (d->n <= 0 || d->batch <= 0) return fail("rp_plan_create: n and batch must be positive");
     if (d->in_mode == RP_IN_PROJ && (d->n_in <= 0 || d->n_in > RP_MAX_IN)) return fail("rp_plan_create: n_in must be in [1,%d] for RP_IN_PROJ", RP_MAX_IN);
     if (d->out_mode == RP_OUT_READOUT && (d->n_out <= 0 || d->n_out > RP_MAX_OUT)) return fail("rp_plan_create: n_out must be in [1,%d] for RP_OUT_READOUT", RP_MAX_OUT);
     if (d->out_var < 0 || d->out_var > RP_VAR_R) return fail("rp_plan_create: bad out_var");
-    if (d->out_var == RP_VAR_R && spiking(d->model)) return fail("rp_plan_create: RP_VAR_R only exists on rate models");
+    if (d->out_var == RP_VAR_R && (spiking(*d) || d->model == RP_JIT)) return fail("rp_plan_create: RP_VAR_R only exists on rate models");
     if (d->out_var != RP_VAR_R && d->out_var >= nsv) return fail("rp_plan_create: out_var %d not a state variable of model %d", d->out_var, d->model);
     if (d->in_target == 1 && d->model != RP_LIF) return fail("rp_plan_create: in_target=1 (s_ext) only exists on the lif template");
     if (!(d->dt > 0.f)) return fail("rp_plan_create: dt must be positive");
@@ -465,7 +502,7 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
         rc |= plan_alloc(p, &p->Wk, (size_t)N * p->ldw);
         rc |= plan_alloc(p, &p->WkT, (size_t)N * p->ldw);
         rc |= plan_alloc(p, &p->g, plane);
-        if (!spiking(d->model)) rc |= plan_alloc(p, &p->src, plane);
+        if (src_plane_of(*d) < 0) rc |= plan_alloc(p, &p->src, plane);
     } else {
         size_t bytes = 0;
         rc |= rp::tc_workspace_create(&p->tc, N, B, f16, !spiking(d->model), &bytes);
@@ -482,7 +519,7 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
         p->ws_bytes += 2 * (size_t)B * sizeof(float2);
     }
     // (iku_op needs a per-step reduction over all neurons of a trial: per-step launch sequences only)
-    if (!p->use_tc && !rp::is_mean_field(d->model) && !getenv("RP_NO_PERSISTENT")) {
+    if (!p->use_tc && !rp::is_mean_field(d->model) && d->model != RP_JIT && !getenv("RP_NO_PERSISTENT")) {
         if (persistent_setup(p, prop)) { rp_plan_destroy(p); return 1; }
     }
     *out = p;
@@ -495,6 +532,7 @@ void rp_plan_destroy(rp_plan* p) {
     for (float* b : bufs) if (b) cudaFree(b);
     if (p->ps_bar) cudaFree(p->ps_bar);
     if (p->ps_part) cudaFree(p->ps_part);
+    if (p->jit_mod) { static pfn_cuModuleUnload unload = drv_entry<pfn_cuModuleUnload>("cuModuleUnload"); if (unload) unload(p->jit_mod); }
     if (p->mf) cudaFree(p->mf);
     if (p->asum) cudaFree(p->asum);
     for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
@@ -504,6 +542,21 @@ void rp_plan_destroy(rp_plan* p) {
 
 long long rp_plan_workspace_bytes(const rp_plan* p) { return p ? (long long)p->ws_bytes : 0; }
 long long rp_plan_launch_count(const rp_plan* p) { return p ? p->launches : 0; }
+
+int rp_plan_set_jit_module(rp_plan* p, const void* image, long long nbytes) {
+    if (!p || !image || nbytes <= 0) return fail("rp_plan_set_jit_module: bad argument");
+    if (p->d.model != RP_JIT) return fail("rp_plan_set_jit_module: the plan was not created with model RP_JIT");
+    static pfn_cuModuleLoadData load = drv_entry<pfn_cuModuleLoadData>("cuModuleLoadData");
+    static pfn_cuModuleGetFunction getf = drv_entry<pfn_cuModuleGetFunction>("cuModuleGetFunction");
+    if (!load || !getf) return fail("rp_plan_set_jit_module: CUDA driver entry points not available");
+    RP_CUDA(cudaFree(0));                                   // make sure the primary context is current
+    CUresult r = load(&p->jit_mod, image);
+    if (r != CUDA_SUCCESS) return fail("rp_plan_set_jit_module: cuModuleLoadData failed with CUresult %d", (int)r);
+    if (getf(&p->jit_fwd, p->jit_mod, "rp_jit_fwd_step") != CUDA_SUCCESS || getf(&p->jit_adj, p->jit_mod, "rp_jit_adj_step") != CUDA_SUCCESS ||
+        getf(&p->jit_init_src, p->jit_mod, "rp_jit_init_src") != CUDA_SUCCESS)
+        return fail("rp_plan_set_jit_module: the image does not define rp_jit_fwd_step / rp_jit_adj_step / rp_jit_init_src");
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------------
 int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
@@ -551,11 +604,14 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
     if (a->t_offset < 0 || a->t_offset + a->T > T_tot) return fail("rp_forward: bad t_offset/T_total");
     if (p->persistent) return persistent_forward(p, a, mp, st);
     float* base = a->history ? a->history : p->pp;
-    const size_t hslot = (size_t)nhist_of(d.model) * plane;          // checkpoint slot stride (ik: + recurrent-drive plane)
+    const size_t hslot = (size_t)nhist_of(d) * plane;          // checkpoint slot stride (ik, run-time compiled fields: + recurrent-drive plane)
     auto slot_ptr = [&](int t) -> float* { return a->history ? base + (size_t)t * hslot : base + (size_t)(t & 1) * slot; };
+    const bool jit = d.model == RP_JIT;
+    const int src_plane = src_plane_of(d);
+    if (jit && !p->jit_fwd) return fail("rp_forward: RP_JIT plan without a module (call rp_plan_set_jit_module first)");
     RP_CUDA(cudaMemcpyAsync(slot_ptr(0), a->y0, slot * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
-    const bool spk = spiking(d.model);
+    const bool spk = spiking(d);
     const bool f16 = p->use_tc && p->tc.f16;
     // binary16 operands: bound of the source variable.  Rate models: static (|tanh| <= 1, sigmoid <= max r_max).  Spiking models:
     // |s_{t+1}| <= |s_t| + 1 (one spike adds exactly 1, nodes.py:385), tracked per step in tc.amax_src.
@@ -578,7 +634,12 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         }
         RP_LAUNCH_CHECK();
     }
-    if (a->T > 0 && (!spk || p->use_tc)) {
+    if (jit && a->T > 0 && src_plane < 0) {          // source = expression of the state: src_0 from y_0
+        JitInitSrcArgs ja{N, B, slot_ptr(0), mp, p->src, N};
+        if (jit_launch(p->jit_init_src, ew_grid(p, plane), 256, &ja, st)) return 1;
+        ++p->launches;
+    }
+    if (!jit && a->T > 0 && (!spk || p->use_tc)) {
         if (f16 && spk) {    // first pass: exact maximum of src_0
             RP_DISPATCH_MODEL(d.model, (rp::k_init_src<M_><<<ew_grid(p, plane), 256, 0, st>>>(N, B, slot_ptr(0), mp, nullptr, N, nullptr, nullptr,
                                         p->tc.ldk, 0, rp::no_scale(), p->tc.amax_src)));
@@ -652,7 +713,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         fa.dt = d.dt; fa.theta = d.theta; fa.v_reset = d.v_reset;
         fa.y_cur = cur; fa.y_next = nxt; fa.u = p->u; fa.ldu = p->ldu;
         fa.x_t = a->x ? a->x + (size_t)t * x_stride : nullptr; fa.W_in = a->W_in; fa.mp = mp;
-        fa.src_next = (!spk && !p->use_tc) ? p->src : nullptr;
+        fa.src_next = (src_plane < 0 && !p->use_tc) ? p->src : nullptr;
         fa.src_hi = p->use_tc ? p->tc.src_hi : nullptr; fa.src_lo = p->use_tc ? p->tc.src_lo : nullptr; fa.ld_src = p->tc.ldk;
         fa.sc_out = rp::no_scale(); fa.amax_out = nullptr;
         rp::ScaleRef sc_in = rp::no_scale();
@@ -665,7 +726,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
                 sc_in = sc_rate; fa.sc_out = sc_rate;
             }
         }
-        fa.urec_out = (rp::is_ik(d.model) && a->history) ? cur + (size_t)nsv * plane : nullptr;
+        fa.urec_out = ((rp::is_ik(d.model) || jit) && a->history) ? cur + (size_t)nsv * plane : nullptr;
         fa.mf = p->mf;
         if (rp::is_mean_field(d.model)) {
             rp::k_trial_means<<<B, 256, 0, st>>>(N, cur, d.theta, p->mf);
@@ -677,9 +738,10 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         fa.no_lean = getenv("RP_NO_FWD_LEAN") ? 1 : 0;
         if (!p->use_tc) {
             // u[b][i] = sum_j (kW)[i][j] src_t[b][j], then the element-wise step
-            const float* srcp = spk ? cur + plane : p->src;
+            const float* srcp = src_plane >= 0 ? cur + (size_t)src_plane * plane : p->src;
             if (gemm_fp32(p, true, N, B, N, p->Wk, p->ldw, srcp, N, p->u, p->ldu, 0, st, &p->launches)) return 1;
-            RP_DISPATCH_MODEL(d.model, (rp::k_fwd_step<M_><<<ew_grid(p, plane), 256, 0, st>>>(fa)));
+            if (jit) { if (jit_launch(p->jit_fwd, ew_grid(p, plane), 256, &fa, st)) return 1; }
+            else RP_DISPATCH_MODEL(d.model, (rp::k_fwd_step<M_><<<ew_grid(p, plane), 256, 0, st>>>(fa)));
             ++p->launches;
             RP_LAUNCH_CHECK();
         } else {
@@ -720,7 +782,8 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
             }
             oa.rec_post = spk ? 0 : 1;     // RateNet: y is post-update (nodes.py:169); SpikeResetNet: pre-update (nodes.py:387)
             stage_mark(p, ST_OTHER, st);
-            RP_DISPATCH_MODEL(d.model, (rp::k_observe<M_><<<B, 256, 0, st>>>(oa)));
+            if (jit) rp::k_observe<RP_QIF><<<B, 256, 0, st>>>(oa);       // state planes only: any instantiation without an activation will do
+            else RP_DISPATCH_MODEL(d.model, (rp::k_observe<M_><<<B, 256, 0, st>>>(oa)));
             ++p->launches;
             RP_LAUNCH_CHECK();
         }
@@ -752,7 +815,10 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     const rp::ModelParams mp = make_params(p, a->params);
     const int fold = rp::fold_slot(d.model);
     const int kstride = d.param_per_neuron[fold] ? 1 : 0;
-    const bool spk = spiking(d.model);
+    const bool spk = spiking(d);
+    const bool jit = d.model == RP_JIT;
+    const int src_plane = src_plane_of(d);
+    if (jit && !p->jit_adj) return fail("rp_backward: RP_JIT plan without a module (call rp_plan_set_jit_module first)");
     const bool need_dW = a->dW != nullptr || a->dparams[rp::fold_slot(d.model)] != nullptr;
     stage_mark(p, ST_OTHER, st);
 
@@ -815,7 +881,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
 
     const size_t x_stride = d.in_mode == RP_IN_DENSE ? plane : (d.in_mode == RP_IN_PROJ ? (size_t)B * d.n_in : 0);
     const size_t out_stride = d.out_mode == RP_OUT_READOUT ? (size_t)B * d.n_out : plane;
-    const size_t hslot = (size_t)nhist_of(d.model) * plane;
+    const size_t hslot = (size_t)nhist_of(d) * plane;
     const int T_tot = a->T_total > 0 ? a->T_total : a->T;
     const int tr = a->truncate_steps;
     const bool truncating = tr > 0 && tr < T_tot;
@@ -834,7 +900,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
     aa.N = N; aa.B = B; aa.m = d.n_in; aa.k = d.n_out; aa.in_mode = d.in_mode; aa.in_target = d.in_target;
     aa.out_mode = d.out_mode; aa.out_var = d.out_var; aa.dt = d.dt; aa.theta = d.theta; aa.slope = d.slope;
     aa.adj = p->adj; aa.Z = p->u; aa.ldz = p->ldu; aa.W_in = a->W_in; aa.W_out = a->W_out; aa.mp = mp;
-    if (!p->use_tc) { aa.g = wg_batched ? p->wg_g : p->g; aa.src = spk ? nullptr : (wg_batched ? p->wg_src : p->src); }
+    if (!p->use_tc) { aa.g = wg_batched ? p->wg_g : p->g; aa.src = src_plane >= 0 ? nullptr : (wg_batched ? p->wg_src : p->src); }
     else if (!f16) { aa.g_hi = (float*)p->tc.g_hi; aa.g_lo = (float*)p->tc.g_lo; aa.ld_g = p->tc.ldk; aa.ld_t = p->tc.ldt; }
     else { aa.g = p->tc.g32; aa.src = spk ? nullptr : p->tc.src32; }      // binary16: fp32 g + exact maximum, converted by k_adj_convert_f16
     int gslot = 1;                  // binary16: meta slot holding max |g_t| of the step being processed
@@ -920,9 +986,9 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                 const float* g_cur = wg_batched ? p->wg_g + (size_t)wg_pos * plane : p->g;
                 if (gemm_fp32(p, true, N, B, N, p->WkT, p->ldw, g_cur, N, p->u, p->ldu, 0, st, &p->launches)) return 1;
                 if (need_dW) {
-                    const float* srcp = spk ? a->history + (size_t)t * hslot + plane : p->src;
+                    const float* srcp = src_plane >= 0 ? a->history + (size_t)t * hslot + (size_t)src_plane * plane : p->src;
                     if (wg_batched) {
-                        if (spk) RP_CUDA(cudaMemcpyAsync(p->wg_src + (size_t)wg_pos * plane, srcp, plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                        if (src_plane >= 0) RP_CUDA(cudaMemcpyAsync(p->wg_src + (size_t)wg_pos * plane, srcp, plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
                         if (wg_pos + 1 == p->wg_chunk || t == 0) {
                             // dWraw[i][j] += sum over the chunk's (step, trial) rows of r[j] * g[i]
                             if (gemm_fp32(p, false, N, N, (wg_pos + 1) * B, p->wg_src, N, p->wg_g, N, p->dWraw, p->ldw, 1, st, &p->launches)) return 1;
@@ -930,7 +996,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                         }
                         ++wg_pos;
                         aa.g = p->wg_g + (size_t)wg_pos * plane;                 // where this launch's "pre" puts g_{t-1}, r_{t-1}
-                        if (!spk) aa.src = p->wg_src + (size_t)wg_pos * plane;
+                        if (src_plane < 0) aa.src = p->wg_src + (size_t)wg_pos * plane;
                     } else if (B <= 16) {
                         dim3 og((N + 255) / 256, N);
                         rp::k_outer_acc<<<og, 256, 0, st>>>(N, B, p->g, N, srcp, N, p->dWraw, p->ldw);
@@ -944,7 +1010,7 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             }
             const Window w = window_of(a->t_offset + t, T_tot, a->sampling_steps, a->cutoff);
             aa.y_t = a->history + (size_t)t * hslot;
-            aa.urec_t = rp::is_ik(d.model) ? a->history + (size_t)t * hslot + (size_t)nsv * plane : nullptr;
+            aa.urec_t = (rp::is_ik(d.model) || jit) ? a->history + (size_t)t * hslot + (size_t)nsv * plane : nullptr;
             if (rp::is_mean_field(d.model)) {
                 // population means of y_t and of the incoming adjoint of u, one block per trial, before the element-wise adjoint
                 rp::k_trial_means<<<B, 256, 0, st>>>(N, aa.y_t, d.theta, p->mf);
@@ -1048,6 +1114,8 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                     });
                 }
                 else     { RP_DISPATCH_MODEL(d.model, (rp::launch_pdl(rp::k_adj_step_v4<M_, true, 8>, dim3(N / 128, B / rp::ADJ4_TB), ablock, 0, st, va))); }
+            } else if (jit) {
+                if (jit_launch(p->jit_adj, ew_grid(p, plane), 256, &aa, st)) return 1;
             } else {
                 RP_DISPATCH_MODEL(d.model, (rp::k_adj_step<M_><<<agrid, ablock, 0, st>>>(aa)));
             }

@@ -56,6 +56,10 @@ class PlanKey:
     slope: float
     per_neuron: Tuple[int, ...]
     device: int
+    jit_key: str = ""        # RP_JIT: key of the compiled program (rectipy_b200.jit) and what rp_desc.jit_* carry
+    jit_nsv: int = 0
+    jit_spiking: int = 0
+    jit_src_plane: int = 0
 
 
 class Plan:
@@ -74,10 +78,17 @@ class Plan:
         d.dt, d.theta, d.v_reset, d.slope = key.dt, key.theta, key.v_reset, key.slope
         for i, v in enumerate(key.per_neuron):
             d.param_per_neuron[i] = v
+        d.jit_nsv, d.jit_spiking, d.jit_src_plane = key.jit_nsv, key.jit_spiking, key.jit_src_plane
         handle = C.c_void_p()
         with torch.cuda.device(key.device):
             abi.check(self.lib.rp_plan_create(C.byref(d), C.byref(handle)), "rp_plan_create")
-        self.handle = handle
+            self.handle = handle
+            if key.model == abi.RP_JIT:
+                from . import jit
+                image = jit.program(key.jit_key).image
+                abi.check(self.lib.rp_plan_set_jit_module(handle, image, len(image)), "rp_plan_set_jit_module")
+        self.nsv = key.jit_nsv if key.model == abi.RP_JIT else int(self.lib.rp_num_state_vars(key.model))
+        self.nh = key.jit_nsv + 1 if key.model == abi.RP_JIT else int(self.lib.rp_num_history_planes(key.model))
 
     def __del__(self):
         try:
@@ -199,7 +210,7 @@ class EngineRun(torch.autograd.Function):
         lib = plan.lib
         dev = y0.device
         B, N = key.batch, key.n
-        nh = lib.rp_num_history_planes(key.model)
+        nh = plan.nh
         n_rec = lib.rp_num_records(cfg.T, cfg.sampling_steps, cfg.cutoff)
         # grad mode is off inside Function.forward; needs_input_grad already accounts for no_grad() at apply time
         needs_grad = any(ctx.needs_input_grad)
@@ -256,8 +267,7 @@ class EngineRun(torch.autograd.Function):
         plan, cfg = ctx.plan, ctx.cfg
         key, lib = plan.key, plan.lib
         B, N = key.batch, key.n
-        nsv = lib.rp_num_state_vars(key.model)
-        nh = lib.rp_num_history_planes(key.model)
+        nsv, nh = plan.nsv, plan.nh
         saved = list(ctx.saved_tensors)
         has_x, has_win, has_wout = ctx.has
         x_c = saved.pop(0) if has_x else None

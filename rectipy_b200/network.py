@@ -79,12 +79,16 @@ def _engine_call(node: RateNet, x: Optional[torch.Tensor], in_mode: int, W_in: O
     slots, ptensors, per_neuron = node.param_slots()
     n_in = W_in.shape[1] if in_mode == abi.RP_IN_PROJ else 0
     n_out = W_out.shape[0] if out_mode == abi.RP_OUT_READOUT else 0
+    prog = node.spec.jit_program
+    if prog is not None and node.precision not in ("auto", "fp32", "float32"):
+        raise NotImplementedError("rectipy_b200: run-time compiled templates run on the per-step fp32 path (precision='fp32' or 'auto')")
+    jit_kw = {} if prog is None else dict(jit_key=prog.key, jit_nsv=prog.nsv, jit_spiking=int(prog.spiking), jit_src_plane=prog.src_plane)
     key = engine.PlanKey(
         model=node.spec.model, n=node.n, batch=node.batch, in_mode=in_mode, n_in=n_in, in_target=node.in_target,
         out_mode=out_mode, n_out=n_out, out_var=node.out_var if out_var is None else out_var,
-        precision=_precision_code(node.precision, node.n, node.batch), dt=node.dt, theta=node.theta,
-        v_reset=node.v_reset, slope=node.slope, per_neuron=per_neuron,
-        device=node.device.index if node.device.index is not None else torch.cuda.current_device())
+        precision=abi.RP_PREC_FP32 if prog is not None else _precision_code(node.precision, node.n, node.batch), dt=node.dt,
+        theta=node.theta, v_reset=node.v_reset, slope=node.slope, per_neuron=per_neuron,
+        device=node.device.index if node.device.index is not None else torch.cuda.current_device(), **jit_kw)
     plan = engine.get_plan(key)
     cfg = engine.RunConfig(T=T, sampling_steps=S, cutoff=cutoff, truncate_steps=truncate, rec_vars=tuple(rec_vars),
                            rec_reduce=tuple(int(r) for r in rec_reduce), want_out=want_out, param_slots=slots)

@@ -114,7 +114,13 @@ class RateNet:
         self.in_target = spec.input_vars[self._in_key]
         if output_var is None:
             output_var = spec.source_var if spec.spiking else spec.state_vars[0][0]
-        self._out_key = spec.resolve(output_var, spec.out_vars)
+        try:
+            self._out_key = spec.resolve(output_var, spec.out_vars)
+        except KeyError:
+            if spec.jit_program is not None:
+                raise NotImplementedError(f"rectipy_b200.jit: output_var {output_var!r} must be one of the state variables "
+                                          f"{sorted(spec.out_vars)} of a run-time compiled template")
+            raise
         self.out_var = spec.out_vars[self._out_key]
         if self.out_var != abi.RP_VAR_R:
             self._var_map["out"] = self._var_map[self._out_key]
@@ -327,7 +333,7 @@ class SpikeResetNet(RateNet):
         if spec.resolve(spike_var, {spec.spike_var: 0}) != spec.spike_var:
             raise KeyError(spike_var)
         rkey = spec.resolve(reset_var, dict(spec.state_vars))
-        if self._var_map[rkey][0] != 0:
+        if self._planes[self._var_map[rkey][0] // self.n] != 0:       # compiled fields: v; run-time compiled fields put it in plane 0
             raise NotImplementedError("rectipy_b200 resets the membrane potential `v`; other reset variables are not supported")
         self._var_map["reset_var"] = self._var_map[rkey]
         self._thresh = float(spike_threshold)
@@ -352,6 +358,13 @@ def node_from_template(node, input_var: str, output_var: str, weights=None, sour
                        **kwargs) -> RateNet:
     """Counterpart of `RateNet.from_pyrates` / `SpikeResetNet.from_pyrates` (rectipy/nodes.py:112-164,363-380)."""
     spec = resolve_template(node)
+    if spec.jit_field is not None and spec.jit_program is None:
+        # equations that match no compiled field: generate + compile the kernels now that the variable roles are known
+        from . import jit
+        if isinstance(spike_var, (list, tuple)):
+            raise NotImplementedError("rectipy_b200: MultiSpikeResetNet (several spike variables) is not built yet")
+        spec = jit.bind_spec(spec, source_var if weights is not None else None, target_var if weights is not None else None,
+                             input_var, spike_var, reset_var if spike_var is not None else None)
     for k in ("clear", "float_precision", "file_name", "verbose", "auto_diff", "vectorize", "backend", "solver"):
         kwargs.pop(k, None)           # PyRates code-generation switches; nothing to generate here
     kwargs.pop("var_mapping", None)

@@ -7,9 +7,9 @@ spiking_neurons/qif.yaml, spiking_neurons/lif.yaml) are recognised by their equa
 vector fields of rectipy_b200/csrc/rp_kernels.cuh.  User YAML files in the same PyRates template syntax
 (`base:`, `equations: replace/add`, `variables:`) are parsed and matched against the compiled fields -- by equation text
 first, then symbolically (sympy: `v*v` for `v^2`, reordered terms, `-(1/tau)*v` for `-v/tau` are the same field) -- so changed
-default values and rewritten but identical equations are honoured; an operator whose equations match none of the compiled fields
-raises NotImplementedError
-(there is no generic/CPU fallback).
+default values and rewritten but identical equations are honoured; an operator set whose equations match none of the compiled
+fields is handed to rectipy_b200/jit.py, which generates its CUDA kernels (step, adjoint) with sympy and compiles them with NVRTC
+(there is no CPU fallback; what the generator cannot express raises NotImplementedError).
 """
 from __future__ import annotations
 
@@ -44,6 +44,8 @@ class TemplateSpec:
     planes: Dict[str, int] = field(default_factory=dict)     # "op/var" -> engine state plane (0 v, 1 s, 2 x/u); the order of
                                                              # `state_vars` is the reference's y order (equation order)
     fold_param: str = ""                                     # "op/name" of the coupling constant folded into the weights
+    jit_field: object = None                                 # rectipy_b200.jit.JitField: equations that match no compiled field
+    jit_program: object = None                               # rectipy_b200.jit.JitProgram once the variable roles are bound
 
     def plane_of(self, key: str) -> int:
         return self.planes[key] if self.planes else [k for k, _ in self.state_vars].index(key)
@@ -240,9 +242,9 @@ def _spec_from_ops(ops: List[OperatorDef]) -> TemplateSpec:
             params={f"{o}/{p}": (_SLOT[p], _val(mv[p])) for p in pn},
             source_var=f"{o}/s", target_var=f"{o}/s_in", input_vars=inputs, spike_var=f"{o}/spike",
             out_vars={f"{o}/{v}": i for i, v in enumerate(sv)})
-    raise NotImplementedError(
-        "rectipy_b200: the operator equations " + str([op.equations for op in ops]) + " do not match any vector field "
-        "compiled into the engine (li_op+tanh_op, li_op+sigmoid_op, qif_op, qif_sfa_op, lif_op, ik_op, iku_op, ik_biexp_op).")
+    # none of the compiled fields: generate the kernels at run time (rectipy_b200/jit.py), as PyRates does for the reference
+    from . import jit
+    return jit.unbound_spec(ops)
 
 
 # ------------------------------------------------------------------------------------------------------------

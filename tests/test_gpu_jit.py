@@ -1,0 +1,213 @@
+"""Run-time compiled vector fields (rectipy_b200/jit.py, RP_JIT): a user template whose equations match none of the compiled fields
+runs through kernels generated from its equations.  The checker is the oracle's node classes (RateNet / SpikeResetNet restatements,
+oracle/rectipy_oracle.py) around the same field written by hand in torch, fp64, one trial at a time -- exactly what the reference
+does with the function PyRates generates (rectipy/nodes.py:58-90,166-170,382-392).
+
+Bars: rate field <= 1e-5 relative (outputs, recorded state, gradients); spiking field: identical spike raster, outputs <= 1e-4,
+gradients <= 2e-3 (fp32 engine vs fp64 truth across threshold dynamics, as for the compiled spiking fields).
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import rel_err, orc
+
+pytestmark = pytest.mark.gpu
+
+YAML = """
+fhn_op:
+  base: OperatorTemplate
+  equations:
+    - "v' = v - v^3/3 - w + I_ext + g*r_in"
+    - "w' = (v + a - b*w)/tau_w"
+    - "r = 1/(1 + exp(-beta*v))"
+  variables:
+    v: output(0.1)
+    w: variable(0.0)
+    r: variable(0.0)
+    g: 0.5
+    a: 0.7
+    b: 0.8
+    tau_w: 12.5
+    beta: 2.0
+    I_ext: input(0.0)
+    r_in: input(0.0)
+fhn:
+  base: NodeTemplate
+  operators:
+    - fhn_op
+adex_op:
+  base: OperatorTemplate
+  equations:
+    - "v' = (E_L - v + delta*exp((v - v_T)/delta) - w + I_ext)/tau + J*s_in"
+    - "w' = (a*(v - E_L) - w)/tau_w + b*spike"
+    - "s' = -s/tau_s + spike"
+  variables:
+    s: output(0.0)
+    v: variable(-1.0)
+    w: variable(0.0)
+    E_L: -1.0
+    delta: 0.5
+    v_T: 0.0
+    tau: 1.0
+    J: 1.0
+    a: 0.2
+    tau_w: 5.0
+    b: 0.1
+    tau_s: 0.5
+    I_ext: input(0.0)
+    spike: input(0.0)
+    s_in: input(0.0)
+adex:
+  base: NodeTemplate
+  operators:
+    - adex_op
+"""
+
+
+@pytest.fixture
+def user_templates(tmp_path, monkeypatch):
+    (tmp_path / "mymodels").mkdir()
+    (tmp_path / "mymodels" / "custom.yaml").write_text(YAML)
+    monkeypatch.chdir(tmp_path)
+
+
+def _fhn_oracle(n, W, dt, p, train):
+    names = ["weights", "g", "a", "b", "tau_w", "beta", "I_ext"]
+
+    def f(t, y, weights, g, a, b, tau_w, beta, I_ext):
+        v, w = y[:n], y[n:]
+        r = 1.0 / (1.0 + torch.exp(-beta * v))
+        return torch.cat((v - v ** 3 / 3 - w + I_ext + g * (weights @ r), (v + a - b * w) / tau_w), 0)
+    args = [torch.cat((torch.full((n,), 0.1), torch.zeros(n))).double(), torch.tensor(W)]
+    args += [torch.as_tensor(np.atleast_1d(p[k]), dtype=torch.float64).clone() for k in names[1:-1]] + [torch.zeros(n, dtype=torch.float64)]
+    pm = {k: i for i, k in enumerate(names)}
+    pm["in"] = pm["I_ext"]
+    vm = {"v": (0, n), "w": (n, 2 * n), "out": (0, n)}
+    return orc.OracleRateNode(f, args, vm, pm, dt, torch.float64, train)
+
+
+def _adex_oracle(n, W, dt, p, train, thresh, reset):
+    names = ["weights", "E_L", "delta", "v_T", "tau", "J", "a", "tau_w", "b", "tau_s", "I_ext", "spike"]
+
+    def f(t, y, weights, E_L, delta, v_T, tau, J, a, tau_w, b, tau_s, I_ext, spike):
+        v, w, s = y[:n], y[n:2 * n], y[2 * n:]
+        dv = (E_L - v + delta * torch.exp((v - v_T) / delta) - w + I_ext) / tau + J * (weights @ s)
+        return torch.cat((dv, (a * (v - E_L) - w) / tau_w + b * spike, -s / tau_s + spike), 0)
+    args = [torch.cat((torch.full((n,), -1.0), torch.zeros(2 * n))).double(), torch.tensor(W)]
+    args += [torch.as_tensor(np.atleast_1d(p[k]), dtype=torch.float64).clone() for k in names[1:-2]]
+    args += [torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)]
+    pm = {k: i for i, k in enumerate(names)}
+    pm["in"], pm["spike_var"] = pm["I_ext"], pm["spike"]
+    vm = {"v": (0, n), "w": (n, 2 * n), "s": (2 * n, 3 * n), "out": (2 * n, 3 * n), "reset_var": (0, n)}
+    return orc.OracleSpikeResetNode(f, args, vm, pm, dt, torch.float64, train, spike_threshold=thresh, spike_reset=reset)
+
+
+@pytest.mark.parametrize("B", [1, 3, 20])
+def test_rate_field_compiled_at_run_time(user_templates, B):
+    import rectipy_b200 as rp
+    n, m, k, T, S, dt = 45, 2, 3, 150, 3, 0.05
+    rng = np.random.default_rng(7 + B)
+    W = rng.standard_normal((n, n)) / np.sqrt(n)
+    w_in, w_out = rng.standard_normal((n, m)) * 0.3, rng.standard_normal((k, n)) / np.sqrt(n)
+    p = dict(g=rng.uniform(0.4, 0.6, n), a=rng.uniform(0.5, 0.9, n), b=0.8, tau_w=12.5, beta=2.0)      # tau_w: shared scalar, a / g: per neuron
+    t = np.arange(T) * dt
+    x = 0.5 * np.sin(2 * np.pi * rng.uniform(0.05, 0.3, (1, B, m)) * t[:, None, None] + rng.uniform(0, 6.28, (1, B, m))) + 0.3
+    targets = rng.standard_normal((len(range(0, T, S)), B, k))
+
+    net = rp.Network(dt, device="cuda:0", batch=B)
+    node = net.add_diffeq_node("rnn", "mymodels.custom.fhn", weights=W, source_var="fhn_op/r", target_var="fhn_op/r_in",
+                               input_var="fhn_op/I_ext", output_var="fhn_op/v", node_vars={"fhn_op/a": p["a"], "fhn_op/g": p["g"]},
+                               train_params=["weights", "fhn_op/a", "fhn_op/tau_w", "fhn_op/g"])
+    assert node.spec.model == rp._cabi.RP_JIT and node.spec.jit_program.src_plane == -1
+    net.add_func_node("inp", m, "identity"); net.add_edge("inp", "rnn", weights=w_in, train="gd")
+    net.add_func_node("out", k, "identity"); net.add_edge("rnn", "out", weights=w_out, train="gd")
+    obs = net.run(x, sampling_steps=S, verbose=False, enable_grad=True, record_vars=[("rnn", "w", False)])
+    out = torch.stack(obs["out"]).reshape(-1, B, k)          # batch=1 networks have no trial axis
+    rec_w = obs.to_numpy(("rnn", "w")).reshape(out.shape[0], B, n)
+    loss = torch.nn.functional.mse_loss(out, torch.tensor(targets, dtype=torch.float32, device="cuda:0"))
+    loss.backward()
+
+    train = ["weights", "a", "tau_w", "g"]
+    g_ref, out_ref, w_ref = None, np.zeros(out.shape), np.zeros(rec_w.shape)
+    for b in range(B):
+        onode = _fhn_oracle(n, W, dt, p, train)
+        onet = orc.OracleNet(onode, w_in=torch.tensor(w_in, requires_grad=True), w_out=torch.tensor(w_out, requires_grad=True))
+        r = onet.run(torch.tensor(x[:, b, :]), sampling_steps=S, enable_grad=True, record_vars=[("w", False)])
+        pred = torch.stack(r["out"])
+        out_ref[:, b, :] = pred.detach().numpy()
+        w_ref[:, b, :] = torch.stack(r["vars"]["w"]).detach().numpy()
+        (torch.nn.functional.mse_loss(pred, torch.tensor(targets[:, b, :]), reduction="sum") / out.numel()).backward()
+        gs = [q.grad.numpy().copy() for q in onet.parameters()]
+        g_ref = gs if g_ref is None else [a + c for a, c in zip(g_ref, gs)]
+    g_eng = [node["weights"].grad, node["fhn_op/a"].grad, node["fhn_op/tau_w"].grad, node["fhn_op/g"].grad,
+             net.get_edge("inp", "rnn").weights.grad, net.get_edge("rnn", "out").weights.grad]
+    names = ["weights", "a", "tau_w", "g", "w_in", "w_out"]
+    errs = {nm: rel_err(ge.detach().cpu().numpy().reshape(gr.shape), gr) for nm, ge, gr in zip(names, g_eng, g_ref)}
+    errs["out"] = rel_err(out.detach().cpu().numpy(), out_ref)
+    errs["rec_w"] = rel_err(rec_w, w_ref)
+    print("jit fhn B=%d" % B, {k_: f"{v:.2e}" for k_, v in errs.items()})
+    assert all(v <= 1e-5 for v in errs.values()), errs
+
+
+@pytest.mark.parametrize("B,truncate", [(2, None), (5, 40)])
+def test_spiking_field_compiled_at_run_time(user_templates, B, truncate):
+    import rectipy_b200 as rp
+    n, m, k, T, S, dt = 40, 2, 2, 400, 4, 0.01
+    thresh, reset = 2.0, -1.5
+    rng = np.random.default_rng(11 + B)
+    W = rng.standard_normal((n, n)) * 1.5 / np.sqrt(n)
+    w_in, w_out = rng.standard_normal((n, m)), rng.standard_normal((k, n)) / np.sqrt(n)
+    p = dict(E_L=-1.0, delta=0.5, v_T=0.0, tau=rng.uniform(0.8, 1.2, n), J=1.0, a=0.2, tau_w=5.0, b=0.1, tau_s=0.5)
+    t = np.arange(T) * dt
+    x = 1.0 * np.sin(2 * np.pi * rng.uniform(0.3, 2, (1, B, m)) * t[:, None, None] + rng.uniform(0, 6.28, (1, B, m))) + 1.2
+    targets = rng.standard_normal((len(range(0, T, S)), B, k))
+
+    net = rp.Network(dt, device="cuda:0", batch=B)
+    node = net.add_diffeq_node("rnn", "mymodels.custom.adex", weights=W, source_var="s", target_var="s_in", input_var="I_ext",
+                               output_var="s", spike_var="spike", reset_var="v", node_vars={"adex_op/tau": p["tau"]},
+                               train_params=["weights", "adex_op/b", "adex_op/tau"], spike_threshold=thresh, spike_reset=reset)
+    assert node.spec.model == rp._cabi.RP_JIT and node.spec.jit_program.spiking
+    net.add_func_node("inp", m, "identity"); net.add_edge("inp", "rnn", weights=w_in, train="gd")
+    net.add_func_node("out", k, "identity"); net.add_edge("rnn", "out", weights=w_out, train="gd")
+    kw = {} if truncate is None else dict(truncate_steps=truncate)
+    obs = net.run(x, sampling_steps=S, verbose=False, enable_grad=True, record_vars=[("rnn", "v", False)], **kw)
+    out = torch.stack(obs["out"]).reshape(-1, B, k)
+    rec_v = obs.to_numpy(("rnn", "v")).reshape(out.shape[0], B, n)
+    torch.nn.functional.mse_loss(out, torch.tensor(targets, dtype=torch.float32, device="cuda:0")).backward()
+
+    train = ["weights", "b", "tau"]
+    g_ref, out_ref, v_ref = None, np.zeros(out.shape), np.zeros(rec_v.shape)
+    for b in range(B):
+        onode = _adex_oracle(n, W, dt, p, train, thresh, reset)
+        onet = orc.OracleNet(onode, w_in=torch.tensor(w_in, requires_grad=True), w_out=torch.tensor(w_out, requires_grad=True))
+        r = onet.run(torch.tensor(x[:, b, :]), sampling_steps=S, enable_grad=True, record_vars=[("v", False)], truncate_steps=truncate)
+        pred = torch.stack(r["out"])
+        out_ref[:, b, :] = pred.detach().numpy()
+        v_ref[:, b, :] = torch.stack(r["vars"]["v"]).detach().numpy()
+        (torch.nn.functional.mse_loss(pred, torch.tensor(targets[:, b, :]), reduction="sum") / out.numel()).backward()
+        gs = [q.grad.numpy().copy() for q in onet.parameters()]
+        g_ref = gs if g_ref is None else [a + c for a, c in zip(g_ref, gs)]
+    # the recorded v of a SpikeResetNet is the pre-update value: v >= theta marks a spike at that record step
+    assert np.array_equal(rec_v >= thresh, v_ref >= thresh) and (v_ref >= thresh).sum() > 0
+    g_eng = [node["weights"].grad, node["adex_op/b"].grad, node["adex_op/tau"].grad,
+             net.get_edge("inp", "rnn").weights.grad, net.get_edge("rnn", "out").weights.grad]
+    names = ["weights", "b", "tau", "w_in", "w_out"]
+    errs = {nm: rel_err(ge.detach().cpu().numpy().reshape(gr.shape), gr) for nm, ge, gr in zip(names, g_eng, g_ref)}
+    e_out = rel_err(out.detach().cpu().numpy(), out_ref)
+    print("jit adex B=%d" % B, f"out {e_out:.2e}", {k_: f"{v:.2e}" for k_, v in errs.items()})
+    assert e_out <= 1e-4
+    assert all(v <= 2e-3 for v in errs.values()), errs
+
+
+def test_jit_rejects_what_it_cannot_express(user_templates):
+    import rectipy_b200 as rp
+    net = rp.Network(1e-3, device="cuda:0")
+    with pytest.raises(NotImplementedError):          # output must be a state variable
+        net.add_diffeq_node("a", "mymodels.custom.fhn", weights=np.zeros((4, 4)), source_var="r", target_var="r_in",
+                            input_var="I_ext", output_var="r")
+    with pytest.raises(NotImplementedError):          # tensor-core precisions are for the compiled fields
+        net2 = rp.Network(1e-3, device="cuda:0", batch=128, precision="3xf16")
+        net2.add_diffeq_node("a", "mymodels.custom.fhn", weights=np.zeros((128, 128)), source_var="r", target_var="r_in",
+                             input_var="I_ext", output_var="v")
+        net2.run(np.zeros((3, 128, 128)), verbose=False)

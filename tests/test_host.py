@@ -53,8 +53,8 @@ def test_user_yaml_template(tmp_path, monkeypatch):
     assert spec.name == "qif_sfa" and spec.ops == ("my_sfa_op",)
     assert spec.params["my_sfa_op/tau"][1] == 2.0 and spec.params["my_sfa_op/alpha"][1] == 0.25
     assert dict(spec.state_vars)["my_sfa_op/v"] == -1.0
-    with pytest.raises(NotImplementedError):
-        templates.resolve_template("mymodels.custom.weird")
+    weird = templates.resolve_template("mymodels.custom.weird")      # no compiled field: handed to the run-time code generator
+    assert weird.model == abi.RP_JIT and weird.jit_field is not None and weird.jit_program is None
 
 
 def test_user_yaml_equivalent_equations_match_symbolically(tmp_path, monkeypatch):
@@ -73,8 +73,8 @@ def test_user_yaml_equivalent_equations_match_symbolically(tmp_path, monkeypatch
     spec = templates.resolve_template("mymodels.rewritten.q_neuron")
     assert spec.name == "qif" and spec.model == abi.RP_QIF and spec.ops == ("q_op",)
     assert spec.params["q_op/tau"][1] == 1.5 and dict(spec.state_vars)["q_op/v"] == -3.0
-    with pytest.raises(NotImplementedError):
-        templates.resolve_template("mymodels.rewritten.cubic_neuron")
+    cubic = templates.resolve_template("mymodels.rewritten.cubic_neuron")
+    assert cubic.model == abi.RP_JIT and [k for k, _ in cubic.state_vars] == ["cubic_op/v", "cubic_op/s"]
     # names that sympy would read as constants / functions stay plain symbols
     assert templates._same_equation("v'=(E_r-v)*g*s_in/C", "v'=g*s_in*(E_r-v)/C")
     assert not templates._same_equation("v'=(E_r-v)*g*s_in/C", "v'=g*s_in*(E_r+v)/C")
