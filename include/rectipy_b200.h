@@ -76,7 +76,9 @@ typedef struct rp_desc {
                                             2 [B] per trial, 3 [B][n] per trial and neuron (parameter sweeps; no gradients) */
     /* RP_JIT only: */
     int jit_nsv;            /* state variables (1..RP_MAX_SV); plane 0 is the reset variable of a spiking field */
-    int jit_spiking;        /* 1: threshold / reset on plane 0 with the surrogate gradient (SpikeResetNet), 0: RateNet */
+    int jit_spiking;        /* number of spike variables: planes 0..jit_spiking-1 are thresholded / reset with the surrogate gradient
+                               (1: SpikeResetNet, several: MultiSpikeResetNet), 0: RateNet */
+    int jit_post_out;       /* 1: outputs are POST-update slices (MultiSpikeResetNet.forward, rectipy/nodes.py:451-465) */
     int jit_src_plane;      /* plane projected by the recurrent weights, or -1: the source is an expression of the state */
 } rp_desc;
 

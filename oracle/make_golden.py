@@ -212,6 +212,56 @@ def save_feedback_net(ref):
     np.savez_compressed(os.path.join(OUT, "feedback_net.npz"), **blob)
 
 
+def save_multispike(ref):
+    """G12: the reference's MultiSpikeResetNet (rectipy/nodes.py:404-465) around a two-population QIF field with two spike /
+    reset variable pairs, inside a reference Network (inp -> Linear -> node -> Linear -> out), BPTT.  Outputs are post-update."""
+    rng = np.random.default_rng(1212)
+    n, m, k, T, dt, S = 16, 2, 2, 1200, 1e-3, 3
+    W = rng.standard_normal((n, n)) * 2.0 / np.sqrt(n)
+    params = dict(eta_e=orc.lorentzian_etas(n) + 8.0, eta_i=rng.uniform(-2.0, 6.0, n), tau_e=1.0, J_ee=1.3, J_ei=2.0, tau_i=0.5, J_ie=3.0, tau_s=0.8)
+    w_in, w_out = rng.standard_normal((n, m)), rng.standard_normal((k, n)) / np.sqrt(n)
+    inputs = sin_inputs(rng, T, m, dt, amp=10.0, offset=12.0)
+    targets = rng.standard_normal((len(range(0, T, S)), k))
+    train = ["weights", "eta_e", "J_ei", "tau_i"]
+    blob = dict(in_W=W, in_w_in=w_in, in_w_out=w_out, in_inputs=inputs, in_targets=targets, param_eta_e=params["eta_e"], param_eta_i=params["eta_i"],
+                meta=np.asarray(repr(dict(n=n, m=m, k=k, T=T, dt=dt, S=S, thresh=100.0, reset=-100.0, train=train,
+                                          **{q: v for q, v in params.items() if np.ndim(v) == 0}))))
+    for dn in ("float64", "float32"):
+        dtype = TD[dn]
+        func, args, var_map, param_map = orc.build_ei_node_args(n, W, params, dtype)
+        node = ref.nodes.MultiSpikeResetNet(func, args, var_map, param_map, dt=dt, dtype=dtype, train_params=train, device="cpu",
+                                            spike_threshold=100.0, spike_reset=-100.0)
+        net = ref.Network(dt, device="cpu", dtype=dtype)
+        net.add_node("rnn", node, node_type="diff_eq")
+        net.add_func_node("inp", m, "identity"); net.add_func_node("out", k, "identity")
+        net.add_edge("inp", "rnn", weights=w_in, train="gd")
+        net.add_edge("rnn", "out", weights=w_out, train="gd")
+        obs = net.run(torch.tensor(inputs, dtype=dtype), sampling_steps=S, verbose=False, enable_grad=True,
+                      record_vars=[("rnn", "v_e", False), ("rnn", "v_i", False)])
+        out = torch.stack(obs["out"])
+        loss = torch.nn.MSELoss()(out, torch.tensor(targets, dtype=dtype))
+        loss.backward()
+        res = dict(out=out.detach().numpy(), steps=np.asarray(obs["steps"]), var_v_e=obs.to_numpy(("rnn", "v_e")), var_v_i=obs.to_numpy(("rnn", "v_i")),
+                   y_final=node.y.detach().numpy(), loss=loss.detach().numpy(),
+                   grad_w_in=net.get_edge("inp", "rnn").weights.grad.numpy(), grad_w_out=net.get_edge("rnn", "out").weights.grad.numpy())
+        for name in train:
+            res[f"grad_{name}"] = node[name].grad.detach().numpy()
+        # the restatement against the class it restates
+        onode = orc.OracleMultiSpikeResetNode(*orc.build_ei_node_args(n, W, params, dtype), dt, dtype, train, spike_threshold=100.0, spike_reset=-100.0)
+        onet = orc.OracleNet(onode, w_in=torch.tensor(w_in, dtype=dtype, requires_grad=True), w_out=torch.tensor(w_out, dtype=dtype, requires_grad=True))
+        r = onet.run(torch.tensor(inputs, dtype=dtype), sampling_steps=S, enable_grad=True)
+        o_out = torch.stack(r["out"])
+        torch.nn.MSELoss()(o_out, torch.tensor(targets, dtype=dtype)).backward()
+        tol = 1e-12 if dn == "float64" else 1e-5
+        assert np.max(np.abs(o_out.detach().numpy() - res["out"])) <= tol * max(1.0, np.abs(res["out"]).max()), "oracle restatement deviates (outputs)"
+        assert np.max(np.abs(onode.get("weights").grad.numpy() - res["grad_weights"])) <= tol * np.abs(res["grad_weights"]).max(), "oracle restatement deviates (dW)"
+        for kk, v in res.items():
+            blob[f"{dn}_{kk}"] = v
+    np.savez_compressed(os.path.join(OUT, "multispike_ei.npz"), **blob)
+    n_spk = int((blob["float64_var_v_e"] == -100.0).sum() + (blob["float64_var_v_i"] == -100.0).sum())
+    print("multispike_ei: out", blob["float64_out"].shape, "resets seen at record steps:", n_spk)
+
+
 def save_edges_square(ref):
     """Square, non-symmetric edge weights: the reference transposes whenever shape == (n_in, n_out), which is always
     true for an N x N matrix (edges.py:22-23,160-161) -- a user's W therefore acts as W.T.  Outputs of the unmodified classes."""
@@ -365,6 +415,8 @@ def main(only=None):
         save_feedback_net(ref)
     if only in (None, "edges_square"):
         save_edges_square(ref)
+    if only in (None, "multispike_ei"):
+        save_multispike(ref)
     rng = rng_main
 
     # ---- G7: output activation + masked input edge (LinearMasked, edges.py:150-174) ---------------

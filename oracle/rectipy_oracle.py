@@ -344,6 +344,87 @@ class OracleSpikeResetNode(OracleRateNode):
         return torch.cat((self.y_a, self.y_v, self.y_b), 0)
 
 
+class OracleMultiSpikeResetNode(OracleRateNode):
+    """MultiSpikeResetNet (nodes.py:404-465): several (spike variable, reset variable) pairs `spike_var_i` / `spike_reset_i`,
+    one shared threshold and reset value.  Differences from SpikeResetNet that the restatement keeps: the spikes of a step are
+    taken from the buffers `_y_reset[i]`, which start as ZEROS (nodes.py:430-436) and afterwards alias the reset slices of the
+    post-update state; `forward` returns the POST-update output slice and `y` is the post-update state (nodes.py:457-465)."""
+
+    spiking = True
+
+    def __init__(self, func, args, var_map, param_map, dt, dtype=torch.float64, train_params=None,
+                 spike_threshold=1e2, spike_reset=-1e2, spike_slope=None, spike_center=1.0):
+        super().__init__(func, args, var_map, param_map, dt, dtype, train_params)
+        if spike_slope is None:
+            spike_slope = 100.0 / abs(spike_threshold - spike_reset)       # nodes.py:417-418
+        self.slope = torch.tensor(spike_slope, dtype=dtype)
+        self.center = torch.tensor(spike_center, dtype=dtype)
+        n_spk = 1
+        while f"spike_var_{n_spk}" in param_map:                           # nodes.py:422-425
+            n_spk += 1
+        self.spike_idx = [param_map[f"spike_var_{i}"] for i in range(n_spk)]
+        self.slices = [var_map[f"spike_reset_{i}"] for i in range(n_spk)]
+        self.v_reset = torch.tensor(spike_reset, dtype=dtype)
+        self.thresh = torch.tensor(spike_threshold, dtype=dtype)
+        self.y_reset = [torch.zeros(b - a, dtype=dtype) for a, b in self.slices]
+
+    def forward(self, x):                                                  # nodes.py:451-465
+        fired = []
+        for idx, buf in zip(self.spike_idx, self.y_reset):
+            spikes = OracleSpike.apply(buf - self.thresh, self.slope, self.center)
+            fired.append(spikes.detach() > 0.0)
+            self.args[idx] = spikes / self.dt
+        self.args[self.inp] = x
+        y_new = self.y + self.dt * self.func(0, self.y, *self.args)
+        pieces, pos = [], 0
+        for i, ((a, b), hit) in enumerate(zip(self.slices, fired)):        # masked assignment of the reset value = no gradient there
+            pieces.append(y_new[pos:a])
+            self.y_reset[i] = torch.where(hit, self.v_reset, y_new[a:b])
+            pieces.append(self.y_reset[i])
+            pos = b
+        pieces.append(y_new[pos:])
+        self.y = torch.cat(pieces, 0)
+        return self.y[self.start:self.stop]
+
+
+def field_ei_qif(n: int) -> Tuple[Callable, List[str]]:
+    """Two coupled QIF populations in one node, each with its own spike variable (a MultiSpikeResetNet use case; not a shipped
+    template -- the engine side is tests/test_gpu_jit.py::EI_YAML):
+        v_e' = (v_e^2 + eta_e + I_ext)/tau_e + J_ee*s_in - J_ei*s_i ;  s_e' = -s_e/tau_s + spike_e
+        v_i' = (v_i^2 + eta_i)/tau_i + J_ie*s_e                     ;  s_i' = -s_i/tau_s + spike_i      (s_in = weights @ s_e)"""
+    names = ["weights", "eta_e", "tau_e", "J_ee", "J_ei", "eta_i", "tau_i", "J_ie", "tau_s", "I_ext", "spike_e", "spike_i"]
+
+    def f(t, y, weights, eta_e, tau_e, J_ee, J_ei, eta_i, tau_i, J_ie, tau_s, I_ext, spike_e, spike_i):
+        v_e, s_e, v_i, s_i = y[:n], y[n:2 * n], y[2 * n:3 * n], y[3 * n:]
+        dv_e = (v_e * v_e + eta_e + I_ext) / tau_e + J_ee * (weights @ s_e) - J_ei * s_i
+        dv_i = (v_i * v_i + eta_i) / tau_i + J_ie * s_e
+        return torch.cat((dv_e, -s_e / tau_s + spike_e, dv_i, -s_i / tau_s + spike_i), 0)
+    return f, names
+
+
+EI_DEFAULTS = dict(eta_e=-5.0, tau_e=1.0, J_ee=1.0, J_ei=2.0, eta_i=-5.0, tau_i=0.5, J_ie=3.0, tau_s=0.8)
+
+
+def build_ei_node_args(n: int, weights, params=None, dtype=torch.float64, y0=None):
+    """(func, args, var_map, param_map) of the two-population node with the MultiSpikeResetNet index maps (nodes.py:438-449)."""
+    func, names = field_ei_qif(n)
+    p = dict(EI_DEFAULTS)
+    p.update(params or {})
+    if y0 is None:
+        y0 = torch.cat([torch.full((n,), v, dtype=dtype) for v in (-2.0, 0.0, -2.0, 0.0)])
+    args = [torch.as_tensor(y0, dtype=dtype).clone(), torch.as_tensor(weights, dtype=dtype).clone()]
+    for name in names[1:]:
+        if name in ("I_ext", "spike_e", "spike_i"):
+            args.append(torch.zeros(n, dtype=dtype))
+        else:
+            args.append(torch.as_tensor(np.atleast_1d(p[name]), dtype=dtype).clone())
+    param_map = {name: i for i, name in enumerate(names)}
+    param_map.update({"in": param_map["I_ext"], "spike_var_0": param_map["spike_e"], "spike_var_1": param_map["spike_i"]})
+    var_map = {"v_e": (0, n), "s_e": (n, 2 * n), "v_i": (2 * n, 3 * n), "s_i": (3 * n, 4 * n)}
+    var_map.update({"out": var_map["s_e"], "spike_reset_0": var_map["v_e"], "spike_reset_1": var_map["v_i"]})
+    return func, args, var_map, param_map
+
+
 def make_node(model: str, n: int, weights, dt: float, params=None, dtype=torch.float64, train_params=None,
               input_var="I_ext", output_var=None, y0=None, **spike_kwargs):
     func, args, var_map, param_map = build_node_args(model, n, weights, params, dtype, input_var, output_var, y0)

@@ -29,7 +29,7 @@ class rp_desc(C.Structure):
                 ("in_target", C.c_int), ("out_mode", C.c_int), ("n_out", C.c_int), ("out_var", C.c_int),
                 ("precision", C.c_int), ("dt", C.c_float), ("theta", C.c_float), ("v_reset", C.c_float),
                 ("slope", C.c_float), ("param_per_neuron", C.c_int * RP_NUM_PARAMS),
-                ("jit_nsv", C.c_int), ("jit_spiking", C.c_int), ("jit_src_plane", C.c_int)]
+                ("jit_nsv", C.c_int), ("jit_spiking", C.c_int), ("jit_post_out", C.c_int), ("jit_src_plane", C.c_int)]
 
 
 class rp_fwd_args(C.Structure):

@@ -453,6 +453,7 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
     if (nsv < 0 || (d->model == RP_JIT && (nsv < 1 || nsv > RP_MAX_SV))) return fail("rp_plan_create: unknown model %d / bad state-variable count", d->model);
     if (d->model == RP_JIT) {
         if (d->precision != RP_PREC_FP32) return fail("rp_plan_create: run-time compiled fields run on the per-step fp32 path (precision must be RP_PREC_FP32)");
+        if (d->jit_spiking < 0 || d->jit_spiking > nsv) return fail("rp_plan_create: RP_JIT with %d spike variables but %d state variables", d->jit_spiking, nsv);
         if (d->jit_src_plane >= nsv || d->out_var >= 3 || d->out_var >= nsv) return fail("rp_plan_create: RP_JIT source / output plane out of range (output planes 0..2)");
     }
     if (d->n <= 0 || d->batch <= 0) return fail("rp_plan_create: n and batch must be positive");
@@ -770,7 +771,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         if (w.j >= 0 && (want_rec || (want_out && (w.close || w.len > 1)))) {
             rp::ObsArgs oa;
             oa.N = N; oa.B = B; oa.k = d.n_out; oa.out_mode = d.out_mode; oa.out_var = d.out_var; oa.model = d.model;
-            oa.y_pre = cur; oa.y_post = nxt; oa.W_out = a->W_out; oa.mp = mp; oa.win_acc = p->win_acc;
+            oa.y_pre = (jit && d.jit_post_out) ? nxt : cur; oa.y_post = nxt; oa.W_out = a->W_out; oa.mp = mp; oa.win_acc = p->win_acc;
             oa.win_first = w.first; oa.win_close = w.close; oa.inv_len = 1.0f / (float)w.len;
             oa.out_rec_j = want_out ? a->out_rec + (size_t)w.j * out_stride : nullptr;
             oa.skip_out = want_out ? 0 : 1;
@@ -780,7 +781,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
                 oa.rec_reduce[r] = r < a->n_rec_vars ? a->rec_reduce[r] : 0;
                 oa.rec_buf_j[r] = r < a->n_rec_vars ? a->rec_buf[r] + (size_t)w.j * (a->rec_reduce[r] ? (size_t)B : plane) : nullptr;
             }
-            oa.rec_post = spk ? 0 : 1;     // RateNet: y is post-update (nodes.py:169); SpikeResetNet: pre-update (nodes.py:387)
+            oa.rec_post = (spk && !(jit && d.jit_post_out)) ? 0 : 1;     // RateNet, MultiSpikeResetNet: y is post-update (nodes.py:169,464); SpikeResetNet: pre-update (nodes.py:387)
             stage_mark(p, ST_OTHER, st);
             if (jit) rp::k_observe<RP_QIF><<<B, 256, 0, st>>>(oa);       // state planes only: any instantiation without an activation will do
             else RP_DISPATCH_MODEL(d.model, (rp::k_observe<M_><<<B, 256, 0, st>>>(oa)));
@@ -1023,6 +1024,14 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
             aa.e_scale = w.j >= 0 ? 1.0f / (float)w.len : 0.f;
             aa.g_x_t = a->g_x ? a->g_x + (size_t)t * plane : nullptr;
             aa.zero_after_post = (truncating && (a->t_offset + t) > 0 && (a->t_offset + t) % tr == 0) ? 1 : 0;
+        }
+        if (jit) {
+            aa.y_t = a->history + (size_t)t * hslot;
+            aa.e_tm1 = nullptr; aa.e_scale_tm1 = 0.f;
+            if (t > 0 && a->g_out_rec) {
+                const Window w1 = window_of(a->t_offset + t - 1, T_tot, a->sampling_steps, a->cutoff);
+                if (w1.j >= 0) { aa.e_tm1 = a->g_out_rec + (size_t)w1.j * out_stride; aa.e_scale_tm1 = 1.0f / (float)w1.len; }
+            }
         }
         if (aa.do_pre) {
             aa.y_tm1 = a->history + (size_t)(t - 1) * hslot;

@@ -88,6 +88,10 @@ struct AdjArgs {
     float* g_x_t;          // dense input gradient of step t [B][N] or nullptr
     int any_param_grad;
     int per_trial;         // 1: some parameter differs between trials (no per-neuron hoisting)
+    // run-time compiled MultiSpikeResetNet fields (outputs are POST-update slices, rectipy/nodes.py:451-465): dL/d out_rec of the record
+    // window that contains step t-1, added to the adjoint of y_t in the launch that finishes step t; y_t is set on every launch
+    const float* e_tm1;
+    float e_scale_tm1;
 };
 
 

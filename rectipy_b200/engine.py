@@ -59,6 +59,7 @@ class PlanKey:
     jit_key: str = ""        # RP_JIT: key of the compiled program (rectipy_b200.jit) and what rp_desc.jit_* carry
     jit_nsv: int = 0
     jit_spiking: int = 0
+    jit_post_out: int = 0
     jit_src_plane: int = 0
 
 
@@ -78,7 +79,7 @@ class Plan:
         d.dt, d.theta, d.v_reset, d.slope = key.dt, key.theta, key.v_reset, key.slope
         for i, v in enumerate(key.per_neuron):
             d.param_per_neuron[i] = v
-        d.jit_nsv, d.jit_spiking, d.jit_src_plane = key.jit_nsv, key.jit_spiking, key.jit_src_plane
+        d.jit_nsv, d.jit_spiking, d.jit_post_out, d.jit_src_plane = key.jit_nsv, key.jit_spiking, key.jit_post_out, key.jit_src_plane
         handle = C.c_void_p()
         with torch.cuda.device(key.device):
             abi.check(self.lib.rp_plan_create(C.byref(d), C.byref(handle)), "rp_plan_create")

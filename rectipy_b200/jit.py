@@ -11,9 +11,10 @@ the templates the reference ships; an operator whose equations match none of the
     of k_fwd_step<MODEL> / k_adj_step<MODEL>.  The contractions (W.src, W^T.g, g (x) src), the Observer, the checkpoints and the
     autograd plumbing are the engine's own.
 
-Semantics are those of the reference's node classes (rectipy/nodes.py:166-170,382-392,468-481): explicit Euler; for spiking nodes
-spike = heaviside(v - theta) with the surrogate gradient, the spike enters the field as spike/dt, the reset variable is blended with
-the detached spike; outputs are pre-update slices.  Restrictions (checked, NotImplementedError otherwise): first-order explicit
+Semantics are those of the reference's node classes (rectipy/nodes.py:166-170,382-392,451-465,468-481): explicit Euler; for spiking
+nodes spike = heaviside(v - theta) with the surrogate gradient, the spike enters the field as spike/dt, the reset variable is blended
+with the detached spike; outputs are pre-update slices -- except MultiSpikeResetNet (several spike / reset variable pairs), whose
+outputs and recorded variables are post-update.  Restrictions (checked, NotImplementedError otherwise): first-order explicit
 equations, at most RP_MAX_SV state variables, df/du must not depend on u, I or the spike; no mean-field `mean(.)` terms.
 """
 from __future__ import annotations
@@ -22,7 +23,7 @@ import hashlib
 import os
 import re
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 from . import _cabi as abi
 
@@ -49,10 +50,11 @@ class JitProgram:
     image: bytes
     key: str
     nsv: int
-    spiking: bool
+    spiking: int                            # number of spike variables (planes 0..spiking-1 are thresholded and reset)
     src_plane: int
     planes: Dict[str, int]                  # state variable -> engine plane
     param_slots: Dict[str, int]             # parameter -> ABI slot
+    post_out: bool = False                  # MultiSpikeResetNet: outputs / recorded variables are post-update
 
 
 _PROGRAMS: Dict[str, JitProgram] = {}
@@ -129,29 +131,36 @@ def unbound_spec(ops):
 
 
 def bind_spec(spec, source_var, target_var, input_var, spike_var, reset_var):
-    """Fix the roles of the template's variables (what `from_pyrates` receives, rectipy/nodes.py:112-164,363-380), generate and
-    compile the kernels, and return the complete TemplateSpec (with `jit_program`)."""
+    """Fix the roles of the template's variables (what `from_pyrates` receives, rectipy/nodes.py:112-164,363-380,438-449), generate
+    and compile the kernels, and return the complete TemplateSpec (with `jit_program`).  `spike_var` / `reset_var` given as lists
+    select the MultiSpikeResetNet semantics (several spike variables, post-update outputs)."""
     from .templates import TemplateSpec
     fld: JitField = spec.jit_field
     short = lambda n: None if n is None else [q for q in str(n).split("/") if q][-1]
     key = lambda n: f"{fld.owner.get(n, fld.ops[0])}/{n}"
-    src, tgt, inp, spk, rst = short(source_var), short(target_var), short(input_var), short(spike_var), short(reset_var)
+    multi = isinstance(spike_var, (list, tuple))
+    spks = [short(v) for v in spike_var] if multi else ([short(spike_var)] if spike_var is not None else [])
+    rsts = [short(v) for v in reset_var] if isinstance(reset_var, (list, tuple)) else ([short(reset_var)] if spks else [])
+    if len(spks) != len(rsts):
+        raise ValueError("`spike_var` and `reset_var` must name the same number of variables")
+    src, tgt, inp = short(source_var), short(target_var), short(input_var)
     if src is None:
         src = fld.states[0]
     if src not in fld.states and src not in fld.algebraic:
         raise KeyError(f"Variable {source_var} was not found on the node template.")
-    for n, what in ((tgt, target_var), (inp, input_var), (spk, spike_var)):
+    for n in [tgt, inp] + spks:
         if n is not None and n not in fld.inputs:
-            raise KeyError(f"Variable {what} was not found among the template's input variables.")
-    if spk is not None and rst not in fld.states:
-        raise KeyError(f"Variable {reset_var} was not found on the node template.")
-    prog = build_program(fld, src, tgt, inp, spk, rst)
+            raise KeyError(f"Variable {n} was not found among the template's input variables.")
+    for r in rsts:
+        if r not in fld.states:
+            raise KeyError(f"Variable {r} was not found on the node template.")
+    prog = build_program(fld, src, tgt, inp, spks, rsts, post_out=multi)
     params = {key(p): (slot, fld.defaults[p]) for p, slot in prog.param_slots.items()}
     params[ONE_KEY] = (abi.RP_P_K, 1.0)
     planes = {key(s): pl for s, pl in prog.planes.items()}
     return TemplateSpec(name="jit:" + prog.key[:10], model=abi.RP_JIT, ops=fld.ops, state_vars=list(spec.state_vars), params=params,
                         source_var=key(src), target_var=key(tgt) if tgt else "", input_vars={key(inp): 0} if inp else {},
-                        spike_var=key(spk) if spk else None, out_vars={k: pl for k, pl in planes.items() if pl < 3}, planes=planes,
+                        spike_var=key(spks[0]) if spks else None, out_vars={k: pl for k, pl in planes.items() if pl < 3}, planes=planes,
                         jit_field=fld, jit_program=prog)
 
 
@@ -173,22 +182,25 @@ def _ccode(expr) -> str:
     return sympy.ccode(expr, type_aliases={real: float32})
 
 
-def build_program(fld: JitField, source_var: str, target_var: str, input_var: Optional[str], spike_var: Optional[str],
-                  reset_var: Optional[str]) -> JitProgram:
-    """Generate, compile (NVRTC, sm_100a) and cache the kernels of one node configuration."""
+def build_program(fld: JitField, source_var: str, target_var: Optional[str], input_var: Optional[str],
+                  spike_vars: Sequence[str] = (), reset_vars: Sequence[str] = (), post_out: bool = False) -> JitProgram:
+    """Generate, compile (NVRTC, sm_100a) and cache the kernels of one node configuration.  `spike_vars[j]` is the input variable that
+    receives spike_j / dt, `reset_vars[j]` the state variable it thresholds and resets (plane j); `post_out`: MultiSpikeResetNet."""
     import sympy
-    spiking = spike_var is not None
-    states = list(fld.states)
-    if spiking:
-        if reset_var not in states:
-            raise KeyError(reset_var)
-        states.remove(reset_var)
-        states.insert(0, reset_var)                      # the engine thresholds / resets plane 0
+    spike_vars, reset_vars = list(spike_vars), list(reset_vars)
+    nspk = len(spike_vars)
+    if len(reset_vars) != nspk or len(set(reset_vars)) != nspk:
+        raise ValueError("every spike variable needs its own reset variable")
+    states = [s for s in reset_vars] + [s for s in fld.states if s not in reset_vars]       # the engine thresholds / resets planes 0..nspk-1
+    for r in reset_vars:
+        if r not in fld.states:
+            raise KeyError(r)
     planes = {s: i for i, s in enumerate(states)}
     nsv = len(states)
     slots = param_slot_table(fld.params)
     # symbols -> C identifiers
-    U, I, SPK = _sym("rp_u"), _sym("rp_I"), _sym("rp_spk")
+    U, I = _sym("rp_u"), _sym("rp_I")
+    SPK = [_sym(f"spk{j}") for j in range(nspk)]
     sub = {_sym(s): _sym(f"y{planes[s]}") for s in states}
     sub.update({_sym(p): _sym(f"p{slots[p]}") for p in fld.params})
     if target_var is not None:
@@ -200,8 +212,8 @@ def build_program(fld: JitField, source_var: str, target_var: str, input_var: Op
             continue
         if input_var is not None and n == input_var:
             sub[_sym(n)] = I
-        elif spiking and n == spike_var:
-            sub[_sym(n)] = SPK
+        elif n in spike_vars:
+            sub[_sym(n)] = SPK[spike_vars.index(n)]
         else:
             sub[_sym(n)] = sympy.Float(fld.defaults.get(n, 0.0))     # an input nobody drives keeps its default
     f = [fld.rhs[s].subs(sub) for s in states]              # not simplified: keep the user's evaluation order
@@ -215,9 +227,9 @@ def build_program(fld: JitField, source_var: str, target_var: str, input_var: Op
     J = [[sympy.diff(f[k], ys[l]) for l in range(nsv)] for k in range(nsv)]
     Ju = [sympy.diff(f[k], U) for k in range(nsv)]
     JI = [sympy.diff(f[k], I) for k in range(nsv)]
-    Js = [sympy.diff(f[k], SPK) for k in range(nsv)]
+    Js = [[sympy.diff(f[k], SPK[j]) for j in range(nspk)] for k in range(nsv)]
     for e in Ju:
-        if e.free_symbols & {U, I, SPK}:
+        if e.free_symbols & ({U, I} | set(SPK)):
             raise NotImplementedError("rectipy_b200.jit: d f / d (coupling input) must not depend on the coupling input, the external input or the spike")
     plist = [(n, slots[n]) for n in fld.params]
     Jp = [[sympy.diff(f[k], _sym(f"p{q}")) for (_, q) in plist] for k in range(nsv)]
@@ -231,16 +243,16 @@ def build_program(fld: JitField, source_var: str, target_var: str, input_var: Op
 
     load_y = "\n".join(f"    const float y{k} = y[{k}];" for k in range(nsv))
     load_p = "\n".join(f"    const float p{q} = rp::ldp(mp, {q}, i, b);" for (_, q) in plist)
-    npar = max(1, len(plist))
-    src_code = _ccode(src)
-    source = _TEMPLATE.format(NSV=nsv, NPAR=npar, NPAR_REAL=len(plist), SPIKING=int(spiking), SRC_PLANE=src_plane, LOAD_Y=load_y, LOAD_P=load_p,
-                              F=lines("f", f), J=lines2("J", J), JU=lines("Ju", Ju), JI=lines("JI", JI), JS=lines("Js", Js),
-                              JP=lines2("Jp", Jp) if plist else "", DSRC=lines("dsrc", dsrc), SRC=src_code,
+    load_s = "\n".join(f"    const float spk{j} = spk[{j}];" for j in range(nspk))
+    source = _TEMPLATE.format(NSV=nsv, NPAR=max(1, len(plist)), NPAR_REAL=len(plist), NSPK=nspk, NSPK1=max(1, nspk), POST_OUT=int(post_out),
+                              LOAD_Y=load_y, LOAD_P=load_p, LOAD_S=load_s,
+                              F=lines("f", f), J=lines2("J", J), JU=lines("Ju", Ju), JI=lines("JI", JI), JS=lines2("Js", Js) if nspk else "",
+                              JP=lines2("Jp", Jp) if plist else "", DSRC=lines("dsrc", dsrc), SRC=_ccode(src),
                               PSLOTS=", ".join(str(q) for (_, q) in plist) if plist else "0")
     key = hashlib.sha1(source.encode()).hexdigest()
     if key not in _PROGRAMS:
-        _PROGRAMS[key] = JitProgram(source=source, image=compile_cuda(source), key=key, nsv=nsv, spiking=spiking, src_plane=src_plane,
-                                    planes=planes, param_slots=slots)
+        _PROGRAMS[key] = JitProgram(source=source, image=compile_cuda(source), key=key, nsv=nsv, spiking=nspk, src_plane=src_plane,
+                                    planes=planes, param_slots=slots, post_out=bool(post_out))
     return _PROGRAMS[key]
 
 
@@ -277,14 +289,16 @@ _TEMPLATE = r'''// generated by rectipy_b200/jit.py from a user template -- forw
 #define NSV {NSV}
 #define NPAR {NPAR}
 #define NPAR_REAL {NPAR_REAL}
-#define SPIKING {SPIKING}
-#define SRC_PLANE {SRC_PLANE}
+#define NSPK {NSPK}          // spike variables: planes 0..NSPK-1 are thresholded and reset
+#define NSPK1 {NSPK1}
+#define POST_OUT {POST_OUT}  // 1: MultiSpikeResetNet (outputs are post-update slices)
 __device__ const int PSLOT[NPAR] = {{ {PSLOTS} }};
 
-// right-hand side f_k(y, u, I, spike argument)
-__device__ __forceinline__ void jit_field(const rp::ModelParams& mp, int i, int b, const float* y, float rp_u, float rp_I, float rp_spk, float* f) {{
+// right-hand side f_k(y, u, I, spike_j / dt)
+__device__ __forceinline__ void jit_field(const rp::ModelParams& mp, int i, int b, const float* y, float rp_u, float rp_I, const float* spk, float* f) {{
 {LOAD_Y}
 {LOAD_P}
+{LOAD_S}
 {F}
 }}
 __device__ __forceinline__ float jit_src(const rp::ModelParams& mp, int i, int b, const float* y) {{
@@ -292,17 +306,35 @@ __device__ __forceinline__ float jit_src(const rp::ModelParams& mp, int i, int b
 {LOAD_P}
     return {SRC};
 }}
-// Jacobians at (y, u, I, spike argument)
-__device__ __forceinline__ void jit_jac(const rp::ModelParams& mp, int i, int b, const float* y, float rp_u, float rp_I, float rp_spk,
-                                        float (*J)[NSV], float* Ju, float* JI, float* Js, float (*Jp)[NPAR], float* dsrc) {{
+// Jacobians at (y, u, I, spike arguments)
+__device__ __forceinline__ void jit_jac(const rp::ModelParams& mp, int i, int b, const float* y, float rp_u, float rp_I, const float* spk,
+                                        float (*J)[NSV], float* Ju, float* JI, float (*Js)[NSPK1], float (*Jp)[NPAR], float* dsrc) {{
 {LOAD_Y}
 {LOAD_P}
+{LOAD_S}
 {J}
 {JU}
 {JI}
 {JS}
 {JP}
 {DSRC}
+}}
+// spike_j = heaviside(y_j - theta, 1.0); the field receives spike_j / dt (rectipy/nodes.py:383-385,453-456)
+__device__ __forceinline__ void jit_spikes(const float* y, float theta, float dt, bool* sp, float* spk) {{
+    spk[0] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NSPK; ++j) {{ sp[j] = y[j] >= theta; spk[j] = sp[j] ? 1.0f / dt : 0.0f; }}
+}}
+// one Euler step with the reset (the adjoint of a post-update output needs y_(t+1) again)
+__device__ __forceinline__ void jit_step(const rp::ModelParams& mp, int i, int b, const float* y, float u, float Iin, float theta, float v_reset,
+                                         float dt, float* y1) {{
+    bool sp[NSPK1]; float spk[NSPK1], f[NSV];
+    jit_spikes(y, theta, dt, sp, spk);
+    jit_field(mp, i, b, y, u, Iin, spk, f);
+#pragma unroll
+    for (int k = 0; k < NSV; ++k) y1[k] = y[k] + dt * f[k];
+#pragma unroll
+    for (int j = 0; j < NSPK; ++j) if (sp[j]) y1[j] = v_reset;          // reset (blend with the detached spike / masked assignment)
 }}
 
 struct JitInitSrcArgs {{ int N, B; const float* y; rp::ModelParams mp; float* src; int ld; }};
@@ -317,21 +349,17 @@ extern "C" __global__ void __launch_bounds__(256) rp_jit_init_src(JitInitSrcArgs
     }}
 }}
 
-// y_{{t+1}} = y_t + dt f(y_t, u_t, I_t, spike_t / dt); threshold / reset on plane 0 (rectipy/nodes.py:166-170,382-392)
+// y_{{t+1}} = y_t + dt f(y_t, u_t, I_t, spike_t / dt), then the reset (rectipy/nodes.py:166-170,382-392,451-465)
 extern "C" __global__ void __launch_bounds__(256) rp_jit_fwd_step(rp::FwdStepArgs a) {{
     const size_t plane = (size_t)a.B * a.N;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane; idx += (size_t)gridDim.x * blockDim.x) {{
         const int b = (int)(idx / a.N), i = (int)(idx - (size_t)b * a.N);
-        float y[NSV], f[NSV], y1[NSV];
+        float y[NSV], y1[NSV];
 #pragma unroll
         for (int k = 0; k < NSV; ++k) y[k] = a.y_cur[(size_t)k * plane + idx];
         const float u = a.u[(size_t)b * a.ldu + i];
         const float Iin = rp::input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i);
-        const bool spike = SPIKING && y[0] >= a.theta;                 // heaviside(v - theta, 1.0)
-        jit_field(a.mp, i, b, y, u, Iin, spike ? 1.0f / a.dt : 0.0f, f);
-#pragma unroll
-        for (int k = 0; k < NSV; ++k) y1[k] = y[k] + a.dt * f[k];
-        if (spike) y1[0] = a.v_reset;                                  // reset blend with the detached spike
+        jit_step(a.mp, i, b, y, u, Iin, a.theta, a.v_reset, a.dt, y1);
         if (a.urec_out) a.urec_out[idx] = u;
 #pragma unroll
         for (int k = 0; k < NSV; ++k) a.y_next[(size_t)k * plane + idx] = y1[k];
@@ -339,8 +367,20 @@ extern "C" __global__ void __launch_bounds__(256) rp_jit_fwd_step(rp::FwdStepArg
     }}
 }}
 
+// gradient of the record window into the output variable (+ dW_out): adj[out] += W_out^T e (readout) | e (dense)
+__device__ __forceinline__ void jit_out_grad(const rp::AdjArgs& a, const float* e, float e_scale, int b, int i, size_t idx, float yout, float* adj) {{
+    if (a.out_mode == RP_OUT_DENSE) {{ adj[a.out_var] += __ldg(e + idx) * e_scale; return; }}
+    float ro = 0.f;
+    for (int q = 0; q < a.k; ++q) {{
+        const float ev = __ldg(e + (size_t)b * a.k + q) * e_scale;
+        ro = fmaf(__ldg(a.W_out + (size_t)q * a.N + i), ev, ro);
+        if (a.dW_out) atomicAdd(a.dW_out + (size_t)q * a.N + i, ev * yout);
+    }}
+    adj[a.out_var] += ro;
+}}
+
 // reverse-time adjoint of one step (SURVEY Appendix A, generalised to an arbitrary field): "post" finishes step t (needs
-// Z_t = (W)^T g_t), "pre" prepares g_{{t-1}} and the source value of step t-1
+// Z_t = W^T g_t), "pre" prepares g_{{t-1}} and the source value of step t-1
 extern "C" __global__ void __launch_bounds__(256) rp_jit_adj_step(rp::AdjArgs a) {{
     const size_t plane = (size_t)a.B * a.N;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane; idx += (size_t)gridDim.x * blockDim.x) {{
@@ -348,19 +388,23 @@ extern "C" __global__ void __launch_bounds__(256) rp_jit_adj_step(rp::AdjArgs a)
         float adj[NSV];
 #pragma unroll
         for (int k = 0; k < NSV; ++k) adj[k] = a.adj[(size_t)k * plane + idx];
-        float J[NSV][NSV], Ju[NSV], JI[NSV], Js[NSV], Jp[NSV][NPAR], dsrc[NSV];
-        if (a.do_post) {{
-            float y[NSV];
+        float J[NSV][NSV], Ju[NSV], JI[NSV], Js[NSV][NSPK1], Jp[NSV][NPAR], dsrc[NSV], spk[NSPK1];
+        bool sp[NSPK1];
+        float y[NSV];
+        if (a.do_post || (POST_OUT && a.e_tm1)) {{
 #pragma unroll
             for (int k = 0; k < NSV; ++k) y[k] = __ldg(a.y_t + (size_t)k * plane + idx);
+        }}
+        if (a.do_post) {{
             const float u = a.urec_t ? __ldg(a.urec_t + idx) : 0.f;
             const float Iin = rp::input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i);
-            const bool spike = SPIKING && y[0] >= a.theta;
-            jit_jac(a.mp, i, b, y, u, Iin, spike ? 1.0f / a.dt : 0.0f, J, Ju, JI, Js, Jp, dsrc);
+            jit_spikes(y, a.theta, a.dt, sp, spk);
+            jit_jac(a.mp, i, b, y, u, Iin, spk, J, Ju, JI, Js, Jp, dsrc);
             float at[NSV];
 #pragma unroll
             for (int k = 0; k < NSV; ++k) at[k] = adj[k];
-            if (spike) at[0] = 0.f;                                    // no gradient through the reset neuron's Euler update
+#pragma unroll
+            for (int j = 0; j < NSPK; ++j) if (sp[j]) at[j] = 0.f;      // no gradient through the Euler update of a variable that is reset
             const float Z = a.Z[(size_t)b * a.ldz + i];
             float nw[NSV];
 #pragma unroll
@@ -370,27 +414,15 @@ extern "C" __global__ void __launch_bounds__(256) rp_jit_adj_step(rp::AdjArgs a)
                 for (int k = 0; k < NSV; ++k) acc = fmaf(a.dt * at[k], J[k][l], acc);
                 nw[l] = fmaf(Z, dsrc[l], acc);
             }}
-            if (SPIKING) {{                                            // surrogate: d spike / d v = 1 / (1 + slope |v - theta|)^2, spike enters f as spike / dt
-                const float dd = 1.0f + a.slope * fabsf(y[0] - a.theta);
+#pragma unroll
+            for (int j = 0; j < NSPK; ++j) {{                            // surrogate: d spike_j / d y_j = 1 / (1 + slope |y_j - theta|)^2; f sees spike_j / dt
+                const float dd = 1.0f + a.slope * fabsf(y[j] - a.theta);
                 float c = 0.f;
 #pragma unroll
-                for (int k = 0; k < NSV; ++k) c = fmaf(at[k], Js[k], c);
-                nw[0] += c / (dd * dd);
+                for (int k = 0; k < NSV; ++k) c = fmaf(at[k], Js[k][j], c);
+                nw[j] += c / (dd * dd);
             }}
-            // readout / record gradient into the output variable, and dW_out
-            if (a.e_t) {{
-                const float yout = y[a.out_var];
-                if (a.out_mode == RP_OUT_DENSE) nw[a.out_var] += __ldg(a.e_t + idx) * a.e_scale;
-                else {{
-                    float ro = 0.f;
-                    for (int q = 0; q < a.k; ++q) {{
-                        const float e = __ldg(a.e_t + (size_t)b * a.k + q) * a.e_scale;
-                        ro = fmaf(__ldg(a.W_out + (size_t)q * a.N + i), e, ro);
-                        if (a.dW_out) atomicAdd(a.dW_out + (size_t)q * a.N + i, e * yout);
-                    }}
-                    nw[a.out_var] += ro;
-                }}
-            }}
+            if (!POST_OUT && a.e_t) jit_out_grad(a, a.e_t, a.e_scale, b, i, idx, y[a.out_var], nw);      // pre-update output: y_t[out]
             float dI = 0.f;
 #pragma unroll
             for (int k = 0; k < NSV; ++k) dI = fmaf(a.dt * at[k], JI[k], dI);
@@ -409,6 +441,9 @@ extern "C" __global__ void __launch_bounds__(256) rp_jit_adj_step(rp::AdjArgs a)
             }}
 #pragma unroll
             for (int k = 0; k < NSV; ++k) adj[k] = a.zero_after_post ? 0.f : nw[k];
+        }}
+        if (POST_OUT && a.e_tm1) jit_out_grad(a, a.e_tm1, a.e_scale_tm1, b, i, idx, y[a.out_var], adj);   // post-update output of step t-1: y_t[out]
+        if (a.do_post || (POST_OUT && a.e_tm1)) {{
 #pragma unroll
             for (int k = 0; k < NSV; ++k) a.adj[(size_t)k * plane + idx] = adj[k];
         }}
@@ -416,11 +451,11 @@ extern "C" __global__ void __launch_bounds__(256) rp_jit_adj_step(rp::AdjArgs a)
             float ym[NSV];
 #pragma unroll
             for (int k = 0; k < NSV; ++k) ym[k] = __ldg(a.y_tm1 + (size_t)k * plane + idx);
-            jit_jac(a.mp, i, b, ym, 0.f, 0.f, 0.f, J, Ju, JI, Js, Jp, dsrc);          // d f / d u depends on the state only (checked at code generation)
-            const bool spike = SPIKING && ym[0] >= a.theta;
+            jit_spikes(ym, a.theta, a.dt, sp, spk);
+            jit_jac(a.mp, i, b, ym, 0.f, 0.f, spk, J, Ju, JI, Js, Jp, dsrc);       // d f / d u depends on the state only (checked at code generation)
             float g = 0.f;
 #pragma unroll
-            for (int k = 0; k < NSV; ++k) g = fmaf(a.dt * ((spike && k == 0) ? 0.f : adj[k]), Ju[k], g);
+            for (int k = 0; k < NSV; ++k) g = fmaf(a.dt * ((k < NSPK && sp[k < NSPK ? k : 0]) ? 0.f : adj[k]), Ju[k], g);
             if (a.g) a.g[idx] = g;
             if (a.src) a.src[idx] = jit_src(a.mp, i, b, ym);
         }}

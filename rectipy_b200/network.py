@@ -82,7 +82,8 @@ def _engine_call(node: RateNet, x: Optional[torch.Tensor], in_mode: int, W_in: O
     prog = node.spec.jit_program
     if prog is not None and node.precision not in ("auto", "fp32", "float32"):
         raise NotImplementedError("rectipy_b200: run-time compiled templates run on the per-step fp32 path (precision='fp32' or 'auto')")
-    jit_kw = {} if prog is None else dict(jit_key=prog.key, jit_nsv=prog.nsv, jit_spiking=int(prog.spiking), jit_src_plane=prog.src_plane)
+    jit_kw = {} if prog is None else dict(jit_key=prog.key, jit_nsv=prog.nsv, jit_spiking=int(prog.spiking), jit_post_out=int(prog.post_out),
+                                            jit_src_plane=prog.src_plane)
     key = engine.PlanKey(
         model=node.spec.model, n=node.n, batch=node.batch, in_mode=in_mode, n_in=n_in, in_target=node.in_target,
         out_mode=out_mode, n_out=n_out, out_var=node.out_var if out_var is None else out_var,

@@ -353,16 +353,43 @@ class SpikeResetNet(RateNet):
         return self._slope
 
 
+class MultiSpikeResetNet(SpikeResetNet):
+    """Several spike / reset variable pairs in one node (rectipy/nodes.py:404-465): every pair is thresholded and reset like
+    SpikeResetNet's, one shared threshold / reset value; `forward` returns the POST-update output slice and `y` is the post-update
+    state (nodes.py:457-465).  Runs on kernels generated from the template's equations (rectipy_b200/jit.py).
+    The reference thresholds a zero vector on the very first step (`_y_reset` is initialised with zeros, nodes.py:430-436); the
+    engine thresholds the actual initial state -- identical unless an initial reset variable is already >= theta or theta <= 0."""
+
+    def __init__(self, spec: TemplateSpec, n: int, weights, spike_threshold: float = 1e2, spike_reset: float = -1e2,
+                 spike_var=("spike",), reset_var=("v",), **kwargs):
+        spike_slope = kwargs.pop("spike_slope", None)
+        spike_center = kwargs.pop("spike_center", 1.0)
+        RateNet.__init__(self, spec, n, weights, **kwargs)
+        prog = spec.jit_program
+        if prog is None or not prog.post_out or prog.spiking != len(spike_var):
+            raise ValueError("MultiSpikeResetNet needs a template bound with lists of spike and reset variables")
+        if float(spike_center) != 1.0:
+            raise NotImplementedError("rectipy_b200 implements the reference default spike_center=1.0 (spike iff v >= theta)")
+        for j, r in enumerate(reset_var):
+            rkey = spec.resolve(r, dict(spec.state_vars))
+            assert self._planes[self._var_map[rkey][0] // self.n] == j
+            self._var_map[f"spike_reset_{j}"] = self._var_map[rkey]
+        self._thresh = float(spike_threshold)
+        self._reset = float(spike_reset)
+        self._slope = float(spike_slope) if spike_slope is not None else 100.0 / abs(self._thresh - self._reset)
+
+
 def node_from_template(node, input_var: str, output_var: str, weights=None, source_var: str = None,
                        target_var: str = None, spike_var=None, reset_var=None, train_params: list = None,
                        **kwargs) -> RateNet:
     """Counterpart of `RateNet.from_pyrates` / `SpikeResetNet.from_pyrates` (rectipy/nodes.py:112-164,363-380)."""
-    spec = resolve_template(node)
+    multi = isinstance(spike_var, (list, tuple))
+    if multi and not isinstance(reset_var, (list, tuple)):
+        raise ValueError("a list of spike variables needs a list of reset variables of the same length")
+    spec = resolve_template(node, force_jit=multi)          # MultiSpikeResetNet semantics only exist as generated kernels
     if spec.jit_field is not None and spec.jit_program is None:
         # equations that match no compiled field: generate + compile the kernels now that the variable roles are known
         from . import jit
-        if isinstance(spike_var, (list, tuple)):
-            raise NotImplementedError("rectipy_b200: MultiSpikeResetNet (several spike variables) is not built yet")
         spec = jit.bind_spec(spec, source_var if weights is not None else None, target_var if weights is not None else None,
                              input_var, spike_var, reset_var if spike_var is not None else None)
     for k in ("clear", "float_precision", "file_name", "verbose", "auto_diff", "vectorize", "backend", "solver"):
@@ -391,7 +418,8 @@ def node_from_template(node, input_var: str, output_var: str, weights=None, sour
     n = weights.shape[0]
     if spike_var is None:
         return RateNet(spec, n, weights, train_params=train_params, input_var=input_var, output_var=output_var, **kwargs)
-    if isinstance(spike_var, (list, tuple)):
-        raise NotImplementedError("rectipy_b200: MultiSpikeResetNet (several spike variables) is not built yet")
+    if multi:
+        return MultiSpikeResetNet(spec, n, weights, train_params=train_params, input_var=input_var, output_var=output_var,
+                                  spike_var=list(spike_var), reset_var=list(reset_var), **kwargs)
     return SpikeResetNet(spec, n, weights, train_params=train_params, input_var=input_var, output_var=output_var,
                          spike_var=spike_var, reset_var=reset_var, **kwargs)

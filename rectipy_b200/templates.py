@@ -187,8 +187,12 @@ def _val(v) -> float:
     return float(v[1]) if isinstance(v, tuple) else float(v)
 
 
-def _spec_from_ops(ops: List[OperatorDef]) -> TemplateSpec:
-    """Recognise the operator combination by its equations and build the engine tables."""
+def _spec_from_ops(ops: List[OperatorDef], force_jit: bool = False) -> TemplateSpec:
+    """Recognise the operator combination by its equations and build the engine tables.  `force_jit`: skip the compiled fields
+    (node semantics they do not implement, e.g. MultiSpikeResetNet)."""
+    if force_jit:
+        from . import jit
+        return jit.unbound_spec(ops)
     eqs = [_normalise([_canon(e) for e in op.equations]) for op in ops]
     main = ops[0]
     mv = main.variables
@@ -332,7 +336,7 @@ def _resolve_operator_path(module_path: str, leaf: str) -> OperatorDef:
     return _load_operator(path, leaf, docs)
 
 
-def resolve_template(node) -> TemplateSpec:
+def resolve_template(node, force_jit: bool = False) -> TemplateSpec:
     """`node`: dotted template path as accepted by the reference (e.g. "neuron_model_templates.spiking_neurons.qif.qif")."""
     if isinstance(node, TemplateSpec):
         return node
@@ -341,7 +345,7 @@ def resolve_template(node) -> TemplateSpec:
                                   f"NodeTemplate/CircuitTemplate instances are not supported (got {type(node).__name__}).")
     if "." not in node and "/" not in node:
         if node in _BUILTIN_NODES:
-            return _spec_from_ops([_BUILTIN_OPS[o] for o in _BUILTIN_NODES[node]])
+            return _spec_from_ops([_BUILTIN_OPS[o] for o in _BUILTIN_NODES[node]], force_jit)
         raise FileNotFoundError(f"Template {node} could not be found.")
     module_path, leaf = node.replace("/", ".").rsplit(".", 1)
     path = _find_yaml(module_path)
@@ -355,10 +359,10 @@ def resolve_template(node) -> TemplateSpec:
         op_names = body.get("operators") or []
         if isinstance(op_names, dict):
             op_names = list(op_names.keys())
-        return _spec_from_ops([_load_operator(path, str(o), docs) for o in op_names])
+        return _spec_from_ops([_load_operator(path, str(o), docs) for o in op_names], force_jit)
     mod = module_path.split(".")[-1]
     if module_path.split(".")[0] == "neuron_model_templates" and mod in _BUILTIN_MODULES:
         if leaf not in _BUILTIN_MODULES[mod]:
             raise AttributeError(f"Template {leaf} is not defined in {module_path}.")
-        return _spec_from_ops([_BUILTIN_OPS[o] for o in _BUILTIN_NODES[leaf]])
+        return _spec_from_ops([_BUILTIN_OPS[o] for o in _BUILTIN_NODES[leaf]], force_jit)
     raise FileNotFoundError(f"Template file {module_path} could not be found.")

@@ -211,3 +211,124 @@ def test_jit_rejects_what_it_cannot_express(user_templates):
         net2.add_diffeq_node("a", "mymodels.custom.fhn", weights=np.zeros((128, 128)), source_var="r", target_var="r_in",
                              input_var="I_ext", output_var="v")
         net2.run(np.zeros((3, 128, 128)), verbose=False)
+
+
+# ---- MultiSpikeResetNet (rectipy/nodes.py:404-465): several spike / reset variable pairs, post-update outputs ------------------
+EI_YAML = """
+ei_op:
+  base: OperatorTemplate
+  equations:
+    - "v_e' = (v_e^2 + eta_e + I_ext)/tau_e + J_ee*s_in - J_ei*s_i"
+    - "s_e' = -s_e/tau_s + spike_e"
+    - "v_i' = (v_i^2 + eta_i)/tau_i + J_ie*s_e"
+    - "s_i' = -s_i/tau_s + spike_i"
+  variables:
+    s_e: output(0.0)
+    v_e: variable(-2.0)
+    v_i: variable(-2.0)
+    s_i: variable(0.0)
+    eta_e: -5.0
+    tau_e: 1.0
+    J_ee: 1.0
+    J_ei: 2.0
+    eta_i: -5.0
+    tau_i: 0.5
+    J_ie: 3.0
+    tau_s: 0.8
+    I_ext: input(0.0)
+    spike_e: input(0.0)
+    spike_i: input(0.0)
+    s_in: input(0.0)
+ei:
+  base: NodeTemplate
+  operators:
+    - ei_op
+"""
+
+
+@pytest.fixture
+def ei_template(tmp_path, monkeypatch):
+    (tmp_path / "mymodels").mkdir()
+    (tmp_path / "mymodels" / "twopop.yaml").write_text(EI_YAML)
+    monkeypatch.chdir(tmp_path)
+
+
+def _ei_engine(rp, z_or_none, n, W, dt, B, node_vars, train, thresh, reset, w_in, w_out):
+    net = rp.Network(dt, device="cuda:0", batch=B)
+    node = net.add_diffeq_node("rnn", "mymodels.twopop.ei", weights=W, source_var="s_e", target_var="s_in", input_var="I_ext",
+                               output_var="s_e", spike_var=["spike_e", "spike_i"], reset_var=["v_e", "v_i"], op="ei_op",
+                               node_vars=node_vars, train_params=train, spike_threshold=thresh, spike_reset=reset)
+    assert type(node).__name__ == "MultiSpikeResetNet" and node.spec.jit_program.spiking == 2 and node.spec.jit_program.post_out
+    net.add_func_node("inp", w_in.shape[1], "identity"); net.add_edge("inp", "rnn", weights=w_in, train="gd")
+    net.add_func_node("out", w_out.shape[0], "identity"); net.add_edge("rnn", "out", weights=w_out, train="gd")
+    return net, node
+
+
+def test_multi_spike_reset_net_matches_reference_fixture(ei_template):
+    """Fixture minted by the reference's own MultiSpikeResetNet inside its Network (oracle/make_golden.py::save_multispike)."""
+    import os
+    import rectipy_b200 as rp
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "multispike_ei.npz"))
+    meta = eval(str(z["meta"]))
+    n, dt, S = meta["n"], meta["dt"], meta["S"]
+    node_vars = {"eta_e": z["param_eta_e"], "eta_i": z["param_eta_i"], **{q: meta[q] for q in ("tau_e", "J_ee", "J_ei", "tau_i", "J_ie", "tau_s")}}
+    net, node = _ei_engine(rp, z, n, z["in_W"], dt, 1, node_vars, meta["train"], meta["thresh"], meta["reset"], z["in_w_in"], z["in_w_out"])
+    obs = net.run(z["in_inputs"], sampling_steps=S, verbose=False, enable_grad=True, record_vars=[("rnn", "v_e", False), ("rnn", "v_i", False)])
+    out = torch.stack(obs["out"])
+    loss = torch.nn.MSELoss()(out, torch.tensor(z["in_targets"], dtype=torch.float32, device="cuda:0"))
+    loss.backward()
+    res = dict(out=out.detach().cpu().numpy(), var_v_e=obs.to_numpy(("rnn", "v_e")), var_v_i=obs.to_numpy(("rnn", "v_i")),
+               y_final=node.y.detach().cpu().numpy(), loss=loss.detach().cpu().numpy(),
+               grad_w_in=net.get_edge("inp", "rnn").weights.grad.cpu().numpy(), grad_w_out=net.get_edge("rnn", "out").weights.grad.cpu().numpy())
+    for name in meta["train"]:
+        res[f"grad_{name}"] = node[name].grad.detach().cpu().numpy()
+    assert np.array_equal(np.asarray(obs["steps"]), z["float64_steps"])
+    # post-update records: a reset shows as exactly the reset value -- the same (step, neuron) entries must have been reset
+    for v in ("var_v_e", "var_v_i"):
+        assert np.array_equal(res[v].reshape(z["float64_" + v].shape) == meta["reset"], z["float64_" + v] == meta["reset"])
+    report = {}
+    for key, val in res.items():
+        ref = z["float64_" + key]
+        err = rel_err(val.reshape(ref.shape), ref)
+        bar = max(2e-5, 10.0 * rel_err(z["float32_" + key], ref))
+        report[key] = (err, bar)
+    print("multispike fixture", {k_: f"{e:.2e}/{b:.1e}" for k_, (e, b) in report.items()})
+    assert not {k_: v for k_, v in report.items() if not v[0] <= v[1]}
+
+
+def test_multi_spike_reset_net_batched_matches_per_trial_oracle(ei_template):
+    import rectipy_b200 as rp
+    n, m, k, T, S, dt, B = 30, 2, 3, 600, 2, 1e-3, 4
+    thresh, reset = 50.0, -50.0
+    rng = np.random.default_rng(99)
+    W = rng.standard_normal((n, n)) * 2.0 / np.sqrt(n)
+    params = dict(eta_e=orc.lorentzian_etas(n) + 8.0, eta_i=rng.uniform(-2.0, 6.0, n), tau_e=1.0, J_ee=1.3, J_ei=2.0, tau_i=0.5, J_ie=3.0, tau_s=0.8)
+    w_in, w_out = rng.standard_normal((n, m)), rng.standard_normal((k, n)) / np.sqrt(n)
+    t = np.arange(T) * dt
+    x = 10.0 * np.sin(2 * np.pi * rng.uniform(0.5, 3, (1, B, m)) * t[:, None, None] + rng.uniform(0, 6.28, (1, B, m))) + 12.0
+    targets = rng.standard_normal((len(range(0, T, S)), B, k))
+    train = ["weights", "eta_e", "J_ie"]
+    net, node = _ei_engine(rp, None, n, W, dt, B, params, train, thresh, reset, w_in, w_out)
+    obs = net.run(x, sampling_steps=S, verbose=False, enable_grad=True, record_vars=[("rnn", "v_i", False)])
+    out = torch.stack(obs["out"])
+    rec = obs.to_numpy(("rnn", "v_i")).reshape(out.shape[0], B, n)
+    torch.nn.functional.mse_loss(out, torch.tensor(targets, dtype=torch.float32, device="cuda:0")).backward()
+    g_ref, out_ref, rec_ref = None, np.zeros(out.shape), np.zeros(rec.shape)
+    for b in range(B):
+        onode = orc.OracleMultiSpikeResetNode(*orc.build_ei_node_args(n, W, params, torch.float64), dt, torch.float64, train,
+                                              spike_threshold=thresh, spike_reset=reset)
+        onet = orc.OracleNet(onode, w_in=torch.tensor(w_in, requires_grad=True), w_out=torch.tensor(w_out, requires_grad=True))
+        r = onet.run(torch.tensor(x[:, b, :]), sampling_steps=S, enable_grad=True, record_vars=[("v_i", False)])
+        pred = torch.stack(r["out"])
+        out_ref[:, b, :] = pred.detach().numpy()
+        rec_ref[:, b, :] = torch.stack(r["vars"]["v_i"]).detach().numpy()
+        (torch.nn.functional.mse_loss(pred, torch.tensor(targets[:, b, :]), reduction="sum") / out.numel()).backward()
+        gs = [q.grad.numpy().copy() for q in onet.parameters()]
+        g_ref = gs if g_ref is None else [a + c for a, c in zip(g_ref, gs)]
+    assert np.array_equal(rec == reset, rec_ref == reset) and (rec_ref == reset).sum() > 0
+    g_eng = [node["weights"].grad, node["eta_e"].grad, node["J_ie"].grad,
+             net.get_edge("inp", "rnn").weights.grad, net.get_edge("rnn", "out").weights.grad]
+    errs = {nm: rel_err(ge.detach().cpu().numpy().reshape(gr.shape), gr) for nm, ge, gr in zip(train + ["w_in", "w_out"], g_eng, g_ref)}
+    e_out = rel_err(out.detach().cpu().numpy(), out_ref)
+    print("multispike batched", f"out {e_out:.2e}", {k_: f"{v:.2e}" for k_, v in errs.items()})
+    assert e_out <= 1e-4 and all(v <= 2e-3 for v in errs.values()), errs
