@@ -139,6 +139,10 @@ int         rp_num_history_planes(int model);                   /* planes per ch
 int         rp_num_records(int T, int sampling_steps, int cutoff); /* records produced by a run  */
 
 int  rp_plan_create(const rp_desc* desc, rp_plan** plan);
+/* Which execution path a plan with this description would take on the current device: 0 per-step launches (fp32), 1 the persistent
+ * few-trial kernels (fp32, the owned rows of kW resident in shared memory), 2 the tcgen05 path; -1 on error.  The host side uses it
+ * to decide whether padding the trial / neuron axes to multiples of 128 (tensor-core path) beats the per-step fp32 path. */
+int  rp_plan_path(const rp_desc* desc);
 void rp_plan_destroy(rp_plan* plan);
 /* bytes of device workspace the plan holds (diagnostics) */
 long long rp_plan_workspace_bytes(const rp_plan* plan);

@@ -52,7 +52,7 @@ class rp_bwd_args(C.Structure):
 EXPORTS = ["rp_abi_version", "rp_last_error", "rp_num_state_vars", "rp_num_history_planes", "rp_num_records", "rp_plan_create",
            "rp_plan_destroy", "rp_plan_workspace_bytes", "rp_plan_launch_count", "rp_forward", "rp_backward", "rp_plan_status",
            "rp_rls_run", "rp_gemm_tn", "rp_plan_time_contraction", "rp_trace_enable", "rp_trace_read", "rp_plan_stage_timing",
-           "rp_plan_stage_times", "rp_plan_set_jit_module"]
+           "rp_plan_stage_times", "rp_plan_set_jit_module", "rp_plan_path"]
 
 _LIB = None
 
@@ -83,6 +83,8 @@ def load():
     lib.rp_num_records.restype = C.c_int
     lib.rp_plan_create.argtypes = [C.POINTER(rp_desc), C.POINTER(C.c_void_p)]
     lib.rp_plan_create.restype = C.c_int
+    lib.rp_plan_path.argtypes = [C.POINTER(rp_desc)]
+    lib.rp_plan_path.restype = C.c_int
     lib.rp_plan_destroy.argtypes = [C.c_void_p]
     lib.rp_plan_destroy.restype = None
     lib.rp_plan_workspace_bytes.argtypes = [C.c_void_p]

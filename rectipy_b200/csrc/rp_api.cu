@@ -270,41 +270,49 @@ int ps_prepare_kernel(K kernel, size_t smem, int grid, const char* what) {
 // geometry of the persistent few-trial kernels; leaves p->persistent false when the shape does not fit.
 // Two-dimensional: n_tb trial blocks of BL <= PS_MAX_B trials x n_rb row blocks.  Among the feasible splits the one with the
 // fewest trials per CTA wins (smallest per-step gather), i.e. the largest n_tb whose rows of kW still fit in shared memory.
-int persistent_setup(rp_plan* p, const cudaDeviceProp& prop) {
-    const int N = p->d.n, B = p->d.batch;
-    int coop = 0, dev = 0;
-    RP_CUDA(cudaGetDevice(&dev));
-    RP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    if (!coop) return 0;
+// Decomposition of the persistent few-trial kernels for an n x batch problem, or false when the owned rows of kW do not fit shared memory
+struct PersistShape { int rows, bl, ntb, nrb, npad, bwd_wres, bwd_dwres; size_t fwd_smem, bwd_smem; };
+bool persistent_shape(int N, int B, int ldw, const cudaDeviceProp& prop, PersistShape* o) {
     const int sms = prop.multiProcessorCount;
     const int npad = round_up(N, 4);
     const size_t budget = std::min<size_t>(prop.sharedMemPerBlockOptin, 200 * 1024);
-    bool found = false;
-    for (int bl = 1; bl <= std::min(B, rp::PS_MAX_B) && !found; ++bl) {
+    for (int bl = 1; bl <= std::min(B, rp::PS_MAX_B); ++bl) {
         const int ntb = (B + bl - 1) / bl;
         if (ntb > sms) continue;
         const int nrb_max = sms / ntb;
         int rows = (N + nrb_max - 1) / nrb_max;
         rows = std::max(8, round_up(rows, 8));
         if (rows > rp::PS_MAX_ROWS || rows * bl > rp::PS_THREADS) continue;
-        const size_t wbytes = (size_t)rows * p->ldw * sizeof(float);
+        const size_t wbytes = (size_t)rows * ldw * sizeof(float);
         const size_t base_f = rp::ps_fwd_base_floats(bl, npad) * sizeof(float);
         const size_t base_b = ((size_t)bl * npad + 2 * rp::PS_MAX_ROWS * rp::PS_MAX_B) * sizeof(float);
         // Only worth it while the owned rows of kW stay in shared memory: streaming them from L2 with one warp per row is
         // slower than the per-step launch sequence (measured: N=4096, B=1: 156 vs 116 us/step).
         if (base_f + wbytes > budget || base_b > budget) continue;
-        p->ps_rows = rows; p->ps_bl = bl; p->ps_ntb = ntb;
-        p->ps_nrb = (N + rows - 1) / rows;
-        p->ps_grid = p->ps_nrb * ntb;
-        p->ps_npad = npad;
-        p->ps_fwd_wres = 1;
-        p->ps_fwd_smem = base_f + wbytes;
-        p->ps_bwd_dwres = (base_b + 2 * wbytes <= budget) ? 1 : 0;
-        p->ps_bwd_wres = (p->ps_bwd_dwres || base_b + wbytes <= budget) ? 1 : 0;
-        p->ps_bwd_smem = base_b + (p->ps_bwd_wres ? wbytes : 0) + (p->ps_bwd_dwres ? wbytes : 0);
-        found = true;
+        o->rows = rows; o->bl = bl; o->ntb = ntb; o->nrb = (N + rows - 1) / rows; o->npad = npad;
+        o->fwd_smem = base_f + wbytes;
+        o->bwd_dwres = (base_b + 2 * wbytes <= budget) ? 1 : 0;
+        o->bwd_wres = (o->bwd_dwres || base_b + wbytes <= budget) ? 1 : 0;
+        o->bwd_smem = base_b + (o->bwd_wres ? wbytes : 0) + (o->bwd_dwres ? wbytes : 0);
+        return true;
     }
-    if (!found) return 0;
+    return false;
+}
+
+int persistent_setup(rp_plan* p, const cudaDeviceProp& prop) {
+    const int B = p->d.batch;
+    int coop = 0, dev = 0;
+    RP_CUDA(cudaGetDevice(&dev));
+    RP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) return 0;
+    PersistShape ps;
+    if (!persistent_shape(p->d.n, B, p->ldw, prop, &ps)) return 0;
+    p->ps_rows = ps.rows; p->ps_bl = ps.bl; p->ps_ntb = ps.ntb; p->ps_nrb = ps.nrb;
+    p->ps_grid = ps.nrb * ps.ntb;
+    p->ps_npad = ps.npad;
+    p->ps_fwd_wres = 1;
+    p->ps_fwd_smem = ps.fwd_smem;
+    p->ps_bwd_dwres = ps.bwd_dwres; p->ps_bwd_wres = ps.bwd_wres; p->ps_bwd_smem = ps.bwd_smem;
     if (plan_alloc(p, &p->ps_vec, 4 * (size_t)B * p->ps_npad)) return 1;
     RP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->ps_bar), sizeof(unsigned int)));
     p->persistent = true;
@@ -445,6 +453,18 @@ int rp_num_records(int T, int S, int cutoff) {
     const int r0 = ((std::max(cutoff, 0) + S - 1) / S) * S;
     if (r0 > T - 1) return 0;
     return (T - 1 - r0) / S + 1;
+}
+
+int rp_plan_path(const rp_desc* d) {
+    if (!d) { fail("rp_plan_path: null argument"); return -1; }
+    if (d->precision == RP_PREC_3XTF32 || d->precision == RP_PREC_3XF16) return rp::tc_supported(d->n, d->batch) ? 2 : -1;
+    if (rp::is_mean_field(d->model) || d->model == RP_JIT || getenv("RP_NO_PERSISTENT")) return 0;
+    int dev = 0, coop = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { fail("rp_plan_path: no CUDA device"); return -1; }
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    PersistShape ps;
+    return (coop && persistent_shape(d->n, d->batch, round_up(d->n, 4), prop, &ps)) ? 1 : 0;
 }
 
 int rp_plan_create(const rp_desc* d, rp_plan** out) {

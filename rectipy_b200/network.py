@@ -12,6 +12,9 @@ the reference has no trial axis (rectipy/nodes.py:90).  With `batch=1` all shape
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
+
 from dataclasses import dataclass
 from time import perf_counter
 from typing import Callable, Dict, Iterator, List, Optional, Tuple, Union
@@ -69,6 +72,52 @@ def _window_mean(per_step: torch.Tensor, S: int, cutoff: int) -> torch.Tensor:
     return torch.stack(out) if out else per_step[:0]
 
 
+def _ceil128(v: int) -> int:
+    return (v + 127) // 128 * 128
+
+
+_PATH_CACHE: Dict[Tuple[int, int, int, int], int] = {}
+
+
+def _padded_shape(node: RateNet, T: int) -> Optional[Tuple[int, int]]:
+    """(n_pad, batch_pad) when the horizon should run on the tensor-core path with the trial / neuron axes padded to multiples of 128,
+    else None.  Applies to precision="auto" on shapes the tcgen05 kernels do not take as they are (batch or n not a multiple of 128)
+    and that the persistent few-trial kernels do not hold either (rp_plan_path): there the alternative is one fp32 FFMA contraction
+    launch per step, 5-9x slower than the padded pass (tools/exp_trial_padding.py: n=1024..4096, 32..96 trials, B200).  Padded
+    trials and neurons are inert by construction -- zero weight rows / columns, zero input and readout weights, zero loss gradient --
+    so results and gradients of the real entries are those of the unpadded problem."""
+    n, B = node.n, node.batch
+    if node.precision != "auto" or node.spec.jit_program is not None or engine.tc_supported(n, B) or T < 8:
+        return None
+    n_pad, b_pad = _ceil128(n), _ceil128(B)
+    if n_pad < 512 or os.environ.get("RECTIPY_B200_NO_PADDING"):
+        return None
+    if n_pad != n and node.spec.model in (abi.RP_IKU, abi.RP_IK_BIEXP):       # population means would see the padded neurons
+        return None
+    dev = node.device.index if node.device.index is not None else torch.cuda.current_device()
+    ck = (node.spec.model, n, B, dev)
+    if ck not in _PATH_CACHE:
+        d = abi.rp_desc()
+        d.model, d.n, d.batch, d.precision = node.spec.model, n, B, abi.RP_PREC_FP32
+        with torch.cuda.device(dev):
+            _PATH_CACHE[ck] = int(abi.load().rp_plan_path(C.byref(d)))
+    return (n_pad, b_pad) if _PATH_CACHE[ck] == 0 else None
+
+
+def _pad_axis(t: torch.Tensor, dim: int, size: int, replicate: bool) -> torch.Tensor:
+    """Grow `dim` of `t` to `size`: zeros, or copies of the last entry (state and parameters: a padded neuron / trial then behaves
+    like a real one -- bounded, no special cases in the kernels -- while nothing it does can reach a real entry)."""
+    cur = t.shape[dim]
+    if cur == size:
+        return t
+    if replicate:
+        idx = torch.arange(size, device=t.device).clamp_(max=cur - 1)
+        return t.index_select(dim, idx)
+    shape = list(t.shape)
+    shape[dim] = size - cur
+    return torch.cat((t, t.new_zeros(shape)), dim)
+
+
 def _engine_call(node: RateNet, x: Optional[torch.Tensor], in_mode: int, W_in: Optional[torch.Tensor],
                  out_mode: int, W_out: Optional[torch.Tensor], T: int, S: int, cutoff: int, truncate: int,
                  rec_vars: Tuple[int, ...], rec_reduce: Tuple[int, ...], want_out: bool, out_var: Optional[int] = None):
@@ -84,19 +133,59 @@ def _engine_call(node: RateNet, x: Optional[torch.Tensor], in_mode: int, W_in: O
         raise NotImplementedError("rectipy_b200: run-time compiled templates run on the per-step fp32 path (precision='fp32' or 'auto')")
     jit_kw = {} if prog is None else dict(jit_key=prog.key, jit_nsv=prog.nsv, jit_spiking=int(prog.spiking), jit_post_out=int(prog.post_out),
                                             jit_src_plane=prog.src_plane)
+    n, B = node.n, node.batch
+    W, state = node["weights"], node.state
+    rec_reduce = tuple(int(r) for r in rec_reduce)
+    eng_reduce = rec_reduce
+    pad = _padded_shape(node, T)
+    if pad is not None:
+        n, B = pad
+        W = _pad_axis(_pad_axis(W, 0, n, False), 1, n, False)
+        state = _pad_axis(_pad_axis(state, 2, n, True), 1, B, True)
+        if W_in is not None:
+            W_in = _pad_axis(W_in, 0, n, False)
+        if W_out is not None:
+            W_out = _pad_axis(W_out, 1, n, False)
+        if x is not None:
+            x = _pad_axis(x, 1, B, False)
+            if in_mode == abi.RP_IN_DENSE:
+                x = _pad_axis(x, 2, n, False)
+            x = x.contiguous()
+        padded = []
+        for t_, mode in zip(ptensors, (per_neuron[s_] for s_ in slots)):       # 0 shared, 1 [n], 2 [B,1], 3 [B,n]
+            if mode & 1:
+                t_ = _pad_axis(t_, t_.dim() - 1, n, True)
+            if mode >= 2:
+                t_ = _pad_axis(t_, 0, B, True)
+            padded.append(t_)
+        ptensors = padded
+        if n != node.n:
+            eng_reduce = tuple(0 for _ in rec_reduce)          # neuron means are taken over the real neurons below
     key = engine.PlanKey(
-        model=node.spec.model, n=node.n, batch=node.batch, in_mode=in_mode, n_in=n_in, in_target=node.in_target,
+        model=node.spec.model, n=n, batch=B, in_mode=in_mode, n_in=n_in, in_target=node.in_target,
         out_mode=out_mode, n_out=n_out, out_var=node.out_var if out_var is None else out_var,
-        precision=abi.RP_PREC_FP32 if prog is not None else _precision_code(node.precision, node.n, node.batch), dt=node.dt,
+        precision=abi.RP_PREC_FP32 if prog is not None else _precision_code(node.precision, n, B), dt=node.dt,
         theta=node.theta, v_reset=node.v_reset, slope=node.slope, per_neuron=per_neuron,
         device=node.device.index if node.device.index is not None else torch.cuda.current_device(), **jit_kw)
     plan = engine.get_plan(key)
     cfg = engine.RunConfig(T=T, sampling_steps=S, cutoff=cutoff, truncate_steps=truncate, rec_vars=tuple(rec_vars),
-                           rec_reduce=tuple(int(r) for r in rec_reduce), want_out=want_out, param_slots=slots)
-    res = engine.EngineRun.apply(plan, cfg, x, node["weights"], W_in, W_out, node.state, *ptensors)
-    out_rec, yT, recs = res[0], res[1], res[2:]
+                           rec_reduce=eng_reduce, want_out=want_out, param_slots=slots)
+    res = engine.EngineRun.apply(plan, cfg, x, W, W_in, W_out, state, *ptensors)
+    out_rec, yT, recs = res[0], res[1], list(res[2:])
+    if pad is not None:
+        nb, nn = node.batch, node.n
+        yT = yT[:, :nb, :nn].contiguous()
+        if want_out:
+            out_rec = out_rec[:, :nb] if out_mode == abi.RP_OUT_READOUT else out_rec[:, :nb, :nn]
+        for i, red in enumerate(rec_reduce):
+            if eng_reduce[i]:
+                recs[i] = recs[i][:, :nb]
+            else:
+                recs[i] = recs[i][:, :nb, :nn]
+                if red:
+                    recs[i] = recs[i].mean(dim=-1)
     node._state = yT
-    return (out_rec if want_out else None), list(recs)
+    return (out_rec if want_out else None), recs
 
 
 def _single_node_step(node: RateNet, x) -> torch.Tensor:
