@@ -83,14 +83,14 @@ def _padded_shape(node: RateNet, T: int) -> Optional[Tuple[int, int]]:
     """(n_pad, batch_pad) when the horizon should run on the tensor-core path with the trial / neuron axes padded to multiples of 128,
     else None.  Applies to precision="auto" on shapes the tcgen05 kernels do not take as they are (batch or n not a multiple of 128)
     and that the persistent few-trial kernels do not hold either (rp_plan_path): there the alternative is one fp32 FFMA contraction
-    launch per step, 5-9x slower than the padded pass (tools/exp_trial_padding.py: n=1024..4096, 32..96 trials, B200).  Padded
+    launch per step, 5-9x slower than the padded pass at 32..96 trials, break-even at 8 (profiles/r2_trial_padding.md, n=1024..4096).  Padded
     trials and neurons are inert by construction -- zero weight rows / columns, zero input and readout weights, zero loss gradient --
     so results and gradients of the real entries are those of the unpadded problem."""
     n, B = node.n, node.batch
     if node.precision != "auto" or node.spec.jit_program is not None or engine.tc_supported(n, B) or T < 8:
         return None
     n_pad, b_pad = _ceil128(n), _ceil128(B)
-    if n_pad < 512 or os.environ.get("RECTIPY_B200_NO_PADDING"):
+    if n_pad < 512 or B <= 8 or os.environ.get("RECTIPY_B200_NO_PADDING"):      # <= 8 trials: the per-step fp32 path is faster (measured)
         return None
     if n_pad != n and node.spec.model in (abi.RP_IKU, abi.RP_IK_BIEXP):       # population means would see the padded neurons
         return None

@@ -34,9 +34,12 @@ def one(n, B, precision, T=200, reps=3, grad=True):
     return best
 
 
+import sys as _sys
+small = len(_sys.argv) > 1 and _sys.argv[1] == "small"
 for grad in (False, True):
-    for n in (1024, 2048, 4096):
-        for B in (32, 64, 96):
+    for n in ((1536, 2048, 4096) if small else (1024, 2048, 4096)):
+        for B in ((1, 2, 4, 8, 16) if small else (32, 64, 96)):
+            os.environ["RECTIPY_B200_NO_PADDING"] = "1"
             a = one(n, B, "fp32", grad=grad)
             b = one(n, 128, "auto", grad=grad)
             print(f"grad={int(grad)} n={n} B={B}: fp32 path {a:8.2f} ms   padded-to-128 tensor-core path {b:8.2f} ms   x{a / b:.2f}", flush=True)
