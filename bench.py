@@ -372,9 +372,14 @@ def run_ours(args):
         hbm = peaks["hbm"]
         f_fwd, f_bptt = 2.0 * n + 2 * N_IN + 2 * N_OUT + 14, 6.0 * n + 60          # flops per neuron-step
         adj_bytes = 44.0                                                              # B per neuron-step of the fused reverse kernel
-        names = {"fwd_fused": "rp::k_gemm_split3<256, EpiFwd<QIF>, f16=%d> (W.s contraction + Euler step + readout)" % int(f16),
-                 "dgrad": "rp::k_gemm_split3<256, EpiStore, f16=%d> (Z = (kW)^T g)" % int(f16),
-                 "wgrad": "rp::k_gemm_split3<256, EpiStore, f16=%d> (dW += g (x) s, K = %d steps x batch)" % (int(f16), int(chunk_steps)),
+        fwd_cnt = stages.get("fwd_fused", (0.0, 0))[1]
+        persist = f16 and 0 < fwd_cnt < T                     # one cooperative launch integrates the whole horizon
+        cg2 = f16 and not os.environ.get("RP_NO_TC_CG2")      # adjoint product / weight gradient on 256x256 CTA-pair tiles (cta_group::2)
+        gemm = "rp::k_gemm_split3_cg2<EpiStore> (256x256 CTA-pair tile, cta_group::2)" if cg2 else "rp::k_gemm_split3<256, EpiStore, f16=%d>" % int(f16)
+        names = {"fwd_fused": ("rp::k_gemm_fwd_persist<256, EpiFwd<QIF>, f16> (persistent over all T steps: W.s contraction + Euler step + readout per step)"
+                               if persist else "rp::k_gemm_split3<256, EpiFwd<QIF>, f16=%d> (W.s contraction + Euler step + readout)" % int(f16)),
+                 "dgrad": gemm + " (Z = (kW)^T g)",
+                 "wgrad": gemm + " (dW += g (x) s, K = %d steps x batch)" % int(chunk_steps),
                  "adjoint_elementwise": "rp::k_adj_fused_f16<QIF> (adjoint step + split operands + dW_out partials)",
                  "other": "per-call kernels (weight split, maxima, dW finish) + the loss between the two calls"}
         stage_total = sum(v[0] for v in stages.values()) or 1.0
@@ -382,7 +387,10 @@ def run_ours(args):
         for key, (ms_tot, cnt) in stages.items():
             ent = {"kernel": names[key], "launches": cnt, "ms_total": ms_tot, "ms_per_launch": ms_tot / max(cnt, 1), "share_of_pass": ms_tot / stage_total}
             if key in ("fwd_fused", "dgrad") and cnt:
-                tf = 2.0 * n * n * B / (ent["ms_per_launch"] * 1e-3) / 1e12
+                steps_cov = T if (key == "fwd_fused" and persist) else cnt       # Euler steps these launches cover
+                ent["steps_covered"] = steps_cov
+                ent["ms_per_step_of_stage"] = ms_tot / steps_cov
+                tf = 2.0 * n * n * B / (ms_tot / steps_cov * 1e-3) / 1e12
                 ent.update(bound="tensor", achieved_tflops=tf, frac_of_burst_peak=tf / peak_logical, frac_of_sustained_peak=tf / (peaks["bf16_sustained"] / 3.0))
             elif key == "wgrad" and cnt:
                 steps_cov = T          # all chunks of the pass together cover T steps
@@ -398,8 +406,8 @@ def run_ours(args):
         roofline = {
             "bound": "tensor", "kernel": names[top], "achieved": top_ent.get("achieved_tflops", ach), "peak": peak_logical, "unit": "TFLOP/s",
             "frac": top_ent.get("frac_of_burst_peak", ach / peak_logical), "traffic": _ncu_traffic(),
-            "note": ("the dominant kernel of the pass as it runs (largest share of the event-timed pass): achieved = logical 2*N*N*B flops per launch / "
-                     "mean launch-to-launch time incl. its element-wise epilogue and the launch gap; the kernel issues 3 kind::f16 MMAs "
+            "note": ("the dominant kernel of the pass as it runs (largest share of the event-timed pass): achieved = logical 2*N*N*B flops per Euler step / "
+                     "mean time per step of that stage incl. its element-wise epilogue and any launch gap (the persistent forward kernel covers T steps per launch); the kernel issues 3 kind::f16 MMAs "
                      "(binary16 hi/lo split words, fp32 accumulate) per logical product, so peak = bf16_tflops burst (%s)/3; `kernels` holds every stage, "
                      "`isolated_contractions` the bare contractions timed alone back to back" % peaks["source"]),
             "kernels": kernels,

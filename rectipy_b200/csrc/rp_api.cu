@@ -16,6 +16,7 @@
 #include "rp_gemm_tc.cuh"
 #include "rp_rls.cuh"
 #include "rp_persistent.cuh"
+#include "rp_fp32_paths.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -60,7 +61,6 @@ inline int nhist_of(const rp_desc& d) { return d.model == RP_JIT ? d.jit_nsv + 1
 // plane of the state that the recurrent weights project (-1: an expression of the state kept in plan->src)
 inline int src_plane_of(const rp_desc& d) { return d.model == RP_JIT ? d.jit_src_plane : (spiking(d.model) ? 1 : -1); }
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
 
@@ -191,37 +191,9 @@ inline int ew_grid(const rp_plan* p, size_t total) {
 // ---- contraction dispatch:  C[q*ldc+p] (+)= sum_k Aop(p,k) Bop(q,k) ------------------------------------
 int gemm_fp32(rp_plan* plan, bool kmajor, int P, int Q, int K, const float* A, int lda, const float* B, int ldb,
               float* C, int ldc, int accumulate, cudaStream_t st, long long* launches) {
-    if (P <= 0 || Q <= 0) return 0;
-    if (K <= 0) {
-        if (!accumulate) RP_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)P * sizeof(float), Q, st));
-        return 0;
-    }
-    const bool al = aligned16(A) && aligned16(B) && aligned16(C) && (lda % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0);
-    if (kmajor && Q <= 16 && !accumulate) {
-        const bool vec = al && (K % 4 == 0);
-        for (int q0 = 0; q0 < Q; q0 += 8) {
-            const int qn = std::min(8, Q - q0);
-            const int blocks = (P + 7) / 8;   // 8 warps per block
-            if (vec) rp::k_gemv_rows<true><<<blocks, 256, 0, st>>>(P, qn, K, A, lda, B + (size_t)q0 * ldb, ldb, C + (size_t)q0 * ldc, ldc);
-            else     rp::k_gemv_rows<false><<<blocks, 256, 0, st>>>(P, qn, K, A, lda, B + (size_t)q0 * ldb, ldb, C + (size_t)q0 * ldc, ldc);
-            ++*launches;
-        }
-        RP_LAUNCH_CHECK();
-        return 0;
-    }
-    dim3 grid((P + rp::SG_BM - 1) / rp::SG_BM, (Q + rp::SG_BN - 1) / rp::SG_BN);
-    if (kmajor) {
-        const bool vec = al && (K % 4 == 0) && (P % 4 == 0);
-        if (vec) rp::k_sgemm<true, true><<<grid, 256, 0, st>>>(P, Q, K, A, lda, B, ldb, C, ldc, accumulate);
-        else     rp::k_sgemm<true, false><<<grid, 256, 0, st>>>(P, Q, K, A, lda, B, ldb, C, ldc, accumulate);
-    } else {
-        const bool vec = al && (P % 4 == 0) && (Q % 4 == 0);
-        if (vec) rp::k_sgemm<false, true><<<grid, 256, 0, st>>>(P, Q, K, A, lda, B, ldb, C, ldc, accumulate);
-        else     rp::k_sgemm<false, false><<<grid, 256, 0, st>>>(P, Q, K, A, lda, B, ldb, C, ldc, accumulate);
-    }
-    ++*launches;
-    RP_LAUNCH_CHECK();
     (void)plan;
+    const cudaError_t e = rp::gemm_fp32_launch(kmajor, P, Q, K, A, lda, B, ldb, C, ldc, accumulate, st, launches);      // rp_fp32_paths.cu
+    if (e != cudaSuccess) return fail("fp32 contraction launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -255,16 +227,17 @@ Window window_of(int t, int T, int S, int cutoff) {
     return w;
 }
 
-template <typename K>
-int ps_prepare_kernel(K kernel, size_t smem, int grid, const char* what) {
-    RP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, rp::PS_THREADS, smem));
-    int dev = 0, sms = 0;
-    RP_CUDA(cudaGetDevice(&dev));
-    RP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (occ < 1 || grid > occ * sms) return fail("%s: persistent grid of %d CTAs is not co-resident (occupancy %d x %d SMs)", what, grid, occ, sms);
-    return 0;
+// launch one of the persistent few-trial kernels (defined and compiled in rp_fp32_paths.cu) and translate its status
+template <typename F, typename A>
+int ps_launch_checked(F launcher, int model, const A* pa, int grid, size_t smem, cudaStream_t st, const char* what) {
+    cudaError_t e = cudaSuccess;
+    int occ = 0, sms = 0;
+    switch (launcher(model, pa, grid, smem, st, &e, &occ, &sms)) {
+        case 0: return 0;
+        case 1: return fail("%s: persistent kernel launch failed: %s", what, cudaGetErrorString(e));
+        case 2: return fail("%s: persistent grid of %d CTAs is not co-resident (occupancy %d x %d SMs)", what, grid, occ, sms);
+        default: return fail("%s: no persistent kernel for model id %d", what, model);
+    }
 }
 
 // geometry of the persistent few-trial kernels; leaves p->persistent false when the shape does not fit.
@@ -365,11 +338,7 @@ int persistent_forward(rp_plan* p, const rp_fwd_args* a, const rp::ModelParams& 
     for (int r = 0; r < a->n_rec_vars; ++r) { pa.rec_var[r] = a->rec_var[r]; pa.rec_reduce[r] = a->rec_reduce[r]; pa.rec_buf[r] = a->rec_buf[r]; }
     pa.rec_post = spiking(d.model) ? 0 : 1;
     pa.barrier = p->ps_bar;
-    void* args[] = {&pa};
-    RP_DISPATCH_MODEL(d.model, {
-        if (ps_prepare_kernel(rp::k_persist_fwd<M_>, p->ps_fwd_smem, p->ps_grid, "rp_forward")) return 1;
-        RP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rp::k_persist_fwd<M_>), dim3(p->ps_grid), dim3(rp::PS_THREADS), args, p->ps_fwd_smem, st));
-    });
+    if (ps_launch_checked(rp::ps_launch_fwd, d.model, &pa, p->ps_grid, p->ps_fwd_smem, st, "rp_forward")) return 1;
     ++p->launches;
     if (ordered) {
         // records that closed inside this segment: [j0, j1)
@@ -424,11 +393,7 @@ int persistent_backward(rp_plan* p, const rp_bwd_args* a, const rp::ModelParams&
     pa.gbuf = reinterpret_cast<uint2*>(p->ps_vec); pa.Npad = p->ps_npad; pa.dWrawT = p->dWraw;
     for (int q = 0; q < RP_NUM_PARAMS; ++q) pa.dparams[q] = (q == fold) ? nullptr : a->dparams[q];
     pa.dW_in = a->dW_in; pa.dW_out = a->dW_out; pa.g_y0 = a->g_y0; pa.g_x = a->g_x; pa.barrier = p->ps_bar;
-    void* args[] = {&pa};
-    RP_DISPATCH_MODEL(d.model, {
-        if (ps_prepare_kernel(rp::k_persist_bwd<M_>, p->ps_bwd_smem, p->ps_grid, "rp_backward")) return 1;
-        RP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rp::k_persist_bwd<M_>), dim3(p->ps_grid), dim3(rp::PS_THREADS), args, p->ps_bwd_smem, st));
-    });
+    if (ps_launch_checked(rp::ps_launch_bwd, d.model, &pa, p->ps_grid, p->ps_bwd_smem, st, "rp_backward")) return 1;
     ++p->launches;
     if (need_dW) {
         dim3 grid((N + 31) / 32, (N + 31) / 32);
@@ -1019,10 +984,8 @@ int rp_backward(rp_plan* p, const rp_bwd_args* a, void* stream) {
                         aa.g = p->wg_g + (size_t)wg_pos * plane;                 // where this launch's "pre" puts g_{t-1}, r_{t-1}
                         if (src_plane < 0) aa.src = p->wg_src + (size_t)wg_pos * plane;
                     } else if (B <= 16) {
-                        dim3 og((N + 255) / 256, N);
-                        rp::k_outer_acc<<<og, 256, 0, st>>>(N, B, p->g, N, srcp, N, p->dWraw, p->ldw);
+                        RP_CUDA(rp::outer_acc_launch(N, B, p->g, N, srcp, N, p->dWraw, p->ldw, st));
                         ++p->launches;
-                        RP_LAUNCH_CHECK();
                     } else {
                         // dWraw[i][j] += sum_b src[b][j] g[b][i]   (p = j, q = i)
                         if (gemm_fp32(p, false, N, N, B, srcp, N, p->g, N, p->dWraw, p->ldw, 1, st, &p->launches)) return 1;

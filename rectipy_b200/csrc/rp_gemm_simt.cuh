@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) k_gemv_rows(int P, int Q, int K, const fl
 }
 
 // Few trials: dW[i][j] += sum_b g[b][i] * src[b][j]   (rank-B update, bound by the read-modify-write of dW)
-__global__ void __launch_bounds__(256) k_outer_acc(int N, int Bq, const float* __restrict__ g, int ldg,
+static __global__ void __launch_bounds__(256) k_outer_acc(int N, int Bq, const float* __restrict__ g, int ldg,
                                                    const float* __restrict__ src, int lds, float* __restrict__ dW, int ldw) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;

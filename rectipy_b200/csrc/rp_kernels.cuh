@@ -22,9 +22,10 @@ namespace rp {
 
 // ---- optional CTA timeline (debug / profiles): one record per traced CTA when rp_trace_enable() armed a buffer ---------------
 struct TraceRec { unsigned tag, smid; unsigned long long t0, t1; };
-__device__ TraceRec* g_trace_buf = nullptr;
-__device__ unsigned g_trace_cap = 0;
-__device__ unsigned g_trace_n = 0;
+// (internal linkage: the headers are compiled into two translation units, see rp_fp32_paths.cu)
+static __device__ TraceRec* g_trace_buf = nullptr;
+static __device__ unsigned g_trace_cap = 0;
+static __device__ unsigned g_trace_n = 0;
 enum { TR_GEMM_STORE = 1, TR_GEMM_WGRAD = 2, TR_GEMM_FWD = 3, TR_GEMM_ADJ = 4, TR_ADJ_STEP = 5, TR_ADJ_CONVERT = 6 };
 __device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // call from ONE thread of the CTA; returns nullptr when tracing is off
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(256) k_init_src(int N, int B, const float* y, 
 
 // ---- absolute maxima that the binary16 operand scales are derived from --------------------------------------------------------
 // dst = max(dst, max |src[r*ld + c] * rowscale[r*rs_stride]|) over rows x cols   (rowscale == nullptr: 1)
-__global__ void __launch_bounds__(256) k_amax_2d(int rows, int cols, const float* __restrict__ src, size_t ld,
+static __global__ void __launch_bounds__(256) k_amax_2d(int rows, int cols, const float* __restrict__ src, size_t ld,
                                                   const float* __restrict__ rowscale, int rs_stride, float* dst) {
     float amax = 0.f;
     const size_t total = (size_t)rows * cols;
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(256) k_amax_2d(int rows, int cols, const float
 // iku_op mean field: one block per trial.  Deterministic (fixed-order block reduction), so trials stay bit-independent.
 // ------------------------------------------------------------------------------------------------------
 // mf[b] = { mean_i v[b][i], mean_i [v[b][i] >= theta] }
-__global__ void __launch_bounds__(256) k_trial_means(int N, const float* __restrict__ v, float theta, float2* mf) {
+static __global__ void __launch_bounds__(256) k_trial_means(int N, const float* __restrict__ v, float theta, float2* mf) {
     __shared__ float red[2][8];
     const int b = blockIdx.x;
     float sv = 0.f, sp = 0.f;
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(256) k_trial_means(int N, const float* __restr
     }
 }
 // asum[b] = { mean_i(ax[b][i] dt b_i / tau_u_i), mean_i(ax[b][i] kappa_i) }     (ax = adjoint of the recovery variable, plane 2)
-__global__ void __launch_bounds__(256) k_trial_adj_sums(int N, int B, const float* __restrict__ ax, ModelParams mp, float dt, float2* asum) {
+static __global__ void __launch_bounds__(256) k_trial_adj_sums(int N, int B, const float* __restrict__ ax, ModelParams mp, float dt, float2* asum) {
     __shared__ float red[2][8];
     const int b = blockIdx.x;
     float s0 = 0.f, s1 = 0.f;
@@ -1117,7 +1118,7 @@ struct ConvArgs {
 };
 
 constexpr int CV_TN = 64, CV_TB = 32;     // block tile: 64 neurons x 32 trials, 17 KB of shared memory (fits beside a GEMM CTA)
-__global__ void __launch_bounds__(256) k_adj_convert_f16(ConvArgs a) {
+static __global__ void __launch_bounds__(256) k_adj_convert_f16(ConvArgs a) {
     __shared__ float tg[CV_TB][CV_TN + 4];
     __shared__ float ts[CV_TB][CV_TN + 4];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;        // tx -> 4 neurons, ty -> trials ty, ty + 16
@@ -1449,7 +1450,7 @@ __global__ void __launch_bounds__(256, RP_FUSED_OCC) k_adj_fused_f16(AdjArgs a, 
 }
 
 // dst[j] = sum over parts (fixed order) of part[p][j]
-__global__ void __launch_bounds__(256) k_sum_parts(const float* __restrict__ part, int nparts, size_t n, float* dst) {
+static __global__ void __launch_bounds__(256) k_sum_parts(const float* __restrict__ part, int nparts, size_t n, float* dst) {
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
         float acc = 0.f;
         for (int p = 0; p < nparts; ++p) acc += part[(size_t)p * n + j];
@@ -1457,10 +1458,10 @@ __global__ void __launch_bounds__(256) k_sum_parts(const float* __restrict__ par
     }
 }
 // *p *= v  (one thread)
-__global__ void k_scale_scalar(float* p, float v) { if (threadIdx.x == 0 && blockIdx.x == 0) *p *= v; }
+static __global__ void k_scale_scalar(float* p, float v) { if (threadIdx.x == 0 && blockIdx.x == 0) *p *= v; }
 
 // max over a short device array (the per-step source maxima of the last forward pass) -> *dst
-__global__ void k_max_of_array(const float* src, int n, float* dst) {
+static __global__ void k_max_of_array(const float* src, int n, float* dst) {
     float m = 0.f;
     for (int i = threadIdx.x; i < n; i += 32) m = fmaxf(m, src[i]);
     m = warp_max(m);
@@ -1471,7 +1472,7 @@ __global__ void k_max_of_array(const float* src, int n, float* dst) {
 // weight preparation / finalisation
 // ------------------------------------------------------------------------------------------------------
 // Wk[i][j] = k_i * W[i][j]  and its transpose; optionally also the tf32 hi/lo splits (padded leading dims)
-__global__ void __launch_bounds__(256) k_prepare_weights(int N, const float* __restrict__ W, const float* __restrict__ kp,
+static __global__ void __launch_bounds__(256) k_prepare_weights(int N, const float* __restrict__ W, const float* __restrict__ kp,
                                                           int k_stride, float* Wk, float* WkT, int ldw,
                                                           float* Wk_hi, float* Wk_lo, float* WkT_hi, float* WkT_lo) {
     __shared__ float tile[32][33];
@@ -1499,7 +1500,7 @@ __global__ void __launch_bounds__(256) k_prepare_weights(int N, const float* __r
 }
 
 // binary16 variant: hi/lo of k_i W[i][j] * 2^e and/or of its transpose; e from the tracked maximum of |kW|
-__global__ void __launch_bounds__(256) k_prepare_weights_f16(int N, const float* __restrict__ W, const float* __restrict__ kp, int k_stride, int ldw,
+static __global__ void __launch_bounds__(256) k_prepare_weights_f16(int N, const float* __restrict__ W, const float* __restrict__ kp, int k_stride, int ldw,
                                                               void* Wk_hi, void* Wk_lo, void* WkT_hi, void* WkT_lo, ScaleRef sc) {
     __shared__ float tile[32][33];
     const float scale = exp2i(scale_expo(sc));
@@ -1558,7 +1559,7 @@ __global__ void __launch_bounds__(128) k_readout_grad(int N, int B, int T, int S
 }
 
 // dW[i][j] = k_i * dWraw[i][j] ;  dk[i] = sum_j dWraw[i][j] * W[i][j]        (one block per row; 16-byte accesses when N % 4 == 0)
-__global__ void __launch_bounds__(256) k_finish_wgrad(int N, const float* __restrict__ dWraw, int ldr, const float* __restrict__ W,
+static __global__ void __launch_bounds__(256) k_finish_wgrad(int N, const float* __restrict__ dWraw, int ldr, const float* __restrict__ W,
                                                        const float* __restrict__ kp, int k_stride, float* dW, float* dk, int n_slices) {
     __shared__ float red[9];
     const int i = blockIdx.x;
@@ -1590,7 +1591,7 @@ __global__ void __launch_bounds__(256) k_finish_wgrad(int N, const float* __rest
     }
 }
 
-__global__ void __launch_bounds__(256) k_fill(float* p, size_t n, float v) {
+static __global__ void __launch_bounds__(256) k_fill(float* p, size_t n, float v) {
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) p[idx] = v;
 }
 

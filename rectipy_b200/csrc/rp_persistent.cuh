@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_fwd(PersistFwdArgs a)
 }
 
 // out[j][e] = scale * sum_rb part[j][rb][e]   (fixed order over the row blocks)
-__global__ void __launch_bounds__(256) k_sum_row_blocks(const float* __restrict__ part, int n_rec, int n_rb, int width, float scale, float* out) {
+static __global__ void __launch_bounds__(256) k_sum_row_blocks(const float* __restrict__ part, int n_rec, int n_rb, int width, float scale, float* out) {
     const size_t total = (size_t)n_rec * width;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const size_t j = idx / width, e = idx - j * width;
@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_bwd(PersistBwdArgs a)
 }
 
 // dWraw^T -> dW = diag(k) dWraw and dk  (persistent path keeps the weight gradient transposed: row = source neuron j)
-__global__ void __launch_bounds__(256) k_finish_wgrad_T(int N, const float* __restrict__ dWrawT, int ldr, const float* __restrict__ W,
+static __global__ void __launch_bounds__(256) k_finish_wgrad_T(int N, const float* __restrict__ dWrawT, int ldr, const float* __restrict__ W,
                                                         const float* __restrict__ kp, int k_stride, float* dW, float* dk, int n_slices) {
     __shared__ float tile[32][33];
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;   // bx: i base, by: j base (rows of dWrawT)
