@@ -59,6 +59,20 @@ def sweep():
 tg = gpu_time(sweep)
 rows.append((f"sweep QIF fwd N={n} B={Bs} T={T} (readout, S=10)", n * Bs * T / tg, float("nan"), tg / T * 1e6))
 
+# ---- sweep, 64 trials: neither the tensor-core shapes (multiples of 128) nor the persistent kernels hold it -> precision="auto" pads to 1024 x 128
+Bs2 = 64
+nets2 = rp.Network(dt, device="cuda:0", batch=Bs2)
+nets2.add_diffeq_node("qif", "neuron_model_templates.spiking_neurons.qif.qif", weights=Ws, source_var="s", target_var="s_in", input_var="I_ext",
+                      output_var="s", spike_var="spike", reset_var="v", op="qif_op", node_vars={"eta": orc.lorentzian_etas(n)})
+nets2.add_func_node("inp", 2, "identity"); nets2.add_edge("inp", "qif", weights=rng.standard_normal((n, 2)))
+nets2.add_func_node("out", 3, "identity"); nets2.add_edge("qif", "out", weights=rng.standard_normal((3, n)) / np.sqrt(n))
+xs2 = torch.randn(T, Bs2, 2, device="cuda") * 5 + 8; y0s2 = nets2.state
+def sweep2():
+    nets2.reset(y0s2); return nets2.run(xs2, sampling_steps=10, verbose=False, enable_grad=False)
+tg = gpu_time(sweep2)
+rows.append((f"sweep QIF fwd N={n} B={Bs2} T={T} (readout, S=10; padded to 1024 x 128, tcgen05)", n * Bs2 * T / tg, float("nan"), tg / T * 1e6))
+del nets2, xs2
+
 # ---- C2: LI-tanh rate net BPTT, N=200, dt=1e-2, T=10000 (documentation/bptt_rate_neurons.py) -----------------------
 for n in (200, 4096):
     T = 10000 if n == 200 else 500

@@ -2,6 +2,8 @@
 
   python tools/summarize_ncu.py launches gpurun_out/launches_r1.csv profiles/r1_launches.md "<command>"
   python tools/summarize_ncu.py full     gpurun_out/prof_gemm_r1.ncu-rep profiles/r1_gemm_full.md
+  python tools/summarize_ncu.py rawcsv   gpurun_out/full_raw.csv profiles/r2_kernels_full.md "<command>"     (raw page exported on the box:
+                                         one column per kernel KIND = (name, grid size), the median-duration launch of the kind)
 """
 import collections
 import csv
@@ -78,8 +80,55 @@ def full(src, dst):
         print("traffic summary skipped:", exc)
 
 
+WANT2 = WANT[:8] + ["smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
+                    "launch__grid_size", "launch__block_size", "launch__cluster_size", "launch__shared_mem_per_block_dynamic",
+                    "launch__shared_mem_per_block_static", "lts__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+
+
+def rawcsv(src, dst, cmd, persist_steps=1):
+    import json, os
+    rows = list(csv.reader(l for l in open(src) if not l.startswith("==")))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    kinds = collections.OrderedDict()
+    for r in rows[2:]:
+        if len(r) < len(hdr):
+            continue
+        name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "").replace("rp::", "")
+        kinds.setdefault((name[:70], r[idx["launch__grid_size"]]), []).append(r)
+
+    def val(r, key):
+        return float(r[idx[key]].replace(",", "")) if r[idx[key]] not in ("", "n/a") else float("nan")
+
+    def scale(key):
+        u = units[idx[key]].lower()
+        return 1e9 if u.startswith("g") else 1e6 if u.startswith("m") else 1e3 if u.startswith("k") else 1.0
+    cols, traffic = [], {}
+    for (name, grid), rs in kinds.items():
+        rs = sorted(rs, key=lambda r: val(r, "gpu__time_duration.sum"))
+        cols.append((f"{name} grid={grid} (n={len(rs)})", rs[len(rs) // 2]))
+        traffic[f"{name} grid={grid}"] = sum(val(r, "dram__bytes_read.sum") * scale("dram__bytes_read.sum") +
+                                             val(r, "dram__bytes_write.sum") * scale("dram__bytes_write.sum") for r in rs) / len(rs)
+    with open(dst, "w") as f:
+        f.write("# ncu --set full --clock-control none, one column per kernel kind (name, grid), the median-duration launch of the kind; every cell carries its own unit\n\n")
+        f.write(f"command: `{cmd}`\n\n")
+        f.write("| metric | " + " | ".join(c[0] for c in cols) + " |\n|---|" + "---:|" * len(cols) + "\n")
+        for w in WANT2:
+            if w in idx:
+                f.write(f"| {w} | " + " | ".join(f"{c[1][idx[w]]} {units[idx[w]]}" for c in cols) + " |\n")
+    top = max(traffic, key=lambda k: ("fwd" in k, traffic[k]))
+    per_step = traffic[top] / (persist_steps if "persist" in top else 1)
+    with open(os.path.join(os.path.dirname(dst), "ncu_traffic.json"), "w") as fh:
+        json.dump({"kernel": top, "dram_bytes_per_launch": per_step, "per_kernel": traffic, "source": os.path.basename(dst),
+                   "note": "dominant kernel: bytes per Euler step (the persistent launch of the capture covered %d steps); per_kernel: bytes per launch" % persist_steps},
+                  fh, indent=1)
+    print("wrote", dst, "and ncu_traffic.json")
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "rawcsv":
+        rawcsv(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "", int(sys.argv[5]) if len(sys.argv) > 5 else 1)
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
     else:
         full(sys.argv[2], sys.argv[3])
