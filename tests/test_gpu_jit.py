@@ -332,3 +332,46 @@ def test_multi_spike_reset_net_batched_matches_per_trial_oracle(ei_template):
     e_out = rel_err(out.detach().cpu().numpy(), out_ref)
     print("multispike batched", f"out {e_out:.2e}", {k_: f"{v:.2e}" for k_, v in errs.items()})
     assert e_out <= 1e-4 and all(v <= 2e-3 for v in errs.values()), errs
+
+
+def test_generated_fields_single_steps_sweeps_and_uncoupled_nodes(user_templates):
+    """The rest of the node protocol on generated kernels: `node.forward(x)` (T = 1 calls), per-trial parameter sweeps, a node without
+    recurrent weights (`weights=None, N=n`, rectipy/nodes.py:134-140)."""
+    import rectipy_b200 as rp
+    n, dt = 12, 0.05
+    rng = np.random.default_rng(3)
+    W = rng.standard_normal((n, n)) / np.sqrt(n)
+    p = dict(g=0.5, a=0.7, b=0.8, tau_w=12.5, beta=2.0)
+    # (a) single steps through node.forward, state protocol
+    net = rp.Network(dt, device="cuda:0")
+    node = net.add_diffeq_node("rnn", "mymodels.custom.fhn", weights=W, source_var="r", target_var="r_in", input_var="I_ext", output_var="v")
+    onode = _fhn_oracle(n, W, dt, p, None)
+    for step in range(6):
+        x = rng.standard_normal(n)
+        out = node.forward(torch.tensor(x, dtype=torch.float32, device="cuda:0")).cpu().numpy()
+        ref = onode.forward(torch.tensor(x)).detach().numpy()
+        assert rel_err(out, ref) <= 1e-5, step
+    assert rel_err(node.y.cpu().numpy(), onode.y.detach().numpy()) <= 1e-5
+    assert rel_err(node["w"].cpu().numpy(), onode.get("w").detach().numpy()) <= 1e-5
+    # (b) a sweep: every trial its own `a` (shared over neurons) and its own per-neuron `tau_w`
+    B, T = 5, 80
+    a_sweep = rng.uniform(0.5, 0.9, (B, 1))
+    tw_sweep = rng.uniform(8.0, 16.0, (B, n))
+    net = rp.Network(dt, device="cuda:0", batch=B)
+    net.add_diffeq_node("rnn", "mymodels.custom.fhn", weights=W, source_var="r", target_var="r_in", input_var="I_ext", output_var="v",
+                        node_vars={"fhn_op/a": a_sweep, "fhn_op/tau_w": tw_sweep})
+    x = rng.standard_normal((T, B, n)) * 0.3
+    out = net.run(x, verbose=False).to_numpy("out")
+    for b in range(B):
+        onode = _fhn_oracle(n, W, dt, dict(p, a=float(a_sweep[b, 0]), tau_w=tw_sweep[b]), None)
+        ref = torch.stack(orc.OracleNet(onode).run(torch.tensor(x[:, b, :]), enable_grad=False)["out"]).numpy()
+        assert rel_err(out[:, b, :], ref) <= 1e-5, b
+    # (c) no recurrent weights
+    net = rp.Network(dt, device="cuda:0")
+    net.add_diffeq_node("rnn", "mymodels.custom.fhn", N=n, input_var="I_ext", output_var="w")
+    x1 = rng.standard_normal((40, n))
+    out = net.run(x1, verbose=False).to_numpy("out")
+    onode = _fhn_oracle(n, np.zeros((n, n)), dt, p, None)
+    onode.start, onode.stop = n, 2 * n
+    ref = torch.stack(orc.OracleNet(onode).run(torch.tensor(x1), enable_grad=False)["out"]).numpy()
+    assert rel_err(out, ref) <= 1e-5
