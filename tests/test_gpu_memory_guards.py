@@ -50,7 +50,8 @@ class GuardedAlloc:
 
 
 CASES = [("qif", 256, 256, "auto", 60), ("qif_sfa", 128, 128, "3xtf32", 40), ("qif", 1000, 1, "fp32", 80), ("lif", 130, 12, "fp32", 60),
-         ("li_tanh", 203, 70, "fp32", 30), ("iku", 128, 128, "auto", 30)]
+         ("li_tanh", 203, 70, "fp32", 30), ("iku", 128, 128, "auto", 30),
+         ("qif", 600, 40, "auto", 40)]         # ragged shape padded onto the tensor-core path (640 x 128): the guarded buffers are the padded ones
 
 
 @pytest.mark.parametrize("model,n,B,prec,T", CASES)
@@ -91,6 +92,42 @@ def test_engine_stays_inside_caller_buffers(model, n, B, prec, T, monkeypatch):
     monkeypatch.setattr(engine.torch, "empty_like", guard.empty_like)
     obs = net.run(x if B > 1 else x[:, 0], sampling_steps=3, cutoff=2, verbose=False, enable_grad=True,
                   record_vars=[("rnn", f"{op}/v", False), ("rnn", f"{op}/v", True)] if prec == "fp32" else [])
+    out = torch.stack(obs["out"])
+    out.square().sum().backward()
+    torch.cuda.synchronize()
+    monkeypatch.undo()
+    guard.check()
+    assert torch.isfinite(out).all() and torch.isfinite(node["weights"].grad).all()
+    engine.clear_plans()
+
+
+@pytest.mark.parametrize("template,B,spiking", [("fhn", 3, False), ("adex", 5, True)])
+def test_generated_kernels_stay_inside_caller_buffers(template, B, spiking, tmp_path, monkeypatch):
+    """The run-time compiled step / adjoint kernels (rectipy_b200/jit.py) under the same canary guard."""
+    import rectipy_b200 as rp
+    from rectipy_b200 import engine
+    from test_gpu_jit import YAML
+    (tmp_path / "mymodels").mkdir()
+    (tmp_path / "mymodels" / "custom.yaml").write_text(YAML)
+    monkeypatch.chdir(tmp_path)
+    engine.clear_plans()
+    n, m, k, T, dt = 37, 2, 3, 50, 0.01
+    rng = np.random.default_rng(B)
+    W = rng.standard_normal((n, n)) / np.sqrt(n)
+    net = rp.Network(dt, device="cuda:0", batch=B)
+    if spiking:
+        node = net.add_diffeq_node("rnn", "mymodels.custom.adex", weights=W, source_var="s", target_var="s_in", input_var="I_ext", output_var="s",
+                                   spike_var="spike", reset_var="v", train_params=["weights", "adex_op/b"], spike_threshold=2.0, spike_reset=-1.5)
+    else:
+        node = net.add_diffeq_node("rnn", "mymodels.custom.fhn", weights=W, source_var="r", target_var="r_in", input_var="I_ext", output_var="v",
+                                   train_params=["weights", "fhn_op/a"])
+    net.add_func_node("inp", m, "identity"); net.add_edge("inp", "rnn", weights=rng.standard_normal((n, m)), train="gd")
+    net.add_func_node("out", k, "identity"); net.add_edge("rnn", "out", weights=rng.standard_normal((k, n)) / np.sqrt(n), train="gd")
+    x = (np.sin(np.arange(T)[:, None, None] * 0.3 + rng.uniform(0, 6.28, (1, B, m))) + 1.2).astype(np.float32)
+    guard = GuardedAlloc()
+    monkeypatch.setattr(engine.torch, "empty", guard.empty)
+    monkeypatch.setattr(engine.torch, "empty_like", guard.empty_like)
+    obs = net.run(x, sampling_steps=3, cutoff=2, verbose=False, enable_grad=True, record_vars=[("rnn", "w", True)])
     out = torch.stack(obs["out"])
     out.square().sum().backward()
     torch.cuda.synchronize()
