@@ -176,10 +176,26 @@ def param_slot_table(params: List[str]) -> Dict[str, int]:
     return {n: slots[i] for i, n in enumerate(params)}
 
 
+_PRINTER = None
+
+
 def _ccode(expr) -> str:
-    import sympy
-    from sympy.codegen.ast import real, float32
-    return sympy.ccode(expr, type_aliases={real: float32})
+    """float32 C code of a sympy expression; small integer powers become products (`v^2` of the templates is `v*v`, as PyRates'
+    torch code computes it -- not powf)."""
+    global _PRINTER
+    if _PRINTER is None:
+        from sympy.codegen.ast import real, float32
+        from sympy.printing.c import C99CodePrinter
+
+        class Printer(C99CodePrinter):
+            def _print_Pow(self, e):
+                if e.exp.is_Integer and 2 <= abs(int(e.exp)) <= 4:
+                    base = self.parenthesize(e.base, 1000)        # atoms stay bare, everything else is bracketed
+                    prod = "*".join([base] * abs(int(e.exp)))
+                    return f"({prod})" if int(e.exp) > 0 else f"(1.0F/({prod}))"
+                return super()._print_Pow(e)
+        _PRINTER = Printer({"type_aliases": {real: float32}})
+    return _PRINTER.doprint(expr)
 
 
 def build_program(fld: JitField, source_var: str, target_var: Optional[str], input_var: Optional[str],

@@ -269,7 +269,8 @@ def test_multi_spike_reset_net_matches_reference_fixture(ei_template):
     import os
     import rectipy_b200 as rp
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "multispike_ei.npz"))
-    meta = eval(str(z["meta"]))
+    import ast
+    meta = ast.literal_eval(str(z["meta"]))
     n, dt, S = meta["n"], meta["dt"], meta["S"]
     node_vars = {"eta_e": z["param_eta_e"], "eta_i": z["param_eta_i"], **{q: meta[q] for q in ("tau_e", "J_ee", "J_ei", "tau_i", "J_ie", "tau_s")}}
     net, node = _ei_engine(rp, z, n, z["in_W"], dt, 1, node_vars, meta["train"], meta["thresh"], meta["reset"], z["in_w_in"], z["in_w_out"])
