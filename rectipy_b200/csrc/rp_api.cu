@@ -89,7 +89,7 @@ struct rp_plan {
     float* dwout_part = nullptr;   // fused reverse kernel: [B/32][k][N] partial sums of dW_out
     // RP_JIT: module with the run-time compiled kernels of the template
     CUmodule jit_mod = nullptr;
-    CUfunction jit_init_src = nullptr, jit_fwd = nullptr, jit_adj = nullptr;
+    CUfunction jit_init_src = nullptr, jit_fwd = nullptr, jit_adj = nullptr, jit_fwd_rows = nullptr;
     // optional per-stage timing (rp_plan_stage_timing): a CUDA event on the launching stream before every launch of the step loops
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -488,7 +488,7 @@ int rp_plan_create(const rp_desc* d, rp_plan** out) {
         rc |= plan_alloc(p, &p->Wk, (size_t)N * p->ldw);
         rc |= plan_alloc(p, &p->WkT, (size_t)N * p->ldw);
         rc |= plan_alloc(p, &p->g, plane);
-        if (src_plane_of(*d) < 0) rc |= plan_alloc(p, &p->src, plane);
+        if (src_plane_of(*d) < 0) rc |= plan_alloc(p, &p->src, (d->model == RP_JIT ? 2 : 1) * plane);      // RP_JIT: double buffered (row kernel)
     } else {
         size_t bytes = 0;
         rc |= rp::tc_workspace_create(&p->tc, N, B, f16, !spiking(d->model), &bytes);
@@ -541,6 +541,7 @@ int rp_plan_set_jit_module(rp_plan* p, const void* image, long long nbytes) {
     if (getf(&p->jit_fwd, p->jit_mod, "rp_jit_fwd_step") != CUDA_SUCCESS || getf(&p->jit_adj, p->jit_mod, "rp_jit_adj_step") != CUDA_SUCCESS ||
         getf(&p->jit_init_src, p->jit_mod, "rp_jit_init_src") != CUDA_SUCCESS)
         return fail("rp_plan_set_jit_module: the image does not define rp_jit_fwd_step / rp_jit_adj_step / rp_jit_init_src");
+    if (getf(&p->jit_fwd_rows, p->jit_mod, "rp_jit_fwd_step_rows") != CUDA_SUCCESS) p->jit_fwd_rows = nullptr;      // optional
     return 0;
 }
 
@@ -725,9 +726,18 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         if (!p->use_tc) {
             // u[b][i] = sum_j (kW)[i][j] src_t[b][j], then the element-wise step
             const float* srcp = src_plane >= 0 ? cur + (size_t)src_plane * plane : p->src;
-            if (gemm_fp32(p, true, N, B, N, p->Wk, p->ldw, srcp, N, p->u, p->ldu, 0, st, &p->launches)) return 1;
-            if (jit) { if (jit_launch(p->jit_fwd, ew_grid(p, plane), 256, &fa, st)) return 1; }
-            else RP_DISPATCH_MODEL(d.model, (rp::k_fwd_step<M_><<<ew_grid(p, plane), 256, 0, st>>>(fa)));
+            if (jit && p->jit_fwd_rows && B <= 8 && !getenv("RP_JIT_NO_ROWS")) {
+                // few trials: the generated kernel forms u = W . src itself (one warp per neuron row) -- one launch per step instead of two.
+                // src_{t+1} goes to the other half of the double-buffered source (this launch still reads src_t)
+                rp::JitRowsArgs ra;
+                ra.a = fa; ra.W = p->Wk; ra.ldw = p->ldw; ra.src = srcp;
+                if (src_plane < 0) { ra.src = p->src + (size_t)(t & 1) * plane; ra.a.src_next = p->src + (size_t)((t + 1) & 1) * plane; }
+                if (jit_launch(p->jit_fwd_rows, (N + 7) / 8, 256, &ra, st)) return 1;
+            } else {
+                if (gemm_fp32(p, true, N, B, N, p->Wk, p->ldw, srcp, N, p->u, p->ldu, 0, st, &p->launches)) return 1;
+                if (jit) { if (jit_launch(p->jit_fwd, ew_grid(p, plane), 256, &fa, st)) return 1; }
+                else RP_DISPATCH_MODEL(d.model, (rp::k_fwd_step<M_><<<ew_grid(p, plane), 256, 0, st>>>(fa)));
+            }
             ++p->launches;
             RP_LAUNCH_CHECK();
         } else {

@@ -95,4 +95,12 @@ struct AdjArgs {
 };
 
 
+// run-time compiled forward step with the recurrent contraction inside (few trials: one warp per neuron row, one launch per step)
+struct JitRowsArgs {
+    FwdStepArgs a;
+    const float* W;        // [N][ldw]  recurrent weights (coupling constants live in the equations)
+    int ldw;
+    const float* src;      // [B][N]    source values of the step
+};
+
 }  // namespace rp

@@ -383,6 +383,60 @@ extern "C" __global__ void __launch_bounds__(256) rp_jit_fwd_step(rp::FwdStepArg
     }}
 }}
 
+// Few trials (B <= 8): the same step with the recurrent contraction inside -- one warp per neuron row forms u_b = W[i][:] . src_b for
+// every trial (coalesced row read, trial vectors from L1/L2), a shuffle tree reduces, lane b steps (trial b, neuron i).
+extern "C" __global__ void __launch_bounds__(256) rp_jit_fwd_step_rows(rp::JitRowsArgs r) {{
+    const rp::FwdStepArgs& a = r.a;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= a.N) return;
+    const size_t plane = (size_t)a.B * a.N;
+    float acc[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[b] = 0.f;
+    const float* wrow = r.W + (size_t)i * r.ldw;
+    if ((a.N & 3) == 0) {{                                   // 16-byte loads, several chunks in flight per lane (the loop is latency-bound otherwise)
+        const float4* w4 = reinterpret_cast<const float4*>(wrow);
+        const int n4 = a.N >> 2;
+#pragma unroll 4
+        for (int j = lane; j < n4; j += 32) {{
+            const float4 w = __ldg(w4 + j);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) if (b < a.B) {{
+                const float4 s = *reinterpret_cast<const float4*>(r.src + (size_t)b * a.N + 4 * j);
+                acc[b] = fmaf(w.x, s.x, fmaf(w.y, s.y, fmaf(w.z, s.z, fmaf(w.w, s.w, acc[b]))));
+            }}
+        }}
+    }} else {{
+#pragma unroll 8
+        for (int j = lane; j < a.N; j += 32) {{
+            const float w = __ldg(wrow + j);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) if (b < a.B) acc[b] = fmaf(w, r.src[(size_t)b * a.N + j], acc[b]);
+        }}
+    }}
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+    float u = 0.f;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) if (lane == b) u = acc[b];
+    if (lane < a.B) {{
+        const int b = lane;
+        const size_t idx = (size_t)b * a.N + i;
+        float y[NSV], y1[NSV];
+#pragma unroll
+        for (int k = 0; k < NSV; ++k) y[k] = a.y_cur[(size_t)k * plane + idx];
+        const float Iin = rp::input_current(a.in_mode, a.m, a.x_t, a.W_in, a.N, b, i);
+        jit_step(a.mp, i, b, y, u, Iin, a.theta, a.v_reset, a.dt, y1);
+        if (a.urec_out) a.urec_out[idx] = u;
+#pragma unroll
+        for (int k = 0; k < NSV; ++k) a.y_next[(size_t)k * plane + idx] = y1[k];
+        if (a.src_next) a.src_next[idx] = jit_src(a.mp, i, b, y1);
+    }}
+}}
+
 // gradient of the record window into the output variable (+ dW_out): adj[out] += W_out^T e (readout) | e (dense)
 __device__ __forceinline__ void jit_out_grad(const rp::AdjArgs& a, const float* e, float e_scale, int b, int i, size_t idx, float yout, float* adj) {{
     if (a.out_mode == RP_OUT_DENSE) {{ adj[a.out_var] += __ldg(e + idx) * e_scale; return; }}
