@@ -691,6 +691,8 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         if (prc == 1) return fail("rp_forward: %s", rp::tc_last_error());
         if (prc == 0) { persisted = true; ++p->launches; }
     }
+    const int env_no_lean = getenv("RP_NO_FWD_LEAN") ? 1 : 0;           // read once per call, not per step
+    const bool jit_rows = jit && p->jit_fwd_rows && B <= 8 && !getenv("RP_JIT_NO_ROWS");
     for (int t = 0; t < (persisted ? 0 : a->T); ++t) {
         float* cur = slot_ptr(t);
         float* nxt = slot_ptr(t + 1);
@@ -722,11 +724,11 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         }
         fa.per_trial = p->per_trial ? 1 : 0;
         stage_mark(p, ST_FWD, st);
-        fa.no_lean = getenv("RP_NO_FWD_LEAN") ? 1 : 0;
+        fa.no_lean = env_no_lean;
         if (!p->use_tc) {
             // u[b][i] = sum_j (kW)[i][j] src_t[b][j], then the element-wise step
             const float* srcp = src_plane >= 0 ? cur + (size_t)src_plane * plane : p->src;
-            if (jit && p->jit_fwd_rows && B <= 8 && !getenv("RP_JIT_NO_ROWS")) {
+            if (jit_rows) {
                 // few trials: the generated kernel forms u = W . src itself (one warp per neuron row) -- one launch per step instead of two.
                 // src_{t+1} goes to the other half of the double-buffered source (this launch still reads src_t)
                 rp::JitRowsArgs ra;
