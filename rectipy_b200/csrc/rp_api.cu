@@ -676,6 +676,7 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         ps.y_hist = a->history; ps.hslot = hslot; ps.y_pp = p->pp; ps.slot = slot;
         ps.x = a->x; ps.x_stride = x_stride; ps.out_rec = a->out_rec; ps.out_stride = out_stride;
         ps.amax_src = spk ? p->tc.amax_src : nullptr; ps.sc_static = sc_rate;
+        { const char* sk = getenv("RP_FWD_SKEW_US"); ps.skew_ns = sk ? atoi(sk) * 1000 : 0; }
         ps.nsv = nsv; ps.plane = plane; ps.urec = (rp::is_ik(d.model) && a->history) ? 1 : 0;
         int prc = 0;
         auto fill0 = [&](auto& epi) {

@@ -814,6 +814,7 @@ struct FwdPersist {
     void* src_hi[2]; void* src_lo[2];
     int nsv; size_t plane; int urec;        // ik: the recurrent drive goes into checkpoint plane nsv of slot t
     unsigned int* done;            // [groups + 1] zero-initialised
+    int skew_ns;                   // trial group g starts g * skew_ns late: the HBM-bound epilogues of the groups then do not coincide
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
@@ -880,6 +881,10 @@ k_gemm_fwd_persist(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         // ===== TMA producer: one elected thread, all steps =====
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
+            if (ps.skew_ns > 0 && by > 0) {
+                const unsigned long long t_start = trace_now(), wait = (unsigned long long)by * (unsigned long long)ps.skew_ns;
+                while (trace_now() - t_start < wait) __nanosleep(500);
+            }
             for (int t = 0; t < ps.T; ++t) {
                 const CUtensorMap* mb_hi = (t & 1) ? &tmB1_hi : &tmB0_hi;
                 const CUtensorMap* mb_lo = (t & 1) ? &tmB1_lo : &tmB0_lo;
