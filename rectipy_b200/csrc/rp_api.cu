@@ -150,6 +150,7 @@ struct JitInitSrcArgs { int N, B; const float* y; rp::ModelParams mp; float* src
 
 int plan_alloc(rp_plan* p, float** ptr, size_t n_floats) {
     RP_CUDA(cudaMalloc(reinterpret_cast<void**>(ptr), n_floats * sizeof(float)));
+    if (const char* poison = getenv("RP_POISON_ALLOC")) RP_CUDA(cudaMemset(*ptr, atoi(poison), n_floats * sizeof(float)));      // debug: uninitialised reads show up
     p->ws_bytes += n_floats * sizeof(float);
     return 0;
 }

@@ -370,7 +370,7 @@ struct EpiFwd {
                     if (l == 0 && smax > 0.f) atomic_max_nonneg(a.amax_out, smax);
                 }
             }
-        } else if (out_rec_j != nullptr) {
+        } else if (out_rec_j != nullptr && p0 == a.N) {      // (a padding tile further out -- CTA-pair grid -- has nothing to do)
             // readout rows: row kk of this tile is W_out[kk]; o_t[b][kk] accumulates into the open record window
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
@@ -1056,6 +1056,205 @@ __global__ void __launch_bounds__(256) k_split_matrix(int rows, int cols, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant of the persistent forward kernel (opt-in: RP_FWD_CG2=1): the protocol of
+// k_gemm_fwd_persist with the operand delivery of k_gemm_split3_cg2.  Two row tiles of the SAME trial group form a cluster and run
+// M = 256 MMAs; each CTA loads its own 128 rows of kW and HALF of the source operand (32 instead of 48 KB of shared-memory fill per
+// CTA and K block), keeps its own 128 x 256 accumulator and runs the unchanged epilogue on it.  grid.x is padded to an even number of
+// row tiles (a tile past the readout rows loads zero rows and has nothing to step, but takes part in every counter).
+// ---------------------------------------------------------------------------------------------------------------------------
+template <class Epi>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_fwd_persist_cg2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                       const __grid_constant__ CUtensorMap tmB0_hi, const __grid_constant__ CUtensorMap tmB0_lo,      // 128-row boxes
+                       const __grid_constant__ CUtensorMap tmB1_hi, const __grid_constant__ CUtensorMap tmB1_lo,
+                       int num_k_blocks, const __grid_constant__ Epi epi0, const __grid_constant__ FwdPersist ps) {
+    using Cfg = TcCfg2;
+    constexpr int BQ = Cfg::BQ;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int CPT = Cfg::COLS_PER_THREAD;
+    constexpr int TC_BK = TcElt<true>::BK;
+    constexpr int TC_KC = TcElt<true>::KC;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);      // used in the leader only
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2] used in the leader only (both CTAs' epilogue warps arrive)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* tile_free_bar = tmem_empty_bar + 3;      // this CTA's epilogue has finished with the tile parked in ITS stage memory
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const bool leader = rank == 0;
+    const int bx = blockIdx.x, by = blockIdx.y;
+    const int p0 = bx * TC_BP, q0 = by * BQ;
+    const int qh = q0 + (int)rank * (BQ / 2);
+    const int num_chunks = (num_k_blocks + TC_KC - 1) / TC_KC;
+    const unsigned int writers = gridDim.x;
+    const unsigned int writers_all = writers * gridDim.y;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB0_hi); tma_prefetch_desc(&tmB0_lo);
+        tma_prefetch_desc(&tmB1_hi); tma_prefetch_desc(&tmB1_lo);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 2 * TC_EPI_WARPS); }
+        mbar_init(tile_free_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs), all steps =====
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = 0; t < ps.T; ++t) {
+                const CUtensorMap* mb_hi = (t & 1) ? &tmB1_hi : &tmB0_hi;
+                const CUtensorMap* mb_lo = (t & 1) ? &tmB1_lo : &tmB0_lo;
+                bool ready = (t == 0);
+                if (t > 0) mbar_wait(tile_free_bar, (uint32_t)((t - 1) & 1));       // own stage memory no longer holds the parked tile
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    tma_load_2d_cg2(sa, &tmA_hi, &full_bar[stage], kb * TC_BK, p0);
+                    tma_load_2d_cg2(sa + Cfg::A_BYTES, &tmA_lo, &full_bar[stage], kb * TC_BK, p0);
+                    if (!ready) {
+                        spin_until(ps.done + by, writers * (unsigned int)t);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        ready = true;
+                    }
+                    tma_load_2d_cg2(sa + 2 * Cfg::A_BYTES, mb_hi, &full_bar[stage], kb * TC_BK, qh);
+                    tma_load_2d_cg2(sa + 2 * Cfg::A_BYTES + Cfg::BH_BYTES, mb_lo, &full_bar[stage], kb * TC_BK, qh);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one elected thread of the LEADER CTA, the chunk counter runs on across the steps =====
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc(true, 2 * TC_BP, BQ);
+            int stage = 0; uint32_t phase = 0;
+            int chunk_g = 0;
+            for (int t = 0; t < ps.T; ++t) {
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    const int kin = kb % TC_KC;
+                    const int buf = chunk_g & 1;
+                    if (kin == 0) {
+                        mbar_wait(&tmem_empty_bar[buf], ((chunk_g >> 1) & 1) ^ 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    mbar_wait(&full_bar[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BQ);
+                        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                        const uint64_t dA_hi = make_sw128_kmajor_desc(sa);
+                        const uint64_t dA_lo = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
+                        const uint64_t dB_hi = make_sw128_kmajor_desc(sa + 2 * Cfg::A_BYTES);
+                        const uint64_t dB_lo = make_sw128_kmajor_desc(sa + 2 * Cfg::A_BYTES + Cfg::BH_BYTES);
+#pragma unroll
+                        for (int k = 0; k < TcElt<true>::KSTEPS; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            umma_ss_cg2(tmem_d, dA_lo + adv, dB_hi + adv, idesc, (kin > 0 || k > 0) ? 1u : 0u);
+                            umma_ss_cg2(tmem_d, dA_hi + adv, dB_lo + adv, idesc, 1u);
+                            umma_ss_cg2(tmem_d, dA_hi + adv, dB_hi + adv, idesc, 1u);
+                        }
+                        umma_commit_cg2_mc(&empty_bar[stage]);
+                        if (kin == TC_KC - 1 || kb == num_k_blocks - 1) umma_commit_cg2_mc(&tmem_full_bar[buf]);
+                    }
+                    __syncwarp();
+                    if (kin == TC_KC - 1 || kb == num_k_blocks - 1) ++chunk_g;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps (both CTAs): own 128 rows x 256 trials, exactly as in k_gemm_fwd_persist =====
+        const int ew = warp - 2;
+        const int lane_base = (warp & 3) * 32;
+        const int half = ew >> 2;
+        const bool f16_spk = ps.amax_src != nullptr;
+        int chunk_g = 0;
+        const int S_ = max(ps.S, 1);
+        const int w_r0 = ((ps.cutoff + S_ - 1) / S_) * S_;
+        int w_j, w_start, w_rec;
+        if (ps.t_offset <= w_r0) { w_j = 0; w_start = ps.cutoff; w_rec = w_r0; }
+        else { w_j = (ps.t_offset - w_r0 + S_ - 1) / S_; w_rec = w_r0 + w_j * S_; w_start = w_rec - S_ + 1; }
+        for (int t = 0; t < ps.T; ++t) {
+            float acc[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+            for (int chunk = 0; chunk < num_chunks; ++chunk, ++chunk_g) {
+                const int buf = chunk_g & 1;
+                mbar_wait(&tmem_full_bar[buf], (chunk_g >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(buf * BQ + half * CPT);
+#pragma unroll
+                for (int c = 0; c < CPT / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + (uint32_t)(c * 32), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[buf]);
+            }
+            Epi e = epi0;
+            if (f16_spk) e.sB = t == 0 ? ScaleRef{ps.amax_src, 0.f, CV_HSRC} : ScaleRef{ps.amax_src + (t - 1), 1.f, CV_HSRC};
+            else e.sB = ps.sc_static;
+            if (t > 0 && f16_spk) { if (lane == 0) spin_until(ps.done + gridDim.y, writers_all * (unsigned int)t); __syncwarp(); }
+            const float2 usc = e.unscale(p0);
+            float* tile = reinterpret_cast<float*>(smem);
+            {
+                float* my = tile + (size_t)(half * CPT) * TC_BP + lane_base + lane;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) my[j * TC_BP] = acc[j] * usc.x * usc.y;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float* cur = ps.y_hist ? ps.y_hist + (size_t)t * ps.hslot : ps.y_pp + (size_t)(t & 1) * ps.slot;
+            float* nxt = ps.y_hist ? const_cast<float*>(ps.y_hist) + (size_t)(t + 1) * ps.hslot : ps.y_pp + (size_t)((t + 1) & 1) * ps.slot;
+            e.a.y_cur = cur; e.a.y_next = nxt;
+            e.a.x_t = ps.x ? ps.x + (size_t)t * ps.x_stride : nullptr;
+            e.a.src_hi = ps.src_hi[(t + 1) & 1]; e.a.src_lo = ps.src_lo[(t + 1) & 1];
+            e.a.urec_out = ps.urec ? const_cast<float*>(cur) + (size_t)ps.nsv * ps.plane : nullptr;
+            if (f16_spk) { e.a.sc_out = ScaleRef{ps.amax_src + t, 1.f, CV_HSRC}; e.a.amax_out = ps.amax_src + (t + 1); }
+            else { e.a.sc_out = ps.sc_static; e.a.amax_out = nullptr; }
+            const int tg = ps.t_offset + t;
+            if (tg > w_rec) { ++w_j; w_start = w_rec + 1; w_rec += S_; }
+            const bool in_win = tg >= ps.cutoff && w_rec < ps.T_total;
+            e.out_rec_j = (ps.readout && in_win && ps.out_rec) ? ps.out_rec + (size_t)w_j * ps.out_stride : nullptr;
+            e.win_first = (tg == w_start); e.win_close = (tg == w_rec);
+            e.inv_len = in_win ? 1.0f / (float)(w_rec - w_start + 1) : 0.f;
+            e.template run_tile<BQ, true>(p0, q0, tile, ew * 32 + lane, tile + (size_t)BQ * TC_BP);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (ew == 0 && lane == 0) {
+                mbar_arrive(tile_free_bar);
+                __threadfence();
+                atomicAdd(ps.done + by, 1u);
+                atomicAdd(ps.done + gridDim.y, 1u);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
@@ -1114,6 +1313,7 @@ struct TcWorkspace {
     CUtensorMap m_g_h[2], m_gT_h[2][2];                     // 128-row boxes of the B operands (CTA-pair kernel)
     void *src2_hi = nullptr, *src2_lo = nullptr;            // second source-operand buffer of the persistent multi-step forward kernel
     CUtensorMap m_src2[2];
+    CUtensorMap m_src_h[2], m_src2_h[2];                    // 128-row boxes of the two source buffers (CTA-pair persistent forward kernel)
     unsigned int* fwd_done = nullptr;                       // [B / bq_fwd + 1] step counters of that kernel
     int bq_fwd = 0, bq_wg = 0;
     CUtensorMap m_W[2], m_WT[2], m_src[2], m_g[2], m_gT[2][2], m_srcT[2][2];     // m_gT[buffer][hi/lo]
@@ -1122,7 +1322,8 @@ struct TcWorkspace {
 
 inline int tc_alloc(void** p, size_t bytes_wanted, size_t* bytes) {
     if (cudaMalloc(p, bytes_wanted) != cudaSuccess) RP_TC_FAIL("cudaMalloc of %zu bytes failed", bytes_wanted);
-    if (cudaMemset(*p, 0, bytes_wanted) != cudaSuccess) RP_TC_FAIL("cudaMemset failed");
+    const char* poison = getenv("RP_POISON_TC_ALLOC");        // debug only: these buffers are zero-initialised BY CONTRACT (scalars, counters, padding)
+    if (cudaMemset(*p, poison ? atoi(poison) : 0, bytes_wanted) != cudaSuccess) RP_TC_FAIL("cudaMemset failed");
     *bytes += bytes_wanted;
     return 0;
 }
@@ -1294,6 +1495,8 @@ inline int tc_workspace_ensure_persist(TcWorkspace* w, size_t* bytes) {
     if (tc_alloc(&w->src2_hi, bn, bytes) || tc_alloc(&w->src2_lo, bn, bytes)) return 1;
     if (tc_alloc(reinterpret_cast<void**>(&w->fwd_done), 64 * sizeof(unsigned int), bytes)) return 1;
     if (tc_make_map(&w->m_src2[0], w->src2_hi, w->f16, w->B, w->N, w->ldk, w->bq_fwd) || tc_make_map(&w->m_src2[1], w->src2_lo, w->f16, w->B, w->N, w->ldk, w->bq_fwd)) return 1;
+    if (tc_make_map(&w->m_src_h[0], w->src_hi, w->f16, w->B, w->N, w->ldk, 128) || tc_make_map(&w->m_src_h[1], w->src_lo, w->f16, w->B, w->N, w->ldk, 128)) return 1;
+    if (tc_make_map(&w->m_src2_h[0], w->src2_hi, w->f16, w->B, w->N, w->ldk, 128) || tc_make_map(&w->m_src2_h[1], w->src2_lo, w->f16, w->B, w->N, w->ldk, 128)) return 1;
     return 0;
 }
 // whole horizon in one cooperative launch (binary16 operands, 256-trial tiles); returns 2 when the grid cannot be co-resident
@@ -1301,20 +1504,46 @@ template <int MODEL, bool GEN>
 inline int tc_forward_persistent(TcWorkspace* w, const EpiFwd<MODEL, GEN>& epi, FwdPersist ps, int sm_count, cudaStream_t st) {
     using Epi = EpiFwd<MODEL, GEN>;
     auto kernel = k_gemm_fwd_persist<256, Epi, true>;
-    static bool attr_done = false;
+    auto kernel2 = k_gemm_fwd_persist_cg2<Epi>;
+    static bool attr_done = false, attr2_done = false;
+    const int gx1 = ps.n_row_tiles + (ps.readout ? 1 : 0);
+    if ((int)(w->B / 256) + 1 > 64) return 2;
+    ps.src_hi[0] = w->src_hi; ps.src_lo[0] = w->src_lo; ps.src_hi[1] = w->src2_hi; ps.src_lo[1] = w->src2_lo;
+    ps.done = w->fwd_done;
+    int kb = w->N / TcElt<true>::BK;
+    Epi e = epi;
+    // CTA-pair variant: opt-in (RP_FWD_CG2=1).  A/B on one box, alternating, 4 runs each: pass 30.43 vs 30.70 ms, forward stage 9.64 vs 9.82 ms
+    // per 100 steps, bit-identical results.  Not the default: in the two full-suite runs that had it enabled, a later, unrelated test (the
+    // finite-difference check of a rate network, which never runs this kernel) saw ten times its usual rounding noise; not reproduced with
+    // any subset of the tests, cause not found -- see DESIGN.md.  A grid of pairs that is not co-resident or a refused cluster launch
+    // falls through to the 1-CTA kernel.
+    if (getenv("RP_FWD_CG2")) {
+        if (!attr2_done) {
+            if (cudaFuncSetAttribute(kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg2::SMEM_BYTES) != cudaSuccess) RP_TC_FAIL("cudaFuncSetAttribute failed");
+            attr2_done = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((gx1 + 1) & ~1, w->B / 256); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcCfg2::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, kernel2, &cfg) == cudaSuccess && 2 * ncl >= (int)(cfg.gridDim.x * cfg.gridDim.y)) {
+            if (cudaMemsetAsync(w->fwd_done, 0, 64 * sizeof(unsigned int), st) != cudaSuccess) RP_TC_FAIL("cudaMemsetAsync failed");
+            if (cudaLaunchKernelEx(&cfg, kernel2, w->m_W[0], w->m_W[1], w->m_src_h[0], w->m_src_h[1], w->m_src2_h[0], w->m_src2_h[1], kb, e, ps) == cudaSuccess) return 0;
+        }
+        cudaGetLastError();
+    }
     if (!attr_done) {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES) != cudaSuccess) RP_TC_FAIL("cudaFuncSetAttribute failed");
         attr_done = true;
     }
-    const dim3 grid(ps.n_row_tiles + (ps.readout ? 1 : 0), w->B / 256);
+    const dim3 grid(gx1, w->B / 256);
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TC_THREADS, TcCfg<256>::SMEM_BYTES) != cudaSuccess || occ < 1) return 2;
-    if ((int)(grid.x * grid.y) > occ * sm_count || (int)grid.y + 1 > 64) return 2;
-    ps.src_hi[0] = w->src_hi; ps.src_lo[0] = w->src_lo; ps.src_hi[1] = w->src2_hi; ps.src_lo[1] = w->src2_lo;
-    ps.done = w->fwd_done;
+    if ((int)(grid.x * grid.y) > occ * sm_count) return 2;
     if (cudaMemsetAsync(w->fwd_done, 0, 64 * sizeof(unsigned int), st) != cudaSuccess) RP_TC_FAIL("cudaMemsetAsync failed");
-    int kb = w->N / TcElt<true>::BK;
-    Epi e = epi;
     void* args[] = {&w->m_W[0], &w->m_W[1], &w->m_src[0], &w->m_src[1], &w->m_src2[0], &w->m_src2[1], &kb, &e, &ps};
     cudaError_t err = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), grid, dim3(TC_THREADS), args, TcCfg<256>::SMEM_BYTES, st);
     if (err != cudaSuccess) { cudaGetLastError(); return 2; }      // e.g. not co-resident next to another tenant's kernels: per-step launches instead
