@@ -1514,8 +1514,8 @@ inline int tc_forward_persistent(TcWorkspace* w, const EpiFwd<MODEL, GEN>& epi, 
     Epi e = epi;
     // CTA-pair variant: opt-in (RP_FWD_CG2=1).  A/B on one box, alternating, 4 runs each: pass 30.43 vs 30.70 ms, forward stage 9.64 vs 9.82 ms
     // per 100 steps, bit-identical results.  Not the default: in the two full-suite runs that had it enabled, a later, unrelated test (the
-    // finite-difference check of a rate network, which never runs this kernel) saw ten times its usual rounding noise; not reproduced with
-    // any subset of the tests, cause not found -- see DESIGN.md.  A grid of pairs that is not co-resident or a refused cluster launch
+    // finite-difference check of a rate network, which never runs this kernel) saw ten times its usual rounding noise; not reproduced
+    // since (subsets, poisoned workspaces, a full run with the variant enabled everywhere), cause not found -- see DESIGN.md.  A grid of pairs that is not co-resident or a refused cluster launch
     // falls through to the 1-CTA kernel.
     if (getenv("RP_FWD_CG2")) {
         if (!attr2_done) {
