@@ -642,6 +642,11 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
     }
     const size_t x_stride = d.in_mode == RP_IN_DENSE ? plane : (d.in_mode == RP_IN_PROJ ? (size_t)B * d.n_in : 0);
     const size_t out_stride = d.out_mode == RP_OUT_READOUT ? (size_t)B * d.n_out : plane;
+    if (p->use_tc && a->T > 0) {          // the source operand is double buffered by step parity on every tensor-core path (see tc_forward_step)
+        size_t bytes = 0;
+        if (rp::tc_workspace_ensure_persist(&p->tc, &bytes)) return fail("rp_forward: %s", rp::tc_last_error());
+        p->ws_bytes += bytes;
+    }
 
     // tensor-core path: the step (and, for spiking nets read out from s, the readout) is the contraction's epilogue
     const bool fuse_readout = p->use_tc && spk && d.out_var == RP_VAR_S && d.out_mode == RP_OUT_READOUT && a->out_rec != nullptr;
@@ -705,7 +710,9 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
         fa.y_cur = cur; fa.y_next = nxt; fa.u = p->u; fa.ldu = p->ldu;
         fa.x_t = a->x ? a->x + (size_t)t * x_stride : nullptr; fa.W_in = a->W_in; fa.mp = mp;
         fa.src_next = (src_plane < 0 && !p->use_tc) ? p->src : nullptr;
-        fa.src_hi = p->use_tc ? p->tc.src_hi : nullptr; fa.src_lo = p->use_tc ? p->tc.src_lo : nullptr; fa.ld_src = p->tc.ldk;
+        // tensor-core path: src_t is read from buffer t & 1, src_{t+1} is written into the other one
+        fa.src_hi = p->use_tc ? ((t & 1) ? p->tc.src_hi : p->tc.src2_hi) : nullptr;
+        fa.src_lo = p->use_tc ? ((t & 1) ? p->tc.src_lo : p->tc.src2_lo) : nullptr; fa.ld_src = p->tc.ldk;
         fa.sc_out = rp::no_scale(); fa.amax_out = nullptr;
         rp::ScaleRef sc_in = rp::no_scale();
         if (f16) {
@@ -755,12 +762,12 @@ int rp_forward(rp_plan* p, const rp_fwd_args* a, void* stream) {
             if (p->per_trial || rp::is_ik(d.model)) {
                 RP_DISPATCH_MODEL(d.model, {
                     rp::EpiFwd<M_, true> epi; fill(epi);
-                    if (rp::tc_forward_step<M_, true>(&p->tc, epi, ro, st)) return fail("rp_forward: %s", rp::tc_last_error());
+                    if (rp::tc_forward_step<M_, true>(&p->tc, epi, ro, st, t & 1)) return fail("rp_forward: %s", rp::tc_last_error());
                 });
             } else {
                 RP_DISPATCH_MODEL(d.model, {
                     rp::EpiFwd<M_, false> epi; fill(epi);
-                    if (rp::tc_forward_step<M_, false>(&p->tc, epi, ro, st)) return fail("rp_forward: %s", rp::tc_last_error());
+                    if (rp::tc_forward_step<M_, false>(&p->tc, epi, ro, st, t & 1)) return fail("rp_forward: %s", rp::tc_last_error());
                 });
             }
             ++p->launches;

@@ -1483,10 +1483,13 @@ inline int tc_launch(bool f16, int bq, int P, int Q, int K, const CUtensorMap* A
 }
 // fused launch: forward step (rows = N, or N+128 when the readout rows are appended)
 template <int MODEL, bool GEN>
-inline int tc_forward_step(TcWorkspace* w, const EpiFwd<MODEL, GEN>& epi, bool readout_rows, cudaStream_t st) {
+// `src_buf`: which of the two source buffers holds src_t (the epilogue writes src_{t+1} into the OTHER one: CTAs of a launch finish
+// their K loops at different times, and a tile that is done must not overwrite operand columns another CTA has yet to load)
+inline int tc_forward_step(TcWorkspace* w, const EpiFwd<MODEL, GEN>& epi, bool readout_rows, cudaStream_t st, int src_buf = 0) {
     const int P = w->N + (readout_rows ? TC_BP : 0);
-    if (w->f16) return tc_launch_epi<EpiFwd<MODEL, GEN>, true>(w->bq_fwd, P, w->B, w->N, w->m_W, w->m_src, epi, st);
-    return tc_launch_epi<EpiFwd<MODEL, GEN>, false>(w->bq_fwd, P, w->B, w->N, w->m_W, w->m_src, epi, st);
+    const CUtensorMap* mb = src_buf ? w->m_src2 : w->m_src;
+    if (w->f16) return tc_launch_epi<EpiFwd<MODEL, GEN>, true>(w->bq_fwd, P, w->B, w->N, w->m_W, mb, epi, st);
+    return tc_launch_epi<EpiFwd<MODEL, GEN>, false>(w->bq_fwd, P, w->B, w->N, w->m_W, mb, epi, st);
 }
 // second source buffer + step counters of the persistent multi-step forward kernel (allocated on first use)
 inline int tc_workspace_ensure_persist(TcWorkspace* w, size_t* bytes) {

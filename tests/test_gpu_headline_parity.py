@@ -232,3 +232,32 @@ def test_persistent_forward_kernel_is_bit_identical_to_per_step_launches(monkeyp
     for key in ("out", "y", "gW", "gWo", "out_nograd", "y_nograd"):
         assert torch.equal(res["persistent"][key], res["per_step"][key]), key
         assert torch.equal(res["persistent_cg2"][key], res["per_step"][key]), key
+
+
+@pytest.mark.parametrize("prec", ["3xtf32", "3xf16"])
+def test_per_step_tensor_core_forward_is_bit_reproducible(prec):
+    """Rate networks with a readout run one tensor-core launch per step.  Round 2 found a write-after-read hazard there: the epilogue of a
+    tile that had finished its K loop wrote src_{t+1} into the operand buffer other CTAs of the launch were still loading src_t from -- on a
+    box whose CTAs drift apart (power throttling) three runs of the same forward gave three different results, 1e-4 apart in the summed
+    output (tools/exp_determinism_v1.py).  The source operand is now double buffered by step parity on every tensor-core path; the
+    forward must be bit-reproducible and within rounding of the fp32 path."""
+    import rectipy_b200 as rp
+    n, B, T, dt = 4096, 1024, 25, 1e-2
+    rng = np.random.default_rng(5)
+    W = (1.5 * rng.standard_normal((n, n)) / np.sqrt(n)).astype(np.float32)
+    w_out = (rng.standard_normal((2, n)) / np.sqrt(n)).astype(np.float32)
+    x = torch.tensor(rng.standard_normal((T, B, n)).astype(np.float32), device="cuda")
+
+    def run(precision):
+        net = rp.Network(dt, device="cuda:0", batch=B, precision=precision)
+        net.add_diffeq_node("rnn", "neuron_model_templates.rate_neurons.leaky_integrator.tanh", weights=W, source_var="tanh_op/r",
+                            target_var="li_op/r_in", input_var="li_op/I_ext", output_var="li_op/v", node_vars={"li_op/tau": 0.5, "li_op/k": 1.3})
+        net.add_func_node("out", 2, "identity"); net.add_edge("rnn", "out", weights=w_out)
+        return torch.stack(net.run(x, verbose=False)["out"])
+    outs = [run(prec) for _ in range(4)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    ref = run("fp32")
+    err = float((outs[0] - ref).abs().max() / ref.abs().max())
+    print(prec, "vs fp32 path:", err)
+    assert err <= 1e-5
