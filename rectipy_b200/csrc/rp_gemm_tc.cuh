@@ -1057,7 +1057,7 @@ __global__ void __launch_bounds__(256) k_split_matrix(int rows, int cols, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// CTA-pair variant of the persistent forward kernel (opt-in: RP_FWD_CG2=1): the protocol of
+// CTA-pair variant of the persistent forward kernel (the default; RP_NO_FWD_CG2=1 selects the 1-CTA kernel): the protocol of
 // k_gemm_fwd_persist with the operand delivery of k_gemm_split3_cg2.  Two row tiles of the SAME trial group form a cluster and run
 // M = 256 MMAs; each CTA loads its own 128 rows of kW and HALF of the source operand (32 instead of 48 KB of shared-memory fill per
 // CTA and K block), keeps its own 128 x 256 accumulator and runs the unchanged epilogue on it.  grid.x is padded to an even number of
@@ -1515,12 +1515,10 @@ inline int tc_forward_persistent(TcWorkspace* w, const EpiFwd<MODEL, GEN>& epi, 
     ps.done = w->fwd_done;
     int kb = w->N / TcElt<true>::BK;
     Epi e = epi;
-    // CTA-pair variant: opt-in (RP_FWD_CG2=1).  A/B on one box, alternating, 4 runs each: pass 30.43 vs 30.70 ms, forward stage 9.64 vs 9.82 ms
-    // per 100 steps, bit-identical results.  Not the default: in the two full-suite runs that had it enabled, a later, unrelated test (the
-    // finite-difference check of a rate network, which never runs this kernel) saw ten times its usual rounding noise; not reproduced
-    // since (subsets, poisoned workspaces, a full run with the variant enabled everywhere), cause not found -- see DESIGN.md.  A grid of pairs that is not co-resident or a refused cluster launch
-    // falls through to the 1-CTA kernel.
-    if (getenv("RP_FWD_CG2")) {
+    // CTA-pair variant first (A/B on one box, alternating, 4 runs each: pass 30.43 vs 30.70 ms, forward stage 9.64 vs 9.82 ms per 100 steps,
+    // bit-identical results); RP_NO_FWD_CG2=1, a grid of pairs that is not co-resident, or a refused cluster launch fall through to the
+    // 1-CTA kernel.
+    if (!getenv("RP_NO_FWD_CG2")) {
         if (!attr2_done) {
             if (cudaFuncSetAttribute(kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg2::SMEM_BYTES) != cudaSuccess) RP_TC_FAIL("cudaFuncSetAttribute failed");
             attr2_done = true;

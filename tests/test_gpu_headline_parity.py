@@ -203,13 +203,13 @@ def test_persistent_forward_kernel_is_bit_identical_to_per_step_launches(monkeyp
     W, w_in, w_out, etas, x, y0 = _qif_problem(n, B, T, seed=5)
     g = torch.tensor(np.random.default_rng(6).standard_normal((T, B, w_out.shape[0])).astype(np.float32), device="cuda:0")
     res = {}
-    for mode in ("persistent", "persistent_cg2", "per_step"):       # persistent_cg2: the opt-in CTA-pair kernel (k_gemm_fwd_persist_cg2)
+    for mode in ("persistent", "persistent_1cta", "per_step"):       # default: the CTA-pair kernel (k_gemm_fwd_persist_cg2)
         monkeypatch.delenv("RP_NO_FWD_PERSIST", raising=False)
-        monkeypatch.delenv("RP_FWD_CG2", raising=False)
+        monkeypatch.delenv("RP_NO_FWD_CG2", raising=False)
         if mode == "per_step":
             monkeypatch.setenv("RP_NO_FWD_PERSIST", "1")
-        elif mode == "persistent_cg2":
-            monkeypatch.setenv("RP_FWD_CG2", "1")
+        elif mode == "persistent_1cta":
+            monkeypatch.setenv("RP_NO_FWD_CG2", "1")
         engine.clear_plans()
         net, node, _cabi = _qif_engine(n, B, W, w_in, w_out, etas, y0, train=True)
         obs = net.run(x, sampling_steps=1, verbose=False, enable_grad=True)
@@ -224,14 +224,14 @@ def test_persistent_forward_kernel_is_bit_identical_to_per_step_launches(monkeyp
         rec["y_nograd"] = node.y.detach().clone()
         res[mode] = rec
     monkeypatch.delenv("RP_NO_FWD_PERSIST", raising=False)
-    monkeypatch.delenv("RP_FWD_CG2", raising=False)
+    monkeypatch.delenv("RP_NO_FWD_CG2", raising=False)
     engine.clear_plans()
     assert res["persistent"]["launches_fwd"] < 20 < res["per_step"]["launches_fwd"], (res["persistent"]["launches_fwd"], res["per_step"]["launches_fwd"])
-    assert res["persistent_cg2"]["launches_fwd"] < 20
+    assert res["persistent_1cta"]["launches_fwd"] < 20
     assert float(res["per_step"]["out"].abs().max()) > 0 and float(res["per_step"]["gW"].abs().max()) > 0
     for key in ("out", "y", "gW", "gWo", "out_nograd", "y_nograd"):
         assert torch.equal(res["persistent"][key], res["per_step"][key]), key
-        assert torch.equal(res["persistent_cg2"][key], res["per_step"][key]), key
+        assert torch.equal(res["persistent_1cta"][key], res["per_step"][key]), key
 
 
 @pytest.mark.parametrize("prec", ["3xtf32", "3xf16"])
