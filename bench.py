@@ -376,7 +376,7 @@ def run_ours(args):
         persist = f16 and 0 < fwd_cnt < T                     # one cooperative launch integrates the whole horizon
         cg2 = f16 and not os.environ.get("RP_NO_TC_CG2")      # adjoint product / weight gradient on 256x256 CTA-pair tiles (cta_group::2)
         gemm = "rp::k_gemm_split3_cg2<EpiStore> (256x256 CTA-pair tile, cta_group::2)" if cg2 else "rp::k_gemm_split3<256, EpiStore, f16=%d>" % int(f16)
-        fwd_cg2 = persist and not os.environ.get("RP_NO_FWD_CG2")
+        fwd_cg2 = persist and not (os.environ.get("RP_NO_FWD_CG2") or os.environ.get("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") or os.environ.get("CUDA_INJECTION64_PATH"))
         names = {"fwd_fused": (("rp::k_gemm_fwd_persist_cg2<EpiFwd<QIF>> (CTA pairs, " if fwd_cg2 else "rp::k_gemm_fwd_persist<256, EpiFwd<QIF>, f16> (") +
                                "persistent over all T steps: W.s contraction + Euler step + readout per step)"
                                if persist else "rp::k_gemm_split3<256, EpiFwd<QIF>, f16=%d> (W.s contraction + Euler step + readout)" % int(f16)),

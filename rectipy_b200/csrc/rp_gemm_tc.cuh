@@ -1517,8 +1517,10 @@ inline int tc_forward_persistent(TcWorkspace* w, const EpiFwd<MODEL, GEN>& epi, 
     Epi e = epi;
     // CTA-pair variant first (A/B on one box, alternating, 4 runs each: pass 30.43 vs 30.70 ms, forward stage 9.64 vs 9.82 ms per 100 steps,
     // bit-identical results); RP_NO_FWD_CG2=1, a grid of pairs that is not co-resident, or a refused cluster launch fall through to the
-    // 1-CTA kernel.
-    if (!getenv("RP_NO_FWD_CG2")) {
+    // 1-CTA kernel.  Under Nsight Compute the cooperative cluster launch is refused asynchronously (LaunchFailed, a sticky error; the same
+    // command runs clean without the profiler), so a profiled / injected process (NV_NSIGHT_INJECTION_TRANSPORT_TYPE, CUDA_INJECTION64_PATH)
+    // gets the 1-CTA kernel: same protocol, same epilogue, bit-identical results.
+    if (!getenv("RP_NO_FWD_CG2") && !getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") && !getenv("CUDA_INJECTION64_PATH")) {
         if (!attr2_done) {
             if (cudaFuncSetAttribute(kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg2::SMEM_BYTES) != cudaSuccess) RP_TC_FAIL("cudaFuncSetAttribute failed");
             attr2_done = true;
