@@ -368,3 +368,43 @@ def test_stateful_edges_match_reference_fixture():
         LinearMemory(n_in, n_out, delays=np.asarray([0, 1]), weights=z["w"])
     with pytest.raises(ValueError):
         LinearFilter(n_in, n_out, filter_weights=np.zeros((n_in, n_in + 1)), weights=z["w"])
+
+
+def test_padding_helpers_are_inert_and_differentiable():
+    """Host side of the padded tensor-core route (network._pad_axis / _ceil128): zero padding for weights / inputs, replication for state
+    and parameters, and gradients that flow back to the real entries only as what the real entries contributed."""
+    from rectipy_b200.network import _pad_axis, _ceil128
+    assert [_ceil128(v) for v in (1, 127, 128, 129, 600)] == [128, 128, 128, 256, 640]
+    w = torch.arange(12.0).reshape(3, 4).requires_grad_(True)
+    wp = _pad_axis(_pad_axis(w, 0, 5, False), 1, 6, False)
+    assert wp.shape == (5, 6) and torch.equal(wp[:3, :4], w) and float(wp[3:].abs().sum()) == 0 and float(wp[:, 4:].abs().sum()) == 0
+    wp.sum().backward()
+    assert torch.equal(w.grad, torch.ones_like(w))
+    st = torch.arange(2 * 3 * 4.0).reshape(2, 3, 4)
+    sp = _pad_axis(_pad_axis(st, 2, 6, True), 1, 5, True)
+    assert sp.shape == (2, 5, 6) and torch.equal(sp[:, :3, :4], st)
+    assert torch.equal(sp[:, :, 4], sp[:, :, 3]) and torch.equal(sp[:, 4], sp[:, 2])          # copies of the last real neuron / trial
+    p = torch.tensor([1.0, 2.0, 3.0], requires_grad=True)
+    pp = _pad_axis(p, 0, 5, True)
+    (pp * torch.tensor([1.0, 1.0, 1.0, 0.0, 0.0])).sum().backward()                          # padded entries carry zero adjoint in the engine
+    assert torch.equal(p.grad, torch.ones(3))
+    assert _pad_axis(p, 0, 3, True) is p
+
+
+def test_multi_spike_binding_checks(tmp_path, monkeypatch):
+    from rectipy_b200 import jit
+    from test_gpu_jit import EI_YAML
+    (tmp_path / "mymodels").mkdir()
+    (tmp_path / "mymodels" / "twopop.yaml").write_text(EI_YAML)
+    monkeypatch.chdir(tmp_path)
+    spec = templates.resolve_template("mymodels.twopop.ei")
+    with pytest.raises(ValueError):
+        jit.bind_spec(spec, "s_e", "s_in", "I_ext", ["spike_e", "spike_i"], ["v_e"])
+    with pytest.raises(KeyError):
+        jit.bind_spec(spec, "s_e", "s_in", "I_ext", ["spike_e", "nope"], ["v_e", "v_i"])
+    with pytest.raises(ValueError):                                  # one reset variable cannot serve two spike variables
+        jit.bind_spec(spec, "s_e", "s_in", "I_ext", ["spike_e", "spike_i"], ["v_e", "v_e"])
+    # a compiled template asked for MultiSpikeResetNet semantics goes through the generator as well
+    q = templates.resolve_template("neuron_model_templates.spiking_neurons.qif.qif", force_jit=True)
+    b = jit.bind_spec(q, "s", "s_in", "I_ext", ["spike"], ["v"])
+    assert b.jit_program.post_out and b.jit_program.spiking == 1 and b.planes == {"qif_op/v": 0, "qif_op/s": 1}
