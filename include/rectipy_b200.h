@@ -16,6 +16,9 @@
  *                     Spike.backward (surrogate)       rectipy/nodes.py:478-481
  *                     truncated BPTT detach            rectipy/network.py:598-599, rectipy/nodes.py:176-196
  *   rp_rls_run   <->  RLS.update applied per step      rectipy/edges.py:227-234, rectipy/network.py:1093-1121
+ *   rp_plan_set_jit_module  <->  the run function PyRates generates for a template that is not one of the compiled vector fields
+ *                     (RateNet.from_pyrates / _circuit_from_yaml -> get_run_func)   rectipy/nodes.py:112-164,232-262
+ *                     incl. MultiSpikeResetNet.forward (several spike / reset pairs, post-update outputs)   rectipy/nodes.py:451-465
  *
  * Conventions
  *   - Plain C: pointers + sizes, no torch types.  All data pointers are DEVICE pointers to fp32, contiguous,
@@ -23,7 +26,8 @@
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises the host.
  *   - Every entry point returns 0 on success, non-zero on error; rp_last_error() gives a thread-local message.
  *   - State layout ("SoA planes"): y[var][trial][neuron], var in {0:v, 1:s, 2:x}; plane stride = batch*n.
- *     (ik_op / iku_op: plane 2 holds the recovery variable u; ik_biexp_op: planes v, s, u, x.)
+ *     (ik_op / iku_op: plane 2 holds the recovery variable u; ik_biexp_op: planes v, s, u, x; RP_JIT: the reset variables first,
+ *     then the remaining state variables in equation order.)
  *   - A plan is not re-entrant: one host thread / one stream at a time per plan.
  */
 #ifndef RECTIPY_B200_H
